@@ -1,0 +1,1849 @@
+/* apk_oracle.c -- CPU ORACLE (test infrastructure, NOT product code). See apk_oracle.h.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fPIC -shared (no FMA contraction, like the reference's
+ * Kokkos-Serial build with g++ -O3 and no -march).
+ * All file:line cites are relative to /root/reference.
+ */
+#include "apk_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* external/parthenon/src/config.hpp.in:86-89 */
+#define TINY_NUMBER 1.0e-20
+#define SQR(x) ((x) * (x))
+#define SIGN(x) (((x) < 0.0) ? -1.0 : 1.0)
+/* std::min / std::max semantics (first argument wins ties) */
+static inline double smin(double a, double b) { return (b < a) ? b : a; }
+static inline double smax(double a, double b) { return (a < b) ? b : a; }
+
+/* variable indices, src/main.hpp:19-33 */
+enum { IDN = 0, IM1 = 1, IM2 = 2, IM3 = 3, IEN = 4, NHYDRO = 5, IB1 = 5, IB2 = 6, IB3 = 7, IPS = 8 };
+enum { IV1 = 1, IV2 = 2, IV3 = 3, IPR = 4 };
+#define NGLMMHD 9
+#define MAXVAR 16
+
+/* ===================================================================================== */
+/* Reconstruction scalars                                                                */
+/* ===================================================================================== */
+
+/* src/recon/plm_simple.hpp:20-37 */
+static void rc_plm(double qm1, double q0, double qp1, double *ql_ip1, double *qr_i) {
+  double dql = q0 - qm1;
+  double dqr = qp1 - q0;
+  double dq2 = dql * dqr;
+  double dqm = 0.0;
+  if (dq2 > 0.0) dqm = dq2 / (dql + dqr);
+  *ql_ip1 = q0 + dqm;
+  *qr_i = q0 - dqm;
+}
+
+/* src/recon/ppm_simple.hpp:38-162 */
+static void rc_ppm(double qm2, double qm1, double q0, double qp1, double qp2, double *ql_ip1,
+                   double *qr_i) {
+  const double C2 = 1.25;
+  /* step 1: interface averages (CW 1.6) */
+  double qa = q0 - qm1;
+  double qb = qp1 - q0;
+  const double dd_m = 0.5 * qa + 0.5 * (qm1 - qm2);
+  const double dd_0 = 0.5 * qb + 0.5 * qa;
+  const double dd_p = 0.5 * (qp2 - qp1) + 0.5 * qb;
+  double fm = 0.5 * (qm1 + q0) + (dd_m - dd_0) / 6.0;  /* face i-1/2 */
+  double fp = 0.5 * (q0 + qp1) + (dd_0 - dd_p) / 6.0;  /* face i+1/2 */
+
+  /* step 2a: second-derivative limiter at the interfaces (CD 4.3.1) */
+  const double d2m = qm2 + q0 - 2.0 * qm1;
+  const double d2c = qm1 + qp1 - 2.0 * q0;
+  const double d2p = q0 + qp2 - 2.0 * qp1;
+
+  double ta = fm - qm1;
+  double tb = q0 - fm;
+  qa = 3.0 * (qm1 + q0 - 2.0 * fm);
+  qb = d2m;
+  double qc = d2c;
+  double qd = 0.0;
+  if (SIGN(qa) == SIGN(qb) && SIGN(qa) == SIGN(qc)) {
+    qd = SIGN(qa) * smin(C2 * fabs(qb), smin(C2 * fabs(qc), fabs(qa)));
+  }
+  double fm_lim = 0.5 * (qm1 + q0) - qd / 6.0;
+  if (ta * tb < 0.0) fm = fm_lim;
+
+  ta = fp - q0;
+  tb = qp1 - fp;
+  qa = 3.0 * (q0 + qp1 - 2.0 * fp);
+  qb = d2c;
+  qc = d2p;
+  qd = 0.0;
+  if (SIGN(qa) == SIGN(qb) && SIGN(qa) == SIGN(qc)) {
+    qd = SIGN(qa) * smin(C2 * fabs(qb), smin(C2 * fabs(qc), fabs(qa)));
+  }
+  double fp_lim = 0.5 * (q0 + qp1) - qd / 6.0;
+  if (ta * tb < 0.0) fp = fp_lim;
+
+  const double d2f = 6.0 * (fm + fp - 2.0 * q0);
+
+  double r_i = fm;
+  double l_ip1 = fp;
+
+  /* step 3 */
+  const double dq_minus = q0 - r_i;
+  const double dq_plus = l_ip1 - q0;
+
+  /* step 4: CS limiters on the parabola */
+  ta = dq_minus * dq_plus;
+  tb = (qp1 - q0) * (q0 - qm1);
+
+  qa = d2m;
+  qb = d2c;
+  qc = d2p;
+  qd = d2f;
+  double qe = 0.0;
+  if (SIGN(qa) == SIGN(qb) && SIGN(qa) == SIGN(qc) && SIGN(qa) == SIGN(qd)) {
+    qe = SIGN(qd) * smin(smin(C2 * fabs(qa), C2 * fabs(qb)), smin(C2 * fabs(qc), fabs(qd)));
+  }
+  qa = smax(fabs(qm1), fabs(qm2));
+  qb = smax(smax(fabs(q0), fabs(qp1)), fabs(qp2));
+
+  double rho = 0.0;
+  if (fabs(qd) > (1.0e-12) * smax(qa, qb)) rho = qe / qd;
+
+  double tmp_m = q0 - rho * dq_minus;
+  double tmp_p = q0 + rho * dq_plus;
+  double tmp2_m = q0 - 2.0 * dq_plus;
+  double tmp2_p = q0 + 2.0 * dq_minus;
+
+  if (ta <= 0.0 || tb <= 0.0) {
+    if (rho <= (1.0 - (1.0e-12))) {
+      r_i = tmp_m;
+      l_ip1 = tmp_p;
+    }
+  } else {
+    if (fabs(dq_minus) >= 2.0 * fabs(dq_plus)) r_i = tmp2_m;
+    if (fabs(dq_plus) >= 2.0 * fabs(dq_minus)) l_ip1 = tmp2_p;
+  }
+  *qr_i = r_i;
+  *ql_ip1 = l_ip1;
+}
+
+/* src/recon/wenoz_simple.hpp:27-81 */
+static void rc_wenoz(double qm2, double qm1, double q0, double qp1, double qp2, double *ql_ip1,
+                     double *qr_i) {
+  const double c0 = 13. / 12., c1 = 0.25;
+  double beta[3];
+  beta[0] = c0 * SQR(qm2 + q0 - 2.0 * qm1) + c1 * SQR(qm2 + 3.0 * q0 - 4.0 * qm1);
+  beta[1] = c0 * SQR(qm1 + qp1 - 2.0 * q0) + c1 * SQR(qm1 - qp1);
+  beta[2] = c0 * SQR(qp2 + q0 - 2.0 * qp1) + c1 * SQR(qp2 + 3.0 * q0 - 4.0 * qp1);
+  const double epsL = 1.0e-42;
+  const double tau5 = fabs(beta[0] - beta[2]);
+  double ind[3];
+  ind[0] = tau5 / (beta[0] + epsL);
+  ind[1] = tau5 / (beta[1] + epsL);
+  ind[2] = tau5 / (beta[2] + epsL);
+
+  double f[3], al[3], asum;
+  f[0] = (2.0 * qm2 - 7.0 * qm1 + 11.0 * q0);
+  f[1] = (-1.0 * qm1 + 5.0 * q0 + 2.0 * qp1);
+  f[2] = (2.0 * q0 + 5.0 * qp1 - qp2);
+  al[0] = 0.1 * (1.0 + SQR(ind[0]));
+  al[1] = 0.6 * (1.0 + SQR(ind[1]));
+  al[2] = 0.3 * (1.0 + SQR(ind[2]));
+  asum = 6.0 * (al[0] + al[1] + al[2]);
+  *ql_ip1 = (f[0] * al[0] + f[1] * al[1] + f[2] * al[2]) / asum;
+
+  f[0] = (2.0 * qp2 - 7.0 * qp1 + 11.0 * q0);
+  f[1] = (-1.0 * qp1 + 5.0 * q0 + 2.0 * qm1);
+  f[2] = (2.0 * q0 + 5.0 * qm1 - qm2);
+  al[0] = 0.1 * (1.0 + SQR(ind[2]));
+  al[1] = 0.6 * (1.0 + SQR(ind[1]));
+  al[2] = 0.3 * (1.0 + SQR(ind[0]));
+  asum = 6.0 * (al[0] + al[1] + al[2]);
+  *qr_i = (f[0] * al[0] + f[1] * al[1] + f[2] * al[2]) / asum;
+}
+
+/* src/recon/weno3_simple.hpp:26-63; dx2 = dx^2 of the sweep direction (:82-83) */
+static void rc_weno3(double qm1, double q0, double qp1, double dx2, double *ql_ip1,
+                     double *qr_i) {
+  double beta[2], ind[2], f[2], al[2], asum;
+  beta[0] = SQR(qp1 - q0);
+  beta[1] = SQR(q0 - qm1);
+  const double tau = SQR(qp1 - 2.0 * q0 + qm1);
+  ind[0] = tau / (beta[0] + dx2);
+  ind[1] = tau / (beta[1] + dx2);
+  f[0] = q0 + qp1;
+  f[1] = -qm1 + 3.0 * q0;
+  al[0] = (1.0 + ind[0]) * 2.0 / 3.0;
+  al[1] = (1.0 + ind[1]) / 3.0;
+  asum = 2.0 * (al[0] + al[1]);
+  *ql_ip1 = (al[0] * f[0] + al[1] * f[1]) / asum;
+  f[0] = q0 + qm1;
+  f[1] = -qp1 + 3.0 * q0;
+  al[0] = (1.0 + ind[1]) * 2.0 / 3.0;
+  al[1] = (1.0 + ind[0]) / 3.0;
+  asum = 2.0 * (al[0] + al[1]);
+  *qr_i = (al[0] * f[0] + al[1] * f[1]) / asum;
+}
+
+/* src/hydro/diffusion/diffusion.hpp:37-47 */
+static double lim_minmod(double A, double B) {
+  if (A * B > 0) {
+    if (A > 0) return smin(A, B);
+    return smax(A, B);
+  }
+  return 0.0;
+}
+
+/* src/recon/limo3_simple.hpp:27-55 */
+static double limo3_limiter(double dvp, double dvm, double dx) {
+  const double r = 0.1;
+  const double eps = 10.0 * DBL_EPSILON;
+  const double theta = dvm / (dvp + TINY_NUMBER);
+  const double q = (2.0 + theta) / 3.0;
+  const double phi =
+      smax(0.0, smin(q, smax(-0.5 * theta, smin(2.0 * theta, smin(q, 1.6)))));
+  double eta = r * dx;
+  eta = (dvm * dvm + dvp * dvp) / (eta * eta);
+  if (eta <= 1.0 - eps) {
+    return q;
+  } else if (eta >= 1.0 + eps) {
+    return phi;
+  }
+  return 0.5 * ((1.0 - (eta - 1.0) / eps) * q + (1.0 + (eta - 1.0) / eps) * phi);
+}
+
+/* src/recon/limo3_simple.hpp:57-78 */
+static void rc_limo3(double qm1, double q0, double qp1, double dx, int positivity,
+                     double *ql_ip1, double *qr_i) {
+  const double dqp = qp1 - q0;
+  const double dqm = q0 - qm1;
+  *ql_ip1 = q0 + 0.5 * dqp * limo3_limiter(dqp, dqm, dx);
+  *qr_i = q0 - 0.5 * dqm * limo3_limiter(dqm, dqp, dx);
+  if (positivity && (*ql_ip1 <= 0.0 || *qr_i <= 0.0)) {
+    double dqmm = lim_minmod(dqp, dqm);
+    *ql_ip1 = q0 + 0.5 * dqmm;
+    *qr_i = q0 - 0.5 * dqmm;
+  }
+}
+
+/* q[0..4] = q_{i-2..i+2}; dx = cell width of the sweep direction */
+void apko_recon_scalar(int recon, const double q[5], double dx, int positivity, double *ql_ip1,
+                       double *qr_i) {
+  switch (recon) {
+  case APKO_RECON_DC: /* src/recon/dc_simple.hpp:33-36 */
+    *ql_ip1 = q[2];
+    *qr_i = q[2];
+    break;
+  case APKO_RECON_PLM:
+    rc_plm(q[1], q[2], q[3], ql_ip1, qr_i);
+    break;
+  case APKO_RECON_PPM:
+    rc_ppm(q[0], q[1], q[2], q[3], q[4], ql_ip1, qr_i);
+    break;
+  case APKO_RECON_WENOZ:
+    rc_wenoz(q[0], q[1], q[2], q[3], q[4], ql_ip1, qr_i);
+    break;
+  case APKO_RECON_WENO3:
+    rc_weno3(q[1], q[2], q[3], dx * dx, ql_ip1, qr_i);
+    break;
+  case APKO_RECON_LIMO3:
+    rc_limo3(q[1], q[2], q[3], dx, positivity, ql_ip1, qr_i);
+    break;
+  default:
+    *ql_ip1 = *qr_i = NAN;
+  }
+}
+
+/* ===================================================================================== */
+/* EOS helpers                                                                           */
+/* ===================================================================================== */
+
+/* src/eos/adiabatic_hydro.hpp:38-41 */
+static double eos_cs(double gamma, double d, double p) { return sqrt(gamma * p / d); }
+
+/* src/eos/adiabatic_glmmhd.hpp:46-54 */
+static double eos_cf(double gamma, double d, double p, double bx, double by, double bz) {
+  double asq = gamma * p;
+  double ct2 = by * by + bz * bz;
+  double qsq = bx * bx + ct2 + asq;
+  double tmp = bx * bx + ct2 - asq;
+  return sqrt(0.5 * (qsq + sqrt(tmp * tmp + 4.0 * asq * ct2)) / d);
+}
+
+/* src/eos/adiabatic_hydro.hpp:51-142 and adiabatic_glmmhd.hpp:61-167 (one cell).
+ * u (cons) is mutated by the floors/ceilings exactly like the reference. Returns 0 ok,
+ * 1 = negative density w/o floor, 2 = negative pressure w/o floor (PARTHENON_REQUIRE). */
+static int c2p_cell(int fluid, int nscalars, double *u, double *w, int stride, double gamma,
+                    double dfloor, double pfloor, double efloor, double vceil, double eceil) {
+  const int nhydro = (fluid == APKO_FLUID_GLMMHD) ? NGLMMHD : NHYDRO;
+  const double gm1 = gamma - 1.0;
+  int err = 0;
+#define U(n) u[(size_t)(n) * stride]
+#define W(n) w[(size_t)(n) * stride]
+  if (!(U(IDN) > 0.0 || dfloor > 0.0)) err = 1;
+  U(IDN) = (U(IDN) > dfloor) ? U(IDN) : dfloor;
+  W(IDN) = U(IDN);
+  double di = 1.0 / U(IDN);
+  W(IV1) = U(IM1) * di;
+  W(IV2) = U(IM2) * di;
+  W(IV3) = U(IM3) * di;
+  double e_B = 0.0;
+  double e_k = 0.5 * di * (SQR(U(IM1)) + SQR(U(IM2)) + SQR(U(IM3)));
+  if (fluid == APKO_FLUID_GLMMHD) {
+    W(IB1) = U(IB1);
+    W(IB2) = U(IB2);
+    W(IB3) = U(IB3);
+    W(IPS) = U(IPS);
+    e_B = 0.5 * (SQR(U(IB1)) + SQR(U(IB2)) + SQR(U(IB3)));
+    W(IPR) = gm1 * (U(IEN) - e_k - e_B);
+  } else {
+    W(IPR) = gm1 * (U(IEN) - e_k);
+  }
+  const double v2 = SQR(W(IV1)) + SQR(W(IV2)) + SQR(W(IV3));
+  if (v2 > SQR(vceil)) {
+    const double v = sqrt(v2);
+    W(IV1) *= vceil / v;
+    W(IV2) *= vceil / v;
+    W(IV3) *= vceil / v;
+    U(IM1) *= vceil / v;
+    U(IM2) *= vceil / v;
+    U(IM3) *= vceil / v;
+    double e_k_new = 0.5 * U(IDN) * SQR(vceil);
+    U(IEN) -= e_k - e_k_new;
+    e_k = e_k_new;
+  }
+  if (!(W(IPR) > 0.0 || pfloor > 0.0 || efloor > 0.0)) err = err ? err : 2;
+  /* note: hydro adds e_k only; MHD adds e_k + e_B, in that order */
+  if ((pfloor > 0.0) && (W(IPR) < pfloor)) {
+    U(IEN) = (fluid == APKO_FLUID_GLMMHD) ? (pfloor / gm1) + e_k + e_B : (pfloor / gm1) + e_k;
+    W(IPR) = pfloor;
+  }
+  const double eff_pfloor = gm1 * U(IDN) * efloor;
+  if (W(IPR) < eff_pfloor) {
+    U(IEN) = (fluid == APKO_FLUID_GLMMHD) ? (U(IDN) * efloor) + e_k + e_B
+                                          : (U(IDN) * efloor) + e_k;
+    W(IPR) = eff_pfloor;
+  }
+  const double eff_pceil = gm1 * U(IDN) * eceil;
+  if (W(IPR) > eff_pceil) {
+    U(IEN) = (fluid == APKO_FLUID_GLMMHD) ? (U(IDN) * eceil) + e_k + e_B
+                                          : (U(IDN) * eceil) + e_k;
+    W(IPR) = eff_pceil;
+  }
+  for (int n = nhydro; n < nhydro + nscalars; ++n) W(n) = U(n) * di;
+#undef U
+#undef W
+  return err;
+}
+
+void apko_c2p_cell(int fluid, int nscalars, double *u, double *w, double gamma, double dfloor,
+                   double pfloor, double efloor, double vceil, double eceil) {
+  c2p_cell(fluid, nscalars, u, w, 1, gamma, dfloor, pfloor, efloor, vceil, eceil);
+}
+
+/* ===================================================================================== */
+/* Riemann solvers: one face. wl/wr/flux are in the *unpermuted* variable layout.        */
+/* ===================================================================================== */
+
+/* src/hydro/rsolvers/hydro_hlle.hpp:39-138 */
+static void rs_hydro_hlle(int ivx, const double *wl, const double *wr, double gamma,
+                          double *flx) {
+  const int ivy = IV1 + ((ivx - IV1) + 1) % 3;
+  const int ivz = IV1 + ((ivx - IV1) + 2) % 3;
+  const double gm1 = gamma - 1.0;
+  const double igm1 = 1.0 / gm1;
+  double L[5] = {wl[IDN], wl[ivx], wl[ivy], wl[ivz], wl[IPR]};
+  double R[5] = {wr[IDN], wr[ivx], wr[ivy], wr[ivz], wr[IPR]};
+  double roe[5], fl[5], fr[5], f[5];
+
+  double sdl = sqrt(L[IDN]);
+  double sdr = sqrt(R[IDN]);
+  double isum = 1.0 / (sdl + sdr);
+  roe[IDN] = sdl * sdr;
+  roe[IV1] = (sdl * L[IV1] + sdr * R[IV1]) * isum;
+  roe[IV2] = (sdl * L[IV2] + sdr * R[IV2]) * isum;
+  roe[IV3] = (sdl * L[IV3] + sdr * R[IV3]) * isum;
+  const double el = L[IPR] * igm1 + 0.5 * L[IDN] * (SQR(L[IV1]) + SQR(L[IV2]) + SQR(L[IV3]));
+  const double er = R[IPR] * igm1 + 0.5 * R[IDN] * (SQR(R[IV1]) + SQR(R[IV2]) + SQR(R[IV3]));
+  const double hroe = ((el + L[IPR]) / sdl + (er + R[IPR]) / sdr) * isum;
+
+  const double cl = eos_cs(gamma, L[IDN], L[IPR]);
+  const double cr = eos_cs(gamma, R[IDN], R[IPR]);
+  double q = hroe - 0.5 * (SQR(roe[IV1]) + SQR(roe[IV2]) + SQR(roe[IV3]));
+  const double a = (q < 0.0) ? 0.0 : sqrt(gm1 * q);
+
+  const double al = smin((roe[IV1] - a), (L[IV1] - cl));
+  const double ar = smax((roe[IV1] + a), (R[IV1] + cr));
+  double bp = ar > 0.0 ? ar : TINY_NUMBER;
+  double bm = al < 0.0 ? al : TINY_NUMBER; /* sic: +TINY (hydro_hlle.hpp:98) */
+
+  double vxl = L[IV1] - bm;
+  double vxr = R[IV1] - bp;
+  fl[IDN] = L[IDN] * vxl;
+  fr[IDN] = R[IDN] * vxr;
+  fl[IV1] = L[IDN] * L[IV1] * vxl;
+  fr[IV1] = R[IDN] * R[IV1] * vxr;
+  fl[IV2] = L[IDN] * L[IV2] * vxl;
+  fr[IV2] = R[IDN] * R[IV2] * vxr;
+  fl[IV3] = L[IDN] * L[IV3] * vxl;
+  fr[IV3] = R[IDN] * R[IV3] * vxr;
+  fl[IV1] += L[IPR];
+  fr[IV1] += R[IPR];
+  fl[IEN] = el * vxl + L[IPR] * L[IV1];
+  fr[IEN] = er * vxr + R[IPR] * R[IV1];
+
+  double tmp = 0.0;
+  if (bp != bm) tmp = 0.5 * (bp + bm) / (bp - bm);
+  for (int n = 0; n < 5; ++n) f[n] = 0.5 * (fl[n] + fr[n]) + (fl[n] - fr[n]) * tmp;
+
+  flx[IDN] = f[IDN];
+  flx[ivx] = f[IV1];
+  flx[ivy] = f[IV2];
+  flx[ivz] = f[IV3];
+  flx[IEN] = f[IEN];
+}
+
+/* src/hydro/rsolvers/hydro_hllc.hpp:31-157 */
+static void rs_hydro_hllc(int ivx, const double *wl, const double *wr, double gamma,
+                          double *flx) {
+  const int ivy = IV1 + ((ivx - IV1) + 1) % 3;
+  const int ivz = IV1 + ((ivx - IV1) + 2) % 3;
+  const double gm1 = gamma - 1.0;
+  const double igm1 = 1.0 / gm1;
+  double L[5] = {wl[IDN], wl[ivx], wl[ivy], wl[ivz], wl[IPR]};
+  double R[5] = {wr[IDN], wr[ivx], wr[ivy], wr[ivz], wr[IPR]};
+  double fl[5], fr[5], f[5];
+
+  double cl = eos_cs(gamma, L[IDN], L[IPR]);
+  double cr = eos_cs(gamma, R[IDN], R[IPR]);
+  double el = L[IPR] * igm1 + 0.5 * L[IDN] * (SQR(L[IV1]) + SQR(L[IV2]) + SQR(L[IV3]));
+  double er = R[IPR] * igm1 + 0.5 * R[IDN] * (SQR(R[IV1]) + SQR(R[IV2]) + SQR(R[IV3]));
+  double rhoa = .5 * (L[IDN] + R[IDN]);
+  double ca = .5 * (cl + cr);
+  double pmid = .5 * (L[IPR] + R[IPR] + (L[IV1] - R[IV1]) * rhoa * ca);
+
+  double ql = (pmid <= L[IPR]) ? 1.0
+                               : sqrt(1.0 + (gamma + 1) / (2 * gamma) * (pmid / L[IPR] - 1.0));
+  double qr = (pmid <= R[IPR]) ? 1.0
+                               : sqrt(1.0 + (gamma + 1) / (2 * gamma) * (pmid / R[IPR] - 1.0));
+
+  double al = L[IV1] - cl * ql;
+  double ar = R[IV1] + cr * qr;
+  double bp = ar > 0.0 ? ar : (TINY_NUMBER);
+  double bm = al < 0.0 ? al : -(TINY_NUMBER);
+
+  double vxl = L[IV1] - al;
+  double vxr = R[IV1] - ar;
+  double tl = L[IPR] + vxl * L[IDN] * L[IV1];
+  double tr = R[IPR] + vxr * R[IDN] * R[IV1];
+  double ml = L[IDN] * vxl;
+  double mr = -(R[IDN] * vxr);
+  double am = (tl - tr) / (ml + mr);
+  double cp = (ml * tr + mr * tl) / (ml + mr);
+  cp = cp > 0.0 ? cp : 0.0;
+
+  vxl = L[IV1] - bm;
+  vxr = R[IV1] - bp;
+  fl[IDN] = L[IDN] * vxl;
+  fr[IDN] = R[IDN] * vxr;
+  fl[IV1] = L[IDN] * L[IV1] * vxl + L[IPR];
+  fr[IV1] = R[IDN] * R[IV1] * vxr + R[IPR];
+  fl[IV2] = L[IDN] * L[IV2] * vxl;
+  fr[IV2] = R[IDN] * R[IV2] * vxr;
+  fl[IV3] = L[IDN] * L[IV3] * vxl;
+  fr[IV3] = R[IDN] * R[IV3] * vxr;
+  fl[IEN] = el * vxl + L[IPR] * L[IV1];
+  fr[IEN] = er * vxr + R[IPR] * R[IV1];
+
+  double sl, sr, sm;
+  if (am >= 0.0) {
+    sl = am / (am - bm);
+    sr = 0.0;
+    sm = -bm / (am - bm);
+  } else {
+    sl = 0.0;
+    sr = -am / (bp - am);
+    sm = bp / (bp - am);
+  }
+  f[IDN] = sl * fl[IDN] + sr * fr[IDN];
+  f[IV1] = sl * fl[IV1] + sr * fr[IV1] + sm * cp;
+  f[IV2] = sl * fl[IV2] + sr * fr[IV2];
+  f[IV3] = sl * fl[IV3] + sr * fr[IV3];
+  f[IEN] = sl * fl[IEN] + sr * fr[IEN] + sm * cp * am;
+
+  flx[IDN] = f[IDN];
+  flx[ivx] = f[IV1];
+  flx[ivy] = f[IV2];
+  flx[ivz] = f[IV3];
+  flx[IEN] = f[IEN];
+}
+
+/* src/hydro/rsolvers/hydro_dc_llf.hpp:42-118 (face part; scalars handled by caller) */
+static void rs_hydro_llf(int ivx, const double *wl, const double *wr, double gamma,
+                         double *flx) {
+  const int ivy = IV1 + ((ivx - IV1) + 1) % 3;
+  const int ivz = IV1 + ((ivx - IV1) + 2) % 3;
+  const double igm1 = 1.0 / (gamma - 1.0);
+  double L[5] = {wl[IDN], wl[ivx], wl[ivy], wl[ivz], wl[IPR]};
+  double R[5] = {wr[IDN], wr[ivx], wr[ivy], wr[ivz], wr[IPR]};
+  double qa = L[IDN] * L[IV1];
+  double qb = R[IDN] * R[IV1];
+  double fs_d = qa + qb;
+  double fs_mx = qa * L[IV1] + qb * R[IV1];
+  double fs_my = qa * L[IV2] + qb * R[IV2];
+  double fs_mz = qa * L[IV3] + qb * R[IV3];
+  double el = L[IPR] * igm1 + 0.5 * L[IDN] * (SQR(L[IV1]) + SQR(L[IV2]) + SQR(L[IV3]));
+  double er = R[IPR] * igm1 + 0.5 * R[IDN] * (SQR(R[IV1]) + SQR(R[IV2]) + SQR(R[IV3]));
+  fs_mx += (L[IPR] + R[IPR]);
+  double fs_e = (el + L[IPR]) * L[IV1] + (er + R[IPR]) * R[IV1];
+  qa = eos_cs(gamma, L[IDN], L[IPR]);
+  qb = eos_cs(gamma, R[IDN], R[IPR]);
+  double a = fmax((fabs(L[IV1]) + qa), (fabs(R[IV1]) + qb));
+  double du_d = a * (R[IDN] - L[IDN]);
+  double du_mx = a * (R[IDN] * R[IV1] - L[IDN] * L[IV1]);
+  double du_my = a * (R[IDN] * R[IV2] - L[IDN] * L[IV2]);
+  double du_mz = a * (R[IDN] * R[IV3] - L[IDN] * L[IV3]);
+  double du_e = a * (er - el);
+  flx[IDN] = 0.5 * (fs_d - du_d);
+  flx[ivx] = 0.5 * (fs_mx - du_mx);
+  flx[ivy] = 0.5 * (fs_my - du_my);
+  flx[ivz] = 0.5 * (fs_mz - du_mz);
+  flx[IEN] = 0.5 * (fs_e - du_e);
+}
+
+/* src/hydro/rsolvers/glmmhd_dc_llf.hpp:45-155 */
+static void rs_mhd_llf(int ivx, const double *wl, const double *wr, double gamma, double c_h,
+                       double *flx) {
+  const int ivy = IV1 + ((ivx - IV1) + 1) % 3;
+  const int ivz = IV1 + ((ivx - IV1) + 2) % 3;
+  const int iBx = ivx - 1 + NHYDRO, iBy = ivy - 1 + NHYDRO, iBz = ivz - 1 + NHYDRO;
+  const double igm1 = 1.0 / (gamma - 1.0);
+  double L[9] = {wl[IDN], wl[ivx], wl[ivy], wl[ivz], wl[IPR], wl[iBx], wl[iBy], wl[iBz], wl[IPS]};
+  double R[9] = {wr[IDN], wr[ivx], wr[ivy], wr[ivz], wr[IPR], wr[iBx], wr[iBy], wr[iBz], wr[IPS]};
+
+  double bxi = 0.5 * (L[IB1] + R[IB1]) - 0.5 / c_h * (R[IPS] - L[IPS]);
+  double psii = 0.5 * (L[IPS] + R[IPS]) - 0.5 * c_h * (R[IB1] - L[IB1]);
+
+  double qa = L[IDN] * L[IV1];
+  double qb = R[IDN] * R[IV1];
+  double qc = 0.5 * (SQR(L[IB2]) + SQR(L[IB3]) - SQR(bxi));
+  double qd = 0.5 * (SQR(R[IB2]) + SQR(R[IB3]) - SQR(bxi));
+
+  double fs_d = qa + qb;
+  double fs_mx = qa * L[IV1] + qb * R[IV1] + qc + qd;
+  double fs_my = qa * L[IV2] + qb * R[IV2] - bxi * (L[IB2] + R[IB2]);
+  double fs_mz = qa * L[IV3] + qb * R[IV3] - bxi * (L[IB3] + R[IB3]);
+  double fs_by = L[IB2] * L[IV1] + R[IB2] * R[IV1] - bxi * (L[IV2] + R[IV2]);
+  double fs_bz = L[IB3] * L[IV1] + R[IB3] * R[IV1] - bxi * (L[IV3] + R[IV3]);
+
+  double el = L[IPR] * igm1 + 0.5 * L[IDN] * (SQR(L[IV1]) + SQR(L[IV2]) + SQR(L[IV3])) + qc +
+              SQR(bxi);
+  double er = R[IPR] * igm1 + 0.5 * R[IDN] * (SQR(R[IV1]) + SQR(R[IV2]) + SQR(R[IV3])) + qd +
+              SQR(bxi);
+  fs_mx += (L[IPR] + R[IPR]);
+  double fs_e = (el + L[IPR] + qc) * L[IV1] + (er + R[IPR] + qd) * R[IV1];
+  fs_e -= bxi * (L[IB2] * L[IV2] + L[IB3] * L[IV3]);
+  fs_e -= bxi * (R[IB2] * R[IV2] + R[IB3] * R[IV3]);
+
+  qa = eos_cf(gamma, L[IDN], L[IPR], L[IB1], L[IB2], L[IB3]);
+  qb = eos_cf(gamma, R[IDN], R[IPR], R[IB1], R[IB2], R[IB3]);
+  double a = fmax((fabs(L[IV1]) + qa), (fabs(R[IV1]) + qb));
+
+  double du_d = a * (R[IDN] - L[IDN]);
+  double du_mx = a * (R[IDN] * R[IV1] - L[IDN] * L[IV1]);
+  double du_my = a * (R[IDN] * R[IV2] - L[IDN] * L[IV2]);
+  double du_mz = a * (R[IDN] * R[IV3] - L[IDN] * L[IV3]);
+  double du_e = a * (er - el);
+  double du_by = a * (R[IB2] - L[IB2]);
+  double du_bz = a * (R[IB3] - L[IB3]);
+
+  flx[IDN] = 0.5 * (fs_d - du_d);
+  flx[ivx] = 0.5 * (fs_mx - du_mx);
+  flx[ivy] = 0.5 * (fs_my - du_my);
+  flx[ivz] = 0.5 * (fs_mz - du_mz);
+  flx[IEN] = 0.5 * (fs_e - du_e);
+  flx[iBx] = psii;
+  flx[iBy] = 0.5 * (fs_by - du_by);
+  flx[iBz] = 0.5 * (fs_bz - du_bz);
+  flx[IPS] = SQR(c_h) * bxi;
+}
+
+/* src/hydro/rsolvers/glmmhd_hlle.hpp:27-192 */
+static void rs_mhd_hlle(int ivx, const double *wl, const double *wr, double gamma, double c_h,
+                        double *flx) {
+  const int ivy = IV1 + ((ivx - IV1) + 1) % 3;
+  const int ivz = IV1 + ((ivx - IV1) + 2) % 3;
+  const int iBx = ivx - 1 + NHYDRO, iBy = ivy - 1 + NHYDRO, iBz = ivz - 1 + NHYDRO;
+  const double gm1 = gamma - 1.0;
+  double L[9] = {wl[IDN], wl[ivx], wl[ivy], wl[ivz], wl[IPR], wl[iBx], wl[iBy], wl[iBz], wl[IPS]};
+  double R[9] = {wr[IDN], wr[ivx], wr[ivy], wr[ivz], wr[IPR], wr[iBx], wr[iBy], wr[iBz], wr[IPS]};
+  double roe[9], fl[9], fr[9], f[9];
+
+  double bxi = 0.5 * (L[IB1] + R[IB1]) - 0.5 / c_h * (R[IPS] - L[IPS]);
+  double psii = 0.5 * (L[IPS] + R[IPS]) - 0.5 * c_h * (R[IB1] - L[IB1]);
+  f[IB1] = psii;
+  f[IPS] = SQR(c_h) * bxi;
+
+  double sdl = sqrt(L[IDN]);
+  double sdr = sqrt(R[IDN]);
+  double isum = 1.0 / (sdl + sdr);
+  roe[IDN] = sdl * sdr;
+  roe[IV1] = (sdl * L[IV1] + sdr * R[IV1]) * isum;
+  roe[IV2] = (sdl * L[IV2] + sdr * R[IV2]) * isum;
+  roe[IV3] = (sdl * L[IV3] + sdr * R[IV3]) * isum;
+  roe[IB2] = (sdr * L[IB2] + sdl * R[IB2]) * isum;
+  roe[IB3] = (sdr * L[IB3] + sdl * R[IB3]) * isum;
+  double x = 0.5 * (SQR(L[IB2] - R[IB2]) + SQR(L[IB3] - R[IB3])) / (SQR(sdl + sdr));
+  double y = 0.5 * (L[IDN] + R[IDN]) / roe[IDN];
+
+  double pbl = 0.5 * (bxi * bxi + SQR(L[IB2]) + SQR(L[IB3]));
+  double pbr = 0.5 * (bxi * bxi + SQR(R[IB2]) + SQR(R[IB3]));
+  double el = L[IPR] / gm1 + 0.5 * L[IDN] * (SQR(L[IV1]) + SQR(L[IV2]) + SQR(L[IV3])) + pbl;
+  double er = R[IPR] / gm1 + 0.5 * R[IDN] * (SQR(R[IV1]) + SQR(R[IV2]) + SQR(R[IV3])) + pbr;
+  double hroe = ((el + L[IPR] + pbl) / sdl + (er + R[IPR] + pbr) / sdr) * isum;
+
+  double cl = eos_cf(gamma, L[IDN], L[IPR], L[IB1], L[IB2], L[IB3]);
+  double cr = eos_cf(gamma, R[IDN], R[IPR], R[IB1], R[IB2], R[IB3]);
+
+  double btsq = SQR(roe[IB2]) + SQR(roe[IB3]);
+  double vaxsq = bxi * bxi / roe[IDN];
+  double bt_starsq = (gm1 - (gm1 - 1.0) * y) * btsq;
+  double hp = hroe - (vaxsq + btsq / roe[IDN]);
+  double vsq = SQR(roe[IV1]) + SQR(roe[IV2]) + SQR(roe[IV3]);
+  double twid_asq = smax((gm1 * (hp - 0.5 * vsq) - (gm1 - 1.0) * x), 0.0);
+  double ct2 = bt_starsq / roe[IDN];
+  double tsum = vaxsq + ct2 + twid_asq;
+  double tdif = vaxsq + ct2 - twid_asq;
+  double cf2_cs2 = sqrt(tdif * tdif + 4.0 * twid_asq * ct2);
+  double cfsq = 0.5 * (tsum + cf2_cs2);
+  double a = sqrt(cfsq);
+
+  double al = smin((roe[IV1] - a), (L[IV1] - cl));
+  double ar = smax((roe[IV1] + a), (R[IV1] + cr));
+  double bp = ar > 0.0 ? ar : 0.0;
+  double bm = al < 0.0 ? al : 0.0;
+
+  double vxl = L[IV1] - bm;
+  double vxr = R[IV1] - bp;
+  fl[IDN] = L[IDN] * vxl;
+  fr[IDN] = R[IDN] * vxr;
+  fl[IV1] = L[IDN] * L[IV1] * vxl + pbl - SQR(bxi);
+  fr[IV1] = R[IDN] * R[IV1] * vxr + pbr - SQR(bxi);
+  fl[IV2] = L[IDN] * L[IV2] * vxl - bxi * L[IB2];
+  fr[IV2] = R[IDN] * R[IV2] * vxr - bxi * R[IB2];
+  fl[IV3] = L[IDN] * L[IV3] * vxl - bxi * L[IB3];
+  fr[IV3] = R[IDN] * R[IV3] * vxr - bxi * R[IB3];
+  fl[IV1] += L[IPR];
+  fr[IV1] += R[IPR];
+  fl[IEN] = el * vxl + L[IV1] * (L[IPR] + pbl - bxi * bxi);
+  fr[IEN] = er * vxr + R[IV1] * (R[IPR] + pbr - bxi * bxi);
+  fl[IEN] -= bxi * (L[IB2] * L[IV2] + L[IB3] * L[IV3]);
+  fr[IEN] -= bxi * (R[IB2] * R[IV2] + R[IB3] * R[IV3]);
+  fl[IB2] = L[IB2] * vxl - bxi * L[IV2];
+  fr[IB2] = R[IB2] * vxr - bxi * R[IV2];
+  fl[IB3] = L[IB3] * vxl - bxi * L[IV3];
+  fr[IB3] = R[IB3] * vxr - bxi * R[IV3];
+
+  double tmp = 0.0;
+  if (bp != bm) tmp = 0.5 * (bp + bm) / (bp - bm);
+  f[IDN] = 0.5 * (fl[IDN] + fr[IDN]) + (fl[IDN] - fr[IDN]) * tmp;
+  f[IV1] = 0.5 * (fl[IV1] + fr[IV1]) + (fl[IV1] - fr[IV1]) * tmp;
+  f[IV2] = 0.5 * (fl[IV2] + fr[IV2]) + (fl[IV2] - fr[IV2]) * tmp;
+  f[IV3] = 0.5 * (fl[IV3] + fr[IV3]) + (fl[IV3] - fr[IV3]) * tmp;
+  f[IEN] = 0.5 * (fl[IEN] + fr[IEN]) + (fl[IEN] - fr[IEN]) * tmp;
+  f[IB2] = 0.5 * (fl[IB2] + fr[IB2]) + (fl[IB2] - fr[IB2]) * tmp;
+  f[IB3] = 0.5 * (fl[IB3] + fr[IB3]) + (fl[IB3] - fr[IB3]) * tmp;
+
+  flx[IDN] = f[IDN];
+  flx[ivx] = f[IV1];
+  flx[ivy] = f[IV2];
+  flx[ivz] = f[IV3];
+  flx[IEN] = f[IEN];
+  flx[iBx] = f[IB1];
+  flx[iBy] = f[IB2];
+  flx[iBz] = f[IB3];
+  flx[IPS] = f[IPS];
+}
+
+typedef struct {
+  double d, mx, my, mz, e, by, bz;
+} cons1d;
+
+#define SMALL_NUMBER 1.0e-8
+
+/* src/hydro/rsolvers/glmmhd_hlld.hpp:39-395 */
+static void rs_mhd_hlld(int ivx, const double *wl, const double *wr, double gamma, double c_h,
+                        double *flx) {
+  const int ivy = IV1 + ((ivx - IV1) + 1) % 3;
+  const int ivz = IV1 + ((ivx - IV1) + 2) % 3;
+  const int iBx = ivx - 1 + NHYDRO, iBy = ivy - 1 + NHYDRO, iBz = ivz - 1 + NHYDRO;
+  const double gm1 = gamma - 1.0;
+  const double igm1 = 1.0 / gm1;
+  double L[9] = {wl[IDN], wl[ivx], wl[ivy], wl[ivz], wl[IPR], wl[iBx], wl[iBy], wl[iBz], wl[IPS]};
+  double R[9] = {wr[IDN], wr[ivx], wr[ivy], wr[ivz], wr[IPR], wr[iBx], wr[iBy], wr[iBz], wr[IPS]};
+  double f[9], spd[5];
+  cons1d ul, ur, ulst, uldst, urdst, urst, fl, fr;
+
+  double bxi = 0.5 * (L[IB1] + R[IB1]) - 0.5 / c_h * (R[IPS] - L[IPS]);
+  double psii = 0.5 * (L[IPS] + R[IPS]) - 0.5 * c_h * (R[IB1] - L[IB1]);
+  f[IB1] = psii;
+  f[IPS] = SQR(c_h) * bxi;
+
+  double bxsq = bxi * bxi;
+  double pbl = 0.5 * (bxsq + (SQR(L[IB2]) + SQR(L[IB3])));
+  double pbr = 0.5 * (bxsq + (SQR(R[IB2]) + SQR(R[IB3])));
+  double kel = 0.5 * L[IDN] * (SQR(L[IV1]) + (SQR(L[IV2]) + SQR(L[IV3])));
+  double ker = 0.5 * R[IDN] * (SQR(R[IV1]) + (SQR(R[IV2]) + SQR(R[IV3])));
+
+  ul.d = L[IDN];
+  ul.mx = L[IV1] * ul.d;
+  ul.my = L[IV2] * ul.d;
+  ul.mz = L[IV3] * ul.d;
+  ul.e = L[IPR] * igm1 + kel + pbl;
+  ul.by = L[IB2];
+  ul.bz = L[IB3];
+
+  ur.d = R[IDN];
+  ur.mx = R[IV1] * ur.d;
+  ur.my = R[IV2] * ur.d;
+  ur.mz = R[IV3] * ur.d;
+  ur.e = R[IPR] * igm1 + ker + pbr;
+  ur.by = R[IB2];
+  ur.bz = R[IB3];
+
+  const double cfl = eos_cf(gamma, L[IDN], L[IPR], L[IB1], L[IB2], L[IB3]);
+  const double cfr = eos_cf(gamma, R[IDN], R[IPR], R[IB1], R[IB2], R[IB3]);
+  spd[0] = smin(L[IV1] - cfl, R[IV1] - cfr);
+  spd[4] = smax(L[IV1] + cfl, R[IV1] + cfr);
+
+  double ptl = L[IPR] + pbl;
+  double ptr = R[IPR] + pbr;
+
+  fl.d = ul.mx;
+  fl.mx = ul.mx * L[IV1] + ptl - bxsq;
+  fl.my = ul.my * L[IV1] - bxi * ul.by;
+  fl.mz = ul.mz * L[IV1] - bxi * ul.bz;
+  fl.e = L[IV1] * (ul.e + ptl - bxsq) - bxi * (L[IV2] * ul.by + L[IV3] * ul.bz);
+  fl.by = ul.by * L[IV1] - bxi * L[IV2];
+  fl.bz = ul.bz * L[IV1] - bxi * L[IV3];
+
+  fr.d = ur.mx;
+  fr.mx = ur.mx * R[IV1] + ptr - bxsq;
+  fr.my = ur.my * R[IV1] - bxi * ur.by;
+  fr.mz = ur.mz * R[IV1] - bxi * ur.bz;
+  fr.e = R[IV1] * (ur.e + ptr - bxsq) - bxi * (R[IV2] * ur.by + R[IV3] * ur.bz);
+  fr.by = ur.by * R[IV1] - bxi * R[IV2];
+  fr.bz = ur.bz * R[IV1] - bxi * R[IV3];
+
+  double sdl = spd[0] - L[IV1];
+  double sdr = spd[4] - R[IV1];
+  spd[2] = (sdr * ur.mx - sdl * ul.mx + (ptl - ptr)) / (sdr * ur.d - sdl * ul.d);
+
+  double sdml = spd[0] - spd[2];
+  double sdmr = spd[4] - spd[2];
+  double sdml_inv = 1.0 / sdml;
+  double sdmr_inv = 1.0 / sdmr;
+  ulst.d = ul.d * sdl * sdml_inv;
+  urst.d = ur.d * sdr * sdmr_inv;
+  double ulst_d_inv = 1.0 / ulst.d;
+  double urst_d_inv = 1.0 / urst.d;
+  double sqrtdl = sqrt(ulst.d);
+  double sqrtdr = sqrt(urst.d);
+
+  spd[1] = spd[2] - fabs(bxi) / sqrtdl;
+  spd[3] = spd[2] + fabs(bxi) / sqrtdr;
+
+  double ptstl = ptl + ul.d * sdl * (spd[2] - L[IV1]);
+  double ptstr = ptr + ur.d * sdr * (spd[2] - R[IV1]);
+  double ptst = 0.5 * (ptstr + ptstl);
+
+  ulst.mx = ulst.d * spd[2];
+  if (fabs(ul.d * sdl * sdml - bxsq) < (SMALL_NUMBER)*ptst) {
+    ulst.my = ulst.d * L[IV2];
+    ulst.mz = ulst.d * L[IV3];
+    ulst.by = ul.by;
+    ulst.bz = ul.bz;
+  } else {
+    double tmp = bxi * (sdl - sdml) / (ul.d * sdl * sdml - bxsq);
+    ulst.my = ulst.d * (L[IV2] - ul.by * tmp);
+    ulst.mz = ulst.d * (L[IV3] - ul.bz * tmp);
+    tmp = (ul.d * SQR(sdl) - bxsq) / (ul.d * sdl * sdml - bxsq);
+    ulst.by = ul.by * tmp;
+    ulst.bz = ul.bz * tmp;
+  }
+  double vbstl = (ulst.mx * bxi + (ulst.my * ulst.by + ulst.mz * ulst.bz)) * ulst_d_inv;
+  ulst.e = (sdl * ul.e - ptl * L[IV1] + ptst * spd[2] +
+            bxi * (L[IV1] * bxi + (L[IV2] * ul.by + L[IV3] * ul.bz) - vbstl)) *
+           sdml_inv;
+
+  urst.mx = urst.d * spd[2];
+  if (fabs(ur.d * sdr * sdmr - bxsq) < (SMALL_NUMBER)*ptst) {
+    urst.my = urst.d * R[IV2];
+    urst.mz = urst.d * R[IV3];
+    urst.by = ur.by;
+    urst.bz = ur.bz;
+  } else {
+    double tmp = bxi * (sdr - sdmr) / (ur.d * sdr * sdmr - bxsq);
+    urst.my = urst.d * (R[IV2] - ur.by * tmp);
+    urst.mz = urst.d * (R[IV3] - ur.bz * tmp);
+    tmp = (ur.d * SQR(sdr) - bxsq) / (ur.d * sdr * sdmr - bxsq);
+    urst.by = ur.by * tmp;
+    urst.bz = ur.bz * tmp;
+  }
+  double vbstr = (urst.mx * bxi + (urst.my * urst.by + urst.mz * urst.bz)) * urst_d_inv;
+  urst.e = (sdr * ur.e - ptr * R[IV1] + ptst * spd[2] +
+            bxi * (R[IV1] * bxi + (R[IV2] * ur.by + R[IV3] * ur.bz) - vbstr)) *
+           sdmr_inv;
+
+  if (0.5 * bxsq < (SMALL_NUMBER)*ptst) {
+    uldst = ulst;
+    urdst = urst;
+  } else {
+    double invsumd = 1.0 / (sqrtdl + sqrtdr);
+    double bxsig = (bxi > 0.0 ? 1.0 : -1.0);
+    uldst.d = ulst.d;
+    urdst.d = urst.d;
+    uldst.mx = ulst.mx;
+    urdst.mx = urst.mx;
+    double tmp = invsumd * (sqrtdl * (ulst.my * ulst_d_inv) + sqrtdr * (urst.my * urst_d_inv) +
+                            bxsig * (urst.by - ulst.by));
+    uldst.my = uldst.d * tmp;
+    urdst.my = urdst.d * tmp;
+    tmp = invsumd * (sqrtdl * (ulst.mz * ulst_d_inv) + sqrtdr * (urst.mz * urst_d_inv) +
+                     bxsig * (urst.bz - ulst.bz));
+    uldst.mz = uldst.d * tmp;
+    urdst.mz = urdst.d * tmp;
+    tmp = invsumd * (sqrtdl * urst.by + sqrtdr * ulst.by +
+                     bxsig * sqrtdl * sqrtdr * ((urst.my * urst_d_inv) - (ulst.my * ulst_d_inv)));
+    uldst.by = urdst.by = tmp;
+    tmp = invsumd * (sqrtdl * urst.bz + sqrtdr * ulst.bz +
+                     bxsig * sqrtdl * sqrtdr * ((urst.mz * urst_d_inv) - (ulst.mz * ulst_d_inv)));
+    uldst.bz = urdst.bz = tmp;
+    tmp = spd[2] * bxi + (uldst.my * uldst.by + uldst.mz * uldst.bz) / uldst.d;
+    uldst.e = ulst.e - sqrtdl * bxsig * (vbstl - tmp);
+    urdst.e = urst.e + sqrtdr * bxsig * (vbstr - tmp);
+  }
+
+#define SCALE_DIFF(out, s, a, b)  \
+  out.d = s * (a.d - b.d);        \
+  out.mx = s * (a.mx - b.mx);     \
+  out.my = s * (a.my - b.my);     \
+  out.mz = s * (a.mz - b.mz);     \
+  out.e = s * (a.e - b.e);        \
+  out.by = s * (a.by - b.by);     \
+  out.bz = s * (a.bz - b.bz);
+  SCALE_DIFF(uldst, spd[1], uldst, ulst)
+  SCALE_DIFF(ulst, spd[0], ulst, ul)
+  SCALE_DIFF(urdst, spd[3], urdst, urst)
+  SCALE_DIFF(urst, spd[4], urst, ur)
+#undef SCALE_DIFF
+
+  if (spd[0] >= 0.0) {
+    f[IDN] = fl.d; f[IV1] = fl.mx; f[IV2] = fl.my; f[IV3] = fl.mz; f[IEN] = fl.e;
+    f[IB2] = fl.by; f[IB3] = fl.bz;
+  } else if (spd[4] <= 0.0) {
+    f[IDN] = fr.d; f[IV1] = fr.mx; f[IV2] = fr.my; f[IV3] = fr.mz; f[IEN] = fr.e;
+    f[IB2] = fr.by; f[IB3] = fr.bz;
+  } else if (spd[1] >= 0.0) {
+    f[IDN] = fl.d + ulst.d; f[IV1] = fl.mx + ulst.mx; f[IV2] = fl.my + ulst.my;
+    f[IV3] = fl.mz + ulst.mz; f[IEN] = fl.e + ulst.e; f[IB2] = fl.by + ulst.by;
+    f[IB3] = fl.bz + ulst.bz;
+  } else if (spd[2] >= 0.0) {
+    f[IDN] = fl.d + ulst.d + uldst.d; f[IV1] = fl.mx + ulst.mx + uldst.mx;
+    f[IV2] = fl.my + ulst.my + uldst.my; f[IV3] = fl.mz + ulst.mz + uldst.mz;
+    f[IEN] = fl.e + ulst.e + uldst.e; f[IB2] = fl.by + ulst.by + uldst.by;
+    f[IB3] = fl.bz + ulst.bz + uldst.bz;
+  } else if (spd[3] > 0.0) {
+    f[IDN] = fr.d + urst.d + urdst.d; f[IV1] = fr.mx + urst.mx + urdst.mx;
+    f[IV2] = fr.my + urst.my + urdst.my; f[IV3] = fr.mz + urst.mz + urdst.mz;
+    f[IEN] = fr.e + urst.e + urdst.e; f[IB2] = fr.by + urst.by + urdst.by;
+    f[IB3] = fr.bz + urst.bz + urdst.bz;
+  } else {
+    f[IDN] = fr.d + urst.d; f[IV1] = fr.mx + urst.mx; f[IV2] = fr.my + urst.my;
+    f[IV3] = fr.mz + urst.mz; f[IEN] = fr.e + urst.e; f[IB2] = fr.by + urst.by;
+    f[IB3] = fr.bz + urst.bz;
+  }
+
+  flx[IDN] = f[IDN];
+  flx[ivx] = f[IV1];
+  flx[ivy] = f[IV2];
+  flx[ivz] = f[IV3];
+  flx[IEN] = f[IEN];
+  flx[iBx] = f[IB1];
+  flx[iBy] = f[IB2];
+  flx[iBz] = f[IB3];
+  flx[IPS] = f[IPS];
+}
+
+static void riemann_face(int fluid, int solver, int ivx, const double *wl, const double *wr,
+                         double gamma, double c_h, double *flx) {
+  const int nh = (fluid == APKO_FLUID_GLMMHD) ? NGLMMHD : NHYDRO;
+  if (solver == APKO_RS_NONE) { /* rsolvers.hpp:35-63 */
+    for (int n = 0; n < nh; ++n) flx[n] = 0.0;
+    return;
+  }
+  if (fluid == APKO_FLUID_EULER) {
+    if (solver == APKO_RS_HLLE) rs_hydro_hlle(ivx, wl, wr, gamma, flx);
+    else if (solver == APKO_RS_HLLC) rs_hydro_hllc(ivx, wl, wr, gamma, flx);
+    else if (solver == APKO_RS_LLF) rs_hydro_llf(ivx, wl, wr, gamma, flx);
+    else for (int n = 0; n < nh; ++n) flx[n] = NAN;
+  } else {
+    if (solver == APKO_RS_HLLE) rs_mhd_hlle(ivx, wl, wr, gamma, c_h, flx);
+    else if (solver == APKO_RS_HLLD) rs_mhd_hlld(ivx, wl, wr, gamma, c_h, flx);
+    else if (solver == APKO_RS_LLF) rs_mhd_llf(ivx, wl, wr, gamma, c_h, flx);
+    else for (int n = 0; n < nh; ++n) flx[n] = NAN;
+  }
+}
+
+void apko_riemann_face(int fluid, int solver, int ivx, const double *wl, const double *wr,
+                       double gamma, double c_h, double *flux) {
+  riemann_face(fluid, solver, ivx, wl, wr, gamma, c_h, flux);
+}
+
+/* ===================================================================================== */
+/* Mesh / engine                                                                         */
+/* ===================================================================================== */
+
+typedef struct {
+  double *cons, *prim, *u1, *flux[3];
+  double xmin[3]; /* coords xmin_ (incl. ghost offset), uniform_coordinates.hpp:32-36 */
+  double dx[3];
+  double bxmin[3], bxmax[3]; /* physical block bounds */
+  int loc[3];
+} block_t;
+
+struct apko_engine {
+  apko_params p;
+  int ndim, nvar, nhydro;
+  int nb[3], nblocks;
+  int n[3];      /* array extents incl. ghosts */
+  int is[3], ie[3];
+  size_t ncell;  /* n1*n2*n3 */
+  block_t *blk;
+  /* driver state (driver.cpp, hydro.cpp Params) */
+  double time, dt, tlim;
+  int ncycle;
+  double c_h, mindx, dt_hyp;
+  double new_dt; /* allowed dt voted by the last EstimateTimestep */
+  /* linear wave pgen state (linear_wave.cpp:43-51) */
+  struct {
+    int set, wave_flag;
+    double amp, vflow, sin_a2, cos_a2, sin_a3, cos_a3, lambda, k_par, d0, p0, u0, gam, gm1;
+    double ev[5], rem[5][5];
+    double tlim_period;
+  } lw;
+};
+
+void apko_default_params(apko_params *p) {
+  memset(p, 0, sizeof(*p));
+  p->fluid = APKO_FLUID_EULER;
+  p->recon = APKO_RECON_PLM;
+  p->riemann = APKO_RS_HLLE;
+  p->integrator = APKO_INT_VL2;
+  for (int d = 0; d < 3; ++d) {
+    p->nx[d] = 1;
+    p->mb[d] = 1;
+    p->xmin[d] = -0.5;
+    p->xmax[d] = 0.5;
+  }
+  p->ng = 2;
+  p->gamma = 5.0 / 3.0;
+  p->cfl = 0.3;
+  p->dfloor = p->pfloor = p->efloor = -1.0; /* hydro.cpp:507-510 */
+  p->vceil = p->eceil = INFINITY;           /* hydro.cpp:525-529 */
+  p->glmmhd_alpha = 0.1;                    /* hydro.cpp:295 */
+}
+
+/* mesh/forest/logical_location.cpp:61-74 */
+static double index_to_sym_coord(int index, int bloc, int nrange) {
+  int64_t noffset = index - (nrange) / 2;
+  int64_t noffset_ceil = index - (nrange + 1) / 2;
+  return (double)(noffset + noffset_ceil + (int64_t)bloc) / (2.0 * nrange);
+}
+/* defs.hpp:106-109 */
+static double sym_logical_to_actual(double u, double xmin, double xmax) {
+  return 0.5 * (xmin + xmax) + (u * xmax - u * xmin);
+}
+static int max_pow2_divisor(int in) { return in & (~(in - 1)); }
+
+/* Block physical bounds: forest.cpp:66-141 (trees) + tree.cpp:296-318 (block in tree) */
+static void block_bounds(const apko_engine *e, int d, int ib, double *bmin, double *bmax) {
+  const apko_params *p = &e->p;
+  int any_sym = 0, mcp2 = 1 << 30;
+  for (int dd = 0; dd < 3; ++dd) {
+    if (p->nx[dd] == 1) {
+      any_sym = 1;
+      continue;
+    }
+    int m = max_pow2_divisor(e->nb[dd]);
+    if (m < mcp2) mcp2 = m;
+  }
+  /* forest.cpp:77-82: hitting a symmetry dir resets the divisor to 1; later dirs can only
+   * lower it further, earlier ones are overwritten -> effectively 1 if x3 (last) is
+   * symmetric; if only an earlier dir is symmetric the min continues from 1 as well. */
+  if (any_sym) mcp2 = 1;
+  if (p->nx[d] == 1) {
+    double u0 = index_to_sym_coord(0, 0, 1), u1 = index_to_sym_coord(0, 2, 1);
+    *bmin = sym_logical_to_actual(u0, p->xmin[d], p->xmax[d]);
+    *bmax = sym_logical_to_actual(u1, p->xmin[d], p->xmax[d]);
+    return;
+  }
+  int ntree = e->nb[d] / mcp2;
+  int it = ib / mcp2, lx = ib % mcp2;
+  double tmin = sym_logical_to_actual(index_to_sym_coord(it, 0, ntree), p->xmin[d], p->xmax[d]);
+  double tmax = sym_logical_to_actual(index_to_sym_coord(it, 2, ntree), p->xmin[d], p->xmax[d]);
+  *bmin = sym_logical_to_actual(index_to_sym_coord(lx, 0, mcp2), tmin, tmax);
+  *bmax = sym_logical_to_actual(index_to_sym_coord(lx, 2, mcp2), tmin, tmax);
+}
+
+static inline size_t IDX(const apko_engine *e, int n, int k, int j, int i) {
+  return (((size_t)n * e->n[2] + k) * e->n[1] + j) * e->n[0] + i;
+}
+
+/* uniform_coordinates.hpp:110-114 */
+static inline double xc(const block_t *b, int d, int idx) {
+  return b->xmin[d] + (idx + 0.5) * b->dx[d];
+}
+
+apko_engine *apko_create(const apko_params *p) {
+  apko_engine *e = (apko_engine *)calloc(1, sizeof(*e));
+  e->p = *p;
+  e->nhydro = (p->fluid == APKO_FLUID_GLMMHD) ? NGLMMHD : NHYDRO;
+  e->nvar = e->nhydro + p->nscalars;
+  e->ndim = (p->nx[2] > 1) ? 3 : ((p->nx[1] > 1) ? 2 : 1);
+  e->nblocks = 1;
+  for (int d = 0; d < 3; ++d) {
+    if (p->nx[d] % p->mb[d] != 0) {
+      free(e);
+      return NULL;
+    }
+    e->nb[d] = p->nx[d] / p->mb[d];
+    e->nblocks *= e->nb[d];
+    int sym = (p->nx[d] == 1);
+    e->n[d] = sym ? 1 : p->mb[d] + 2 * p->ng;
+    e->is[d] = sym ? 0 : p->ng;
+    e->ie[d] = sym ? 0 : p->ng + p->mb[d] - 1;
+  }
+  e->ncell = (size_t)e->n[0] * e->n[1] * e->n[2];
+  e->blk = (block_t *)calloc(e->nblocks, sizeof(block_t));
+  size_t nfield = e->ncell * e->nvar;
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    B->cons = (double *)calloc(nfield, sizeof(double));
+    B->prim = (double *)calloc(nfield, sizeof(double));
+    B->u1 = (double *)calloc(nfield, sizeof(double));
+    for (int d = 0; d < 3; ++d) B->flux[d] = (double *)calloc(nfield, sizeof(double));
+    B->loc[0] = b % e->nb[0];
+    B->loc[1] = (b / e->nb[0]) % e->nb[1];
+    B->loc[2] = b / (e->nb[0] * e->nb[1]);
+    for (int d = 0; d < 3; ++d) {
+      block_bounds(e, d, B->loc[d], &B->bxmin[d], &B->bxmax[d]);
+      /* uniform_coordinates.hpp:32-36 */
+      B->dx[d] = (B->bxmax[d] - B->bxmin[d]) / p->mb[d];
+      int istart = (p->nx[d] == 1) ? 0 : p->ng;
+      B->xmin[d] = B->bxmin[d] - istart * B->dx[d];
+    }
+  }
+  e->dt = DBL_MAX;
+  e->mindx = DBL_MAX;
+  e->dt_hyp = DBL_MAX;
+  e->new_dt = DBL_MAX;
+  e->tlim = DBL_MAX;
+  return e;
+}
+
+void apko_destroy(apko_engine *e) {
+  if (!e) return;
+  for (int b = 0; b < e->nblocks; ++b) {
+    free(e->blk[b].cons);
+    free(e->blk[b].prim);
+    free(e->blk[b].u1);
+    for (int d = 0; d < 3; ++d) free(e->blk[b].flux[d]);
+  }
+  free(e->blk);
+  free(e);
+}
+
+int apko_num_blocks(const apko_engine *e) { return e->nblocks; }
+void apko_block_dims(const apko_engine *e, int *n) { n[0] = e->n[0]; n[1] = e->n[1]; n[2] = e->n[2]; }
+int apko_nvar(const apko_engine *e) { return e->nvar; }
+double *apko_cons(apko_engine *e, int b) { return e->blk[b].cons; }
+double *apko_prim(apko_engine *e, int b) { return e->blk[b].prim; }
+double *apko_flux(apko_engine *e, int b, int dir) { return e->blk[b].flux[dir]; }
+void apko_block_coords(const apko_engine *e, int b, double *xmin3, double *dx3) {
+  for (int d = 0; d < 3; ++d) {
+    xmin3[d] = e->blk[b].xmin[d];
+    dx3[d] = e->blk[b].dx[d];
+  }
+}
+double apko_time(const apko_engine *e) { return e->time; }
+double apko_dt(const apko_engine *e) { return e->dt; }
+int apko_ncycle(const apko_engine *e) { return e->ncycle; }
+double apko_c_h(const apko_engine *e) { return e->c_h; }
+void apko_set_c_h(apko_engine *e, double c_h) { e->c_h = c_h; }
+double apko_lw_tlim(const apko_engine *e) { return e->lw.tlim_period; }
+
+/* ===================================================================================== */
+/* CalculateFluxes: src/hydro/hydro.cpp:1025-1208                                         */
+/* ===================================================================================== */
+
+/* reconstruct all variables of cell (k,j,i) along dir d -> ql (left state of face +1), qr
+ * (right state of the cell's lower face); the Reconstruct<> wrappers in src/recon */
+static void recon_cell(const apko_engine *e, const block_t *B, int recon, int d, int k, int j,
+                       int i, double *ql, double *qr) {
+  const ptrdiff_t st = (d == 0) ? 1 : (d == 1) ? e->n[0] : (ptrdiff_t)e->n[0] * e->n[1];
+  for (int n = 0; n < e->nvar; ++n) {
+    const double *q = &B->prim[IDX(e, n, k, j, i)];
+    switch (recon) {
+    case APKO_RECON_DC:
+      ql[n] = qr[n] = q[0];
+      break;
+    case APKO_RECON_PLM:
+      rc_plm(q[-st], q[0], q[st], &ql[n], &qr[n]);
+      break;
+    case APKO_RECON_PPM:
+      rc_ppm(q[-2 * st], q[-st], q[0], q[st], q[2 * st], &ql[n], &qr[n]);
+      break;
+    case APKO_RECON_WENOZ:
+      rc_wenoz(q[-2 * st], q[-st], q[0], q[st], q[2 * st], &ql[n], &qr[n]);
+      break;
+    case APKO_RECON_WENO3:
+      rc_weno3(q[-st], q[0], q[st], B->dx[d] * B->dx[d], &ql[n], &qr[n]);
+      break;
+    case APKO_RECON_LIMO3:
+      rc_limo3(q[-st], q[0], q[st], B->dx[d], (n == IDN || n == IPR), &ql[n], &qr[n]);
+      break;
+    }
+  }
+}
+
+/* Riemann solve + passive scalar upwinding for one face, store to flux array */
+static void face_flux(const apko_engine *e, block_t *B, int d, int k, int j, int i,
+                      const double *wl, const double *wr) {
+  double f[MAXVAR];
+  riemann_face(e->p.fluid, e->p.riemann, IV1 + d, wl, wr, e->p.gamma, e->c_h, f);
+  /* hydro.cpp:1089-1097: scalars upwinded by the sign of the mass flux */
+  for (int n = e->nhydro; n < e->nvar; ++n) f[n] = (f[IDN] >= 0.0) ? f[IDN] * wl[n] : f[IDN] * wr[n];
+  for (int n = 0; n < e->nvar; ++n) B->flux[d][IDX(e, n, k, j, i)] = f[n];
+}
+
+void apko_calc_fluxes(apko_engine *e, int recon) {
+  if (e->p.riemann == APKO_RS_LLF) {
+    /* CalculateFluxesTight, hydro.cpp:980-1022 (DC + LLF, cell-wise) */
+    for (int b = 0; b < e->nblocks; ++b) {
+      block_t *B = &e->blk[b];
+      int ku = e->ie[2] + (e->ndim >= 3), ju = e->ie[1] + (e->ndim >= 2);
+      for (int k = e->is[2]; k <= ku; ++k)
+        for (int j = e->is[1]; j <= ju; ++j)
+          for (int i = e->is[0]; i <= e->ie[0] + 1; ++i)
+            for (int d = 0; d < e->ndim; ++d) {
+              double wl[MAXVAR], wr[MAXVAR];
+              int kk = k - (d == 2), jj = j - (d == 1), ii = i - (d == 0);
+              for (int n = 0; n < e->nvar; ++n) {
+                wl[n] = B->prim[IDX(e, n, kk, jj, ii)];
+                wr[n] = B->prim[IDX(e, n, k, j, i)];
+              }
+              face_flux(e, B, d, k, j, i, wl, wr);
+            }
+    }
+    return;
+  }
+  const int n1 = e->n[0];
+  double *wl = (double *)malloc(sizeof(double) * MAXVAR * (n1 + 1) * 3);
+  double *wr = wl + MAXVAR * (n1 + 1);
+  double *wlb = wr + MAXVAR * (n1 + 1);
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    const int is = e->is[0], ie = e->ie[0], js = e->is[1], je = e->ie[1], ks = e->is[2],
+              ke = e->ie[2];
+    /* x1: loop limits hydro.cpp:1031-1039 (over-compute into transverse ghosts) */
+    int jl = js, ju = je, kl = ks, ku = ke;
+    if (e->ndim >= 2) { jl = js - 1; ju = je + 1; }
+    if (e->ndim >= 3) { kl = ks - 1; ku = ke + 1; }
+    for (int k = kl; k <= ku; ++k)
+      for (int j = jl; j <= ju; ++j) {
+        for (int i = is - 1; i <= ie + 1; ++i) /* ql(n,i+1), qr(n,i) */
+          recon_cell(e, B, recon, 0, k, j, i, &wl[MAXVAR * (i + 1)], &wr[MAXVAR * i]);
+        for (int i = is; i <= ie + 1; ++i)
+          face_flux(e, B, 0, k, j, i, &wl[MAXVAR * i], &wr[MAXVAR * i]);
+      }
+    /* x2: hydro.cpp:1101-1153 */
+    if (e->ndim >= 2) {
+      int il = is - 1, iu = ie + 1;
+      kl = ks; ku = ke;
+      if (e->ndim >= 3) { kl = ks - 1; ku = ke + 1; }
+      for (int k = kl; k <= ku; ++k) {
+        double *pl = wl, *plb = wlb;
+        for (int j = js - 1; j <= je + 1; ++j) {
+          for (int i = il; i <= iu; ++i)
+            recon_cell(e, B, recon, 1, k, j, i, &plb[MAXVAR * i], &wr[MAXVAR * i]);
+          if (j > js - 1)
+            for (int i = il; i <= iu; ++i)
+              face_flux(e, B, 1, k, j, i, &pl[MAXVAR * i], &wr[MAXVAR * i]);
+          double *t = pl; pl = plb; plb = t;
+        }
+      }
+    }
+    /* x3: hydro.cpp:1156-1199 */
+    if (e->ndim >= 3) {
+      int il = is - 1, iu = ie + 1;
+      for (int j = js - 1; j <= je + 1; ++j) {
+        double *pl = wl, *plb = wlb;
+        for (int k = ks - 1; k <= ke + 1; ++k) {
+          for (int i = il; i <= iu; ++i)
+            recon_cell(e, B, recon, 2, k, j, i, &plb[MAXVAR * i], &wr[MAXVAR * i]);
+          if (k > ks - 1)
+            for (int i = il; i <= iu; ++i)
+              face_flux(e, B, 2, k, j, i, &pl[MAXVAR * i], &wr[MAXVAR * i]);
+          double *t = pl; pl = plb; plb = t;
+        }
+      }
+    }
+  }
+  free(wl);
+}
+
+/* ===================================================================================== */
+/* Flux divergence update: external/parthenon/src/interface/update.hpp:42-56,             */
+/* update.cpp:115-141                                                                     */
+/* ===================================================================================== */
+static inline double flux_div(const apko_engine *e, const block_t *B, int l, int k, int j,
+                              int i) {
+  /* uniform_coordinates.hpp:37-40 */
+  const double a1 = B->dx[1] * B->dx[2], a2 = B->dx[0] * B->dx[2], a3 = B->dx[0] * B->dx[1];
+  const double vol = B->dx[0] * B->dx[1] * B->dx[2];
+  double du = (a1 * B->flux[0][IDX(e, l, k, j, i + 1)] - a1 * B->flux[0][IDX(e, l, k, j, i)]);
+  if (e->ndim >= 2)
+    du += (a2 * B->flux[1][IDX(e, l, k, j + 1, i)] - a2 * B->flux[1][IDX(e, l, k, j, i)]);
+  if (e->ndim == 3)
+    du += (a3 * B->flux[2][IDX(e, l, k + 1, j, i)] - a3 * B->flux[2][IDX(e, l, k, j, i)]);
+  return -du / vol;
+}
+
+void apko_flux_div_update(apko_engine *e, double g0, double g1, double bdt) {
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    for (int l = 0; l < e->nvar; ++l)
+      for (int k = e->is[2]; k <= e->ie[2]; ++k)
+        for (int j = e->is[1]; j <= e->ie[1]; ++j)
+          for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+            size_t c = IDX(e, l, k, j, i);
+            B->cons[c] = g0 * B->cons[c] + g1 * B->u1[c] + bdt * flux_div(e, B, l, k, j, i);
+          }
+  }
+}
+
+/* ===================================================================================== */
+/* First-order flux correction: src/hydro/hydro.cpp:1223-1342                             */
+/* ===================================================================================== */
+static void llf_face(const apko_engine *e, block_t *B, double *const *fdst, int d, int k, int j,
+                     int i) {
+  double wl[MAXVAR], wr[MAXVAR], f[MAXVAR];
+  int kk = k - (d == 2), jj = j - (d == 1), ii = i - (d == 0);
+  for (int n = 0; n < e->nvar; ++n) {
+    wl[n] = B->prim[IDX(e, n, kk, jj, ii)];
+    wr[n] = B->prim[IDX(e, n, k, j, i)];
+  }
+  if (e->p.fluid == APKO_FLUID_EULER) rs_hydro_llf(IV1 + d, wl, wr, e->p.gamma, f);
+  else rs_mhd_llf(IV1 + d, wl, wr, e->p.gamma, e->c_h, f);
+  /* scalar fluxes: *_dc_llf.hpp "Passive scalar fluxes" */
+  for (int n = e->nhydro; n < e->nvar; ++n) f[n] = (f[IDN] >= 0.0) ? f[IDN] * wl[n] : f[IDN] * wr[n];
+  for (int n = 0; n < e->nvar; ++n) fdst[d][IDX(e, n, k, j, i)] = f[n];
+}
+
+long long apko_fofc(apko_engine *e, double g0, double g1, double bdt) {
+  long long total = 0, num_corrected;
+  int attempts = 0;
+  const int nh = e->nhydro; /* NVAR = GetNVars<fluid>() : scalars are not part of the check */
+  size_t nfield = e->ncell * e->nvar;
+  double *snap[3] = {NULL, NULL, NULL};
+  do {
+    num_corrected = 0;
+    for (int b = 0; b < e->nblocks; ++b) {
+      block_t *B = &e->blk[b];
+      double *fsrc[3] = {B->flux[0], B->flux[1], B->flux[2]};
+      if (e->p.fofc_jacobi) {
+        /* Jacobi variant: decisions from a snapshot of the fluxes of the previous attempt */
+        for (int d = 0; d < e->ndim; ++d) {
+          if (!snap[d]) snap[d] = (double *)malloc(nfield * sizeof(double));
+          memcpy(snap[d], B->flux[d], nfield * sizeof(double));
+          fsrc[d] = snap[d];
+        }
+      }
+      block_t S = *B;
+      for (int d = 0; d < 3; ++d) S.flux[d] = fsrc[d];
+      for (int k = e->is[2]; k <= e->ie[2]; ++k)
+        for (int j = e->is[1]; j <= e->ie[1]; ++j)
+          for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+            double nc[NGLMMHD];
+            for (int v = 0; v < nh; ++v) {
+              size_t c = IDX(e, v, k, j, i);
+              nc[v] = g0 * B->cons[c] + g1 * B->u1[c] + bdt * flux_div(e, &S, v, k, j, i);
+            }
+            double new_p =
+                nc[IEN] - 0.5 * (SQR(nc[IM1]) + SQR(nc[IM2]) + SQR(nc[IM3])) / nc[IDN];
+            if (e->p.fluid == APKO_FLUID_GLMMHD)
+              new_p -= 0.5 * (SQR(nc[IB1]) + SQR(nc[IB2]) + SQR(nc[IB3]));
+            if (nc[IDN] > 0.0 && new_p > 0.0) continue;
+            if (attempts > 2 && nc[IDN] > 0.0 && new_p < 0.0) continue;
+            llf_face(e, B, B->flux, 0, k, j, i);
+            llf_face(e, B, B->flux, 0, k, j, i + 1);
+            if (e->ndim >= 2) {
+              llf_face(e, B, B->flux, 1, k, j, i);
+              llf_face(e, B, B->flux, 1, k, j + 1, i);
+            }
+            if (e->ndim >= 3) {
+              llf_face(e, B, B->flux, 2, k, j, i);
+              llf_face(e, B, B->flux, 2, k + 1, j, i);
+            }
+            num_corrected += 1;
+          }
+    }
+    total += num_corrected;
+    attempts += 1;
+  } while (num_corrected > 0 && attempts < 4);
+  for (int d = 0; d < 3; ++d) free(snap[d]);
+  return total;
+}
+
+/* ===================================================================================== */
+/* Dedner source: src/hydro/glmmhd/dedner_source.cpp:17-75                                */
+/* ===================================================================================== */
+void apko_dedner(apko_engine *e, double bdt) {
+  if (e->p.fluid != APKO_FLUID_GLMMHD) return;
+  const double coeff = exp(-e->p.glmmhd_alpha * e->c_h * bdt / e->mindx);
+  const int ko = (e->ndim < 3) ? 0 : 1;
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    for (int k = e->is[2]; k <= e->ie[2]; ++k)
+      for (int j = e->is[1]; j <= e->ie[1]; ++j)
+        for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+          if (e->p.dedner_extended) {
+#define P(n, kk, jj, ii) B->prim[IDX(e, n, kk, jj, ii)]
+            /* NOTE: 2-D assumed to have j-neighbours (ndim>=2) like the reference */
+            const double divB =
+                0.5 * ((P(IB1, k, j, i + 1) - P(IB1, k, j, i - 1)) / B->dx[0] +
+                       (P(IB2, k, j + 1, i) - P(IB2, k, j - 1, i)) / B->dx[1] +
+                       (P(IB3, k + ko, j, i) - P(IB3, k - ko, j, i)) / B->dx[2]);
+            B->cons[IDX(e, IM1, k, j, i)] -= bdt * divB * P(IB1, k, j, i);
+            B->cons[IDX(e, IM2, k, j, i)] -= bdt * divB * P(IB2, k, j, i);
+            B->cons[IDX(e, IM3, k, j, i)] -= bdt * divB * P(IB3, k, j, i);
+            B->cons[IDX(e, IEN, k, j, i)] -=
+                0.5 * bdt *
+                (P(IB1, k, j, i) * (P(IPS, k, j, i + 1) - P(IPS, k, j, i - 1)) / B->dx[0] +
+                 P(IB2, k, j, i) * (P(IPS, k, j + 1, i) - P(IPS, k, j - 1, i)) / B->dx[1] +
+                 P(IB3, k, j, i) * (P(IPS, k + ko, j, i) - P(IPS, k - ko, j, i)) / B->dx[2]);
+#undef P
+          }
+          B->cons[IDX(e, IPS, k, j, i)] *= coeff;
+        }
+  }
+}
+
+/* ===================================================================================== */
+/* Ghost exchange (same level) + physical BCs                                             */
+/* bvals/comms/bnd_info.cpp:105-230 (index ranges), boundary_communication.cpp:48-348,    */
+/* bvals/boundary_conditions.cpp:36-59, boundary_conditions_generic.hpp:174-262,          */
+/* src/bvals/boundary_conditions_apk.hpp:38-85                                            */
+/* ===================================================================================== */
+static void apply_bc(apko_engine *e, block_t *B, int d, int outer, int type) {
+  if (e->p.nx[d] == 1) return;
+  int lo[3] = {0, 0, 0}, hi[3] = {e->n[0] - 1, e->n[1] - 1, e->n[2] - 1};
+  const int ref = outer ? e->ie[d] : e->is[d];
+  if (outer) lo[d] = e->ie[d] + 1;
+  else hi[d] = e->is[d] - 1;
+  const int offset = 2 * ref + (outer ? 1 : -1);
+  for (int n = 0; n < e->nvar; ++n) {
+    /* AthenaPK ReflectBC flips v == DIR, i.e. the normal momentum (euler only) */
+    const double sgn = (type == APKO_BC_REFLECT && n == d + 1) ? -1.0 : 1.0;
+    for (int k = lo[2]; k <= hi[2]; ++k)
+      for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) {
+          int c[3] = {i, j, k};
+          c[d] = (type == APKO_BC_REFLECT) ? offset - c[d] : ref;
+          B->cons[IDX(e, n, k, j, i)] = sgn * B->cons[IDX(e, n, c[2], c[1], c[0])];
+        }
+  }
+}
+
+void apko_exchange(apko_engine *e) {
+  const int ng = e->p.ng;
+  /* same-level neighbour copies; reads interiors only, writes ghosts only */
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    int omax[3] = {e->p.nx[0] > 1, e->p.nx[1] > 1, e->p.nx[2] > 1};
+    for (int o3 = -omax[2]; o3 <= omax[2]; ++o3)
+      for (int o2 = -omax[1]; o2 <= omax[1]; ++o2)
+        for (int o1 = -omax[0]; o1 <= omax[0]; ++o1) {
+          if (!o1 && !o2 && !o3) continue;
+          int off[3] = {o1, o2, o3}, nl[3], valid = 1;
+          for (int d = 0; d < 3; ++d) {
+            nl[d] = B->loc[d] + off[d];
+            if (nl[d] < 0 || nl[d] >= e->nb[d]) {
+              int face = 2 * d + (nl[d] < 0 ? 0 : 1);
+              if (e->p.bc[face] != APKO_BC_PERIODIC) valid = 0;
+              nl[d] = (nl[d] + e->nb[d]) % e->nb[d];
+            }
+          }
+          if (!valid) continue;
+          const block_t *N = &e->blk[nl[0] + e->nb[0] * (nl[1] + e->nb[1] * nl[2])];
+          int dlo[3], dhi[3], shift[3];
+          for (int d = 0; d < 3; ++d) {
+            if (off[d] == 0) { dlo[d] = e->is[d]; dhi[d] = e->ie[d]; shift[d] = 0; }
+            else if (off[d] > 0) { dlo[d] = e->ie[d] + 1; dhi[d] = e->ie[d] + ng; shift[d] = -e->p.mb[d]; }
+            else { dlo[d] = e->is[d] - ng; dhi[d] = e->is[d] - 1; shift[d] = e->p.mb[d]; }
+          }
+          for (int n = 0; n < e->nvar; ++n)
+            for (int k = dlo[2]; k <= dhi[2]; ++k)
+              for (int j = dlo[1]; j <= dhi[1]; ++j)
+                for (int i = dlo[0]; i <= dhi[0]; ++i)
+                  B->cons[IDX(e, n, k, j, i)] =
+                      N->cons[IDX(e, n, k + shift[2], j + shift[1], i + shift[0])];
+        }
+  }
+  /* physical BCs in face order ix1, ox1, ix2, ox2, ix3, ox3 (boundary_conditions.cpp:47-56) */
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    for (int face = 0; face < 6; ++face) {
+      int d = face / 2, outer = face % 2;
+      if (d >= e->ndim) continue;
+      if (e->p.bc[face] == APKO_BC_PERIODIC) continue;
+      if (outer ? (B->loc[d] != e->nb[d] - 1) : (B->loc[d] != 0)) continue;
+      apply_bc(e, B, d, outer, e->p.bc[face]);
+    }
+  }
+}
+
+/* ===================================================================================== */
+/* cons -> prim over the ENTIRE index range: src/eos/adiabatic_glmmhd.cpp:33-56           */
+/* ===================================================================================== */
+void apko_cons_to_prim(apko_engine *e) {
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    for (size_t c = 0; c < e->ncell; ++c) {
+      int err = c2p_cell(e->p.fluid, e->p.nscalars, B->cons + c, B->prim + c, (int)e->ncell,
+                         e->p.gamma, e->p.dfloor, e->p.pfloor, e->p.efloor, e->p.vceil,
+                         e->p.eceil);
+      if (err) {
+        fprintf(stderr, "apk_oracle: negative %s in cons2prim (block %d cell %zu)\n",
+                err == 1 ? "density" : "pressure", b, c);
+        abort(); /* PARTHENON_REQUIRE, adiabatic_hydro.hpp:77-79,111-113 */
+      }
+    }
+  }
+}
+
+/* ===================================================================================== */
+/* Timestep: src/hydro/hydro.cpp:828-976                                                  */
+/* ===================================================================================== */
+double apko_estimate_dt(apko_engine *e) {
+  double min_dt = DBL_MAX;
+  for (int b = 0; b < e->nblocks; ++b) {
+    const block_t *B = &e->blk[b];
+    for (int k = e->is[2]; k <= e->ie[2]; ++k)
+      for (int j = e->is[1]; j <= e->ie[1]; ++j)
+        for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+#define P(n) B->prim[IDX(e, n, k, j, i)]
+          double lx, ly = 0, lz = 0;
+          if (e->p.fluid == APKO_FLUID_EULER) {
+            lx = eos_cs(e->p.gamma, P(IDN), P(IPR));
+            ly = lx;
+            lz = lx;
+          } else {
+            lx = eos_cf(e->p.gamma, P(IDN), P(IPR), P(IB1), P(IB2), P(IB3));
+            if (e->ndim > 1) ly = eos_cf(e->p.gamma, P(IDN), P(IPR), P(IB2), P(IB3), P(IB1));
+            if (e->ndim > 2) lz = eos_cf(e->p.gamma, P(IDN), P(IPR), P(IB3), P(IB1), P(IB2));
+          }
+          min_dt = fmin(min_dt, B->dx[0] / (fabs(P(IV1)) + lx));
+          if (e->ndim > 1) min_dt = fmin(min_dt, B->dx[1] / (fabs(P(IV2)) + ly));
+          if (e->ndim > 2) min_dt = fmin(min_dt, B->dx[2] / (fabs(P(IV3)) + lz));
+#undef P
+        }
+  }
+  if (e->p.riemann == APKO_RS_NONE) return DBL_MAX; /* calc_dt_hyp=false, hydro.cpp:354-361 */
+  /* hydro.cpp:903-908: dt_hyp Param keeps the raw hyperbolic estimate (MHD only) */
+  if (e->p.fluid == APKO_FLUID_GLMMHD) {
+    if (e->p.cfl * min_dt < e->dt_hyp) e->dt_hyp = e->p.cfl * min_dt;
+  }
+  return e->p.cfl * min_dt;
+}
+
+/* hydro.cpp:65-95 */
+static double global_min_dx(const apko_engine *e) {
+  double m = DBL_MAX;
+  for (int b = 0; b < e->nblocks; ++b) {
+    m = fmin(m, e->blk[b].dx[0]);
+    if (e->n[1] > 1) m = fmin(m, e->blk[b].dx[1]);
+    if (e->n[2] > 1) m = fmin(m, e->blk[b].dx[2]);
+  }
+  return m;
+}
+
+/* driver.cpp:210-242,267-269 with default dt_* parameters */
+static void set_global_dt(apko_engine *e) {
+  if (e->dt < 0.1 * DBL_MAX) e->dt *= 2.0;
+  e->dt = smin(e->dt, e->new_dt);
+  e->new_dt = DBL_MAX;
+  if (e->time < e->tlim && (e->tlim - e->time) < e->dt) e->dt = e->tlim - e->time;
+}
+
+void apko_save_u1(apko_engine *e) { /* hydro_driver.cpp:474-495 */
+  for (int b = 0; b < e->nblocks; ++b)
+    memcpy(e->blk[b].u1, e->blk[b].cons, e->ncell * e->nvar * sizeof(double));
+}
+
+void apko_initialize(apko_engine *e, double tlim) {
+  e->tlim = tlim;
+  e->time = 0.0;
+  e->ncycle = 0;
+  apko_exchange(e);
+  apko_cons_to_prim(e);
+  /* EvolutionDriver::InitializeBlockTimeSteps + SetGlobalTimeStep (driver.cpp:194-242) */
+  e->dt = DBL_MAX;
+  e->dt_hyp = DBL_MAX;
+  e->new_dt = apko_estimate_dt(e);
+  set_global_dt(e);
+}
+
+/* low_storage_integrator.cpp:53-132 */
+static int integrator_coeffs(int integ, double *g0, double *g1, double *beta) {
+  switch (integ) {
+  case APKO_INT_RK1:
+    g0[0] = 0.0; g1[0] = 1.0; beta[0] = 1.0;
+    return 1;
+  case APKO_INT_RK2:
+    g0[0] = 0.0; g1[0] = 1.0; beta[0] = 1.0;
+    g0[1] = 0.5; g1[1] = 0.5; beta[1] = 0.5;
+    return 2;
+  case APKO_INT_VL2:
+    g0[0] = 0.0; g1[0] = 1.0; beta[0] = 0.5;
+    g0[1] = 0.0; g1[1] = 1.0; beta[1] = 1.0;
+    return 2;
+  case APKO_INT_RK3:
+    g0[0] = 0.0; g1[0] = 1.0; beta[0] = 1.0;
+    g0[1] = 0.25; g1[1] = 0.75; beta[1] = 0.25;
+    g0[2] = 2.0 / 3.0; g1[2] = 1.0 / 3.0; beta[2] = 2.0 / 3.0;
+    return 3;
+  }
+  return 0;
+}
+
+/* One cycle: driver.cpp:101-133 + hydro_driver.cpp:474-613 */
+void apko_cycle(apko_engine *e) {
+  /* PreStepMeshUserWorkInLoop, hydro.cpp:102-143 */
+  if (e->p.fluid == APKO_FLUID_GLMMHD) {
+    e->mindx = global_min_dx(e);
+    e->c_h = e->p.cfl * e->mindx / e->dt_hyp;
+  }
+  double g0[3], g1[3], beta[3];
+  int nstages = integrator_coeffs(e->p.integrator, g0, g1, beta);
+  for (int s = 0; s < nstages; ++s) {
+    if (s == 0) apko_save_u1(e);
+    /* VL2 predictor uses donor cell, hydro.cpp:459-464 */
+    int recon = (s == 0 && e->p.integrator == APKO_INT_VL2) ? APKO_RECON_DC : e->p.recon;
+    const double bdt = beta[s] * e->dt;
+    apko_calc_fluxes(e, recon);
+    if (e->p.fofc) apko_fofc(e, g0[s], g1[s], bdt);
+    apko_flux_div_update(e, g0[s], g1[s], bdt);
+    apko_dedner(e, bdt);
+    apko_exchange(e);
+    apko_cons_to_prim(e);
+    if (s == nstages - 1) {
+      /* hydro_driver.cpp:589-613: reset reduction Params, then EstimateTimestep */
+      e->mindx = DBL_MAX;
+      e->dt_hyp = DBL_MAX;
+      e->new_dt = apko_estimate_dt(e);
+    }
+  }
+  e->ncycle++;
+  e->time += e->dt;
+  set_global_dt(e);
+}
+
+int apko_run(apko_engine *e, double tlim, int nlim) {
+  int n0 = e->ncycle;
+  if (tlim != e->tlim) {
+    e->tlim = tlim;
+    if (e->time < e->tlim && (e->tlim - e->time) < e->dt) e->dt = e->tlim - e->time;
+  }
+  /* SimTime::KeepGoing, basic_types.hpp:244 */
+  while ((e->time < e->tlim) && (nlim < 0 || e->ncycle < nlim)) apko_cycle(e);
+  return e->ncycle - n0;
+}
+
+/* ===================================================================================== */
+/* Problem generators (input side only; src/pgen)                                         */
+/* ===================================================================================== */
+
+/* src/pgen/linear_wave.cpp:424-505 (hydro eigensystem, right eigenvectors only) */
+static void lw_eigensystem(double gm1, double d, double v1, double v2, double v3, double h,
+                           double ev[5], double rem[5][5]) {
+  (void)d;
+  double vsq = v1 * v1 + v2 * v2 + v3 * v3;
+  double asq = gm1 * smax((h - 0.5 * vsq), TINY_NUMBER);
+  double a = sqrt(asq);
+  ev[0] = v1 - a; ev[1] = v1; ev[2] = v1; ev[3] = v1; ev[4] = v1 + a;
+  rem[0][0] = 1.0; rem[1][0] = v1 - a; rem[2][0] = v2; rem[3][0] = v3; rem[4][0] = h - v1 * a;
+  rem[0][1] = 0.0; rem[1][1] = 0.0; rem[2][1] = 1.0; rem[3][1] = 0.0; rem[4][1] = v2;
+  rem[0][2] = 0.0; rem[1][2] = 0.0; rem[2][2] = 0.0; rem[3][2] = 1.0; rem[4][2] = v3;
+  rem[0][3] = 1.0; rem[1][3] = v1; rem[2][3] = v2; rem[3][3] = v3; rem[4][3] = 0.5 * vsq;
+  rem[0][4] = 1.0; rem[1][4] = v1 + a; rem[2][4] = v2; rem[3][4] = v3; rem[4][4] = h + v1 * a;
+}
+
+/* src/pgen/linear_wave.cpp:69-175 (InitUserMeshData). pars = {wave_flag, amp, vflow,
+ * ang_2, ang_3, ang_2_vert, ang_3_vert}; angles -999.9 => automatic */
+static void lw_setup(apko_engine *e, const double *pars, int npars) {
+  const apko_params *p = &e->p;
+  e->lw.wave_flag = (npars > 0) ? (int)pars[0] : 0;
+  e->lw.amp = (npars > 1) ? pars[1] : 1.0e-6;
+  e->lw.vflow = (npars > 2) ? pars[2] : 0.0;
+  double ang_2 = (npars > 3) ? pars[3] : -999.9;
+  double ang_3 = (npars > 4) ? pars[4] : -999.9;
+  int ang_2_vert = (npars > 5) ? (int)pars[5] : 0;
+  int ang_3_vert = (npars > 6) ? (int)pars[6] : 0;
+  e->lw.gam = p->gamma;
+  e->lw.gm1 = p->gamma - 1.0;
+  double x1size = p->xmax[0] - p->xmin[0];
+  double x2size = p->xmax[1] - p->xmin[1];
+  double x3size = p->xmax[2] - p->xmin[2];
+  if (ang_3 == -999.9) ang_3 = atan(x1size / x2size);
+  double sin_a3 = sin(ang_3), cos_a3 = cos(ang_3);
+  if (ang_3_vert) { sin_a3 = 1.0; cos_a3 = 0.0; ang_3 = 0.5 * M_PI; }
+  if (ang_2 == -999.9) ang_2 = atan(0.5 * (x1size * cos_a3 + x2size * sin_a3) / x3size);
+  double sin_a2 = sin(ang_2), cos_a2 = cos(ang_2);
+  if (ang_2_vert) { sin_a2 = 1.0; cos_a2 = 0.0; ang_2 = 0.5 * M_PI; }
+  double x1 = x1size * cos_a2 * cos_a3;
+  double x2 = x2size * cos_a2 * sin_a3;
+  double x3 = x3size * sin_a2;
+  const int f2 = (p->nx[1] > 1), f3 = (p->nx[2] > 1);
+  double lambda = x1;
+  if (f2 && ang_3 != 0.0) lambda = smin(lambda, x2);
+  if (f3 && ang_2 != 0.0) lambda = smin(lambda, x3);
+  if (ang_3_vert) lambda = x2;
+  if (ang_2_vert) lambda = x3;
+  e->lw.sin_a2 = sin_a2; e->lw.cos_a2 = cos_a2; e->lw.sin_a3 = sin_a3; e->lw.cos_a3 = cos_a3;
+  e->lw.lambda = lambda;
+  e->lw.k_par = 2.0 * (M_PI) / lambda;
+  e->lw.d0 = 1.0;
+  e->lw.u0 = e->lw.vflow;
+  double v0 = 0.0, w0 = 0.0;
+  e->lw.p0 = 1.0 / e->lw.gam;
+  double h0 = ((e->lw.p0 / e->lw.gm1 +
+                0.5 * e->lw.d0 * (e->lw.u0 * e->lw.u0 + v0 * v0 + w0 * w0)) + e->lw.p0) / e->lw.d0;
+  lw_eigensystem(e->lw.gm1, e->lw.d0, e->lw.u0, v0, w0, h0, e->lw.ev, e->lw.rem);
+  /* test=true: tlim counted in wave periods (linear_wave.cpp:166-174), tlim=1 */
+  e->lw.tlim_period = lambda / fabs(e->lw.ev[e->lw.wave_flag]) * 1.0;
+  e->lw.set = 1;
+}
+
+/* analytic/initial state at a cell, linear_wave.cpp:356-372 */
+static void lw_state(const apko_engine *e, const block_t *B, int k, int j, int i, double u[5]) {
+  const int wf = e->lw.wave_flag;
+  const double amp = e->lw.amp;
+  double x = e->lw.cos_a2 * (xc(B, 0, i) * e->lw.cos_a3 + xc(B, 1, j) * e->lw.sin_a3) +
+             xc(B, 2, k) * e->lw.sin_a2;
+  double sn = sin(e->lw.k_par * x);
+  u[IDN] = e->lw.d0 + amp * sn * e->lw.rem[0][wf];
+  double mx = e->lw.d0 * e->lw.vflow + amp * sn * e->lw.rem[1][wf];
+  double my = amp * sn * e->lw.rem[2][wf];
+  double mz = amp * sn * e->lw.rem[3][wf];
+  u[IM1] = mx * e->lw.cos_a2 * e->lw.cos_a3 - my * e->lw.sin_a3 - mz * e->lw.sin_a2 * e->lw.cos_a3;
+  u[IM2] = mx * e->lw.cos_a2 * e->lw.sin_a3 + my * e->lw.cos_a3 - mz * e->lw.sin_a2 * e->lw.sin_a3;
+  u[IM3] = mx * e->lw.sin_a2 + mz * e->lw.cos_a2;
+  u[IEN] = e->lw.p0 / e->lw.gm1 + 0.5 * e->lw.d0 * e->lw.u0 * e->lw.u0 + amp * sn * e->lw.rem[4][wf];
+}
+
+/* deterministic hash -> [0,1) for APKO_PGEN_RANDOM (our own synthetic generator) */
+static double hash01(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  x = x ^ (x >> 31);
+  return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+
+int apko_pgen(apko_engine *e, int id, const double *pars, int npars) {
+  const apko_params *p = &e->p;
+  const double gm1 = p->gamma - 1.0;
+  const int mhd = (p->fluid == APKO_FLUID_GLMMHD);
+  if (id == APKO_PGEN_LINEAR_WAVE) lw_setup(e, pars, npars);
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    memset(B->cons, 0, e->ncell * e->nvar * sizeof(double));
+    for (int k = e->is[2]; k <= e->ie[2]; ++k)
+      for (int j = e->is[1]; j <= e->ie[1]; ++j)
+        for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+#define U(n) B->cons[IDX(e, n, k, j, i)]
+          switch (id) {
+          case APKO_PGEN_LINEAR_WAVE: {
+            double u[5];
+            lw_state(e, B, k, j, i, u);
+            for (int n = 0; n < 5; ++n) U(n) = u[n];
+          } break;
+          case APKO_PGEN_SOD: { /* src/pgen/sod.cpp:23-50; pars = rho_l,pres_l,u_l,rho_r,pres_r,u_r,x_discont */
+            double rho_l = npars > 0 ? pars[0] : 1.0, pres_l = npars > 1 ? pars[1] : 1.0;
+            double u_l = npars > 2 ? pars[2] : 0.0, rho_r = npars > 3 ? pars[3] : 0.125;
+            double pres_r = npars > 4 ? pars[4] : 0.1, u_r = npars > 5 ? pars[5] : 0.0;
+            double x_discont = npars > 6 ? pars[6] : 0.5;
+            if (xc(B, 0, i) < x_discont) {
+              U(IDN) = rho_l;
+              U(IM1) = rho_l * u_l;
+              U(IEN) = 0.5 * rho_l * u_l * u_l + pres_l / (p->gamma - 1.0);
+            } else {
+              U(IDN) = rho_r;
+              U(IM1) = rho_r * u_r;
+              U(IEN) = 0.5 * rho_r * u_r * u_r + pres_r / (p->gamma - 1.0);
+            }
+          } break;
+          case APKO_PGEN_ORSZAG_TANG: { /* src/pgen/orszag_tang.cpp:34-61 */
+            if (!mhd) return -1;
+            double B0 = 1.0 / sqrt(4.0 * M_PI);
+            double d0 = 25.0 / (36.0 * M_PI);
+            double v0 = 1.0;
+            double p0 = 5.0 / (12.0 * M_PI);
+            U(IDN) = d0;
+            U(IM1) = d0 * v0 * sin(2.0 * M_PI * xc(B, 1, j));
+            U(IM2) = -d0 * v0 * sin(2.0 * M_PI * xc(B, 0, i));
+            U(IM3) = 0.0;
+            U(IB1) = B0 * sin(2.0 * M_PI * xc(B, 1, j));
+            U(IB2) = B0 * sin(4.0 * M_PI * xc(B, 0, i));
+            U(IB3) = 0.0;
+            U(IEN) = p0 / gm1 + 0.5 * (SQR(U(IB1)) + SQR(U(IB2)) + SQR(U(IB3)) +
+                                       (SQR(U(IM1)) + SQR(U(IM2)) + SQR(U(IM3))) / U(IDN));
+          } break;
+          case APKO_PGEN_UNIFORM: { /* src/pgen/turbulence.cpp:241-356 with zero velocity;
+                                       pars = rho0, p0, b0 */
+            double rho0 = npars > 0 ? pars[0] : 1.0, p0 = npars > 1 ? pars[1] : 1.0;
+            double b0 = npars > 2 ? pars[2] : 0.01;
+            U(IDN) = rho0;
+            U(IEN) = p0 / gm1 + 0.5 * rho0 * (SQR(0.0) + SQR(0.0) + SQR(0.0));
+            if (mhd) {
+              U(IB1) = b0;
+              U(IEN) += 0.5 * b0 * b0;
+            }
+          } break;
+          case APKO_PGEN_OT3D: { /* closed-form 3-D Orszag-Tang-like */
+            double B0 = 1.0 / sqrt(4.0 * M_PI);
+            double d0 = 25.0 / (36.0 * M_PI);
+            double p0 = 5.0 / (12.0 * M_PI);
+            double x = xc(B, 0, i), y = xc(B, 1, j), z = xc(B, 2, k);
+            double v1 = sin(2.0 * M_PI * y), v2 = -sin(2.0 * M_PI * x), v3 = 0.2 * sin(2.0 * M_PI * z);
+            U(IDN) = d0;
+            U(IM1) = d0 * v1;
+            U(IM2) = d0 * v2;
+            U(IM3) = d0 * v3;
+            double eb = 0.0;
+            if (mhd) {
+              U(IB1) = B0 * sin(2.0 * M_PI * y);
+              U(IB2) = B0 * sin(4.0 * M_PI * x);
+              U(IB3) = B0 * 0.2 * sin(2.0 * M_PI * x);
+              eb = 0.5 * (SQR(U(IB1)) + SQR(U(IB2)) + SQR(U(IB3)));
+            }
+            U(IEN) = p0 / gm1 + 0.5 * d0 * (SQR(v1) + SQR(v2) + SQR(v3)) + eb;
+          } break;
+          case APKO_PGEN_BLAST: { /* src/pgen/blast.cpp (spherical over-pressure; B=0);
+                                     pars = radius, pamb, prat, damb */
+            double rad = npars > 0 ? pars[0] : 0.1, pa = npars > 1 ? pars[1] : 0.1;
+            double prat = npars > 2 ? pars[2] : 100.0, da = npars > 3 ? pars[3] : 1.0;
+            double x = xc(B, 0, i), y = (e->ndim > 1) ? xc(B, 1, j) : 0.0,
+                   z = (e->ndim > 2) ? xc(B, 2, k) : 0.0;
+            double r = sqrt(SQR(x) + SQR(y) + SQR(z));
+            U(IDN) = da;
+            U(IEN) = ((r < rad) ? prat * pa : pa) / gm1;
+          } break;
+          case APKO_PGEN_RANDOM: { /* synthetic smooth-ish random state; pars = seed, amplitude */
+            uint64_t seed = npars > 0 ? (uint64_t)pars[0] : 1;
+            double amp = npars > 1 ? pars[1] : 0.2;
+            uint64_t gi = (uint64_t)(B->loc[0] * p->mb[0] + (i - e->is[0]));
+            uint64_t gj = (uint64_t)(B->loc[1] * p->mb[1] + (j - e->is[1]));
+            uint64_t gk = (uint64_t)(B->loc[2] * p->mb[2] + (k - e->is[2]));
+            uint64_t cell = (gk * (uint64_t)p->nx[1] + gj) * (uint64_t)p->nx[0] + gi;
+            double r[8];
+            for (int q = 0; q < 8; ++q) r[q] = 2.0 * hash01(seed * 1315423911ULL + cell * 8 + q) - 1.0;
+            double d = 1.0 + amp * r[0], pr = 1.0 + amp * r[1];
+            double v1 = amp * r[2], v2 = amp * r[3], v3 = amp * r[4];
+            U(IDN) = d;
+            U(IM1) = d * v1;
+            U(IM2) = d * v2;
+            U(IM3) = d * v3;
+            double eb = 0.0;
+            if (mhd) {
+              U(IB1) = 0.5 + amp * r[5];
+              U(IB2) = 0.3 + amp * r[6];
+              U(IB3) = -0.2 + amp * r[7];
+              eb = 0.5 * (SQR(U(IB1)) + SQR(U(IB2)) + SQR(U(IB3)));
+            }
+            U(IEN) = pr / gm1 + 0.5 * d * (SQR(v1) + SQR(v2) + SQR(v3)) + eb;
+          } break;
+          default:
+            return -1;
+          }
+          for (int n = e->nhydro; n < e->nvar; ++n)
+            U(n) = U(IDN) * (0.25 + 0.5 * ((i + j + k + n) % 2));
+#undef U
+        }
+  }
+  return 0;
+}
+
+/* linear_wave::UserWorkAfterLoop, src/pgen/linear_wave.cpp:183-295 */
+void apko_linear_wave_errors(apko_engine *e, double *out) {
+  double l1[5] = {0, 0, 0, 0, 0};
+  for (int b = 0; b < e->nblocks; ++b) {
+    const block_t *B = &e->blk[b];
+    const double vol = B->dx[0] * B->dx[1] * B->dx[2];
+    for (int k = e->is[2]; k <= e->ie[2]; ++k)
+      for (int j = e->is[1]; j <= e->ie[1]; ++j)
+        for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+          double u[5];
+          lw_state(e, B, k, j, i, u);
+          for (int n = 0; n < 5; ++n) l1[n] += fabs(u[n] - B->cons[IDX(e, n, k, j, i)]) * vol;
+        }
+  }
+  const double vol = (e->p.xmax[0] - e->p.xmin[0]) * (e->p.xmax[1] - e->p.xmin[1]) *
+                     (e->p.xmax[2] - e->p.xmin[2]);
+  double rms = 0.0;
+  for (int n = 0; n < 5; ++n) {
+    l1[n] = l1[n] / vol;
+    rms += SQR(l1[n]);
+    out[1 + n] = l1[n];
+  }
+  out[0] = sqrt(rms);
+}
+
+/* HydroHst, src/hydro/hydro.cpp:145-208 */
+void apko_history(apko_engine *e, double *out) {
+  for (int q = 0; q < 8; ++q) out[q] = 0.0;
+  const int mhd = (e->p.fluid == APKO_FLUID_GLMMHD);
+  for (int b = 0; b < e->nblocks; ++b) {
+    const block_t *B = &e->blk[b];
+    const double vol = B->dx[0] * B->dx[1] * B->dx[2];
+    for (int k = e->is[2]; k <= e->ie[2]; ++k)
+      for (int j = e->is[1]; j <= e->ie[1]; ++j)
+        for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+#define C(n, kk, jj, ii) B->cons[IDX(e, n, kk, jj, ii)]
+          out[0] += C(IDN, k, j, i) * vol;
+          out[1] += C(IM1, k, j, i) * vol;
+          out[2] += C(IM2, k, j, i) * vol;
+          out[3] += C(IM3, k, j, i) * vol;
+          out[4] += 0.5 / C(IDN, k, j, i) *
+                    (SQR(C(IM1, k, j, i)) + SQR(C(IM2, k, j, i)) + SQR(C(IM3, k, j, i))) * vol;
+          out[5] += C(IEN, k, j, i) * vol;
+          if (mhd && e->ndim >= 2) {
+            out[6] += 0.5 * (SQR(C(IB1, k, j, i)) + SQR(C(IB2, k, j, i)) + SQR(C(IB3, k, j, i))) * vol;
+            double divb = (C(IB1, k, j, i + 1) - C(IB1, k, j, i - 1)) / B->dx[0] +
+                          (C(IB2, k, j + 1, i) - C(IB2, k, j - 1, i)) / B->dx[1];
+            if (e->ndim == 3) divb += (C(IB3, k + 1, j, i) - C(IB3, k - 1, j, i)) / B->dx[2];
+            double abs_b = sqrt(SQR(C(IB1, k, j, i)) + SQR(C(IB2, k, j, i)) + SQR(C(IB3, k, j, i)));
+            out[7] += (abs_b != 0)
+                          ? 0.5 * (sqrt(SQR(B->dx[0]) + SQR(B->dx[1]) + SQR(B->dx[2]))) *
+                                fabs(divb) / abs_b * vol
+                          : 0;
+          }
+#undef C
+        }
+  }
+}

@@ -1,0 +1,105 @@
+/* apk_oracle.h -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * Plain-C, fp64, no-FMA restatement of AthenaPK's per-stage hot path
+ * (reconstruct -> Riemann -> flux divergence -> Dedner GLM source -> cons2prim, plus the
+ * same-level ghost exchange, physical BCs and the dt/c_h logic of the driver) for uniform
+ * (non-AMR) meshes.  Every function cites the reference file:line it restates
+ * (paths relative to /root/reference).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library.  The product (athenapk_b200/) never links or calls it.
+ *
+ * Parity pinning: see oracle/README.md -- pinned against (a) the reference's own scalar
+ * kernels compiled from /root/reference headers (oracle/_ref), (b) the reference's golden
+ * linear-wave error 1.547584e-08 (tst/regression/test_suites/convergence/convergence.py:163)
+ * and (c) reference-run scalars recorded in SURVEY.md section 8(c).
+ */
+#ifndef APK_ORACLE_H_
+#define APK_ORACLE_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* enums mirror src/main.hpp:19-50 (values are our own) */
+enum { APKO_FLUID_EULER = 0, APKO_FLUID_GLMMHD = 1 };
+enum { APKO_RECON_DC = 0, APKO_RECON_PLM, APKO_RECON_PPM, APKO_RECON_WENOZ, APKO_RECON_WENO3,
+       APKO_RECON_LIMO3 };
+enum { APKO_RS_NONE = 0, APKO_RS_HLLE, APKO_RS_LLF, APKO_RS_HLLC, APKO_RS_HLLD };
+enum { APKO_INT_RK1 = 0, APKO_INT_RK2, APKO_INT_VL2, APKO_INT_RK3 };
+enum { APKO_BC_PERIODIC = 0, APKO_BC_OUTFLOW = 1, APKO_BC_REFLECT = 2 };
+enum { APKO_PGEN_LINEAR_WAVE = 0, APKO_PGEN_SOD, APKO_PGEN_ORSZAG_TANG, APKO_PGEN_UNIFORM,
+       APKO_PGEN_OT3D, APKO_PGEN_BLAST, APKO_PGEN_RANDOM };
+
+typedef struct {
+  int fluid, recon, riemann, integrator;
+  int nx[3];        /* mesh cells per direction (1 => symmetry direction) */
+  int mb[3];        /* meshblock cells per direction */
+  int ng;           /* ghost cells */
+  int bc[6];        /* ix1, ox1, ix2, ox2, ix3, ox3 */
+  double xmin[3], xmax[3];
+  double gamma, cfl;
+  double dfloor, pfloor, efloor, vceil, eceil; /* <=0 / +inf disable (hydro.cpp:507-537) */
+  int fofc;            /* hydro/first_order_flux_correct */
+  int fofc_jacobi;     /* 0: reference serial sweep order; 1: Jacobi (GPU-deterministic) */
+  int dedner_extended; /* hydro/glmmhd_source = dedner_extended */
+  double glmmhd_alpha;
+  int nscalars;
+} apko_params;
+
+typedef struct apko_engine apko_engine;
+
+void apko_default_params(apko_params *p);
+apko_engine *apko_create(const apko_params *p);
+void apko_destroy(apko_engine *e);
+
+/* problem generators (src/pgen/*.cpp); pars meaning depends on id, see apk_oracle.c */
+int apko_pgen(apko_engine *e, int id, const double *pars, int npars);
+/* finish initialisation: ghost exchange + BCs + cons2prim + first dt (Mesh::Initialize,
+ * EvolutionDriver::InitializeBlockTimeSteps + SetGlobalTimeStep) */
+void apko_initialize(apko_engine *e, double tlim);
+/* run until tlim / nlim reached; returns number of cycles taken in this call */
+int apko_run(apko_engine *e, double tlim, int nlim);
+/* single cycle (all stages + dt) */
+void apko_cycle(apko_engine *e);
+
+int apko_num_blocks(const apko_engine *e);
+void apko_block_dims(const apko_engine *e, int *n /*[3] incl ghosts: n1,n2,n3*/);
+int apko_nvar(const apko_engine *e);
+double *apko_cons(apko_engine *e, int b);
+double *apko_prim(apko_engine *e, int b);
+double *apko_flux(apko_engine *e, int b, int dir);
+void apko_block_coords(const apko_engine *e, int b, double *xmin3, double *dx3);
+double apko_time(const apko_engine *e);
+double apko_dt(const apko_engine *e);
+int apko_ncycle(const apko_engine *e);
+double apko_c_h(const apko_engine *e);
+double apko_lw_tlim(const apko_engine *e); /* linear-wave "test=true" tlim (one period) */
+/* linear_wave::UserWorkAfterLoop L1 errors: out[0]=rms, out[1..5]=l1 per var */
+void apko_linear_wave_errors(apko_engine *e, double *out);
+/* history sums (hydro.cpp:145-208): mass, m1, m2, m3, KE, E, ME, relDivB */
+void apko_history(apko_engine *e, double *out8);
+
+/* individual tasks, same order/semantics as hydro_driver.cpp:499-613 */
+void apko_calc_fluxes(apko_engine *e, int recon);                       /* hydro.cpp:1025-1208 */
+long long apko_fofc(apko_engine *e, double g0, double g1, double bdt);  /* hydro.cpp:1223-1342 */
+void apko_flux_div_update(apko_engine *e, double g0, double g1, double bdt);
+void apko_dedner(apko_engine *e, double bdt);
+void apko_exchange(apko_engine *e);
+void apko_cons_to_prim(apko_engine *e);
+double apko_estimate_dt(apko_engine *e);
+void apko_save_u1(apko_engine *e);
+void apko_set_c_h(apko_engine *e, double c_h);
+
+/* scalar building blocks for unit parity tests */
+void apko_recon_scalar(int recon, const double q[5], double dx, int positivity, double *ql_ip1,
+                       double *qr_i);
+void apko_riemann_face(int fluid, int solver, int ivx, const double *wl, const double *wr,
+                       double gamma, double c_h, double *flux);
+void apko_c2p_cell(int fluid, int nscalars, double *u, double *w, double gamma, double dfloor,
+                   double pfloor, double efloor, double vceil, double eceil);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,224 @@
+"""ctypes binding of the CPU oracle (oracle/libapk_oracle.so) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+
+FLUID = {"euler": 0, "glmmhd": 1}
+RECON = {"dc": 0, "plm": 1, "ppm": 2, "wenoz": 3, "weno3": 4, "limo3": 5}
+RIEMANN = {"none": 0, "hlle": 1, "llf": 2, "hllc": 3, "hlld": 4}
+INTEGRATOR = {"rk1": 0, "rk2": 1, "vl2": 2, "rk3": 3}
+BC = {"periodic": 0, "outflow": 1, "reflecting": 2}
+PGEN = {"linear_wave": 0, "sod": 1, "orszag_tang": 2, "uniform": 3, "ot3d": 4, "blast": 5,
+        "random": 6}
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("fluid", C.c_int), ("recon", C.c_int), ("riemann", C.c_int), ("integrator", C.c_int),
+        ("nx", C.c_int * 3), ("mb", C.c_int * 3), ("ng", C.c_int), ("bc", C.c_int * 6),
+        ("xmin", C.c_double * 3), ("xmax", C.c_double * 3),
+        ("gamma", C.c_double), ("cfl", C.c_double),
+        ("dfloor", C.c_double), ("pfloor", C.c_double), ("efloor", C.c_double),
+        ("vceil", C.c_double), ("eceil", C.c_double),
+        ("fofc", C.c_int), ("fofc_jacobi", C.c_int), ("dedner_extended", C.c_int),
+        ("glmmhd_alpha", C.c_double), ("nscalars", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "libapk_oracle.so"])
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = os.path.join(ORACLE_DIR, "libapk_oracle.so")
+    src = os.path.join(ORACLE_DIR, "apk_oracle.c")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        build()
+    L = C.CDLL(path)
+    dp = C.POINTER(C.c_double)
+    L.apko_default_params.argtypes = [C.POINTER(Params)]
+    L.apko_create.argtypes = [C.POINTER(Params)]
+    L.apko_create.restype = C.c_void_p
+    L.apko_destroy.argtypes = [C.c_void_p]
+    L.apko_pgen.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
+    L.apko_initialize.argtypes = [C.c_void_p, C.c_double]
+    L.apko_run.argtypes = [C.c_void_p, C.c_double, C.c_int]
+    L.apko_cycle.argtypes = [C.c_void_p]
+    L.apko_num_blocks.argtypes = [C.c_void_p]
+    L.apko_block_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.apko_nvar.argtypes = [C.c_void_p]
+    for f in ("apko_cons", "apko_prim"):
+        getattr(L, f).argtypes = [C.c_void_p, C.c_int]
+        getattr(L, f).restype = dp
+    L.apko_flux.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.apko_flux.restype = dp
+    L.apko_block_coords.argtypes = [C.c_void_p, C.c_int, dp, dp]
+    for f in ("apko_time", "apko_dt", "apko_c_h", "apko_lw_tlim", "apko_estimate_dt"):
+        getattr(L, f).argtypes = [C.c_void_p]
+        getattr(L, f).restype = C.c_double
+    L.apko_ncycle.argtypes = [C.c_void_p]
+    L.apko_linear_wave_errors.argtypes = [C.c_void_p, dp]
+    L.apko_history.argtypes = [C.c_void_p, dp]
+    L.apko_calc_fluxes.argtypes = [C.c_void_p, C.c_int]
+    L.apko_fofc.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+    L.apko_fofc.restype = C.c_longlong
+    L.apko_flux_div_update.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+    L.apko_dedner.argtypes = [C.c_void_p, C.c_double]
+    L.apko_exchange.argtypes = [C.c_void_p]
+    L.apko_cons_to_prim.argtypes = [C.c_void_p]
+    L.apko_save_u1.argtypes = [C.c_void_p]
+    L.apko_set_c_h.argtypes = [C.c_void_p, C.c_double]
+    L.apko_recon_scalar.argtypes = [C.c_int, dp, C.c_double, C.c_int, dp, dp]
+    L.apko_riemann_face.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, C.c_double, dp]
+    L.apko_c2p_cell.argtypes = [C.c_int, C.c_int, dp, dp] + [C.c_double] * 6
+    _lib = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def make_params(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx=(64, 32, 32),
+                mb=None, ng=2, bc="periodic", xmin=(0.0, 0.0, 0.0), xmax=(3.0, 1.5, 1.5),
+                gamma=5.0 / 3.0, cfl=0.3, fofc=False, fofc_jacobi=False, dedner_extended=False,
+                glmmhd_alpha=0.1, nscalars=0, dfloor=-1.0, pfloor=-1.0, efloor=-1.0,
+                vceil=float("inf"), eceil=float("inf")):
+    p = Params()
+    lib().apko_default_params(C.byref(p))
+    p.fluid, p.recon, p.riemann = FLUID[fluid], RECON[recon], RIEMANN[riemann]
+    p.integrator = INTEGRATOR[integrator]
+    mb = mb or nx
+    for d in range(3):
+        p.nx[d], p.mb[d] = nx[d], mb[d]
+        p.xmin[d], p.xmax[d] = xmin[d], xmax[d]
+    p.ng = ng
+    bcs = [bc] * 6 if isinstance(bc, str) else list(bc)
+    for f in range(6):
+        p.bc[f] = BC[bcs[f]]
+    p.gamma, p.cfl = gamma, cfl
+    p.fofc, p.fofc_jacobi, p.dedner_extended = int(fofc), int(fofc_jacobi), int(dedner_extended)
+    p.glmmhd_alpha, p.nscalars = glmmhd_alpha, nscalars
+    p.dfloor, p.pfloor, p.efloor, p.vceil, p.eceil = dfloor, pfloor, efloor, vceil, eceil
+    return p
+
+
+class Oracle:
+    """Thin object wrapper around an apko_engine."""
+
+    def __init__(self, **kw):
+        self.L = lib()
+        self.p = make_params(**kw)
+        self.h = self.L.apko_create(C.byref(self.p))
+        if not self.h:
+            raise ValueError("apko_create failed (mesh not divisible by meshblock?)")
+        n = (C.c_int * 3)()
+        self.L.apko_block_dims(self.h, n)
+        self.n = tuple(n)  # (n1, n2, n3)
+        self.nvar = self.L.apko_nvar(self.h)
+        self.nblocks = self.L.apko_num_blocks(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.apko_destroy(self.h)
+            self.h = None
+
+    def pgen(self, name, pars=()):
+        a = np.asarray(pars, dtype=np.float64)
+        rc = self.L.apko_pgen(self.h, PGEN[name], _dp(a) if a.size else None, a.size)
+        if rc != 0:
+            raise ValueError("pgen failed")
+
+    def initialize(self, tlim=float("inf")):
+        self.L.apko_initialize(self.h, 1.0e300 if tlim == float("inf") else tlim)
+
+    def run(self, tlim=None, nlim=-1):
+        t = self.L.apko_time(self.h) + 1e300 if tlim is None else tlim
+        return self.L.apko_run(self.h, t, nlim)
+
+    def cycle(self):
+        self.L.apko_cycle(self.h)
+
+    def _arr(self, ptr):
+        shape = (self.nvar, self.n[2], self.n[1], self.n[0])
+        return np.ctypeslib.as_array(ptr, shape=shape)
+
+    def cons(self, b):
+        return self._arr(self.L.apko_cons(self.h, b))
+
+    def prim(self, b):
+        return self._arr(self.L.apko_prim(self.h, b))
+
+    def flux(self, b, d):
+        return self._arr(self.L.apko_flux(self.h, b, d))
+
+    def all_cons(self):
+        return np.stack([self.cons(b).copy() for b in range(self.nblocks)])
+
+    def all_prim(self):
+        return np.stack([self.prim(b).copy() for b in range(self.nblocks)])
+
+    def set_cons(self, arr):
+        for b in range(self.nblocks):
+            self.cons(b)[...] = arr[b]
+
+    @property
+    def time(self):
+        return self.L.apko_time(self.h)
+
+    @property
+    def dt(self):
+        return self.L.apko_dt(self.h)
+
+    @property
+    def ncycle(self):
+        return self.L.apko_ncycle(self.h)
+
+    @property
+    def c_h(self):
+        return self.L.apko_c_h(self.h)
+
+    @property
+    def lw_tlim(self):
+        return self.L.apko_lw_tlim(self.h)
+
+    def linear_wave_errors(self):
+        out = np.zeros(6)
+        self.L.apko_linear_wave_errors(self.h, _dp(out))
+        return out
+
+    def history(self):
+        out = np.zeros(8)
+        self.L.apko_history(self.h, _dp(out))
+        return out
+
+
+def recon_scalar(kind, q, dx=1.0, positivity=False):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    ql, qr = C.c_double(), C.c_double()
+    lib().apko_recon_scalar(RECON[kind], _dp(q), dx, int(positivity), C.byref(ql), C.byref(qr))
+    return ql.value, qr.value
+
+
+def riemann_face(fluid, solver, ivx, wl, wr, gamma, c_h=1.0):
+    wl = np.ascontiguousarray(wl, dtype=np.float64)
+    wr = np.ascontiguousarray(wr, dtype=np.float64)
+    out = np.zeros(9 if fluid == "glmmhd" else 5)
+    lib().apko_riemann_face(FLUID[fluid], RIEMANN[solver], ivx, _dp(wl), _dp(wr), gamma, c_h,
+                            _dp(out))
+    return out
