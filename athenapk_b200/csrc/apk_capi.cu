@@ -1,0 +1,199 @@
+// apk_capi.cu -- the C-ABI of include/apk_b200.h: argument checks, FP-mode dispatch and the
+// few host-side pieces the reference also keeps on the host (exp() of the Dedner coefficient,
+// the blocking reductions of dt and of the FOFC correction count).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "apk_launch.h"
+
+namespace {
+inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int check(const apk_pack_desc_t *d, const void *blocks, const char *who) {
+  if (!d || !blocks) {
+    apk_common::set_error("null descriptor or block array");
+    return 1;
+  }
+  const int nh = (d->fluid == APK_FLUID_GLMMHD) ? 9 : 5;
+  if (d->nblocks <= 0 || d->ndim < 1 || d->ndim > 3 || d->nvar != nh + d->nscalars ||
+      d->nscalars < 0 || d->ng < 1 || d->nx[0] < 1 ||
+      (d->fluid != APK_FLUID_EULER && d->fluid != APK_FLUID_GLMMHD) ||
+      (d->fp_mode != APK_FP_FAST && d->fp_mode != APK_FP_STRICT)) {
+    apk_common::set_error(who);
+    return 1;
+  }
+  return 0;
+}
+
+int cuda_ok(const char *who) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    static thread_local char buf[256];
+    snprintf(buf, sizeof(buf), "%s: %s", who, cudaGetErrorString(e));
+    apk_common::set_error(buf);
+    return 2;
+  }
+  return 0;
+}
+}  // namespace
+
+#define DISPATCH(d, call) ((d)->fp_mode == APK_FP_STRICT ? apk_strict::call : apk_fast::call)
+
+extern "C" {
+
+const char *apk_last_error(void) { return apk_common::last_error(); }
+int apk_abi_version(void) { return APK_ABI_VERSION; }
+long long apk_launch_count(void) { return apk_common::launches(); }
+void apk_reset_launch_count(void) { apk_common::reset_launches(); }
+
+int apk_calc_fluxes(const apk_pack_desc_t *d, const apk_block_t *blocks, double c_h,
+                    int recon_override, void *stream) {
+  if (check(d, blocks, "apk_calc_fluxes: bad descriptor")) return 1;
+  int rc = DISPATCH(d, launch_calc_fluxes(*d, blocks, c_h, recon_override, S(stream)));
+  return rc ? rc : cuda_ok("apk_calc_fluxes");
+}
+
+size_t apk_fofc_workspace_bytes(const apk_pack_desc_t *d) {
+  const ApkGeom g = apk_make_geom(*d);
+  return (size_t)g.ncell * g.nb + 16;
+}
+
+int apk_first_order_flux_correct(const apk_pack_desc_t *d, const apk_block_t *blocks,
+                                 double gam0, double gam1, double beta_dt, double c_h,
+                                 void *d_work, long long *n_corrected, void *stream) {
+  if (check(d, blocks, "apk_first_order_flux_correct: bad descriptor")) return 1;
+  if (!d_work) {
+    apk_common::set_error("apk_first_order_flux_correct: null workspace");
+    return 1;
+  }
+  const ApkGeom g = apk_make_geom(*d);
+  // workspace: [counter (16 B)] [flags: nb*ncell bytes]
+  unsigned long long *counter = reinterpret_cast<unsigned long long *>(d_work);
+  unsigned char *flags = reinterpret_cast<unsigned char *>(d_work) + 16;
+  long long total = 0;
+  int attempts = 0;
+  unsigned long long num_corrected = 0;
+  do {  // hydro.cpp:1263-1339
+    cudaMemsetAsync(d_work, 0, (size_t)g.ncell * g.nb + 16, S(stream));
+    DISPATCH(d, launch_fofc_flag(*d, blocks, gam0, gam1, beta_dt, attempts, flags, counter, S(stream)));
+    cudaMemcpyAsync(&num_corrected, counter, sizeof(num_corrected), cudaMemcpyDeviceToHost,
+                    S(stream));
+    cudaStreamSynchronize(S(stream));
+    if (num_corrected > 0) DISPATCH(d, launch_fofc_fix(*d, blocks, c_h, flags, S(stream)));
+    total += (long long)num_corrected;
+    attempts += 1;
+  } while (num_corrected > 0 && attempts < 4);
+  if (n_corrected) *n_corrected = total;
+  return cuda_ok("apk_first_order_flux_correct");
+}
+
+int apk_flux_div_update(const apk_pack_desc_t *d, const apk_block_t *blocks, double gam0,
+                        double gam1, double beta_dt, void *stream) {
+  if (check(d, blocks, "apk_flux_div_update: bad descriptor")) return 1;
+  DISPATCH(d, launch_flux_div_update(*d, blocks, gam0, gam1, beta_dt, S(stream)));
+  return cuda_ok("apk_flux_div_update");
+}
+
+int apk_dedner_source(const apk_pack_desc_t *d, const apk_block_t *blocks, double c_h,
+                      double mindx, double alpha, double beta_dt, int extended, void *stream) {
+  if (check(d, blocks, "apk_dedner_source: bad descriptor")) return 1;
+  if (d->fluid != APK_FLUID_GLMMHD) return 0;
+  // dedner_source.cpp:34 (host std::exp, like the reference)
+  const double coeff = std::exp(-alpha * c_h * beta_dt / mindx);
+  DISPATCH(d, launch_dedner(*d, blocks, coeff, beta_dt, extended, S(stream)));
+  return cuda_ok("apk_dedner_source");
+}
+
+int apk_cons_to_prim(const apk_pack_desc_t *d, const apk_block_t *blocks, int *d_status,
+                     void *stream) {
+  if (check(d, blocks, "apk_cons_to_prim: bad descriptor")) return 1;
+  DISPATCH(d, launch_cons_to_prim(*d, blocks, d_status, S(stream)));
+  return cuda_ok("apk_cons_to_prim");
+}
+
+int apk_min_dt_async(const apk_pack_desc_t *d, const apk_block_t *blocks, double *d_out,
+                     void *stream) {
+  if (check(d, blocks, "apk_min_dt: bad descriptor")) return 1;
+  DISPATCH(d, launch_min_dt(*d, blocks, d_out, S(stream)));
+  return cuda_ok("apk_min_dt");
+}
+
+int apk_min_dt(const apk_pack_desc_t *d, const apk_block_t *blocks, double cfl, void *d_work,
+               double *h_dt, void *stream) {
+  int rc = apk_min_dt_async(d, blocks, reinterpret_cast<double *>(d_work), stream);
+  if (rc) return rc;
+  double m = 0.0;
+  cudaMemcpyAsync(&m, d_work, sizeof(double), cudaMemcpyDeviceToHost, S(stream));
+  cudaStreamSynchronize(S(stream));
+  *h_dt = cfl * m;  // hydro.cpp:909
+  return cuda_ok("apk_min_dt");
+}
+
+int apk_copy_ghosts_local(const apk_pack_desc_t *d, const apk_block_t *blocks, int with_prim,
+                          void *stream) {
+  if (check(d, blocks, "apk_copy_ghosts_local: bad descriptor")) return 1;
+  apk_common::launch_fill_ghosts(*d, blocks, with_prim, S(stream));
+  return cuda_ok("apk_copy_ghosts_local");
+}
+
+int apk_apply_physical_bcs(const apk_pack_desc_t *d, const apk_block_t *blocks,
+                           unsigned bc_face_mask, int with_prim, void *stream) {
+  if (check(d, blocks, "apk_apply_physical_bcs: bad descriptor")) return 1;
+  apk_common::launch_physical_bcs(*d, blocks, bc_face_mask, with_prim, S(stream));
+  return cuda_ok("apk_apply_physical_bcs");
+}
+
+int apk_fill_ghosts_local(const apk_pack_desc_t *d, const apk_block_t *blocks,
+                          unsigned bc_face_mask, int with_prim, void *stream) {
+  int rc = apk_copy_ghosts_local(d, blocks, with_prim, stream);
+  if (rc) return rc;
+  return apk_apply_physical_bcs(d, blocks, bc_face_mask, with_prim, stream);
+}
+
+int apk_halo_pack(const apk_pack_desc_t *d, const apk_block_t *blocks,
+                  const apk_halo_item_t *items, int nitems, int with_prim, double *buf,
+                  void *stream) {
+  if (check(d, blocks, "apk_halo_pack: bad descriptor")) return 1;
+  apk_common::launch_halo_pack(*d, blocks, items, nitems, with_prim, buf, S(stream));
+  return cuda_ok("apk_halo_pack");
+}
+
+int apk_halo_unpack(const apk_pack_desc_t *d, const apk_block_t *blocks,
+                    const apk_halo_item_t *items, int nitems, int with_prim, const double *buf,
+                    void *stream) {
+  if (check(d, blocks, "apk_halo_unpack: bad descriptor")) return 1;
+  apk_common::launch_halo_unpack(*d, blocks, items, nitems, with_prim, buf, S(stream));
+  return cuda_ok("apk_halo_unpack");
+}
+
+int apk_stage_fused(const apk_pack_desc_t *d, const apk_block_t *blocks,
+                    double *const *d_prim_out, double gam0, double gam1, double beta_dt,
+                    double c_h, double mindx, double alpha, int recon_override, double *d_dtmin,
+                    void *stream) {
+  if (check(d, blocks, "apk_stage_fused: bad descriptor")) return 1;
+  if (!d_prim_out) {
+    apk_common::set_error("apk_stage_fused: null prim_out");
+    return 1;
+  }
+  const double coeff =
+      (d->fluid == APK_FLUID_GLMMHD) ? std::exp(-alpha * c_h * beta_dt / mindx) : 1.0;
+  int rc = DISPATCH(d, launch_stage_fused(*d, blocks, d_prim_out, gam0, gam1, beta_dt, c_h, coeff,
+                                          recon_override, d_dtmin, S(stream)));
+  return rc ? rc : cuda_ok("apk_stage_fused");
+}
+
+int apk_save_u1(const apk_pack_desc_t *d, const apk_block_t *blocks, void *stream) {
+  if (check(d, blocks, "apk_save_u1: bad descriptor")) return 1;
+  apk_common::launch_save_u1(*d, blocks, S(stream));
+  return cuda_ok("apk_save_u1");
+}
+
+int apk_fp64_probe(int n_blocks, int n_threads, int n_iter, double *d_out, double *flops,
+                   void *stream) {
+  apk_common::launch_fp64_probe(n_blocks, n_threads, n_iter, d_out, S(stream));
+  if (flops) *flops = 2.0 * 8.0 * (double)n_iter * (double)n_blocks * (double)n_threads;
+  return cuda_ok("apk_fp64_probe");
+}
+
+}  // extern "C"

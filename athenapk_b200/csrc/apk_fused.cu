@@ -1,0 +1,339 @@
+// apk_fused.cu -- the fused stage kernel: reconstruct -> Riemann -> flux divergence -> low-storage
+// update -> Dedner damping -> cons->prim (+ dt reduction) in ONE pass over the pack, without
+// materialising cons.flux (replaces K1-K3, K6, K7, K10 and K11 of SURVEY.md 2.3).
+//
+// Work decomposition (B200: 148 SMs, 1 CTA of 9 warps per SM, <=224 regs/thread for HLLD):
+//  * a CTA owns a TX x TY = 32 x 8 column of one meshblock and MARCHES along x3.  x3-reconstruction
+//    of plane k yields the right state of face k and the left state of face k+1, so every x3 face
+//    is reconstructed and solved exactly once (no redundant work along the march); x1/x2 faces of
+//    a plane are solved inside the plane tile (33/32 and 9/8 faces per cell).
+//  * per plane three phases separated by __syncthreads():
+//      recon   : warp tasks (variable, row) -> 32 lanes along x1 (coalesced 256 B rows); L/R
+//                states go to shared memory in sweep-local slot order,
+//      riemann : warp tasks (direction, face row); the flux overwrites the L state in place,
+//      finalize: one thread per cell; the x1+x2 divergence and the lower x3 flux stay in
+//                REGISTERS across the march, the cell is finished one plane later when its upper
+//                x3 flux exists; association order of the reference's FluxDivHelper is kept.
+//  * 288 threads: 264 x1-faces + 288 x2-faces + 256 x3-faces = 26 warp tasks on 9 warps.
+// Compiled twice (APK_NS = apk_fast / apk_strict), see apk_launch.h.
+#include <cstdint>
+
+#include "apk_launch.h"
+#include "apk_math.cuh"
+
+namespace APK_NS {
+namespace {
+
+constexpr int TX = 32, TY = 8, NWARPS = 9, NTHREADS = NWARPS * 32;
+
+APK_DEV constexpr int slot_of_var(int v, int dir) {
+  // inverse of var_of_slot(): sweep-local slot that holds memory variable v
+  if (v >= 1 && v <= 3) return 1 + (v - 1 - dir + 3) % 3;
+  if (v >= 5 && v <= 7) return 5 + (v - 5 - dir + 3) % 3;
+  return v;
+}
+
+template <int NH>
+struct Smem {
+  double wlx[NH][TY][TX + 1], wrx[NH][TY][TX + 1];
+  double wly[NH][TY + 1][TX], wry[NH][TY + 1][TX];
+  double wrz[NH][TY][TX], wlz[2][NH][TY][TX];
+};
+
+template <int FLUID, int RECON, int RS, int NDIM>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *__restrict__ prim_out,
+              double g0, double g1, double bdt, double gamma, double c_h, double dedner_coeff,
+              EosPars eos, int ntx, unsigned long long *dtmin) {
+  constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<NH> &sm = *reinterpret_cast<Smem<NH> *>(smem_raw);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const apk_block_t &B = blocks[blockIdx.y];
+  const int tix = blockIdx.x % ntx, tiy = blockIdx.x / ntx;
+  const int i0 = g.is + tix * TX, j0 = g.js + tiy * TY;
+  const int txe = min(TX, g.ie + 1 - i0);                      // valid cells of the tile in x1
+  const int tye = (NDIM >= 2) ? min(TY, g.je + 1 - j0) : 1;    // ... in x2
+  const long sj = g.n1, sk = (long)g.n1 * g.n2;
+  const double *__restrict__ prim = B.prim;
+  const double dx1 = B.dx[0], dx2 = B.dx[1], dx3 = B.dx[2];
+  // uniform_coordinates.hpp:37-40
+  const double a1 = dx2 * dx3, a2 = dx1 * dx3, a3 = dx1 * dx2, vol = dx1 * dx2 * dx3;
+
+  // finalize-phase ownership: thread -> cell (cj, ci) of the tile
+  const int ci = threadIdx.x & 31, cj = threadIdx.x >> 5;
+  const bool owner = (threadIdx.x < TX * TY) && ci < txe && cj < tye;
+  double du[NH], fzlo[NH];
+#pragma unroll
+  for (int v = 0; v < NH; ++v) du[v] = fzlo[v] = 0.0;
+  double my_min = DBL_MAX;
+
+  const int kfirst = (NDIM == 3) ? g.ks - 1 : g.ks;
+  const int klast = (NDIM == 3) ? g.ke + 1 : g.ke;
+  int cur = 0;
+  for (int kp = kfirst; kp <= klast; ++kp) {
+    const bool inplane = (kp >= g.ks && kp <= g.ke);
+    // ------------------------------------------------------------------ recon phase
+    if (NDIM == 3) {
+      for (int t = warp; t < NH * TY; t += NWARPS) {
+        const int n = t / TY, j = t % TY;
+        if (j < tye && lane < txe) {
+          const double *q = prim + (long)var_of_slot(n, 2) * g.ncell + (long)kp * sk +
+                            (long)(j0 + j) * sj + (i0 + lane);
+          double ql, qr;
+          recon_cell<RECON>(q, sk, dx3, (n == 0 || n == 4), ql, qr);
+          sm.wrz[n][j][lane] = qr;
+          sm.wlz[cur ^ 1][n][j][lane] = ql;
+        }
+      }
+    }
+    if (inplane) {
+      // x1: cells 0..txe-1 of each row, ql -> face c+1, qr -> face c
+      for (int t = warp; t < NH * TY; t += NWARPS) {
+        const int n = t / TY, j = t % TY;
+        if (j < tye && lane < txe) {
+          const double *q = prim + (long)var_of_slot(n, 0) * g.ncell + (long)kp * sk +
+                            (long)(j0 + j) * sj + (i0 + lane);
+          double ql, qr;
+          recon_cell<RECON>(q, 1, dx1, (n == 0 || n == 4), ql, qr);
+          sm.wlx[n][j][lane + 1] = ql;
+          sm.wrx[n][j][lane] = qr;
+        }
+      }
+      // x1 end cells: cell -1 gives the L state of face 0, cell txe the R state of face txe
+      for (int t = threadIdx.x; t < NH * TY * 2; t += NTHREADS) {
+        const int side = t & 1, j = (t >> 1) % TY, n = (t >> 1) / TY;
+        if (j < tye) {
+          const int c = side ? txe : -1;
+          const double *q = prim + (long)var_of_slot(n, 0) * g.ncell + (long)kp * sk +
+                            (long)(j0 + j) * sj + (i0 + c);
+          double ql, qr;
+          recon_cell<RECON>(q, 1, dx1, (n == 0 || n == 4), ql, qr);
+          if (side) sm.wrx[n][j][txe] = qr;
+          else sm.wlx[n][j][0] = ql;
+        }
+      }
+      if (NDIM >= 2) {
+        // x2: rows -1..tye ; ql -> face row r+1, qr -> face row r
+        for (int t = warp; t < NH * (TY + 2); t += NWARPS) {
+          const int n = t / (TY + 2), r = t % (TY + 2) - 1;
+          if (r <= tye && lane < txe) {
+            const double *q = prim + (long)var_of_slot(n, 1) * g.ncell + (long)kp * sk +
+                              (long)(j0 + r) * sj + (i0 + lane);
+            double ql, qr;
+            recon_cell<RECON>(q, sj, dx2, (n == 0 || n == 4), ql, qr);
+            if (r + 1 <= tye) sm.wly[n][r + 1][lane] = ql;
+            if (r >= 0) sm.wry[n][r][lane] = qr;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------ riemann phase
+    {
+      // warp-task list: [0,TY) x1 rows, TY: x1 last faces, [TY+1, 2TY+2) x2 face rows,
+      // [2TY+2, 3TY+2) x3 rows
+      const int ntask = 3 * TY + 2;
+      for (int t = warp; t < ntask; t += NWARPS) {
+        double L[NH], R[NH], F[NH];
+        double *dst = nullptr;
+        long dstride = 0;
+        if (t <= TY) {
+          if (!inplane) continue;
+          int j, f;
+          if (t < TY) { j = t; f = lane; if (f > txe || f >= TX) continue; }
+          else { j = lane; f = TX; if (txe < TX || j >= TY) continue; }
+          if (j >= tye) continue;
+#pragma unroll
+          for (int n = 0; n < NH; ++n) { L[n] = sm.wlx[n][j][f]; R[n] = sm.wrx[n][j][f]; }
+          dst = &sm.wlx[0][j][f];
+          dstride = TY * (TX + 1);
+        } else if (t < 2 * TY + 2) {
+          if (!inplane || NDIM < 2) continue;
+          const int r = t - (TY + 1);
+          if (r > tye || lane >= txe) continue;
+#pragma unroll
+          for (int n = 0; n < NH; ++n) { L[n] = sm.wly[n][r][lane]; R[n] = sm.wry[n][r][lane]; }
+          dst = &sm.wly[0][r][lane];
+          dstride = (TY + 1) * TX;
+        } else {
+          if (NDIM < 3 || kp < g.ks) continue;
+          const int j = t - (2 * TY + 2);
+          if (j >= tye || lane >= txe) continue;
+#pragma unroll
+          for (int n = 0; n < NH; ++n) { L[n] = sm.wlz[cur][n][j][lane]; R[n] = sm.wrz[n][j][lane]; }
+          dst = &sm.wlz[cur][0][j][lane];
+          dstride = TY * TX;
+        }
+        riemann_solve<FLUID, RS>(L, R, gamma, c_h, F);
+#pragma unroll
+        for (int n = 0; n < NH; ++n) dst[n * dstride] = F[n];
+      }
+    }
+    __syncthreads();
+    // ------------------------------------------------------------------ finalize phase
+    if (owner) {
+      const int kfin = (NDIM == 3) ? kp - 1 : kp;  // plane whose cells can be finished now
+      if (NDIM < 3) {
+#pragma unroll
+        for (int v = 0; v < NH; ++v) {
+          const int sx = slot_of_var(v, 0);
+          du[v] = (a1 * sm.wlx[sx][cj][ci + 1] - a1 * sm.wlx[sx][cj][ci]);
+          if (NDIM >= 2) {
+            const int sy = slot_of_var(v, 1);
+            du[v] += (a2 * sm.wly[sy][cj + 1][ci] - a2 * sm.wly[sy][cj][ci]);
+          }
+        }
+      }
+      if (kfin >= g.ks && kfin <= g.ke) {
+        const long c = (long)kfin * sk + (long)(j0 + cj) * sj + (i0 + ci);
+        double u[NH], w[NH];
+#pragma unroll
+        for (int v = 0; v < NH; ++v) {
+          double d = du[v];
+          if (NDIM == 3) {
+            const int sz = slot_of_var(v, 2);
+            d += (a3 * sm.wlz[cur][sz][cj][ci] - a3 * fzlo[v]);
+          }
+          const long o = (long)v * g.ncell + c;
+          // update.cpp:135-137 / update.hpp:55
+          u[v] = g0 * B.cons[o] + g1 * B.cons_u1[o] + bdt * (-d / vol);
+        }
+        if constexpr (FLUID == APK_FLUID_GLMMHD) u[8] *= dedner_coeff;  // dedner_source.cpp:72
+        cons_to_prim<NH>(u, w, eos);
+        double *__restrict__ po = prim_out[blockIdx.y];
+#pragma unroll
+        for (int v = 0; v < NH; ++v) {
+          const long o = (long)v * g.ncell + c;
+          B.cons[o] = u[v];
+          po[o] = w[v];
+        }
+        if (dtmin) {  // hydro.cpp:845-895
+          double lx, ly, lz;
+          if constexpr (FLUID == APK_FLUID_EULER) {
+            lx = ly = lz = sound_speed(gamma, w[0], w[4]);
+          } else {
+            lx = fast_speed(gamma, w[0], w[4], w[5], w[6], w[7]);
+            ly = (NDIM > 1) ? fast_speed(gamma, w[0], w[4], w[6], w[7], w[5]) : 0.0;
+            lz = (NDIM > 2) ? fast_speed(gamma, w[0], w[4], w[7], w[5], w[6]) : 0.0;
+          }
+          my_min = fmin(my_min, dx1 / (fabs(w[1]) + lx));
+          if (NDIM > 1) my_min = fmin(my_min, dx2 / (fabs(w[2]) + ly));
+          if (NDIM > 2) my_min = fmin(my_min, dx3 / (fabs(w[3]) + lz));
+        }
+      }
+      if (NDIM == 3 && inplane) {
+#pragma unroll
+        for (int v = 0; v < NH; ++v) {
+          const int sx = slot_of_var(v, 0), sy = slot_of_var(v, 1), sz = slot_of_var(v, 2);
+          du[v] = (a1 * sm.wlx[sx][cj][ci + 1] - a1 * sm.wlx[sx][cj][ci]);
+          du[v] += (a2 * sm.wly[sy][cj + 1][ci] - a2 * sm.wly[sy][cj][ci]);
+          fzlo[v] = sm.wlz[cur][sz][cj][ci];
+        }
+      }
+    }
+    cur ^= 1;
+    __syncthreads();
+  }
+  if (dtmin) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_min = fmin(my_min, __shfl_xor_sync(0xffffffffu, my_min, o));
+    if (lane == 0 && my_min < DBL_MAX)
+      atomicMin(dtmin, (unsigned long long)__double_as_longlong(my_min));
+  }
+}
+
+template <int FLUID, int RECON, int RS>
+int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
+              double *const *prim_out, double g0, double g1, double bdt, double c_h,
+              double coeff, double *d_dtmin, cudaStream_t s) {
+  constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
+  const EosPars eos = {d.gamma, d.dfloor, d.pfloor, d.efloor, d.vceil, d.eceil};
+  const int ntx = (d.nx[0] + TX - 1) / TX;
+  const int nty = (g.ndim >= 2) ? (d.nx[1] + TY - 1) / TY : 1;
+  dim3 grid(ntx * nty, g.nb);
+  const size_t smem = sizeof(Smem<NH>);
+  unsigned long long *dt = reinterpret_cast<unsigned long long *>(d_dtmin);
+#define APK_LAUNCH_FUSED(ND)                                                                     \
+  {                                                                                              \
+    auto kern = k_stage_fused<FLUID, RECON, RS, ND>;                                             \
+    static bool attr_set = false;                                                                \
+    if (!attr_set) {                                                                             \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+      attr_set = true;                                                                           \
+    }                                                                                            \
+    kern<<<grid, NTHREADS, smem, s>>>(g, blocks, prim_out, g0, g1, bdt, d.gamma, c_h, coeff, eos, \
+                                      ntx, dt);                                                  \
+  }
+  if (g.ndim == 3) APK_LAUNCH_FUSED(3)
+  else if (g.ndim == 2) APK_LAUNCH_FUSED(2)
+  else APK_LAUNCH_FUSED(1)
+#undef APK_LAUNCH_FUSED
+  apk_common::count_launch();
+  return 0;
+}
+
+template <int FLUID, int RS>
+int fused_recon(int recon, const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
+                double *const *prim_out, double g0, double g1, double bdt, double c_h,
+                double coeff, double *dt, cudaStream_t s) {
+  switch (recon) {
+  case APK_RECON_DC: return run_fused<FLUID, APK_RECON_DC, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, dt, s);
+  case APK_RECON_PLM: return run_fused<FLUID, APK_RECON_PLM, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, dt, s);
+  case APK_RECON_PPM: return run_fused<FLUID, APK_RECON_PPM, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, dt, s);
+  case APK_RECON_WENOZ: return run_fused<FLUID, APK_RECON_WENOZ, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, dt, s);
+  case APK_RECON_WENO3: return run_fused<FLUID, APK_RECON_WENO3, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, dt, s);
+  case APK_RECON_LIMO3: return run_fused<FLUID, APK_RECON_LIMO3, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, dt, s);
+  }
+  apk_common::set_error("apk_stage_fused: unknown reconstruction");
+  return 1;
+}
+
+}  // namespace
+
+#ifndef APK_FUSED_PART
+#define APK_FUSED_PART 0
+#endif
+#if APK_FUSED_PART == 0
+int launch_stage_fused_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
+                           double *const *prim_out, double g0, double g1, double bdt, double c_h,
+                           double dedner_coeff, int recon, double *d_dtmin, cudaStream_t s);
+
+int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
+                       double *const *prim_out, double g0, double g1, double bdt, double c_h,
+                       double dedner_coeff, int recon, double *d_dtmin, cudaStream_t s) {
+  const ApkGeom g = apk_make_geom(d);
+  if (recon < 0) recon = d.recon;
+  if (d.nscalars != 0) {
+    apk_common::set_error("apk_stage_fused: passive scalars need the un-fused tasks");
+    return 1;
+  }
+  if (d.fluid == APK_FLUID_EULER) {
+    switch (d.riemann) {
+    case APK_RIEMANN_NONE: return run_fused<APK_FLUID_EULER, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, d_dtmin, s);
+    case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, d_dtmin, s);
+    case APK_RIEMANN_HLLC: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLC>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, d_dtmin, s);
+    }
+  } else {
+    return launch_stage_fused_mhd(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, recon,
+                                  d_dtmin, s);
+  }
+  apk_common::set_error("apk_stage_fused: unsupported fluid/riemann combination");
+  return 1;
+}
+#else
+int launch_stage_fused_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
+                           double *const *prim_out, double g0, double g1, double bdt, double c_h,
+                           double dedner_coeff, int recon, double *d_dtmin, cudaStream_t s) {
+  switch (d.riemann) {
+  case APK_RIEMANN_NONE: return run_fused<APK_FLUID_GLMMHD, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, d_dtmin, s);
+  case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, d_dtmin, s);
+  case APK_RIEMANN_HLLD: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLD>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, d_dtmin, s);
+  }
+  apk_common::set_error("apk_stage_fused: unsupported fluid/riemann combination");
+  return 1;
+}
+#endif
+
+}  // namespace APK_NS

@@ -1,0 +1,86 @@
+// apk_launch.h -- internal: host-side launchers implemented once per floating-point mode.
+// apk_tasks.cu / apk_fused.cu are compiled twice (APK_NS=apk_fast with FMA contraction,
+// APK_NS=apk_strict with -fmad=false); apk_capi.cu dispatches on apk_pack_desc_t::fp_mode.
+#ifndef APK_LAUNCH_H_
+#define APK_LAUNCH_H_
+
+#include <cuda_runtime.h>
+
+#include "../../include/apk_b200.h"
+
+#define APK_DECLARE_LAUNCHERS(NS)                                                               \
+  namespace NS {                                                                                \
+  int launch_calc_fluxes(const apk_pack_desc_t &d, const apk_block_t *blocks, double c_h,       \
+                         int recon, cudaStream_t s);                                            \
+  int launch_fofc_flag(const apk_pack_desc_t &d, const apk_block_t *blocks, double g0,          \
+                       double g1, double bdt, int attempt, unsigned char *flags,                \
+                       unsigned long long *counter, cudaStream_t s);                            \
+  int launch_fofc_fix(const apk_pack_desc_t &d, const apk_block_t *blocks, double c_h,          \
+                      const unsigned char *flags, cudaStream_t s);                              \
+  int launch_flux_div_update(const apk_pack_desc_t &d, const apk_block_t *blocks, double g0,    \
+                             double g1, double bdt, cudaStream_t s);                            \
+  int launch_dedner(const apk_pack_desc_t &d, const apk_block_t *blocks, double coeff,          \
+                    double bdt, int extended, cudaStream_t s);                                  \
+  int launch_cons_to_prim(const apk_pack_desc_t &d, const apk_block_t *blocks, int *status,     \
+                          cudaStream_t s);                                                      \
+  int launch_min_dt(const apk_pack_desc_t &d, const apk_block_t *blocks, double *d_out,         \
+                    cudaStream_t s);                                                            \
+  int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,                   \
+                         double *const *prim_out, double g0, double g1, double bdt, double c_h, \
+                         double dedner_coeff, int recon, double *d_dtmin, cudaStream_t s);      \
+  }
+
+APK_DECLARE_LAUNCHERS(apk_fast)
+APK_DECLARE_LAUNCHERS(apk_strict)
+
+// mode-independent (pure data movement) launchers, apk_halo.cu
+namespace apk_common {
+int launch_fill_ghosts(const apk_pack_desc_t &d, const apk_block_t *blocks, int with_prim,
+                       cudaStream_t s);
+int launch_physical_bcs(const apk_pack_desc_t &d, const apk_block_t *blocks, unsigned face_mask,
+                        int with_prim, cudaStream_t s);
+int launch_halo_pack(const apk_pack_desc_t &d, const apk_block_t *blocks,
+                     const apk_halo_item_t *items, int nitems, int with_prim, double *buf,
+                     cudaStream_t s);
+int launch_halo_unpack(const apk_pack_desc_t &d, const apk_block_t *blocks,
+                       const apk_halo_item_t *items, int nitems, int with_prim,
+                       const double *buf, cudaStream_t s);
+int launch_save_u1(const apk_pack_desc_t &d, const apk_block_t *blocks, cudaStream_t s);
+int launch_fp64_probe(int nb, int nt, int niter, double *out, cudaStream_t s);
+void count_launch(int n = 1);
+long long launches();
+void reset_launches();
+const char *last_error();
+void set_error(const char *msg);
+}  // namespace apk_common
+
+// geometry shared by all kernels
+struct ApkGeom {
+  int nb, nvar, nhydro, nscalars, ndim, ng;
+  int n1, n2, n3;  // array extents incl. ghosts
+  int is, ie, js, je, ks, ke;
+  long ncell;  // n1*n2*n3
+};
+
+static inline ApkGeom apk_make_geom(const apk_pack_desc_t &d) {
+  ApkGeom g;
+  g.nb = d.nblocks;
+  g.nvar = d.nvar;
+  g.nscalars = d.nscalars;
+  g.nhydro = d.nvar - d.nscalars;
+  g.ndim = d.ndim;
+  g.ng = d.ng;
+  g.n1 = d.nx[0] + 2 * d.ng;
+  g.n2 = (d.ndim >= 2) ? d.nx[1] + 2 * d.ng : 1;
+  g.n3 = (d.ndim >= 3) ? d.nx[2] + 2 * d.ng : 1;
+  g.is = d.ng;
+  g.ie = d.ng + d.nx[0] - 1;
+  g.js = (d.ndim >= 2) ? d.ng : 0;
+  g.je = (d.ndim >= 2) ? d.ng + d.nx[1] - 1 : 0;
+  g.ks = (d.ndim >= 3) ? d.ng : 0;
+  g.ke = (d.ndim >= 3) ? d.ng + d.nx[2] - 1 : 0;
+  g.ncell = (long)g.n1 * g.n2 * g.n3;
+  return g;
+}
+
+#endif  // APK_LAUNCH_H_

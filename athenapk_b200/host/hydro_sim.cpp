@@ -1,0 +1,732 @@
+// hydro_sim.cpp -- see hydro_sim.hpp.  Host C++ only: device work goes through the C-ABI.
+#include "hydro_sim.hpp"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+
+namespace apk_host {
+
+namespace {
+void cuda_check(cudaError_t e, const char *what) {
+  if (e != cudaSuccess) {
+    // product path must fail loudly (no CPU fallback)
+    throw std::runtime_error(std::string("apk_host: CUDA failure in ") + what + ": " +
+                             cudaGetErrorString(e));
+  }
+}
+void abi_check(int rc, const char *what) {
+  if (rc != 0)
+    throw std::runtime_error(std::string("apk_host: ") + what + " failed: " + apk_last_error());
+}
+cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// mesh/forest/logical_location.cpp:61-74
+double IndexToSymmetrizedCoordinate(int index, int bloc, int nrange) {
+  const std::int64_t noffset = index - (nrange) / 2;
+  const std::int64_t noffset_ceil = index - (nrange + 1) / 2;
+  return static_cast<double>(noffset + noffset_ceil + static_cast<std::int64_t>(bloc)) /
+         (2.0 * nrange);
+}
+// defs.hpp:106-109
+double SymmetrizedLogicalToActualPosition(double u, double xmin, double xmax) {
+  return 0.5 * (xmin + xmax) + (u * xmax - u * xmin);
+}
+int MaximumPowerOf2Divisor(int in) { return in & (~(in - 1)); }  // utils/bit_hacks.hpp:91
+
+std::uint64_t Morton(int x, int y, int z) {
+  std::uint64_t m = 0;
+  for (int bit = 0; bit < 20; ++bit) {
+    m |= (std::uint64_t)((x >> bit) & 1) << (3 * bit);
+    m |= (std::uint64_t)((y >> bit) & 1) << (3 * bit + 1);
+    m |= (std::uint64_t)((z >> bit) & 1) << (3 * bit + 2);
+  }
+  return m;
+}
+}  // namespace
+
+LowStorageIntegrator::LowStorageIntegrator(Integrator which) {
+  switch (which) {
+  case Integrator::rk1:
+    nstages = 1; gam0 = {0.0}; gam1 = {1.0}; beta = {1.0};
+    break;
+  case Integrator::rk2:
+    nstages = 2; gam0 = {0.0, 0.5}; gam1 = {1.0, 0.5}; beta = {1.0, 0.5};
+    break;
+  case Integrator::vl2:
+    nstages = 2; gam0 = {0.0, 0.0}; gam1 = {1.0, 1.0}; beta = {0.5, 1.0};
+    break;
+  case Integrator::rk3:
+    nstages = 3; gam0 = {0.0, 0.25, 2.0 / 3.0}; gam1 = {1.0, 0.75, 1.0 / 3.0};
+    beta = {1.0, 0.25, 2.0 / 3.0};
+    break;
+  }
+}
+
+TaskStatus TaskList::Execute() {
+  // Parthenon re-enqueues tasks that return `incomplete` (tasks/tasks.cpp:119-153); with a
+  // single in-order list that is a poll loop on the head task.
+  for (auto &t : tasks) {
+    TaskStatus st;
+    long polls = 0;
+    while ((st = t.second()) == TaskStatus::incomplete) {
+      if (++polls > 2000000000L) return TaskStatus::fail;
+    }
+    if (st == TaskStatus::fail) return st;
+  }
+  return TaskStatus::complete;
+}
+
+HydroSim::HydroSim(const SimConfig &cfg)
+    : cfg_(cfg), integrator_(static_cast<Integrator>(cfg.integrator)) {
+  int ndev = 0;
+  cuda_check(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount (is there a GPU?)");
+  if (ndev == 0) throw std::runtime_error("apk_host: no CUDA device");
+  nhydro_ = (cfg_.fluid == APK_FLUID_GLMMHD) ? 9 : 5;
+  nvar_ = nhydro_ + cfg_.nscalars;
+  ndim_ = (cfg_.nx[2] > 1) ? 3 : ((cfg_.nx[1] > 1) ? 2 : 1);
+  // hydro.cpp:317-339,444-447: ghost zones required by the reconstruction
+  const int need = (cfg_.recon == APK_RECON_DC) ? 1
+                   : (cfg_.recon == APK_RECON_PPM || cfg_.recon == APK_RECON_WENOZ) ? 3 : 2;
+  if (cfg_.ng < need)
+    throw std::runtime_error("AthenaPK hydro: Need more ghost zones for chosen reconstruction.");
+  if (cfg_.riemann == APK_RIEMANN_LLF && cfg_.recon != APK_RECON_DC)
+    throw std::runtime_error("LLF Riemann solver only implemented with DC reconstruction.");
+  if (cfg_.fluid == APK_FLUID_EULER && cfg_.riemann == APK_RIEMANN_HLLD)
+    throw std::runtime_error("HLLD requires fluid = glmmhd");
+  if (cfg_.fluid == APK_FLUID_GLMMHD && cfg_.riemann == APK_RIEMANN_HLLC)
+    throw std::runtime_error("HLLC requires fluid = euler");
+  for (int d = 0; d < 3; ++d) {
+    if (cfg_.nx[d] % cfg_.mb[d] != 0)
+      throw std::runtime_error("Block size is not evenly divisible into the base mesh size.");
+    nb_[d] = cfg_.nx[d] / cfg_.mb[d];
+    n_[d] = (cfg_.nx[d] == 1) ? 1 : cfg_.mb[d] + 2 * cfg_.ng;
+  }
+  nblocks_global_ = nb_[0] * nb_[1] * nb_[2];
+  fused_ = cfg_.fused && !cfg_.fofc && !cfg_.dedner_extended && cfg_.riemann != APK_RIEMANN_LLF &&
+           cfg_.nscalars == 0;
+  cudaStream_t st;
+  cuda_check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate");
+  stream_ = st;
+  BuildMesh();
+  BuildNeighbors();
+  UploadBlocks();
+  BuildHaloPlan();
+}
+
+HydroSim::~HydroSim() {
+  cudaDeviceSynchronize();
+  if (comm_) ncclCommDestroy(reinterpret_cast<ncclComm_t>(comm_));
+  cudaFree(d_cons_);
+  cudaFree(d_prim_[0]);
+  cudaFree(d_prim_[1]);
+  cudaFree(d_u1_);
+  for (int d = 0; d < 3; ++d) cudaFree(d_flux_[d]);
+  cudaFree(d_blocks_[0]);
+  cudaFree(d_blocks_[1]);
+  cudaFree(d_prim_out_[0]);
+  cudaFree(d_prim_out_[1]);
+  cudaFree(d_scalars_);
+  cudaFree(d_status_);
+  cudaFree(d_fofc_work_);
+  cudaFree(d_send_items_);
+  cudaFree(d_recv_items_);
+  cudaFree(d_sendbuf_);
+  cudaFree(d_recvbuf_);
+  if (comm_event_) cudaEventDestroy(reinterpret_cast<cudaEvent_t>(comm_event_));
+  if (stream_) cudaStreamDestroy(S(stream_));
+}
+
+void HydroSim::Synchronize() { cuda_check(cudaStreamSynchronize(S(stream_)), "sync"); }
+
+// Block list in Morton (Z) order like Parthenon's forest (forest.cpp:106-160); contiguous gid
+// ranges go to ranks (what Parthenon's load balancer does for equal-cost blocks).
+void HydroSim::BuildMesh() {
+  std::vector<std::pair<std::uint64_t, std::array<int, 3>>> order;
+  for (int z = 0; z < nb_[2]; ++z)
+    for (int y = 0; y < nb_[1]; ++y)
+      for (int x = 0; x < nb_[0]; ++x) order.push_back({Morton(x, y, z), {x, y, z}});
+  std::sort(order.begin(), order.end());
+  gid_of_loc_.assign(nblocks_global_, -1);
+  loc_of_gid_.resize(nblocks_global_);
+  for (int g = 0; g < nblocks_global_; ++g) {
+    loc_of_gid_[g] = order[g].second;
+    const auto &l = order[g].second;
+    gid_of_loc_[l[0] + nb_[0] * (l[1] + nb_[1] * l[2])] = g;
+  }
+  // equal split (remainder to the first ranks)
+  const int base = nblocks_global_ / cfg_.nranks, rem = nblocks_global_ % cfg_.nranks;
+  gid_lo_ = cfg_.rank * base + std::min(cfg_.rank, rem);
+  gid_hi_ = gid_lo_ + base + (cfg_.rank < rem ? 1 : 0);
+  if (gid_hi_ <= gid_lo_) throw std::runtime_error("apk_host: rank without meshblocks");
+
+  // forest.cpp:66-141 + tree.cpp:296-318: tree decomposition then block-in-tree bounds
+  bool any_sym = false;
+  int mcp2 = 1 << 30;
+  for (int d = 0; d < 3; ++d) {
+    if (cfg_.nx[d] == 1) { any_sym = true; continue; }
+    mcp2 = std::min(mcp2, MaximumPowerOf2Divisor(nb_[d]));
+  }
+  if (any_sym) mcp2 = 1;
+  blocks_.clear();
+  for (int g = gid_lo_; g < gid_hi_; ++g) {
+    BlockInfo B{};
+    B.gid = g;
+    for (int d = 0; d < 3; ++d) {
+      B.loc[d] = loc_of_gid_[g][d];
+      if (cfg_.nx[d] == 1) {
+        B.bxmin[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(0, 0, 1),
+                                                        cfg_.xmin[d], cfg_.xmax[d]);
+        B.bxmax[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(0, 2, 1),
+                                                        cfg_.xmin[d], cfg_.xmax[d]);
+      } else {
+        const int ntree = nb_[d] / mcp2, it = B.loc[d] / mcp2, lx = B.loc[d] % mcp2;
+        const double tmin = SymmetrizedLogicalToActualPosition(
+            IndexToSymmetrizedCoordinate(it, 0, ntree), cfg_.xmin[d], cfg_.xmax[d]);
+        const double tmax = SymmetrizedLogicalToActualPosition(
+            IndexToSymmetrizedCoordinate(it, 2, ntree), cfg_.xmin[d], cfg_.xmax[d]);
+        B.bxmin[d] =
+            SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(lx, 0, mcp2), tmin, tmax);
+        B.bxmax[d] =
+            SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(lx, 2, mcp2), tmin, tmax);
+      }
+      // uniform_coordinates.hpp:32-36
+      B.dx[d] = (B.bxmax[d] - B.bxmin[d]) / cfg_.mb[d];
+      const int istart = (cfg_.nx[d] == 1) ? 0 : cfg_.ng;
+      B.xmin[d] = B.bxmin[d] - istart * B.dx[d];
+    }
+    blocks_.push_back(B);
+  }
+
+  desc_.nblocks = (int)blocks_.size();
+  desc_.nvar = nvar_;
+  desc_.nscalars = cfg_.nscalars;
+  for (int d = 0; d < 3; ++d) desc_.nx[d] = cfg_.mb[d];
+  desc_.ng = cfg_.ng;
+  desc_.ndim = ndim_;
+  desc_.fluid = cfg_.fluid;
+  desc_.recon = cfg_.recon;
+  desc_.riemann = cfg_.riemann;
+  desc_.fp_mode = cfg_.fp_mode;
+  desc_.gamma = cfg_.gamma;
+  desc_.dfloor = cfg_.dfloor;
+  desc_.pfloor = cfg_.pfloor;
+  desc_.efloor = cfg_.efloor;
+  desc_.vceil = cfg_.vceil;
+  desc_.eceil = cfg_.eceil;
+}
+
+void HydroSim::BuildNeighbors() {
+  h_blocks_.assign(blocks_.size(), apk_block_t{});
+  bc_face_mask_ = 0;
+  for (size_t b = 0; b < blocks_.size(); ++b) {
+    apk_block_t &hb = h_blocks_[b];
+    const BlockInfo &B = blocks_[b];
+    for (int d = 0; d < 3; ++d) {
+      hb.dx[d] = B.dx[d];
+      hb.xmin[d] = B.xmin[d];
+    }
+    // tree.cpp:320-333 GetBlockBCs
+    for (int f = 0; f < 6; ++f) {
+      const int d = f / 2;
+      const bool on_edge = (f % 2 == 0) ? (B.loc[d] == 0) : (B.loc[d] == nb_[d] - 1);
+      hb.bc[f] = APK_BC_BLOCK;
+      if (d < ndim_ && on_edge && cfg_.bc[f] != APK_BC_PERIODIC) {
+        hb.bc[f] = cfg_.bc[f];
+        bc_face_mask_ |= 1u << f;
+      }
+    }
+    for (int o3 = -1; o3 <= 1; ++o3)
+      for (int o2 = -1; o2 <= 1; ++o2)
+        for (int o1 = -1; o1 <= 1; ++o1) {
+          const int idx = (o3 + 1) * 9 + (o2 + 1) * 3 + (o1 + 1);
+          hb.nbr[idx] = APK_NBR_NONE;
+          const int off[3] = {o1, o2, o3};
+          if (!o1 && !o2 && !o3) continue;
+          bool valid = true;
+          int nl[3];
+          for (int d = 0; d < 3; ++d) {
+            if (off[d] != 0 && cfg_.nx[d] == 1) valid = false;
+            nl[d] = B.loc[d] + off[d];
+            if (nl[d] < 0 || nl[d] >= nb_[d]) {
+              const int face = 2 * d + (nl[d] < 0 ? 0 : 1);
+              if (cfg_.bc[face] != APK_BC_PERIODIC) valid = false;
+              nl[d] = (nl[d] + nb_[d]) % nb_[d];
+            }
+          }
+          if (!valid) continue;
+          const int ngid = gid_of_loc_[nl[0] + nb_[0] * (nl[1] + nb_[1] * nl[2])];
+          if (ngid >= gid_lo_ && ngid < gid_hi_) hb.nbr[idx] = ngid - gid_lo_;
+          else hb.nbr[idx] = APK_NBR_REMOTE(0);  // slot resolved by the halo plan
+        }
+  }
+}
+
+void HydroSim::UploadBlocks() {
+  const size_t per = BlockFieldElems();
+  const size_t nbl = blocks_.size();
+  const size_t bytes = per * nbl * sizeof(double);
+  cuda_check(cudaMalloc(&d_cons_, bytes), "cudaMalloc cons");
+  cuda_check(cudaMalloc(&d_prim_[0], bytes), "cudaMalloc prim");
+  cuda_check(cudaMalloc(&d_u1_, bytes), "cudaMalloc u1");
+  cuda_check(cudaMemset(d_cons_, 0, bytes), "memset");
+  cuda_check(cudaMemset(d_prim_[0], 0, bytes), "memset");
+  cuda_check(cudaMemset(d_u1_, 0, bytes), "memset");
+  if (fused_) {
+    cuda_check(cudaMalloc(&d_prim_[1], bytes), "cudaMalloc prim scratch");
+    cuda_check(cudaMemset(d_prim_[1], 0, bytes), "memset");
+  } else {
+    for (int d = 0; d < ndim_; ++d) {
+      cuda_check(cudaMalloc(&d_flux_[d], bytes), "cudaMalloc flux");
+      cuda_check(cudaMemset(d_flux_[d], 0, bytes), "memset");
+    }
+  }
+  for (int which = 0; which < (fused_ ? 2 : 1); ++which) {
+    std::vector<apk_block_t> hb = h_blocks_;
+    std::vector<double *> pout(nbl);
+    for (size_t b = 0; b < nbl; ++b) {
+      hb[b].cons = d_cons_ + b * per;
+      hb[b].prim = d_prim_[which] + b * per;
+      hb[b].cons_u1 = d_u1_ + b * per;
+      for (int d = 0; d < 3; ++d) hb[b].flux[d] = d_flux_[d] ? d_flux_[d] + b * per : nullptr;
+      pout[b] = fused_ ? d_prim_[1 - which] + b * per : nullptr;
+    }
+    cuda_check(cudaMalloc(&d_blocks_[which], nbl * sizeof(apk_block_t)), "cudaMalloc blocks");
+    cuda_check(cudaMemcpy(d_blocks_[which], hb.data(), nbl * sizeof(apk_block_t),
+                          cudaMemcpyHostToDevice), "upload blocks");
+    cuda_check(cudaMalloc(&d_prim_out_[which], nbl * sizeof(double *)), "cudaMalloc prim_out");
+    cuda_check(cudaMemcpy(d_prim_out_[which], pout.data(), nbl * sizeof(double *),
+                          cudaMemcpyHostToDevice), "upload prim_out");
+  }
+  cuda_check(cudaMalloc(&d_scalars_, 64 * sizeof(double)), "cudaMalloc scalars");
+  cuda_check(cudaMalloc(&d_status_, sizeof(int)), "cudaMalloc status");
+  cuda_check(cudaMemset(d_status_, 0, sizeof(int)), "memset");
+  if (cfg_.fofc) {
+    cuda_check(cudaMalloc(&d_fofc_work_, apk_fofc_workspace_bytes(&desc_)), "cudaMalloc fofc");
+  }
+}
+
+// Remote halo plan: every (local block, offset) whose neighbour lives on another rank
+// contributes one slab to that peer's send buffer and one to its receive buffer.  Both sides
+// order slabs by (receiver gid, receiver-side offset index) so offsets agree without talking.
+void HydroSim::BuildHaloPlan() {
+  if (cfg_.nranks == 1) return;
+  const int ng = cfg_.ng;
+  const int s[3] = {cfg_.ng, ndim_ >= 2 ? cfg_.ng : 0, ndim_ >= 3 ? cfg_.ng : 0};
+  struct Entry {
+    long long key;
+    apk_halo_item_t item;
+    long long cells;
+  };
+  std::map<int, std::vector<Entry>> sends, recvs;
+  const int base = nblocks_global_ / cfg_.nranks, rem = nblocks_global_ % cfg_.nranks;
+  auto rank_of = [&](int gid) {
+    const int cut = rem * (base + 1);
+    return (gid < cut) ? gid / (base + 1) : rem + (gid - cut) / base;
+  };
+  for (size_t b = 0; b < blocks_.size(); ++b) {
+    const BlockInfo &B = blocks_[b];
+    for (int o3 = -1; o3 <= 1; ++o3)
+      for (int o2 = -1; o2 <= 1; ++o2)
+        for (int o1 = -1; o1 <= 1; ++o1) {
+          const int idx = (o3 + 1) * 9 + (o2 + 1) * 3 + (o1 + 1);
+          if (h_blocks_[b].nbr[idx] > APK_NBR_NONE || h_blocks_[b].nbr[idx] == APK_NBR_NONE)
+            continue;
+          const int off[3] = {o1, o2, o3};
+          int nl[3];
+          for (int d = 0; d < 3; ++d) nl[d] = ((B.loc[d] + off[d]) % nb_[d] + nb_[d]) % nb_[d];
+          const int ngid = gid_of_loc_[nl[0] + nb_[0] * (nl[1] + nb_[1] * nl[2])];
+          const int peer = rank_of(ngid);
+          // receive: my ghost slab at offset `off` (bnd_info.cpp:136-230)
+          Entry r{};
+          r.item.block = (int)b;
+          r.cells = 1;
+          // send: my interior slab adjacent to the neighbour
+          Entry sd{};
+          sd.item.block = (int)b;
+          sd.cells = 1;
+          for (int d = 0; d < 3; ++d) {
+            const int e = s[d] + cfg_.mb[d] - 1;
+            if (off[d] == 0) {
+              r.item.lo[d] = sd.item.lo[d] = s[d];
+              r.item.ext[d] = sd.item.ext[d] = (cfg_.nx[d] == 1) ? 1 : cfg_.mb[d];
+            } else if (off[d] > 0) {
+              r.item.lo[d] = e + 1;
+              sd.item.lo[d] = e - ng + 1;
+              r.item.ext[d] = sd.item.ext[d] = ng;
+            } else {
+              r.item.lo[d] = s[d] - ng;
+              sd.item.lo[d] = s[d];
+              r.item.ext[d] = sd.item.ext[d] = ng;
+            }
+            r.cells *= r.item.ext[d];
+            sd.cells *= sd.item.ext[d];
+          }
+          r.key = (long long)B.gid * 27 + idx;
+          const int ridx = (-o3 + 1) * 9 + (-o2 + 1) * 3 + (-o1 + 1);
+          sd.key = (long long)ngid * 27 + ridx;
+          recvs[peer].push_back(r);
+          sends[peer].push_back(sd);
+        }
+  }
+  send_items_.clear();
+  recv_items_.clear();
+  peers_.clear();
+  long long soff = 0, roff = 0;
+  // factor 2 leaves room for prim when the fused path exchanges cons+prim
+  const long long per_cell = (long long)nvar_ * 2;
+  for (auto &kv : sends) {
+    Peer p{};
+    p.rank = kv.first;
+    auto &sv = kv.second;
+    auto &rv = recvs[kv.first];
+    auto by_key = [](const Entry &a, const Entry &b) { return a.key < b.key; };
+    std::sort(sv.begin(), sv.end(), by_key);
+    std::sort(rv.begin(), rv.end(), by_key);
+    p.send_off = soff;
+    for (auto &e : sv) {
+      e.item.offset = soff;
+      soff += e.cells * per_cell;
+      send_items_.push_back(e.item);
+    }
+    p.send_cnt = soff - p.send_off;
+    p.recv_off = roff;
+    for (auto &e : rv) {
+      e.item.offset = roff;
+      roff += e.cells * per_cell;
+      recv_items_.push_back(e.item);
+    }
+    p.recv_cnt = roff - p.recv_off;
+    peers_.push_back(p);
+  }
+  send_total_ = soff;
+  recv_total_ = roff;
+  cuda_check(cudaMalloc(&d_sendbuf_, std::max<long long>(soff, 1) * sizeof(double)), "sendbuf");
+  cuda_check(cudaMalloc(&d_recvbuf_, std::max<long long>(roff, 1) * sizeof(double)), "recvbuf");
+  cuda_check(cudaMalloc(&d_send_items_, std::max<size_t>(send_items_.size(), 1) * sizeof(apk_halo_item_t)), "items");
+  cuda_check(cudaMalloc(&d_recv_items_, std::max<size_t>(recv_items_.size(), 1) * sizeof(apk_halo_item_t)), "items");
+  cuda_check(cudaMemcpy(d_send_items_, send_items_.data(), send_items_.size() * sizeof(apk_halo_item_t), cudaMemcpyHostToDevice), "items");
+  cuda_check(cudaMemcpy(d_recv_items_, recv_items_.data(), recv_items_.size() * sizeof(apk_halo_item_t), cudaMemcpyHostToDevice), "items");
+}
+
+int HydroSim::CommUniqueId(void *out, int nbytes) {
+  if (nbytes < (int)sizeof(ncclUniqueId)) return -1;
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return -2;
+  std::memcpy(out, &id, sizeof(id));
+  return (int)sizeof(id);
+}
+
+int HydroSim::InitComm(const void *uid, int nbytes) {
+  if (cfg_.nranks == 1) return 0;
+  if (nbytes < (int)sizeof(ncclUniqueId)) return -1;
+  ncclUniqueId id;
+  std::memcpy(&id, uid, sizeof(id));
+  ncclComm_t c;
+  if (ncclCommInitRank(&c, cfg_.nranks, id, cfg_.rank) != ncclSuccess) return -2;
+  comm_ = reinterpret_cast<ncclComm *>(c);
+  return 0;
+}
+
+double *HydroSim::DevicePtr(int field, int block) {
+  const size_t per = BlockFieldElems();
+  switch (field) {
+  case 0: return d_cons_ + block * per;
+  case 1: return d_prim_[cur_] + block * per;
+  case 2: return d_u1_ + block * per;
+  case 3: case 4: case 5:
+    return d_flux_[field - 3] ? d_flux_[field - 3] + block * per : nullptr;
+  }
+  return nullptr;
+}
+
+int HydroSim::CopyFromHost(int field, int block, const double *src) {
+  double *p = DevicePtr(field, block);
+  if (!p) return -1;
+  cuda_check(cudaMemcpyAsync(p, src, BlockFieldElems() * sizeof(double), cudaMemcpyHostToDevice,
+                             S(stream_)), "H2D");
+  Synchronize();
+  return 0;
+}
+
+int HydroSim::CopyToHost(int field, int block, double *dst) {
+  double *p = DevicePtr(field, block);
+  if (!p) return -1;
+  cuda_check(cudaMemcpyAsync(dst, p, BlockFieldElems() * sizeof(double), cudaMemcpyDeviceToHost,
+                             S(stream_)), "D2H");
+  Synchronize();
+  return 0;
+}
+
+// ================================================================================================
+// Tasks (hydro_driver.cpp:474-613)
+// ================================================================================================
+TaskStatus HydroSim::InitU1() {  // hydro_driver.cpp:474-495
+  abi_check(apk_save_u1(&desc_, d_blocks_[cur_], stream_), "apk_save_u1");
+  return TaskStatus::complete;
+}
+
+TaskStatus HydroSim::CalculateFluxes(int stage) {
+  // flux_first_stage: VL2 predictor uses donor cell (hydro.cpp:459-464)
+  const int recon = (stage == 1 && cfg_.integrator == (int)Integrator::vl2) ? APK_RECON_DC : -1;
+  abi_check(apk_calc_fluxes(&desc_, d_blocks_[cur_], c_h, recon, stream_), "apk_calc_fluxes");
+  return TaskStatus::complete;
+}
+
+TaskStatus HydroSim::FirstOrderFluxCorrect(Real gam0, Real gam1, Real beta_dt) {
+  long long n = 0;
+  abi_check(apk_first_order_flux_correct(&desc_, d_blocks_[cur_], gam0, gam1, beta_dt, c_h,
+                                         d_fofc_work_, &n, stream_), "apk_first_order_flux_correct");
+  fofc_corrections += n;
+  return TaskStatus::complete;
+}
+
+TaskStatus HydroSim::UpdateWithFluxDivergence(Real gam0, Real gam1, Real beta_dt) {
+  abi_check(apk_flux_div_update(&desc_, d_blocks_[cur_], gam0, gam1, beta_dt, stream_),
+            "apk_flux_div_update");
+  return TaskStatus::complete;
+}
+
+TaskStatus HydroSim::AddUnsplitSources(Real beta_dt) {  // hydro.cpp:227-246
+  if (cfg_.fluid == APK_FLUID_GLMMHD) {
+    abi_check(apk_dedner_source(&desc_, d_blocks_[cur_], c_h, mindx, cfg_.glmmhd_alpha, beta_dt,
+                                cfg_.dedner_extended, stream_), "apk_dedner_source");
+  }
+  return TaskStatus::complete;
+}
+
+TaskStatus HydroSim::FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, bool last_stage) {
+  const int recon = (stage == 1 && cfg_.integrator == (int)Integrator::vl2) ? APK_RECON_DC : -1;
+  double *dtmin = nullptr;
+  if (last_stage) {
+    dtmin = d_scalars_;
+    const double big = DBL_MAX;
+    cuda_check(cudaMemcpyAsync(d_scalars_, &big, sizeof(double), cudaMemcpyHostToDevice, S(stream_)),
+               "init dtmin");
+  }
+  abi_check(apk_stage_fused(&desc_, d_blocks_[cur_], d_prim_out_[cur_], gam0, gam1, beta_dt, c_h,
+                            mindx, cfg_.glmmhd_alpha, recon, dtmin, stream_), "apk_stage_fused");
+  cur_ ^= 1;  // prim_out becomes "prim"
+  return TaskStatus::complete;
+}
+
+TaskStatus HydroSim::StartReceiveBoundBufs() {
+  // NCCL receives are posted together with the sends inside one group (SendBoundBufs); the
+  // task exists to keep the reference's task graph shape (hydro_driver.cpp:505-506).
+  recv_posted_ = true;
+  return TaskStatus::complete;
+}
+
+TaskStatus HydroSim::SendBoundBufs(bool with_prim) {
+  // same-device neighbours: direct ghost fill, no buffers
+  abi_check(apk_copy_ghosts_local(&desc_, d_blocks_[cur_], with_prim ? 1 : 0, stream_),
+            "apk_copy_ghosts_local");
+  if (cfg_.nranks == 1) return TaskStatus::complete;
+  if (!comm_) throw std::runtime_error("apk_host: multi-rank run without InitComm");
+  // one pack launch for all peers, one grouped send/recv per peer
+  abi_check(apk_halo_pack(&desc_, d_blocks_[cur_], d_send_items_, (int)send_items_.size(),
+                          with_prim ? 1 : 0, d_sendbuf_, stream_), "apk_halo_pack");
+  ncclComm_t c = reinterpret_cast<ncclComm_t>(comm_);
+  // buffers are laid out for cons+prim; without prim each item only fills its first half, the
+  // whole (fixed-size) segment is still what both sides agree on.
+  ncclGroupStart();
+  for (const Peer &p : peers_) {
+    ncclSend(d_sendbuf_ + p.send_off, (size_t)p.send_cnt, ncclDouble, p.rank, c, S(stream_));
+    ncclRecv(d_recvbuf_ + p.recv_off, (size_t)p.recv_cnt, ncclDouble, p.rank, c, S(stream_));
+  }
+  if (ncclGroupEnd() != ncclSuccess) return TaskStatus::fail;
+  if (!comm_event_) {
+    cudaEvent_t ev;
+    cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+    comm_event_ = ev;
+  }
+  cuda_check(cudaEventRecord(reinterpret_cast<cudaEvent_t>(comm_event_), S(stream_)), "record");
+  return TaskStatus::complete;
+}
+
+TaskStatus HydroSim::ReceiveBoundBufs() {
+  // The reference polls MPI_Test and returns `incomplete` (boundary_communication.cpp:200-235).
+  // The NCCL transfer is stream-ordered, so the unpack can simply be enqueued behind it; the
+  // task therefore completes immediately (no host polling, no fence).
+  return TaskStatus::complete;
+}
+
+TaskStatus HydroSim::SetBounds(bool with_prim) {
+  if (cfg_.nranks > 1) {
+    abi_check(apk_halo_unpack(&desc_, d_blocks_[cur_], d_recv_items_, (int)recv_items_.size(),
+                              with_prim ? 1 : 0, d_recvbuf_, stream_), "apk_halo_unpack");
+  }
+  recv_posted_ = false;
+  return TaskStatus::complete;
+}
+
+TaskStatus HydroSim::ApplyBoundaryConditions(bool with_prim) {
+  if (bc_face_mask_)
+    abi_check(apk_apply_physical_bcs(&desc_, d_blocks_[cur_], bc_face_mask_, with_prim ? 1 : 0,
+                                     stream_), "apk_apply_physical_bcs");
+  return TaskStatus::complete;
+}
+
+TaskStatus HydroSim::FillDerived() {  // Update::FillDerived -> ConsToPrim (hydro.cpp:707,712)
+  abi_check(apk_cons_to_prim(&desc_, d_blocks_[cur_], d_status_, stream_), "apk_cons_to_prim");
+  return TaskStatus::complete;
+}
+
+double HydroSim::HostMinDt(double local_min) {
+  if (cfg_.nranks == 1) return local_min;
+  return local_min;
+}
+
+TaskStatus HydroSim::EstimateTimestep(bool have_device_min) {
+  // hydro.cpp:828-976 + update.hpp:269-278. have_device_min: the fused last stage already left
+  // min dx/(|v|+c) in d_scalars_[0].
+  if (cfg_.riemann == APK_RIEMANN_NONE) {  // calc_dt_hyp = false, hydro.cpp:354-361
+    new_dt_ = std::numeric_limits<Real>::max();
+    return TaskStatus::complete;
+  }
+  if (!have_device_min)
+    abi_check(apk_min_dt_async(&desc_, d_blocks_[cur_], d_scalars_, stream_), "apk_min_dt_async");
+  if (cfg_.nranks > 1) {
+    // replaces MPI_Allreduce(MIN) of driver.cpp:237 / hydro.cpp:127
+    ncclAllReduce(d_scalars_, d_scalars_, 1, ncclDouble, ncclMin,
+                  reinterpret_cast<ncclComm_t>(comm_), S(stream_));
+  }
+  double m = 0.0;
+  int status = 0;
+  cuda_check(cudaMemcpyAsync(&m, d_scalars_, sizeof(double), cudaMemcpyDeviceToHost, S(stream_)),
+             "dt D2H");
+  cuda_check(cudaMemcpyAsync(&status, d_status_, sizeof(int), cudaMemcpyDeviceToHost, S(stream_)),
+             "status D2H");
+  Synchronize();
+  if (status != 0) {
+    // PARTHENON_REQUIRE in ConsToPrim (adiabatic_hydro.hpp:77-79,111-113)
+    throw std::runtime_error(status == 1
+                                 ? "Got negative density. Consider enabling first-order flux "
+                                   "correction or setting a reasonble density floor."
+                                 : "Got negative pressure. Consider enabling first-order flux "
+                                   "correction or setting a reasonble pressure or temperature floor.");
+  }
+  const Real dt = cfg_.cfl * m;
+  if (cfg_.fluid == APK_FLUID_GLMMHD && dt < dt_hyp) dt_hyp = dt;  // hydro.cpp:903-908
+  new_dt_ = dt;
+  return TaskStatus::complete;
+}
+
+void HydroSim::PreStepMeshUserWorkInLoop() {  // hydro.cpp:102-143 (+ CalculateGlobalMinDx :65-95)
+  if (cfg_.fluid != APK_FLUID_GLMMHD) return;
+  Real m = std::numeric_limits<Real>::max();
+  // dx is identical on all ranks of a uniform mesh; no reduction needed
+  for (const auto &B : blocks_) {
+    m = std::fmin(m, B.dx[0]);
+    if (n_[1] > 1) m = std::fmin(m, B.dx[1]);
+    if (n_[2] > 1) m = std::fmin(m, B.dx[2]);
+  }
+  mindx = m;
+  c_h = cfg_.cfl * mindx / dt_hyp;
+}
+
+void HydroSim::SetGlobalTimeStep() {  // driver.cpp:210-242,267-269 (default dt_* knobs)
+  if (tm.dt < 0.1 * std::numeric_limits<Real>::max()) tm.dt *= 2.0;
+  tm.dt = std::min(tm.dt, new_dt_);
+  new_dt_ = std::numeric_limits<Real>::max();
+  if (tm.time < tm.tlim && (tm.tlim - tm.time) < tm.dt) tm.dt = tm.tlim - tm.time;
+}
+
+void HydroSim::Initialize(double tlim) {
+  tm = SimTime{};
+  tm.tlim = tlim;
+  cur_ = 0;
+  // Mesh::Initialize: exchange ghosts, BCs, FillDerived
+  SendBoundBufs(false);
+  ReceiveBoundBufs();
+  SetBounds(false);
+  ApplyBoundaryConditions(false);
+  FillDerived();
+  dt_hyp = std::numeric_limits<Real>::max();
+  EstimateTimestep(false);
+  SetGlobalTimeStep();
+}
+
+void HydroSim::MakeTaskCollection(TaskList &tl, int stage) {
+  const Real gam0 = integrator_.gam0[stage - 1], gam1 = integrator_.gam1[stage - 1];
+  const Real beta_dt = integrator_.beta[stage - 1] * integrator_.dt;
+  const bool last = (stage == integrator_.nstages);
+  if (stage == 1) tl.AddTask("init_u1", [this] { return InitU1(); });
+  tl.AddTask("start_bnd", [this] { return StartReceiveBoundBufs(); });
+  if (fused_) {
+    // calc_flux + update + source_unsplit + cons2prim(interior) [+ dt reduce] in one kernel;
+    // ghosts of cons AND prim are then exchanged together (pointwise cons->prim commutes with
+    // the copy), so the separate FillDerived region disappears.
+    tl.AddTask("fused_stage", [=] { return FusedStage(stage, gam0, gam1, beta_dt, last); });
+    tl.AddTask("send", [this] { return SendBoundBufs(true); });
+    tl.AddTask("recv", [this] { return ReceiveBoundBufs(); });
+    tl.AddTask("set", [this] { return SetBounds(true); });
+    tl.AddTask("fbound", [this] { return ApplyBoundaryConditions(true); });
+  } else {
+    tl.AddTask("calc_flux", [=] { return CalculateFluxes(stage); });
+    if (cfg_.fofc)
+      tl.AddTask("first_order_flux_correct",
+                 [=] { return FirstOrderFluxCorrect(gam0, gam1, beta_dt); });
+    tl.AddTask("update", [=] { return UpdateWithFluxDivergence(gam0, gam1, beta_dt); });
+    tl.AddTask("source_unsplit", [=] { return AddUnsplitSources(beta_dt); });
+    tl.AddTask("send", [this] { return SendBoundBufs(false); });
+    tl.AddTask("recv", [this] { return ReceiveBoundBufs(); });
+    tl.AddTask("set", [this] { return SetBounds(false); });
+    tl.AddTask("fbound", [this] { return ApplyBoundaryConditions(false); });
+    tl.AddTask("fill_derived", [this] { return FillDerived(); });
+  }
+  if (last) {
+    // hydro_driver.cpp:589-613: reset reduction Params, then EstimateTimestep
+    tl.AddTask("reset_reduction_vars", [this] {
+      mindx = std::numeric_limits<Real>::max();
+      dt_hyp = std::numeric_limits<Real>::max();
+      return TaskStatus::complete;
+    });
+    tl.AddTask("new_dt", [this] { return EstimateTimestep(fused_); });
+  }
+}
+
+TaskStatus HydroSim::Step() {  // multistage.hpp:39-53
+  integrator_.dt = tm.dt;
+  for (int stage = 1; stage <= integrator_.nstages; ++stage) {
+    TaskList tl;
+    MakeTaskCollection(tl, stage);
+    const TaskStatus st = tl.Execute();
+    if (st != TaskStatus::complete) return st;
+  }
+  if (fused_ && cur_ != 0) {
+    // odd number of stages: bring the final primitives back into the caller-visible array
+    cuda_check(cudaMemcpyAsync(d_prim_[0], d_prim_[1], BlockFieldElems() * blocks_.size() * sizeof(double),
+                               cudaMemcpyDeviceToDevice, S(stream_)), "prim copy-back");
+    cur_ = 0;
+  }
+  return TaskStatus::complete;
+}
+
+int HydroSim::Execute(double tlim, int nlim) {  // driver.cpp:67-165
+  const int n0 = tm.ncycle;
+  if (tlim != tm.tlim) {
+    tm.tlim = tlim;
+    if (tm.time < tm.tlim && (tm.tlim - tm.time) < tm.dt) tm.dt = tm.tlim - tm.time;
+  }
+  tm.nlim = nlim;
+  while (tm.KeepGoing()) {
+    PreStepMeshUserWorkInLoop();
+    if (Step() != TaskStatus::complete) throw std::runtime_error("Step failed to complete all tasks.");
+    tm.ncycle++;
+    tm.time += tm.dt;
+    cycles_done++;
+    SetGlobalTimeStep();
+  }
+  Synchronize();
+  return tm.ncycle - n0;
+}
+
+}  // namespace apk_host

@@ -1,0 +1,207 @@
+// hydro_sim.hpp -- host-side C++ mirror of the slice of AthenaPK/Parthenon that drives the hot
+// path: HydroDriver::MakeTaskCollection's stage region (src/hydro/hydro_driver.cpp:474-613),
+// the LowStorageIntegrator coefficients (time_integration/low_storage_integrator.cpp:53-132),
+// EvolutionDriver's dt logic (driver/driver.cpp:67-165,210-242) and PreStepMeshUserWorkInLoop
+// (src/hydro/hydro.cpp:102-143).  Same task names, argument meaning and TaskStatus contract;
+// every device operation goes through the C-ABI of include/apk_b200.h -- this file contains no
+// CUDA kernels and is what a Parthenon-side shim replaces one-for-one.
+#ifndef APK_HOST_HYDRO_SIM_HPP_
+#define APK_HOST_HYDRO_SIM_HPP_
+
+#include <array>
+#include <cstdint>
+#include <functional>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/apk_b200.h"
+
+struct ncclComm;
+
+namespace apk_host {
+
+using Real = double;
+
+// parthenon basic_types.hpp:62
+enum class TaskStatus { complete, incomplete, iterate, fail };
+enum class Integrator { rk1 = 0, rk2 = 1, vl2 = 2, rk3 = 3 };
+
+// what the input deck provides (docs/input.md; hydro.cpp:267-744)
+struct SimConfig {
+  int fluid = APK_FLUID_EULER;
+  int recon = APK_RECON_PLM;
+  int riemann = APK_RIEMANN_HLLE;
+  int integrator = (int)Integrator::vl2;
+  int nx[3] = {1, 1, 1};  // parthenon/mesh/nx*
+  int mb[3] = {1, 1, 1};  // parthenon/meshblock/nx*
+  int ng = 2;             // parthenon/mesh/nghost
+  int bc[6] = {0, 0, 0, 0, 0, 0};  // ix1,ox1,... APK_BC_PERIODIC/OUTFLOW/REFLECT
+  double xmin[3] = {-0.5, -0.5, -0.5}, xmax[3] = {0.5, 0.5, 0.5};
+  double gamma = 5.0 / 3.0, cfl = 0.3;
+  double dfloor = -1.0, pfloor = -1.0, efloor = -1.0;
+  double vceil = std::numeric_limits<double>::infinity();
+  double eceil = std::numeric_limits<double>::infinity();
+  int fofc = 0;             // hydro/first_order_flux_correct
+  int dedner_extended = 0;  // hydro/glmmhd_source = dedner_extended
+  double glmmhd_alpha = 0.1;
+  int nscalars = 0;
+  int fp_mode = APK_FP_FAST;
+  int fused = 1;  // use apk_stage_fused when legal (no FOFC / extended source)
+  int rank = 0, nranks = 1;
+};
+
+// time_integration/low_storage_integrator.cpp:53-132
+struct LowStorageIntegrator {
+  int nstages = 0;
+  std::vector<Real> gam0, gam1, beta;
+  Real dt = 0.0;
+  explicit LowStorageIntegrator(Integrator which);
+};
+
+// parthenon SimTime (basic_types.hpp:200-245)
+struct SimTime {
+  Real time = 0.0, tlim = std::numeric_limits<Real>::max(), dt = std::numeric_limits<Real>::max();
+  int ncycle = 0, nlim = -1;
+  bool KeepGoing() const { return ((time < tlim) && (nlim < 0 || ncycle < nlim)); }
+};
+
+struct BlockInfo {
+  int gid;        // position in the Morton-ordered global block list
+  int loc[3];     // logical location (lx1,lx2,lx3)
+  double bxmin[3], bxmax[3];
+  double dx[3], xmin[3];  // UniformCartesian: dx_, xmin_ (uniform_coordinates.hpp:32-36)
+};
+
+struct TaskList {  // minimal stand-in for parthenon::TaskList (tasks/tasks.hpp): in-order
+  std::vector<std::pair<std::string, std::function<TaskStatus()>>> tasks;
+  void AddTask(const std::string &name, std::function<TaskStatus()> f) {
+    tasks.emplace_back(name, std::move(f));
+  }
+  TaskStatus Execute();  // re-polls `incomplete` tasks like Parthenon's task loop
+};
+
+class HydroSim {
+ public:
+  explicit HydroSim(const SimConfig &cfg);
+  ~HydroSim();
+  HydroSim(const HydroSim &) = delete;
+
+  // ---- mesh ----
+  int NumLocalBlocks() const { return (int)blocks_.size(); }
+  int NumGlobalBlocks() const { return nblocks_global_; }
+  const BlockInfo &Block(int b) const { return blocks_[b]; }
+  const SimConfig &Config() const { return cfg_; }
+  int nvar() const { return nvar_; }
+  const int *dims() const { return n_; }  // n1,n2,n3 incl. ghosts
+  size_t BlockFieldElems() const { return (size_t)nvar_ * n_[0] * n_[1] * n_[2]; }
+  const apk_pack_desc_t &desc() const { return desc_; }
+  const apk_block_t *d_blocks() const { return d_blocks_[cur_]; }
+
+  // ---- data movement (host <-> device), field: 0 cons, 1 prim, 2 u1, 3..5 flux x1..x3 ----
+  int CopyFromHost(int field, int block, const double *src);
+  int CopyToHost(int field, int block, double *dst);
+  double *DevicePtr(int field, int block);
+
+  // ---- problem generators (input side; src/pgen/*.cpp) ----
+  int ProblemGenerator(const std::string &id, const std::vector<double> &pars);
+  double LinearWavePeriod() const { return lw_.tlim_period; }
+  void LinearWaveErrors(double *out6);  // linear_wave.cpp:183-295 (local blocks only)
+
+  // ---- driver (driver.cpp / multistage.hpp / hydro_driver.cpp) ----
+  void Initialize(double tlim);  // Mesh::Initialize + InitializeBlockTimeSteps + SetGlobalTimeStep
+  TaskStatus Step();             // MultiStageDriver::Step: all stages of one cycle
+  int Execute(double tlim, int nlim);  // EvolutionDriver::Execute main loop; returns #cycles
+  void MakeTaskCollection(TaskList &tl, int stage);
+
+  // individual tasks (names follow the reference)
+  TaskStatus InitU1();
+  TaskStatus CalculateFluxes(int stage);
+  TaskStatus FirstOrderFluxCorrect(Real gam0, Real gam1, Real beta_dt);
+  TaskStatus UpdateWithFluxDivergence(Real gam0, Real gam1, Real beta_dt);
+  TaskStatus AddUnsplitSources(Real beta_dt);
+  TaskStatus FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, bool last_stage);
+  TaskStatus StartReceiveBoundBufs();
+  TaskStatus SendBoundBufs(bool with_prim);
+  TaskStatus ReceiveBoundBufs();
+  TaskStatus SetBounds(bool with_prim);
+  TaskStatus ApplyBoundaryConditions(bool with_prim);
+  TaskStatus FillDerived();
+  TaskStatus EstimateTimestep(bool have_device_min);
+  void PreStepMeshUserWorkInLoop();
+  void SetGlobalTimeStep();
+
+  // multi-GPU: one NCCL communicator over the ranks of the box
+  int InitComm(const void *nccl_unique_id, int nbytes);
+  static int CommUniqueId(void *out, int nbytes);
+
+  SimTime tm;
+  Real c_h = 0.0, mindx = std::numeric_limits<Real>::max(),
+       dt_hyp = std::numeric_limits<Real>::max();
+  long long fofc_corrections = 0;
+  long long cycles_done = 0;
+  bool FusedActive() const { return fused_; }
+  void Synchronize();
+  void *stream() const { return stream_; }
+
+ private:
+  void BuildMesh();
+  void BuildNeighbors();
+  void BuildHaloPlan();
+  void UploadBlocks();
+  double HostMinDt(double local_min);
+
+  SimConfig cfg_;
+  LowStorageIntegrator integrator_;
+  int ndim_ = 1, nvar_ = 5, nhydro_ = 5;
+  int nb_[3] = {1, 1, 1}, n_[3] = {1, 1, 1};
+  int nblocks_global_ = 1;
+  std::vector<int> gid_of_loc_;        // lexicographic loc -> gid (Morton order)
+  std::vector<std::array<int, 3>> loc_of_gid_;
+  int gid_lo_ = 0, gid_hi_ = 1;        // this rank owns gids [lo,hi)
+  std::vector<BlockInfo> blocks_;
+  std::vector<apk_block_t> h_blocks_;
+  apk_pack_desc_t desc_{};
+  unsigned bc_face_mask_ = 0;
+  bool fused_ = false;
+  int cur_ = 0;  // which prim buffer is the current "prim" (fused ping-pong)
+
+  // device storage (one slab per field for all local blocks)
+  double *d_cons_ = nullptr, *d_prim_[2] = {nullptr, nullptr}, *d_u1_ = nullptr,
+         *d_flux_[3] = {nullptr, nullptr, nullptr};
+  apk_block_t *d_blocks_[2] = {nullptr, nullptr};
+  double **d_prim_out_[2] = {nullptr, nullptr};
+  double *d_scalars_ = nullptr;  // [0] dt-min, [2..] misc
+  int *d_status_ = nullptr;
+  void *d_fofc_work_ = nullptr;
+  void *stream_ = nullptr;
+
+  // halo plan
+  struct Peer {
+    int rank;
+    long long send_off, send_cnt, recv_off, recv_cnt;  // in doubles (for with_prim = 0)
+  };
+  std::vector<Peer> peers_;
+  std::vector<apk_halo_item_t> send_items_, recv_items_;
+  apk_halo_item_t *d_send_items_ = nullptr, *d_recv_items_ = nullptr;
+  double *d_sendbuf_ = nullptr, *d_recvbuf_ = nullptr;
+  long long send_total_ = 0, recv_total_ = 0;
+  ncclComm *comm_ = nullptr;
+  void *comm_event_ = nullptr;
+  bool recv_posted_ = false;
+
+  // linear wave pgen state (src/pgen/linear_wave.cpp:43-51)
+  struct {
+    bool set = false;
+    int wave_flag = 0;
+    double amp = 0, vflow = 0, sin_a2 = 0, cos_a2 = 1, sin_a3 = 0, cos_a3 = 1, lambda = 1, k_par = 1,
+           d0 = 1, p0 = 1, u0 = 0, gm1 = 1, tlim_period = 1;
+    double ev[5], rem[5][5];
+  } lw_;
+  void LinearWaveSetup(const std::vector<double> &pars);
+  void LinearWaveState(const BlockInfo &B, int k, int j, int i, double u[5]) const;
+  Real new_dt_ = std::numeric_limits<Real>::max();
+};
+
+}  // namespace apk_host
+#endif

@@ -1,0 +1,151 @@
+// sim_capi.cpp -- flat C interface of the host driver (HydroSim) for tests/bench bindings.
+// Declared in include/apk_b200_sim.h.
+#include <cstring>
+#include <exception>
+#include <string>
+#include <vector>
+
+#include "../../include/apk_b200_sim.h"
+#include "hydro_sim.hpp"
+
+using apk_host::HydroSim;
+using apk_host::SimConfig;
+
+namespace {
+thread_local std::string g_sim_err;
+template <class F>
+int guarded(F &&f) {
+  try {
+    return f();
+  } catch (const std::exception &e) {
+    g_sim_err = e.what();
+    return -100;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+const char *apk_sim_last_error(void) { return g_sim_err.c_str(); }
+
+void apk_sim_default_config(apk_sim_config_t *c) {
+  SimConfig d;
+  std::memset(c, 0, sizeof(*c));
+  c->fluid = d.fluid; c->recon = d.recon; c->riemann = d.riemann; c->integrator = d.integrator;
+  for (int i = 0; i < 3; ++i) { c->nx[i] = 1; c->mb[i] = 1; c->xmin[i] = -0.5; c->xmax[i] = 0.5; }
+  c->ng = d.ng; c->gamma = d.gamma; c->cfl = d.cfl;
+  c->dfloor = d.dfloor; c->pfloor = d.pfloor; c->efloor = d.efloor;
+  c->vceil = d.vceil; c->eceil = d.eceil;
+  c->glmmhd_alpha = d.glmmhd_alpha; c->fp_mode = d.fp_mode; c->fused = d.fused;
+  c->rank = 0; c->nranks = 1;
+}
+
+apk_sim_t *apk_sim_create(const apk_sim_config_t *c) {
+  HydroSim *s = nullptr;
+  guarded([&] {
+    SimConfig k;
+    k.fluid = c->fluid; k.recon = c->recon; k.riemann = c->riemann; k.integrator = c->integrator;
+    for (int i = 0; i < 3; ++i) { k.nx[i] = c->nx[i]; k.mb[i] = c->mb[i]; k.xmin[i] = c->xmin[i]; k.xmax[i] = c->xmax[i]; }
+    for (int i = 0; i < 6; ++i) k.bc[i] = c->bc[i];
+    k.ng = c->ng; k.gamma = c->gamma; k.cfl = c->cfl;
+    k.dfloor = c->dfloor; k.pfloor = c->pfloor; k.efloor = c->efloor; k.vceil = c->vceil; k.eceil = c->eceil;
+    k.fofc = c->fofc; k.dedner_extended = c->dedner_extended; k.glmmhd_alpha = c->glmmhd_alpha;
+    k.nscalars = c->nscalars; k.fp_mode = c->fp_mode; k.fused = c->fused;
+    k.rank = c->rank; k.nranks = c->nranks;
+    s = new HydroSim(k);
+    return 0;
+  });
+  return reinterpret_cast<apk_sim_t *>(s);
+}
+
+void apk_sim_destroy(apk_sim_t *s) { delete reinterpret_cast<HydroSim *>(s); }
+
+#define SIM(s) (reinterpret_cast<HydroSim *>(s))
+
+int apk_sim_nccl_unique_id(void *out, int nbytes) { return HydroSim::CommUniqueId(out, nbytes); }
+int apk_sim_init_comm(apk_sim_t *s, const void *uid, int nbytes) {
+  return guarded([&] { return SIM(s)->InitComm(uid, nbytes); });
+}
+int apk_sim_pgen(apk_sim_t *s, const char *id, const double *pars, int npars) {
+  return guarded([&] {
+    return SIM(s)->ProblemGenerator(id, std::vector<double>(pars, pars + (pars ? npars : 0)));
+  });
+}
+int apk_sim_initialize(apk_sim_t *s, double tlim) {
+  return guarded([&] { SIM(s)->Initialize(tlim); return 0; });
+}
+int apk_sim_execute(apk_sim_t *s, double tlim, int nlim) {
+  int n = -1;
+  int rc = guarded([&] { n = SIM(s)->Execute(tlim, nlim); return 0; });
+  return rc ? rc : n;
+}
+int apk_sim_step(apk_sim_t *s) {
+  return guarded([&] {
+    HydroSim *h = SIM(s);
+    h->PreStepMeshUserWorkInLoop();
+    if (h->Step() != apk_host::TaskStatus::complete) return -1;
+    h->tm.ncycle++;
+    h->tm.time += h->tm.dt;
+    h->SetGlobalTimeStep();
+    return 0;
+  });
+}
+int apk_sim_num_local_blocks(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->NumLocalBlocks(); }
+int apk_sim_num_global_blocks(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->NumGlobalBlocks(); }
+int apk_sim_nvar(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->nvar(); }
+void apk_sim_block_dims(const apk_sim_t *s, int *n3) {
+  const int *n = SIM(const_cast<apk_sim_t *>(s))->dims();
+  n3[0] = n[0]; n3[1] = n[1]; n3[2] = n[2];
+}
+void apk_sim_block_info(const apk_sim_t *s, int b, int *gid, int *loc3, double *xmin3, double *dx3) {
+  const auto &B = SIM(const_cast<apk_sim_t *>(s))->Block(b);
+  *gid = B.gid;
+  for (int d = 0; d < 3; ++d) { loc3[d] = B.loc[d]; xmin3[d] = B.xmin[d]; dx3[d] = B.dx[d]; }
+}
+int apk_sim_copy_to_host(apk_sim_t *s, int field, int block, double *dst) {
+  return guarded([&] { return SIM(s)->CopyToHost(field, block, dst); });
+}
+int apk_sim_copy_from_host(apk_sim_t *s, int field, int block, const double *src) {
+  return guarded([&] { return SIM(s)->CopyFromHost(field, block, src); });
+}
+void *apk_sim_device_ptr(apk_sim_t *s, int field, int block) { return SIM(s)->DevicePtr(field, block); }
+double apk_sim_time(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->tm.time; }
+double apk_sim_dt(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->tm.dt; }
+int apk_sim_ncycle(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->tm.ncycle; }
+double apk_sim_c_h(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->c_h; }
+long long apk_sim_fofc_corrections(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->fofc_corrections; }
+int apk_sim_fused_active(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->FusedActive() ? 1 : 0; }
+double apk_sim_linear_wave_period(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->LinearWavePeriod(); }
+int apk_sim_linear_wave_errors(apk_sim_t *s, double *out6) {
+  return guarded([&] { SIM(s)->LinearWaveErrors(out6); return 0; });
+}
+void *apk_sim_stream(apk_sim_t *s) { return SIM(s)->stream(); }
+const void *apk_sim_pack_desc(const apk_sim_t *s) { return &SIM(const_cast<apk_sim_t *>(s))->desc(); }
+const void *apk_sim_device_blocks(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->d_blocks(); }
+int apk_sim_synchronize(apk_sim_t *s) {
+  return guarded([&] { SIM(s)->Synchronize(); return 0; });
+}
+/* run individual tasks of one stage (for task-level parity tests) */
+int apk_sim_task(apk_sim_t *s, const char *name, int stage, double g0, double g1, double bdt) {
+  return guarded([&] {
+    HydroSim *h = SIM(s);
+    const std::string n(name);
+    using apk_host::TaskStatus;
+    TaskStatus st = TaskStatus::fail;
+    if (n == "init_u1") st = h->InitU1();
+    else if (n == "calc_flux") st = h->CalculateFluxes(stage);
+    else if (n == "first_order_flux_correct") st = h->FirstOrderFluxCorrect(g0, g1, bdt);
+    else if (n == "update") st = h->UpdateWithFluxDivergence(g0, g1, bdt);
+    else if (n == "source_unsplit") st = h->AddUnsplitSources(bdt);
+    else if (n == "exchange") {
+      h->SendBoundBufs(false); h->ReceiveBoundBufs(); h->SetBounds(false);
+      st = h->ApplyBoundaryConditions(false);
+    } else if (n == "fill_derived") st = h->FillDerived();
+    else if (n == "pre_step") { h->PreStepMeshUserWorkInLoop(); st = TaskStatus::complete; }
+    h->Synchronize();
+    return st == TaskStatus::complete ? 0 : -1;
+  });
+}
+void apk_sim_set_c_h(apk_sim_t *s, double c_h, double mindx) { SIM(s)->c_h = c_h; SIM(s)->mindx = mindx; }
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+/* apk_b200.h -- C-ABI of the B200-native AthenaPK hot path (libapk_b200.so).
+ *
+ * Drop-in boundary: every entry point below replaces one task/kernel that AthenaPK's
+ * HydroDriver schedules per stage (hydro_driver.cpp:499-613 of the reference).  Plain
+ * pointers and sizes only: no C++/torch/Kokkos types cross this boundary.  All work is
+ * stream-ordered on the cudaStream_t passed in (as void*, 0 = default stream), no hidden
+ * device synchronisation except where the reference itself blocks on a reduction
+ * (apk_min_dt, apk_first_order_flux_correct).  Return value: 0 = ok, non-zero = error
+ * (apk_last_error() gives the text); the Parthenon-side shim maps non-zero to
+ * PARTHENON_FAIL.
+ *
+ * Ownership: the caller (Parthenon) owns every field array; the library never allocates,
+ * frees or retains field memory.  apk_block_t arrays live in DEVICE memory.
+ *
+ * file:line cites are relative to the reference tree (parthenon-hpc-lab/athenapk).
+ */
+#ifndef APK_B200_H_
+#define APK_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APK_ABI_VERSION 1
+
+/* src/main.hpp:19-50 (enum values are ours; the shim translates) */
+enum { APK_FLUID_EULER = 0, APK_FLUID_GLMMHD = 1 };
+enum { APK_RECON_DC = 0, APK_RECON_PLM = 1, APK_RECON_PPM = 2, APK_RECON_WENOZ = 3,
+       APK_RECON_WENO3 = 4, APK_RECON_LIMO3 = 5 };
+enum { APK_RIEMANN_NONE = 0, APK_RIEMANN_HLLE = 1, APK_RIEMANN_LLF = 2, APK_RIEMANN_HLLC = 3,
+       APK_RIEMANN_HLLD = 4 };
+enum { APK_BC_PERIODIC = 0, APK_BC_OUTFLOW = 1, APK_BC_REFLECT = 2, APK_BC_BLOCK = 3 };
+/* floating-point contract of the kernels */
+enum { APK_FP_FAST = 0,   /* FMA contraction on (what nvcc/Kokkos-CUDA does by default) */
+       APK_FP_STRICT = 1  /* -fmad=false: bit-identical to the reference's CPU (serial) build */
+};
+
+/* neighbour table entry kinds for apk_block_t.nbr[] (27 entries, index (o3+1)*9+(o2+1)*3+(o1+1)) */
+#define APK_NBR_NONE (-1)        /* no same-level neighbour: physical boundary or unused dim */
+#define APK_NBR_REMOTE(slot) (-2 - (slot)) /* neighbour lives on another GPU: halo slot index */
+
+/* One meshblock.  Field arrays are C-order [nvar][n3][n2][n1] with n* = nx* + 2*ng (1 in a
+ * symmetry direction), exactly Parthenon's ParArrayND layout (variable_pack.hpp).
+ * flux[d] has the same extents; entry (n,k,j,i) is the flux through the LOWER d-face of cell
+ * (k,j,i) (hydro.cpp:1025-1208, metadata.cpp:174-205). */
+typedef struct apk_block {
+  double *cons;      /* "cons" of register base (u0)                       */
+  double *prim;      /* "prim" of register base                            */
+  double *cons_u1;   /* "cons" of register u1 (hydro_driver.cpp:474-495)   */
+  double *flux[3];   /* bnd_flux::cons; may be NULL when only fused stages are used */
+  double dx[3];      /* coords.Dxc<d>()  (uniform_coordinates.hpp:32-40)   */
+  double xmin[3];    /* coords.Xf<d>(0): position of the first (ghost) face */
+  int nbr[27];       /* same-level neighbour block index on THIS device, APK_NBR_NONE or
+                        APK_NBR_REMOTE(slot)                               */
+  int bc[6];         /* per-face flag ix1,ox1,ix2,ox2,ix3,ox3: APK_BC_* (APK_BC_BLOCK = interior
+                        or periodic face handled by the neighbour table)   */
+} apk_block_t;
+
+/* One MeshBlockPack (mesh/meshblock_pack.hpp:35-91): what the kernels need to know */
+typedef struct apk_pack_desc {
+  int nblocks;
+  int nvar;      /* nhydro + nscalars (5 / 9 + nscalars)                   */
+  int nscalars;  /* hydro/nscalars, hydro.cpp:741-742                      */
+  int nx[3];     /* interior cells per block                               */
+  int ng;        /* parthenon/mesh/nghost                                  */
+  int ndim;
+  int fluid;     /* APK_FLUID_*                                            */
+  int recon;     /* APK_RECON_*   (hydro/reconstruction)                   */
+  int riemann;   /* APK_RIEMANN_* (hydro/riemann)                          */
+  int fp_mode;   /* APK_FP_*                                               */
+  double gamma;  /* hydro/gamma                                            */
+  double dfloor, pfloor, efloor; /* <= 0 disables (hydro.cpp:507-523)      */
+  double vceil, eceil;           /* +inf disables (hydro.cpp:525-537)      */
+} apk_pack_desc_t;
+
+const char *apk_last_error(void);
+int apk_abi_version(void);
+/* number of kernel launches issued by this library since load / since reset (bench evidence) */
+long long apk_launch_count(void);
+void apk_reset_launch_count(void);
+
+/* ---- Hydro::CalculateFluxes<fluid,recon,riemann> (src/hydro/hydro.cpp:1025-1208, FluxFun_t
+ * src/hydro/hydro.hpp:43-46) and CalculateFluxesTight (DC+LLF, hydro.cpp:980-1022).
+ * Reads prim (ghosts valid), writes flux[0..ndim-1] over the reference's loop ranges.
+ * recon_override >= 0 replaces desc->recon (VL2 predictor uses DC, hydro.cpp:459-464). */
+int apk_calc_fluxes(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, double c_h,
+                    int recon_override, void *stream);
+
+/* ---- Hydro::FirstOrderFluxCorrect<fluid> (src/hydro/hydro.cpp:1223-1342).
+ * Jacobi variant (all cells of one attempt test the fluxes of the previous attempt; the
+ * reference's serial build is Gauss-Seidel in (b,k,j,i) order and its CUDA build is racy, see
+ * DESIGN.md).  Blocks the host per attempt like the reference.  d_work: device scratch of
+ * apk_fofc_workspace_bytes().  n_corrected (host) receives the total number of corrections. */
+size_t apk_fofc_workspace_bytes(const apk_pack_desc_t *desc);
+int apk_first_order_flux_correct(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                                 double gam0, double gam1, double beta_dt, double c_h,
+                                 void *d_work, long long *n_corrected, void *stream);
+
+/* ---- parthenon::Update::UpdateWithFluxDivergence<MeshData> (interface/update.cpp:115-141,
+ * FluxDivHelper update.hpp:42-56): u0 = gam0*u0 + gam1*u1 + beta_dt*(-div F) on interior cells */
+int apk_flux_div_update(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, double gam0,
+                        double gam1, double beta_dt, void *stream);
+
+/* ---- GLMMHD::DednerSource<extended> (src/hydro/glmmhd/dedner_source.cpp:17-75); the damping
+ * coefficient exp(-alpha*c_h*beta_dt/mindx) is evaluated on the host like the reference */
+int apk_dedner_source(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, double c_h,
+                      double mindx, double alpha, double beta_dt, int extended, void *stream);
+
+/* ---- EOS::ConservedToPrimitive (src/eos/adiabatic_{hydro,glmmhd}.cpp:33-56; cell kernels
+ * adiabatic_hydro.hpp:51-142, adiabatic_glmmhd.hpp:61-167) over the ENTIRE index range.
+ * d_status (device int, may be NULL): set to 1/2 on negative density/pressure without floor
+ * (the reference aborts via PARTHENON_REQUIRE). */
+int apk_cons_to_prim(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, int *d_status,
+                     void *stream);
+
+/* ---- Hydro::EstimateHyperbolicTimestep<fluid> (src/hydro/hydro.cpp:828-910): returns
+ * cfl * min over interior cells/dirs of dx/(|v|+c) in *h_dt (blocking, like the reference's
+ * parallel_reduce to a host value).  d_work: device scratch of >= 8 bytes. */
+int apk_min_dt(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, double cfl,
+               void *d_work, double *h_dt, void *stream);
+/* non-blocking variant: leaves min dx/(|v|+c) (without cfl) in d_out[0] (device) */
+int apk_min_dt_async(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, double *d_out,
+                     void *stream);
+
+/* ---- same-device part of parthenon::AddBoundaryExchangeTasks (bvals/comms/
+ * boundary_communication.cpp:48-348, bnd_info.cpp:105-230) + physical boundary conditions
+ * (bvals/boundary_conditions.cpp:36-59, boundary_conditions_generic.hpp:174-262,
+ * src/bvals/boundary_conditions_apk.hpp:38-85): fills the ghost cells of `cons` straight
+ * from the neighbour block's interior (no pack->buffer->unpack round trip), then applies
+ * outflow/reflecting BCs in face order (= apk_copy_ghosts_local + apk_apply_physical_bcs).
+ * with_prim != 0 additionally copies `prim` (valid
+ * because cons->prim is pointwise) so no ghost cons->prim pass is needed. */
+int apk_fill_ghosts_local(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                          unsigned bc_face_mask, int with_prim, void *stream);
+/* physical BCs only (after apk_halo_unpack of remote neighbours); bit f of bc_face_mask set
+ * = some block of the pack has an outflow/reflecting BC on face f (ix1,ox1,ix2,ox2,ix3,ox3) */
+int apk_apply_physical_bcs(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                           unsigned bc_face_mask, int with_prim, void *stream);
+/* neighbour copies only (no BCs) */
+int apk_copy_ghosts_local(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                          int with_prim, void *stream);
+
+/* ---- remote part of the exchange: pack all outgoing (block,neighbour) slabs of one peer
+ * into ONE contiguous send buffer / unpack one contiguous receive buffer (replaces
+ * SendBoundBufs/SetBounds per-buffer kernels + per-buffer MPI messages,
+ * boundary_communication.cpp:95-140,273-334; utils/communication_buffer.hpp:209-236).
+ * d_items: device array of apk_halo_item_t describing each slab. */
+typedef struct apk_halo_item {
+  int block;      /* local block index                                  */
+  int lo[3];      /* first cell (i,j,k) of the slab in the block array   */
+  int ext[3];     /* slab extents (i,j,k)                                */
+  long long offset; /* offset (in doubles) of this slab in the peer buffer */
+} apk_halo_item_t;
+int apk_halo_pack(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                  const apk_halo_item_t *d_items, int nitems, int with_prim, double *d_buf,
+                  void *stream);
+int apk_halo_unpack(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                    const apk_halo_item_t *d_items, int nitems, int with_prim,
+                    const double *d_buf, void *stream);
+
+/* ---- fused stage: calc_flux -> flux divergence update -> Dedner source -> cons->prim of the
+ * interior cells (+ optional dt reduction on the last stage) without materialising fluxes
+ * (K1-K3+K6+K7+K10(+K11) of SURVEY.md 2.3).  Legal only when nothing else consumes cons.flux
+ * (no FOFC, no AMR flux correction, no unsplit diffusion; hydro_driver.cpp:517-531).
+ * Reads prim_in (= block.prim), cons (u0), cons_u1; writes cons (interior) and prim_out.
+ * prim_out[b] may not alias prim (neighbouring tiles still read it); d_prim_out is a device
+ * array of nblocks pointers.  d_dtmin (device, may be NULL) accumulates min dx/(|v|+c). */
+int apk_stage_fused(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                    double *const *d_prim_out, double gam0, double gam1, double beta_dt,
+                    double c_h, double mindx, double alpha, int recon_override,
+                    double *d_dtmin, void *stream);
+
+/* copy cons -> cons_u1 for all blocks (u1 <- u0 at stage 1, hydro_driver.cpp:474-495) */
+int apk_save_u1(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, void *stream);
+
+/* FP64 pipe microbenchmark (roofline evidence): runs n_iter dependent-chain-free DFMAs per
+ * thread, returns measured FLOP count in *flops; time it with CUDA events from the caller */
+int apk_fp64_probe(int n_blocks, int n_threads, int n_iter, double *d_out, double *flops,
+                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APK_B200_H_ */

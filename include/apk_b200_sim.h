@@ -1,0 +1,69 @@
+/* apk_b200_sim.h -- flat C interface of the host-side driver mirror (athenapk_b200/host):
+ * a HydroDriver-equivalent time loop (src/hydro/hydro_driver.cpp:347-673,
+ * external/parthenon/src/driver/driver.cpp:67-242) built on the task-level C-ABI of
+ * apk_b200.h.  Used by tests/bench through ctypes; a Parthenon integration does not need it
+ * (it keeps its own driver and calls apk_b200.h directly). */
+#ifndef APK_B200_SIM_H_
+#define APK_B200_SIM_H_
+
+#include "apk_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct apk_sim apk_sim_t;
+
+/* input-deck values (docs/input.md): <parthenon/mesh>, <parthenon/meshblock>,
+ * <parthenon/time>, <hydro> */
+typedef struct apk_sim_config {
+  int fluid, recon, riemann, integrator; /* integrator: 0 rk1, 1 rk2, 2 vl2, 3 rk3 */
+  int nx[3], mb[3], ng, bc[6];
+  double xmin[3], xmax[3];
+  double gamma, cfl;
+  double dfloor, pfloor, efloor, vceil, eceil;
+  int fofc, dedner_extended;
+  double glmmhd_alpha;
+  int nscalars;
+  int fp_mode; /* APK_FP_FAST / APK_FP_STRICT */
+  int fused;   /* use the fused stage kernel when legal */
+  int rank, nranks;
+} apk_sim_config_t;
+
+const char *apk_sim_last_error(void);
+void apk_sim_default_config(apk_sim_config_t *c);
+apk_sim_t *apk_sim_create(const apk_sim_config_t *c);
+void apk_sim_destroy(apk_sim_t *s);
+int apk_sim_nccl_unique_id(void *out, int nbytes);
+int apk_sim_init_comm(apk_sim_t *s, const void *uid, int nbytes);
+int apk_sim_pgen(apk_sim_t *s, const char *id, const double *pars, int npars);
+int apk_sim_initialize(apk_sim_t *s, double tlim);
+int apk_sim_execute(apk_sim_t *s, double tlim, int nlim); /* returns #cycles or <0 */
+int apk_sim_step(apk_sim_t *s);
+int apk_sim_num_local_blocks(const apk_sim_t *s);
+int apk_sim_num_global_blocks(const apk_sim_t *s);
+int apk_sim_nvar(const apk_sim_t *s);
+void apk_sim_block_dims(const apk_sim_t *s, int *n3);
+void apk_sim_block_info(const apk_sim_t *s, int b, int *gid, int *loc3, double *xmin3, double *dx3);
+int apk_sim_copy_to_host(apk_sim_t *s, int field, int block, double *dst);
+int apk_sim_copy_from_host(apk_sim_t *s, int field, int block, const double *src);
+void *apk_sim_device_ptr(apk_sim_t *s, int field, int block);
+double apk_sim_time(const apk_sim_t *s);
+double apk_sim_dt(const apk_sim_t *s);
+int apk_sim_ncycle(const apk_sim_t *s);
+double apk_sim_c_h(const apk_sim_t *s);
+long long apk_sim_fofc_corrections(const apk_sim_t *s);
+int apk_sim_fused_active(const apk_sim_t *s);
+double apk_sim_linear_wave_period(const apk_sim_t *s);
+int apk_sim_linear_wave_errors(apk_sim_t *s, double *out6);
+void *apk_sim_stream(apk_sim_t *s);
+const void *apk_sim_pack_desc(const apk_sim_t *s);
+const void *apk_sim_device_blocks(const apk_sim_t *s);
+int apk_sim_synchronize(apk_sim_t *s);
+int apk_sim_task(apk_sim_t *s, const char *name, int stage, double g0, double g1, double bdt);
+void apk_sim_set_c_h(apk_sim_t *s, double c_h, double mindx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

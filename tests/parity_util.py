@@ -1,0 +1,67 @@
+"""Helpers shared by the GPU parity tests: run the same deck through the CUDA product
+(athenapk_b200.HydroSim, via the C-ABI) and through the CPU oracle, and compare."""
+import numpy as np
+
+from oracle_lib import Oracle
+
+SIM_ONLY = {"fp_mode", "fused", "rank", "nranks"}
+ORACLE_ONLY = {"fofc_jacobi"}
+
+
+def make_pair(apk, pgen="random", pgen_pars=(), tlim=float("inf"), **kw):
+    okw = {k: v for k, v in kw.items() if k not in SIM_ONLY}
+    skw = {k: v for k, v in kw.items() if k not in ORACLE_ONLY}
+    o = Oracle(**okw)
+    s = apk.HydroSim(**skw)
+    o.pgen(pgen, pgen_pars)
+    s.pgen(pgen, pgen_pars)
+    if pgen == "linear_wave" and tlim is None:
+        tlim = o.lw_tlim
+    o.initialize(tlim)
+    s.initialize(tlim)
+    return s, o
+
+
+def oracle_block(s, o, b):
+    loc = s.block_info(b)[1]
+    nb = [o.p.nx[d] // o.p.mb[d] for d in range(3)]
+    return loc[0] + nb[0] * (loc[1] + nb[1] * loc[2])
+
+
+def max_abs_diff(s, o, fields=("cons", "prim")):
+    worst = 0.0
+    for b in range(s.nblocks):
+        ob = oracle_block(s, o, b)
+        for f in fields:
+            ref = o.cons(ob) if f == "cons" else o.prim(ob)
+            worst = max(worst, float(np.max(np.abs(s.get(f, b) - ref))))
+    return worst
+
+
+def rel_l1(s, o, field="cons"):
+    """relative L1 difference per variable, max over variables (interior + ghosts)"""
+    num = None
+    den = None
+    for b in range(s.nblocks):
+        ob = oracle_block(s, o, b)
+        ref = o.cons(ob) if field == "cons" else o.prim(ob)
+        got = s.get(field, b)
+        n = np.abs(got - ref).reshape(ref.shape[0], -1).sum(axis=1)
+        d = np.abs(ref).reshape(ref.shape[0], -1).sum(axis=1)
+        num = n if num is None else num + n
+        den = d if den is None else den + d
+    scale = max(float(den.max()), 1e-300)
+    return float(np.max(num / np.maximum(den, 1e-8 * scale)))
+
+
+def assert_bitexact(s, o, what=""):
+    for b in range(s.nblocks):
+        ob = oracle_block(s, o, b)
+        for f in ("cons", "prim"):
+            ref = o.cons(ob) if f == "cons" else o.prim(ob)
+            got = s.get(f, b)
+            if not np.array_equal(got, ref):
+                bad = np.argwhere(got != ref)
+                raise AssertionError("%s: %s differs in block %d at %d entries, first %s: %r vs %r"
+                                     % (what, f, b, len(bad), tuple(bad[0]), got[tuple(bad[0])],
+                                        ref[tuple(bad[0])]))

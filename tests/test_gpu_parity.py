@@ -1,0 +1,282 @@
+"""GPU parity tests (run on the B200 box): the CUDA hot path, called through the C-ABI / host
+driver, against the CPU oracle on the same seeded inputs.
+
+Bar: BIT-EXACT in APK_FP_STRICT mode (-fmad=false kernels vs the no-FMA CPU restatement, which is
+itself pinned to the reference); in APK_FP_FAST mode (FMA contraction, what the reference's own
+Kokkos-CUDA build does) <= 1e-12 relative L1 on the linear wave and <= 1e-6 on MHD problems
+(BASELINE.json north_star)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from parity_util import assert_bitexact, make_pair, max_abs_diff, oracle_block, rel_l1
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_scalars.json")))
+
+
+@pytest.fixture(scope="module")
+def apk():
+    import athenapk_b200 as m
+    m.lib()
+    return m
+
+
+BOX3 = dict(xmin=(0.0, 0.0, 0.0), xmax=(1.0, 1.0, 1.0))
+
+# every (fluid, recon, riemann) the reference registers (hydro.cpp:386-420), 3-D multi-block
+COMBOS = [("euler", r, s, 3 if r in ("ppm", "wenoz") else 2)
+          for r in ("dc", "plm", "ppm", "wenoz", "weno3", "limo3") for s in ("hlle", "hllc")]
+COMBOS += [("glmmhd", r, s, 3 if r in ("ppm", "wenoz") else 2)
+           for r in ("dc", "plm", "ppm", "wenoz", "weno3", "limo3") for s in ("hlle", "hlld")]
+COMBOS += [("euler", "dc", "llf", 2), ("glmmhd", "dc", "llf", 2), ("euler", "dc", "none", 2),
+           ("glmmhd", "dc", "none", 2)]
+
+
+@pytest.mark.parametrize("fluid,recon,riemann,ng", COMBOS)
+def test_flux_arrays_bitexact(apk, fluid, recon, riemann, ng):
+    """apk_calc_fluxes vs CalculateFluxes restatement: whole flux arrays incl. the reference's
+    over-computed transverse ghost faces."""
+    s, o = make_pair(apk, "random", (3, 0.3), fluid=fluid, recon=recon, riemann=riemann, ng=ng,
+                     nx=(16, 12, 8), mb=(8, 6, 4), integrator="rk2", fp_mode="strict",
+                     fused=False, **BOX3)
+    o.L.apko_set_c_h(o.h, 1.7)
+    s.set_c_h(1.7, 0.1)
+    o.L.apko_calc_fluxes(o.h, o.p.recon)
+    s.task("calc_flux", stage=2)
+    for b in range(s.nblocks):
+        ob = oracle_block(s, o, b)
+        for d in range(3):
+            assert np.array_equal(s.get("flux%d" % (d + 1), b), o.flux(ob, d)), (b, d)
+    s.close()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("fluid,recon,riemann,integrator,ng", [
+    ("euler", "plm", "hlle", "rk2", 2), ("euler", "plm", "hllc", "vl2", 2),
+    ("euler", "ppm", "hlle", "rk3", 3), ("euler", "wenoz", "hllc", "rk3", 3),
+    ("euler", "weno3", "hlle", "rk1", 2), ("euler", "limo3", "hllc", "vl2", 2),
+    ("glmmhd", "plm", "hlle", "vl2", 2), ("glmmhd", "ppm", "hlld", "vl2", 3),
+    ("glmmhd", "wenoz", "hlld", "rk3", 3), ("glmmhd", "limo3", "hlld", "rk2", 2),
+])
+def test_cycles_bitexact_3d(apk, fused, fluid, recon, riemann, integrator, ng):
+    """3 full cycles (all stages, ghost exchange over 2x2x2 periodic meshblocks, Dedner source,
+    cons->prim, dt) in strict mode == oracle, bit for bit, incl. time and dt."""
+    s, o = make_pair(apk, "random", (11, 0.2), fluid=fluid, recon=recon, riemann=riemann,
+                     integrator=integrator, ng=ng, nx=(32, 16, 16), mb=(16, 8, 8),
+                     fp_mode="strict", fused=fused, **BOX3)
+    assert s.fused_active == fused
+    assert_bitexact(s, o, "after init")
+    assert s.dt == o.dt
+    o.run(None, 3)
+    s.execute(None, 3)
+    assert (s.ncycle, s.time, s.dt) == (o.ncycle, o.time, o.dt)
+    assert_bitexact(s, o, "after 3 cycles")
+    s.close()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("nx,mb", [((64, 1, 1), (16, 1, 1)), ((24, 20, 1), (12, 10, 1)),
+                                   ((40, 12, 1), (40, 12, 1)), ((36, 10, 6), (36, 10, 6))])
+def test_dimensionality_and_ragged_tiles(apk, fused, nx, mb):
+    """1-D / 2-D decks and block sizes that are not multiples of the 32x8 tile."""
+    for fluid, recon, riemann in (("euler", "plm", "hllc"), ("glmmhd", "ppm", "hlld")):
+        s, o = make_pair(apk, "random", (5, 0.25), fluid=fluid, recon=recon, riemann=riemann,
+                         integrator="vl2", ng=3, nx=nx, mb=mb, fp_mode="strict", fused=fused,
+                         **BOX3)
+        o.run(None, 2)
+        s.execute(None, 2)
+        assert (s.time, s.dt) == (o.time, o.dt)
+        assert_bitexact(s, o, "%s %s" % (fluid, nx))
+        s.close()
+
+
+@pytest.mark.parametrize("bc", ["outflow", "reflecting"])
+def test_physical_boundaries(apk, bc):
+    """outflow / reflecting BCs (GenericBC, ReflectBC) incl. corner fill order, 2x2 blocks."""
+    for fused in (False, True):
+        s, o = make_pair(apk, "blast", (0.2, 0.1, 20.0, 1.0), fluid="euler", recon="plm",
+                         riemann="hllc", integrator="vl2", ng=2, nx=(32, 32, 1), mb=(16, 16, 1),
+                         bc=[bc] * 4 + ["periodic"] * 2, xmin=(-0.5, -0.5, -0.5),
+                         xmax=(0.5, 0.5, 0.5), gamma=1.4, fp_mode="strict", fused=fused)
+        o.run(None, 12)
+        s.execute(None, 12)
+        assert (s.time, s.dt) == (o.time, o.dt)
+        assert_bitexact(s, o, bc)
+        s.close()
+
+
+def test_extended_dedner_and_scalars_unfused(apk):
+    s, o = make_pair(apk, "random", (2, 0.2), fluid="glmmhd", recon="plm", riemann="hlld",
+                     integrator="vl2", ng=2, nx=(16, 16, 16), mb=(8, 8, 8), dedner_extended=True,
+                     nscalars=2, fp_mode="strict", **BOX3)
+    assert not s.fused_active
+    o.run(None, 3)
+    s.execute(None, 3)
+    assert (s.time, s.dt) == (o.time, o.dt)
+    assert_bitexact(s, o, "extended dedner + scalars")
+    s.close()
+
+
+def test_floors_and_ceilings(apk):
+    kw = dict(fluid="glmmhd", recon="plm", riemann="hlle", integrator="rk2", ng=2,
+              nx=(16, 16, 16), mb=(8, 8, 8), dfloor=0.9, pfloor=0.95, vceil=0.15, **BOX3)
+    for fused in (False, True):
+        s, o = make_pair(apk, "random", (8, 0.3), fp_mode="strict", fused=fused, **kw)
+        o.run(None, 2)
+        s.execute(None, 2)
+        assert_bitexact(s, o, "floors")
+        s.close()
+
+
+def test_first_order_flux_correct_jacobi(apk):
+    """FOFC on a strong blast: identical to the oracle's Jacobi ordering (see DESIGN.md for the
+    reference's serial Gauss-Seidel vs racy CUDA behaviour)."""
+    kw = dict(fluid="glmmhd", recon="ppm", riemann="hlld", integrator="vl2", ng=3,
+              nx=(32, 32, 1), mb=(16, 16, 1), fofc=True, xmin=(-0.5,) * 3, xmax=(0.5,) * 3)
+    s, o = make_pair(apk, "blast", (0.1, 0.01, 1.0e4, 1.0), fp_mode="strict", fofc_jacobi=True, **kw)
+    o.run(None, 10)
+    s.execute(None, 10)
+    assert s.fofc_corrections > 0
+    assert (s.time, s.dt) == (o.time, o.dt)
+    assert_bitexact(s, o, "fofc")
+    s.close()
+
+
+# ---------------------------------------------------------------- golden known answers
+def _lw(apk, N, row, **kw):
+    s = apk.HydroSim(nx=(2 * N, N, N), fluid=row["fluid"], integrator=row["integrator"],
+                     recon=row["recon"], riemann=row["riemann"], ng=row["ng"], **kw)
+    s.pgen("linear_wave", [0, 1e-6, 0.0])
+    s.initialize(s.lw_tlim)
+    s.execute(s.lw_tlim, 100000)
+    return s
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("row", GOLD["linear_wave_rms_l1"],
+                         ids=lambda r: "-".join([r["fluid"], r["integrator"], r["recon"], r["riemann"]]))
+def test_linear_wave_convergence_table_bitmatch(apk, row, fused):
+    """reference convergence table: 7 printed digits, N=16 and N=32, strict mode"""
+    for N in (16, 32):
+        s = _lw(apk, N, row, fp_mode="strict", fused=fused)
+        assert s.ncycle == GOLD["linear_wave_cycles"]["N%d" % N]
+        assert "%.6e" % s.linear_wave_errors()[0] == row["N%d" % N]
+        s.close()
+
+
+def test_reference_regression_threshold(apk):
+    """tst/regression/test_suites/convergence/convergence.py:163 : 128x64x64 VL2+PLM+HLLE
+    RMS-L1 <= 1.547584e-08 -- both FP modes print the same 7 digits."""
+    row = GOLD["linear_wave_rms_l1"][1]
+    for fp_mode in ("strict", "fast"):
+        s = _lw(apk, 64, row, fp_mode=fp_mode)
+        assert s.ncycle == GOLD["linear_wave_cycles"]["N64"]
+        assert "%.6e" % s.linear_wave_errors()[0] == GOLD["convergence_py_163"]["rms_l1"], fp_mode
+        s.close()
+
+
+def test_mhd_north_star_method_N64(apk):
+    row = GOLD["linear_wave_rms_l1"][6]
+    s = _lw(apk, 64, row, fp_mode="strict")
+    assert "%.6e" % s.linear_wave_errors()[0] == row["N64"]
+    s.close()
+
+
+def test_sod_dt_trace(apk):
+    for fused in (False, True):
+        s = apk.HydroSim(nx=(256, 1, 1), mb=(64, 1, 1), ng=2,
+                         bc=["outflow", "outflow"] + ["periodic"] * 4, xmin=(0.0, -0.5, -0.5),
+                         xmax=(1.0, 0.5, 0.5), gamma=1.4, cfl=0.5, recon="plm", riemann="hllc",
+                         integrator="vl2", fp_mode="strict", fused=fused)
+        s.pgen("sod")
+        s.initialize(0.4)
+        s.execute(0.4, 10000)
+        assert s.ncycle == GOLD["sod_hllc"]["cycles"]
+        assert "%.16e" % s.dt == GOLD["sod_hllc"]["final_dt"]
+        s.close()
+
+
+def test_orszag_tang_50_cycles(apk):
+    """inputs/orszag_tang.in (FOFC on): 17-digit (time, dt) after 50 cycles as printed by the
+    reference."""
+    g = GOLD["orszag_tang_50"]
+    s = apk.HydroSim(fluid="glmmhd", nx=(256, 256, 1), mb=(64, 256, 1), ng=3, xmin=(-0.5,) * 3,
+                     xmax=(0.5,) * 3, gamma=1.666666666666667, cfl=0.4, recon="ppm",
+                     riemann="hlld", integrator="vl2", fofc=True, fp_mode="strict")
+    s.pgen("orszag_tang")
+    s.initialize(1.0)
+    s.execute(1.0, 50)
+    assert "%.16e" % s.time == g["time"]
+    assert "%.16e" % s.dt == g["dt"]
+    s.close()
+    # same deck through the fused kernel (FOFC never triggers in these 50 cycles)
+    s = apk.HydroSim(fluid="glmmhd", nx=(256, 256, 1), mb=(64, 256, 1), ng=3, xmin=(-0.5,) * 3,
+                     xmax=(0.5,) * 3, gamma=1.666666666666667, cfl=0.4, recon="ppm",
+                     riemann="hlld", integrator="vl2", fofc=False, fp_mode="strict")
+    s.pgen("orszag_tang")
+    s.initialize(1.0)
+    s.execute(1.0, 50)
+    assert "%.16e" % s.time == g["time"]
+    assert "%.16e" % s.dt == g["dt"]
+    s.close()
+
+
+# ---------------------------------------------------------------- FMA (default) mode tolerances
+def test_fast_mode_linear_wave_within_1e12(apk):
+    for row in (GOLD["linear_wave_rms_l1"][1], GOLD["linear_wave_rms_l1"][6]):
+        s, o = make_pair(apk, "linear_wave", (0, 1e-6, 0.0), tlim=None, nx=(64, 32, 32),
+                         mb=(32, 16, 16), fluid=row["fluid"], integrator=row["integrator"],
+                         recon=row["recon"], riemann=row["riemann"], ng=row["ng"], fp_mode="fast")
+        o.run(o.lw_tlim, 100000)
+        s.execute(s.lw_tlim, 100000)
+        assert s.ncycle == o.ncycle
+        assert rel_l1(s, o, "cons") <= 1e-12
+        assert abs(s.linear_wave_errors()[0] / o.linear_wave_errors()[0] - 1) < 1e-6
+        s.close()
+
+
+def test_fast_mode_mhd_within_1e6(apk):
+    s, o = make_pair(apk, "ot3d", fluid="glmmhd", recon="ppm", riemann="hlld", integrator="vl2",
+                     ng=3, nx=(64, 64, 64), mb=(32, 32, 32), fp_mode="fast", **BOX3)
+    o.run(None, 20)
+    s.execute(None, 20)
+    assert rel_l1(s, o, "cons") <= 1e-6
+    assert rel_l1(s, o, "prim") <= 1e-6
+    assert abs(s.dt / o.dt - 1) <= 1e-9
+    s.close()
+
+
+# ---------------------------------------------------------------- size-independent properties
+def test_uniform_state_is_static_and_conservation_128(apk):
+    """Config-4 geometry at 128^3 (64 meshblocks of 32^3): the deck's uniform magnetised state is
+    an exact fixed point; a perturbed periodic state conserves mass/momentum/energy/B sums."""
+    kw = dict(fluid="glmmhd", recon="ppm", riemann="hlld", integrator="vl2", ng=3,
+              nx=(128, 128, 128), mb=(32, 32, 32), gamma=1.0001, **BOX3)
+    s = apk.HydroSim(**kw)
+    s.pgen("uniform", [1.0, 1.0, 0.01])
+    s.initialize()
+    before = s.get("cons", 7)
+    s.execute(None, 3)
+    assert np.array_equal(s.get("cons", 7), before)
+    s.close()
+    kw["gamma"] = 5.0 / 3.0
+    s = apk.HydroSim(**kw)
+    s.pgen("ot3d")
+    s.initialize()
+    ng = 3
+
+    def totals():
+        t = np.zeros(s.nvar)
+        for b in range(s.nblocks):
+            t += s.get("cons", b)[:, ng:-ng, ng:-ng, ng:-ng].sum(axis=(1, 2, 3))
+        return t
+    t0 = totals()
+    s.execute(None, 5)
+    t1 = totals()
+    scale = 128.0 ** 3
+    assert np.all(np.abs(t1[:8] - t0[:8]) <= 1e-11 * scale)
+    s.close()
