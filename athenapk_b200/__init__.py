@@ -77,7 +77,8 @@ SIM_SYMBOLS = [
     "apk_sim_ncycle", "apk_sim_c_h", "apk_sim_fofc_corrections", "apk_sim_fused_active",
     "apk_sim_linear_wave_period", "apk_sim_linear_wave_errors", "apk_sim_stream",
     "apk_sim_pack_desc", "apk_sim_device_blocks", "apk_sim_synchronize", "apk_sim_task",
-    "apk_sim_set_c_h",
+    "apk_sim_set_c_h", "apk_sim_upload_all", "apk_sim_download_all",
+    "apk_sim_enable_task_timing", "apk_sim_task_timing",
 ]
 
 _lib = None
@@ -162,6 +163,10 @@ def lib():
         getattr(L, f).restype = vp
     L.apk_sim_task.argtypes = [vp, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_double]
     L.apk_sim_set_c_h.argtypes = [vp, C.c_double, C.c_double]
+    L.apk_sim_upload_all.argtypes = [vp, C.c_int, vp]
+    L.apk_sim_download_all.argtypes = [vp, C.c_int, vp]
+    L.apk_sim_enable_task_timing.argtypes = [vp, C.c_int]
+    L.apk_sim_task_timing.argtypes = [vp, C.c_char_p, dp, C.POINTER(C.c_longlong)]
     _lib = L
     return L
 
@@ -277,6 +282,22 @@ class HydroSim:
 
     def locs(self):
         return [self.block_info(b)[1] for b in range(self.nblocks)]
+
+    def upload_all(self, field, host_ptr):
+        """async H2D of a whole field ([nblocks][nvar][n3][n2][n1] doubles at host_ptr)"""
+        self._chk(self.L.apk_sim_upload_all(self.h, FIELD[field], host_ptr), "upload_all")
+
+    def download_all(self, field, host_ptr):
+        self._chk(self.L.apk_sim_download_all(self.h, FIELD[field], host_ptr), "download_all")
+
+    def enable_task_timing(self, on=True):
+        self.L.apk_sim_enable_task_timing(self.h, int(on))
+
+    def task_timing(self, name):
+        ms, cnt = C.c_double(), C.c_longlong()
+        if self.L.apk_sim_task_timing(self.h, name.encode(), C.byref(ms), C.byref(cnt)) != 0:
+            return 0.0, 0
+        return ms.value, cnt.value
 
     def synchronize(self):
         self._chk(self.L.apk_sim_synchronize(self.h), "sync")

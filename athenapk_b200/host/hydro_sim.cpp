@@ -465,6 +465,56 @@ int HydroSim::CopyToHost(int field, int block, double *dst) {
   return 0;
 }
 
+int HydroSim::UploadAll(int field, const double *src) {
+  double *p = DevicePtr(field, 0);
+  if (!p) return -1;
+  cuda_check(cudaMemcpyAsync(p, src, BlockFieldElems() * blocks_.size() * sizeof(double),
+                             cudaMemcpyHostToDevice, S(stream_)), "H2D all");
+  return 0;
+}
+
+int HydroSim::DownloadAll(int field, double *dst) {
+  double *p = DevicePtr(field, 0);
+  if (!p) return -1;
+  cuda_check(cudaMemcpyAsync(dst, p, BlockFieldElems() * blocks_.size() * sizeof(double),
+                             cudaMemcpyDeviceToHost, S(stream_)), "D2H all");
+  return 0;
+}
+
+bool HydroSim::TaskTiming(const std::string &name, double *ms_total, long long *count) const {
+  auto it = timing_.find(name);
+  if (it == timing_.end()) return false;
+  *ms_total = it->second.ms;
+  *count = it->second.count;
+  return true;
+}
+
+// run a task list with a CUDA event pair around every task (events on the launching stream)
+TaskStatus HydroSim::ExecuteTimed(TaskList &tl) {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evs(tl.tasks.size());
+  for (size_t t = 0; t < tl.tasks.size(); ++t) {
+    cuda_check(cudaEventCreate(&evs[t].first), "event");
+    cuda_check(cudaEventCreate(&evs[t].second), "event");
+    cuda_check(cudaEventRecord(evs[t].first, S(stream_)), "record");
+    TaskStatus st;
+    while ((st = tl.tasks[t].second()) == TaskStatus::incomplete) {
+    }
+    if (st == TaskStatus::fail) return st;
+    cuda_check(cudaEventRecord(evs[t].second, S(stream_)), "record");
+  }
+  Synchronize();
+  for (size_t t = 0; t < tl.tasks.size(); ++t) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, evs[t].first, evs[t].second);
+    auto &T = timing_[tl.tasks[t].first];
+    T.ms += ms;
+    T.count += 1;
+    cudaEventDestroy(evs[t].first);
+    cudaEventDestroy(evs[t].second);
+  }
+  return TaskStatus::complete;
+}
+
 // ================================================================================================
 // Tasks (hydro_driver.cpp:474-613)
 // ================================================================================================
@@ -579,11 +629,6 @@ TaskStatus HydroSim::FillDerived() {  // Update::FillDerived -> ConsToPrim (hydr
   return TaskStatus::complete;
 }
 
-double HydroSim::HostMinDt(double local_min) {
-  if (cfg_.nranks == 1) return local_min;
-  return local_min;
-}
-
 TaskStatus HydroSim::EstimateTimestep(bool have_device_min) {
   // hydro.cpp:828-976 + update.hpp:269-278. have_device_min: the fused last stage already left
   // min dx/(|v|+c) in d_scalars_[0].
@@ -664,7 +709,8 @@ void HydroSim::MakeTaskCollection(TaskList &tl, int stage) {
     // calc_flux + update + source_unsplit + cons2prim(interior) [+ dt reduce] in one kernel;
     // ghosts of cons AND prim are then exchanged together (pointwise cons->prim commutes with
     // the copy), so the separate FillDerived region disappears.
-    tl.AddTask("fused_stage", [=] { return FusedStage(stage, gam0, gam1, beta_dt, last); });
+    tl.AddTask(stage == 1 ? "fused_stage_first" : "fused_stage_other",
+               [=] { return FusedStage(stage, gam0, gam1, beta_dt, last); });
     tl.AddTask("send", [this] { return SendBoundBufs(true); });
     tl.AddTask("recv", [this] { return ReceiveBoundBufs(); });
     tl.AddTask("set", [this] { return SetBounds(true); });
@@ -698,7 +744,7 @@ TaskStatus HydroSim::Step() {  // multistage.hpp:39-53
   for (int stage = 1; stage <= integrator_.nstages; ++stage) {
     TaskList tl;
     MakeTaskCollection(tl, stage);
-    const TaskStatus st = tl.Execute();
+    const TaskStatus st = timing_on_ ? ExecuteTimed(tl) : tl.Execute();
     if (st != TaskStatus::complete) return st;
   }
   if (fused_ && cur_ != 0) {

@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <functional>
 #include <limits>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -100,6 +101,13 @@ class HydroSim {
 
   // ---- data movement (host <-> device), field: 0 cons, 1 prim, 2 u1, 3..5 flux x1..x3 ----
   int CopyFromHost(int field, int block, const double *src);
+  // whole-pack transfers (all local blocks, one contiguous copy; async on the sim stream)
+  int UploadAll(int field, const double *src);
+  int DownloadAll(int field, double *dst);
+  // per-task device timing (CUDA events on the launching stream)
+  void EnableTaskTiming(bool on) { timing_on_ = on; }
+  bool TaskTiming(const std::string &name, double *ms_total, long long *count) const;
+  void ResetTaskTiming() { timing_.clear(); }
   int CopyToHost(int field, int block, double *dst);
   double *DevicePtr(int field, int block);
 
@@ -149,7 +157,6 @@ class HydroSim {
   void BuildNeighbors();
   void BuildHaloPlan();
   void UploadBlocks();
-  double HostMinDt(double local_min);
 
   SimConfig cfg_;
   LowStorageIntegrator integrator_;
@@ -201,6 +208,10 @@ class HydroSim {
   void LinearWaveSetup(const std::vector<double> &pars);
   void LinearWaveState(const BlockInfo &B, int k, int j, int i, double u[5]) const;
   Real new_dt_ = std::numeric_limits<Real>::max();
+  struct Timing { double ms = 0.0; long long count = 0; };
+  std::map<std::string, Timing> timing_;
+  bool timing_on_ = false;
+  TaskStatus ExecuteTimed(TaskList &tl);
 };
 
 }  // namespace apk_host

@@ -108,6 +108,19 @@ int apk_sim_copy_to_host(apk_sim_t *s, int field, int block, double *dst) {
 int apk_sim_copy_from_host(apk_sim_t *s, int field, int block, const double *src) {
   return guarded([&] { return SIM(s)->CopyFromHost(field, block, src); });
 }
+int apk_sim_upload_all(apk_sim_t *s, int field, const double *src) {
+  return guarded([&] { return SIM(s)->UploadAll(field, src); });
+}
+int apk_sim_download_all(apk_sim_t *s, int field, double *dst) {
+  return guarded([&] { return SIM(s)->DownloadAll(field, dst); });
+}
+void apk_sim_enable_task_timing(apk_sim_t *s, int on) {
+  SIM(s)->EnableTaskTiming(on != 0);
+  if (!on) SIM(s)->ResetTaskTiming();
+}
+int apk_sim_task_timing(const apk_sim_t *s, const char *name, double *ms_total, long long *count) {
+  return SIM(const_cast<apk_sim_t *>(s))->TaskTiming(name, ms_total, count) ? 0 : -1;
+}
 void *apk_sim_device_ptr(apk_sim_t *s, int field, int block) { return SIM(s)->DevicePtr(field, block); }
 double apk_sim_time(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->tm.time; }
 double apk_sim_dt(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->tm.dt; }

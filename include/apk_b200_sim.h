@@ -47,6 +47,12 @@ void apk_sim_block_dims(const apk_sim_t *s, int *n3);
 void apk_sim_block_info(const apk_sim_t *s, int b, int *gid, int *loc3, double *xmin3, double *dx3);
 int apk_sim_copy_to_host(apk_sim_t *s, int field, int block, double *dst);
 int apk_sim_copy_from_host(apk_sim_t *s, int field, int block, const double *src);
+/* whole-pack async copies on the sim stream (host buffer: [nblocks][nvar][n3][n2][n1]) */
+int apk_sim_upload_all(apk_sim_t *s, int field, const double *src);
+int apk_sim_download_all(apk_sim_t *s, int field, double *dst);
+/* per-task device time (CUDA events on the launching stream), summed since enabling */
+void apk_sim_enable_task_timing(apk_sim_t *s, int on);
+int apk_sim_task_timing(const apk_sim_t *s, const char *name, double *ms_total, long long *count);
 void *apk_sim_device_ptr(apk_sim_t *s, int field, int block);
 double apk_sim_time(const apk_sim_t *s);
 double apk_sim_dt(const apk_sim_t *s);

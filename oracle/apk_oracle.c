@@ -928,6 +928,7 @@ struct apko_engine {
   int ncycle;
   double c_h, mindx, dt_hyp;
   double new_dt; /* allowed dt voted by the last EstimateTimestep */
+  long long fofc_total;
   /* linear wave pgen state (linear_wave.cpp:43-51) */
   struct {
     int set, wave_flag;
@@ -1085,6 +1086,7 @@ int apko_ncycle(const apko_engine *e) { return e->ncycle; }
 double apko_c_h(const apko_engine *e) { return e->c_h; }
 void apko_set_c_h(apko_engine *e, double c_h) { e->c_h = c_h; }
 double apko_lw_tlim(const apko_engine *e) { return e->lw.tlim_period; }
+long long apko_fofc_total(const apko_engine *e) { return e->fofc_total; }
 
 /* ===================================================================================== */
 /* CalculateFluxes: src/hydro/hydro.cpp:1025-1208                                         */
@@ -1546,7 +1548,7 @@ void apko_cycle(apko_engine *e) {
     int recon = (s == 0 && e->p.integrator == APKO_INT_VL2) ? APKO_RECON_DC : e->p.recon;
     const double bdt = beta[s] * e->dt;
     apko_calc_fluxes(e, recon);
-    if (e->p.fofc) apko_fofc(e, g0[s], g1[s], bdt);
+    if (e->p.fofc) e->fofc_total += apko_fofc(e, g0[s], g1[s], bdt);
     apko_flux_div_update(e, g0[s], g1[s], bdt);
     apko_dedner(e, bdt);
     apko_exchange(e);

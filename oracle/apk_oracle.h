@@ -53,7 +53,7 @@ void apko_default_params(apko_params *p);
 apko_engine *apko_create(const apko_params *p);
 void apko_destroy(apko_engine *e);
 
-/* problem generators (src/pgen/*.cpp); pars meaning depends on id, see apk_oracle.c */
+/* problem generators (src/pgen); pars meaning depends on id, see apk_oracle.c */
 int apko_pgen(apko_engine *e, int id, const double *pars, int npars);
 /* finish initialisation: ghost exchange + BCs + cons2prim + first dt (Mesh::Initialize,
  * EvolutionDriver::InitializeBlockTimeSteps + SetGlobalTimeStep) */
@@ -75,6 +75,7 @@ double apko_dt(const apko_engine *e);
 int apko_ncycle(const apko_engine *e);
 double apko_c_h(const apko_engine *e);
 double apko_lw_tlim(const apko_engine *e); /* linear-wave "test=true" tlim (one period) */
+long long apko_fofc_total(const apko_engine *e); /* FOFC corrections applied so far */
 /* linear_wave::UserWorkAfterLoop L1 errors: out[0]=rms, out[1..5]=l1 per var */
 void apko_linear_wave_errors(apko_engine *e, double *out);
 /* history sums (hydro.cpp:145-208): mass, m1, m2, m3, KE, E, ME, relDivB */

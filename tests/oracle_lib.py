@@ -72,6 +72,8 @@ def lib():
         getattr(L, f).argtypes = [C.c_void_p]
         getattr(L, f).restype = C.c_double
     L.apko_ncycle.argtypes = [C.c_void_p]
+    L.apko_fofc_total.argtypes = [C.c_void_p]
+    L.apko_fofc_total.restype = C.c_longlong
     L.apko_linear_wave_errors.argtypes = [C.c_void_p, dp]
     L.apko_history.argtypes = [C.c_void_p, dp]
     L.apko_calc_fluxes.argtypes = [C.c_void_p, C.c_int]
@@ -188,6 +190,10 @@ class Oracle:
     @property
     def ncycle(self):
         return self.L.apko_ncycle(self.h)
+
+    @property
+    def fofc_total(self):
+        return self.L.apko_fofc_total(self.h)
 
     @property
     def c_h(self):
