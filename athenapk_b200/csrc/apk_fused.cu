@@ -24,7 +24,12 @@
 namespace APK_NS {
 namespace {
 
-constexpr int TX = 32, TY = 8, NWARPS = 9, NTHREADS = NWARPS * 32;
+#ifndef APK_FUSED_NWARPS
+#define APK_FUSED_NWARPS 12
+#endif
+// register file is split over 4 SM sub-partitions: 9..12 warps all cap at 168 regs/thread,
+// so 12 warps (3 per scheduler) cost nothing extra and hide more latency than 9.
+constexpr int TX = 32, TY = 8, NWARPS = APK_FUSED_NWARPS, NTHREADS = NWARPS * 32;
 
 APK_DEV constexpr int slot_of_var(int v, int dir) {
   // inverse of var_of_slot(): sweep-local slot that holds memory variable v
@@ -57,6 +62,9 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   const int tye = (NDIM >= 2) ? min(TY, g.je + 1 - j0) : 1;    // ... in x2
   const long sj = g.n1, sk = (long)g.n1 * g.n2;
   const double *__restrict__ prim = B.prim;
+  double *__restrict__ cons = B.cons;
+  const double *__restrict__ cons_u1 = B.cons_u1;
+  double *__restrict__ po = prim_out[blockIdx.y];
   const double dx1 = B.dx[0], dx2 = B.dx[1], dx3 = B.dx[2];
   // uniform_coordinates.hpp:37-40
   const double a1 = dx2 * dx3, a2 = dx1 * dx3, a3 = dx1 * dx2, vol = dx1 * dx2 * dx3;
@@ -71,60 +79,68 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
 
   const int kfirst = (NDIM == 3) ? g.ks - 1 : g.ks;
   const int klast = (NDIM == 3) ? g.ke + 1 : g.ke;
+  // recon work of one plane as a flat list of warp tasks (one task = one variable x one row of
+  // 32 cells): [0,NZ) x3 rows, [NZ,NZ+NX) x1 rows, [NZ+NX, NZ+NX+NY) x2 rows -1..TY.
+  // UNROLL tasks are fetched before the first one is evaluated (memory-level parallelism; with
+  // 9 warps per SM there are too few warps to hide HBM/L2 latency otherwise).
+  constexpr int NZ = (NDIM == 3) ? NH * TY : 0, NX = NH * TY, NY = (NDIM >= 2) ? NH * (TY + 2) : 0;
+  constexpr int UNROLL = (RECON == APK_RECON_DC) ? 4 : 2;
   int cur = 0;
   for (int kp = kfirst; kp <= klast; ++kp) {
     const bool inplane = (kp >= g.ks && kp <= g.ke);
     // ------------------------------------------------------------------ recon phase
-    if (NDIM == 3) {
-      for (int t = warp; t < NH * TY; t += NWARPS) {
-        const int n = t / TY, j = t % TY;
-        if (j < tye && lane < txe) {
-          const double *q = prim + (long)var_of_slot(n, 2) * g.ncell + (long)kp * sk +
-                            (long)(j0 + j) * sj + (i0 + lane);
-          double ql, qr;
-          recon_cell<RECON>(q, sk, dx3, (n == 0 || n == 4), ql, qr);
-          sm.wrz[n][j][lane] = qr;
-          sm.wlz[cur ^ 1][n][j][lane] = ql;
+    {
+      const int t_end = inplane ? NZ + NX + NY : NZ;
+      const long plane = (long)kp * sk + (long)j0 * sj + i0;
+      for (int t0 = warp; t0 < t_end; t0 += UNROLL * NWARPS) {
+        double v[UNROLL][5];
+        int dirs[UNROLL], ns[UNROLL], rows[UNROLL];
+        bool ok[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const int t = t0 + u * NWARPS;
+          int dir, n, r;
+          if (t < NZ) { dir = 2; n = t / TY; r = t % TY; }
+          else if (t < NZ + NX) { dir = 0; n = (t - NZ) / TY; r = (t - NZ) % TY; }
+          else { dir = 1; n = (t - NZ - NX) / (TY + 2); r = (t - NZ - NX) % (TY + 2) - 1; }
+          dirs[u] = dir; ns[u] = n; rows[u] = r;
+          ok[u] = (t < t_end) && lane < txe && (dir == 1 ? r <= tye : r < tye);
+          if (ok[u]) {
+            const double *q = prim + (long)var_of_slot(n, dir) * g.ncell + plane + (long)r * sj + lane;
+            load_stencil<RECON>(q, dir == 0 ? 1 : (dir == 1 ? sj : sk), v[u]);
+          }
         }
-      }
-    }
-    if (inplane) {
-      // x1: cells 0..txe-1 of each row, ql -> face c+1, qr -> face c
-      for (int t = warp; t < NH * TY; t += NWARPS) {
-        const int n = t / TY, j = t % TY;
-        if (j < tye && lane < txe) {
-          const double *q = prim + (long)var_of_slot(n, 0) * g.ncell + (long)kp * sk +
-                            (long)(j0 + j) * sj + (i0 + lane);
-          double ql, qr;
-          recon_cell<RECON>(q, 1, dx1, (n == 0 || n == 4), ql, qr);
-          sm.wlx[n][j][lane + 1] = ql;
-          sm.wrx[n][j][lane] = qr;
-        }
-      }
-      // x1 end cells: cell -1 gives the L state of face 0, cell txe the R state of face txe
-      for (int t = threadIdx.x; t < NH * TY * 2; t += NTHREADS) {
-        const int side = t & 1, j = (t >> 1) % TY, n = (t >> 1) / TY;
-        if (j < tye) {
-          const int c = side ? txe : -1;
-          const double *q = prim + (long)var_of_slot(n, 0) * g.ncell + (long)kp * sk +
-                            (long)(j0 + j) * sj + (i0 + c);
-          double ql, qr;
-          recon_cell<RECON>(q, 1, dx1, (n == 0 || n == 4), ql, qr);
-          if (side) sm.wrx[n][j][txe] = qr;
-          else sm.wlx[n][j][0] = ql;
-        }
-      }
-      if (NDIM >= 2) {
-        // x2: rows -1..tye ; ql -> face row r+1, qr -> face row r
-        for (int t = warp; t < NH * (TY + 2); t += NWARPS) {
-          const int n = t / (TY + 2), r = t % (TY + 2) - 1;
-          if (r <= tye && lane < txe) {
-            const double *q = prim + (long)var_of_slot(n, 1) * g.ncell + (long)kp * sk +
-                              (long)(j0 + r) * sj + (i0 + lane);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          if (ok[u]) {
+            const int dir = dirs[u], n = ns[u], r = rows[u];
             double ql, qr;
-            recon_cell<RECON>(q, sj, dx2, (n == 0 || n == 4), ql, qr);
-            if (r + 1 <= tye) sm.wly[n][r + 1][lane] = ql;
-            if (r >= 0) sm.wry[n][r][lane] = qr;
+            recon_stencil<RECON>(v[u], dir == 0 ? dx1 : (dir == 1 ? dx2 : dx3), (n == 0 || n == 4),
+                                 ql, qr);
+            if (dir == 2) {
+              sm.wrz[n][r][lane] = qr;
+              sm.wlz[cur ^ 1][n][r][lane] = ql;
+            } else if (dir == 0) {
+              sm.wlx[n][r][lane + 1] = ql;
+              sm.wrx[n][r][lane] = qr;
+            } else {
+              if (r + 1 <= tye) sm.wly[n][r + 1][lane] = ql;
+              if (r >= 0) sm.wry[n][r][lane] = qr;
+            }
+          }
+        }
+      }
+      if (inplane) {
+        // x1 end cells: cell -1 gives the L state of face 0, cell txe the R state of face txe
+        for (int t = threadIdx.x; t < NH * TY * 2; t += NTHREADS) {
+          const int side = t & 1, j = (t >> 1) % TY, n = (t >> 1) / TY;
+          if (j < tye) {
+            const int c = side ? txe : -1;
+            const double *q = prim + (long)var_of_slot(n, 0) * g.ncell + plane + (long)j * sj + c;
+            double ql, qr;
+            recon_cell<RECON>(q, 1, dx1, (n == 0 || n == 4), ql, qr);
+            if (side) sm.wrx[n][j][txe] = qr;
+            else sm.wlx[n][j][0] = ql;
           }
         }
       }
@@ -198,15 +214,14 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           }
           const long o = (long)v * g.ncell + c;
           // update.cpp:135-137 / update.hpp:55
-          u[v] = g0 * B.cons[o] + g1 * B.cons_u1[o] + bdt * (-d / vol);
+          u[v] = g0 * cons[o] + g1 * cons_u1[o] + bdt * fdiv(-d, vol);
         }
         if constexpr (FLUID == APK_FLUID_GLMMHD) u[8] *= dedner_coeff;  // dedner_source.cpp:72
         cons_to_prim<NH>(u, w, eos);
-        double *__restrict__ po = prim_out[blockIdx.y];
 #pragma unroll
         for (int v = 0; v < NH; ++v) {
           const long o = (long)v * g.ncell + c;
-          B.cons[o] = u[v];
+          cons[o] = u[v];
           po[o] = w[v];
         }
         if (dtmin) {  // hydro.cpp:845-895
@@ -218,9 +233,9 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
             ly = (NDIM > 1) ? fast_speed(gamma, w[0], w[4], w[6], w[7], w[5]) : 0.0;
             lz = (NDIM > 2) ? fast_speed(gamma, w[0], w[4], w[7], w[5], w[6]) : 0.0;
           }
-          my_min = fmin(my_min, dx1 / (fabs(w[1]) + lx));
-          if (NDIM > 1) my_min = fmin(my_min, dx2 / (fabs(w[2]) + ly));
-          if (NDIM > 2) my_min = fmin(my_min, dx3 / (fabs(w[3]) + lz));
+          my_min = fmin(my_min, fdiv(dx1, (fabs(w[1]) + lx)));
+          if (NDIM > 1) my_min = fmin(my_min, fdiv(dx2, (fabs(w[2]) + ly)));
+          if (NDIM > 2) my_min = fmin(my_min, fdiv(dx3, (fabs(w[3]) + lz)));
         }
       }
       if (NDIM == 3 && inplane) {

@@ -122,7 +122,7 @@ __device__ __forceinline__ double flux_div(const ApkGeom &g, const apk_block_t &
   double du = (a1 * B.flux[0][o + 1] - a1 * B.flux[0][o]);
   if (g.ndim >= 2) du += (a2 * B.flux[1][o + g.n1] - a2 * B.flux[1][o]);
   if (g.ndim == 3) du += (a3 * B.flux[2][o + (long)g.n1 * g.n2] - a3 * B.flux[2][o]);
-  return -du / vol;
+  return fdiv(-du, vol);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -163,7 +163,7 @@ k_fofc_flag(ApkGeom g, const apk_block_t *__restrict__ blocks, double g0, double
     const long o = (long)v * g.ncell + c;
     nc[v] = g0 * B.cons[o] + g1 * B.cons_u1[o] + bdt * flux_div(g, B, v, c, a1, a2, a3, vol);
   }
-  double new_p = nc[4] - 0.5 * (sqr(nc[1]) + sqr(nc[2]) + sqr(nc[3])) / nc[0];
+  double new_p = nc[4] - fdiv(0.5 * (sqr(nc[1]) + sqr(nc[2]) + sqr(nc[3])), nc[0]);
   if constexpr (FLUID == APK_FLUID_GLMMHD) new_p -= 0.5 * (sqr(nc[5]) + sqr(nc[6]) + sqr(nc[7]));
   if (nc[0] > 0.0 && new_p > 0.0) return;
   if (attempt > 2 && nc[0] > 0.0 && new_p < 0.0) return;
@@ -221,15 +221,15 @@ k_dedner(ApkGeom g, const apk_block_t *__restrict__ blocks, double coeff, double
     const long sj = g.n1, sk = (g.ndim < 3) ? 0 : (long)g.n1 * g.n2;
     const double *pb1 = B.prim + 5 * g.ncell + c, *pb2 = B.prim + 6 * g.ncell + c,
                  *pb3 = B.prim + 7 * g.ncell + c, *pps = B.prim + 8 * g.ncell + c;
-    const double divB = 0.5 * ((pb1[1] - pb1[-1]) / B.dx[0] + (pb2[sj] - pb2[-sj]) / B.dx[1] +
-                               (pb3[sk] - pb3[-sk]) / B.dx[2]);
+    const double divB = 0.5 * (fdiv((pb1[1] - pb1[-1]), B.dx[0]) + fdiv((pb2[sj] - pb2[-sj]), B.dx[1]) +
+                               fdiv((pb3[sk] - pb3[-sk]), B.dx[2]));
     B.cons[1 * g.ncell + c] -= bdt * divB * pb1[0];
     B.cons[2 * g.ncell + c] -= bdt * divB * pb2[0];
     B.cons[3 * g.ncell + c] -= bdt * divB * pb3[0];
     B.cons[4 * g.ncell + c] -=
         0.5 * bdt *
-        (pb1[0] * (pps[1] - pps[-1]) / B.dx[0] + pb2[0] * (pps[sj] - pps[-sj]) / B.dx[1] +
-         pb3[0] * (pps[sk] - pps[-sk]) / B.dx[2]);
+        (fdiv(pb1[0] * (pps[1] - pps[-1]), B.dx[0]) + fdiv(pb2[0] * (pps[sj] - pps[-sj]), B.dx[1]) +
+         fdiv(pb3[0] * (pps[sk] - pps[-sk]), B.dx[2]));
   }
   B.cons[8 * g.ncell + c] *= coeff;
 }
@@ -286,9 +286,9 @@ k_min_dt(ApkGeom g, const apk_block_t *__restrict__ blocks, double gamma,
       ly = (g.ndim > 1) ? fast_speed(gamma, d, p, b2, b3, b1) : 0.0;
       lz = (g.ndim > 2) ? fast_speed(gamma, d, p, b3, b1, b2) : 0.0;
     }
-    m = fmin(m, B.dx[0] / (fabs(v1) + lx));
-    if (g.ndim > 1) m = fmin(m, B.dx[1] / (fabs(v2) + ly));
-    if (g.ndim > 2) m = fmin(m, B.dx[2] / (fabs(v3) + lz));
+    m = fmin(m, fdiv(B.dx[0], (fabs(v1) + lx)));
+    if (g.ndim > 1) m = fmin(m, fdiv(B.dx[1], (fabs(v2) + ly)));
+    if (g.ndim > 2) m = fmin(m, fdiv(B.dx[2], (fabs(v3) + lz)));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));

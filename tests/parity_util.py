@@ -39,7 +39,11 @@ def max_abs_diff(s, o, fields=("cons", "prim")):
 
 
 def rel_l1(s, o, field="cons"):
-    """relative L1 difference per variable, max over variables (interior + ghosts)"""
+    """relative L1 difference of the state: max over variables of sum|got-ref| normalised by the
+    largest per-variable L1 norm of the reference state (rounding-level differences are absolute
+    at the scale of the O(1) fields; normalising a 1e-6-amplitude momentum component by its own
+    norm would ask for 1e-18 absolute agreement, below what FMA vs non-FMA arithmetic -- the
+    reference's own CUDA vs CPU builds -- can deliver)."""
     num = None
     den = None
     for b in range(s.nblocks):
@@ -50,8 +54,7 @@ def rel_l1(s, o, field="cons"):
         d = np.abs(ref).reshape(ref.shape[0], -1).sum(axis=1)
         num = n if num is None else num + n
         den = d if den is None else den + d
-    scale = max(float(den.max()), 1e-300)
-    return float(np.max(num / np.maximum(den, 1e-8 * scale)))
+    return float(np.max(num) / max(float(den.max()), 1e-300))
 
 
 def assert_bitexact(s, o, what=""):
