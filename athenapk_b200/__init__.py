@@ -128,7 +128,7 @@ def lib():
     L.apk_copy_ghosts_local.argtypes = [vp, vp, C.c_int, vp]
     L.apk_halo_pack.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp]
     L.apk_halo_unpack.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp]
-    L.apk_stage_fused.argtypes = [vp, vp, vp] + [C.c_double] * 6 + [C.c_int, vp, vp]
+    L.apk_stage_fused.argtypes = [vp, vp, vp] + [C.c_double] * 6 + [C.c_int, C.c_int, vp, vp]
     L.apk_save_u1.argtypes = [vp, vp, vp]
     L.apk_fp64_probe.argtypes = [C.c_int, C.c_int, C.c_int, vp, dp, vp]
 

@@ -169,8 +169,8 @@ int apk_halo_unpack(const apk_pack_desc_t *d, const apk_block_t *blocks,
 
 int apk_stage_fused(const apk_pack_desc_t *d, const apk_block_t *blocks,
                     double *const *d_prim_out, double gam0, double gam1, double beta_dt,
-                    double c_h, double mindx, double alpha, int recon_override, double *d_dtmin,
-                    void *stream) {
+                    double c_h, double mindx, double alpha, int recon_override, int flags,
+                    double *d_dtmin, void *stream) {
   if (check(d, blocks, "apk_stage_fused: bad descriptor")) return 1;
   if (!d_prim_out) {
     apk_common::set_error("apk_stage_fused: null prim_out");
@@ -179,7 +179,7 @@ int apk_stage_fused(const apk_pack_desc_t *d, const apk_block_t *blocks,
   const double coeff =
       (d->fluid == APK_FLUID_GLMMHD) ? std::exp(-alpha * c_h * beta_dt / mindx) : 1.0;
   int rc = DISPATCH(d, launch_stage_fused(*d, blocks, d_prim_out, gam0, gam1, beta_dt, c_h, coeff,
-                                          recon_override, d_dtmin, S(stream)));
+                                          recon_override, flags, d_dtmin, S(stream)));
   return rc ? rc : cuda_ok("apk_stage_fused");
 }
 

@@ -29,7 +29,13 @@ namespace {
 #endif
 // register file is split over 4 SM sub-partitions: 9..12 warps all cap at 168 regs/thread,
 // so 12 warps (3 per scheduler) cost nothing extra and hide more latency than 9.
-constexpr int TX = 32, TY = 8, NWARPS = APK_FUSED_NWARPS, NTHREADS = NWARPS * 32;
+#ifndef APK_FUSED_TY
+#define APK_FUSED_TY 11
+#endif
+// TY = 11 with 12 warps: 12 x1 + 12 x2 + 11 x3 face rows = 35 Riemann warp tasks = 3 full rounds
+// (97 % slot use; TY = 8 gives 26 tasks = 12 + 12 + 2) and less x2 halo work (13/11 vs 10/8).
+constexpr int TX = 32, TY = APK_FUSED_TY, NWARPS = APK_FUSED_NWARPS, NTHREADS = NWARPS * 32;
+static_assert(NTHREADS >= TX * TY, "finalize phase needs one thread per tile cell");
 
 APK_DEV constexpr int slot_of_var(int v, int dir) {
   // inverse of var_of_slot(): sweep-local slot that holds memory variable v
@@ -49,7 +55,7 @@ template <int FLUID, int RECON, int RS, int NDIM>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *__restrict__ prim_out,
               double g0, double g1, double bdt, double gamma, double c_h, double dedner_coeff,
-              EosPars eos, int ntx, unsigned long long *dtmin) {
+              EosPars eos, int ntx, int flags, unsigned long long *dtmin) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<NH> &sm = *reinterpret_cast<Smem<NH> *>(smem_raw);
@@ -63,7 +69,8 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   const long sj = g.n1, sk = (long)g.n1 * g.n2;
   const double *__restrict__ prim = B.prim;
   double *__restrict__ cons = B.cons;
-  const double *__restrict__ cons_u1 = B.cons_u1;
+  double *__restrict__ cons_u1 = B.cons_u1;
+  const bool save_u1 = (flags & APK_FUSED_SAVE_U1) != 0;
   double *__restrict__ po = prim_out[blockIdx.y];
   const double dx1 = B.dx[0], dx2 = B.dx[1], dx3 = B.dx[2];
   // uniform_coordinates.hpp:37-40
@@ -214,7 +221,15 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           }
           const long o = (long)v * g.ncell + c;
           // update.cpp:135-137 / update.hpp:55
-          u[v] = g0 * cons[o] + g1 * cons_u1[o] + bdt * fdiv(-d, vol);
+          const double c0 = cons[o];
+          double c1;
+          if (save_u1) {  // first stage: u1 <- u0 (hydro_driver.cpp:474-495) folded into the pass
+            c1 = c0;
+            cons_u1[o] = c0;
+          } else {
+            c1 = cons_u1[o];
+          }
+          u[v] = g0 * c0 + g1 * c1 + bdt * fdiv(-d, vol);
         }
         if constexpr (FLUID == APK_FLUID_GLMMHD) u[8] *= dedner_coeff;  // dedner_source.cpp:72
         cons_to_prim<NH>(u, w, eos);
@@ -262,7 +277,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
 template <int FLUID, int RECON, int RS>
 int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
               double *const *prim_out, double g0, double g1, double bdt, double c_h,
-              double coeff, double *d_dtmin, cudaStream_t s) {
+              double coeff, int flags, double *d_dtmin, cudaStream_t s) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
   const EosPars eos = {d.gamma, d.dfloor, d.pfloor, d.efloor, d.vceil, d.eceil};
   const int ntx = (d.nx[0] + TX - 1) / TX;
@@ -279,7 +294,7 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
       attr_set = true;                                                                           \
     }                                                                                            \
     kern<<<grid, NTHREADS, smem, s>>>(g, blocks, prim_out, g0, g1, bdt, d.gamma, c_h, coeff, eos, \
-                                      ntx, dt);                                                  \
+                                      ntx, flags, dt);                                                  \
   }
   if (g.ndim == 3) APK_LAUNCH_FUSED(3)
   else if (g.ndim == 2) APK_LAUNCH_FUSED(2)
@@ -292,14 +307,14 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
 template <int FLUID, int RS>
 int fused_recon(int recon, const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
                 double *const *prim_out, double g0, double g1, double bdt, double c_h,
-                double coeff, double *dt, cudaStream_t s) {
+                double coeff, int flags, double *dt, cudaStream_t s) {
   switch (recon) {
-  case APK_RECON_DC: return run_fused<FLUID, APK_RECON_DC, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, dt, s);
-  case APK_RECON_PLM: return run_fused<FLUID, APK_RECON_PLM, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, dt, s);
-  case APK_RECON_PPM: return run_fused<FLUID, APK_RECON_PPM, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, dt, s);
-  case APK_RECON_WENOZ: return run_fused<FLUID, APK_RECON_WENOZ, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, dt, s);
-  case APK_RECON_WENO3: return run_fused<FLUID, APK_RECON_WENO3, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, dt, s);
-  case APK_RECON_LIMO3: return run_fused<FLUID, APK_RECON_LIMO3, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, dt, s);
+  case APK_RECON_DC: return run_fused<FLUID, APK_RECON_DC, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, s);
+  case APK_RECON_PLM: return run_fused<FLUID, APK_RECON_PLM, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, s);
+  case APK_RECON_PPM: return run_fused<FLUID, APK_RECON_PPM, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, s);
+  case APK_RECON_WENOZ: return run_fused<FLUID, APK_RECON_WENOZ, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, s);
+  case APK_RECON_WENO3: return run_fused<FLUID, APK_RECON_WENO3, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, s);
+  case APK_RECON_LIMO3: return run_fused<FLUID, APK_RECON_LIMO3, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, s);
   }
   apk_common::set_error("apk_stage_fused: unknown reconstruction");
   return 1;
@@ -313,11 +328,12 @@ int fused_recon(int recon, const apk_pack_desc_t &d, const ApkGeom &g, const apk
 #if APK_FUSED_PART == 0
 int launch_stage_fused_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
                            double *const *prim_out, double g0, double g1, double bdt, double c_h,
-                           double dedner_coeff, int recon, double *d_dtmin, cudaStream_t s);
+                           double dedner_coeff, int recon, int flags, double *d_dtmin,
+                           cudaStream_t s);
 
 int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
                        double *const *prim_out, double g0, double g1, double bdt, double c_h,
-                       double dedner_coeff, int recon, double *d_dtmin, cudaStream_t s) {
+                       double dedner_coeff, int recon, int flags, double *d_dtmin, cudaStream_t s) {
   const ApkGeom g = apk_make_geom(d);
   if (recon < 0) recon = d.recon;
   if (d.nscalars != 0) {
@@ -326,13 +342,13 @@ int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
   }
   if (d.fluid == APK_FLUID_EULER) {
     switch (d.riemann) {
-    case APK_RIEMANN_NONE: return run_fused<APK_FLUID_EULER, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, d_dtmin, s);
-    case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, d_dtmin, s);
-    case APK_RIEMANN_HLLC: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLC>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, d_dtmin, s);
+    case APK_RIEMANN_NONE: return run_fused<APK_FLUID_EULER, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, s);
+    case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, s);
+    case APK_RIEMANN_HLLC: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLC>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, s);
     }
   } else {
     return launch_stage_fused_mhd(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, recon,
-                                  d_dtmin, s);
+                                  flags, d_dtmin, s);
   }
   apk_common::set_error("apk_stage_fused: unsupported fluid/riemann combination");
   return 1;
@@ -340,11 +356,11 @@ int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
 #else
 int launch_stage_fused_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
                            double *const *prim_out, double g0, double g1, double bdt, double c_h,
-                           double dedner_coeff, int recon, double *d_dtmin, cudaStream_t s) {
+                           double dedner_coeff, int recon, int flags, double *d_dtmin, cudaStream_t s) {
   switch (d.riemann) {
-  case APK_RIEMANN_NONE: return run_fused<APK_FLUID_GLMMHD, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, d_dtmin, s);
-  case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, d_dtmin, s);
-  case APK_RIEMANN_HLLD: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLD>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, d_dtmin, s);
+  case APK_RIEMANN_NONE: return run_fused<APK_FLUID_GLMMHD, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, s);
+  case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, s);
+  case APK_RIEMANN_HLLD: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLD>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, s);
   }
   apk_common::set_error("apk_stage_fused: unsupported fluid/riemann combination");
   return 1;

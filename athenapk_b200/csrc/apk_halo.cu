@@ -60,7 +60,9 @@ k_fill_ghosts(ApkGeom g, const apk_block_t *__restrict__ blocks, int nx1, int nx
   if (nb < 0) return;  // physical boundary or remote (filled by k_halo_unpack)
   const apk_block_t &N = blocks[nb];
   const long cs = ((long)(k - o3 * nx3) * g.n2 + (j - o2 * nx2)) * g.n1 + (i - o1 * nx1);
-  for (int n = 0; n < g.nvar; ++n) B.cons[(long)n * g.ncell + c] = N.cons[(long)n * g.ncell + cs];
+  // with_prim: 0 = cons only, 1 = cons + prim, 2 = prim only
+  if (with_prim != 2)
+    for (int n = 0; n < g.nvar; ++n) B.cons[(long)n * g.ncell + c] = N.cons[(long)n * g.ncell + cs];
   if (with_prim)
     for (int n = 0; n < g.nvar; ++n) B.prim[(long)n * g.ncell + c] = N.prim[(long)n * g.ncell + cs];
 }
@@ -94,7 +96,7 @@ k_bc(ApkGeom g, const apk_block_t *__restrict__ blocks, int face, int with_prim)
   for (int n = 0; n < g.nvar; ++n) {
     // AthenaPK ReflectBC flips variable index == DIR, i.e. the normal momentum / velocity
     const double sgn = (type == APK_BC_REFLECT && n == d + 1) ? -1.0 : 1.0;
-    B.cons[(long)n * g.ncell + c] = sgn * B.cons[(long)n * g.ncell + cs];
+    if (with_prim != 2) B.cons[(long)n * g.ncell + c] = sgn * B.cons[(long)n * g.ncell + cs];
     if (with_prim) B.prim[(long)n * g.ncell + c] = sgn * B.prim[(long)n * g.ncell + cs];
   }
 }
@@ -106,7 +108,7 @@ k_halo_copy(ApkGeom g, const apk_block_t *__restrict__ blocks,
             const apk_halo_item_t *__restrict__ items, int with_prim, double *buf) {
   const apk_halo_item_t it = items[blockIdx.y];
   const long cells = (long)it.ext[0] * it.ext[1] * it.ext[2];
-  const int nf = with_prim ? 2 : 1;
+  const int nf = (with_prim == 1) ? 2 : 1;
   const long total = cells * g.nvar * nf;
   const apk_block_t &B = blocks[it.block];
   for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -120,7 +122,7 @@ k_halo_copy(ApkGeom g, const apk_block_t *__restrict__ blocks,
     const int jj = (int)(rem / it.ext[0]);
     const int ii = (int)(rem - (long)jj * it.ext[0]);
     const long c = ((long)(it.lo[2] + kk) * g.n2 + (it.lo[1] + jj)) * g.n1 + (it.lo[0] + ii);
-    double *field = f ? B.prim : B.cons;
+    double *field = (f || with_prim == 2) ? B.prim : B.cons;
     if (PACK) buf[it.offset + t] = field[(long)n * g.ncell + c];
     else field[(long)n * g.ncell + c] = buf[it.offset + t];
   }

@@ -562,7 +562,8 @@ TaskStatus HydroSim::FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, b
                "init dtmin");
   }
   abi_check(apk_stage_fused(&desc_, d_blocks_[cur_], d_prim_out_[cur_], gam0, gam1, beta_dt, c_h,
-                            mindx, cfg_.glmmhd_alpha, recon, dtmin, stream_), "apk_stage_fused");
+                            mindx, cfg_.glmmhd_alpha, recon, stage == 1 ? APK_FUSED_SAVE_U1 : 0,
+                            dtmin, stream_), "apk_stage_fused");
   cur_ ^= 1;  // prim_out becomes "prim"
   return TaskStatus::complete;
 }
@@ -574,15 +575,15 @@ TaskStatus HydroSim::StartReceiveBoundBufs() {
   return TaskStatus::complete;
 }
 
-TaskStatus HydroSim::SendBoundBufs(bool with_prim) {
+TaskStatus HydroSim::SendBoundBufs(int with_prim) {
   // same-device neighbours: direct ghost fill, no buffers
-  abi_check(apk_copy_ghosts_local(&desc_, d_blocks_[cur_], with_prim ? 1 : 0, stream_),
+  abi_check(apk_copy_ghosts_local(&desc_, d_blocks_[cur_], with_prim, stream_),
             "apk_copy_ghosts_local");
   if (cfg_.nranks == 1) return TaskStatus::complete;
   if (!comm_) throw std::runtime_error("apk_host: multi-rank run without InitComm");
   // one pack launch for all peers, one grouped send/recv per peer
   abi_check(apk_halo_pack(&desc_, d_blocks_[cur_], d_send_items_, (int)send_items_.size(),
-                          with_prim ? 1 : 0, d_sendbuf_, stream_), "apk_halo_pack");
+                          with_prim, d_sendbuf_, stream_), "apk_halo_pack");
   ncclComm_t c = reinterpret_cast<ncclComm_t>(comm_);
   // buffers are laid out for cons+prim; without prim each item only fills its first half, the
   // whole (fixed-size) segment is still what both sides agree on.
@@ -608,18 +609,18 @@ TaskStatus HydroSim::ReceiveBoundBufs() {
   return TaskStatus::complete;
 }
 
-TaskStatus HydroSim::SetBounds(bool with_prim) {
+TaskStatus HydroSim::SetBounds(int with_prim) {
   if (cfg_.nranks > 1) {
     abi_check(apk_halo_unpack(&desc_, d_blocks_[cur_], d_recv_items_, (int)recv_items_.size(),
-                              with_prim ? 1 : 0, d_recvbuf_, stream_), "apk_halo_unpack");
+                              with_prim, d_recvbuf_, stream_), "apk_halo_unpack");
   }
   recv_posted_ = false;
   return TaskStatus::complete;
 }
 
-TaskStatus HydroSim::ApplyBoundaryConditions(bool with_prim) {
+TaskStatus HydroSim::ApplyBoundaryConditions(int with_prim) {
   if (bc_face_mask_)
-    abi_check(apk_apply_physical_bcs(&desc_, d_blocks_[cur_], bc_face_mask_, with_prim ? 1 : 0,
+    abi_check(apk_apply_physical_bcs(&desc_, d_blocks_[cur_], bc_face_mask_, with_prim,
                                      stream_), "apk_apply_physical_bcs");
   return TaskStatus::complete;
 }
@@ -689,10 +690,10 @@ void HydroSim::Initialize(double tlim) {
   tm.tlim = tlim;
   cur_ = 0;
   // Mesh::Initialize: exchange ghosts, BCs, FillDerived
-  SendBoundBufs(false);
+  SendBoundBufs(0);
   ReceiveBoundBufs();
-  SetBounds(false);
-  ApplyBoundaryConditions(false);
+  SetBounds(0);
+  ApplyBoundaryConditions(0);
   FillDerived();
   dt_hyp = std::numeric_limits<Real>::max();
   EstimateTimestep(false);
@@ -703,7 +704,8 @@ void HydroSim::MakeTaskCollection(TaskList &tl, int stage) {
   const Real gam0 = integrator_.gam0[stage - 1], gam1 = integrator_.gam1[stage - 1];
   const Real beta_dt = integrator_.beta[stage - 1] * integrator_.dt;
   const bool last = (stage == integrator_.nstages);
-  if (stage == 1) tl.AddTask("init_u1", [this] { return InitU1(); });
+  // fused path: the u1 <- u0 copy is folded into the first fused stage (APK_FUSED_SAVE_U1)
+  if (stage == 1 && !fused_) tl.AddTask("init_u1", [this] { return InitU1(); });
   tl.AddTask("start_bnd", [this] { return StartReceiveBoundBufs(); });
   if (fused_) {
     // calc_flux + update + source_unsplit + cons2prim(interior) [+ dt reduce] in one kernel;
@@ -711,10 +713,13 @@ void HydroSim::MakeTaskCollection(TaskList &tl, int stage) {
     // the copy), so the separate FillDerived region disappears.
     tl.AddTask(stage == 1 ? "fused_stage_first" : "fused_stage_other",
                [=] { return FusedStage(stage, gam0, gam1, beta_dt, last); });
-    tl.AddTask("send", [this] { return SendBoundBufs(true); });
+    // between stages only prim ghosts are consumed; the last stage also completes cons so the
+    // state handed back after the cycle is identical to the reference's, ghosts included
+    const int fields = last ? 1 : 2;
+    tl.AddTask("send", [=] { return SendBoundBufs(fields); });
     tl.AddTask("recv", [this] { return ReceiveBoundBufs(); });
-    tl.AddTask("set", [this] { return SetBounds(true); });
-    tl.AddTask("fbound", [this] { return ApplyBoundaryConditions(true); });
+    tl.AddTask("set", [=] { return SetBounds(fields); });
+    tl.AddTask("fbound", [=] { return ApplyBoundaryConditions(fields); });
   } else {
     tl.AddTask("calc_flux", [=] { return CalculateFluxes(stage); });
     if (cfg_.fofc)
@@ -722,10 +727,10 @@ void HydroSim::MakeTaskCollection(TaskList &tl, int stage) {
                  [=] { return FirstOrderFluxCorrect(gam0, gam1, beta_dt); });
     tl.AddTask("update", [=] { return UpdateWithFluxDivergence(gam0, gam1, beta_dt); });
     tl.AddTask("source_unsplit", [=] { return AddUnsplitSources(beta_dt); });
-    tl.AddTask("send", [this] { return SendBoundBufs(false); });
+    tl.AddTask("send", [this] { return SendBoundBufs(0); });
     tl.AddTask("recv", [this] { return ReceiveBoundBufs(); });
-    tl.AddTask("set", [this] { return SetBounds(false); });
-    tl.AddTask("fbound", [this] { return ApplyBoundaryConditions(false); });
+    tl.AddTask("set", [this] { return SetBounds(0); });
+    tl.AddTask("fbound", [this] { return ApplyBoundaryConditions(0); });
     tl.AddTask("fill_derived", [this] { return FillDerived(); });
   }
   if (last) {

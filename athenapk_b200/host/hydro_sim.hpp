@@ -130,10 +130,10 @@ class HydroSim {
   TaskStatus AddUnsplitSources(Real beta_dt);
   TaskStatus FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, bool last_stage);
   TaskStatus StartReceiveBoundBufs();
-  TaskStatus SendBoundBufs(bool with_prim);
+  TaskStatus SendBoundBufs(int with_prim);  // 0 cons, 1 cons+prim, 2 prim only
   TaskStatus ReceiveBoundBufs();
-  TaskStatus SetBounds(bool with_prim);
-  TaskStatus ApplyBoundaryConditions(bool with_prim);
+  TaskStatus SetBounds(int with_prim);
+  TaskStatus ApplyBoundaryConditions(int with_prim);
   TaskStatus FillDerived();
   TaskStatus EstimateTimestep(bool have_device_min);
   void PreStepMeshUserWorkInLoop();

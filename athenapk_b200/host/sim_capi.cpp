@@ -151,8 +151,8 @@ int apk_sim_task(apk_sim_t *s, const char *name, int stage, double g0, double g1
     else if (n == "update") st = h->UpdateWithFluxDivergence(g0, g1, bdt);
     else if (n == "source_unsplit") st = h->AddUnsplitSources(bdt);
     else if (n == "exchange") {
-      h->SendBoundBufs(false); h->ReceiveBoundBufs(); h->SetBounds(false);
-      st = h->ApplyBoundaryConditions(false);
+      h->SendBoundBufs(0); h->ReceiveBoundBufs(); h->SetBounds(0);
+      st = h->ApplyBoundaryConditions(0);
     } else if (n == "fill_derived") st = h->FillDerived();
     else if (n == "pre_step") { h->PreStepMeshUserWorkInLoop(); st = TaskStatus::complete; }
     h->Synchronize();

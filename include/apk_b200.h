@@ -130,7 +130,8 @@ int apk_min_dt_async(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, d
  * src/bvals/boundary_conditions_apk.hpp:38-85): fills the ghost cells of `cons` straight
  * from the neighbour block's interior (no pack->buffer->unpack round trip), then applies
  * outflow/reflecting BCs in face order (= apk_copy_ghosts_local + apk_apply_physical_bcs).
- * with_prim != 0 additionally copies `prim` (valid
+ * with_prim (here and in the halo/BC entry points): 0 = cons only, 1 = cons and prim, 2 = prim
+ * only (between fused stages nothing reads the ghost cells of cons).  with_prim != 0 additionally copies `prim` (valid
  * because cons->prim is pointwise) so no ghost cons->prim pass is needed. */
 int apk_fill_ghosts_local(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
                           unsigned bc_face_mask, int with_prim, void *stream);
@@ -169,8 +170,10 @@ int apk_halo_unpack(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
  * array of nblocks pointers.  d_dtmin (device, may be NULL) accumulates min dx/(|v|+c). */
 int apk_stage_fused(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
                     double *const *d_prim_out, double gam0, double gam1, double beta_dt,
-                    double c_h, double mindx, double alpha, int recon_override,
+                    double c_h, double mindx, double alpha, int recon_override, int flags,
                     double *d_dtmin, void *stream);
+#define APK_FUSED_SAVE_U1 1 /* flags: also store the incoming cons into cons_u1 (first stage:
+                               replaces the u1 <- u0 DeepCopy of hydro_driver.cpp:474-495) */
 
 /* copy cons -> cons_u1 for all blocks (u1 <- u0 at stage 1, hydro_driver.cpp:474-495) */
 int apk_save_u1(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, void *stream);
