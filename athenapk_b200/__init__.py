@@ -13,7 +13,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libapk_b200.so")
+# APK_B200_LIB selects an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("APK_B200_LIB", os.path.join(_HERE, "lib", "libapk_b200.so"))
 
 FLUID = {"euler": 0, "glmmhd": 1}
 RECON = {"dc": 0, "plm": 1, "ppm": 2, "wenoz": 3, "weno3": 4, "limo3": 5}

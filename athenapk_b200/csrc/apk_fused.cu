@@ -29,8 +29,11 @@ namespace {
 #endif
 // register file is split over 4 SM sub-partitions: 9..12 warps all cap at 168 regs/thread,
 // so 12 warps (3 per scheduler) cost nothing extra and hide more latency than 9.
+#ifndef APK_FUSED_UNROLL
+#define APK_FUSED_UNROLL 2
+#endif
 #ifndef APK_FUSED_TY
-#define APK_FUSED_TY 11
+#define APK_FUSED_TY 8
 #endif
 // TY = 11 with 12 warps: 12 x1 + 12 x2 + 11 x3 face rows = 35 Riemann warp tasks = 3 full rounds
 // (97 % slot use; TY = 8 gives 26 tasks = 12 + 12 + 2) and less x2 halo work (13/11 vs 10/8).
@@ -91,7 +94,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   // UNROLL tasks are fetched before the first one is evaluated (memory-level parallelism; with
   // 9 warps per SM there are too few warps to hide HBM/L2 latency otherwise).
   constexpr int NZ = (NDIM == 3) ? NH * TY : 0, NX = NH * TY, NY = (NDIM >= 2) ? NH * (TY + 2) : 0;
-  constexpr int UNROLL = (RECON == APK_RECON_DC) ? 4 : 2;
+  constexpr int UNROLL = (RECON == APK_RECON_DC) ? 4 : APK_FUSED_UNROLL;
   int cur = 0;
   for (int kp = kfirst; kp <= klast; ++kp) {
     const bool inplane = (kp >= g.ks && kp <= g.ke);
@@ -211,7 +214,21 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       }
       if (kfin >= g.ks && kfin <= g.ke) {
         const long c = (long)kfin * sk + (long)(j0 + cj) * sj + (i0 + ci);
-        double u[NH], w[NH];
+        double u[NH], w[NH], c0[NH], c1[NH];
+        // batch the global loads (uniform branch: stage 1 saves u1 <- u0 instead of reading it,
+        // hydro_driver.cpp:474-495 folded into this pass)
+#pragma unroll
+        for (int v = 0; v < NH; ++v) c0[v] = cons[(long)v * g.ncell + c];
+        if (save_u1) {
+#pragma unroll
+          for (int v = 0; v < NH; ++v) {
+            c1[v] = c0[v];
+            cons_u1[(long)v * g.ncell + c] = c0[v];
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < NH; ++v) c1[v] = cons_u1[(long)v * g.ncell + c];
+        }
 #pragma unroll
         for (int v = 0; v < NH; ++v) {
           double d = du[v];
@@ -219,17 +236,8 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
             const int sz = slot_of_var(v, 2);
             d += (a3 * sm.wlz[cur][sz][cj][ci] - a3 * fzlo[v]);
           }
-          const long o = (long)v * g.ncell + c;
           // update.cpp:135-137 / update.hpp:55
-          const double c0 = cons[o];
-          double c1;
-          if (save_u1) {  // first stage: u1 <- u0 (hydro_driver.cpp:474-495) folded into the pass
-            c1 = c0;
-            cons_u1[o] = c0;
-          } else {
-            c1 = cons_u1[o];
-          }
-          u[v] = g0 * c0 + g1 * c1 + bdt * fdiv(-d, vol);
+          u[v] = g0 * c0[v] + g1 * c1[v] + bdt * fdiv(-d, vol);
         }
         if constexpr (FLUID == APK_FLUID_GLMMHD) u[8] *= dedner_coeff;  // dedner_source.cpp:72
         cons_to_prim<NH>(u, w, eos);

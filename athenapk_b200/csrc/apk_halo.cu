@@ -39,32 +39,76 @@ constexpr int kThreads = 256;
 // ghost cell -> neighbour offset in one dimension: -1 below, 0 interior, +1 above
 __device__ __forceinline__ int side(int idx, int s, int e) { return (idx < s) ? -1 : (idx > e) ? 1 : 0; }
 
-// One thread per ghost cell of the entire (ghost-inflated) index range of every block; copies
-// all variables of cons (and optionally prim) from the owning neighbour's interior.
+// One thread per GHOST cell (interior cells get no thread).  Ghost cells of a block are enumerated
+// in memory order in two groups so that warps stay dense: (a) rows (k,j) that lie entirely in the
+// ghost region (all n1 cells), (b) the 2*ng end cells of the rows that cross the interior.
+// Every thread first LOADS all variables of its cell, then stores them (the per-variable planes
+// are ncell doubles apart: 9..18 independent 256 B-coalesced streams in flight per warp).
+struct GhostEnum {
+  int full_rows;      // rows entirely ghost
+  int kghost_rows;    // of which: rows of the k-ghost planes (2*ng*n2), 0 below 3-D
+  int part_rows;      // rows crossing the interior (nx2*nx3)
+  long per_block;     // ghost cells per block
+};
+
+__device__ __forceinline__ void ghost_decode(const ApkGeom &g, const GhostEnum &e, int nx2, long gi,
+                                             int &k, int &j, int &i) {
+  const long nfull = (long)e.full_rows * g.n1;
+  if (gi < nfull) {
+    const int fr = (int)(gi / g.n1);
+    i = (int)(gi - (long)fr * g.n1);
+    if (fr < e.kghost_rows) {  // planes k < ks or k > ke, all rows
+      int kk = fr / g.n2;
+      j = fr - kk * g.n2;
+      k = (kk < g.ng) ? kk : g.ke + 1 + (kk - g.ng);
+    } else {                   // interior planes, rows j < js or j > je
+      const int r = fr - e.kghost_rows;
+      const int per_plane = 2 * g.ng;
+      const int kk = r / per_plane, jj = r - kk * per_plane;
+      k = g.ks + kk;
+      j = (jj < g.ng) ? jj : g.je + 1 + (jj - g.ng);
+    }
+  } else {
+    const long p = gi - nfull;
+    const int row = (int)(p / (2 * g.ng)), ii = (int)(p - (long)row * 2 * g.ng);
+    i = (ii < g.ng) ? ii : g.ie + 1 + (ii - g.ng);
+    const int kk = row / nx2;
+    k = g.ks + kk;
+    j = g.js + (row - kk * nx2);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
-k_fill_ghosts(ApkGeom g, const apk_block_t *__restrict__ blocks, int nx1, int nx2, int nx3,
-              int with_prim) {
+k_fill_ghosts(ApkGeom g, GhostEnum e, const apk_block_t *__restrict__ blocks, int nx1, int nx2,
+              int nx3, int with_prim) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= g.ncell * g.nb) return;
-  const int b = (int)(t / g.ncell);
-  const long c = t - (long)b * g.ncell;
-  const int k = (int)(c / ((long)g.n1 * g.n2));
-  const int j = (int)((c / g.n1) % g.n2);
-  const int i = (int)(c % g.n1);
+  if (t >= e.per_block * g.nb) return;
+  const int b = (int)(t / e.per_block);
+  int k, j, i;
+  ghost_decode(g, e, nx2, t - (long)b * e.per_block, k, j, i);
   const int o1 = side(i, g.is, g.ie);
   const int o2 = (g.ndim >= 2) ? side(j, g.js, g.je) : 0;
   const int o3 = (g.ndim >= 3) ? side(k, g.ks, g.ke) : 0;
-  if (!(o1 | o2 | o3)) return;
   const apk_block_t &B = blocks[b];
   const int nb = B.nbr[(o3 + 1) * 9 + (o2 + 1) * 3 + (o1 + 1)];
   if (nb < 0) return;  // physical boundary or remote (filled by k_halo_unpack)
   const apk_block_t &N = blocks[nb];
+  const long c = ((long)k * g.n2 + j) * g.n1 + i;
   const long cs = ((long)(k - o3 * nx3) * g.n2 + (j - o2 * nx2)) * g.n1 + (i - o1 * nx1);
   // with_prim: 0 = cons only, 1 = cons + prim, 2 = prim only
-  if (with_prim != 2)
-    for (int n = 0; n < g.nvar; ++n) B.cons[(long)n * g.ncell + c] = N.cons[(long)n * g.ncell + cs];
-  if (with_prim)
-    for (int n = 0; n < g.nvar; ++n) B.prim[(long)n * g.ncell + c] = N.prim[(long)n * g.ncell + cs];
+  for (int f = (with_prim == 2) ? 1 : 0; f < ((with_prim == 0) ? 1 : 2); ++f) {
+    const double *__restrict__ src = (f ? N.prim : N.cons) + cs;
+    double *__restrict__ dst = (f ? B.prim : B.cons) + c;
+    for (int n0 = 0; n0 < g.nvar; n0 += 9) {
+      double tmp[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q)
+        if (n0 + q < g.nvar) tmp[q] = src[(long)(n0 + q) * g.ncell];
+#pragma unroll
+      for (int q = 0; q < 9; ++q)
+        if (n0 + q < g.nvar) dst[(long)(n0 + q) * g.ncell] = tmp[q];
+    }
+  }
 }
 
 // physical BC of one face (0..5) for all blocks whose bc[face] is outflow/reflect
@@ -161,8 +205,14 @@ inline unsigned grid_for(long total, int threads) {
 int launch_fill_ghosts(const apk_pack_desc_t &d, const apk_block_t *blocks, int with_prim,
                        cudaStream_t s) {
   const ApkGeom g = apk_make_geom(d);
-  k_fill_ghosts<<<grid_for(g.ncell * g.nb, kThreads), kThreads, 0, s>>>(g, blocks, d.nx[0],
-                                                                       d.nx[1], d.nx[2], with_prim);
+  GhostEnum e;
+  const int nx2 = (g.ndim >= 2) ? d.nx[1] : 1, nx3 = (g.ndim >= 3) ? d.nx[2] : 1;
+  e.kghost_rows = (g.ndim >= 3) ? 2 * g.ng * g.n2 : 0;
+  e.full_rows = e.kghost_rows + ((g.ndim >= 2) ? 2 * g.ng * nx3 : 0);
+  e.part_rows = nx2 * nx3;
+  e.per_block = (long)e.full_rows * g.n1 + (long)e.part_rows * 2 * g.ng;
+  k_fill_ghosts<<<grid_for(e.per_block * g.nb, kThreads), kThreads, 0, s>>>(
+      g, e, blocks, d.nx[0], nx2, nx3, with_prim);
   count_launch();
   return 0;
 }
