@@ -36,8 +36,14 @@ class SimConfig(C.Structure):
         ("vceil", C.c_double), ("eceil", C.c_double),
         ("fofc", C.c_int), ("dedner_extended", C.c_int), ("glmmhd_alpha", C.c_double),
         ("nscalars", C.c_int), ("fp_mode", C.c_int), ("fused", C.c_int),
-        ("rank", C.c_int), ("nranks", C.c_int),
+        ("rank", C.c_int), ("nranks", C.c_int), ("plan_only", C.c_int),
     ]
+
+
+class HaloItem(C.Structure):
+    """Mirror of apk_halo_item_t (include/apk_b200.h)."""
+    _fields_ = [("block", C.c_int), ("lo", C.c_int * 3), ("ext", C.c_int * 3),
+                ("offset", C.c_longlong)]
 
 
 class PackDesc(C.Structure):
@@ -79,7 +85,8 @@ SIM_SYMBOLS = [
     "apk_sim_linear_wave_period", "apk_sim_linear_wave_errors", "apk_sim_stream",
     "apk_sim_pack_desc", "apk_sim_device_blocks", "apk_sim_synchronize", "apk_sim_task",
     "apk_sim_set_c_h", "apk_sim_upload_all", "apk_sim_download_all",
-    "apk_sim_enable_task_timing", "apk_sim_task_timing",
+    "apk_sim_enable_task_timing", "apk_sim_task_timing", "apk_sim_num_peers", "apk_sim_peer",
+    "apk_sim_num_halo_items", "apk_sim_halo_item", "apk_sim_neighbor",
 ]
 
 _lib = None
@@ -168,6 +175,12 @@ def lib():
     L.apk_sim_download_all.argtypes = [vp, C.c_int, vp]
     L.apk_sim_enable_task_timing.argtypes = [vp, C.c_int]
     L.apk_sim_task_timing.argtypes = [vp, C.c_char_p, dp, C.POINTER(C.c_longlong)]
+    llp = C.POINTER(C.c_longlong)
+    L.apk_sim_num_peers.argtypes = [vp]
+    L.apk_sim_peer.argtypes = [vp, C.c_int, ip, llp, llp, llp, llp]
+    L.apk_sim_num_halo_items.argtypes = [vp, C.c_int]
+    L.apk_sim_halo_item.argtypes = [vp, C.c_int, C.c_int, C.POINTER(HaloItem)]
+    L.apk_sim_neighbor.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     _lib = L
     return L
 
@@ -176,7 +189,8 @@ def make_config(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
                 mb=None, ng=2, bc="periodic", xmin=(0.0, 0.0, 0.0), xmax=(3.0, 1.5, 1.5),
                 gamma=5.0 / 3.0, cfl=0.3, fofc=False, dedner_extended=False, glmmhd_alpha=0.1,
                 nscalars=0, dfloor=-1.0, pfloor=-1.0, efloor=-1.0, vceil=float("inf"),
-                eceil=float("inf"), fp_mode="fast", fused=True, rank=0, nranks=1):
+                eceil=float("inf"), fp_mode="fast", fused=True, rank=0, nranks=1,
+                plan_only=False):
     """Input-deck style configuration (same keys/meaning as docs/input.md of the reference)."""
     c = SimConfig()
     lib().apk_sim_default_config(C.byref(c))
@@ -197,6 +211,7 @@ def make_config(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
     c.fp_mode = FP_MODE[fp_mode]
     c.fused = int(fused)
     c.rank, c.nranks = rank, nranks
+    c.plan_only = int(plan_only)
     return c
 
 
@@ -299,6 +314,27 @@ class HydroSim:
         if self.L.apk_sim_task_timing(self.h, name.encode(), C.byref(ms), C.byref(cnt)) != 0:
             return 0.0, 0
         return ms.value, cnt.value
+
+    def peers(self):
+        out = []
+        for p in range(self.L.apk_sim_num_peers(self.h)):
+            r = C.c_int()
+            v = [C.c_longlong() for _ in range(4)]
+            self.L.apk_sim_peer(self.h, p, C.byref(r), *[C.byref(x) for x in v])
+            out.append(dict(rank=r.value, send_off=v[0].value, send_cnt=v[1].value,
+                            recv_off=v[2].value, recv_cnt=v[3].value))
+        return out
+
+    def halo_items(self, recv):
+        out = []
+        for i in range(self.L.apk_sim_num_halo_items(self.h, int(recv))):
+            it = HaloItem()
+            self.L.apk_sim_halo_item(self.h, int(recv), i, C.byref(it))
+            out.append(dict(block=it.block, lo=tuple(it.lo), ext=tuple(it.ext), offset=it.offset))
+        return out
+
+    def neighbor(self, block, o1, o2, o3):
+        return self.L.apk_sim_neighbor(self.h, block, o1, o2, o3)
 
     def synchronize(self):
         self._chk(self.L.apk_sim_synchronize(self.h), "sync")

@@ -86,9 +86,11 @@ TaskStatus TaskList::Execute() {
 
 HydroSim::HydroSim(const SimConfig &cfg)
     : cfg_(cfg), integrator_(static_cast<Integrator>(cfg.integrator)) {
-  int ndev = 0;
-  cuda_check(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount (is there a GPU?)");
-  if (ndev == 0) throw std::runtime_error("apk_host: no CUDA device");
+  if (!cfg_.plan_only) {
+    int ndev = 0;
+    cuda_check(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount (is there a GPU?)");
+    if (ndev == 0) throw std::runtime_error("apk_host: no CUDA device");
+  }
   nhydro_ = (cfg_.fluid == APK_FLUID_GLMMHD) ? 9 : 5;
   nvar_ = nhydro_ + cfg_.nscalars;
   ndim_ = (cfg_.nx[2] > 1) ? 3 : ((cfg_.nx[1] > 1) ? 2 : 1);
@@ -112,16 +114,19 @@ HydroSim::HydroSim(const SimConfig &cfg)
   nblocks_global_ = nb_[0] * nb_[1] * nb_[2];
   fused_ = cfg_.fused && !cfg_.fofc && !cfg_.dedner_extended && cfg_.riemann != APK_RIEMANN_LLF &&
            cfg_.nscalars == 0;
-  cudaStream_t st;
-  cuda_check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate");
-  stream_ = st;
   BuildMesh();
   BuildNeighbors();
-  UploadBlocks();
+  if (!cfg_.plan_only) {
+    cudaStream_t st;
+    cuda_check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate");
+    stream_ = st;
+    UploadBlocks();
+  }
   BuildHaloPlan();
 }
 
 HydroSim::~HydroSim() {
+  if (cfg_.plan_only) return;
   cudaDeviceSynchronize();
   if (comm_) ncclCommDestroy(reinterpret_cast<ncclComm_t>(comm_));
   cudaFree(d_cons_);
@@ -408,6 +413,7 @@ void HydroSim::BuildHaloPlan() {
   }
   send_total_ = soff;
   recv_total_ = roff;
+  if (cfg_.plan_only) return;
   cuda_check(cudaMalloc(&d_sendbuf_, std::max<long long>(soff, 1) * sizeof(double)), "sendbuf");
   cuda_check(cudaMalloc(&d_recvbuf_, std::max<long long>(roff, 1) * sizeof(double)), "recvbuf");
   cuda_check(cudaMalloc(&d_send_items_, std::max<size_t>(send_items_.size(), 1) * sizeof(apk_halo_item_t)), "items");

@@ -50,6 +50,7 @@ struct SimConfig {
   int fp_mode = APK_FP_FAST;
   int fused = 1;  // use apk_stage_fused when legal (no FOFC / extended source)
   int rank = 0, nranks = 1;
+  int plan_only = 0;  // mesh partition + halo plan only, no CUDA (CPU-side tests of the N>1 logic)
 };
 
 // time_integration/low_storage_integrator.cpp:53-132
@@ -149,6 +150,16 @@ class HydroSim {
   long long fofc_corrections = 0;
   long long cycles_done = 0;
   bool FusedActive() const { return fused_; }
+  // halo plan introspection
+  struct PeerInfo { int rank; long long send_off, send_cnt, recv_off, recv_cnt; };
+  int NumPeers() const { return (int)peers_.size(); }
+  PeerInfo GetPeer(int p) const {
+    return {peers_[p].rank, peers_[p].send_off, peers_[p].send_cnt, peers_[p].recv_off, peers_[p].recv_cnt};
+  }
+  const std::vector<apk_halo_item_t> &HaloItems(bool recv) const { return recv ? recv_items_ : send_items_; }
+  int Neighbor(int block, int o1, int o2, int o3) const {
+    return h_blocks_[block].nbr[(o3 + 1) * 9 + (o2 + 1) * 3 + (o1 + 1)];
+  }
   void Synchronize();
   void *stream() const { return stream_; }
 

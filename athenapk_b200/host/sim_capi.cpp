@@ -51,7 +51,7 @@ apk_sim_t *apk_sim_create(const apk_sim_config_t *c) {
     k.dfloor = c->dfloor; k.pfloor = c->pfloor; k.efloor = c->efloor; k.vceil = c->vceil; k.eceil = c->eceil;
     k.fofc = c->fofc; k.dedner_extended = c->dedner_extended; k.glmmhd_alpha = c->glmmhd_alpha;
     k.nscalars = c->nscalars; k.fp_mode = c->fp_mode; k.fused = c->fused;
-    k.rank = c->rank; k.nranks = c->nranks;
+    k.rank = c->rank; k.nranks = c->nranks; k.plan_only = c->plan_only;
     s = new HydroSim(k);
     return 0;
   });
@@ -160,5 +160,26 @@ int apk_sim_task(apk_sim_t *s, const char *name, int stage, double g0, double g1
   });
 }
 void apk_sim_set_c_h(apk_sim_t *s, double c_h, double mindx) { SIM(s)->c_h = c_h; SIM(s)->mindx = mindx; }
+int apk_sim_num_peers(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->NumPeers(); }
+int apk_sim_peer(const apk_sim_t *s, int p, int *rank, long long *send_off, long long *send_cnt,
+                 long long *recv_off, long long *recv_cnt) {
+  HydroSim *h = SIM(const_cast<apk_sim_t *>(s));
+  if (p < 0 || p >= h->NumPeers()) return -1;
+  const auto q = h->GetPeer(p);
+  *rank = q.rank; *send_off = q.send_off; *send_cnt = q.send_cnt; *recv_off = q.recv_off; *recv_cnt = q.recv_cnt;
+  return 0;
+}
+int apk_sim_num_halo_items(const apk_sim_t *s, int recv) {
+  return (int)SIM(const_cast<apk_sim_t *>(s))->HaloItems(recv != 0).size();
+}
+int apk_sim_halo_item(const apk_sim_t *s, int recv, int idx, apk_halo_item_t *out) {
+  const auto &v = SIM(const_cast<apk_sim_t *>(s))->HaloItems(recv != 0);
+  if (idx < 0 || idx >= (int)v.size()) return -1;
+  *out = v[idx];
+  return 0;
+}
+int apk_sim_neighbor(const apk_sim_t *s, int block, int o1, int o2, int o3) {
+  return SIM(const_cast<apk_sim_t *>(s))->Neighbor(block, o1, o2, o3);
+}
 
 }  // extern "C"

@@ -28,6 +28,7 @@ typedef struct apk_sim_config {
   int fp_mode; /* APK_FP_FAST / APK_FP_STRICT */
   int fused;   /* use the fused stage kernel when legal */
   int rank, nranks;
+  int plan_only; /* build mesh partition + halo plan only: no CUDA calls (CPU-side tests) */
 } apk_sim_config_t;
 
 const char *apk_sim_last_error(void);
@@ -68,6 +69,14 @@ const void *apk_sim_device_blocks(const apk_sim_t *s);
 int apk_sim_synchronize(apk_sim_t *s);
 int apk_sim_task(apk_sim_t *s, const char *name, int stage, double g0, double g1, double bdt);
 void apk_sim_set_c_h(apk_sim_t *s, double c_h, double mindx);
+/* halo plan introspection (valid in plan_only mode too): peers and per-peer slab lists.
+ * counts/offsets are in doubles and sized for cons+prim (2*nvar values per cell). */
+int apk_sim_num_peers(const apk_sim_t *s);
+int apk_sim_peer(const apk_sim_t *s, int p, int *rank, long long *send_off, long long *send_cnt,
+                 long long *recv_off, long long *recv_cnt);
+int apk_sim_num_halo_items(const apk_sim_t *s, int recv);
+int apk_sim_halo_item(const apk_sim_t *s, int recv, int idx, apk_halo_item_t *out);
+int apk_sim_neighbor(const apk_sim_t *s, int block, int o1, int o2, int o3);
 
 #ifdef __cplusplus
 }
