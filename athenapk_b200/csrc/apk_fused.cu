@@ -217,8 +217,11 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
         double u[NH], w[NH], c0[NH], c1[NH];
         // batch the global loads (uniform branch: stage 1 saves u1 <- u0 instead of reading it,
         // hydro_driver.cpp:474-495 folded into this pass)
+        // gam0 == 0 (every VL2 stage, first stage of all integrators): 0*u0 contributes an exact
+        // zero, so u0 need not be read at all unless it is also the source of the u1 copy
+        const bool need_u0 = save_u1 || (g0 != 0.0);
 #pragma unroll
-        for (int v = 0; v < NH; ++v) c0[v] = cons[(long)v * g.ncell + c];
+        for (int v = 0; v < NH; ++v) c0[v] = need_u0 ? cons[(long)v * g.ncell + c] : 0.0;
         if (save_u1) {
 #pragma unroll
           for (int v = 0; v < NH; ++v) {
