@@ -108,25 +108,32 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
         bool ok[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          const int t = t0 + u * NWARPS;
+          // out-of-range tasks / lanes evaluate a clamped (valid) stencil and skip the store, so
+          // the UNROLL reconstructions are straight-line code the scheduler can interleave
+          const int tr = t0 + u * NWARPS;
+          const int t = min(tr, t_end - 1);
           int dir, n, r;
           if (t < NZ) { dir = 2; n = t / TY; r = t % TY; }
           else if (t < NZ + NX) { dir = 0; n = (t - NZ) / TY; r = (t - NZ) % TY; }
           else { dir = 1; n = (t - NZ - NX) / (TY + 2); r = (t - NZ - NX) % (TY + 2) - 1; }
           dirs[u] = dir; ns[u] = n; rows[u] = r;
-          ok[u] = (t < t_end) && lane < txe && (dir == 1 ? r <= tye : r < tye);
-          if (ok[u]) {
-            const double *q = prim + (long)var_of_slot(n, dir) * g.ncell + plane + (long)r * sj + lane;
-            load_stencil<RECON>(q, dir == 0 ? 1 : (dir == 1 ? sj : sk), v[u]);
-          }
+          ok[u] = (tr < t_end) && lane < txe && (dir == 1 ? r <= tye : r < tye);
+          const int rc = min(r, dir == 1 ? tye : tye - 1), lc = min(lane, txe - 1);
+          const double *q = prim + (long)var_of_slot(n, dir) * g.ncell + plane + (long)rc * sj + lc;
+          load_stencil<RECON>(q, dir == 0 ? 1 : (dir == 1 ? sj : sk), v[u]);
+        }
+        double qls[UNROLL], qrs[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const int dir = dirs[u], n = ns[u];
+          recon_stencil<RECON>(v[u], dir == 0 ? dx1 : (dir == 1 ? dx2 : dx3), (n == 0 || n == 4),
+                               qls[u], qrs[u]);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
           if (ok[u]) {
             const int dir = dirs[u], n = ns[u], r = rows[u];
-            double ql, qr;
-            recon_stencil<RECON>(v[u], dir == 0 ? dx1 : (dir == 1 ? dx2 : dx3), (n == 0 || n == 4),
-                                 ql, qr);
+            const double ql = qls[u], qr = qrs[u];
             if (dir == 2) {
               sm.wrz[n][r][lane] = qr;
               sm.wlz[cur ^ 1][n][r][lane] = ql;
