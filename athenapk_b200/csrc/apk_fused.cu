@@ -25,10 +25,12 @@ namespace APK_NS {
 namespace {
 
 #ifndef APK_FUSED_NWARPS
-#define APK_FUSED_NWARPS 12
+#define APK_FUSED_NWARPS 16
 #endif
-// register file is split over 4 SM sub-partitions: 9..12 warps all cap at 168 regs/thread,
-// so 12 warps (3 per scheduler) cost nothing extra and hide more latency than 9.
+// register file is split over 4 SM sub-partitions (16 K regs each): 9..12 warps cap at 168
+// regs/thread, 13..16 warps at 128.  Measured (profiles/r01_notes.md): 16 warps with ~400 B of
+// spills beat 12 warps with ~100 B and 8 warps without spills -- resident warps hide the FP64
+// dependency latency that dominates this kernel.
 #ifndef APK_FUSED_UNROLL
 #define APK_FUSED_UNROLL 2
 #endif
@@ -99,7 +101,9 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   for (int kp = kfirst; kp <= klast; ++kp) {
     const bool inplane = (kp >= g.ks && kp <= g.ke);
     // ------------------------------------------------------------------ recon phase
-    {
+    // (donor cell: L/R states are the neighbouring cell values themselves; the Riemann tasks read
+    //  them straight from global memory, no staging pass and no barrier)
+    if constexpr (RECON != APK_RECON_DC) {
       const int t_end = inplane ? NZ + NX + NY : NZ;
       const long plane = (long)kp * sk + (long)j0 * sj + i0;
       for (int t0 = warp; t0 < t_end; t0 += UNROLL * NWARPS) {
@@ -162,8 +166,22 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
         }
       }
     }
-    __syncthreads();
+    if constexpr (RECON != APK_RECON_DC) __syncthreads();
     // ------------------------------------------------------------------ riemann phase
+    if (owner) {
+      // the finalize phase of this iteration streams cons / u1 of plane kfin exactly once: start
+      // the HBM fetch now so it overlaps the Riemann solves (12-16 warps/SM cannot hide it later)
+      const int kfin = (NDIM == 3) ? kp - 1 : kp;
+      if (kfin >= g.ks && kfin <= g.ke) {
+        const long c = (long)kfin * sk + (long)(j0 + cj) * sj + (i0 + ci);
+        const bool need_u0 = save_u1 || (g0 != 0.0);
+#pragma unroll
+        for (int v = 0; v < NH; ++v) {
+          if (need_u0) asm volatile("prefetch.global.L1 [%0];" ::"l"(cons + (long)v * g.ncell + c));
+          if (!save_u1) asm volatile("prefetch.global.L1 [%0];" ::"l"(cons_u1 + (long)v * g.ncell + c));
+        }
+      }
+    }
     {
       // warp-task list: [0,TY) x1 rows, TY: x1 last faces, [TY+1, 2TY+2) x2 face rows,
       // [2TY+2, 3TY+2) x3 rows
@@ -178,24 +196,54 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           if (t < TY) { j = t; f = lane; if (f > txe || f >= TX) continue; }
           else { j = lane; f = TX; if (txe < TX || j >= TY) continue; }
           if (j >= tye) continue;
+          if constexpr (RECON == APK_RECON_DC) {
+            const double *q = prim + (long)kp * sk + (long)(j0 + j) * sj + (i0 + f);
 #pragma unroll
-          for (int n = 0; n < NH; ++n) { L[n] = sm.wlx[n][j][f]; R[n] = sm.wrx[n][j][f]; }
+            for (int n = 0; n < NH; ++n) {
+              const long o = (long)var_of_slot(n, 0) * g.ncell;
+              L[n] = q[o - 1];
+              R[n] = q[o];
+            }
+          } else {
+#pragma unroll
+            for (int n = 0; n < NH; ++n) { L[n] = sm.wlx[n][j][f]; R[n] = sm.wrx[n][j][f]; }
+          }
           dst = &sm.wlx[0][j][f];
           dstride = TY * (TX + 1);
         } else if (t < 2 * TY + 2) {
           if (!inplane || NDIM < 2) continue;
           const int r = t - (TY + 1);
           if (r > tye || lane >= txe) continue;
+          if constexpr (RECON == APK_RECON_DC) {
+            const double *q = prim + (long)kp * sk + (long)(j0 + r) * sj + (i0 + lane);
 #pragma unroll
-          for (int n = 0; n < NH; ++n) { L[n] = sm.wly[n][r][lane]; R[n] = sm.wry[n][r][lane]; }
+            for (int n = 0; n < NH; ++n) {
+              const long o = (long)var_of_slot(n, 1) * g.ncell;
+              L[n] = q[o - sj];
+              R[n] = q[o];
+            }
+          } else {
+#pragma unroll
+            for (int n = 0; n < NH; ++n) { L[n] = sm.wly[n][r][lane]; R[n] = sm.wry[n][r][lane]; }
+          }
           dst = &sm.wly[0][r][lane];
           dstride = (TY + 1) * TX;
         } else {
           if (NDIM < 3 || kp < g.ks) continue;
           const int j = t - (2 * TY + 2);
           if (j >= tye || lane >= txe) continue;
+          if constexpr (RECON == APK_RECON_DC) {
+            const double *q = prim + (long)kp * sk + (long)(j0 + j) * sj + (i0 + lane);
 #pragma unroll
-          for (int n = 0; n < NH; ++n) { L[n] = sm.wlz[cur][n][j][lane]; R[n] = sm.wrz[n][j][lane]; }
+            for (int n = 0; n < NH; ++n) {
+              const long o = (long)var_of_slot(n, 2) * g.ncell;
+              L[n] = q[o - sk];
+              R[n] = q[o];
+            }
+          } else {
+#pragma unroll
+            for (int n = 0; n < NH; ++n) { L[n] = sm.wlz[cur][n][j][lane]; R[n] = sm.wrz[n][j][lane]; }
+          }
           dst = &sm.wlz[cur][0][j][lane];
           dstride = TY * TX;
         }
