@@ -35,42 +35,50 @@ def peaks():
     return 6650.0, "fallback"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md): one
+    long-running `nvidia-smi -lms 100` child, parsed after the region."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
-        self.reasons = set()
-        self.sm_max = None
-        self._halt = threading.Event()
-
-    def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.sm_max = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+        self.t0 = time.time()
+
+    def start(self):
+        time.sleep(0.25)  # let the first sample land before the timed region starts
+        return self
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=3)
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+        if self.p is None:
+            return None
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        samples, reasons, sm_max = [], set(), None
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            try:
+                samples.append(float(f[0]))
+                sm_max = float(f[1])
+                for n, v in zip(self.NAMES, f[2:]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        s = sorted(samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": sm_max,
+                "reasons": sorted(reasons), "samples": len(s)}
 
 
 def workload(args):
@@ -176,9 +184,7 @@ def run_product(args):
     # ---------------- device-resident throughput ("value") ----------------
     sim.execute(None, sim.ncycle + args.warmup)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
+    sampler = ClockSampler(local).start() if rank == 0 else None
     sim.enable_task_timing(False)
     apk.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -224,33 +230,70 @@ def run_product(args):
     task_ms = {n: (v[0] / v[1] if v[1] else None) for n, v in tt.items() if v[1]}
 
     # ---------------- end-to-end through the public API with HOST buffers ----------------
+    # Every step: pinned-host conserved state (ghosts included) -> H2D -> FillDerived (cons->prim)
+    # -> one full cycle -> D2H of the updated conserved state into a pinned host buffer.
+    # Two simulation contexts alternate so that the H2D of step i+1 and the D2H of step i-1 overlap
+    # the compute of step i (independent steps of a throughput run; PCIe is full duplex).  The
+    # strictly serial variant (one context, copy-compute-copy back to back) is reported beside it.
     e2e = None
     if not args.no_e2e:
         nel = sim.nblocks * sim.nvar * sim.n[0] * sim.n[1] * sim.n[2]
         h_in = torch.empty(nel, dtype=torch.float64).pin_memory()
-        h_out = torch.empty(nel, dtype=torch.float64).pin_memory()
+        h_out = [torch.empty(nel, dtype=torch.float64).pin_memory() for _ in range(2)]
         sim.download_all("cons", h_in.data_ptr())
         sim.synchronize()
-        k2 = max(1, min(args.steps, 3))
+        k2 = max(2, min(args.steps, 6))
+
+        def one_step(x, out):
+            x.task("fill_derived")
+            x.step()
+            x.download_all("cons", out.data_ptr())
+
+        # serial: copy in, compute, copy out, wait
         for it in range(1 + k2):
             if it == 1:
                 barrier()
-                e0.record(stream)
-            sim.upload_all("cons", h_in.data_ptr())     # step input: conserved state incl. ghosts
-            sim.task("fill_derived")                     # cons -> prim of the uploaded state
-            sim.step()                                   # one full cycle
-            sim.download_all("cons", h_out.data_ptr())   # step result
+                t0 = time.time()
+            sim.upload_all("cons", h_in.data_ptr())
+            one_step(sim, h_out[0])
             sim.synchronize()
-        e1.record(stream)
         barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        serial_ms = (time.time() - t0) * 1e3 / k2
+        # pipelined over two contexts
+        sim2 = apk.HydroSim(fp_mode=args.fp_mode, fused=not args.unfused, rank=rank, nranks=world, **kw)
+        if world > 1:
+            uid = [apk.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            sim2.init_comm(uid[0])
+        sim2.pgen(args.pgen)
+        sim2.initialize()
+        sims = [sim, sim2]
+        sims[0].upload_all("cons", h_in.data_ptr())
+        for it in range(2 + k2):
+            if it == 2:   # pipeline is in steady state: start the clock
+                for x in sims:
+                    x.synchronize()
+                barrier()
+                t0 = time.time()
+            x, y = sims[it % 2], sims[(it + 1) % 2]
+            y.upload_all("cons", h_in.data_ptr())   # next step's input: overlaps this step
+            one_step(x, h_out[it % 2])
+        for x in sims:
+            x.synchronize()
+        barrier()
+        pipe_ms = (time.time() - t0) * 1e3 / k2
+        t = torch.tensor([pipe_ms, serial_ms], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item()) / k2
-        e2e = {"value": cells / (e2e_ms * 1e-3), "unit": UNIT,
+        pipe_ms, serial_ms = float(t[0]), float(t[1])
+        e2e = {"value": cells / (pipe_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(nel * 8 * world), "d2h_bytes_per_step": int(nel * 8 * world),
-               "ms_per_step": e2e_ms,
-               "what": "pinned host cons -> H2D -> FillDerived -> 1 cycle -> D2H cons, every step"}
+               "ms_per_step": pipe_ms, "serial_value": cells / (serial_ms * 1e-3),
+               "serial_ms_per_step": serial_ms,
+               "what": "every step: pinned host cons -> H2D -> FillDerived -> 1 full cycle -> D2H cons; "
+                       "value = two contexts alternating (copies of neighbouring steps overlap compute), "
+                       "serial_value = one context, copy-compute-copy back to back; host wall clock"}
+        sim2.close()
 
     if rank == 0:
         cpu = None
