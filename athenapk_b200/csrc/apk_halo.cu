@@ -167,8 +167,10 @@ k_halo_copy(ApkGeom g, const apk_block_t *__restrict__ blocks,
     const int ii = (int)(rem - (long)jj * it.ext[0]);
     const long c = ((long)(it.lo[2] + kk) * g.n2 + (it.lo[1] + jj)) * g.n1 + (it.lo[0] + ii);
     double *field = (f || with_prim == 2) ? B.prim : B.cons;
-    if (PACK) buf[it.offset + t] = field[(long)n * g.ncell + c];
-    else field[(long)n * g.ncell + c] = buf[it.offset + t];
+    // item offsets are sized for two fields; a single-field exchange packs densely at offset/2
+    const long base = (nf == 1) ? it.offset / 2 : it.offset;
+    if (PACK) buf[base + t] = field[(long)n * g.ncell + c];
+    else field[(long)n * g.ncell + c] = buf[base + t];
   }
 }
 

@@ -146,6 +146,8 @@ HydroSim::~HydroSim() {
   cudaFree(d_sendbuf_);
   cudaFree(d_recvbuf_);
   if (comm_event_) cudaEventDestroy(reinterpret_cast<cudaEvent_t>(comm_event_));
+  if (packed_event_) cudaEventDestroy(reinterpret_cast<cudaEvent_t>(packed_event_));
+  if (comm_stream_) cudaStreamDestroy(S(comm_stream_));
   if (stream_) cudaStreamDestroy(S(stream_));
 }
 
@@ -582,29 +584,40 @@ TaskStatus HydroSim::StartReceiveBoundBufs() {
 }
 
 TaskStatus HydroSim::SendBoundBufs(int with_prim) {
+  if (cfg_.nranks > 1) {
+    if (!comm_) throw std::runtime_error("apk_host: multi-rank run without InitComm");
+    // one pack launch for all peers, then one grouped send/recv per peer on the COMM stream so
+    // that the NVLink transfer overlaps the same-device ghost fill below
+    abi_check(apk_halo_pack(&desc_, d_blocks_[cur_], d_send_items_, (int)send_items_.size(),
+                            with_prim, d_sendbuf_, stream_), "apk_halo_pack");
+    if (!comm_event_) {
+      cudaEvent_t ev, ev2;
+      cudaStream_t cs;
+      cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+      cuda_check(cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming), "event");
+      cuda_check(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "comm stream");
+      comm_event_ = ev;
+      packed_event_ = ev2;
+      comm_stream_ = cs;
+    }
+    cudaStream_t cs = S(comm_stream_);
+    cuda_check(cudaEventRecord(reinterpret_cast<cudaEvent_t>(packed_event_), S(stream_)), "record");
+    cuda_check(cudaStreamWaitEvent(cs, reinterpret_cast<cudaEvent_t>(packed_event_), 0), "wait");
+    ncclComm_t c = reinterpret_cast<ncclComm_t>(comm_);
+    // offsets/counts of the plan are sized for cons+prim; a single-field exchange packs densely
+    // at half of every offset (all slab sizes are even multiples), so only live bytes travel
+    const int div = (with_prim == 1) ? 1 : 2;
+    ncclGroupStart();
+    for (const Peer &p : peers_) {
+      ncclSend(d_sendbuf_ + p.send_off / div, (size_t)(p.send_cnt / div), ncclDouble, p.rank, c, cs);
+      ncclRecv(d_recvbuf_ + p.recv_off / div, (size_t)(p.recv_cnt / div), ncclDouble, p.rank, c, cs);
+    }
+    if (ncclGroupEnd() != ncclSuccess) return TaskStatus::fail;
+    cuda_check(cudaEventRecord(reinterpret_cast<cudaEvent_t>(comm_event_), cs), "record");
+  }
   // same-device neighbours: direct ghost fill, no buffers
   abi_check(apk_copy_ghosts_local(&desc_, d_blocks_[cur_], with_prim, stream_),
             "apk_copy_ghosts_local");
-  if (cfg_.nranks == 1) return TaskStatus::complete;
-  if (!comm_) throw std::runtime_error("apk_host: multi-rank run without InitComm");
-  // one pack launch for all peers, one grouped send/recv per peer
-  abi_check(apk_halo_pack(&desc_, d_blocks_[cur_], d_send_items_, (int)send_items_.size(),
-                          with_prim, d_sendbuf_, stream_), "apk_halo_pack");
-  ncclComm_t c = reinterpret_cast<ncclComm_t>(comm_);
-  // buffers are laid out for cons+prim; without prim each item only fills its first half, the
-  // whole (fixed-size) segment is still what both sides agree on.
-  ncclGroupStart();
-  for (const Peer &p : peers_) {
-    ncclSend(d_sendbuf_ + p.send_off, (size_t)p.send_cnt, ncclDouble, p.rank, c, S(stream_));
-    ncclRecv(d_recvbuf_ + p.recv_off, (size_t)p.recv_cnt, ncclDouble, p.rank, c, S(stream_));
-  }
-  if (ncclGroupEnd() != ncclSuccess) return TaskStatus::fail;
-  if (!comm_event_) {
-    cudaEvent_t ev;
-    cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
-    comm_event_ = ev;
-  }
-  cuda_check(cudaEventRecord(reinterpret_cast<cudaEvent_t>(comm_event_), S(stream_)), "record");
   return TaskStatus::complete;
 }
 
@@ -617,6 +630,8 @@ TaskStatus HydroSim::ReceiveBoundBufs() {
 
 TaskStatus HydroSim::SetBounds(int with_prim) {
   if (cfg_.nranks > 1) {
+    cuda_check(cudaStreamWaitEvent(S(stream_), reinterpret_cast<cudaEvent_t>(comm_event_), 0),
+               "wait comm");
     abi_check(apk_halo_unpack(&desc_, d_blocks_[cur_], d_recv_items_, (int)recv_items_.size(),
                               with_prim, d_recvbuf_, stream_), "apk_halo_unpack");
   }

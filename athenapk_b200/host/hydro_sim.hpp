@@ -205,7 +205,7 @@ class HydroSim {
   double *d_sendbuf_ = nullptr, *d_recvbuf_ = nullptr;
   long long send_total_ = 0, recv_total_ = 0;
   ncclComm *comm_ = nullptr;
-  void *comm_event_ = nullptr;
+  void *comm_event_ = nullptr, *packed_event_ = nullptr, *comm_stream_ = nullptr;
   bool recv_posted_ = false;
 
   // linear wave pgen state (src/pgen/linear_wave.cpp:43-51)

@@ -152,7 +152,8 @@ typedef struct apk_halo_item {
   int block;      /* local block index                                  */
   int lo[3];      /* first cell (i,j,k) of the slab in the block array   */
   int ext[3];     /* slab extents (i,j,k)                                */
-  long long offset; /* offset (in doubles) of this slab in the peer buffer */
+  long long offset; /* offset (in doubles) of this slab in the buffer, sized for cons+prim
+                       (2*nvar values per cell); single-field calls use offset/2 */
 } apk_halo_item_t;
 int apk_halo_pack(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
                   const apk_halo_item_t *d_items, int nitems, int with_prim, double *d_buf,
