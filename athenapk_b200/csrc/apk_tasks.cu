@@ -255,7 +255,7 @@ k_cons_to_prim(ApkGeom g, const apk_block_t *__restrict__ blocks, EosPars eos, i
   for (int n = 0; n < 5; ++n) B.cons[(long)n * g.ncell + c] = u[n];
 #pragma unroll
   for (int n = 0; n < NH; ++n) B.prim[(long)n * g.ncell + c] = w[n];
-  const double di = 1.0 / u[0];
+  const double di = frcp(u[0]);
   for (int n = NH; n < g.nvar; ++n) B.prim[(long)n * g.ncell + c] = B.cons[(long)n * g.ncell + c] * di;
 }
 
