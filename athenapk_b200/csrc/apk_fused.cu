@@ -34,6 +34,12 @@ namespace {
 #ifndef APK_FUSED_UNROLL
 #define APK_FUSED_UNROLL 2
 #endif
+#ifndef APK_FUSED_MINBLOCKS
+#define APK_FUSED_MINBLOCKS 1  // CTAs per SM the register budget is sized for
+#endif
+#ifndef APK_FUSED_PREFETCH
+#define APK_FUSED_PREFETCH 1
+#endif
 #ifndef APK_FUSED_TY
 #define APK_FUSED_TY 8
 #endif
@@ -49,21 +55,36 @@ APK_DEV constexpr int slot_of_var(int v, int dir) {
   return v;
 }
 
-template <int NH>
+// One reconstruction warp task = one variable x one row of 32 cells.  The (direction, variable,
+// row) -> (global offset, stride, shared-memory destinations) decode is plane independent, so it
+// is done ONCE per CTA into a shared table; the per-plane loop then costs one LDS.128 and a few
+// integer instructions per task instead of ~90 (divisions by TY / TY+2, slot permutation, 64-bit
+// address arithmetic, row / tile-edge clamps) -- measured 45 % of the recon loop before.
+struct ReconTask {
+  int goff;    // element offset of the (clamped) row start relative to prim + plane offset
+  int stride;  // element stride along the sweep | dir << 28 | positivity << 30
+  int sl, sr;  // shared-memory element index of the L / R destination of lane 0, or -1
+};
+
+template <int NH, int NDIM>
 struct Smem {
+  static constexpr int NZ = (NDIM == 3) ? NH * TY : 0, NX = NH * TY,
+                       NY = (NDIM >= 2) ? NH * (TY + 2) : 0, NT = NZ + NX + NY;
   double wlx[NH][TY][TX + 1], wrx[NH][TY][TX + 1];
   double wly[NH][TY + 1][TX], wry[NH][TY + 1][TX];
   double wrz[NH][TY][TX], wlz[2][NH][TY][TX];
+  alignas(16) ReconTask tab[NT > 0 ? NT : 1];
+  double *push_prim[27], *push_cons[27];  // ghost-push destinations per neighbour offset (or null)
 };
 
 template <int FLUID, int RECON, int RS, int NDIM>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, APK_FUSED_MINBLOCKS)
 k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *__restrict__ prim_out,
               double g0, double g1, double bdt, double gamma, double c_h, double dedner_coeff,
               EosPars eos, int ntx, int flags, unsigned long long *dtmin) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<NH> &sm = *reinterpret_cast<Smem<NH> *>(smem_raw);
+  Smem<NH, NDIM> &sm = *reinterpret_cast<Smem<NH, NDIM> *>(smem_raw);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const apk_block_t &B = blocks[blockIdx.y];
@@ -94,9 +115,52 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   // recon work of one plane as a flat list of warp tasks (one task = one variable x one row of
   // 32 cells): [0,NZ) x3 rows, [NZ,NZ+NX) x1 rows, [NZ+NX, NZ+NX+NY) x2 rows -1..TY.
   // UNROLL tasks are fetched before the first one is evaluated (memory-level parallelism; with
-  // 9 warps per SM there are too few warps to hide HBM/L2 latency otherwise).
-  constexpr int NZ = (NDIM == 3) ? NH * TY : 0, NX = NH * TY, NY = (NDIM >= 2) ? NH * (TY + 2) : 0;
+  // 4 warps per scheduler there are too few warps to hide L2 latency otherwise).
+  constexpr int NZ = Smem<NH, NDIM>::NZ, NX = Smem<NH, NDIM>::NX, NT = Smem<NH, NDIM>::NT;
   constexpr int UNROLL = (RECON == APK_RECON_DC) ? 4 : APK_FUSED_UNROLL;
+  constexpr int ZBUF = NH * TY * TX;  // elements between wlz[0] and wlz[1]
+  double *const smd = reinterpret_cast<double *>(smem_raw);
+  if constexpr (RECON != APK_RECON_DC) {
+    for (int t = threadIdx.x; t < NT; t += NTHREADS) {
+      int dir, n, r;
+      if (t < NZ) { dir = 2; n = t / TY; r = t % TY; }
+      else if (t < NZ + NX) { dir = 0; n = (t - NZ) / TY; r = (t - NZ) % TY; }
+      else { dir = 1; n = (t - NZ - NX) / (TY + 2); r = (t - NZ - NX) % (TY + 2) - 1; }
+      // out-of-range rows evaluate a clamped (valid) stencil and skip the store, so the UNROLL
+      // reconstructions stay straight-line code the scheduler can interleave
+      const bool rok = (dir == 1) ? r <= tye : r < tye;
+      const int rc = min(r, dir == 1 ? tye : tye - 1);
+      ReconTask e;
+      e.goff = var_of_slot(n, dir) * (int)g.ncell + rc * (int)sj;
+      e.stride = (dir == 0 ? 1 : (dir == 1 ? (int)sj : (int)sk)) | (dir << 28) |
+                 ((n == 0 || n == 4) ? (1 << 30) : 0);
+      e.sl = e.sr = -1;
+      if (rok) {
+        if (dir == 2) {
+          e.sl = (int)(&sm.wlz[0][n][r][0] - smd);
+          e.sr = (int)(&sm.wrz[n][r][0] - smd);
+        } else if (dir == 0) {
+          e.sl = (int)(&sm.wlx[n][r][1] - smd);
+          e.sr = (int)(&sm.wrx[n][r][0] - smd);
+        } else {
+          if (r + 1 <= tye) e.sl = (int)(&sm.wly[n][r + 1][0] - smd);
+          if (r >= 0) e.sr = (int)(&sm.wry[n][r][0] - smd);
+        }
+      }
+      sm.tab[t] = e;
+    }
+    __syncthreads();
+  }
+  if (flags & (APK_FUSED_PUSH_PRIM | APK_FUSED_PUSH_CONS)) {
+    if (threadIdx.x < 27) {
+      const int nb = B.nbr[threadIdx.x];
+      sm.push_prim[threadIdx.x] = (nb >= 0 && (flags & APK_FUSED_PUSH_PRIM)) ? prim_out[nb] : nullptr;
+      sm.push_cons[threadIdx.x] = (nb >= 0 && (flags & APK_FUSED_PUSH_CONS)) ? blocks[nb].cons : nullptr;
+    }
+    __syncthreads();
+  }
+  const int lc = min(lane, txe - 1);
+  const bool lane_ok = lane < txe;
   int cur = 0;
   for (int kp = kfirst; kp <= klast; ++kp) {
     const bool inplane = (kp >= g.ks && kp <= g.ke);
@@ -104,51 +168,34 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
     // (donor cell: L/R states are the neighbouring cell values themselves; the Riemann tasks read
     //  them straight from global memory, no staging pass and no barrier)
     if constexpr (RECON != APK_RECON_DC) {
-      const int t_end = inplane ? NZ + NX + NY : NZ;
+      const int t_end = inplane ? NT : NZ;
       const long plane = (long)kp * sk + (long)j0 * sj + i0;
+      const double *__restrict__ pbase = prim + plane + lc;
+      const int zoff = (cur ^ 1) * ZBUF;
       for (int t0 = warp; t0 < t_end; t0 += UNROLL * NWARPS) {
         double v[UNROLL][5];
-        int dirs[UNROLL], ns[UNROLL], rows[UNROLL];
-        bool ok[UNROLL];
+        int sls[UNROLL], srs[UNROLL], sts[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          // out-of-range tasks / lanes evaluate a clamped (valid) stencil and skip the store, so
-          // the UNROLL reconstructions are straight-line code the scheduler can interleave
           const int tr = t0 + u * NWARPS;
-          const int t = min(tr, t_end - 1);
-          int dir, n, r;
-          if (t < NZ) { dir = 2; n = t / TY; r = t % TY; }
-          else if (t < NZ + NX) { dir = 0; n = (t - NZ) / TY; r = (t - NZ) % TY; }
-          else { dir = 1; n = (t - NZ - NX) / (TY + 2); r = (t - NZ - NX) % (TY + 2) - 1; }
-          dirs[u] = dir; ns[u] = n; rows[u] = r;
-          ok[u] = (tr < t_end) && lane < txe && (dir == 1 ? r <= tye : r < tye);
-          const int rc = min(r, dir == 1 ? tye : tye - 1), lc = min(lane, txe - 1);
-          const double *q = prim + (long)var_of_slot(n, dir) * g.ncell + plane + (long)rc * sj + lc;
-          load_stencil<RECON>(q, dir == 0 ? 1 : (dir == 1 ? sj : sk), v[u]);
+          const int4 e = *reinterpret_cast<const int4 *>(&sm.tab[min(tr, t_end - 1)]);
+          const bool ok = lane_ok && tr < t_end;
+          sls[u] = ok ? e.z + (tr < NZ ? zoff : 0) : -1;
+          srs[u] = ok ? e.w : -1;
+          sts[u] = e.y;
+          load_stencil<RECON>(pbase + e.x, e.y & 0x0fffffff, v[u]);
         }
         double qls[UNROLL], qrs[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          const int dir = dirs[u], n = ns[u];
-          recon_stencil<RECON>(v[u], dir == 0 ? dx1 : (dir == 1 ? dx2 : dx3), (n == 0 || n == 4),
+          const int dir = (sts[u] >> 28) & 3;
+          recon_stencil<RECON>(v[u], dir == 0 ? dx1 : (dir == 1 ? dx2 : dx3), (sts[u] >> 30) & 1,
                                qls[u], qrs[u]);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          if (ok[u]) {
-            const int dir = dirs[u], n = ns[u], r = rows[u];
-            const double ql = qls[u], qr = qrs[u];
-            if (dir == 2) {
-              sm.wrz[n][r][lane] = qr;
-              sm.wlz[cur ^ 1][n][r][lane] = ql;
-            } else if (dir == 0) {
-              sm.wlx[n][r][lane + 1] = ql;
-              sm.wrx[n][r][lane] = qr;
-            } else {
-              if (r + 1 <= tye) sm.wly[n][r + 1][lane] = ql;
-              if (r >= 0) sm.wry[n][r][lane] = qr;
-            }
-          }
+          if (sls[u] >= 0) smd[sls[u] + lane] = qls[u];
+          if (srs[u] >= 0) smd[srs[u] + lane] = qrs[u];
         }
       }
       if (inplane) {
@@ -168,6 +215,31 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
     }
     if constexpr (RECON != APK_RECON_DC) __syncthreads();
     // ------------------------------------------------------------------ riemann phase
+    if constexpr (RECON != APK_RECON_DC && APK_FUSED_PREFETCH) {
+      // The Riemann phase touches no global memory: use it to pull everything the NEXT recon phase
+      // reads for the first time into L1 -- the new top plane of the x3 stencils (kp+1+R) and,
+      // if plane kp+1 is swept in x1/x2, its halo rows/columns (one prefetch per 128 B line;
+      // ~2 per thread).  Measured before: 19 % of the recon loop was spent waiting for these
+      // L2/HBM misses (first use after the stencil loads).
+      constexpr int R = ReconTraits<RECON>::radius;
+      const int pn = kp + 1;
+      if (pn <= klast) {
+        const bool next_in = (pn >= g.ks && pn <= g.ke);
+        const int nzr = (NDIM == 3) ? tye : 0;                // rows of plane pn+R (x3 stencil top)
+        const int nyr = next_in ? (NDIM >= 2 ? tye + 2 + 2 * R : 1) : 0;  // rows of plane pn
+        const int ylo = (NDIM >= 2) ? -1 - R : 0;
+        const int nrow = nzr + nyr;
+        const int lo = -(1 + R), hi = txe + R;                // cell range along x1 (inclusive)
+        const int nseg = ((hi - lo + 1) * 8 + 127) / 128 + 1;
+        for (int p = threadIdx.x; p < NH * nrow * nseg; p += NTHREADS) {
+          const int seg = p % nseg, rv = p / nseg, rr = rv % nrow, v = rv / nrow;
+          const long row = (rr < nzr) ? (long)(pn + R) * sk + (long)(j0 + rr) * sj
+                                      : (long)pn * sk + (long)(j0 + ylo + (rr - nzr)) * sj;
+          const int c = min(lo + seg * 16, hi);
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(prim + (long)v * g.ncell + row + i0 + c));
+        }
+      }
+    }
     if (owner) {
       // the finalize phase of this iteration streams cons / u1 of plane kfin exactly once: start
       // the HBM fetch now so it overlaps the Riemann solves (12-16 warps/SM cannot hide it later)
@@ -305,6 +377,45 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           cons[o] = u[v];
           po[o] = w[v];
         }
+        if (flags & (APK_FUSED_PUSH_PRIM | APK_FUSED_PUSH_CONS)) {
+          // Same-device ghost exchange folded into the epilogue ("push"): a finished cell within
+          // ng of a block face is also the source of ghost cells of up to 7 neighbour blocks
+          // (sender side of bnd_info.cpp:136-230).  The neighbours' prim_out / cons ghost cells
+          // are not read by any CTA of this launch, so the stores are race free and the separate
+          // fill-ghosts pass (2 x 1 ms per cycle at 256^3) disappears.
+          const int gi = i0 + ci, gj = j0 + cj;
+          const bool lo1 = gi < g.is + g.ng, hi1 = gi > g.ie - g.ng;
+          const bool lo2 = NDIM >= 2 && gj < g.js + g.ng, hi2 = NDIM >= 2 && gj > g.je - g.ng;
+          const bool lo3 = NDIM == 3 && kfin < g.ks + g.ng, hi3 = NDIM == 3 && kfin > g.ke - g.ng;
+          if (lo1 | hi1 | lo2 | hi2 | lo3 | hi3) {
+            const long e1 = g.ie - g.is + 1, e2 = (long)(g.je - g.js + 1) * sj,
+                       e3 = (long)(g.ke - g.ks + 1) * sk;
+#pragma unroll 1
+            for (int o3 = (NDIM == 3 ? -1 : 0); o3 <= (NDIM == 3 ? 1 : 0); ++o3) {
+              if ((o3 < 0 && !lo3) || (o3 > 0 && !hi3)) continue;
+#pragma unroll 1
+              for (int o2 = (NDIM >= 2 ? -1 : 0); o2 <= (NDIM >= 2 ? 1 : 0); ++o2) {
+                if ((o2 < 0 && !lo2) || (o2 > 0 && !hi2)) continue;
+#pragma unroll 1
+                for (int o1 = -1; o1 <= 1; ++o1) {
+                  if ((o1 < 0 && !lo1) || (o1 > 0 && !hi1) || (o1 | o2 | o3) == 0) continue;
+                  const int o = (o3 + 1) * 9 + (o2 + 1) * 3 + (o1 + 1);
+                  const long cd = c - (o3 * e3 + o2 * e2 + o1 * e1);
+                  double *__restrict__ pd = sm.push_prim[o];
+                  double *__restrict__ cdst = sm.push_cons[o];
+                  if (pd) {  // null: physical boundary (k_bc), remote (k_halo_copy) or not requested
+#pragma unroll
+                    for (int v = 0; v < NH; ++v) pd[(long)v * g.ncell + cd] = w[v];
+                  }
+                  if (cdst) {
+#pragma unroll
+                    for (int v = 0; v < NH; ++v) cdst[(long)v * g.ncell + cd] = u[v];
+                  }
+                }
+              }
+            }
+          }
+        }
         if (dtmin) {  // hydro.cpp:845-895
           double lx, ly, lz;
           if constexpr (FLUID == APK_FLUID_EULER) {
@@ -349,7 +460,7 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
   const int ntx = (d.nx[0] + TX - 1) / TX;
   const int nty = (g.ndim >= 2) ? (d.nx[1] + TY - 1) / TY : 1;
   dim3 grid(ntx * nty, g.nb);
-  const size_t smem = sizeof(Smem<NH>);
+  const size_t smem = (g.ndim == 3) ? sizeof(Smem<NH, 3>) : (g.ndim == 2 ? sizeof(Smem<NH, 2>) : sizeof(Smem<NH, 1>));
   unsigned long long *dt = reinterpret_cast<unsigned long long *>(d_dtmin);
 #define APK_LAUNCH_FUSED(ND)                                                                     \
   {                                                                                              \

@@ -570,7 +570,9 @@ TaskStatus HydroSim::FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, b
                "init dtmin");
   }
   abi_check(apk_stage_fused(&desc_, d_blocks_[cur_], d_prim_out_[cur_], gam0, gam1, beta_dt, c_h,
-                            mindx, cfg_.glmmhd_alpha, recon, stage == 1 ? APK_FUSED_SAVE_U1 : 0,
+                            mindx, cfg_.glmmhd_alpha, recon,
+                            (stage == 1 ? APK_FUSED_SAVE_U1 : 0) | APK_FUSED_PUSH_PRIM |
+                                (last_stage ? APK_FUSED_PUSH_CONS : 0),
                             dtmin, stream_), "apk_stage_fused");
   cur_ ^= 1;  // prim_out becomes "prim"
   return TaskStatus::complete;
@@ -583,7 +585,7 @@ TaskStatus HydroSim::StartReceiveBoundBufs() {
   return TaskStatus::complete;
 }
 
-TaskStatus HydroSim::SendBoundBufs(int with_prim) {
+TaskStatus HydroSim::SendBoundBufs(int with_prim, bool local_done) {
   if (cfg_.nranks > 1) {
     if (!comm_) throw std::runtime_error("apk_host: multi-rank run without InitComm");
     // one pack launch for all peers, then one grouped send/recv per peer on the COMM stream so
@@ -615,9 +617,11 @@ TaskStatus HydroSim::SendBoundBufs(int with_prim) {
     if (ncclGroupEnd() != ncclSuccess) return TaskStatus::fail;
     cuda_check(cudaEventRecord(reinterpret_cast<cudaEvent_t>(comm_event_), cs), "record");
   }
-  // same-device neighbours: direct ghost fill, no buffers
-  abi_check(apk_copy_ghosts_local(&desc_, d_blocks_[cur_], with_prim, stream_),
-            "apk_copy_ghosts_local");
+  // same-device neighbours: direct ghost fill, no buffers (fused stages have already pushed
+  // their boundary cells into the neighbours' ghost zones, APK_FUSED_PUSH_*)
+  if (!local_done)
+    abi_check(apk_copy_ghosts_local(&desc_, d_blocks_[cur_], with_prim, stream_),
+              "apk_copy_ghosts_local");
   return TaskStatus::complete;
 }
 
@@ -737,7 +741,7 @@ void HydroSim::MakeTaskCollection(TaskList &tl, int stage) {
     // between stages only prim ghosts are consumed; the last stage also completes cons so the
     // state handed back after the cycle is identical to the reference's, ghosts included
     const int fields = last ? 1 : 2;
-    tl.AddTask("send", [=] { return SendBoundBufs(fields); });
+    tl.AddTask("send", [=] { return SendBoundBufs(fields, true); });
     tl.AddTask("recv", [this] { return ReceiveBoundBufs(); });
     tl.AddTask("set", [=] { return SetBounds(fields); });
     tl.AddTask("fbound", [=] { return ApplyBoundaryConditions(fields); });

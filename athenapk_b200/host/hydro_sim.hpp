@@ -131,7 +131,8 @@ class HydroSim {
   TaskStatus AddUnsplitSources(Real beta_dt);
   TaskStatus FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, bool last_stage);
   TaskStatus StartReceiveBoundBufs();
-  TaskStatus SendBoundBufs(int with_prim);  // 0 cons, 1 cons+prim, 2 prim only
+  // with_prim: 0 cons, 1 cons+prim, 2 prim only; local_done: same-device ghosts already pushed
+  TaskStatus SendBoundBufs(int with_prim, bool local_done = false);
   TaskStatus ReceiveBoundBufs();
   TaskStatus SetBounds(int with_prim);
   TaskStatus ApplyBoundaryConditions(int with_prim);

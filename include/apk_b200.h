@@ -175,6 +175,11 @@ int apk_stage_fused(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
                     double *d_dtmin, void *stream);
 #define APK_FUSED_SAVE_U1 1 /* flags: also store the incoming cons into cons_u1 (first stage:
                                replaces the u1 <- u0 DeepCopy of hydro_driver.cpp:474-495) */
+#define APK_FUSED_PUSH_PRIM 2 /* flags: finished cells within ng of a block face are also written
+                                 into the ghost cells of prim_out of the same-device neighbour
+                                 blocks (nbr[] >= 0): replaces apk_copy_ghosts_local(prim)     */
+#define APK_FUSED_PUSH_CONS 4 /* same for cons (last stage: the caller-visible state after the
+                                 cycle has valid cons ghosts like the reference's)            */
 
 /* copy cons -> cons_u1 for all blocks (u1 <- u0 at stage 1, hydro_driver.cpp:474-495) */
 int apk_save_u1(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, void *stream);
