@@ -40,6 +40,9 @@ namespace {
 #ifndef APK_FUSED_PREFETCH
 #define APK_FUSED_PREFETCH 1
 #endif
+#ifndef APK_FUSED_SWPIPE
+#define APK_FUSED_SWPIPE 0  // measured: no gain at 256^3 (the loads are not the limiter), costs registers
+#endif
 #ifndef APK_FUSED_TY
 #define APK_FUSED_TY 8
 #endif
@@ -172,30 +175,62 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       const long plane = (long)kp * sk + (long)j0 * sj + i0;
       const double *__restrict__ pbase = prim + plane + lc;
       const int zoff = (cur ^ 1) * ZBUF;
-      for (int t0 = warp; t0 < t_end; t0 += UNROLL * NWARPS) {
+      // Software pipeline over batches of UNROLL tasks: the stencil loads of batch b+1 are in
+      // flight while batch b is evaluated (two register buffers A/B, loop unrolled by two so no
+      // register copies).  With <= 4 warps per scheduler and ~40 KB of L1 next to the shared
+      // arrays of three resident CTAs, most of these loads are L2 hits (~300-600 cycles) that
+      // nothing else can hide (measured 22 % of the recon phase in long_scoreboard before).
+      constexpr int STEP = UNROLL * NWARPS;
+      struct Batch {
         double v[UNROLL][5];
-        int sls[UNROLL], srs[UNROLL], sts[UNROLL];
+        int sl[UNROLL], sr[UNROLL], st[UNROLL];
+      };
+      auto fetch = [&](Batch &b, int t0) {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
           const int tr = t0 + u * NWARPS;
           const int4 e = *reinterpret_cast<const int4 *>(&sm.tab[min(tr, t_end - 1)]);
           const bool ok = lane_ok && tr < t_end;
-          sls[u] = ok ? e.z + (tr < NZ ? zoff : 0) : -1;
-          srs[u] = ok ? e.w : -1;
-          sts[u] = e.y;
-          load_stencil<RECON>(pbase + e.x, e.y & 0x0fffffff, v[u]);
+          b.sl[u] = ok ? e.z + (tr < NZ ? zoff : 0) : -1;
+          b.sr[u] = ok ? e.w : -1;
+          b.st[u] = e.y;
+          load_stencil<RECON>(pbase + e.x, e.y & 0x0fffffff, b.v[u]);
         }
+      };
+      auto evaluate = [&](const Batch &b) {
         double qls[UNROLL], qrs[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          const int dir = (sts[u] >> 28) & 3;
-          recon_stencil<RECON>(v[u], dir == 0 ? dx1 : (dir == 1 ? dx2 : dx3), (sts[u] >> 30) & 1,
-                               qls[u], qrs[u]);
+          const int dir = (b.st[u] >> 28) & 3;
+          recon_stencil<RECON>(b.v[u], dir == 0 ? dx1 : (dir == 1 ? dx2 : dx3),
+                               (b.st[u] >> 30) & 1, qls[u], qrs[u]);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          if (sls[u] >= 0) smd[sls[u] + lane] = qls[u];
-          if (srs[u] >= 0) smd[srs[u] + lane] = qrs[u];
+          if (b.sl[u] >= 0) smd[b.sl[u] + lane] = qls[u];
+          if (b.sr[u] >= 0) smd[b.sr[u] + lane] = qrs[u];
+        }
+      };
+      if constexpr (APK_FUSED_SWPIPE) {
+        Batch A, Bb;
+        int t0 = warp;
+        if (t0 < t_end) fetch(A, t0);
+        while (t0 < t_end) {
+          const bool more1 = t0 + STEP < t_end;
+          if (more1) fetch(Bb, t0 + STEP);
+          evaluate(A);
+          if (!more1) break;
+          const bool more2 = t0 + 2 * STEP < t_end;
+          if (more2) fetch(A, t0 + 2 * STEP);
+          evaluate(Bb);
+          t0 += 2 * STEP;
+          if (!more2) break;
+        }
+      } else {
+        for (int t0 = warp; t0 < t_end; t0 += STEP) {
+          Batch A;
+          fetch(A, t0);
+          evaluate(A);
         }
       }
       if (inplane) {
