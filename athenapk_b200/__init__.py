@@ -72,7 +72,7 @@ ABI_SYMBOLS = [
     "apk_calc_fluxes", "apk_fofc_workspace_bytes", "apk_first_order_flux_correct",
     "apk_flux_div_update", "apk_dedner_source", "apk_cons_to_prim", "apk_min_dt",
     "apk_min_dt_async", "apk_fill_ghosts_local", "apk_apply_physical_bcs",
-    "apk_copy_ghosts_local", "apk_halo_pack", "apk_halo_unpack", "apk_stage_fused",
+    "apk_copy_ghosts_local", "apk_halo_pack", "apk_halo_unpack", "apk_stage_fused", "apk_stage_fused_p2p",
     "apk_save_u1", "apk_fp64_probe",
 ]
 SIM_SYMBOLS = [
@@ -81,7 +81,7 @@ SIM_SYMBOLS = [
     "apk_sim_execute", "apk_sim_step", "apk_sim_num_local_blocks", "apk_sim_num_global_blocks",
     "apk_sim_nvar", "apk_sim_block_dims", "apk_sim_block_info", "apk_sim_copy_to_host",
     "apk_sim_copy_from_host", "apk_sim_device_ptr", "apk_sim_time", "apk_sim_dt",
-    "apk_sim_ncycle", "apk_sim_c_h", "apk_sim_fofc_corrections", "apk_sim_fused_active",
+    "apk_sim_ncycle", "apk_sim_c_h", "apk_sim_fofc_corrections", "apk_sim_fused_active", "apk_sim_p2p_active",
     "apk_sim_linear_wave_period", "apk_sim_linear_wave_errors", "apk_sim_stream",
     "apk_sim_pack_desc", "apk_sim_device_blocks", "apk_sim_synchronize", "apk_sim_task",
     "apk_sim_set_c_h", "apk_sim_upload_all", "apk_sim_download_all",
@@ -152,7 +152,7 @@ def lib():
     L.apk_sim_execute.argtypes = [vp, C.c_double, C.c_int]
     L.apk_sim_step.argtypes = [vp]
     for f in ("apk_sim_num_local_blocks", "apk_sim_num_global_blocks", "apk_sim_nvar",
-              "apk_sim_ncycle", "apk_sim_fused_active", "apk_sim_synchronize"):
+              "apk_sim_ncycle", "apk_sim_fused_active", "apk_sim_p2p_active", "apk_sim_synchronize"):
         getattr(L, f).argtypes = [vp]
     L.apk_sim_block_dims.argtypes = [vp, ip]
     L.apk_sim_block_info.argtypes = [vp, C.c_int, ip, ip, dp, dp]
@@ -345,6 +345,7 @@ class HydroSim:
     c_h = property(lambda s: s.L.apk_sim_c_h(s.h))
     fofc_corrections = property(lambda s: s.L.apk_sim_fofc_corrections(s.h))
     fused_active = property(lambda s: bool(s.L.apk_sim_fused_active(s.h)))
+    p2p_active = property(lambda s: bool(s.L.apk_sim_p2p_active(s.h)))
     lw_tlim = property(lambda s: s.L.apk_sim_linear_wave_period(s.h))
     stream = property(lambda s: s.L.apk_sim_stream(s.h))
 

@@ -167,10 +167,10 @@ int apk_halo_unpack(const apk_pack_desc_t *d, const apk_block_t *blocks,
   return cuda_ok("apk_halo_unpack");
 }
 
-int apk_stage_fused(const apk_pack_desc_t *d, const apk_block_t *blocks,
-                    double *const *d_prim_out, double gam0, double gam1, double beta_dt,
-                    double c_h, double mindx, double alpha, int recon_override, int flags,
-                    double *d_dtmin, void *stream) {
+int apk_stage_fused_p2p(const apk_pack_desc_t *d, const apk_block_t *blocks,
+                        double *const *d_prim_out, const apk_push_dst_t *d_push, double gam0,
+                        double gam1, double beta_dt, double c_h, double mindx, double alpha,
+                        int recon_override, int flags, double *d_dtmin, void *stream) {
   if (check(d, blocks, "apk_stage_fused: bad descriptor")) return 1;
   if (!d_prim_out) {
     apk_common::set_error("apk_stage_fused: null prim_out");
@@ -179,8 +179,16 @@ int apk_stage_fused(const apk_pack_desc_t *d, const apk_block_t *blocks,
   const double coeff =
       (d->fluid == APK_FLUID_GLMMHD) ? std::exp(-alpha * c_h * beta_dt / mindx) : 1.0;
   int rc = DISPATCH(d, launch_stage_fused(*d, blocks, d_prim_out, gam0, gam1, beta_dt, c_h, coeff,
-                                          recon_override, flags, d_dtmin, S(stream)));
+                                          recon_override, flags, d_dtmin, d_push, S(stream)));
   return rc ? rc : cuda_ok("apk_stage_fused");
+}
+
+int apk_stage_fused(const apk_pack_desc_t *d, const apk_block_t *blocks,
+                    double *const *d_prim_out, double gam0, double gam1, double beta_dt,
+                    double c_h, double mindx, double alpha, int recon_override, int flags,
+                    double *d_dtmin, void *stream) {
+  return apk_stage_fused_p2p(d, blocks, d_prim_out, nullptr, gam0, gam1, beta_dt, c_h, mindx, alpha,
+                             recon_override, flags, d_dtmin, stream);
 }
 
 int apk_save_u1(const apk_pack_desc_t *d, const apk_block_t *blocks, void *stream) {

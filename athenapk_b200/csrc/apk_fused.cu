@@ -84,7 +84,8 @@ template <int FLUID, int RECON, int RS, int NDIM>
 __global__ void __launch_bounds__(NTHREADS, APK_FUSED_MINBLOCKS)
 k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *__restrict__ prim_out,
               double g0, double g1, double bdt, double gamma, double c_h, double dedner_coeff,
-              EosPars eos, int ntx, int flags, unsigned long long *dtmin) {
+              EosPars eos, int ntx, int flags, unsigned long long *dtmin,
+              const apk_push_dst_t *__restrict__ push) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<NH, NDIM> &sm = *reinterpret_cast<Smem<NH, NDIM> *>(smem_raw);
@@ -156,9 +157,19 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   }
   if (flags & (APK_FUSED_PUSH_PRIM | APK_FUSED_PUSH_CONS)) {
     if (threadIdx.x < 27) {
-      const int nb = B.nbr[threadIdx.x];
-      sm.push_prim[threadIdx.x] = (nb >= 0 && (flags & APK_FUSED_PUSH_PRIM)) ? prim_out[nb] : nullptr;
-      sm.push_cons[threadIdx.x] = (nb >= 0 && (flags & APK_FUSED_PUSH_CONS)) ? blocks[nb].cons : nullptr;
+      double *pp = nullptr, *pc = nullptr;
+      if (push) {  // explicit destinations (may be peer-GPU memory: halo exchange as NVLink stores)
+        pp = push[blockIdx.y * 27 + threadIdx.x].prim;
+        pc = push[blockIdx.y * 27 + threadIdx.x].cons;
+      } else {
+        const int nb = B.nbr[threadIdx.x];
+        if (nb >= 0) {
+          pp = prim_out[nb];
+          pc = blocks[nb].cons;
+        }
+      }
+      sm.push_prim[threadIdx.x] = (flags & APK_FUSED_PUSH_PRIM) ? pp : nullptr;
+      sm.push_cons[threadIdx.x] = (flags & APK_FUSED_PUSH_CONS) ? pc : nullptr;
     }
     __syncthreads();
   }
@@ -489,7 +500,8 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
 template <int FLUID, int RECON, int RS>
 int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
               double *const *prim_out, double g0, double g1, double bdt, double c_h,
-              double coeff, int flags, double *d_dtmin, cudaStream_t s) {
+              double coeff, int flags, double *d_dtmin, const apk_push_dst_t *push,
+              cudaStream_t s) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
   const EosPars eos = {d.gamma, d.dfloor, d.pfloor, d.efloor, d.vceil, d.eceil};
   const int ntx = (d.nx[0] + TX - 1) / TX;
@@ -506,7 +518,7 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
       attr_set = true;                                                                           \
     }                                                                                            \
     kern<<<grid, NTHREADS, smem, s>>>(g, blocks, prim_out, g0, g1, bdt, d.gamma, c_h, coeff, eos, \
-                                      ntx, flags, dt);                                                  \
+                                      ntx, flags, dt, push);                                            \
   }
   if (g.ndim == 3) APK_LAUNCH_FUSED(3)
   else if (g.ndim == 2) APK_LAUNCH_FUSED(2)
@@ -519,14 +531,15 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
 template <int FLUID, int RS>
 int fused_recon(int recon, const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
                 double *const *prim_out, double g0, double g1, double bdt, double c_h,
-                double coeff, int flags, double *dt, cudaStream_t s) {
+                double coeff, int flags, double *dt, const apk_push_dst_t *push,
+                cudaStream_t s) {
   switch (recon) {
-  case APK_RECON_DC: return run_fused<FLUID, APK_RECON_DC, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, s);
-  case APK_RECON_PLM: return run_fused<FLUID, APK_RECON_PLM, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, s);
-  case APK_RECON_PPM: return run_fused<FLUID, APK_RECON_PPM, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, s);
-  case APK_RECON_WENOZ: return run_fused<FLUID, APK_RECON_WENOZ, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, s);
-  case APK_RECON_WENO3: return run_fused<FLUID, APK_RECON_WENO3, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, s);
-  case APK_RECON_LIMO3: return run_fused<FLUID, APK_RECON_LIMO3, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, s);
+  case APK_RECON_DC: return run_fused<FLUID, APK_RECON_DC, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, push, s);
+  case APK_RECON_PLM: return run_fused<FLUID, APK_RECON_PLM, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, push, s);
+  case APK_RECON_PPM: return run_fused<FLUID, APK_RECON_PPM, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, push, s);
+  case APK_RECON_WENOZ: return run_fused<FLUID, APK_RECON_WENOZ, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, push, s);
+  case APK_RECON_WENO3: return run_fused<FLUID, APK_RECON_WENO3, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, push, s);
+  case APK_RECON_LIMO3: return run_fused<FLUID, APK_RECON_LIMO3, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, push, s);
   }
   apk_common::set_error("apk_stage_fused: unknown reconstruction");
   return 1;
@@ -541,11 +554,12 @@ int fused_recon(int recon, const apk_pack_desc_t &d, const ApkGeom &g, const apk
 int launch_stage_fused_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
                            double *const *prim_out, double g0, double g1, double bdt, double c_h,
                            double dedner_coeff, int recon, int flags, double *d_dtmin,
-                           cudaStream_t s);
+                           const apk_push_dst_t *push, cudaStream_t s);
 
 int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
                        double *const *prim_out, double g0, double g1, double bdt, double c_h,
-                       double dedner_coeff, int recon, int flags, double *d_dtmin, cudaStream_t s) {
+                       double dedner_coeff, int recon, int flags, double *d_dtmin,
+                       const apk_push_dst_t *push, cudaStream_t s) {
   const ApkGeom g = apk_make_geom(d);
   if (recon < 0) recon = d.recon;
   if (d.nscalars != 0) {
@@ -554,13 +568,13 @@ int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
   }
   if (d.fluid == APK_FLUID_EULER) {
     switch (d.riemann) {
-    case APK_RIEMANN_NONE: return run_fused<APK_FLUID_EULER, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, s);
-    case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, s);
-    case APK_RIEMANN_HLLC: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLC>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, s);
+    case APK_RIEMANN_NONE: return run_fused<APK_FLUID_EULER, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, push, s);
+    case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, push, s);
+    case APK_RIEMANN_HLLC: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLC>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, push, s);
     }
   } else {
     return launch_stage_fused_mhd(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, recon,
-                                  flags, d_dtmin, s);
+                                  flags, d_dtmin, push, s);
   }
   apk_common::set_error("apk_stage_fused: unsupported fluid/riemann combination");
   return 1;
@@ -568,11 +582,12 @@ int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
 #else
 int launch_stage_fused_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
                            double *const *prim_out, double g0, double g1, double bdt, double c_h,
-                           double dedner_coeff, int recon, int flags, double *d_dtmin, cudaStream_t s) {
+                           double dedner_coeff, int recon, int flags, double *d_dtmin,
+                           const apk_push_dst_t *push, cudaStream_t s) {
   switch (d.riemann) {
-  case APK_RIEMANN_NONE: return run_fused<APK_FLUID_GLMMHD, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, s);
-  case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, s);
-  case APK_RIEMANN_HLLD: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLD>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, s);
+  case APK_RIEMANN_NONE: return run_fused<APK_FLUID_GLMMHD, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, push, s);
+  case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, push, s);
+  case APK_RIEMANN_HLLD: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLD>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, push, s);
   }
   apk_common::set_error("apk_stage_fused: unsupported fluid/riemann combination");
   return 1;

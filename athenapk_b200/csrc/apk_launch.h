@@ -28,7 +28,7 @@
   int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,                   \
                          double *const *prim_out, double g0, double g1, double bdt, double c_h, \
                          double dedner_coeff, int recon, int flags, double *d_dtmin,            \
-                         cudaStream_t s);                                                       \
+                         const apk_push_dst_t *push, cudaStream_t s);                           \
   }
 
 APK_DECLARE_LAUNCHERS(apk_fast)

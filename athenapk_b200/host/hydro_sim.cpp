@@ -5,6 +5,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <array>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -143,6 +144,10 @@ HydroSim::~HydroSim() {
   cudaFree(d_fofc_work_);
   cudaFree(d_send_items_);
   cudaFree(d_recv_items_);
+  for (void *m : peer_mapped_) cudaIpcCloseMemHandle(m);
+  cudaFree(d_push_[0]);
+  cudaFree(d_push_[1]);
+  cudaFree(d_barrier_);
   cudaFree(d_sendbuf_);
   cudaFree(d_recvbuf_);
   if (comm_event_) cudaEventDestroy(reinterpret_cast<cudaEvent_t>(comm_event_));
@@ -440,7 +445,115 @@ int HydroSim::InitComm(const void *uid, int nbytes) {
   ncclComm_t c;
   if (ncclCommInitRank(&c, cfg_.nranks, id, cfg_.rank) != ncclSuccess) return -2;
   comm_ = reinterpret_cast<ncclComm *>(c);
+  SetupPeerPush();
   return 0;
+}
+
+// Map the field buffers of every neighbour rank (CUDA IPC over NVLink/NVSwitch peer access) and
+// build, per prim ping-pong parity, the [nblocks][27] table of ghost-push destinations used by
+// apk_stage_fused_p2p.  Any failure (no peer access, ranks sharing a process, APK_B200_P2P=0) on
+// any rank keeps every rank on the packed NCCL send/recv path.
+void HydroSim::SetupPeerPush() {
+  p2p_ = false;
+  if (!fused_ || cfg_.plan_only || cfg_.nranks == 1) return;
+  ncclComm_t c = reinterpret_cast<ncclComm_t>(comm_);
+  cudaStream_t st = S(stream_);
+  const int nr = cfg_.nranks;
+  const char *env = std::getenv("APK_B200_P2P");
+  int ok = !(env && env[0] == '0');
+  struct Handles {
+    cudaIpcMemHandle_t h[3];
+  };
+  Handles mine{};
+  double *bufs[3] = {d_cons_, d_prim_[0], d_prim_[1]};
+  for (int f = 0; f < 3; ++f)
+    if (cudaIpcGetMemHandle(&mine.h[f], bufs[f]) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  std::vector<Handles> all(nr);
+  char *d_all = nullptr;
+  cuda_check(cudaMalloc(&d_all, sizeof(Handles) * nr), "ipc gather");
+  cuda_check(cudaMalloc(&d_barrier_, 2 * sizeof(int)), "barrier word");
+  cuda_check(cudaMemset(d_barrier_, 0, 2 * sizeof(int)), "barrier word");
+  cuda_check(cudaMemcpyAsync(d_all + sizeof(Handles) * cfg_.rank, &mine, sizeof(Handles),
+                             cudaMemcpyHostToDevice, st), "ipc handles");
+  ncclAllGather(d_all + sizeof(Handles) * cfg_.rank, d_all, sizeof(Handles), ncclChar, c, st);
+  cuda_check(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * nr, cudaMemcpyDeviceToHost, st),
+             "ipc handles");
+  cuda_check(cudaStreamSynchronize(st), "ipc handles");
+  cudaFree(d_all);
+
+  const int base = nblocks_global_ / nr, rem = nblocks_global_ % nr;
+  auto rank_of = [&](int gid) {
+    const int cut = rem * (base + 1);
+    return (gid < cut) ? gid / (base + 1) : rem + (gid - cut) / base;
+  };
+  auto first_gid = [&](int r) { return r * base + std::min(r, rem); };
+  // remote neighbour of (block, offset index): its global id
+  auto remote_gid = [&](size_t b, int idx) {
+    const int off[3] = {idx % 3 - 1, (idx / 3) % 3 - 1, idx / 9 - 1};
+    int nl[3];
+    for (int d = 0; d < 3; ++d) nl[d] = ((blocks_[b].loc[d] + off[d]) % nb_[d] + nb_[d]) % nb_[d];
+    return gid_of_loc_[nl[0] + nb_[0] * (nl[1] + nb_[1] * nl[2])];
+  };
+  std::vector<std::array<double *, 3>> peer(nr, std::array<double *, 3>{nullptr, nullptr, nullptr});
+  for (size_t b = 0; b < blocks_.size() && ok; ++b)
+    for (int idx = 0; idx < 27 && ok; ++idx) {
+      const int nb = h_blocks_[b].nbr[idx];
+      if (nb >= 0 || nb == APK_NBR_NONE) continue;
+      const int r = rank_of(remote_gid(b, idx));
+      if (peer[r][0]) continue;
+      for (int f = 0; f < 3; ++f) {
+        void *m = nullptr;
+        if (cudaIpcOpenMemHandle(&m, all[r].h[f], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          ok = 0;
+          cudaGetLastError();
+          break;
+        }
+        peer_mapped_.push_back(m);
+        peer[r][f] = static_cast<double *>(m);
+      }
+    }
+  // all ranks must agree
+  cuda_check(cudaMemcpyAsync(d_barrier_ + 1, &ok, sizeof(int), cudaMemcpyHostToDevice, st), "p2p flag");
+  ncclAllReduce(d_barrier_ + 1, d_barrier_ + 1, 1, ncclInt, ncclMin, c, st);
+  int all_ok = 0;
+  cuda_check(cudaMemcpyAsync(&all_ok, d_barrier_ + 1, sizeof(int), cudaMemcpyDeviceToHost, st), "p2p flag");
+  cuda_check(cudaStreamSynchronize(st), "p2p flag");
+  if (!all_ok) {
+    for (void *m : peer_mapped_) cudaIpcCloseMemHandle(m);
+    peer_mapped_.clear();
+    return;
+  }
+  const size_t per = BlockFieldElems(), nbl = blocks_.size();
+  for (int which = 0; which < 2; ++which) {
+    std::vector<apk_push_dst_t> tab(nbl * 27, apk_push_dst_t{nullptr, nullptr});
+    for (size_t b = 0; b < nbl; ++b)
+      for (int idx = 0; idx < 27; ++idx) {
+        const int nb = h_blocks_[b].nbr[idx];
+        if (nb == APK_NBR_NONE) continue;
+        apk_push_dst_t &e = tab[b * 27 + idx];
+        if (nb >= 0) {
+          e.prim = d_prim_[1 - which] + nb * per;
+          e.cons = d_cons_ + nb * per;
+        } else {
+          const int ngid = remote_gid(b, idx), r = rank_of(ngid);
+          const size_t l = (size_t)(ngid - first_gid(r));
+          e.prim = peer[r][1 + (1 - which)] + l * per;
+          e.cons = peer[r][0] + l * per;
+        }
+      }
+    cuda_check(cudaMalloc(&d_push_[which], tab.size() * sizeof(apk_push_dst_t)), "push table");
+    cuda_check(cudaMemcpy(d_push_[which], tab.data(), tab.size() * sizeof(apk_push_dst_t),
+                          cudaMemcpyHostToDevice), "push table");
+  }
+  p2p_ = true;
+}
+
+// cross-rank barrier in stream order: every rank's stage kernel (and its peer stores) has
+// completed before any rank's next kernel on this stream starts
+void HydroSim::StageBarrier() {
+  ncclAllReduce(d_barrier_, d_barrier_, 1, ncclInt, ncclSum, reinterpret_cast<ncclComm_t>(comm_),
+                S(stream_));
 }
 
 double *HydroSim::DevicePtr(int field, int block) {
@@ -569,7 +682,8 @@ TaskStatus HydroSim::FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, b
     cuda_check(cudaMemcpyAsync(d_scalars_, &big, sizeof(double), cudaMemcpyHostToDevice, S(stream_)),
                "init dtmin");
   }
-  abi_check(apk_stage_fused(&desc_, d_blocks_[cur_], d_prim_out_[cur_], gam0, gam1, beta_dt, c_h,
+  abi_check(apk_stage_fused_p2p(&desc_, d_blocks_[cur_], d_prim_out_[cur_],
+                                p2p_ ? d_push_[cur_] : nullptr, gam0, gam1, beta_dt, c_h,
                             mindx, cfg_.glmmhd_alpha, recon,
                             (stage == 1 ? APK_FUSED_SAVE_U1 : 0) | APK_FUSED_PUSH_PRIM |
                                 (last_stage ? APK_FUSED_PUSH_CONS : 0),
@@ -585,8 +699,16 @@ TaskStatus HydroSim::StartReceiveBoundBufs() {
   return TaskStatus::complete;
 }
 
-TaskStatus HydroSim::SendBoundBufs(int with_prim, bool local_done) {
+TaskStatus HydroSim::SendBoundBufs(int with_prim, bool local_done, bool need_barrier) {
+  nccl_inflight_ = false;
+  if (cfg_.nranks > 1 && local_done && p2p_) {
+    // remote neighbours were served by peer stores of the stage kernel as well: no pack, no
+    // send/recv, no unpack -- only the stage boundary
+    if (need_barrier) StageBarrier();
+    return TaskStatus::complete;
+  }
   if (cfg_.nranks > 1) {
+    nccl_inflight_ = true;
     if (!comm_) throw std::runtime_error("apk_host: multi-rank run without InitComm");
     // one pack launch for all peers, then one grouped send/recv per peer on the COMM stream so
     // that the NVLink transfer overlaps the same-device ghost fill below
@@ -633,7 +755,7 @@ TaskStatus HydroSim::ReceiveBoundBufs() {
 }
 
 TaskStatus HydroSim::SetBounds(int with_prim) {
-  if (cfg_.nranks > 1) {
+  if (cfg_.nranks > 1 && nccl_inflight_) {
     cuda_check(cudaStreamWaitEvent(S(stream_), reinterpret_cast<cudaEvent_t>(comm_event_), 0),
                "wait comm");
     abi_check(apk_halo_unpack(&desc_, d_blocks_[cur_], d_recv_items_, (int)recv_items_.size(),
@@ -741,7 +863,10 @@ void HydroSim::MakeTaskCollection(TaskList &tl, int stage) {
     // between stages only prim ghosts are consumed; the last stage also completes cons so the
     // state handed back after the cycle is identical to the reference's, ghosts included
     const int fields = last ? 1 : 2;
-    tl.AddTask("send", [=] { return SendBoundBufs(fields, true); });
+    // p2p mode: the dt all-reduce of the last stage doubles as the stage barrier unless physical
+    // BCs (which read neighbour-filled ghost cells) run before it
+    const bool barrier = !last || bc_face_mask_ != 0 || cfg_.riemann == APK_RIEMANN_NONE;
+    tl.AddTask("send", [=] { return SendBoundBufs(fields, true, barrier); });
     tl.AddTask("recv", [this] { return ReceiveBoundBufs(); });
     tl.AddTask("set", [=] { return SetBounds(fields); });
     tl.AddTask("fbound", [=] { return ApplyBoundaryConditions(fields); });

@@ -132,7 +132,7 @@ class HydroSim {
   TaskStatus FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, bool last_stage);
   TaskStatus StartReceiveBoundBufs();
   // with_prim: 0 cons, 1 cons+prim, 2 prim only; local_done: same-device ghosts already pushed
-  TaskStatus SendBoundBufs(int with_prim, bool local_done = false);
+  TaskStatus SendBoundBufs(int with_prim, bool local_done = false, bool need_barrier = true);
   TaskStatus ReceiveBoundBufs();
   TaskStatus SetBounds(int with_prim);
   TaskStatus ApplyBoundaryConditions(int with_prim);
@@ -151,6 +151,7 @@ class HydroSim {
   long long fofc_corrections = 0;
   long long cycles_done = 0;
   bool FusedActive() const { return fused_; }
+  bool P2PActive() const { return p2p_; }
   // halo plan introspection
   struct PeerInfo { int rank; long long send_off, send_cnt, recv_off, recv_cnt; };
   int NumPeers() const { return (int)peers_.size(); }
@@ -208,6 +209,15 @@ class HydroSim {
   ncclComm *comm_ = nullptr;
   void *comm_event_ = nullptr, *packed_event_ = nullptr, *comm_stream_ = nullptr;
   bool recv_posted_ = false;
+  // peer-to-peer ghost push (fused stages, nranks > 1): the stage kernel stores boundary cells
+  // straight into the neighbour GPU's ghost zones through CUDA-IPC mapped pointers
+  bool p2p_ = false;            // all ranks mapped their neighbours' field buffers
+  bool nccl_inflight_ = false;  // the last SendBoundBufs used the packed NCCL path
+  apk_push_dst_t *d_push_[2] = {nullptr, nullptr};  // [nblocks][27] per prim ping-pong parity
+  int *d_barrier_ = nullptr;
+  std::vector<void *> peer_mapped_;
+  void SetupPeerPush();
+  void StageBarrier();
 
   // linear wave pgen state (src/pgen/linear_wave.cpp:43-51)
   struct {

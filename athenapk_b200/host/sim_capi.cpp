@@ -128,6 +128,7 @@ int apk_sim_ncycle(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))-
 double apk_sim_c_h(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->c_h; }
 long long apk_sim_fofc_corrections(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->fofc_corrections; }
 int apk_sim_fused_active(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->FusedActive() ? 1 : 0; }
+int apk_sim_p2p_active(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->P2PActive() ? 1 : 0; }
 double apk_sim_linear_wave_period(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->LinearWavePeriod(); }
 int apk_sim_linear_wave_errors(apk_sim_t *s, double *out6) {
   return guarded([&] { SIM(s)->LinearWaveErrors(out6); return 0; });

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define APK_ABI_VERSION 1
+#define APK_ABI_VERSION 2
 
 /* src/main.hpp:19-50 (enum values are ours; the shim translates) */
 enum { APK_FLUID_EULER = 0, APK_FLUID_GLMMHD = 1 };
@@ -180,6 +180,23 @@ int apk_stage_fused(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
                                  blocks (nbr[] >= 0): replaces apk_copy_ghosts_local(prim)     */
 #define APK_FUSED_PUSH_CONS 4 /* same for cons (last stage: the caller-visible state after the
                                  cycle has valid cons ghosts like the reference's)            */
+
+/* Same as apk_stage_fused with explicit ghost-push destinations: d_push is a device array
+ * [nblocks][27] (neighbour offset index (o3+1)*9+(o2+1)*3+(o1+1)) holding the BLOCK BASE of the
+ * neighbour's prim_out and cons arrays, or NULL to skip that neighbour.  The pointers may refer to
+ * another GPU's memory (mapped with cudaIpcOpenMemHandle / peer access): the halo exchange with
+ * remote neighbours then happens inside the stage kernel as peer stores over NVLink -- no pack /
+ * ncclSend / ncclRecv / unpack (boundary_communication.cpp:48-348, communication_buffer.hpp
+ * :209-236).  The caller must separate consecutive stages with a cross-rank barrier (any stream-
+ * ordered collective, e.g. the dt all-reduce). */
+typedef struct apk_push_dst {
+  double *prim;
+  double *cons;
+} apk_push_dst_t;
+int apk_stage_fused_p2p(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                        double *const *d_prim_out, const apk_push_dst_t *d_push, double gam0,
+                        double gam1, double beta_dt, double c_h, double mindx, double alpha,
+                        int recon_override, int flags, double *d_dtmin, void *stream);
 
 /* copy cons -> cons_u1 for all blocks (u1 <- u0 at stage 1, hydro_driver.cpp:474-495) */
 int apk_save_u1(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, void *stream);

@@ -61,6 +61,9 @@ int apk_sim_ncycle(const apk_sim_t *s);
 double apk_sim_c_h(const apk_sim_t *s);
 long long apk_sim_fofc_corrections(const apk_sim_t *s);
 int apk_sim_fused_active(const apk_sim_t *s);
+/* 1 when the remote halo exchange runs as peer stores inside the stage kernel (CUDA IPC over
+ * NVLink), 0 when it uses the packed ncclSend/ncclRecv path */
+int apk_sim_p2p_active(const apk_sim_t *s);
 double apk_sim_linear_wave_period(const apk_sim_t *s);
 int apk_sim_linear_wave_errors(apk_sim_t *s, double *out6);
 void *apk_sim_stream(apk_sim_t *s);

@@ -28,6 +28,10 @@ def main():
     uid = [apk.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     sim.init_comm(uid[0])
+    want_p2p = os.environ.get("APK_B200_P2P", "1") != "0"
+    # fused decks exchange remote ghosts as peer stores inside the stage kernel (CUDA IPC);
+    # APK_B200_P2P=0 keeps the packed ncclSend/ncclRecv path
+    assert sim.p2p_active == (want_p2p and sim.fused_active), (sim.p2p_active, want_p2p)
     sim.pgen(pgen, pars)
     sim.initialize()
     sim.execute(None, ncyc)
@@ -45,7 +49,7 @@ def main():
             assert np.array_equal(got, ref), (rank, b, f, float(np.max(np.abs(got - ref))))
     dist.barrier()
     if rank == 0:
-        print("MULTIGPU_OK blocks/rank=%d" % sim.nblocks)
+        print("MULTIGPU_OK blocks/rank=%d p2p=%d" % (sim.nblocks, sim.p2p_active))
     sim.close()
     dist.destroy_process_group()
 

@@ -34,9 +34,14 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("p2p", [1, 0])
 @pytest.mark.parametrize("case", range(len(CASES)))
 @pytest.mark.parametrize("world", [2, 4])
-def test_multi_gpu_bitexact(case, world):
+def test_multi_gpu_bitexact(case, world, p2p):
+    """p2p=1: remote ghosts are peer stores of the fused stage kernel (apk_stage_fused_p2p);
+    p2p=0: packed ncclSend/ncclRecv exchange.  Both must reproduce the oracle bit for bit."""
+    if p2p == 0 and not CASES[case]["fused"]:
+        pytest.skip("un-fused decks always use the NCCL path")
     if ngpus() < world:
         pytest.skip("needs %d GPUs" % world)
     s = socket.socket()
@@ -46,7 +51,8 @@ def test_multi_gpu_bitexact(case, world):
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(port), APK_CASE=json.dumps(CASES[case]))
+                   MASTER_PORT=str(port), APK_CASE=json.dumps(CASES[case]),
+                   APK_B200_P2P=str(p2p))
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "multigpu_worker.py")],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                       text=True))
