@@ -17,6 +17,8 @@
 //  * 288 threads: 264 x1-faces + 288 x2-faces + 256 x3-faces = 26 warp tasks on 9 warps.
 // Compiled twice (APK_NS = apk_fast / apk_strict), see apk_launch.h.
 #include <cstdint>
+#include <cstdlib>
+#include <algorithm>
 
 #include "apk_launch.h"
 #include "apk_math.cuh"
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(NTHREADS, APK_FUSED_MINBLOCKS)
 k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *__restrict__ prim_out,
               double g0, double g1, double bdt, double gamma, double c_h, double dedner_coeff,
               EosPars eos, int ntx, int flags, unsigned long long *dtmin,
-              const apk_push_dst_t *__restrict__ push) {
+              const apk_push_dst_t *__restrict__ push, int kchunk) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<NH, NDIM> &sm = *reinterpret_cast<Smem<NH, NDIM> *>(smem_raw);
@@ -114,8 +116,14 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   for (int v = 0; v < NH; ++v) du[v] = fzlo[v] = 0.0;
   double my_min = DBL_MAX;
 
-  const int kfirst = (NDIM == 3) ? g.ks - 1 : g.ks;
-  const int klast = (NDIM == 3) ? g.ke + 1 : g.ke;
+  // x3 range of this CTA: the march is cut into chunks of `kchunk` planes (blockIdx.z) so that small
+  // packs (strong scaling: 64 meshblocks per GPU) still fill every SM for several waves; a chunk
+  // re-does one x3-only reconstruction plane and one x3 face row of its lower neighbour (~0.3
+  // plane of work per chunk)
+  const int kbeg = (NDIM == 3) ? g.ks + (int)blockIdx.z * kchunk : g.ks;
+  const int kend = (NDIM == 3) ? min(kbeg + kchunk - 1, g.ke) : g.ke;
+  const int kfirst = (NDIM == 3) ? kbeg - 1 : kbeg;
+  const int klast = (NDIM == 3) ? kend + 1 : kend;
   // recon work of one plane as a flat list of warp tasks (one task = one variable x one row of
   // 32 cells): [0,NZ) x3 rows, [NZ,NZ+NX) x1 rows, [NZ+NX, NZ+NX+NY) x2 rows -1..TY.
   // UNROLL tasks are fetched before the first one is evaluated (memory-level parallelism; with
@@ -177,7 +185,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   const bool lane_ok = lane < txe;
   int cur = 0;
   for (int kp = kfirst; kp <= klast; ++kp) {
-    const bool inplane = (kp >= g.ks && kp <= g.ke);
+    const bool inplane = (kp >= kbeg && kp <= kend);
     // ------------------------------------------------------------------ recon phase
     // (donor cell: L/R states are the neighbouring cell values themselves; the Riemann tasks read
     //  them straight from global memory, no staging pass and no barrier)
@@ -270,7 +278,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       constexpr int R = ReconTraits<RECON>::radius;
       const int pn = kp + 1;
       if (pn <= klast) {
-        const bool next_in = (pn >= g.ks && pn <= g.ke);
+        const bool next_in = (pn >= kbeg && pn <= kend);
         const int nzr = (NDIM == 3) ? tye : 0;                // rows of plane pn+R (x3 stencil top)
         const int nyr = next_in ? (NDIM >= 2 ? tye + 2 + 2 * R : 1) : 0;  // rows of plane pn
         const int ylo = (NDIM >= 2) ? -1 - R : 0;
@@ -290,7 +298,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       // the finalize phase of this iteration streams cons / u1 of plane kfin exactly once: start
       // the HBM fetch now so it overlaps the Riemann solves (12-16 warps/SM cannot hide it later)
       const int kfin = (NDIM == 3) ? kp - 1 : kp;
-      if (kfin >= g.ks && kfin <= g.ke) {
+      if (kfin >= kbeg && kfin <= kend) {
         const long c = (long)kfin * sk + (long)(j0 + cj) * sj + (i0 + ci);
         const bool need_u0 = save_u1 || (g0 != 0.0);
 #pragma unroll
@@ -347,7 +355,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           dst = &sm.wly[0][r][lane];
           dstride = (TY + 1) * TX;
         } else {
-          if (NDIM < 3 || kp < g.ks) continue;
+          if (NDIM < 3 || kp < kbeg) continue;
           const int j = t - (2 * TY + 2);
           if (j >= tye || lane >= txe) continue;
           if constexpr (RECON == APK_RECON_DC) {
@@ -385,7 +393,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           }
         }
       }
-      if (kfin >= g.ks && kfin <= g.ke) {
+      if (kfin >= kbeg && kfin <= kend) {
         const long c = (long)kfin * sk + (long)(j0 + cj) * sj + (i0 + ci);
         double u[NH], w[NH], c0[NH], c1[NH];
         // batch the global loads (uniform branch: stage 1 saves u1 <- u0 instead of reading it,
@@ -506,7 +514,28 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
   const EosPars eos = {d.gamma, d.dfloor, d.pfloor, d.efloor, d.vceil, d.eceil};
   const int ntx = (d.nx[0] + TX - 1) / TX;
   const int nty = (g.ndim >= 2) ? (d.nx[1] + TY - 1) / TY : 1;
-  dim3 grid(ntx * nty, g.nb);
+  // x3 chunks: aim for >= 16 waves of CTAs (tail < 6 %) while chunks stay >= 8 planes
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  int nchunk = 1;
+  if (g.ndim == 3) {
+    static const char *env = std::getenv("APK_B200_KCHUNKS");
+    if (env && std::atoi(env) > 0) {
+      nchunk = std::min(std::atoi(env), d.nx[2]);
+    } else {
+      const long slots = (long)sm_count * APK_FUSED_MINBLOCKS;
+      while (nchunk < 8 && (long)ntx * nty * g.nb * nchunk < 16 * slots &&
+             d.nx[2] / (nchunk * 2) >= 8)
+        nchunk *= 2;
+    }
+  }
+  const int kchunk = (g.ndim == 3) ? (d.nx[2] + nchunk - 1) / nchunk : 1;
+  dim3 grid(ntx * nty, g.nb, (g.ndim == 3) ? (d.nx[2] + kchunk - 1) / kchunk : 1);
   const size_t smem = (g.ndim == 3) ? sizeof(Smem<NH, 3>) : (g.ndim == 2 ? sizeof(Smem<NH, 2>) : sizeof(Smem<NH, 1>));
   unsigned long long *dt = reinterpret_cast<unsigned long long *>(d_dtmin);
 #define APK_LAUNCH_FUSED(ND)                                                                     \
@@ -518,7 +547,7 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
       attr_set = true;                                                                           \
     }                                                                                            \
     kern<<<grid, NTHREADS, smem, s>>>(g, blocks, prim_out, g0, g1, bdt, d.gamma, c_h, coeff, eos, \
-                                      ntx, flags, dt, push);                                            \
+                                      ntx, flags, dt, push, kchunk);                                    \
   }
   if (g.ndim == 3) APK_LAUNCH_FUSED(3)
   else if (g.ndim == 2) APK_LAUNCH_FUSED(2)
