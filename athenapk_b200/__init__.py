@@ -85,6 +85,7 @@ SIM_SYMBOLS = [
     "apk_sim_linear_wave_period", "apk_sim_linear_wave_errors", "apk_sim_stream",
     "apk_sim_pack_desc", "apk_sim_device_blocks", "apk_sim_synchronize", "apk_sim_task",
     "apk_sim_set_c_h", "apk_sim_upload_all", "apk_sim_download_all",
+    "apk_sim_interior_elems", "apk_sim_load_interior", "apk_sim_store_interior",
     "apk_sim_enable_task_timing", "apk_sim_task_timing", "apk_sim_num_peers", "apk_sim_peer",
     "apk_sim_num_halo_items", "apk_sim_halo_item", "apk_sim_neighbor",
 ]
@@ -173,6 +174,10 @@ def lib():
     L.apk_sim_set_c_h.argtypes = [vp, C.c_double, C.c_double]
     L.apk_sim_upload_all.argtypes = [vp, C.c_int, vp]
     L.apk_sim_download_all.argtypes = [vp, C.c_int, vp]
+    L.apk_sim_interior_elems.argtypes = [vp]
+    L.apk_sim_interior_elems.restype = C.c_longlong
+    L.apk_sim_load_interior.argtypes = [vp, vp]
+    L.apk_sim_store_interior.argtypes = [vp, vp]
     L.apk_sim_enable_task_timing.argtypes = [vp, C.c_int]
     L.apk_sim_task_timing.argtypes = [vp, C.c_char_p, dp, C.POINTER(C.c_longlong)]
     llp = C.POINTER(C.c_longlong)
@@ -302,6 +307,18 @@ class HydroSim:
     def upload_all(self, field, host_ptr):
         """async H2D of a whole field ([nblocks][nvar][n3][n2][n1] doubles at host_ptr)"""
         self._chk(self.L.apk_sim_upload_all(self.h, FIELD[field], host_ptr), "upload_all")
+
+    @property
+    def interior_elems(self):
+        return int(self.L.apk_sim_interior_elems(self.h))
+
+    def load_interior(self, host_ptr):
+        """async: dense interior-only cons [nblocks][nvar][nx3][nx2][nx1] -> device, ghosts, prim"""
+        self._chk(self.L.apk_sim_load_interior(self.h, host_ptr), "load_interior")
+
+    def store_interior(self, host_ptr):
+        """async: device cons interiors -> dense host buffer"""
+        self._chk(self.L.apk_sim_store_interior(self.h, host_ptr), "store_interior")
 
     def download_all(self, field, host_ptr):
         self._chk(self.L.apk_sim_download_all(self.h, FIELD[field], host_ptr), "download_all")

@@ -148,6 +148,8 @@ HydroSim::~HydroSim() {
   cudaFree(d_push_[0]);
   cudaFree(d_push_[1]);
   cudaFree(d_barrier_);
+  cudaFree(d_stage_);
+  cudaFree(d_int_items_);
   cudaFree(d_sendbuf_);
   cudaFree(d_recvbuf_);
   if (comm_event_) cudaEventDestroy(reinterpret_cast<cudaEvent_t>(comm_event_));
@@ -583,6 +585,53 @@ int HydroSim::CopyToHost(int field, int block, double *dst) {
   cuda_check(cudaMemcpyAsync(dst, p, BlockFieldElems() * sizeof(double), cudaMemcpyDeviceToHost,
                              S(stream_)), "D2H");
   Synchronize();
+  return 0;
+}
+
+size_t HydroSim::InteriorElems() const {
+  return blocks_.size() * (size_t)nvar_ * cfg_.mb[0] * cfg_.mb[1] * cfg_.mb[2];
+}
+
+void HydroSim::EnsureStage() {
+  if (d_stage_) return;
+  const size_t per = (size_t)nvar_ * cfg_.mb[0] * cfg_.mb[1] * cfg_.mb[2];
+  std::vector<apk_halo_item_t> items(blocks_.size());
+  for (size_t b = 0; b < blocks_.size(); ++b) {
+    apk_halo_item_t &it = items[b];
+    it.block = (int)b;
+    for (int d = 0; d < 3; ++d) {
+      it.lo[d] = (d < ndim_) ? cfg_.ng : 0;
+      it.ext[d] = cfg_.mb[d];
+    }
+    it.offset = (long long)(2 * b * per);  // single-field copies use offset / 2 (apk_halo_item_t)
+  }
+  cuda_check(cudaMalloc(&d_stage_, InteriorElems() * sizeof(double)), "interior staging");
+  cuda_check(cudaMalloc(&d_int_items_, items.size() * sizeof(apk_halo_item_t)), "interior items");
+  cuda_check(cudaMemcpy(d_int_items_, items.data(), items.size() * sizeof(apk_halo_item_t),
+                        cudaMemcpyHostToDevice), "interior items");
+}
+
+int HydroSim::LoadStateInterior(const double *h_src) {
+  EnsureStage();
+  cuda_check(cudaMemcpyAsync(d_stage_, h_src, InteriorElems() * sizeof(double),
+                             cudaMemcpyHostToDevice, S(stream_)), "H2D interior");
+  abi_check(apk_halo_unpack(&desc_, d_blocks_[cur_], d_int_items_, (int)blocks_.size(), 0, d_stage_,
+                            stream_), "scatter interior");
+  // Mesh::Initialize sequence: exchange ghosts, BCs, FillDerived
+  SendBoundBufs(0);
+  ReceiveBoundBufs();
+  SetBounds(0);
+  ApplyBoundaryConditions(0);
+  FillDerived();
+  return 0;
+}
+
+int HydroSim::StoreStateInterior(double *h_dst) {
+  EnsureStage();
+  abi_check(apk_halo_pack(&desc_, d_blocks_[cur_], d_int_items_, (int)blocks_.size(), 0, d_stage_,
+                          stream_), "gather interior");
+  cuda_check(cudaMemcpyAsync(h_dst, d_stage_, InteriorElems() * sizeof(double),
+                             cudaMemcpyDeviceToHost, S(stream_)), "D2H interior");
   return 0;
 }
 

@@ -152,6 +152,13 @@ class HydroSim {
   long long cycles_done = 0;
   bool FusedActive() const { return fused_; }
   bool P2PActive() const { return p2p_; }
+  // Host <-> device exchange of the conserved state WITHOUT ghost cells (what a restart file or
+  // an external producer holds): dense [nblocks][nvar][nx3][nx2][nx1].  Load = H2D + scatter into
+  // the block interiors + ghost exchange + physical BCs + FillDerived; Store = gather + D2H.
+  // Everything is enqueued on the simulation stream (no host synchronisation).
+  size_t InteriorElems() const;
+  int LoadStateInterior(const double *h_src);
+  int StoreStateInterior(double *h_dst);
   // halo plan introspection
   struct PeerInfo { int rank; long long send_off, send_cnt, recv_off, recv_cnt; };
   int NumPeers() const { return (int)peers_.size(); }
@@ -215,6 +222,9 @@ class HydroSim {
   bool nccl_inflight_ = false;  // the last SendBoundBufs used the packed NCCL path
   apk_push_dst_t *d_push_[2] = {nullptr, nullptr};  // [nblocks][27] per prim ping-pong parity
   int *d_barrier_ = nullptr;
+  double *d_stage_ = nullptr;               // interior-only staging buffer
+  apk_halo_item_t *d_int_items_ = nullptr;  // one slab per block: its interior
+  void EnsureStage();
   std::vector<void *> peer_mapped_;
   void SetupPeerPush();
   void StageBarrier();

@@ -111,6 +111,15 @@ int apk_sim_copy_from_host(apk_sim_t *s, int field, int block, const double *src
 int apk_sim_upload_all(apk_sim_t *s, int field, const double *src) {
   return guarded([&] { return SIM(s)->UploadAll(field, src); });
 }
+long long apk_sim_interior_elems(const apk_sim_t *s) {
+  return (long long)SIM(const_cast<apk_sim_t *>(s))->InteriorElems();
+}
+int apk_sim_load_interior(apk_sim_t *s, const double *src) {
+  return guarded([&] { return SIM(s)->LoadStateInterior(src); });
+}
+int apk_sim_store_interior(apk_sim_t *s, double *dst) {
+  return guarded([&] { return SIM(s)->StoreStateInterior(dst); });
+}
 int apk_sim_download_all(apk_sim_t *s, int field, double *dst) {
   return guarded([&] { return SIM(s)->DownloadAll(field, dst); });
 }

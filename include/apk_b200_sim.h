@@ -51,6 +51,13 @@ int apk_sim_copy_from_host(apk_sim_t *s, int field, int block, const double *src
 /* whole-pack async copies on the sim stream (host buffer: [nblocks][nvar][n3][n2][n1]) */
 int apk_sim_upload_all(apk_sim_t *s, int field, const double *src);
 int apk_sim_download_all(apk_sim_t *s, int field, double *dst);
+/* conserved state without ghost cells, dense [nblocks][nvar][nx3][nx2][nx1] (what a restart file
+ * or an external producer holds).  load = H2D + scatter into the block interiors + ghost exchange
+ * + physical BCs + FillDerived (the Mesh::Initialize sequence); store = gather + D2H.  Both are
+ * enqueued on the simulation stream without host synchronisation (host buffers should be pinned). */
+long long apk_sim_interior_elems(const apk_sim_t *s);
+int apk_sim_load_interior(apk_sim_t *s, const double *src);
+int apk_sim_store_interior(apk_sim_t *s, double *dst);
 /* per-task device time (CUDA events on the launching stream), summed since enabling */
 void apk_sim_enable_task_timing(apk_sim_t *s, int on);
 int apk_sim_task_timing(const apk_sim_t *s, const char *name, double *ms_total, long long *count);
