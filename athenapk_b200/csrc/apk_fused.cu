@@ -45,6 +45,9 @@ namespace {
 #ifndef APK_FUSED_SWPIPE
 #define APK_FUSED_SWPIPE 0  // measured: no gain at 256^3 (the loads are not the limiter), costs registers
 #endif
+#ifndef APK_FUSED_PPM_VOTE
+#define APK_FUSED_PPM_VOTE 1
+#endif
 #ifndef APK_FUSED_TY
 #define APK_FUSED_TY 8
 #endif
@@ -218,11 +221,15 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       };
       auto evaluate = [&](const Batch &b) {
         double qls[UNROLL], qrs[UNROLL];
+        if constexpr (RECON == APK_RECON_PPM && APK_FUSED_PPM_VOTE) {
+          recon_ppm_warp<UNROLL>(b.v, qls, qrs);  // all 32 lanes are here: the loop is warp uniform
+        } else {
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-          const int dir = (b.st[u] >> 28) & 3;
-          recon_stencil<RECON>(b.v[u], dir == 0 ? dx1 : (dir == 1 ? dx2 : dx3),
-                               (b.st[u] >> 30) & 1, qls[u], qrs[u]);
+          for (int u = 0; u < UNROLL; ++u) {
+            const int dir = (b.st[u] >> 28) & 3;
+            recon_stencil<RECON>(b.v[u], dir == 0 ? dx1 : (dir == 1 ? dx2 : dx3),
+                                 (b.st[u] >> 30) & 1, qls[u], qrs[u]);
+          }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {

@@ -176,7 +176,8 @@ def run_product(args):
         uid = [apk.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         sim.init_comm(uid[0])
-    sim.pgen(args.pgen)
+    pgen_pars = (3, 0.2) if args.pgen == "random" else ()
+    sim.pgen(args.pgen, pgen_pars)
     sim.initialize()
     cells = float(args.n) ** 3
     stream = torch.cuda.ExternalStream(sim.stream)
@@ -268,7 +269,7 @@ def run_product(args):
                 uid = [apk.nccl_unique_id() if rank == 0 else None]
                 dist.broadcast_object_list(uid, src=0)
                 sx.init_comm(uid[0])
-            sx.pgen(args.pgen)
+            sx.pgen(args.pgen, pgen_pars)
             sx.initialize()
             sims.append(sx)
         nctx = len(sims)
@@ -343,7 +344,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--n", type=int, default=256, help="mesh cells per direction")
     ap.add_argument("--mb", type=int, default=32, help="meshblock cells per direction")
-    ap.add_argument("--pgen", default="ot3d", choices=["ot3d", "uniform"])
+    ap.add_argument("--pgen", default="ot3d", choices=["ot3d", "uniform", "random"])
     ap.add_argument("--fp-mode", dest="fp_mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
