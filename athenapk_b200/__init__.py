@@ -57,6 +57,14 @@ class PackDesc(C.Structure):
     ]
 
 
+class AmrItem(C.Structure):
+    """Mirror of apk_amr_item_t (include/apk_b200.h)."""
+    _fields_ = [
+        ("fine", C.c_void_p), ("coarse", C.c_void_p), ("nf", C.c_int * 3), ("nc", C.c_int * 3),
+        ("lo", C.c_int * 3), ("hi", C.c_int * 3), ("xmin", C.c_double * 3), ("dx", C.c_double * 3),
+    ]
+
+
 class Block(C.Structure):
     """Mirror of apk_block_t (include/apk_b200.h)."""
     _fields_ = [
@@ -73,7 +81,8 @@ ABI_SYMBOLS = [
     "apk_flux_div_update", "apk_dedner_source", "apk_cons_to_prim", "apk_min_dt",
     "apk_min_dt_async", "apk_fill_ghosts_local", "apk_apply_physical_bcs",
     "apk_copy_ghosts_local", "apk_halo_pack", "apk_halo_unpack", "apk_stage_fused", "apk_stage_fused_p2p",
-    "apk_save_u1", "apk_fp64_probe",
+    "apk_save_u1", "apk_fp64_probe", "apk_restrict_average", "apk_prolongate_minmod_multid",
+    "apk_tag_pressure_gradient",
 ]
 SIM_SYMBOLS = [
     "apk_sim_last_error", "apk_sim_default_config", "apk_sim_create", "apk_sim_destroy",

@@ -191,6 +191,44 @@ int apk_stage_fused(const apk_pack_desc_t *d, const apk_block_t *blocks,
                              recon_override, flags, d_dtmin, stream);
 }
 
+int apk_restrict_average(int ndim, int ng, int nvar, int element, const apk_amr_item_t *d_items,
+                         int nitems, int fp_mode, void *stream) {
+  if (ndim < 1 || ndim > 3 || ng < 0 || nvar < 1 || element < 0 || element > ndim ||
+      (nitems > 0 && !d_items)) {
+    apk_common::set_error("apk_restrict_average: bad arguments");
+    return 1;
+  }
+  if (fp_mode == APK_FP_STRICT)
+    apk_strict::launch_restrict_average(ndim, ng, nvar, element, d_items, nitems, S(stream));
+  else
+    apk_fast::launch_restrict_average(ndim, ng, nvar, element, d_items, nitems, S(stream));
+  return cuda_ok("apk_restrict_average");
+}
+
+int apk_prolongate_minmod_multid(int ndim, int ng, int nvar, const apk_amr_item_t *d_items,
+                                 int nitems, int fp_mode, void *stream) {
+  if (ndim < 1 || ndim > 3 || ng < 1 || nvar < 1 || (nitems > 0 && !d_items)) {
+    apk_common::set_error("apk_prolongate_minmod_multid: bad arguments");
+    return 1;
+  }
+  if (fp_mode == APK_FP_STRICT)
+    apk_strict::launch_prolongate_minmod(ndim, ng, nvar, d_items, nitems, S(stream));
+  else
+    apk_fast::launch_prolongate_minmod(ndim, ng, nvar, d_items, nitems, S(stream));
+  return cuda_ok("apk_prolongate_minmod_multid");
+}
+
+int apk_tag_pressure_gradient(const apk_pack_desc_t *d, const apk_block_t *blocks, double threshold,
+                              int *d_tags, double *d_maxeps, void *stream) {
+  if (check(d, blocks, "apk_tag_pressure_gradient: bad descriptor")) return 1;
+  if (!d_tags || !d_maxeps) {
+    apk_common::set_error("apk_tag_pressure_gradient: null output");
+    return 1;
+  }
+  DISPATCH(d, launch_pressure_gradient(*d, blocks, threshold, d_tags, d_maxeps, S(stream)));
+  return cuda_ok("apk_tag_pressure_gradient");
+}
+
 int apk_save_u1(const apk_pack_desc_t *d, const apk_block_t *blocks, void *stream) {
   if (check(d, blocks, "apk_save_u1: bad descriptor")) return 1;
   apk_common::launch_save_u1(*d, blocks, S(stream));

@@ -29,6 +29,12 @@
                          double *const *prim_out, double g0, double g1, double bdt, double c_h, \
                          double dedner_coeff, int recon, int flags, double *d_dtmin,            \
                          const apk_push_dst_t *push, cudaStream_t s);                           \
+  int launch_restrict_average(int ndim, int ng, int nvar, int el, const apk_amr_item_t *items,  \
+                              int nitems, cudaStream_t s);                                      \
+  int launch_prolongate_minmod(int ndim, int ng, int nvar, const apk_amr_item_t *items,         \
+                               int nitems, cudaStream_t s);                                     \
+  int launch_pressure_gradient(const apk_pack_desc_t &d, const apk_block_t *blocks,             \
+                               double threshold, int *tags, double *maxeps, cudaStream_t s);    \
   }
 
 APK_DECLARE_LAUNCHERS(apk_fast)

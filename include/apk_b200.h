@@ -201,6 +201,35 @@ int apk_stage_fused_p2p(const apk_pack_desc_t *desc, const apk_block_t *d_blocks
 /* copy cons -> cons_u1 for all blocks (u1 <- u0 at stage 1, hydro_driver.cpp:474-495) */
 int apk_save_u1(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, void *stream);
 
+/* ---- AMR building blocks (config 5).  One item = one (fine array, coarse buffer)
+ * pair and an inclusive COARSE index range; arrays are C-order [nvar][n3][n2][n1]; interior start
+ * index = ng in active dimensions on both levels (Parthenon's cellbounds / c_cellbounds). */
+typedef struct apk_amr_item {
+  double *fine;    /* fine block field (cons, or one direction of bnd_flux::cons)          */
+  double *coarse;  /* coarse buffer, nx/2 + 2*ng cells per active dimension               */
+  int nf[3];       /* fine extents (i,j,k), ghosts included                                */
+  int nc[3];       /* coarse extents (i,j,k)                                               */
+  int lo[3], hi[3]; /* inclusive coarse index range (i,j,k) to process                     */
+  double xmin[3];  /* RegionSize::xmin of the fine block (first interior face)             */
+  double dx[3];    /* fine cell sizes                                                      */
+} apk_amr_item_t;
+/* parthenon::refinement_ops::RestrictAverage (prolong_restrict/pr_ops.hpp:105-165): volume
+ * weighted mean of the 2^ndim children (element 0), or area weighted mean of the 2^(ndim-1) fine
+ * faces (element 1/2/3 = x1/x2/x3 face field: the restriction step of the flux correction,
+ * bvals_in_one.hpp:69-80, bnd_info.cpp:71-103). */
+int apk_restrict_average(int ndim, int ng, int nvar, int element, const apk_amr_item_t *d_items,
+                         int nitems, int fp_mode, void *stream);
+/* Hydro::refinement_ops::ProlongateCellMinModMultiD (src/hydro/prolongation/custom_ops.hpp
+ * :49-186, registered for cons at hydro.cpp:780-781): multi-D minmod-limited prolongation that
+ * writes the 2^ndim fine children of every coarse cell in the range. */
+int apk_prolongate_minmod_multid(int ndim, int ng, int nvar, const apk_amr_item_t *d_items,
+                                 int nitems, int fp_mode, void *stream);
+/* refinement::gradient::PressureGradient (src/refinement/gradient.cpp:18-61): per block
+ * max |grad p| / p over interior +- 1 -> d_maxeps[b] and the AmrTag d_tags[b] (-1 derefine,
+ * 0 same, 1 refine). */
+int apk_tag_pressure_gradient(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                              double threshold, int *d_tags, double *d_maxeps, void *stream);
+
 /* FP64 pipe microbenchmark (roofline evidence): runs n_iter dependent-chain-free DFMAs per
  * thread, returns measured FLOP count in *flops; time it with CUDA events from the caller */
 int apk_fp64_probe(int n_blocks, int n_threads, int n_iter, double *d_out, double *flops,

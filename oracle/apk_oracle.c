@@ -1849,3 +1849,204 @@ void apko_history(apko_engine *e, double *out) {
         }
   }
 }
+
+
+/* ============================================================================================
+ * AMR operators
+ * ============================================================================================ */
+/* uniform_coordinates.hpp:31-58: fine coords of a block and the coarsen=2 copy used by the
+ * coarse buffers */
+typedef struct {
+  double dx[3], xmin[3], cdx[3], cxmin[3];
+  int istart[3];
+} amr_coords;
+
+static amr_coords amr_make_coords(int ndim, int ng, const double *xmin_block, const double *dx) {
+  amr_coords c;
+  for (int d = 0; d < 3; ++d) {
+    c.istart[d] = (d < ndim) ? ng : 0;
+    c.dx[d] = dx[d];
+    c.xmin[d] = xmin_block[d] - c.istart[d] * c.dx[d];
+    c.cxmin[d] = c.xmin[d];
+    c.cdx[d] = c.dx[d];
+  }
+  const int coarsen = 2;
+  for (int d = 0; d < 3; ++d) c.cxmin[d] += c.istart[d] * c.cdx[d] * (1 - coarsen);
+  c.cdx[0] *= coarsen;
+  c.cdx[1] *= (c.istart[1] > 0 ? coarsen : 1);
+  c.cdx[2] *= (c.istart[2] > 0 ? coarsen : 1);
+  return c;
+}
+
+#define AMR_F(n, k, j, i) fine[(((size_t)(n)*nfine[2] + (k)) * nfine[1] + (j)) * nfine[0] + (i)]
+#define AMR_C(n, k, j, i)                                                                      \
+  coarse[(((size_t)(n)*ncoarse[2] + (k)) * ncoarse[1] + (j)) * ncoarse[0] + (i)]
+
+void apko_restrict_average(int ndim, int ng, int el, const double *xmin_block, const double *dx,
+                           int nv, const int *nfine, const double *fine, const int *ncoarse,
+                           double *coarse, const int *lo, const int *hi) {
+  const amr_coords c = amr_make_coords(ndim, ng, xmin_block, dx);
+  /* pr_ops.hpp:118-123: which directions are averaged for this element */
+  const int inc1 = (ndim > 0) && (el == 0 || el == 2 || el == 3);
+  const int inc2 = (ndim > 1) && (el == 0 || el == 3 || el == 1);
+  const int inc3 = (ndim > 2) && (el == 0 || el == 1 || el == 2);
+  /* uniform_coordinates.hpp:284-307 Volume<el>: cell volume or face area */
+  double v;
+  if (el == 0) v = c.dx[0] * c.dx[1] * c.dx[2];
+  else if (el == 1) v = c.dx[1] * c.dx[2];
+  else if (el == 2) v = c.dx[0] * c.dx[2];
+  else v = c.dx[0] * c.dx[1];
+  for (int n = 0; n < nv; ++n)
+    for (int ck = lo[2]; ck <= hi[2]; ++ck)
+      for (int cj = lo[1]; cj <= hi[1]; ++cj)
+        for (int ci = lo[0]; ci <= hi[0]; ++ci) {
+          const int i = (ndim > 0) ? (ci - c.istart[0]) * 2 + c.istart[0] : c.istart[0];
+          const int j = (ndim > 1) ? (cj - c.istart[1]) * 2 + c.istart[1] : c.istart[1];
+          const int k = (ndim > 2) ? (ck - c.istart[2]) * 2 + c.istart[2] : c.istart[2];
+          double vol[2][2][2], terms[2][2][2];
+          for (int ok = 0; ok < 2; ++ok)
+            for (int oj = 0; oj < 2; ++oj)
+              for (int oi = 0; oi < 2; ++oi) vol[ok][oj][oi] = terms[ok][oj][oi] = 0;
+          for (int ok = 0; ok < 1 + inc3; ++ok)
+            for (int oj = 0; oj < 1 + inc2; ++oj)
+              for (int oi = 0; oi < 1 + inc1; ++oi) {
+                vol[ok][oj][oi] = v;
+                terms[ok][oj][oi] = vol[ok][oj][oi] * AMR_F(n, k + ok, j + oj, i + oi);
+              }
+          /* pr_ops.hpp:154-161: off-centred quantities first (FP symmetry) */
+          const double tvol = ((vol[0][0][0] + vol[0][1][0]) + (vol[0][0][1] + vol[0][1][1])) +
+                              ((vol[1][0][0] + vol[1][1][0]) + (vol[1][0][1] + vol[1][1][1]));
+          AMR_C(n, ck, cj, ci) =
+              (((terms[0][0][0] + terms[0][1][0]) + (terms[0][0][1] + terms[0][1][1])) +
+               ((terms[1][0][0] + terms[1][1][0]) + (terms[1][0][1] + terms[1][1][1]))) /
+              tvol;
+        }
+}
+
+/* pr_ops.hpp:94-100 */
+static double amr_grad_minmod(double fc, double fm, double fp, double dxm, double dxp) {
+  const double gxm = (fc - fm) / dxm;
+  const double gxp = (fp - fc) / dxp;
+  return 0.5 * (SIGN(gxm) + SIGN(gxp)) * fmin(fabs(gxm), fabs(gxp));
+}
+
+/* pr_ops.hpp:75-91 for cell-centred data: X<DIM,CC>(i) = xmin + (i + 0.5) dx */
+static void amr_spacings(const amr_coords *c, int d, int i, int fi, double *dxm, double *dxp,
+                         double *dxfm, double *dxfp) {
+  const double xm = c->cxmin[d] + ((i - 1) + 0.5) * c->cdx[d];
+  const double xc = c->cxmin[d] + (i + 0.5) * c->cdx[d];
+  const double xp = c->cxmin[d] + ((i + 1) + 0.5) * c->cdx[d];
+  *dxm = xc - xm;
+  *dxp = xp - xc;
+  const double fxm = c->xmin[d] + (fi + 0.5) * c->dx[d];
+  const double fxp = c->xmin[d] + ((fi + 1) + 0.5) * c->dx[d];
+  *dxfm = xc - fxm;
+  *dxfp = fxp - xc;
+}
+
+void apko_prolongate_minmod_multid(int ndim, int ng, const double *xmin_block, const double *dx,
+                                   int nv, const int *nfine, double *fine, const int *ncoarse,
+                                   const double *coarse, const int *lo, const int *hi) {
+  const amr_coords c = amr_make_coords(ndim, ng, xmin_block, dx);
+  for (int n = 0; n < nv; ++n)
+    for (int k = lo[2]; k <= hi[2]; ++k)
+      for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) {
+          const int fi = (ndim > 0) ? (i - c.istart[0]) * 2 + c.istart[0] : c.istart[0];
+          const int fj = (ndim > 1) ? (j - c.istart[1]) * 2 + c.istart[1] : c.istart[1];
+          const int fk = (ndim > 2) ? (k - c.istart[2]) * 2 + c.istart[2] : c.istart[2];
+          const double fc = AMR_C(n, k, j, i);
+          double dx1fm = 0, dx1fp = 0, gx1c = 0, dx2fm = 0, dx2fp = 0, gx2c = 0, dx3fm = 0,
+                 dx3fp = 0, gx3c = 0;
+          double dm, dp;
+          amr_spacings(&c, 0, i, fi, &dm, &dp, &dx1fm, &dx1fp);
+          gx1c = amr_grad_minmod(fc, AMR_C(n, k, j, i - 1), AMR_C(n, k, j, i + 1), dm, dp);
+          if (ndim > 1) {
+            amr_spacings(&c, 1, j, fj, &dm, &dp, &dx2fm, &dx2fp);
+            gx2c = amr_grad_minmod(fc, AMR_C(n, k, j - 1, i), AMR_C(n, k, j + 1, i), dm, dp);
+          }
+          if (ndim > 2) {
+            amr_spacings(&c, 2, k, fk, &dm, &dp, &dx3fm, &dx3fp);
+            gx3c = amr_grad_minmod(fc, AMR_C(n, k - 1, j, i), AMR_C(n, k + 1, j, i), dm, dp);
+          }
+          /* custom_ops.hpp:121-152 */
+          double dqmax = fabs(gx1c) * fmax(dx1fm, dx1fp);
+          int jlim = 0, klim = 0;
+          if (ndim > 1) {
+            dqmax += fabs(gx2c) * fmax(dx2fm, dx2fp);
+            jlim = 1;
+          }
+          if (ndim > 2) {
+            dqmax += fabs(gx3c) * fmax(dx3fm, dx3fp);
+            klim = 1;
+          }
+          double qmin = fc, qmax = fc;
+          for (int koff = -klim; koff <= klim; koff++)
+            for (int joff = -jlim; joff <= jlim; joff++)
+              for (int ioff = -1; ioff <= 1; ioff++) {
+                qmin = fmin(qmin, AMR_C(n, k + koff, j + joff, i + ioff));
+                qmax = fmax(qmax, AMR_C(n, k + koff, j + joff, i + ioff));
+              }
+          double alpha = 1.0;
+          if (dqmax * alpha > (qmax - fc)) alpha = (qmax - fc) / dqmax;
+          if (dqmax * alpha > (fc - qmin)) alpha = (fc - qmin) / dqmax;
+          gx1c *= alpha;
+          gx2c *= alpha;
+          gx3c *= alpha;
+          /* custom_ops.hpp:159-181 */
+          AMR_F(n, fk, fj, fi) = fc - (gx1c * dx1fm + gx2c * dx2fm + gx3c * dx3fm);
+          AMR_F(n, fk, fj, fi + 1) = fc + (gx1c * dx1fp - gx2c * dx2fm - gx3c * dx3fm);
+          if (ndim > 1) {
+            AMR_F(n, fk, fj + 1, fi) = fc - (gx1c * dx1fm - gx2c * dx2fp + gx3c * dx3fm);
+            AMR_F(n, fk, fj + 1, fi + 1) = fc + (gx1c * dx1fp + gx2c * dx2fp - gx3c * dx3fm);
+          }
+          if (ndim > 2) {
+            AMR_F(n, fk + 1, fj, fi) = fc - (gx1c * dx1fm + gx2c * dx2fm - gx3c * dx3fp);
+            AMR_F(n, fk + 1, fj, fi + 1) = fc + (gx1c * dx1fp - gx2c * dx2fm + gx3c * dx3fp);
+            AMR_F(n, fk + 1, fj + 1, fi) = fc - (gx1c * dx1fm - gx2c * dx2fp - gx3c * dx3fp);
+            AMR_F(n, fk + 1, fj + 1, fi + 1) = fc + (gx1c * dx1fp + gx2c * dx2fp + gx3c * dx3fp);
+          }
+        }
+}
+#undef AMR_F
+#undef AMR_C
+
+int apko_pressure_gradient_tag(int ndim, int ng, const int *n, const double *prim, int ipr,
+                               double threshold, double *maxeps_out) {
+  /* gradient.cpp:18-61: loops over interior +- 1 */
+  if (ndim < 2) {
+    if (maxeps_out) *maxeps_out = 0.0;
+    return 0;
+  }
+  const size_t n1 = n[0], n2 = n[1], ncell = (size_t)n[0] * n[1] * n[2];
+  const double *w = prim + (size_t)ipr * ncell;
+#define W(k, j, i) w[((size_t)(k)*n2 + (j)) * n1 + (i)]
+  const int is = ng, ie = n[0] - ng - 1, js = ng, je = n[1] - ng - 1;
+  const int ks = (ndim == 3) ? ng : 0, ke = (ndim == 3) ? n[2] - ng - 1 : 0;
+  double maxeps = 0.0;
+  if (ndim == 3) {
+    for (int k = ks - 1; k <= ke + 1; ++k)
+      for (int j = js - 1; j <= je + 1; ++j)
+        for (int i = is - 1; i <= ie + 1; ++i) {
+          const double eps = sqrt(SQR(0.5 * (W(k, j, i + 1) - W(k, j, i - 1))) +
+                                  SQR(0.5 * (W(k, j + 1, i) - W(k, j - 1, i))) +
+                                  SQR(0.5 * (W(k + 1, j, i) - W(k - 1, j, i)))) /
+                             W(k, j, i);
+          maxeps = fmax(maxeps, eps);
+        }
+  } else {
+    const int k = ks;
+    for (int j = js - 1; j <= je + 1; ++j)
+      for (int i = is - 1; i <= ie + 1; ++i) {
+        const double eps = sqrt(SQR(0.5 * (W(k, j, i + 1) - W(k, j, i - 1))) +
+                                SQR(0.5 * (W(k, j + 1, i) - W(k, j - 1, i)))) /
+                           W(k, j, i);
+        maxeps = fmax(maxeps, eps);
+      }
+  }
+#undef W
+  if (maxeps_out) *maxeps_out = maxeps;
+  if (maxeps > threshold) return 1;
+  if (maxeps < 0.25 * threshold) return -1;
+  return 0;
+}

@@ -100,6 +100,26 @@ void apko_riemann_face(int fluid, int solver, int ivx, const double *wl, const d
 void apko_c2p_cell(int fluid, int nscalars, double *u, double *w, double gamma, double dfloor,
                    double pfloor, double efloor, double vceil, double eceil);
 
+/* ---- AMR operators.  Arrays: fine [nv][nf3][nf2][nf1], coarse [nv][nc3][nc2][nc1];
+ * lo/hi = inclusive COARSE index range (i,j,k); interior start index = ng in active dimensions
+ * (0 otherwise) on both levels; xmin_block = position of the first interior face of the fine
+ * block (RegionSize::xmin), dx = fine cell sizes. */
+/* parthenon::refinement_ops::RestrictAverage (prolong_restrict/pr_ops.hpp:105-165):
+ * el 0 = cell centred (volume weights), 1/2/3 = x1/x2/x3 face field (area weights; the flux
+ * correction of bvals_in_one.hpp:69-80 / bnd_info.cpp:71-103 restricts cons.flux with it) */
+void apko_restrict_average(int ndim, int ng, int el, const double *xmin_block, const double *dx,
+                           int nv, const int *nfine, const double *fine, const int *ncoarse,
+                           double *coarse, const int *lo, const int *hi);
+/* Hydro::refinement_ops::ProlongateCellMinModMultiD (src/hydro/prolongation/custom_ops.hpp
+ * :49-186) with util::GetGridSpacings / GradMinMod (pr_ops.hpp:75-102) */
+void apko_prolongate_minmod_multid(int ndim, int ng, const double *xmin_block, const double *dx,
+                                   int nv, const int *nfine, double *fine, const int *ncoarse,
+                                   const double *coarse, const int *lo, const int *hi);
+/* refinement::gradient::PressureGradient (src/refinement/gradient.cpp:18-61) for one block:
+ * prim [nv][n3][n2][n1]; returns the tag (-1 derefine, 0 same, 1 refine), *maxeps_out = max eps */
+int apko_pressure_gradient_tag(int ndim, int ng, const int *n, const double *prim, int ipr,
+                               double threshold, double *maxeps_out);
+
 #ifdef __cplusplus
 }
 #endif

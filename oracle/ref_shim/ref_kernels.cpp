@@ -24,6 +24,7 @@ int apk_ref_require_failed = 0;
 #include "recon/weno3_simple.hpp"
 #include "recon/wenoz_simple.hpp"
 #include "hydro/rsolvers/rsolvers.hpp"
+#include "hydro/prolongation/custom_ops.hpp"  // + Parthenon's own prolong_restrict/pr_ops.hpp
 
 // the pack-level drivers live in .cpp files we do not build; give the vtable a home
 void AdiabaticHydroEOS::ConservedToPrimitive(parthenon::MeshData<Real> *) const {}
@@ -161,3 +162,71 @@ double apk_ref_fast_speed(double gamma, double d, double p, double bx, double by
   return eos.FastMagnetosonicSpeed(d, p, bx, by, bz);
 }
 } // extern "C"
+
+
+// ---- AMR operators: the reference's own structs on caller-owned arrays --------
+// fine: [nv][n3][n2][n1], coarse: [nv][c3][c2][c1]; coarse index range [lo, hi] per dimension;
+// fine/coarse interior start indices as in Parthenon (ng in active dimensions, 0 otherwise).
+namespace {
+struct AmrGeom {
+  parthenon::Coordinates_t coords, coarse_coords;
+  IndexRange cib, cjb, ckb, ib, jb, kb;
+};
+AmrGeom amr_geom(int ndim, int ng, const double *xmin_block, const double *dx) {
+  int istart[3] = {ng, ndim >= 2 ? ng : 0, ndim >= 3 ? ng : 0};
+  AmrGeom g;
+  g.coords = parthenon::Coordinates_t(xmin_block, dx, istart);
+  g.coarse_coords = parthenon::Coordinates_t(g.coords, 2);
+  g.ib.s = g.cib.s = istart[0];
+  g.jb.s = g.cjb.s = istart[1];
+  g.kb.s = g.ckb.s = istart[2];
+  return g;
+}
+template <class Op, parthenon::TE el, class... A>
+void amr_dispatch(int ndim, A... a) {
+  if (ndim == 1) Op::template Do<1, el>(a...);
+  else if (ndim == 2) Op::template Do<2, el>(a...);
+  else Op::template Do<3, el>(a...);
+}
+}  // namespace
+
+extern "C" {
+// el: 0 = cell centred (RestrictAverage on cons), 1/2/3 = x1/x2/x3 face flux (flux correction)
+void apk_ref_restrict_average(int ndim, int ng, int el, const double *xmin_block, const double *dx,
+                              int nv, const int *nfine, double *fine, const int *ncoarse,
+                              double *coarse, const int *lo, const int *hi) {
+  AmrGeom g = amr_geom(ndim, ng, xmin_block, dx);
+  ParArrayND<Real, parthenon::VariableState> f(fine, nv, nfine[2], nfine[1], nfine[0]);
+  ParArrayND<Real, parthenon::VariableState> c(coarse, nv, ncoarse[2], ncoarse[1], ncoarse[0]);
+  using Op = parthenon::refinement_ops::RestrictAverage;
+  for (int n = 0; n < nv; ++n)
+    for (int k = lo[2]; k <= hi[2]; ++k)
+      for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i) {
+#define APK_REF_CALL(E)                                                                        \
+  amr_dispatch<Op, E>(ndim, 0, 0, n, k, j, i, g.ckb, g.cjb, g.cib, g.kb, g.jb, g.ib, g.coords, \
+                      g.coarse_coords, &c, &f)
+          if (el == 0) APK_REF_CALL(parthenon::TE::CC);
+          else if (el == 1) APK_REF_CALL(parthenon::TE::F1);
+          else if (el == 2) APK_REF_CALL(parthenon::TE::F2);
+          else APK_REF_CALL(parthenon::TE::F3);
+#undef APK_REF_CALL
+        }
+}
+
+void apk_ref_prolongate_minmod_multid(int ndim, int ng, const double *xmin_block,
+                                      const double *dx, int nv, const int *nfine, double *fine,
+                                      const int *ncoarse, double *coarse, const int *lo,
+                                      const int *hi) {
+  AmrGeom g = amr_geom(ndim, ng, xmin_block, dx);
+  ParArrayND<Real, parthenon::VariableState> f(fine, nv, nfine[2], nfine[1], nfine[0]);
+  ParArrayND<Real, parthenon::VariableState> c(coarse, nv, ncoarse[2], ncoarse[1], ncoarse[0]);
+  using Op = Hydro::refinement_ops::ProlongateCellMinModMultiD;
+  for (int n = 0; n < nv; ++n)
+    for (int k = lo[2]; k <= hi[2]; ++k)
+      for (int j = lo[1]; j <= hi[1]; ++j)
+        for (int i = lo[0]; i <= hi[0]; ++i)
+          amr_dispatch<Op, parthenon::TE::CC>(ndim, 0, 0, n, k, j, i, g.ckb, g.cjb, g.cib, g.kb,
+                                              g.jb, g.ib, g.coords, g.coarse_coords, &c, &f);
+}
+}

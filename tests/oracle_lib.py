@@ -228,3 +228,41 @@ def riemann_face(fluid, solver, ivx, wl, wr, gamma, c_h=1.0):
     lib().apko_riemann_face(FLUID[fluid], RIEMANN[solver], ivx, _dp(wl), _dp(wr), gamma, c_h,
                             _dp(out))
     return out
+
+
+# ---- AMR operators: arrays are [nv][n3][n2][n1]; lo/hi inclusive coarse (i,j,k) ----
+def _amr_args(ndim, ng, xmin_block, dx, fine, coarse, lo, hi):
+    assert fine.dtype == np.float64 and coarse.dtype == np.float64
+    assert fine.flags.c_contiguous and coarse.flags.c_contiguous
+    ip = C.POINTER(C.c_int)
+    nf = np.asarray(fine.shape[:0:-1], dtype=np.int32)
+    nc = np.asarray(coarse.shape[:0:-1], dtype=np.int32)
+    x = np.asarray(xmin_block, dtype=np.float64)
+    d = np.asarray(dx, dtype=np.float64)
+    l = np.asarray(lo, dtype=np.int32)
+    h = np.asarray(hi, dtype=np.int32)
+    keep = (nf, nc, x, d, l, h)
+    return keep, (_dp(x), _dp(d), fine.shape[0], nf.ctypes.data_as(ip), _dp(fine),
+                  nc.ctypes.data_as(ip), _dp(coarse), l.ctypes.data_as(ip), h.ctypes.data_as(ip))
+
+
+def restrict_average(ndim, ng, el, xmin_block, dx, fine, coarse, lo, hi):
+    keep, a = _amr_args(ndim, ng, xmin_block, dx, fine, coarse, lo, hi)
+    getattr(lib(), 'apko_' + "restrict_average")(ndim, ng, el, *a)
+
+
+def prolongate_minmod_multid(ndim, ng, xmin_block, dx, fine, coarse, lo, hi):
+    keep, a = _amr_args(ndim, ng, xmin_block, dx, fine, coarse, lo, hi)
+    getattr(lib(), 'apko_' + "prolongate_minmod_multid")(ndim, ng, *a)
+
+
+def pressure_gradient_tag(ndim, ng, prim, ipr, threshold):
+    """(tag, maxeps) of refinement::gradient::PressureGradient for one block"""
+    prim = np.ascontiguousarray(prim, dtype=np.float64)
+    n = np.asarray(prim.shape[:0:-1], dtype=np.int32)
+    m = C.c_double()
+    f = lib().apko_pressure_gradient_tag
+    f.restype = C.c_int
+    tag = f(ndim, ng, n.ctypes.data_as(C.POINTER(C.c_int)), _dp(prim), ipr, C.c_double(threshold),
+            C.byref(m))
+    return tag, m.value

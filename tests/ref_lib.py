@@ -79,3 +79,29 @@ def c2p_cell(fluid, u, gamma, nscalars=0, dfloor=-1.0, pfloor=-1.0, efloor=-1.0,
     err = lib().apk_ref_c2p_cell(FLUID[fluid], nscalars, _dp(u), _dp(w), gamma, dfloor, pfloor,
                                  efloor, vceil, eceil)
     return u, w, err
+
+
+# ---- AMR operators: arrays are [nv][n3][n2][n1]; lo/hi inclusive coarse (i,j,k) ----
+def _amr_args(ndim, ng, xmin_block, dx, fine, coarse, lo, hi):
+    assert fine.dtype == np.float64 and coarse.dtype == np.float64
+    assert fine.flags.c_contiguous and coarse.flags.c_contiguous
+    ip = C.POINTER(C.c_int)
+    nf = np.asarray(fine.shape[:0:-1], dtype=np.int32)
+    nc = np.asarray(coarse.shape[:0:-1], dtype=np.int32)
+    x = np.asarray(xmin_block, dtype=np.float64)
+    d = np.asarray(dx, dtype=np.float64)
+    l = np.asarray(lo, dtype=np.int32)
+    h = np.asarray(hi, dtype=np.int32)
+    keep = (nf, nc, x, d, l, h)
+    return keep, (_dp(x), _dp(d), fine.shape[0], nf.ctypes.data_as(ip), _dp(fine),
+                  nc.ctypes.data_as(ip), _dp(coarse), l.ctypes.data_as(ip), h.ctypes.data_as(ip))
+
+
+def restrict_average(ndim, ng, el, xmin_block, dx, fine, coarse, lo, hi):
+    keep, a = _amr_args(ndim, ng, xmin_block, dx, fine, coarse, lo, hi)
+    getattr(lib(), 'apk_ref_' + "restrict_average")(ndim, ng, el, *a)
+
+
+def prolongate_minmod_multid(ndim, ng, xmin_block, dx, fine, coarse, lo, hi):
+    keep, a = _amr_args(ndim, ng, xmin_block, dx, fine, coarse, lo, hi)
+    getattr(lib(), 'apk_ref_' + "prolongate_minmod_multid")(ndim, ng, *a)
