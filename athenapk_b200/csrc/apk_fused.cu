@@ -74,14 +74,19 @@ struct ReconTask {
   int sl, sr;  // shared-memory element index of the L / R destination of lane 0, or -1
 };
 
-template <int NH, int NDIM>
+template <int NH, int NDIM, bool DC>
 struct Smem {
   static constexpr int NZ = (NDIM == 3) ? NH * TY : 0, NX = NH * TY,
                        NY = (NDIM >= 2) ? NH * (TY + 2) : 0, NT = NZ + NX + NY;
-  double wlx[NH][TY][TX + 1], wrx[NH][TY][TX + 1];
-  double wly[NH][TY + 1][TX], wry[NH][TY + 1][TX];
-  double wrz[NH][TY][TX], wlz[2][NH][TY][TX];
-  alignas(16) ReconTask tab[NT > 0 ? NT : 1];
+  // donor cell (DC) stages need no L/R state arrays (the states are the cell values): they keep the
+  // three flux arrays and instead stage three halo'd prim planes (k-1, k and the one in flight)
+  static constexpr int NR = DC ? 1 : NH, ZB = DC ? 1 : 2, NP = DC ? 3 : 1, NPV = DC ? NH : 1;
+  static constexpr int RY = DC ? 1 : TY, RX = DC ? 1 : TX;  // R-state arrays collapse for DC
+  double wlx[NH][TY][TX + 1], wrx[NR][RY][RX + 1];
+  double wly[NH][TY + 1][TX], wry[NR][RY + 1][RX];
+  double wrz[NR][RY][RX], wlz[ZB][NH][TY][TX];
+  double pl[NP][NPV][TY + 2][TX + 2];  // DC: prim planes, cells -1..TX x rows -1..TY
+  alignas(16) ReconTask tab[(!DC && NT > 0) ? NT : 1];
   double *push_prim[27], *push_cons[27];  // ghost-push destinations per neighbour offset (or null)
 };
 
@@ -93,7 +98,9 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
               const apk_push_dst_t *__restrict__ push, int kchunk) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<NH, NDIM> &sm = *reinterpret_cast<Smem<NH, NDIM> *>(smem_raw);
+  constexpr bool DC = (RECON == APK_RECON_DC);
+  using SmemT = Smem<NH, NDIM, DC>;
+  SmemT &sm = *reinterpret_cast<SmemT *>(smem_raw);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const apk_block_t &B = blocks[blockIdx.y];
@@ -131,7 +138,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   // 32 cells): [0,NZ) x3 rows, [NZ,NZ+NX) x1 rows, [NZ+NX, NZ+NX+NY) x2 rows -1..TY.
   // UNROLL tasks are fetched before the first one is evaluated (memory-level parallelism; with
   // 4 warps per scheduler there are too few warps to hide L2 latency otherwise).
-  constexpr int NZ = Smem<NH, NDIM>::NZ, NX = Smem<NH, NDIM>::NX, NT = Smem<NH, NDIM>::NT;
+  constexpr int NZ = SmemT::NZ, NX = SmemT::NX, NT = SmemT::NT;
   constexpr int UNROLL = (RECON == APK_RECON_DC) ? 4 : APK_FUSED_UNROLL;
   constexpr int ZBUF = NH * TY * TX;  // elements between wlz[0] and wlz[1]
   double *const smd = reinterpret_cast<double *>(smem_raw);
@@ -186,9 +193,36 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   }
   const int lc = min(lane, txe - 1);
   const bool lane_ok = lane < txe;
+  // DC: asynchronous copy (cp.async, 8 B granules: always aligned) of one halo'd prim plane into
+  // the staging ring; indices beyond the tile are clamped to valid cells and never used.  The
+  // plane needed by iteration k+1 is requested at the start of iteration k and has the whole
+  // iteration to land: the Riemann tasks then read L/R from shared memory instead of issuing 18
+  // long-latency global loads per face (3.3 faces per cell, every value fetched ~6 times).
+  auto stage_plane = [&](int k) {
+    if constexpr (DC) {
+      constexpr int ROWS = (NDIM >= 2) ? TY + 2 : 1, PER = ROWS * (TX + 2);
+      const int buf = k % 3;
+      for (int e = threadIdx.x; e < NH * PER; e += NTHREADS) {
+        const int v = e / PER, r = (e % PER) / (TX + 2), c = e % (TX + 2);
+        const int jj = (NDIM >= 2) ? min(r - 1, tye) : 0, ii = min(c - 1, txe);
+        const double *src = prim + (long)v * g.ncell + (long)k * sk + (long)(j0 + jj) * sj + (i0 + ii);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.pl[buf][v][(NDIM >= 2) ? r : 1][c]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  };
+  if constexpr (DC) {
+    stage_plane(kfirst);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+  }
   int cur = 0;
   for (int kp = kfirst; kp <= klast; ++kp) {
     const bool inplane = (kp >= kbeg && kp <= kend);
+    if constexpr (DC) {
+      if (kp < klast) stage_plane(kp + 1);
+    }
     // ------------------------------------------------------------------ recon phase
     // (donor cell: L/R states are the neighbouring cell values themselves; the Riemann tasks read
     //  them straight from global memory, no staging pass and no barrier)
@@ -330,12 +364,12 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           else { j = lane; f = TX; if (txe < TX || j >= TY) continue; }
           if (j >= tye) continue;
           if constexpr (RECON == APK_RECON_DC) {
-            const double *q = prim + (long)kp * sk + (long)(j0 + j) * sj + (i0 + f);
+            const int pb = kp % 3, pr = (NDIM >= 2) ? j + 1 : 1;
 #pragma unroll
             for (int n = 0; n < NH; ++n) {
-              const long o = (long)var_of_slot(n, 0) * g.ncell;
-              L[n] = q[o - 1];
-              R[n] = q[o];
+              const int vs = var_of_slot(n, 0);
+              L[n] = sm.pl[pb][vs][pr][f];
+              R[n] = sm.pl[pb][vs][pr][f + 1];
             }
           } else {
 #pragma unroll
@@ -348,12 +382,12 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           const int r = t - (TY + 1);
           if (r > tye || lane >= txe) continue;
           if constexpr (RECON == APK_RECON_DC) {
-            const double *q = prim + (long)kp * sk + (long)(j0 + r) * sj + (i0 + lane);
+            const int pb = kp % 3;
 #pragma unroll
             for (int n = 0; n < NH; ++n) {
-              const long o = (long)var_of_slot(n, 1) * g.ncell;
-              L[n] = q[o - sj];
-              R[n] = q[o];
+              const int vs = var_of_slot(n, 1);
+              L[n] = sm.pl[pb][vs][r][lane + 1];
+              R[n] = sm.pl[pb][vs][r + 1][lane + 1];
             }
           } else {
 #pragma unroll
@@ -366,12 +400,12 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           const int j = t - (2 * TY + 2);
           if (j >= tye || lane >= txe) continue;
           if constexpr (RECON == APK_RECON_DC) {
-            const double *q = prim + (long)kp * sk + (long)(j0 + j) * sj + (i0 + lane);
+            const int pb = kp % 3, pa = (kp + 2) % 3, pr = (NDIM >= 2) ? j + 1 : 1;  // planes k, k-1
 #pragma unroll
             for (int n = 0; n < NH; ++n) {
-              const long o = (long)var_of_slot(n, 2) * g.ncell;
-              L[n] = q[o - sk];
-              R[n] = q[o];
+              const int vs = var_of_slot(n, 2);
+              L[n] = sm.pl[pa][vs][pr][lane + 1];
+              R[n] = sm.pl[pb][vs][pr][lane + 1];
             }
           } else {
 #pragma unroll
@@ -501,7 +535,11 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
         }
       }
     }
-    cur ^= 1;
+    if constexpr (DC) {
+      asm volatile("cp.async.wait_all;" ::: "memory");  // the next plane has landed
+    } else {
+      cur ^= 1;
+    }
     __syncthreads();
   }
   if (dtmin) {
@@ -543,7 +581,10 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
   }
   const int kchunk = (g.ndim == 3) ? (d.nx[2] + nchunk - 1) / nchunk : 1;
   dim3 grid(ntx * nty, g.nb, (g.ndim == 3) ? (d.nx[2] + kchunk - 1) / kchunk : 1);
-  const size_t smem = (g.ndim == 3) ? sizeof(Smem<NH, 3>) : (g.ndim == 2 ? sizeof(Smem<NH, 2>) : sizeof(Smem<NH, 1>));
+  constexpr bool DC = (RECON == APK_RECON_DC);
+  static_assert(!DC || 3 * (sizeof(Smem<9, 3, DC>) + 1024) <= 233472 || APK_FUSED_MINBLOCKS < 3 ||
+                    TY != 4, "DC stage must keep 3 CTAs per SM");
+  const size_t smem = (g.ndim == 3) ? sizeof(Smem<NH, 3, DC>) : (g.ndim == 2 ? sizeof(Smem<NH, 2, DC>) : sizeof(Smem<NH, 1, DC>));
   unsigned long long *dt = reinterpret_cast<unsigned long long *>(d_dtmin);
 #define APK_LAUNCH_FUSED(ND)                                                                     \
   {                                                                                              \
