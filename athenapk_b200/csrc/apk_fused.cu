@@ -113,6 +113,8 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   double *__restrict__ cons = B.cons;
   double *__restrict__ cons_u1 = B.cons_u1;
   const bool save_u1 = (flags & APK_FUSED_SAVE_U1) != 0;
+  const bool prim_only = (flags & APK_FUSED_PRIM_ONLY) != 0;      // no cons / u1 stores
+  const bool u1_is_cons = (flags & APK_FUSED_U1_FROM_CONS) != 0;  // u1 lives in cons
   double *__restrict__ po = prim_out[blockIdx.y];
   const double dx1 = B.dx[0], dx2 = B.dx[1], dx3 = B.dx[2];
   // uniform_coordinates.hpp:37-40
@@ -341,11 +343,12 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       const int kfin = (NDIM == 3) ? kp - 1 : kp;
       if (kfin >= kbeg && kfin <= kend) {
         const long c = (long)kfin * sk + (long)(j0 + cj) * sj + (i0 + ci);
-        const bool need_u0 = save_u1 || (g0 != 0.0);
+        const bool need_u0 = save_u1 || prim_only || u1_is_cons || (g0 != 0.0);
+        const bool need_u1 = !(save_u1 || prim_only || u1_is_cons);
 #pragma unroll
         for (int v = 0; v < NH; ++v) {
           if (need_u0) asm volatile("prefetch.global.L1 [%0];" ::"l"(cons + (long)v * g.ncell + c));
-          if (!save_u1) asm volatile("prefetch.global.L1 [%0];" ::"l"(cons_u1 + (long)v * g.ncell + c));
+          if (need_u1) asm volatile("prefetch.global.L1 [%0];" ::"l"(cons_u1 + (long)v * g.ncell + c));
         }
       }
     }
@@ -441,14 +444,21 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
         // hydro_driver.cpp:474-495 folded into this pass)
         // gam0 == 0 (every VL2 stage, first stage of all integrators): 0*u0 contributes an exact
         // zero, so u0 need not be read at all unless it is also the source of the u1 copy
-        const bool need_u0 = save_u1 || (g0 != 0.0);
+        // VL2 special case (APK_FUSED_PRIM_ONLY / APK_FUSED_U1_FROM_CONS): the predictor's cons is
+        // never read again (gam0 == 0 in the corrector), so stage 1 stores only prim_out and leaves
+        // cons == u^n in place, and stage 2 takes u1 from cons: 18 stores per cell fewer
+        const bool src_cons = save_u1 || prim_only || u1_is_cons;  // u1 term comes from cons
+        const bool need_u0 = src_cons || (g0 != 0.0);
+        double cc[NH];
 #pragma unroll
-        for (int v = 0; v < NH; ++v) c0[v] = need_u0 ? cons[(long)v * g.ncell + c] : 0.0;
-        if (save_u1) {
+        for (int v = 0; v < NH; ++v) cc[v] = need_u0 ? cons[(long)v * g.ncell + c] : 0.0;
+#pragma unroll
+        for (int v = 0; v < NH; ++v) c0[v] = (g0 != 0.0 || save_u1 || prim_only) ? cc[v] : 0.0;
+        if (src_cons) {
 #pragma unroll
           for (int v = 0; v < NH; ++v) {
-            c1[v] = c0[v];
-            cons_u1[(long)v * g.ncell + c] = c0[v];
+            c1[v] = cc[v];
+            if (save_u1 && !prim_only) cons_u1[(long)v * g.ncell + c] = cc[v];
           }
         } else {
 #pragma unroll
@@ -469,7 +479,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
 #pragma unroll
         for (int v = 0; v < NH; ++v) {
           const long o = (long)v * g.ncell + c;
-          cons[o] = u[v];
+          if (!prim_only) cons[o] = u[v];
           po[o] = w[v];
         }
         if (flags & (APK_FUSED_PUSH_PRIM | APK_FUSED_PUSH_CONS)) {

@@ -724,6 +724,12 @@ TaskStatus HydroSim::AddUnsplitSources(Real beta_dt) {  // hydro.cpp:227-246
 
 TaskStatus HydroSim::FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, bool last_stage) {
   const int recon = (stage == 1 && cfg_.integrator == (int)Integrator::vl2) ? APK_RECON_DC : -1;
+  // VL2: u^{n+1} = u^n + dt L(w^{n+1/2}) never reads the predictor's cons (gam0 == 0), so stage 1
+  // produces only the half-step primitives and u^n stays in cons, where stage 2 picks it up as
+  // u1 (no u1 <- u0 copy, no predictor cons store).  Other integrators: u1 saved by stage 1.
+  const bool vl2 = cfg_.integrator == (int)Integrator::vl2;
+  const int stage_flags = vl2 ? (stage == 1 ? APK_FUSED_PRIM_ONLY : APK_FUSED_U1_FROM_CONS)
+                              : (stage == 1 ? APK_FUSED_SAVE_U1 : 0);
   double *dtmin = nullptr;
   if (last_stage) {
     dtmin = d_scalars_;
@@ -734,7 +740,7 @@ TaskStatus HydroSim::FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, b
   abi_check(apk_stage_fused_p2p(&desc_, d_blocks_[cur_], d_prim_out_[cur_],
                                 p2p_ ? d_push_[cur_] : nullptr, gam0, gam1, beta_dt, c_h,
                             mindx, cfg_.glmmhd_alpha, recon,
-                            (stage == 1 ? APK_FUSED_SAVE_U1 : 0) | APK_FUSED_PUSH_PRIM |
+                            stage_flags | APK_FUSED_PUSH_PRIM |
                                 (last_stage ? APK_FUSED_PUSH_CONS : 0),
                             dtmin, stream_), "apk_stage_fused");
   cur_ ^= 1;  // prim_out becomes "prim"

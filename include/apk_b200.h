@@ -178,6 +178,11 @@ int apk_stage_fused(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
 #define APK_FUSED_PUSH_PRIM 2 /* flags: finished cells within ng of a block face are also written
                                  into the ghost cells of prim_out of the same-device neighbour
                                  blocks (nbr[] >= 0): replaces apk_copy_ghosts_local(prim)     */
+#define APK_FUSED_PRIM_ONLY 8  /* flags: store prim_out only -- cons and cons_u1 stay untouched (the u1
+                                 term is taken from cons).  For a predictor stage whose cons nobody
+                                 reads again (VL2: gam0 == 0 in the corrector).                 */
+#define APK_FUSED_U1_FROM_CONS 16 /* flags: read the u1 term from cons instead of cons_u1 (corrector
+                                 after an APK_FUSED_PRIM_ONLY predictor; cons_u1 is not touched)  */
 #define APK_FUSED_PUSH_CONS 4 /* same for cons (last stage: the caller-visible state after the
                                  cycle has valid cons ghosts like the reference's)            */
 
