@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(NTHREADS, APK_FUSED_MINBLOCKS)
 k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *__restrict__ prim_out,
               double g0, double g1, double bdt, double gamma, double c_h, double dedner_coeff,
               EosPars eos, int ntx, int flags, unsigned long long *dtmin,
-              const apk_push_dst_t *__restrict__ push, int kchunk) {
+              const apk_push_dst_t *__restrict__ push, int nchunk) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool DC = (RECON == APK_RECON_DC);
@@ -128,12 +128,13 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   for (int v = 0; v < NH; ++v) du[v] = fzlo[v] = 0.0;
   double my_min = DBL_MAX;
 
-  // x3 range of this CTA: the march is cut into chunks of `kchunk` planes (blockIdx.z) so that small
+  // x3 range of this CTA: the march is cut into `nchunk` balanced chunks (blockIdx.z) so that small
   // packs (strong scaling: 64 meshblocks per GPU) still fill every SM for several waves; a chunk
   // re-does one x3-only reconstruction plane and one x3 face row of its lower neighbour (~0.3
   // plane of work per chunk)
-  const int kbeg = (NDIM == 3) ? g.ks + (int)blockIdx.z * kchunk : g.ks;
-  const int kend = (NDIM == 3) ? min(kbeg + kchunk - 1, g.ke) : g.ke;
+  const int nx3c = g.ke - g.ks + 1;  // chunk c covers planes [c nx3 / nchunk, (c+1) nx3 / nchunk)
+  const int kbeg = (NDIM == 3) ? g.ks + ((int)blockIdx.z * nx3c) / nchunk : g.ks;
+  const int kend = (NDIM == 3) ? g.ks + (((int)blockIdx.z + 1) * nx3c) / nchunk - 1 : g.ke;
   const int kfirst = (NDIM == 3) ? kbeg - 1 : kbeg;
   const int klast = (NDIM == 3) ? kend + 1 : kend;
   // recon work of one plane as a flat list of warp tasks (one task = one variable x one row of
@@ -589,8 +590,7 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
         nchunk *= 2;
     }
   }
-  const int kchunk = (g.ndim == 3) ? (d.nx[2] + nchunk - 1) / nchunk : 1;
-  dim3 grid(ntx * nty, g.nb, (g.ndim == 3) ? (d.nx[2] + kchunk - 1) / kchunk : 1);
+  dim3 grid(ntx * nty, g.nb, nchunk);
   constexpr bool DC = (RECON == APK_RECON_DC);
   static_assert(!DC || 3 * (sizeof(Smem<9, 3, DC>) + 1024) <= 233472 || APK_FUSED_MINBLOCKS < 3 ||
                     TY != 4, "DC stage must keep 3 CTAs per SM");
@@ -605,7 +605,7 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
       attr_set = true;                                                                           \
     }                                                                                            \
     kern<<<grid, NTHREADS, smem, s>>>(g, blocks, prim_out, g0, g1, bdt, d.gamma, c_h, coeff, eos, \
-                                      ntx, flags, dt, push, kchunk);                                    \
+                                      ntx, flags, dt, push, nchunk);                                    \
   }
   if (g.ndim == 3) APK_LAUNCH_FUSED(3)
   else if (g.ndim == 2) APK_LAUNCH_FUSED(2)
