@@ -140,6 +140,7 @@ HydroSim::~HydroSim() {
   cudaFree(d_prim_out_[0]);
   cudaFree(d_prim_out_[1]);
   cudaFree(d_scalars_);
+  if (h_scalars_) cudaFreeHost(h_scalars_);
   cudaFree(d_status_);
   cudaFree(d_fofc_work_);
   cudaFree(d_send_items_);
@@ -320,6 +321,13 @@ void HydroSim::UploadBlocks() {
                           cudaMemcpyHostToDevice), "upload prim_out");
   }
   cuda_check(cudaMalloc(&d_scalars_, 64 * sizeof(double)), "cudaMalloc scalars");
+  cuda_check(cudaMemset(d_scalars_, 0, 64 * sizeof(double)), "memset scalars");
+  {
+    const double big = DBL_MAX;
+    cuda_check(cudaMemcpy(d_scalars_ + 8, &big, sizeof(double), cudaMemcpyHostToDevice), "scalars");
+  }
+  cuda_check(cudaHostAlloc(reinterpret_cast<void **>(&h_scalars_), 8 * sizeof(double),
+                           cudaHostAllocDefault), "pinned scalars");
   cuda_check(cudaMalloc(&d_status_, sizeof(int)), "cudaMalloc status");
   cuda_check(cudaMemset(d_status_, 0, sizeof(int)), "memset");
   if (cfg_.fofc) {
@@ -733,9 +741,10 @@ TaskStatus HydroSim::FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, b
   double *dtmin = nullptr;
   if (last_stage) {
     dtmin = d_scalars_;
-    const double big = DBL_MAX;
-    cuda_check(cudaMemcpyAsync(d_scalars_, &big, sizeof(double), cudaMemcpyHostToDevice, S(stream_)),
-               "init dtmin");
+    // device-to-device from a resident DBL_MAX constant: fully asynchronous (a pageable H2D copy
+    // stalls the launch queue, which shows at 64 meshblocks per GPU)
+    cuda_check(cudaMemcpyAsync(d_scalars_, d_scalars_ + 8, sizeof(double), cudaMemcpyDeviceToDevice,
+                               S(stream_)), "init dtmin");
   }
   abi_check(apk_stage_fused_p2p(&desc_, d_blocks_[cur_], d_prim_out_[cur_],
                                 p2p_ ? d_push_[cur_] : nullptr, gam0, gam1, beta_dt, c_h,
@@ -846,13 +855,15 @@ TaskStatus HydroSim::EstimateTimestep(bool have_device_min) {
     ncclAllReduce(d_scalars_, d_scalars_, 1, ncclDouble, ncclMin,
                   reinterpret_cast<ncclComm_t>(comm_), S(stream_));
   }
-  double m = 0.0;
-  int status = 0;
-  cuda_check(cudaMemcpyAsync(&m, d_scalars_, sizeof(double), cudaMemcpyDeviceToHost, S(stream_)),
-             "dt D2H");
-  cuda_check(cudaMemcpyAsync(&status, d_status_, sizeof(int), cudaMemcpyDeviceToHost, S(stream_)),
+  // pinned destinations: both copies are truly asynchronous, one synchronisation per cycle
+  int *h_status = reinterpret_cast<int *>(h_scalars_ + 1);
+  cuda_check(cudaMemcpyAsync(h_scalars_, d_scalars_, sizeof(double), cudaMemcpyDeviceToHost,
+                             S(stream_)), "dt D2H");
+  cuda_check(cudaMemcpyAsync(h_status, d_status_, sizeof(int), cudaMemcpyDeviceToHost, S(stream_)),
              "status D2H");
   Synchronize();
+  const double m = h_scalars_[0];
+  const int status = *h_status;
   if (status != 0) {
     // PARTHENON_REQUIRE in ConsToPrim (adiabatic_hydro.hpp:77-79,111-113)
     throw std::runtime_error(status == 1

@@ -198,7 +198,8 @@ class HydroSim {
          *d_flux_[3] = {nullptr, nullptr, nullptr};
   apk_block_t *d_blocks_[2] = {nullptr, nullptr};
   double **d_prim_out_[2] = {nullptr, nullptr};
-  double *d_scalars_ = nullptr;  // [0] dt-min, [2..] misc
+  double *d_scalars_ = nullptr;  // [0] dt-min, [1] status (as double), [8] DBL_MAX constant
+  double *h_scalars_ = nullptr;  // pinned host mirror of d_scalars_[0..1] (one async D2H per cycle)
   int *d_status_ = nullptr;
   void *d_fofc_work_ = nullptr;
   void *stream_ = nullptr;
