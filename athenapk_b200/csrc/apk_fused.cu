@@ -93,7 +93,7 @@ struct Smem {
 template <int FLUID, int RECON, int RS, int NDIM>
 __global__ void __launch_bounds__(NTHREADS, APK_FUSED_MINBLOCKS)
 k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *__restrict__ prim_out,
-              double g0, double g1, double bdt, double gamma, double c_h, double dedner_coeff,
+              double g0, double g1, double bdt, RsPars rsp, double dedner_coeff,
               EosPars eos, int ntx, int flags, unsigned long long *dtmin,
               const apk_push_dst_t *__restrict__ push, int nchunk) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
@@ -119,6 +119,9 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   const double dx1 = B.dx[0], dx2 = B.dx[1], dx3 = B.dx[2];
   // uniform_coordinates.hpp:37-40
   const double a1 = dx2 * dx3, a2 = dx1 * dx3, a3 = dx1 * dx2, vol = dx1 * dx2 * dx3;
+#ifndef APK_STRICT
+  const double ivol = frcp(vol);
+#endif
 
   // finalize-phase ownership: thread -> cell (cj, ci) of the tile
   const int ci = threadIdx.x & 31, cj = threadIdx.x >> 5;
@@ -418,7 +421,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           dst = &sm.wlz[cur][0][j][lane];
           dstride = TY * TX;
         }
-        riemann_solve<FLUID, RS>(L, R, gamma, c_h, F);
+        riemann_solve<FLUID, RS>(L, R, rsp, F);
 #pragma unroll
         for (int n = 0; n < NH; ++n) dst[n * dstride] = F[n];
       }
@@ -473,7 +476,11 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
             d += (a3 * sm.wlz[cur][sz][cj][ci] - a3 * fzlo[v]);
           }
           // update.cpp:135-137 / update.hpp:55
+#ifdef APK_STRICT
           u[v] = g0 * c0[v] + g1 * c1[v] + bdt * fdiv(-d, vol);
+#else
+          u[v] = g0 * c0[v] + g1 * c1[v] + bdt * (-d * ivol);  // 1/V once per thread (<= 1 ulp)
+#endif
         }
         if constexpr (FLUID == APK_FLUID_GLMMHD) u[8] *= dedner_coeff;  // dedner_source.cpp:72
         cons_to_prim<NH>(u, w, eos);
@@ -525,15 +532,15 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
         if (dtmin) {  // hydro.cpp:845-895
           double lx, ly, lz;
           if constexpr (FLUID == APK_FLUID_EULER) {
-            lx = ly = lz = sound_speed(gamma, w[0], w[4]);
+            lx = ly = lz = sound_speed(rsp.gamma, w[0], w[4]);
           } else {
-            lx = fast_speed(gamma, w[0], w[4], w[5], w[6], w[7]);
-            ly = (NDIM > 1) ? fast_speed(gamma, w[0], w[4], w[6], w[7], w[5]) : 0.0;
-            lz = (NDIM > 2) ? fast_speed(gamma, w[0], w[4], w[7], w[5], w[6]) : 0.0;
+            lx = fast_speed(rsp.gamma, w[0], w[4], w[5], w[6], w[7]);
+            ly = (NDIM > 1) ? fast_speed(rsp.gamma, w[0], w[4], w[6], w[7], w[5]) : 0.0;
+            lz = (NDIM > 2) ? fast_speed(rsp.gamma, w[0], w[4], w[7], w[5], w[6]) : 0.0;
           }
-          my_min = fmin(my_min, fdiv(dx1, (fabs(w[1]) + lx)));
-          if (NDIM > 1) my_min = fmin(my_min, fdiv(dx2, (fabs(w[2]) + ly)));
-          if (NDIM > 2) my_min = fmin(my_min, fdiv(dx3, (fabs(w[3]) + lz)));
+          my_min = dmin(my_min, qdiv(dx1, (fabs(w[1]) + lx)));
+          if (NDIM > 1) my_min = dmin(my_min, qdiv(dx2, (fabs(w[2]) + ly)));
+          if (NDIM > 2) my_min = dmin(my_min, qdiv(dx3, (fabs(w[3]) + lz)));
         }
       }
       if (NDIM == 3 && inplane) {
@@ -568,6 +575,8 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
               cudaStream_t s) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
   const EosPars eos = {d.gamma, d.dfloor, d.pfloor, d.efloor, d.vceil, d.eceil};
+  // IEEE quotients evaluated once on the host (== frcp / fdiv on the device)
+  const RsPars rsp = {d.gamma, 1.0 / (d.gamma - 1.0), c_h, 0.5 / c_h};
   const int ntx = (d.nx[0] + TX - 1) / TX;
   const int nty = (g.ndim >= 2) ? (d.nx[1] + TY - 1) / TY : 1;
   // x3 chunks: aim for >= 16 waves of CTAs (tail < 6 %) while chunks stay >= 8 planes
@@ -604,7 +613,7 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
       attr_set = true;                                                                           \
     }                                                                                            \
-    kern<<<grid, NTHREADS, smem, s>>>(g, blocks, prim_out, g0, g1, bdt, d.gamma, c_h, coeff, eos, \
+    kern<<<grid, NTHREADS, smem, s>>>(g, blocks, prim_out, g0, g1, bdt, rsp, coeff, eos,           \
                                       ntx, flags, dt, push, nchunk);                                    \
   }
   if (g.ndim == 3) APK_LAUNCH_FUSED(3)

@@ -195,8 +195,7 @@ k_fofc_fix(ApkGeom g, const apk_block_t *__restrict__ blocks, int dir, double ga
     L[n] = q[-st];
     R[n] = q[0];
   }
-  if constexpr (FLUID == APK_FLUID_GLMMHD) riemann_mhd_llf(L, R, gamma, c_h, F);
-  else riemann_hydro_llf(L, R, gamma, F);
+  riemann_solve<FLUID, APK_RIEMANN_LLF>(L, R, gamma, c_h, F);
   double *__restrict__ flux = B.flux[dir];
 #pragma unroll
   for (int n = 0; n < NH; ++n) flux[(long)var_of_slot(n, dir) * g.ncell + c] = F[n];
