@@ -82,7 +82,7 @@ ABI_SYMBOLS = [
     "apk_min_dt_async", "apk_fill_ghosts_local", "apk_apply_physical_bcs",
     "apk_copy_ghosts_local", "apk_halo_pack", "apk_halo_unpack", "apk_stage_fused", "apk_stage_fused_p2p",
     "apk_save_u1", "apk_fp64_probe", "apk_restrict_average", "apk_prolongate_minmod_multid",
-    "apk_tag_pressure_gradient",
+    "apk_tag_pressure_gradient", "apk_history_workspace_bytes", "apk_history_sums",
 ]
 SIM_SYMBOLS = [
     "apk_sim_last_error", "apk_sim_default_config", "apk_sim_create", "apk_sim_destroy",
@@ -94,7 +94,7 @@ SIM_SYMBOLS = [
     "apk_sim_linear_wave_period", "apk_sim_linear_wave_errors", "apk_sim_stream",
     "apk_sim_pack_desc", "apk_sim_device_blocks", "apk_sim_synchronize", "apk_sim_task",
     "apk_sim_set_c_h", "apk_sim_upload_all", "apk_sim_download_all",
-    "apk_sim_interior_elems", "apk_sim_load_interior", "apk_sim_store_interior",
+    "apk_sim_interior_elems", "apk_sim_load_interior", "apk_sim_store_interior", "apk_sim_history",
     "apk_sim_enable_task_timing", "apk_sim_task_timing", "apk_sim_num_peers", "apk_sim_peer",
     "apk_sim_num_halo_items", "apk_sim_halo_item", "apk_sim_neighbor",
 ]
@@ -186,6 +186,7 @@ def lib():
     L.apk_sim_interior_elems.argtypes = [vp]
     L.apk_sim_interior_elems.restype = C.c_longlong
     L.apk_sim_load_interior.argtypes = [vp, vp]
+    L.apk_sim_history.argtypes = [vp, dp]
     L.apk_sim_store_interior.argtypes = [vp, vp]
     L.apk_sim_enable_task_timing.argtypes = [vp, C.c_int]
     L.apk_sim_task_timing.argtypes = [vp, C.c_char_p, dp, C.POINTER(C.c_longlong)]
@@ -316,6 +317,12 @@ class HydroSim:
     def upload_all(self, field, host_ptr):
         """async H2D of a whole field ([nblocks][nvar][n3][n2][n1] doubles at host_ptr)"""
         self._chk(self.L.apk_sim_upload_all(self.h, FIELD[field], host_ptr), "upload_all")
+
+    def history(self):
+        """HydroHst volume sums of the local blocks: mass, mom1-3, KE, E, ME, relDivB"""
+        out = np.zeros(8)
+        self._chk(self.L.apk_sim_history(self.h, out.ctypes.data_as(C.POINTER(C.c_double))), "history")
+        return out
 
     @property
     def interior_elems(self):

@@ -231,8 +231,92 @@ __global__ void k_pressure_gradient_tags(int nb, double threshold, const double 
   tags[b] = (m > threshold) ? 1 : ((m < 0.25 * threshold) ? -1 : 0);
 }
 
-inline long max_cells(const apk_amr_item_t *, int) { return 1 << 16; }
+// ---- history sums (hydro.cpp:145-208).  Level 1: one CTA per (block, slice) reduces its cells in
+// a fixed order (thread-strided partial sums -> shuffle tree -> shared-memory tree); level 2: one
+// CTA adds the partials in index order.  No atomics: bitwise reproducible.
+constexpr int kHistSlices = 8;
+
+template <int FLUID>
+__global__ void __launch_bounds__(kThreads)
+k_history_partial(ApkGeom g, const apk_block_t *__restrict__ blocks, double *__restrict__ partial) {
+  const apk_block_t &B = blocks[blockIdx.y];
+  const double *__restrict__ u = B.cons;
+  const int e1 = g.ie - g.is + 1, e2 = g.je - g.js + 1, e3 = g.ke - g.ks + 1;
+  const long total = (long)e1 * e2 * e3;
+  const long per = (total + kHistSlices - 1) / kHistSlices;
+  const long lo = (long)blockIdx.x * per, hi = min(lo + per, total);
+  const long sj = g.n1, sk = (long)g.n1 * g.n2;
+  const double vol = B.dx[0] * B.dx[1] * B.dx[2];
+  const double diag = sqrt(B.dx[0] * B.dx[0] + B.dx[1] * B.dx[1] + B.dx[2] * B.dx[2]);
+  double s[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s[q] = 0.0;
+  for (long t = lo + threadIdx.x; t < hi; t += blockDim.x) {
+    const int kk = (int)(t / ((long)e1 * e2));
+    const long r = t - (long)kk * e1 * e2;
+    const int jj = (int)(r / e1), ii = (int)(r - (long)jj * e1);
+    const long c = (long)(g.ks + kk) * sk + (long)(g.js + jj) * sj + (g.is + ii);
+    const double d = u[c], m1 = u[g.ncell + c], m2 = u[2 * g.ncell + c], m3 = u[3 * g.ncell + c];
+    s[0] += d * vol;
+    s[1] += m1 * vol;
+    s[2] += m2 * vol;
+    s[3] += m3 * vol;
+    s[4] += 0.5 / d * (m1 * m1 + m2 * m2 + m3 * m3) * vol;
+    s[5] += u[4 * g.ncell + c] * vol;
+    if (FLUID == APK_FLUID_GLMMHD && g.ndim >= 2) {
+      const double *b1 = u + 5 * g.ncell + c, *b2 = u + 6 * g.ncell + c, *b3 = u + 7 * g.ncell + c;
+      s[6] += 0.5 * (b1[0] * b1[0] + b2[0] * b2[0] + b3[0] * b3[0]) * vol;
+      double divb = (b1[1] - b1[-1]) / B.dx[0] + (b2[sj] - b2[-sj]) / B.dx[1];
+      if (g.ndim == 3) divb += (b3[sk] - b3[-sk]) / B.dx[2];
+      const double abs_b = sqrt(b1[0] * b1[0] + b2[0] * b2[0] + b3[0] * b3[0]);
+      s[7] += (abs_b != 0) ? 0.5 * diag * fabs(divb) / abs_b * vol : 0;
+    }
+  }
+  __shared__ double sh[8][kThreads / 32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    double v = s[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double v = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) v += sh[threadIdx.x][w];
+    partial[((long)blockIdx.y * kHistSlices + blockIdx.x) * 8 + threadIdx.x] = v;
+  }
+}
+
+__global__ void k_history_final(int npartial, const double *__restrict__ partial,
+                                double *__restrict__ out) {
+  // 8 warps, one per quantity: lanes take strided partials in a fixed order, then a shuffle tree
+  const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double v = 0.0;
+  for (int p = lane; p < npartial; p += 32) v += partial[(long)p * 8 + q];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) out[q] = v;
+}
 }  // namespace
+
+size_t history_workspace_bytes(const apk_pack_desc_t &d) {
+  return ((size_t)d.nblocks * kHistSlices + 1) * 8 * sizeof(double);
+}
+
+int launch_history(const apk_pack_desc_t &d, const apk_block_t *blocks, double *work,
+                   cudaStream_t s) {
+  const ApkGeom g = apk_make_geom(d);
+  double *out = work + (size_t)g.nb * kHistSlices * 8;
+  dim3 grid(kHistSlices, g.nb);
+  if (d.fluid == APK_FLUID_GLMMHD)
+    k_history_partial<APK_FLUID_GLMMHD><<<grid, kThreads, 0, s>>>(g, blocks, work);
+  else
+    k_history_partial<APK_FLUID_EULER><<<grid, kThreads, 0, s>>>(g, blocks, work);
+  k_history_final<<<1, 256, 0, s>>>(g.nb * kHistSlices, work, out);
+  apk_common::count_launch(2);
+  return 0;
+}
 
 int launch_restrict_average(int ndim, int ng, int nvar, int el, const apk_amr_item_t *items,
                             int nitems, cudaStream_t s) {

@@ -229,6 +229,27 @@ int apk_tag_pressure_gradient(const apk_pack_desc_t *d, const apk_block_t *block
   return cuda_ok("apk_tag_pressure_gradient");
 }
 
+size_t apk_history_workspace_bytes(const apk_pack_desc_t *d) {
+  return d ? apk_fast::history_workspace_bytes(*d) : 0;
+}
+
+int apk_history_sums(const apk_pack_desc_t *d, const apk_block_t *blocks, void *d_work,
+                     double *h_out8, void *stream) {
+  if (check(d, blocks, "apk_history_sums: bad descriptor")) return 1;
+  if (!d_work || !h_out8) {
+    apk_common::set_error("apk_history_sums: null workspace / output");
+    return 1;
+  }
+  double *work = static_cast<double *>(d_work);
+  DISPATCH(d, launch_history(*d, blocks, work, S(stream)));
+  const size_t off = (size_t)d->nblocks * 8 * 8;  // kHistSlices partials per block
+  if (cudaMemcpyAsync(h_out8, work + off, 8 * sizeof(double), cudaMemcpyDeviceToHost, S(stream)) !=
+          cudaSuccess ||
+      cudaStreamSynchronize(S(stream)) != cudaSuccess)
+    return cuda_ok("apk_history_sums") ? 1 : 1;
+  return cuda_ok("apk_history_sums");
+}
+
 int apk_save_u1(const apk_pack_desc_t *d, const apk_block_t *blocks, void *stream) {
   if (check(d, blocks, "apk_save_u1: bad descriptor")) return 1;
   apk_common::launch_save_u1(*d, blocks, S(stream));

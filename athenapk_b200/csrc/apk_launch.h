@@ -35,6 +35,9 @@
                                int nitems, cudaStream_t s);                                     \
   int launch_pressure_gradient(const apk_pack_desc_t &d, const apk_block_t *blocks,             \
                                double threshold, int *tags, double *maxeps, cudaStream_t s);    \
+  size_t history_workspace_bytes(const apk_pack_desc_t &d);                                     \
+  int launch_history(const apk_pack_desc_t &d, const apk_block_t *blocks, double *work,         \
+                     cudaStream_t s);                                                           \
   }
 
 APK_DECLARE_LAUNCHERS(apk_fast)

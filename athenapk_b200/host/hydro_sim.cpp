@@ -150,6 +150,7 @@ HydroSim::~HydroSim() {
   cudaFree(d_push_[1]);
   cudaFree(d_barrier_);
   cudaFree(d_stage_);
+  cudaFree(d_hist_);
   cudaFree(d_int_items_);
   cudaFree(d_sendbuf_);
   cudaFree(d_recvbuf_);
@@ -594,6 +595,11 @@ int HydroSim::CopyToHost(int field, int block, double *dst) {
                              S(stream_)), "D2H");
   Synchronize();
   return 0;
+}
+
+void HydroSim::History(double *out8) {
+  if (!d_hist_) cuda_check(cudaMalloc(&d_hist_, apk_history_workspace_bytes(&desc_)), "history");
+  abi_check(apk_history_sums(&desc_, d_blocks_[cur_], d_hist_, out8, stream_), "apk_history_sums");
 }
 
 size_t HydroSim::InteriorElems() const {

@@ -156,6 +156,8 @@ class HydroSim {
   // an external producer holds): dense [nblocks][nvar][nx3][nx2][nx1].  Load = H2D + scatter into
   // the block interiors + ghost exchange + physical BCs + FillDerived; Store = gather + D2H.
   // Everything is enqueued on the simulation stream (no host synchronisation).
+  // HydroHst volume sums of the local blocks (hydro.cpp:145-208): mass, mom1-3, KE, E, ME, relDivB
+  void History(double *out8);
   size_t InteriorElems() const;
   int LoadStateInterior(const double *h_src);
   int StoreStateInterior(double *h_dst);
@@ -223,6 +225,7 @@ class HydroSim {
   bool nccl_inflight_ = false;  // the last SendBoundBufs used the packed NCCL path
   apk_push_dst_t *d_push_[2] = {nullptr, nullptr};  // [nblocks][27] per prim ping-pong parity
   int *d_barrier_ = nullptr;
+  double *d_hist_ = nullptr;                // history-reduction workspace
   double *d_stage_ = nullptr;               // interior-only staging buffer
   apk_halo_item_t *d_int_items_ = nullptr;  // one slab per block: its interior
   void EnsureStage();

@@ -111,6 +111,9 @@ int apk_sim_copy_from_host(apk_sim_t *s, int field, int block, const double *src
 int apk_sim_upload_all(apk_sim_t *s, int field, const double *src) {
   return guarded([&] { return SIM(s)->UploadAll(field, src); });
 }
+int apk_sim_history(apk_sim_t *s, double *out8) {
+  return guarded([&] { SIM(s)->History(out8); return 0; });
+}
 long long apk_sim_interior_elems(const apk_sim_t *s) {
   return (long long)SIM(const_cast<apk_sim_t *>(s))->InteriorElems();
 }

@@ -235,6 +235,16 @@ int apk_prolongate_minmod_multid(int ndim, int ng, int nvar, const apk_amr_item_
 int apk_tag_pressure_gradient(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
                               double threshold, int *d_tags, double *d_maxeps, void *stream);
 
+/* ---- history reducers HydroHst<...> (src/hydro/hydro.cpp:145-208, registered :422-441): volume
+ * sums over the interior cells of the pack: out8 = {mass, mom1, mom2, mom3, kinetic energy, total
+ * energy, magnetic energy, relative div(B) error}; the last two are 0 for hydro / 1-D.  Blocking
+ * (the result lands in host memory).  Deterministic: fixed-order two-level tree, so two calls on the
+ * same state agree bit for bit (the reference's Kokkos reduction order is unspecified; compare with
+ * a tolerance).  d_work: device scratch of apk_history_workspace_bytes(). */
+size_t apk_history_workspace_bytes(const apk_pack_desc_t *desc);
+int apk_history_sums(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, void *d_work,
+                     double *h_out8, void *stream);
+
 /* FP64 pipe microbenchmark (roofline evidence): runs n_iter dependent-chain-free DFMAs per
  * thread, returns measured FLOP count in *flops; time it with CUDA events from the caller */
 int apk_fp64_probe(int n_blocks, int n_threads, int n_iter, double *d_out, double *flops,

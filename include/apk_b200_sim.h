@@ -55,6 +55,8 @@ int apk_sim_download_all(apk_sim_t *s, int field, double *dst);
  * or an external producer holds).  load = H2D + scatter into the block interiors + ghost exchange
  * + physical BCs + FillDerived (the Mesh::Initialize sequence); store = gather + D2H.  Both are
  * enqueued on the simulation stream without host synchronisation (host buffers should be pinned). */
+/* HydroHst volume sums of the local blocks (hydro.cpp:145-208): mass, mom1-3, KE, E, ME, relDivB */
+int apk_sim_history(apk_sim_t *s, double *out8);
 long long apk_sim_interior_elems(const apk_sim_t *s);
 int apk_sim_load_interior(apk_sim_t *s, const double *src);
 int apk_sim_store_interior(apk_sim_t *s, double *dst);
