@@ -2,19 +2,22 @@
 // update -> Dedner damping -> cons->prim (+ dt reduction) in ONE pass over the pack, without
 // materialising cons.flux (replaces K1-K3, K6, K7, K10 and K11 of SURVEY.md 2.3).
 //
-// Work decomposition (B200: 148 SMs, 1 CTA of 9 warps per SM, <=224 regs/thread for HLLD):
-//  * a CTA owns a TX x TY = 32 x 8 column of one meshblock and MARCHES along x3.  x3-reconstruction
-//    of plane k yields the right state of face k and the left state of face k+1, so every x3 face
-//    is reconstructed and solved exactly once (no redundant work along the march); x1/x2 faces of
-//    a plane are solved inside the plane tile (33/32 and 9/8 faces per cell).
+// Work decomposition (B200: 148 SMs; defaults NW = 4 warps, TY = 4, 3 CTAs per SM, 168 regs):
+//  * a CTA owns a TX x TY = 32 x 4 column of one meshblock and MARCHES along x3 (one of `nchunk`
+//    x3 chunks, blockIdx.z).  x3-reconstruction of plane k yields the right state of face k and
+//    the left state of face k+1, so every x3 face is reconstructed and solved exactly once;
+//    x1/x2 faces of a plane are solved inside the plane tile (33/32 and 5/4 faces per cell).
+//    Three independent CTAs per SM interleave their phases (hides barrier and latency stalls).
 //  * per plane three phases separated by __syncthreads():
-//      recon   : warp tasks (variable, row) -> 32 lanes along x1 (coalesced 256 B rows); L/R
-//                states go to shared memory in sweep-local slot order,
+//      recon   : warp tasks (variable, row) from a per-CTA task table -> 32 lanes along x1
+//                (coalesced 256 B rows); L/R states go to shared memory in sweep-local slot order;
+//                PPM runs warp-vote guarded (recon_ppm_warp).  DC stages instead stage halo'd
+//                prim planes with cp.async and have no recon phase,
 //      riemann : warp tasks (direction, face row); the flux overwrites the L state in place,
 //      finalize: one thread per cell; the x1+x2 divergence and the lower x3 flux stay in
 //                REGISTERS across the march, the cell is finished one plane later when its upper
-//                x3 flux exists; association order of the reference's FluxDivHelper is kept.
-//  * 288 threads: 264 x1-faces + 288 x2-faces + 256 x3-faces = 26 warp tasks on 9 warps.
+//                x3 flux exists (association order of the reference's FluxDivHelper), cons->prim,
+//                dt reduction, and the ghost PUSH into same-device / peer-GPU neighbour blocks.
 // Compiled twice (APK_NS = apk_fast / apk_strict), see apk_launch.h.
 #include <cstdint>
 #include <cstdlib>
@@ -27,17 +30,17 @@ namespace APK_NS {
 namespace {
 
 #ifndef APK_FUSED_NWARPS
-#define APK_FUSED_NWARPS 16
+#define APK_FUSED_NWARPS 4
 #endif
-// register file is split over 4 SM sub-partitions (16 K regs each): 9..12 warps cap at 168
-// regs/thread, 13..16 warps at 128.  Measured (profiles/r01_notes.md): 16 warps with ~400 B of
-// spills beat 12 warps with ~100 B and 8 warps without spills -- resident warps hide the FP64
-// dependency latency that dominates this kernel.
+// The register file is split over 4 SM sub-partitions (16 K regs each): <= 12 resident warps cap at
+// 168 regs/thread, 13..16 at 128.  Measured (profiles/r01_notes.md): 3 CTAs x 4 warps (32x4 tiles)
+// beat 1 x 16, 1 x 12, 2 x 8, 2 x 6 and 3 x 5 warps -- independent CTAs fill each other's barrier
+// and latency bubbles.
 #ifndef APK_FUSED_UNROLL
 #define APK_FUSED_UNROLL 2
 #endif
 #ifndef APK_FUSED_MINBLOCKS
-#define APK_FUSED_MINBLOCKS 1  // CTAs per SM the register budget is sized for
+#define APK_FUSED_MINBLOCKS 3  // CTAs per SM the register budget is sized for
 #endif
 #ifndef APK_FUSED_PREFETCH
 #define APK_FUSED_PREFETCH 1
@@ -49,10 +52,8 @@ namespace {
 #define APK_FUSED_PPM_VOTE 1
 #endif
 #ifndef APK_FUSED_TY
-#define APK_FUSED_TY 8
+#define APK_FUSED_TY 4
 #endif
-// TY = 11 with 12 warps: 12 x1 + 12 x2 + 11 x3 face rows = 35 Riemann warp tasks = 3 full rounds
-// (97 % slot use; TY = 8 gives 26 tasks = 12 + 12 + 2) and less x2 halo work (13/11 vs 10/8).
 constexpr int TX = 32, TY = APK_FUSED_TY, NWARPS = APK_FUSED_NWARPS, NTHREADS = NWARPS * 32;
 static_assert(NTHREADS >= TX * TY, "finalize phase needs one thread per tile cell");
 
