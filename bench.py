@@ -245,6 +245,39 @@ def run_product(args):
             except Exception:
                 pass
     task_ms = {n: (v[0] / v[1] if v[1] else None) for n, v in tt.items() if v[1]}
+    # FP64 context for the roofline: the kernel is bound by the half-rate FP64 pipe, not by HBM
+    # (DESIGN.md 3.1).  Live DFMA peak of this GPU from the library's probe kernel, and the FP64 /
+    # issue utilisation ncu measured for the same kernel (profiles/ncu_r01_final_256.csv).
+    if roof is not None and rank == 0:
+        try:
+            import ctypes as C
+            L = apk.lib()
+            scratch = torch.zeros(8, dtype=torch.float64, device="cuda")
+            flops = C.c_double()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = 0.0
+            for it in range(3):
+                a.record(stream)
+                L.apk_fp64_probe(148 * 8, 256, 20000, C.c_void_p(scratch.data_ptr()), C.byref(flops),
+                                 C.c_void_p(sim.stream))
+                b.record(stream)
+                torch.cuda.synchronize()
+                best = max(best, flops.value / (a.elapsed_time(b) * 1e-3) / 1e12)
+            roof["fp64_dfma_peak_tflops_measured"] = best
+        except Exception:
+            pass
+        try:
+            import csv
+            rows = {r[0]: r[1:] for r in csv.reader(open(os.path.join(ROOT, "profiles",
+                                                                      "ncu_r01_final_256.csv")))}
+            roof["ncu_fp64_pipe_active_pct"] = float(
+                rows["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"][-1])
+            roof["ncu_issue_active_pct"] = float(
+                rows["smsp__issue_active.avg.pct_of_peak_sustained_active"][-1])
+            roof["note"] = ("HBM is the contract roofline; the kernel is limited by the half-rate "
+                            "FP64 pipe and FP64 dependency latency (ncu figures from profiles/)")
+        except Exception:
+            pass
 
     # ---------------- end-to-end through the public API with HOST buffers ----------------
     # Every step: pinned-host conserved state (ghosts included) -> H2D -> FillDerived (cons->prim)
