@@ -96,7 +96,7 @@ SIM_SYMBOLS = [
     "apk_sim_set_c_h", "apk_sim_upload_all", "apk_sim_download_all",
     "apk_sim_interior_elems", "apk_sim_load_interior", "apk_sim_store_interior", "apk_sim_history",
     "apk_sim_enable_task_timing", "apk_sim_task_timing", "apk_sim_num_peers", "apk_sim_peer",
-    "apk_sim_num_halo_items", "apk_sim_halo_item", "apk_sim_neighbor",
+    "apk_sim_num_halo_items", "apk_sim_halo_item", "apk_sim_neighbor", "apk_sim_push_target",
 ]
 
 _lib = None
@@ -368,6 +368,13 @@ class HydroSim:
 
     def neighbor(self, block, o1, o2, o3):
         return self.L.apk_sim_neighbor(self.h, block, o1, o2, o3)
+
+    def push_target(self, block, o1, o2, o3):
+        """(rank, local block index) that receives this block's ghost push in direction (o1,o2,o3),
+        or None (physical boundary / unused dimension)"""
+        r, l = C.c_int(), C.c_int()
+        rc = self.L.apk_sim_push_target(self.h, block, o1, o2, o3, C.byref(r), C.byref(l))
+        return None if rc != 0 else (r.value, l.value)
 
     def synchronize(self):
         self._chk(self.L.apk_sim_synchronize(self.h), "sync")

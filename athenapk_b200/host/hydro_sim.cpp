@@ -460,6 +460,27 @@ int HydroSim::InitComm(const void *uid, int nbytes) {
   return 0;
 }
 
+bool HydroSim::PushTarget(int b, int idx, int *rank, int *local_index) const {
+  const int nb = h_blocks_[b].nbr[idx];
+  if (nb == APK_NBR_NONE || idx == 13) return false;
+  if (nb >= 0) {
+    *rank = cfg_.rank;
+    *local_index = nb;
+    return true;
+  }
+  const int nr = cfg_.nranks;
+  const int base = nblocks_global_ / nr, rem = nblocks_global_ % nr;
+  const int off[3] = {idx % 3 - 1, (idx / 3) % 3 - 1, idx / 9 - 1};
+  int nl[3];
+  for (int d = 0; d < 3; ++d) nl[d] = ((blocks_[b].loc[d] + off[d]) % nb_[d] + nb_[d]) % nb_[d];
+  const int ngid = gid_of_loc_[nl[0] + nb_[0] * (nl[1] + nb_[1] * nl[2])];
+  const int cut = rem * (base + 1);
+  const int r = (ngid < cut) ? ngid / (base + 1) : rem + (ngid - cut) / base;
+  *rank = r;
+  *local_index = ngid - (r * base + std::min(r, rem));
+  return true;
+}
+
 // Map the field buffers of every neighbour rank (CUDA IPC over NVLink/NVSwitch peer access) and
 // build, per prim ping-pong parity, the [nblocks][27] table of ghost-push destinations used by
 // apk_stage_fused_p2p.  Any failure (no peer access, ranks sharing a process, APK_B200_P2P=0) on
@@ -493,26 +514,13 @@ void HydroSim::SetupPeerPush() {
   cuda_check(cudaStreamSynchronize(st), "ipc handles");
   cudaFree(d_all);
 
-  const int base = nblocks_global_ / nr, rem = nblocks_global_ % nr;
-  auto rank_of = [&](int gid) {
-    const int cut = rem * (base + 1);
-    return (gid < cut) ? gid / (base + 1) : rem + (gid - cut) / base;
-  };
-  auto first_gid = [&](int r) { return r * base + std::min(r, rem); };
-  // remote neighbour of (block, offset index): its global id
-  auto remote_gid = [&](size_t b, int idx) {
-    const int off[3] = {idx % 3 - 1, (idx / 3) % 3 - 1, idx / 9 - 1};
-    int nl[3];
-    for (int d = 0; d < 3; ++d) nl[d] = ((blocks_[b].loc[d] + off[d]) % nb_[d] + nb_[d]) % nb_[d];
-    return gid_of_loc_[nl[0] + nb_[0] * (nl[1] + nb_[1] * nl[2])];
-  };
   std::vector<std::array<double *, 3>> peer(nr, std::array<double *, 3>{nullptr, nullptr, nullptr});
   for (size_t b = 0; b < blocks_.size() && ok; ++b)
     for (int idx = 0; idx < 27 && ok; ++idx) {
       const int nb = h_blocks_[b].nbr[idx];
       if (nb >= 0 || nb == APK_NBR_NONE) continue;
-      const int r = rank_of(remote_gid(b, idx));
-      if (peer[r][0]) continue;
+      int r = 0, l = 0;
+      if (!PushTarget((int)b, idx, &r, &l) || peer[r][0]) continue;
       for (int f = 0; f < 3; ++f) {
         void *m = nullptr;
         if (cudaIpcOpenMemHandle(&m, all[r].h[f], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
@@ -547,10 +555,10 @@ void HydroSim::SetupPeerPush() {
           e.prim = d_prim_[1 - which] + nb * per;
           e.cons = d_cons_ + nb * per;
         } else {
-          const int ngid = remote_gid(b, idx), r = rank_of(ngid);
-          const size_t l = (size_t)(ngid - first_gid(r));
-          e.prim = peer[r][1 + (1 - which)] + l * per;
-          e.cons = peer[r][0] + l * per;
+          int r = 0, l = 0;
+          PushTarget((int)b, idx, &r, &l);
+          e.prim = peer[r][1 + (1 - which)] + (size_t)l * per;
+          e.cons = peer[r][0] + (size_t)l * per;
         }
       }
     cuda_check(cudaMalloc(&d_push_[which], tab.size() * sizeof(apk_push_dst_t)), "push table");

@@ -231,6 +231,11 @@ class HydroSim {
   void EnsureStage();
   std::vector<void *> peer_mapped_;
   void SetupPeerPush();
+ public:
+  // ghost-push destination of (block, neighbour offset index): owning rank and the block's local
+  // index there; returns false when there is no neighbour (physical boundary / unused dimension)
+  bool PushTarget(int block, int idx, int *rank, int *local_index) const;
+ private:
   void StageBarrier();
 
   // linear wave pgen state (src/pgen/linear_wave.cpp:43-51)

@@ -191,6 +191,11 @@ int apk_sim_halo_item(const apk_sim_t *s, int recv, int idx, apk_halo_item_t *ou
   *out = v[idx];
   return 0;
 }
+int apk_sim_push_target(const apk_sim_t *s, int block, int o1, int o2, int o3, int *rank,
+                        int *local_index) {
+  const int idx = (o3 + 1) * 9 + (o2 + 1) * 3 + (o1 + 1);
+  return SIM(const_cast<apk_sim_t *>(s))->PushTarget(block, idx, rank, local_index) ? 0 : -1;
+}
 int apk_sim_neighbor(const apk_sim_t *s, int block, int o1, int o2, int o3) {
   return SIM(const_cast<apk_sim_t *>(s))->Neighbor(block, o1, o2, o3);
 }

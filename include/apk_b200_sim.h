@@ -88,6 +88,10 @@ int apk_sim_peer(const apk_sim_t *s, int p, int *rank, long long *send_off, long
                  long long *recv_off, long long *recv_cnt);
 int apk_sim_num_halo_items(const apk_sim_t *s, int recv);
 int apk_sim_halo_item(const apk_sim_t *s, int recv, int idx, apk_halo_item_t *out);
+/* ghost-push destination of (block, offset): owning rank and local block index there (the table
+ * apk_stage_fused_p2p is fed with); -1 when the offset has no neighbour */
+int apk_sim_push_target(const apk_sim_t *s, int block, int o1, int o2, int o3, int *rank,
+                        int *local_index);
 int apk_sim_neighbor(const apk_sim_t *s, int block, int o1, int o2, int o3);
 
 #ifdef __cplusplus

@@ -76,6 +76,43 @@ def main():
                             dst.append(slice(s[d] - ng, s[d])); src.append(slice(e - ng + 1, e + 1))
                     blocks[b][:, dst[2], dst[1], dst[0]] = blocks[nb][:, src[2], src[1], src[0]]
 
+    # ---- peer-push table (what apk_stage_fused_p2p is fed with): every (block, offset) names the
+    # rank and local index of the receiving block; check it against the gathered block lists and
+    # that the relation is symmetric (the receiver's opposite offset points back at the sender)
+    mine = [(sim.block_info(b)[0], tuple(sim.block_info(b)[1])) for b in range(sim.nblocks)]
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    targets = {}
+    nblk = [nx[d] // mb[d] for d in range(3)]
+    for b in range(sim.nblocks):
+        gid, loc = mine[b]
+        for o3 in (-1, 0, 1):
+            for o2 in (-1, 0, 1):
+                for o1 in (-1, 0, 1):
+                    off = (o1, o2, o3)
+                    t = sim.push_target(b, o1, o2, o3)
+                    has_nbr = off != (0, 0, 0)
+                    for d in range(3):
+                        l = loc[d] + off[d]
+                        if off[d] != 0 and (nx[d] == 1 or ((l < 0 or l >= nblk[d]) and bc != "periodic")):
+                            has_nbr = False
+                    assert (t is not None) == has_nbr, (rank, b, off, t)
+                    if t is None:
+                        continue
+                    want_loc = tuple((loc[d] + off[d]) % nblk[d] for d in range(3))
+                    tgid, tloc = everyone[t[0]][t[1]]
+                    assert tloc == want_loc, (rank, b, off, t, tloc, want_loc)
+                    assert (t[0] == rank) == (sim.neighbor(b, o1, o2, o3) >= 0)
+                    targets[(gid, off)] = tgid
+    all_targets = [None] * world
+    dist.all_gather_object(all_targets, targets)
+    merged = {}
+    for t in all_targets:
+        merged.update(t)
+    for (gid, off), tgid in targets.items():
+        back = merged[(tgid, tuple(-o for o in off))]
+        assert back == gid, (gid, off, tgid, back)
+
     # remote neighbours: pack -> gloo send/recv per peer -> unpack
     peers = sim.peers()
     send_items, recv_items = sim.halo_items(False), sim.halo_items(True)
