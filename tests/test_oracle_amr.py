@@ -99,3 +99,34 @@ def test_pressure_gradient_tag_thresholds():
     assert tag == 1 and m == 1.0   # 0.5 * (3 - 1) / 1
     tag, _ = oracle_lib.pressure_gradient_tag(ndim, ng, prim, 4, 3.0)
     assert tag == 0
+
+
+@pytest.mark.parametrize("el", [1, 2, 3])
+def test_flux_restriction_is_conservative(el):
+    """Flux correction (bvals_in_one.hpp:69-80): the restricted coarse-face flux times the coarse
+    face area equals the sum of the fine-face fluxes times the fine face areas, so replacing the
+    coarse flux by it makes the coarse and fine updates see the same mass through the shared face."""
+    ndim, nx, ng, nv = 3, 8, 3, 5
+    nf, nc = shapes(ndim, nx, ng)
+    rng = np.random.default_rng(el)
+    fine = rng.standard_normal((nv, nf[2], nf[1], nf[0]))
+    dx = (0.02, 0.03, 0.05)
+    lo, hi = [ng] * 3, [ng + nx // 2 - 1] * 3
+    hi[el - 1] += 1
+    coarse = np.full((nv, nc[2], nc[1], nc[0]), np.nan)
+    oracle_lib.restrict_average(ndim, ng, el, (0.0, 0.0, 0.0), dx, fine, coarse, lo, hi)
+    t = [d for d in range(3) if d != el - 1]          # transverse directions of the face
+    fine_area = dx[t[0]] * dx[t[1]]
+    for ck in range(lo[2], hi[2] + 1):
+        for cj in range(lo[1], hi[1] + 1):
+            for ci in range(lo[0], hi[0] + 1):
+                c = [ci, cj, ck]
+                f0 = [(c[d] - ng) * 2 + ng for d in range(3)]
+                tot = 0.0
+                for a in (0, 1):
+                    for b in (0, 1):
+                        f = list(f0)
+                        f[t[0]] += a
+                        f[t[1]] += b
+                        tot = tot + fine[:, f[2], f[1], f[0]] * fine_area
+                assert np.allclose(coarse[:, ck, cj, ci] * (4 * fine_area), tot, rtol=1e-14, atol=1e-16)
