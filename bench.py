@@ -98,7 +98,7 @@ def bind_to_gpu_numa_node(index):
 
 def workload(args):
     n = args.n
-    return dict(fluid="glmmhd", recon="ppm", riemann="hlld", integrator="vl2", nx=(n, n, n),
+    return dict(fluid="glmmhd", recon=args.recon, riemann="hlld", integrator="vl2", nx=(n, n, n),
                 mb=(args.mb,) * 3, ng=3, xmin=(0.0, 0.0, 0.0), xmax=(1.0, 1.0, 1.0),
                 gamma=5.0 / 3.0, cfl=0.3)
 
@@ -234,7 +234,7 @@ def run_product(args):
         dur_ms = tt[dom][0] / tt[dom][1]
         bytes_launch = ALG_BYTES_STAGE.get(dom, 288.0) * local_cells
         achieved = bytes_launch / (dur_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_stage_fused<glmmhd,ppm,hlld,3d> (stage 2)" if dom ==
+        roof = {"bound": "hbm", "kernel": ("k_stage_fused<glmmhd,%s,hlld,3d> (stage 2)" % args.recon) if dom ==
                 "fused_stage_other" else dom, "achieved": achieved, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "alg_bytes_per_launch": bytes_launch, "launch_ms": dur_ms}
@@ -368,9 +368,10 @@ def run_product(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "uniform %d^3 GLM-MHD (%s), VL2+PPM+HLLD, meshblock %d^3, "
+                "config": {"workload": "uniform %d^3 GLM-MHD (%s), VL2+%s+HLLD, meshblock %d^3, "
                                        "%d meshblocks, nghost 3, cfl 0.3" %
-                                       (args.n, args.pgen, args.mb, sim.nblocks_global),
+                                       (args.n, args.pgen, args.recon.upper(), args.mb,
+                                        sim.nblocks_global),
                            "fp_mode": args.fp_mode, "fused": sim.fused_active,
                            "l2": "state (%.1f GB/GPU) >> 126 MB L2; no flush needed" %
                                  (sim.nblocks * sim.nvar * sim.n[0] * sim.n[1] * sim.n[2] * 8 * 4 / 1e9),
@@ -396,6 +397,8 @@ def main():
     ap.add_argument("--n", type=int, default=256, help="mesh cells per direction")
     ap.add_argument("--mb", type=int, default=32, help="meshblock cells per direction")
     ap.add_argument("--pgen", default="ot3d", choices=["ot3d", "uniform", "random"])
+    ap.add_argument("--recon", default="ppm", choices=["ppm", "wenoz", "plm", "weno3", "limo3"],
+                    help="reconstruction of the corrector stage (headline metric: ppm)")
     ap.add_argument("--fp-mode", dest="fp_mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
