@@ -254,7 +254,8 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           const int tr = t0 + u * NWARPS;
           const int4 e = *reinterpret_cast<const int4 *>(&sm.tab[min(tr, t_end - 1)]);
           const bool ok = lane_ok && tr < t_end;
-          b.sl[u] = ok ? e.z + (tr < NZ ? zoff : 0) : -1;
+          // (rows beyond the tile have e.z == -1: the x3 double-buffer offset must not revive them)
+          b.sl[u] = (ok && e.z >= 0) ? e.z + (tr < NZ ? zoff : 0) : -1;
           b.sr[u] = ok ? e.w : -1;
           b.st[u] = e.y;
           load_stencil<RECON>(pbase + e.x, e.y & 0x0fffffff, b.v[u]);

@@ -80,9 +80,13 @@ def test_cycles_bitexact_3d(apk, fused, fluid, recon, riemann, integrator, ng):
 
 @pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("nx,mb", [((64, 1, 1), (16, 1, 1)), ((24, 20, 1), (12, 10, 1)),
-                                   ((40, 12, 1), (40, 12, 1)), ((36, 10, 6), (36, 10, 6))])
+                                   ((40, 12, 1), (40, 12, 1)), ((36, 10, 6), (36, 10, 6)),
+                                   ((32, 7, 8), (32, 7, 8)), ((64, 11, 6), (32, 11, 6)),
+                                   ((30, 5, 9), (30, 5, 9))])
 def test_dimensionality_and_ragged_tiles(apk, fused, nx, mb):
-    """1-D / 2-D decks and block sizes that are not multiples of the 32x8 tile."""
+    """1-D / 2-D decks and block sizes that are not multiples of the 32x4 tile (incl. x2 extents
+    with nx2 % 4 == 1, 2, 3: the last x2 tile is ragged; regression for the x3 double-buffer
+    offset reviving skipped rows, found with compute-sanitizer racecheck)."""
     for fluid, recon, riemann in (("euler", "plm", "hllc"), ("glmmhd", "ppm", "hlld")):
         s, o = make_pair(apk, "random", (5, 0.25), fluid=fluid, recon=recon, riemann=riemann,
                          integrator="vl2", ng=3, nx=nx, mb=mb, fp_mode="strict", fused=fused,
