@@ -263,9 +263,12 @@ k_history_partial(ApkGeom g, const apk_block_t *__restrict__ blocks, double *__r
     s[3] += m3 * vol;
     s[4] += 0.5 / d * (m1 * m1 + m2 * m2 + m3 * m3) * vol;
     s[5] += u[4 * g.ncell + c] * vol;
-    if (FLUID == APK_FLUID_GLMMHD && g.ndim >= 2) {
+    if (FLUID == APK_FLUID_GLMMHD) {  // Hst::emag sums in any dimensionality (hydro.cpp:179-183)
       const double *b1 = u + 5 * g.ncell + c, *b2 = u + 6 * g.ncell + c, *b3 = u + 7 * g.ncell + c;
       s[6] += 0.5 * (b1[0] * b1[0] + b2[0] * b2[0] + b3[0] * b3[0]) * vol;
+    }
+    if (FLUID == APK_FLUID_GLMMHD && g.ndim >= 2) {  // the j +- 1 neighbours exist from 2-D on
+      const double *b1 = u + 5 * g.ncell + c, *b2 = u + 6 * g.ncell + c, *b3 = u + 7 * g.ncell + c;
       double divb = (b1[1] - b1[-1]) / B.dx[0] + (b2[sj] - b2[-sj]) / B.dx[1];
       if (g.ndim == 3) divb += (b3[sk] - b3[-sk]) / B.dx[2];
       const double abs_b = sqrt(b1[0] * b1[0] + b2[0] * b2[0] + b3[0] * b3[0]);

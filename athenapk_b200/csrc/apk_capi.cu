@@ -167,20 +167,41 @@ int apk_halo_unpack(const apk_pack_desc_t *d, const apk_block_t *blocks,
   return cuda_ok("apk_halo_unpack");
 }
 
+int apk_stage_fused_ex(const apk_pack_desc_t *d, const apk_block_t *blocks,
+                       double *const *d_prim_out, const apk_stage_args_t *a, void *stream) {
+  if (check(d, blocks, "apk_stage_fused: bad descriptor")) return 1;
+  if (!d_prim_out || !a) {
+    apk_common::set_error("apk_stage_fused: null prim_out / args");
+    return 1;
+  }
+  if ((a->flags & APK_FUSED_FOFC_CHECK) && !a->d_fofc_count) {
+    apk_common::set_error("apk_stage_fused: APK_FUSED_FOFC_CHECK needs d_fofc_count");
+    return 1;
+  }
+  // dedner_source.cpp:34 (host std::exp, like the reference)
+  const double coeff =
+      (d->fluid == APK_FLUID_GLMMHD) ? std::exp(-a->alpha * a->c_h * a->beta_dt / a->mindx) : 1.0;
+  int rc = DISPATCH(d, launch_stage_fused(*d, blocks, d_prim_out, *a, coeff, S(stream)));
+  return rc ? rc : cuda_ok("apk_stage_fused");
+}
+
 int apk_stage_fused_p2p(const apk_pack_desc_t *d, const apk_block_t *blocks,
                         double *const *d_prim_out, const apk_push_dst_t *d_push, double gam0,
                         double gam1, double beta_dt, double c_h, double mindx, double alpha,
                         int recon_override, int flags, double *d_dtmin, void *stream) {
-  if (check(d, blocks, "apk_stage_fused: bad descriptor")) return 1;
-  if (!d_prim_out) {
-    apk_common::set_error("apk_stage_fused: null prim_out");
-    return 1;
-  }
-  const double coeff =
-      (d->fluid == APK_FLUID_GLMMHD) ? std::exp(-alpha * c_h * beta_dt / mindx) : 1.0;
-  int rc = DISPATCH(d, launch_stage_fused(*d, blocks, d_prim_out, gam0, gam1, beta_dt, c_h, coeff,
-                                          recon_override, flags, d_dtmin, d_push, S(stream)));
-  return rc ? rc : cuda_ok("apk_stage_fused");
+  apk_stage_args_t a;
+  memset(&a, 0, sizeof(a));
+  a.gam0 = gam0;
+  a.gam1 = gam1;
+  a.beta_dt = beta_dt;
+  a.c_h = c_h;
+  a.mindx = mindx;
+  a.alpha = alpha;
+  a.recon_override = recon_override;
+  a.flags = flags;
+  a.d_dtmin = d_dtmin;
+  a.d_push = d_push;
+  return apk_stage_fused_ex(d, blocks, d_prim_out, &a, stream);
 }
 
 int apk_stage_fused(const apk_pack_desc_t *d, const apk_block_t *blocks,

@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(NTHREADS, APK_FUSED_MINBLOCKS)
 k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *__restrict__ prim_out,
               double g0, double g1, double bdt, RsPars rsp, double dedner_coeff,
               EosPars eos, int ntx, int flags, unsigned long long *dtmin,
-              const apk_push_dst_t *__restrict__ push, int nchunk) {
+              const apk_push_dst_t *__restrict__ push, int nchunk, int *status,
+              unsigned long long *fofc_count) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool DC = (RECON == APK_RECON_DC);
@@ -484,8 +485,16 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           u[v] = g0 * c0[v] + g1 * c1[v] + bdt * (-d * ivol);  // 1/V once per thread (<= 1 ulp)
 #endif
         }
+        bool fofc_bad = false;
+        if (flags & APK_FUSED_FOFC_CHECK) {
+          // first attempt of FirstOrderFluxCorrect on this very trial update (hydro.cpp:1287-1306)
+          fofc_bad = fofc_needs_correction<NH>(u);
+          if (fofc_bad) atomicAdd(fofc_count, 1ULL);
+        }
         if constexpr (FLUID == APK_FLUID_GLMMHD) u[8] *= dedner_coeff;  // dedner_source.cpp:72
-        cons_to_prim<NH>(u, w, eos);
+        const int err = cons_to_prim<NH>(u, w, eos);
+        // PARTHENON_REQUIRE of ConsToPrim (a cell FOFC flagged is redone by the caller instead)
+        if (err && status && !fofc_bad) atomicMax(status, err);
 #pragma unroll
         for (int v = 0; v < NH; ++v) {
           const long o = (long)v * g.ncell + c;
@@ -572,9 +581,11 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
 
 template <int FLUID, int RECON, int RS>
 int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
-              double *const *prim_out, double g0, double g1, double bdt, double c_h,
-              double coeff, int flags, double *d_dtmin, const apk_push_dst_t *push,
-              cudaStream_t s) {
+              double *const *prim_out, const apk_stage_args_t &a, double coeff, cudaStream_t s) {
+  const double g0 = a.gam0, g1 = a.gam1, bdt = a.beta_dt, c_h = a.c_h;
+  const int flags = a.flags;
+  double *d_dtmin = a.d_dtmin;
+  const apk_push_dst_t *push = a.d_push;
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
   const EosPars eos = {d.gamma, d.dfloor, d.pfloor, d.efloor, d.vceil, d.eceil};
   // IEEE quotients evaluated once on the host (== frcp / fdiv on the device)
@@ -582,13 +593,7 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
   const int ntx = (d.nx[0] + TX - 1) / TX;
   const int nty = (g.ndim >= 2) ? (d.nx[1] + TY - 1) / TY : 1;
   // x3 chunks: aim for >= 16 waves of CTAs (tail < 6 %) while chunks stay >= 8 planes
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (sm_count <= 0) sm_count = 148;
-  }
+  const int sm_count = apk_common::sm_count();
   int nchunk = 1;
   if (g.ndim == 3) {
     static const char *env = std::getenv("APK_B200_KCHUNKS");
@@ -610,13 +615,16 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
 #define APK_LAUNCH_FUSED(ND)                                                                     \
   {                                                                                              \
     auto kern = k_stage_fused<FLUID, RECON, RS, ND>;                                             \
-    static bool attr_set = false;                                                                \
-    if (!attr_set) {                                                                             \
+    /* per-device attribute (a process may drive several GPUs): set once per device */          \
+    static unsigned long long attr_set = 0;                                                      \
+    const int dev = apk_common::current_device();                                                \
+    if (dev >= 64 || !(attr_set >> dev & 1ULL)) {                                                \
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-      attr_set = true;                                                                           \
+      if (dev < 64) attr_set |= 1ULL << dev;                                                     \
     }                                                                                            \
-    kern<<<grid, NTHREADS, smem, s>>>(g, blocks, prim_out, g0, g1, bdt, rsp, coeff, eos,           \
-                                      ntx, flags, dt, push, nchunk);                                    \
+    kern<<<grid, NTHREADS, smem, s>>>(g, blocks, prim_out, g0, g1, bdt, rsp, coeff, eos,         \
+                                      ntx, flags, dt, push, nchunk, a.d_status,                  \
+                                      a.d_fofc_count);                                           \
   }
   if (g.ndim == 3) APK_LAUNCH_FUSED(3)
   else if (g.ndim == 2) APK_LAUNCH_FUSED(2)
@@ -628,16 +636,14 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
 
 template <int FLUID, int RS>
 int fused_recon(int recon, const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
-                double *const *prim_out, double g0, double g1, double bdt, double c_h,
-                double coeff, int flags, double *dt, const apk_push_dst_t *push,
-                cudaStream_t s) {
+                double *const *prim_out, const apk_stage_args_t &a, double coeff, cudaStream_t s) {
   switch (recon) {
-  case APK_RECON_DC: return run_fused<FLUID, APK_RECON_DC, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, push, s);
-  case APK_RECON_PLM: return run_fused<FLUID, APK_RECON_PLM, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, push, s);
-  case APK_RECON_PPM: return run_fused<FLUID, APK_RECON_PPM, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, push, s);
-  case APK_RECON_WENOZ: return run_fused<FLUID, APK_RECON_WENOZ, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, push, s);
-  case APK_RECON_WENO3: return run_fused<FLUID, APK_RECON_WENO3, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, push, s);
-  case APK_RECON_LIMO3: return run_fused<FLUID, APK_RECON_LIMO3, RS>(d, g, blocks, prim_out, g0, g1, bdt, c_h, coeff, flags, dt, push, s);
+  case APK_RECON_DC: return run_fused<FLUID, APK_RECON_DC, RS>(d, g, blocks, prim_out, a, coeff, s);
+  case APK_RECON_PLM: return run_fused<FLUID, APK_RECON_PLM, RS>(d, g, blocks, prim_out, a, coeff, s);
+  case APK_RECON_PPM: return run_fused<FLUID, APK_RECON_PPM, RS>(d, g, blocks, prim_out, a, coeff, s);
+  case APK_RECON_WENOZ: return run_fused<FLUID, APK_RECON_WENOZ, RS>(d, g, blocks, prim_out, a, coeff, s);
+  case APK_RECON_WENO3: return run_fused<FLUID, APK_RECON_WENO3, RS>(d, g, blocks, prim_out, a, coeff, s);
+  case APK_RECON_LIMO3: return run_fused<FLUID, APK_RECON_LIMO3, RS>(d, g, blocks, prim_out, a, coeff, s);
   }
   apk_common::set_error("apk_stage_fused: unknown reconstruction");
   return 1;
@@ -650,42 +656,38 @@ int fused_recon(int recon, const apk_pack_desc_t &d, const ApkGeom &g, const apk
 #endif
 #if APK_FUSED_PART == 0
 int launch_stage_fused_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
-                           double *const *prim_out, double g0, double g1, double bdt, double c_h,
-                           double dedner_coeff, int recon, int flags, double *d_dtmin,
-                           const apk_push_dst_t *push, cudaStream_t s);
+                           double *const *prim_out, const apk_stage_args_t &a,
+                           double dedner_coeff, int recon, cudaStream_t s);
 
 int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
-                       double *const *prim_out, double g0, double g1, double bdt, double c_h,
-                       double dedner_coeff, int recon, int flags, double *d_dtmin,
-                       const apk_push_dst_t *push, cudaStream_t s) {
+                       double *const *prim_out, const apk_stage_args_t &a, double dedner_coeff,
+                       cudaStream_t s) {
   const ApkGeom g = apk_make_geom(d);
-  if (recon < 0) recon = d.recon;
+  const int recon = (a.recon_override < 0) ? d.recon : a.recon_override;
   if (d.nscalars != 0) {
     apk_common::set_error("apk_stage_fused: passive scalars need the un-fused tasks");
     return 1;
   }
   if (d.fluid == APK_FLUID_EULER) {
     switch (d.riemann) {
-    case APK_RIEMANN_NONE: return run_fused<APK_FLUID_EULER, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, push, s);
-    case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, push, s);
-    case APK_RIEMANN_HLLC: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLC>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, push, s);
+    case APK_RIEMANN_NONE: return run_fused<APK_FLUID_EULER, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, a, dedner_coeff, s);
+    case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, a, dedner_coeff, s);
+    case APK_RIEMANN_HLLC: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLC>(recon, d, g, blocks, prim_out, a, dedner_coeff, s);
     }
   } else {
-    return launch_stage_fused_mhd(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, recon,
-                                  flags, d_dtmin, push, s);
+    return launch_stage_fused_mhd(d, g, blocks, prim_out, a, dedner_coeff, recon, s);
   }
   apk_common::set_error("apk_stage_fused: unsupported fluid/riemann combination");
   return 1;
 }
 #else
 int launch_stage_fused_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
-                           double *const *prim_out, double g0, double g1, double bdt, double c_h,
-                           double dedner_coeff, int recon, int flags, double *d_dtmin,
-                           const apk_push_dst_t *push, cudaStream_t s) {
+                           double *const *prim_out, const apk_stage_args_t &a,
+                           double dedner_coeff, int recon, cudaStream_t s) {
   switch (d.riemann) {
-  case APK_RIEMANN_NONE: return run_fused<APK_FLUID_GLMMHD, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, push, s);
-  case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, push, s);
-  case APK_RIEMANN_HLLD: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLD>(recon, d, g, blocks, prim_out, g0, g1, bdt, c_h, dedner_coeff, flags, d_dtmin, push, s);
+  case APK_RIEMANN_NONE: return run_fused<APK_FLUID_GLMMHD, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, a, dedner_coeff, s);
+  case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, a, dedner_coeff, s);
+  case APK_RIEMANN_HLLD: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLD>(recon, d, g, blocks, prim_out, a, dedner_coeff, s);
   }
   apk_common::set_error("apk_stage_fused: unsupported fluid/riemann combination");
   return 1;

@@ -25,6 +25,22 @@ static std::mutex g_err_mutex;
 static std::string g_err;
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+int sm_count() {
+  static int cache[64] = {0};
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64) return 148;
+  if (!cache[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = (n > 0) ? n : 148;
+  }
+  return cache[dev];
+}
 long long launches() { return g_launches.load(); }
 void reset_launches() { g_launches.store(0); }
 void set_error(const char *msg) {

@@ -26,9 +26,8 @@
   int launch_min_dt(const apk_pack_desc_t &d, const apk_block_t *blocks, double *d_out,         \
                     cudaStream_t s);                                                            \
   int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,                   \
-                         double *const *prim_out, double g0, double g1, double bdt, double c_h, \
-                         double dedner_coeff, int recon, int flags, double *d_dtmin,            \
-                         const apk_push_dst_t *push, cudaStream_t s);                           \
+                         double *const *prim_out, const apk_stage_args_t &a,                    \
+                         double dedner_coeff, cudaStream_t s);                                  \
   int launch_restrict_average(int ndim, int ng, int nvar, int el, const apk_amr_item_t *items,  \
                               int nitems, cudaStream_t s);                                      \
   int launch_prolongate_minmod(int ndim, int ng, int nvar, const apk_amr_item_t *items,         \
@@ -58,6 +57,8 @@ int launch_halo_unpack(const apk_pack_desc_t &d, const apk_block_t *blocks,
 int launch_save_u1(const apk_pack_desc_t &d, const apk_block_t *blocks, cudaStream_t s);
 int launch_fp64_probe(int nb, int nt, int niter, double *out, cudaStream_t s);
 void count_launch(int n = 1);
+int current_device();
+int sm_count();  // of the current device
 long long launches();
 void reset_launches();
 const char *last_error();

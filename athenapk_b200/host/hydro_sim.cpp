@@ -106,6 +106,9 @@ HydroSim::HydroSim(const SimConfig &cfg)
     throw std::runtime_error("HLLD requires fluid = glmmhd");
   if (cfg_.fluid == APK_FLUID_GLMMHD && cfg_.riemann == APK_RIEMANN_HLLC)
     throw std::runtime_error("HLLC requires fluid = euler");
+  for (int f = 0; f < 6; ++f)  // src/bvals/boundary_conditions_apk.hpp:50-52
+    if (cfg_.bc[f] == APK_BC_REFLECT && cfg_.fluid == APK_FLUID_GLMMHD)
+      throw std::runtime_error("Reflecting boundary conditions for MHD need special treatment.");
   for (int d = 0; d < 3; ++d) {
     if (cfg_.nx[d] % cfg_.mb[d] != 0)
       throw std::runtime_error("Block size is not evenly divisible into the base mesh size.");
@@ -760,12 +763,20 @@ TaskStatus HydroSim::FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, b
     cuda_check(cudaMemcpyAsync(d_scalars_, d_scalars_ + 8, sizeof(double), cudaMemcpyDeviceToDevice,
                                S(stream_)), "init dtmin");
   }
-  abi_check(apk_stage_fused_p2p(&desc_, d_blocks_[cur_], d_prim_out_[cur_],
-                                p2p_ ? d_push_[cur_] : nullptr, gam0, gam1, beta_dt, c_h,
-                            mindx, cfg_.glmmhd_alpha, recon,
-                            stage_flags | APK_FUSED_PUSH_PRIM |
-                                (last_stage ? APK_FUSED_PUSH_CONS : 0),
-                            dtmin, stream_), "apk_stage_fused");
+  apk_stage_args_t a{};
+  a.gam0 = gam0;
+  a.gam1 = gam1;
+  a.beta_dt = beta_dt;
+  a.c_h = c_h;
+  a.mindx = mindx;
+  a.alpha = cfg_.glmmhd_alpha;
+  a.recon_override = recon;
+  a.flags = stage_flags | APK_FUSED_PUSH_PRIM | (last_stage ? APK_FUSED_PUSH_CONS : 0);
+  a.d_dtmin = dtmin;
+  a.d_status = d_status_;
+  a.d_push = p2p_ ? d_push_[cur_] : nullptr;
+  abi_check(apk_stage_fused_ex(&desc_, d_blocks_[cur_], d_prim_out_[cur_], &a, stream_),
+            "apk_stage_fused");
   cur_ ^= 1;  // prim_out becomes "prim"
   return TaskStatus::complete;
 }
@@ -982,12 +993,10 @@ TaskStatus HydroSim::Step() {  // multistage.hpp:39-53
     const TaskStatus st = timing_on_ ? ExecuteTimed(tl) : tl.Execute();
     if (st != TaskStatus::complete) return st;
   }
-  if (fused_ && cur_ != 0) {
-    // odd number of stages: bring the final primitives back into the caller-visible array
-    cuda_check(cudaMemcpyAsync(d_prim_[0], d_prim_[1], BlockFieldElems() * blocks_.size() * sizeof(double),
-                               cudaMemcpyDeviceToDevice, S(stream_)), "prim copy-back");
-    cur_ = 0;
-  }
+  // Integrators with an odd number of stages leave the final primitives in the second ping-pong
+  // buffer: cur_ simply persists into the next cycle (every table is indexed by parity).  No
+  // copy-back: in p2p mode a copy here would race with the neighbour rank's next stage-1 kernel,
+  // which already peer-stores into the buffer being copied.
   return TaskStatus::complete;
 }
 

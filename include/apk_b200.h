@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define APK_ABI_VERSION 2
+#define APK_ABI_VERSION 3
 
 /* src/main.hpp:19-50 (enum values are ours; the shim translates) */
 enum { APK_FLUID_EULER = 0, APK_FLUID_GLMMHD = 1 };
@@ -202,6 +202,33 @@ int apk_stage_fused_p2p(const apk_pack_desc_t *desc, const apk_block_t *d_blocks
                         double *const *d_prim_out, const apk_push_dst_t *d_push, double gam0,
                         double gam1, double beta_dt, double c_h, double mindx, double alpha,
                         int recon_override, int flags, double *d_dtmin, void *stream);
+
+/* Full-argument form of the fused stage (ABI 3); apk_stage_fused / apk_stage_fused_p2p are thin
+ * wrappers that leave d_status / d_fofc_count NULL.
+ *  d_status (device int, may be NULL): atomicMax'ed with 1 / 2 when a finished cell has negative
+ *    density / pressure and no floor is active -- the PARTHENON_REQUIRE of ConsToPrim
+ *    (adiabatic_hydro.hpp:77-79,111-113, adiabatic_glmmhd.hpp:97,137); the caller aborts on it.
+ *  d_fofc_count (device uint64, may be NULL; flag APK_FUSED_FOFC_CHECK): the stage also evaluates
+ *    the first attempt of FirstOrderFluxCorrect (hydro.cpp:1268-1306) on its own trial update --
+ *    the number of cells with rho_new <= 0 or (E - KE - ME)_new <= 0 is added to *d_fofc_count.
+ *    Zero means FOFC would not have touched any flux and the stage result is final (the common
+ *    case: the whole Orszag-Tang golden run); non-zero means the caller must discard the stage
+ *    (restore cons from the copy APK_FUSED_SAVE_U1 left in cons_u1, or from cons itself after an
+ *    APK_FUSED_PRIM_ONLY stage) and redo it with the flux-materialising tasks
+ *    apk_calc_fluxes -> apk_first_order_flux_correct -> apk_flux_div_update -> ... */
+typedef struct apk_stage_args {
+  double gam0, gam1, beta_dt;   /* low_storage_integrator.cpp:53-132 */
+  double c_h, mindx, alpha;     /* GLM: hydro.cpp:102-143, dedner_source.cpp:34 */
+  int recon_override;           /* >= 0 replaces desc->recon (VL2 predictor: DC) */
+  int flags;                    /* APK_FUSED_* */
+  double *d_dtmin;              /* may be NULL */
+  int *d_status;                /* may be NULL */
+  const apk_push_dst_t *d_push; /* may be NULL: same-device neighbours from nbr[] */
+  unsigned long long *d_fofc_count; /* may be NULL */
+} apk_stage_args_t;
+#define APK_FUSED_FOFC_CHECK 32
+int apk_stage_fused_ex(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                       double *const *d_prim_out, const apk_stage_args_t *args, void *stream);
 
 /* copy cons -> cons_u1 for all blocks (u1 <- u0 at stage 1, hydro_driver.cpp:474-495) */
 int apk_save_u1(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, void *stream);

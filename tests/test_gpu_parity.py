@@ -136,6 +136,23 @@ def test_floors_and_ceilings(apk):
         s.close()
 
 
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("nx,mb", [((32, 32, 32), (16, 16, 16)), ((64, 32, 1), (32, 16, 1))])
+def test_negative_state_without_floor_aborts(apk, fused, nx, mb):
+    """ConsToPrim's PARTHENON_REQUIRE (adiabatic_hydro.hpp:77-79,111-113): with no floor set, a
+    negative density / pressure aborts the run.  The fused stage kernel has to raise the same flag
+    as the un-fused k_cons_to_prim (an unstable CFL number drives a strong blast negative)."""
+    s = apk.HydroSim(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", ng=2, nx=nx,
+                     mb=mb, cfl=6.0, gamma=1.4, xmin=(-0.5,) * 3, xmax=(0.5,) * 3,
+                     fp_mode="strict", fused=fused)
+    assert s.fused_active == fused
+    s.pgen("blast", (0.2, 1.0e-3, 1.0e6, 1.0))
+    s.initialize()
+    with pytest.raises(RuntimeError, match="negative (density|pressure)"):
+        s.execute(None, 40)
+    s.close()
+
+
 @pytest.mark.parametrize("fluid,recon,riemann,ng", [("glmmhd", "ppm", "hlld", 3),
                                                     ("euler", "plm", "hllc", 2)])
 @pytest.mark.parametrize("fac", [4.0, 8.0])
