@@ -57,13 +57,6 @@ namespace {
 constexpr int TX = 32, TY = APK_FUSED_TY, NWARPS = APK_FUSED_NWARPS, NTHREADS = NWARPS * 32;
 static_assert(NTHREADS >= TX * TY, "finalize phase needs one thread per tile cell");
 
-APK_DEV constexpr int slot_of_var(int v, int dir) {
-  // inverse of var_of_slot(): sweep-local slot that holds memory variable v
-  if (v >= 1 && v <= 3) return 1 + (v - 1 - dir + 3) % 3;
-  if (v >= 5 && v <= 7) return 5 + (v - 5 - dir + 3) % 3;
-  return v;
-}
-
 // One reconstruction warp task = one variable x one row of 32 cells.  The (direction, variable,
 // row) -> (global offset, stride, shared-memory destinations) decode is plane independent, so it
 // is done ONCE per CTA into a shared table; the per-plane loop then costs one LDS.128 and a few
@@ -654,6 +647,12 @@ int fused_recon(int recon, const apk_pack_desc_t &d, const ApkGeom &g, const apk
 #ifndef APK_FUSED_PART
 #define APK_FUSED_PART 0
 #endif
+int launch_stage_rows_euler(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
+                            double *const *prim_out, const apk_stage_args_t &a, double coeff,
+                            int recon, cudaStream_t s);
+int launch_stage_rows_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
+                          double *const *prim_out, const apk_stage_args_t &a, double coeff,
+                          int recon, cudaStream_t s);
 #if APK_FUSED_PART == 0
 int launch_stage_fused_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
                            double *const *prim_out, const apk_stage_args_t &a,
@@ -667,6 +666,16 @@ int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
   if (d.nscalars != 0) {
     apk_common::set_error("apk_stage_fused: passive scalars need the un-fused tasks");
     return 1;
+  }
+  // APK_B200_FUSED_V=2 selects the row-task kernel (apk_rows.cu, 2-D / 3-D meshes) for A/B runs:
+  // bit-identical results, 3 % fewer instructions, but 34 % slower at 256^3 -- its 115 KB of
+  // straight-line SASS per plane overflows the 32 KB L1.5 instruction cache (ncu: 2.1 warps stalled
+  // on `no_instruction` per issue against 0.11 here; profiles/r02_notes.md)
+  static const char *ver = std::getenv("APK_B200_FUSED_V");
+  if (g.ndim >= 2 && ver && ver[0] == '2') {
+    if (d.fluid == APK_FLUID_EULER)
+      return launch_stage_rows_euler(d, g, blocks, prim_out, a, dedner_coeff, recon, s);
+    return launch_stage_rows_mhd(d, g, blocks, prim_out, a, dedner_coeff, recon, s);
   }
   if (d.fluid == APK_FLUID_EULER) {
     switch (d.riemann) {

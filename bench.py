@@ -3,11 +3,15 @@
 
 Metric (BASELINE.json): cell-updates/s (== Parthenon zone-cycles/s, driver.cpp:53-64) of uniform
 256^3 GLM-MHD, VL2 + PPM + HLLD, 32^3 meshblocks, on 1/2/4/8 B200 (strong scaling: the 256^3 mesh
-is split over the ranks, ghost zones exchanged with packed NCCL send/recv).  One "step" = one
-full cycle (both VL2 stages, Dedner source, cons->prim, ghost exchange, dt reduction).
+is split over the ranks; ghost zones of remote neighbours are peer stores of the stage kernel over
+CUDA-IPC mapped NVLink memory -- `config.halo` says which exchange ran; NCCL carries the 4-byte stage
+barrier and the dt min).  One "step" = one full cycle (both VL2 stages, Dedner source, cons->prim,
+ghost exchange, dt reduction).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]      # product arm (this repo's CUDA path)
-  python bench.py --impl reference ...                      # reference arm: CPU implementation
+  python bench.py --impl reference ...                      # reference arm: the UNMODIFIED reference,
+                                                            # Kokkos-Serial build, one copy per core
+  python bench.py --config ot2d                             # BASELINE config 3 (Orszag-Tang, FOFC on)
 
 Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the byte model.
 """
@@ -98,9 +102,18 @@ def bind_to_gpu_numa_node(index):
 
 def workload(args):
     n = args.n
-    return dict(fluid="glmmhd", recon=args.recon, riemann="hlld", integrator="vl2", nx=(n, n, n),
-                mb=(args.mb,) * 3, ng=3, xmin=(0.0, 0.0, 0.0), xmax=(1.0, 1.0, 1.0),
-                gamma=5.0 / 3.0, cfl=0.3)
+    if args.config == "ot2d":  # BASELINE config 3: inputs/orszag_tang.in scaled up, FOFC on
+        return dict(fluid="glmmhd", recon=args.recon, riemann="hlld", integrator="vl2", nx=(n, n, 1),
+                    mb=(args.mb, args.mb, 1), ng=3, xmin=(-0.5, -0.5, -0.5), xmax=(0.5, 0.5, 0.5),
+                    gamma=5.0 / 3.0, cfl=0.4, fofc=True)
+    kw = dict(fluid="glmmhd", recon=args.recon, riemann="hlld", integrator="vl2", nx=(n, n, n),
+              mb=(args.mb,) * 3, ng=3, xmin=(0.0, 0.0, 0.0), xmax=(1.0, 1.0, 1.0),
+              gamma=5.0 / 3.0, cfl=0.3)
+    if args.pgen == "uniform":       # the deck's own state and gamma (turbulence.in:63-69)
+        kw["gamma"] = 1.0001
+    if args.pgen == "orszag_tang":   # baseline/decks/orszag_tang_3d.in
+        kw.update(xmin=(-0.5, -0.5, -0.5), xmax=(0.5, 0.5, 0.5))
+    return kw
 
 
 def cpu_sample(cycles, n=64, mb=32):
@@ -396,7 +409,9 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--n", type=int, default=256, help="mesh cells per direction")
     ap.add_argument("--mb", type=int, default=32, help="meshblock cells per direction")
-    ap.add_argument("--pgen", default="ot3d", choices=["ot3d", "uniform", "random"])
+    ap.add_argument("--pgen", default="ot3d", choices=["ot3d", "uniform", "random", "orszag_tang"])
+    ap.add_argument("--config", default="uni256", choices=["uni256", "ot2d"],
+                    help="uni256: BASELINE config 4 (headline); ot2d: config 3, 2-D Orszag-Tang + FOFC")
     ap.add_argument("--recon", default="ppm", choices=["ppm", "wenoz", "plm", "weno3", "limo3"],
                     help="reconstruction of the corrector stage (headline metric: ppm)")
     ap.add_argument("--fp-mode", dest="fp_mode", default="fast", choices=["fast", "strict"])
