@@ -90,7 +90,7 @@ SIM_SYMBOLS = [
     "apk_sim_execute", "apk_sim_step", "apk_sim_num_local_blocks", "apk_sim_num_global_blocks",
     "apk_sim_nvar", "apk_sim_block_dims", "apk_sim_block_info", "apk_sim_copy_to_host",
     "apk_sim_copy_from_host", "apk_sim_device_ptr", "apk_sim_time", "apk_sim_dt",
-    "apk_sim_ncycle", "apk_sim_c_h", "apk_sim_fofc_corrections", "apk_sim_fused_active", "apk_sim_p2p_active",
+    "apk_sim_ncycle", "apk_sim_c_h", "apk_sim_fofc_corrections", "apk_sim_fofc_redone_stages", "apk_sim_fused_active", "apk_sim_p2p_active",
     "apk_sim_linear_wave_period", "apk_sim_linear_wave_errors", "apk_sim_stream",
     "apk_sim_pack_desc", "apk_sim_device_blocks", "apk_sim_synchronize", "apk_sim_task",
     "apk_sim_set_c_h", "apk_sim_upload_all", "apk_sim_download_all",
@@ -175,6 +175,8 @@ def lib():
         getattr(L, f).restype = C.c_double
     L.apk_sim_fofc_corrections.argtypes = [vp]
     L.apk_sim_fofc_corrections.restype = C.c_longlong
+    L.apk_sim_fofc_redone_stages.argtypes = [vp]
+    L.apk_sim_fofc_redone_stages.restype = C.c_longlong
     L.apk_sim_linear_wave_errors.argtypes = [vp, dp]
     for f in ("apk_sim_stream", "apk_sim_pack_desc", "apk_sim_device_blocks"):
         getattr(L, f).argtypes = [vp]
@@ -384,13 +386,15 @@ class HydroSim:
     ncycle = property(lambda s: s.L.apk_sim_ncycle(s.h))
     c_h = property(lambda s: s.L.apk_sim_c_h(s.h))
     fofc_corrections = property(lambda s: s.L.apk_sim_fofc_corrections(s.h))
+    fofc_redone_stages = property(lambda s: s.L.apk_sim_fofc_redone_stages(s.h))
     fused_active = property(lambda s: bool(s.L.apk_sim_fused_active(s.h)))
     p2p_active = property(lambda s: bool(s.L.apk_sim_p2p_active(s.h)))
     lw_tlim = property(lambda s: s.L.apk_sim_linear_wave_period(s.h))
     stream = property(lambda s: s.L.apk_sim_stream(s.h))
 
     def linear_wave_errors(self):
-        out = np.zeros(6)
+        """[RMS-L1, per-variable L1 ...]: 5 variables (linear_wave) or 8 (linear_wave_mhd)"""
+        out = np.zeros(9)
         self._chk(self.L.apk_sim_linear_wave_errors(self.h, out.ctypes.data_as(
             C.POINTER(C.c_double))), "linear_wave_errors")
         return out

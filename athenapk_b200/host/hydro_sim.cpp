@@ -116,7 +116,10 @@ HydroSim::HydroSim(const SimConfig &cfg)
     n_[d] = (cfg_.nx[d] == 1) ? 1 : cfg_.mb[d] + 2 * cfg_.ng;
   }
   nblocks_global_ = nb_[0] * nb_[1] * nb_[2];
-  fused_ = cfg_.fused && !cfg_.fofc && !cfg_.dedner_extended && cfg_.riemann != APK_RIEMANN_LLF &&
+  // FOFC decks run fused too: the stage kernel evaluates FirstOrderFluxCorrect's first attempt on
+  // its own trial update, and only a stage in which a cell actually fails is redone with the
+  // flux-materialising tasks (FusedFofcCheck)
+  fused_ = cfg_.fused && !cfg_.dedner_extended && cfg_.riemann != APK_RIEMANN_LLF &&
            cfg_.nscalars == 0;
   BuildMesh();
   BuildNeighbors();
@@ -146,6 +149,7 @@ HydroSim::~HydroSim() {
   if (h_scalars_) cudaFreeHost(h_scalars_);
   cudaFree(d_status_);
   cudaFree(d_fofc_work_);
+  cudaFree(d_undo_);
   cudaFree(d_send_items_);
   cudaFree(d_recv_items_);
   for (void *m : peer_mapped_) cudaIpcCloseMemHandle(m);
@@ -301,11 +305,16 @@ void HydroSim::UploadBlocks() {
   if (fused_) {
     cuda_check(cudaMalloc(&d_prim_[1], bytes), "cudaMalloc prim scratch");
     cuda_check(cudaMemset(d_prim_[1], 0, bytes), "memset");
-  } else {
+  }
+  if (!fused_ || cfg_.fofc) {
     for (int d = 0; d < ndim_; ++d) {
       cuda_check(cudaMalloc(&d_flux_[d], bytes), "cudaMalloc flux");
       cuda_check(cudaMemset(d_flux_[d], 0, bytes), "memset");
     }
+  }
+  if (fused_ && cfg_.fofc && cfg_.integrator != (int)Integrator::vl2 && integrator_.nstages > 1) {
+    // stages after the first overwrite their input cons: keep a copy to roll back to
+    cuda_check(cudaMalloc(&d_undo_, bytes), "cudaMalloc fofc undo");
   }
   for (int which = 0; which < (fused_ ? 2 : 1); ++which) {
     std::vector<apk_block_t> hb = h_blocks_;
@@ -753,8 +762,21 @@ TaskStatus HydroSim::FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, b
   // produces only the half-step primitives and u^n stays in cons, where stage 2 picks it up as
   // u1 (no u1 <- u0 copy, no predictor cons store).  Other integrators: u1 saved by stage 1.
   const bool vl2 = cfg_.integrator == (int)Integrator::vl2;
-  const int stage_flags = vl2 ? (stage == 1 ? APK_FUSED_PRIM_ONLY : APK_FUSED_U1_FROM_CONS)
-                              : (stage == 1 ? APK_FUSED_SAVE_U1 : 0);
+  int stage_flags = vl2 ? (stage == 1 ? APK_FUSED_PRIM_ONLY : APK_FUSED_U1_FROM_CONS)
+                        : (stage == 1 ? APK_FUSED_SAVE_U1 : 0);
+  unsigned long long *d_fofc_count = nullptr;
+  if (cfg_.fofc) {
+    // optimistic FOFC: count the cells that fail the first attempt and keep the stage's input
+    // cons restorable -- VL2 stage 1 leaves cons alone, stage 1 of the other integrators and the
+    // VL2 corrector save it into cons_u1, later stages of rk2 / rk3 into d_undo_
+    stage_flags |= APK_FUSED_FOFC_CHECK;
+    if (vl2 && stage == 2) stage_flags |= APK_FUSED_SAVE_U1;
+    if (!vl2 && stage > 1)
+      cuda_check(cudaMemcpyAsync(d_undo_, d_cons_, BlockFieldElems() * blocks_.size() * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, S(stream_)), "fofc undo copy");
+    d_fofc_count = reinterpret_cast<unsigned long long *>(d_scalars_ + 16);
+    cuda_check(cudaMemsetAsync(d_fofc_count, 0, sizeof(unsigned long long), S(stream_)), "fofc count");
+  }
   double *dtmin = nullptr;
   if (last_stage) {
     dtmin = d_scalars_;
@@ -775,9 +797,55 @@ TaskStatus HydroSim::FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, b
   a.d_dtmin = dtmin;
   a.d_status = d_status_;
   a.d_push = p2p_ ? d_push_[cur_] : nullptr;
+  a.d_fofc_count = d_fofc_count;
   abi_check(apk_stage_fused_ex(&desc_, d_blocks_[cur_], d_prim_out_[cur_], &a, stream_),
             "apk_stage_fused");
   cur_ ^= 1;  // prim_out becomes "prim"
+  return TaskStatus::complete;
+}
+
+// FirstOrderFluxCorrect for a fused stage (hydro.cpp:1223-1342).  The stage kernel has counted the
+// cells whose trial update fails the first attempt's test.  Zero (the usual case): FOFC would not
+// have changed any flux and the fused result stands.  Otherwise the stage is rolled back and redone
+// with the reference's task sequence (calc_flux -> first_order_flux_correct -> update -> source ->
+// exchange -> fill_derived); the read-back blocks the host like the reference's own reduction.
+TaskStatus HydroSim::FusedFofcCheck(int stage, Real gam0, Real gam1, Real beta_dt, bool last_stage) {
+  unsigned long long *d_count = reinterpret_cast<unsigned long long *>(d_scalars_ + 16);
+  if (cfg_.nranks > 1)
+    ncclAllReduce(d_count, d_count, 1, ncclUint64, ncclSum, reinterpret_cast<ncclComm_t>(comm_),
+                  S(stream_));
+  unsigned long long *h_count = reinterpret_cast<unsigned long long *>(h_scalars_ + 2);
+  cuda_check(cudaMemcpyAsync(h_count, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             S(stream_)), "fofc count D2H");
+  Synchronize();
+  if (*h_count == 0) return TaskStatus::complete;
+  fofc_redone_stages += 1;
+  const bool vl2 = cfg_.integrator == (int)Integrator::vl2;
+  const size_t bytes = BlockFieldElems() * blocks_.size() * sizeof(double);
+  cur_ ^= 1;  // back to the stage's input primitives (the un-fused tasks work in place)
+  // restore the stage's input cons
+  if (vl2 && stage == 2)
+    cuda_check(cudaMemcpyAsync(d_cons_, d_u1_, bytes, cudaMemcpyDeviceToDevice, S(stream_)), "undo");
+  else if (!vl2 && stage == 1)
+    cuda_check(cudaMemcpyAsync(d_cons_, d_u1_, bytes, cudaMemcpyDeviceToDevice, S(stream_)), "undo");
+  else if (!vl2)
+    cuda_check(cudaMemcpyAsync(d_cons_, d_undo_, bytes, cudaMemcpyDeviceToDevice, S(stream_)), "undo");
+  if (stage == 1) InitU1();
+  CalculateFluxes(stage);
+  FirstOrderFluxCorrect(gam0, gam1, beta_dt);
+  UpdateWithFluxDivergence(gam0, gam1, beta_dt);
+  AddUnsplitSources(beta_dt);
+  SendBoundBufs(0);
+  ReceiveBoundBufs();
+  SetBounds(0);
+  ApplyBoundaryConditions(0);
+  FillDerived();
+  if (vl2 && stage == 1) {
+    // back to the fused convention of the VL2 corrector: u^n lives in cons
+    cuda_check(cudaMemcpyAsync(d_cons_, d_u1_, bytes, cudaMemcpyDeviceToDevice, S(stream_)),
+               "restore u^n");
+  }
+  if (last_stage) last_stage_unfused_ = true;
   return TaskStatus::complete;
 }
 
@@ -951,6 +1019,9 @@ void HydroSim::MakeTaskCollection(TaskList &tl, int stage) {
     // the copy), so the separate FillDerived region disappears.
     tl.AddTask(stage == 1 ? "fused_stage_first" : "fused_stage_other",
                [=] { return FusedStage(stage, gam0, gam1, beta_dt, last); });
+    if (cfg_.fofc)
+      tl.AddTask("first_order_flux_correct",
+                 [=] { return FusedFofcCheck(stage, gam0, gam1, beta_dt, last); });
     // between stages only prim ghosts are consumed; the last stage also completes cons so the
     // state handed back after the cycle is identical to the reference's, ghosts included
     const int fields = last ? 1 : 2;
@@ -981,7 +1052,11 @@ void HydroSim::MakeTaskCollection(TaskList &tl, int stage) {
       dt_hyp = std::numeric_limits<Real>::max();
       return TaskStatus::complete;
     });
-    tl.AddTask("new_dt", [this] { return EstimateTimestep(fused_); });
+    tl.AddTask("new_dt", [this] {
+      const bool have = fused_ && !last_stage_unfused_;
+      last_stage_unfused_ = false;
+      return EstimateTimestep(have);
+    });
   }
 }
 

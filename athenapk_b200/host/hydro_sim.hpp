@@ -115,7 +115,9 @@ class HydroSim {
   // ---- problem generators (input side; src/pgen/*.cpp) ----
   int ProblemGenerator(const std::string &id, const std::vector<double> &pars);
   double LinearWavePeriod() const { return lw_.tlim_period; }
-  void LinearWaveErrors(double *out6);  // linear_wave.cpp:183-295 (local blocks only)
+  // linear_wave.cpp:183-295 / linear_wave_mhd.cpp:183-330 (local blocks only): out[0] = RMS-L1,
+  // out[1..] = per-variable L1 (5 values, or 8 for the magnetised wave); out has 9 entries
+  void LinearWaveErrors(double *out9);
 
   // ---- driver (driver.cpp / multistage.hpp / hydro_driver.cpp) ----
   void Initialize(double tlim);  // Mesh::Initialize + InitializeBlockTimeSteps + SetGlobalTimeStep
@@ -130,6 +132,7 @@ class HydroSim {
   TaskStatus UpdateWithFluxDivergence(Real gam0, Real gam1, Real beta_dt);
   TaskStatus AddUnsplitSources(Real beta_dt);
   TaskStatus FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, bool last_stage);
+  TaskStatus FusedFofcCheck(int stage, Real gam0, Real gam1, Real beta_dt, bool last_stage);
   TaskStatus StartReceiveBoundBufs();
   // with_prim: 0 cons, 1 cons+prim, 2 prim only; local_done: same-device ghosts already pushed
   TaskStatus SendBoundBufs(int with_prim, bool local_done = false, bool need_barrier = true);
@@ -149,6 +152,7 @@ class HydroSim {
   Real c_h = 0.0, mindx = std::numeric_limits<Real>::max(),
        dt_hyp = std::numeric_limits<Real>::max();
   long long fofc_corrections = 0;
+  long long fofc_redone_stages = 0;  // fused stages rolled back and redone with the FOFC tasks
   long long cycles_done = 0;
   bool FusedActive() const { return fused_; }
   bool P2PActive() const { return p2p_; }
@@ -204,6 +208,8 @@ class HydroSim {
   double *h_scalars_ = nullptr;  // pinned host mirror of d_scalars_[0..1] (one async D2H per cycle)
   int *d_status_ = nullptr;
   void *d_fofc_work_ = nullptr;
+  double *d_undo_ = nullptr;         // copy of a stage's input cons (fused FOFC, rk2 / rk3)
+  bool last_stage_unfused_ = false;  // the cycle's last stage was redone un-fused: no device dt min
   void *stream_ = nullptr;
 
   // halo plan
@@ -245,9 +251,15 @@ class HydroSim {
     double amp = 0, vflow = 0, sin_a2 = 0, cos_a2 = 1, sin_a3 = 0, cos_a3 = 1, lambda = 1, k_par = 1,
            d0 = 1, p0 = 1, u0 = 0, gm1 = 1, tlim_period = 1;
     double ev[5], rem[5][5];
+    // magnetised wave (src/pgen/linear_wave_mhd.cpp:40-48)
+    bool mhd = false;
+    double bx0 = 0, by0 = 0, bz0 = 0, dby = 0, dbz = 0;
+    double ev7[7], rem7[7][7];
   } lw_;
-  void LinearWaveSetup(const std::vector<double> &pars);
+  void LinearWaveSetup(const std::vector<double> &pars, bool mhd_wave);
   void LinearWaveState(const BlockInfo &B, int k, int j, int i, double u[5]) const;
+  void LinearWaveMhdState(const BlockInfo &B, int k, int j, int i, double u[8]) const;
+  double LinearWaveMhdA(int c, double x1, double x2, double x3) const;
   Real new_dt_ = std::numeric_limits<Real>::max();
   struct Timing { double ms = 0.0; long long count = 0; };
   std::map<std::string, Timing> timing_;

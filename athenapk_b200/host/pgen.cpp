@@ -23,8 +23,93 @@ double hash01(std::uint64_t x) {  // splitmix64 -> [0,1)
 }
 }  // namespace
 
-// linear_wave.cpp:69-175 (InitUserMeshData) + :424-505 (hydro eigensystem, right vectors)
-void HydroSim::LinearWaveSetup(const std::vector<double> &pars) {
+namespace {
+// linear_wave_mhd.cpp:484-640: eigenvalues and RIGHT eigenvectors (columns) of adiabatic MHD in
+// (d, m1, m2, m3, E, b2, b3); x, y: Roe-averaging factors (0 and 1 for a single state)
+void MhdEigensystem(double gm1, double d, double v1, double v2, double v3, double h, double b1,
+                    double b2, double b3, double x, double y, double ev[7], double rem[7][7]) {
+  const double vsq = v1 * v1 + v2 * v2 + v3 * v3;
+  const double btsq = b2 * b2 + b3 * b3;
+  const double bt_starsq = (gm1 - (gm1 - 1.0) * y) * btsq;
+  const double vaxsq = b1 * b1 / d;
+  const double hp = h - (vaxsq + btsq / d);
+  const double twid_asq = std::max((gm1 * (hp - 0.5 * vsq) - (gm1 - 1.0) * x), 1.0e-20);
+  const double ct2 = bt_starsq / d;
+  const double tsum = vaxsq + ct2 + twid_asq;
+  const double tdif = vaxsq + ct2 - twid_asq;
+  const double cf2_cs2 = std::sqrt(tdif * tdif + 4.0 * twid_asq * ct2);
+  const double cfsq = 0.5 * (tsum + cf2_cs2);
+  const double cf = std::sqrt(cfsq);
+  const double cssq = twid_asq * vaxsq / cfsq;
+  const double cs = std::sqrt(cssq);
+  const double bt = std::sqrt(btsq);
+  const double bt_star = std::sqrt(bt_starsq);
+  double bet2 = 1.0, bet3 = 0.0;
+  if (bt != 0.0) {
+    bet2 = b2 / bt;
+    bet3 = b3 / bt;
+  }
+  const double bet2_star = bet2 / std::sqrt(gm1 - (gm1 - 1.0) * y);
+  const double bet3_star = bet3 / std::sqrt(gm1 - (gm1 - 1.0) * y);
+  const double bet_starsq = bet2_star * bet2_star + bet3_star * bet3_star;
+  const double vbet = v2 * bet2_star + v3 * bet3_star;
+  double alpha_f, alpha_s;
+  if ((cfsq - cssq) == 0.0) {
+    alpha_f = 1.0;
+    alpha_s = 0.0;
+  } else if ((twid_asq - cssq) <= 0.0) {
+    alpha_f = 0.0;
+    alpha_s = 1.0;
+  } else if ((cfsq - twid_asq) <= 0.0) {
+    alpha_f = 1.0;
+    alpha_s = 0.0;
+  } else {
+    alpha_f = std::sqrt((twid_asq - cssq) / (cfsq - cssq));
+    alpha_s = std::sqrt((cfsq - twid_asq) / (cfsq - cssq));
+  }
+  const double sqrtd = std::sqrt(d);
+  const double isqrtd = 1.0 / sqrtd;
+  const double sg = (b1 < 0.0) ? -1.0 : 1.0;
+  const double twid_a = std::sqrt(twid_asq);
+  const double qf = cf * alpha_f * sg;
+  const double qs = cs * alpha_s * sg;
+  const double af_prime = twid_a * alpha_f * isqrtd;
+  const double as_prime = twid_a * alpha_s * isqrtd;
+  const double afpbb = af_prime * bt_star * bet_starsq;
+  const double aspbb = as_prime * bt_star * bet_starsq;
+  const double vax = std::sqrt(vaxsq);
+  ev[0] = v1 - cf; ev[1] = v1 - vax; ev[2] = v1 - cs; ev[3] = v1;
+  ev[4] = v1 + cs; ev[5] = v1 + vax; ev[6] = v1 + cf;
+  rem[0][0] = alpha_f; rem[0][1] = 0.0; rem[0][2] = alpha_s; rem[0][3] = 1.0;
+  rem[0][4] = alpha_s; rem[0][5] = 0.0; rem[0][6] = alpha_f;
+  rem[1][0] = alpha_f * ev[0]; rem[1][1] = 0.0; rem[1][2] = alpha_s * ev[2]; rem[1][3] = v1;
+  rem[1][4] = alpha_s * ev[4]; rem[1][5] = 0.0; rem[1][6] = alpha_f * ev[6];
+  double qa = alpha_f * v2, qb = alpha_s * v2, qc = qs * bet2_star, qd = qf * bet2_star;
+  rem[2][0] = qa + qc; rem[2][1] = -bet3; rem[2][2] = qb - qd; rem[2][3] = v2;
+  rem[2][4] = qb + qd; rem[2][5] = bet3; rem[2][6] = qa - qc;
+  qa = alpha_f * v3; qb = alpha_s * v3; qc = qs * bet3_star; qd = qf * bet3_star;
+  rem[3][0] = qa + qc; rem[3][1] = bet2; rem[3][2] = qb - qd; rem[3][3] = v3;
+  rem[3][4] = qb + qd; rem[3][5] = -bet2; rem[3][6] = qa - qc;
+  rem[4][0] = alpha_f * (hp - v1 * cf) + qs * vbet + aspbb;
+  rem[4][1] = -(v2 * bet3 - v3 * bet2);
+  rem[4][2] = alpha_s * (hp - v1 * cs) - qf * vbet - afpbb;
+  rem[4][3] = 0.5 * vsq + (gm1 - 1.0) * x / gm1;
+  rem[4][4] = alpha_s * (hp + v1 * cs) + qf * vbet - afpbb;
+  rem[4][5] = -rem[4][1];
+  rem[4][6] = alpha_f * (hp + v1 * cf) - qs * vbet + aspbb;
+  rem[5][0] = as_prime * bet2_star; rem[5][1] = -bet3 * sg * isqrtd;
+  rem[5][2] = -af_prime * bet2_star; rem[5][3] = 0.0;
+  rem[5][4] = rem[5][2]; rem[5][5] = rem[5][1]; rem[5][6] = rem[5][0];
+  rem[6][0] = as_prime * bet3_star; rem[6][1] = bet2 * sg * isqrtd;
+  rem[6][2] = -af_prime * bet3_star; rem[6][3] = 0.0;
+  rem[6][4] = rem[6][2]; rem[6][5] = rem[6][1]; rem[6][6] = rem[6][0];
+}
+}  // namespace
+
+// linear_wave.cpp:69-175 (InitUserMeshData) + :424-505 (hydro eigensystem, right vectors);
+// mhd_wave: linear_wave_mhd.cpp:68-177
+void HydroSim::LinearWaveSetup(const std::vector<double> &pars, bool mhd_wave) {
+  lw_.mhd = mhd_wave;
   auto par = [&](size_t i, double def) { return pars.size() > i ? pars[i] : def; };
   lw_.wave_flag = (int)par(0, 0);
   lw_.amp = par(1, 1.0e-6);
@@ -54,8 +139,21 @@ void HydroSim::LinearWaveSetup(const std::vector<double> &pars) {
   lw_.u0 = lw_.vflow;
   const double v0 = 0.0, w0 = 0.0;
   lw_.p0 = 1.0 / gam;
-  const double h0 =
+  double h0 =
       ((lw_.p0 / lw_.gm1 + 0.5 * lw_.d0 * (lw_.u0 * lw_.u0 + v0 * v0 + w0 * w0)) + lw_.p0) / lw_.d0;
+  if (mhd_wave) {
+    lw_.bx0 = 1.0;
+    lw_.by0 = std::sqrt(2.0);
+    lw_.bz0 = 0.5;
+    h0 += (lw_.bx0 * lw_.bx0 + lw_.by0 * lw_.by0 + lw_.bz0 * lw_.bz0) / lw_.d0;
+    MhdEigensystem(lw_.gm1, lw_.d0, lw_.u0, v0, w0, h0, lw_.bx0, lw_.by0, lw_.bz0, 0.0, 1.0,
+                   lw_.ev7, lw_.rem7);
+    lw_.tlim_period = lambda / std::abs(lw_.ev7[lw_.wave_flag]) * 1.0;
+    lw_.dby = lw_.amp * lw_.rem7[5][lw_.wave_flag];  // linear_wave_mhd.cpp:392-393
+    lw_.dbz = lw_.amp * lw_.rem7[6][lw_.wave_flag];
+    lw_.set = true;
+    return;
+  }
   // eigensystem
   const double v1 = lw_.u0, v2 = v0, v3 = w0;
   const double vsq = v1 * v1 + v2 * v2 + v3 * v3;
@@ -89,14 +187,58 @@ void HydroSim::LinearWaveState(const BlockInfo &B, int k, int j, int i, double u
   u[IEN] = lw_.p0 / lw_.gm1 + 0.5 * lw_.d0 * lw_.u0 * lw_.u0 + amp * sn * lw_.rem[4][wf];
 }
 
+// analytic cell-centre state of the magnetised wave (d, m1..m3, E, b1..b3),
+// linear_wave_mhd.cpp:200-232
+void HydroSim::LinearWaveMhdState(const BlockInfo &B, int k, int j, int i, double u[8]) const {
+  const int wf = lw_.wave_flag;
+  const double amp = lw_.amp, cos_a2 = lw_.cos_a2, sin_a2 = lw_.sin_a2, cos_a3 = lw_.cos_a3,
+               sin_a3 = lw_.sin_a3;
+  const double x = cos_a2 * (xc(B, 0, i) * cos_a3 + xc(B, 1, j) * sin_a3) + xc(B, 2, k) * sin_a2;
+  const double sn = std::sin(lw_.k_par * x);
+  u[IDN] = lw_.d0 + amp * sn * lw_.rem7[0][wf];
+  const double mx = lw_.d0 * lw_.vflow + amp * sn * lw_.rem7[1][wf];
+  const double my = amp * sn * lw_.rem7[2][wf];
+  const double mz = amp * sn * lw_.rem7[3][wf];
+  u[IM1] = mx * cos_a2 * cos_a3 - my * sin_a3 - mz * sin_a2 * cos_a3;
+  u[IM2] = mx * cos_a2 * sin_a3 + my * cos_a3 - mz * sin_a2 * sin_a3;
+  u[IM3] = mx * sin_a2 + mz * cos_a2;
+  double e0 = lw_.p0 / lw_.gm1 + 0.5 * lw_.d0 * lw_.u0 * lw_.u0 + amp * sn * lw_.rem7[4][wf];
+  e0 += 0.5 * (lw_.bx0 * lw_.bx0 + lw_.by0 * lw_.by0 + lw_.bz0 * lw_.bz0);
+  u[IEN] = e0;
+  const double bx = lw_.bx0;
+  const double by = lw_.by0 + amp * sn * lw_.rem7[5][wf];
+  const double bz = lw_.bz0 + amp * sn * lw_.rem7[6][wf];
+  u[IB1] = bx * cos_a2 * cos_a3 - by * sin_a3 - bz * sin_a2 * cos_a3;
+  u[IB2] = bx * cos_a2 * sin_a3 + by * cos_a3 - bz * sin_a2 * sin_a3;
+  u[IB3] = bx * sin_a2 + bz * cos_a2;
+}
+
+// vector potential component c = 1, 2, 3 (linear_wave_mhd.cpp:441-480)
+double HydroSim::LinearWaveMhdA(int c, double x1, double x2, double x3) const {
+  const double cos_a2 = lw_.cos_a2, sin_a2 = lw_.sin_a2, cos_a3 = lw_.cos_a3, sin_a3 = lw_.sin_a3,
+               k_par = lw_.k_par;
+  const double x = x1 * cos_a2 * cos_a3 + x2 * cos_a2 * sin_a3 + x3 * sin_a2;
+  const double y = -x1 * sin_a3 + x2 * cos_a3;
+  const double Ay = lw_.bz0 * x - (lw_.dbz / k_par) * std::cos(k_par * (x));
+  const double Az = -lw_.by0 * x + (lw_.dby / k_par) * std::cos(k_par * (x)) + lw_.bx0 * y;
+  if (c == 1) return -Ay * sin_a3 - Az * sin_a2 * cos_a3;
+  if (c == 2) return Ay * cos_a3 - Az * sin_a2 * sin_a3;
+  return Az * cos_a2;
+}
+
 int HydroSim::ProblemGenerator(const std::string &id, const std::vector<double> &pars) {
   auto par = [&](size_t i, double def) { return pars.size() > i ? pars[i] : def; };
   const bool mhd = cfg_.fluid == APK_FLUID_GLMMHD;
   const double gm1 = cfg_.gamma - 1.0;
   const int is = cfg_.ng, js = (ndim_ >= 2) ? cfg_.ng : 0, ks = (ndim_ >= 3) ? cfg_.ng : 0;
   const size_t ncell = (size_t)n_[0] * n_[1] * n_[2];
-  if (id == "linear_wave") LinearWaveSetup(pars);
-  const bool known = id == "linear_wave" || id == "sod" || id == "orszag_tang" ||
+  if (id == "linear_wave") LinearWaveSetup(pars, false);
+  if (id == "linear_wave_mhd") {
+    if (!mhd || ndim_ != 3) return -2;
+    LinearWaveSetup(pars, true);
+  }
+  const bool known = id == "linear_wave" || id == "linear_wave_mhd" || id == "sod" ||
+                     id == "orszag_tang" ||
                      id == "uniform" || id == "ot3d" || id == "random" || id == "blast";
   if (!known) return -1;
   if (id == "orszag_tang" && !mhd) return -2;
@@ -113,6 +255,21 @@ int HydroSim::ProblemGenerator(const std::string &id, const std::vector<double> 
             double u[5];
             LinearWaveState(B, k, j, i, u);
             for (int n = 0; n < 5; ++n) U(n) = u[n];
+          } else if (id == "linear_wave_mhd") {  // linear_wave_mhd.cpp:373-430
+            double u[8];
+            LinearWaveMhdState(B, k, j, i, u);
+            for (int n = 0; n < 5; ++n) U(n) = u[n];
+            // cell-centred B = curl of the cell-centred vector potential, centred differences
+            const double X1 = xc(B, 0, i), X2 = xc(B, 1, j), X3 = xc(B, 2, k);
+            const double X1m = xc(B, 0, i - 1), X1p = xc(B, 0, i + 1);
+            const double X2m = xc(B, 1, j - 1), X2p = xc(B, 1, j + 1);
+            const double X3m = xc(B, 2, k - 1), X3p = xc(B, 2, k + 1);
+            U(IB1) = (LinearWaveMhdA(3, X1, X2p, X3) - LinearWaveMhdA(3, X1, X2m, X3)) / B.dx[1] / 2.0 -
+                     (LinearWaveMhdA(2, X1, X2, X3p) - LinearWaveMhdA(2, X1, X2, X3m)) / B.dx[2] / 2.0;
+            U(IB2) = (LinearWaveMhdA(1, X1, X2, X3p) - LinearWaveMhdA(1, X1, X2, X3m)) / B.dx[2] / 2.0 -
+                     (LinearWaveMhdA(3, X1p, X2, X3) - LinearWaveMhdA(3, X1m, X2, X3)) / B.dx[0] / 2.0;
+            U(IB3) = (LinearWaveMhdA(2, X1p, X2, X3) - LinearWaveMhdA(2, X1m, X2, X3)) / B.dx[0] / 2.0 -
+                     (LinearWaveMhdA(1, X1, X2p, X3) - LinearWaveMhdA(1, X1, X2m, X3)) / B.dx[1] / 2.0;
           } else if (id == "sod") {  // sod.cpp:23-50
             const double rho_l = par(0, 1.0), pres_l = par(1, 1.0), u_l = par(2, 0.0),
                          rho_r = par(3, 0.125), pres_r = par(4, 0.1), u_r = par(5, 0.0),
@@ -208,7 +365,9 @@ int HydroSim::ProblemGenerator(const std::string &id, const std::vector<double> 
 // per-variable L1 sums in out[1..5] are divided by the domain volume, out[0] = RMS (valid for
 // single-rank runs; multi-rank callers sum out[1..5] first).
 void HydroSim::LinearWaveErrors(double *out) {
-  double l1[5] = {0, 0, 0, 0, 0};
+  const int nerr = lw_.mhd ? 8 : 5;  // linear_wave_mhd.cpp:186: psi excluded
+  for (int n = 0; n < 9; ++n) out[n] = 0.0;
+  double l1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<double> host(BlockFieldElems());
   const int is = cfg_.ng, js = (ndim_ >= 2) ? cfg_.ng : 0, ks = (ndim_ >= 3) ? cfg_.ng : 0;
   const size_t ncell = (size_t)n_[0] * n_[1] * n_[2];
@@ -219,16 +378,17 @@ void HydroSim::LinearWaveErrors(double *out) {
     for (int k = ks; k < ks + cfg_.mb[2]; ++k)
       for (int j = js; j < js + cfg_.mb[1]; ++j)
         for (int i = is; i < is + cfg_.mb[0]; ++i) {
-          double u[5];
-          LinearWaveState(B, k, j, i, u);
+          double u[8];
+          if (lw_.mhd) LinearWaveMhdState(B, k, j, i, u);
+          else LinearWaveState(B, k, j, i, u);
           const size_t c = ((size_t)k * n_[1] + j) * n_[0] + i;
-          for (int n = 0; n < 5; ++n) l1[n] += std::abs(u[n] - host[(size_t)n * ncell + c]) * vol;
+          for (int n = 0; n < nerr; ++n) l1[n] += std::abs(u[n] - host[(size_t)n * ncell + c]) * vol;
         }
   }
   const double vol = (cfg_.xmax[0] - cfg_.xmin[0]) * (cfg_.xmax[1] - cfg_.xmin[1]) *
                      (cfg_.xmax[2] - cfg_.xmin[2]);
   double rms = 0.0;
-  for (int n = 0; n < 5; ++n) {
+  for (int n = 0; n < nerr; ++n) {
     l1[n] = l1[n] / vol;
     rms += SQR(l1[n]);
     out[1 + n] = l1[n];

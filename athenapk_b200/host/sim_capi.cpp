@@ -139,6 +139,7 @@ double apk_sim_dt(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->
 int apk_sim_ncycle(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->tm.ncycle; }
 double apk_sim_c_h(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->c_h; }
 long long apk_sim_fofc_corrections(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->fofc_corrections; }
+long long apk_sim_fofc_redone_stages(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->fofc_redone_stages; }
 int apk_sim_fused_active(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->FusedActive() ? 1 : 0; }
 int apk_sim_p2p_active(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->P2PActive() ? 1 : 0; }
 double apk_sim_linear_wave_period(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->LinearWavePeriod(); }

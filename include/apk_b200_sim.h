@@ -69,12 +69,16 @@ double apk_sim_dt(const apk_sim_t *s);
 int apk_sim_ncycle(const apk_sim_t *s);
 double apk_sim_c_h(const apk_sim_t *s);
 long long apk_sim_fofc_corrections(const apk_sim_t *s);
+/* fused stages whose FOFC acceptance test failed somewhere and that were redone with the
+ * flux-materialising tasks (0 for decks where FOFC never triggers) */
+long long apk_sim_fofc_redone_stages(const apk_sim_t *s);
 int apk_sim_fused_active(const apk_sim_t *s);
 /* 1 when the remote halo exchange runs as peer stores inside the stage kernel (CUDA IPC over
  * NVLink), 0 when it uses the packed ncclSend/ncclRecv path */
 int apk_sim_p2p_active(const apk_sim_t *s);
 double apk_sim_linear_wave_period(const apk_sim_t *s);
-int apk_sim_linear_wave_errors(apk_sim_t *s, double *out6);
+/* out9[0] = RMS-L1, out9[1..] = per-variable L1 errors (5, or 8 for linear_wave_mhd) */
+int apk_sim_linear_wave_errors(apk_sim_t *s, double *out9);
 void *apk_sim_stream(apk_sim_t *s);
 const void *apk_sim_pack_desc(const apk_sim_t *s);
 const void *apk_sim_device_blocks(const apk_sim_t *s);

@@ -935,6 +935,10 @@ struct apko_engine {
     double amp, vflow, sin_a2, cos_a2, sin_a3, cos_a3, lambda, k_par, d0, p0, u0, gam, gm1;
     double ev[5], rem[5][5];
     double tlim_period;
+    /* magnetised wave (linear_wave_mhd.cpp:40-48) */
+    int mhd;
+    double bx0, by0, bz0, dby, dbz;
+    double ev7[7], rem7[7][7];
   } lw;
 };
 
@@ -1595,10 +1599,97 @@ static void lw_eigensystem(double gm1, double d, double v1, double v2, double v3
   rem[0][4] = 1.0; rem[1][4] = v1 + a; rem[2][4] = v2; rem[3][4] = v3; rem[4][4] = h + v1 * a;
 }
 
+/* src/pgen/linear_wave_mhd.cpp:484-640: eigenvalues and RIGHT eigenvectors (columns) of adiabatic
+ * MHD in the conserved variables (d, m1, m2, m3, E, b2, b3); x, y are the Roe-averaging factors
+ * (0, 1 here) */
+static void lw_mhd_eigensystem(double gm1, double d, double v1, double v2, double v3, double h,
+                               double b1, double b2, double b3, double x, double y, double ev[7],
+                               double rem[7][7]) {
+  double vsq = v1 * v1 + v2 * v2 + v3 * v3;
+  double btsq = b2 * b2 + b3 * b3;
+  double bt_starsq = (gm1 - (gm1 - 1.0) * y) * btsq;
+  double vaxsq = b1 * b1 / d;
+  double hp = h - (vaxsq + btsq / d);
+  double twid_asq = smax((gm1 * (hp - 0.5 * vsq) - (gm1 - 1.0) * x), TINY_NUMBER);
+  double ct2 = bt_starsq / d;
+  double tsum = vaxsq + ct2 + twid_asq;
+  double tdif = vaxsq + ct2 - twid_asq;
+  double cf2_cs2 = sqrt(tdif * tdif + 4.0 * twid_asq * ct2);
+  double cfsq = 0.5 * (tsum + cf2_cs2);
+  double cf = sqrt(cfsq);
+  double cssq = twid_asq * vaxsq / cfsq;
+  double cs = sqrt(cssq);
+  double bt = sqrt(btsq);
+  double bt_star = sqrt(bt_starsq);
+  double bet2, bet3;
+  if (bt == 0.0) {
+    bet2 = 1.0;
+    bet3 = 0.0;
+  } else {
+    bet2 = b2 / bt;
+    bet3 = b3 / bt;
+  }
+  double bet2_star = bet2 / sqrt(gm1 - (gm1 - 1.0) * y);
+  double bet3_star = bet3 / sqrt(gm1 - (gm1 - 1.0) * y);
+  double bet_starsq = bet2_star * bet2_star + bet3_star * bet3_star;
+  double vbet = v2 * bet2_star + v3 * bet3_star;
+  double alpha_f, alpha_s;
+  if ((cfsq - cssq) == 0.0) {
+    alpha_f = 1.0;
+    alpha_s = 0.0;
+  } else if ((twid_asq - cssq) <= 0.0) {
+    alpha_f = 0.0;
+    alpha_s = 1.0;
+  } else if ((cfsq - twid_asq) <= 0.0) {
+    alpha_f = 1.0;
+    alpha_s = 0.0;
+  } else {
+    alpha_f = sqrt((twid_asq - cssq) / (cfsq - cssq));
+    alpha_s = sqrt((cfsq - twid_asq) / (cfsq - cssq));
+  }
+  double sqrtd = sqrt(d);
+  double isqrtd = 1.0 / sqrtd;
+  double sg = SIGN(b1);
+  double twid_a = sqrt(twid_asq);
+  double qf = cf * alpha_f * sg;
+  double qs = cs * alpha_s * sg;
+  double af_prime = twid_a * alpha_f * isqrtd;
+  double as_prime = twid_a * alpha_s * isqrtd;
+  double afpbb = af_prime * bt_star * bet_starsq;
+  double aspbb = as_prime * bt_star * bet_starsq;
+  double vax = sqrt(vaxsq);
+  ev[0] = v1 - cf; ev[1] = v1 - vax; ev[2] = v1 - cs; ev[3] = v1;
+  ev[4] = v1 + cs; ev[5] = v1 + vax; ev[6] = v1 + cf;
+  rem[0][0] = alpha_f; rem[0][1] = 0.0; rem[0][2] = alpha_s; rem[0][3] = 1.0;
+  rem[0][4] = alpha_s; rem[0][5] = 0.0; rem[0][6] = alpha_f;
+  rem[1][0] = alpha_f * ev[0]; rem[1][1] = 0.0; rem[1][2] = alpha_s * ev[2]; rem[1][3] = v1;
+  rem[1][4] = alpha_s * ev[4]; rem[1][5] = 0.0; rem[1][6] = alpha_f * ev[6];
+  double qa = alpha_f * v2, qb = alpha_s * v2, qc = qs * bet2_star, qd = qf * bet2_star;
+  rem[2][0] = qa + qc; rem[2][1] = -bet3; rem[2][2] = qb - qd; rem[2][3] = v2;
+  rem[2][4] = qb + qd; rem[2][5] = bet3; rem[2][6] = qa - qc;
+  qa = alpha_f * v3; qb = alpha_s * v3; qc = qs * bet3_star; qd = qf * bet3_star;
+  rem[3][0] = qa + qc; rem[3][1] = bet2; rem[3][2] = qb - qd; rem[3][3] = v3;
+  rem[3][4] = qb + qd; rem[3][5] = -bet2; rem[3][6] = qa - qc;
+  rem[4][0] = alpha_f * (hp - v1 * cf) + qs * vbet + aspbb;
+  rem[4][1] = -(v2 * bet3 - v3 * bet2);
+  rem[4][2] = alpha_s * (hp - v1 * cs) - qf * vbet - afpbb;
+  rem[4][3] = 0.5 * vsq + (gm1 - 1.0) * x / gm1;
+  rem[4][4] = alpha_s * (hp + v1 * cs) + qf * vbet - afpbb;
+  rem[4][5] = -rem[4][1];
+  rem[4][6] = alpha_f * (hp + v1 * cf) - qs * vbet + aspbb;
+  rem[5][0] = as_prime * bet2_star; rem[5][1] = -bet3 * sg * isqrtd;
+  rem[5][2] = -af_prime * bet2_star; rem[5][3] = 0.0;
+  rem[5][4] = rem[5][2]; rem[5][5] = rem[5][1]; rem[5][6] = rem[5][0];
+  rem[6][0] = as_prime * bet3_star; rem[6][1] = bet2 * sg * isqrtd;
+  rem[6][2] = -af_prime * bet3_star; rem[6][3] = 0.0;
+  rem[6][4] = rem[6][2]; rem[6][5] = rem[6][1]; rem[6][6] = rem[6][0];
+}
+
 /* src/pgen/linear_wave.cpp:69-175 (InitUserMeshData). pars = {wave_flag, amp, vflow,
  * ang_2, ang_3, ang_2_vert, ang_3_vert}; angles -999.9 => automatic */
-static void lw_setup(apko_engine *e, const double *pars, int npars) {
+static void lw_setup(apko_engine *e, const double *pars, int npars, int mhd_wave) {
   const apko_params *p = &e->p;
+  e->lw.mhd = mhd_wave;
   e->lw.wave_flag = (npars > 0) ? (int)pars[0] : 0;
   e->lw.amp = (npars > 1) ? pars[1] : 1.0e-6;
   e->lw.vflow = (npars > 2) ? pars[2] : 0.0;
@@ -1635,6 +1726,20 @@ static void lw_setup(apko_engine *e, const double *pars, int npars) {
   e->lw.p0 = 1.0 / e->lw.gam;
   double h0 = ((e->lw.p0 / e->lw.gm1 +
                 0.5 * e->lw.d0 * (e->lw.u0 * e->lw.u0 + v0 * v0 + w0 * w0)) + e->lw.p0) / e->lw.d0;
+  if (mhd_wave) { /* linear_wave_mhd.cpp:143-168 */
+    e->lw.bx0 = 1.0;
+    e->lw.by0 = sqrt(2.0);
+    e->lw.bz0 = 0.5;
+    h0 += (e->lw.bx0 * e->lw.bx0 + e->lw.by0 * e->lw.by0 + e->lw.bz0 * e->lw.bz0) / e->lw.d0;
+    lw_mhd_eigensystem(e->lw.gm1, e->lw.d0, e->lw.u0, v0, w0, h0, e->lw.bx0, e->lw.by0, e->lw.bz0,
+                       0.0, 1.0, e->lw.ev7, e->lw.rem7);
+    e->lw.tlim_period = lambda / fabs(e->lw.ev7[e->lw.wave_flag]) * 1.0;
+    /* wave amplitudes of the transverse field (linear_wave_mhd.cpp:392-393) */
+    e->lw.dby = e->lw.amp * e->lw.rem7[5][e->lw.wave_flag];
+    e->lw.dbz = e->lw.amp * e->lw.rem7[6][e->lw.wave_flag];
+    e->lw.set = 1;
+    return;
+  }
   lw_eigensystem(e->lw.gm1, e->lw.d0, e->lw.u0, v0, w0, h0, e->lw.ev, e->lw.rem);
   /* test=true: tlim counted in wave periods (linear_wave.cpp:166-174), tlim=1 */
   e->lw.tlim_period = lambda / fabs(e->lw.ev[e->lw.wave_flag]) * 1.0;
@@ -1658,6 +1763,47 @@ static void lw_state(const apko_engine *e, const block_t *B, int k, int j, int i
   u[IEN] = e->lw.p0 / e->lw.gm1 + 0.5 * e->lw.d0 * e->lw.u0 * e->lw.u0 + amp * sn * e->lw.rem[4][wf];
 }
 
+/* analytic state of the magnetised wave at a cell centre (d, m1..m3, E, b1..b3),
+ * linear_wave_mhd.cpp:200-232 (the reference measures the error against these) */
+static void lw_mhd_state(const apko_engine *e, const block_t *B, int k, int j, int i, double u[8]) {
+  const int wf = e->lw.wave_flag;
+  const double amp = e->lw.amp;
+  const double cos_a2 = e->lw.cos_a2, sin_a2 = e->lw.sin_a2, cos_a3 = e->lw.cos_a3,
+               sin_a3 = e->lw.sin_a3;
+  double x = cos_a2 * (xc(B, 0, i) * cos_a3 + xc(B, 1, j) * sin_a3) + xc(B, 2, k) * sin_a2;
+  double sn = sin(e->lw.k_par * x);
+  u[IDN] = e->lw.d0 + amp * sn * e->lw.rem7[0][wf];
+  double mx = e->lw.d0 * e->lw.vflow + amp * sn * e->lw.rem7[1][wf];
+  double my = amp * sn * e->lw.rem7[2][wf];
+  double mz = amp * sn * e->lw.rem7[3][wf];
+  u[IM1] = mx * cos_a2 * cos_a3 - my * sin_a3 - mz * sin_a2 * cos_a3;
+  u[IM2] = mx * cos_a2 * sin_a3 + my * cos_a3 - mz * sin_a2 * sin_a3;
+  u[IM3] = mx * sin_a2 + mz * cos_a2;
+  double e0 = e->lw.p0 / e->lw.gm1 + 0.5 * e->lw.d0 * e->lw.u0 * e->lw.u0 +
+              amp * sn * e->lw.rem7[4][wf];
+  e0 += 0.5 * (e->lw.bx0 * e->lw.bx0 + e->lw.by0 * e->lw.by0 + e->lw.bz0 * e->lw.bz0);
+  u[IEN] = e0;
+  double bx = e->lw.bx0;
+  double by = e->lw.by0 + amp * sn * e->lw.rem7[5][wf];
+  double bz = e->lw.bz0 + amp * sn * e->lw.rem7[6][wf];
+  u[5] = bx * cos_a2 * cos_a3 - by * sin_a3 - bz * sin_a2 * cos_a3;
+  u[6] = bx * cos_a2 * sin_a3 + by * cos_a3 - bz * sin_a2 * sin_a3;
+  u[7] = bx * sin_a2 + bz * cos_a2;
+}
+
+/* vector potential of the magnetised wave, linear_wave_mhd.cpp:441-480; c = 1, 2, 3 */
+static double lw_mhd_A(const apko_engine *e, int c, double x1, double x2, double x3) {
+  const double cos_a2 = e->lw.cos_a2, sin_a2 = e->lw.sin_a2, cos_a3 = e->lw.cos_a3,
+               sin_a3 = e->lw.sin_a3, k_par = e->lw.k_par;
+  double x = x1 * cos_a2 * cos_a3 + x2 * cos_a2 * sin_a3 + x3 * sin_a2;
+  double y = -x1 * sin_a3 + x2 * cos_a3;
+  double Ay = e->lw.bz0 * x - (e->lw.dbz / k_par) * cos(k_par * (x));
+  double Az = -e->lw.by0 * x + (e->lw.dby / k_par) * cos(k_par * (x)) + e->lw.bx0 * y;
+  if (c == 1) return -Ay * sin_a3 - Az * sin_a2 * cos_a3;
+  if (c == 2) return Ay * cos_a3 - Az * sin_a2 * sin_a3;
+  return Az * cos_a2;
+}
+
 /* deterministic hash -> [0,1) for APKO_PGEN_RANDOM (our own synthetic generator) */
 static double hash01(uint64_t x) {
   x += 0x9E3779B97F4A7C15ULL;
@@ -1671,7 +1817,11 @@ int apko_pgen(apko_engine *e, int id, const double *pars, int npars) {
   const apko_params *p = &e->p;
   const double gm1 = p->gamma - 1.0;
   const int mhd = (p->fluid == APKO_FLUID_GLMMHD);
-  if (id == APKO_PGEN_LINEAR_WAVE) lw_setup(e, pars, npars);
+  if (id == APKO_PGEN_LINEAR_WAVE) lw_setup(e, pars, npars, 0);
+  if (id == APKO_PGEN_LINEAR_WAVE_MHD) {
+    if (!mhd) return -1;
+    lw_setup(e, pars, npars, 1);
+  }
   for (int b = 0; b < e->nblocks; ++b) {
     block_t *B = &e->blk[b];
     memset(B->cons, 0, e->ncell * e->nvar * sizeof(double));
@@ -1684,6 +1834,22 @@ int apko_pgen(apko_engine *e, int id, const double *pars, int npars) {
             double u[5];
             lw_state(e, B, k, j, i, u);
             for (int n = 0; n < 5; ++n) U(n) = u[n];
+          } break;
+          case APKO_PGEN_LINEAR_WAVE_MHD: { /* linear_wave_mhd.cpp:373-430 (3-D meshes) */
+            double u[8];
+            lw_mhd_state(e, B, k, j, i, u);
+            for (int n = 0; n < 5; ++n) U(n) = u[n];
+            /* cell-centred B = curl of the cell-centred vector potential, centred differences */
+            const double X1 = xc(B, 0, i), X2 = xc(B, 1, j), X3 = xc(B, 2, k);
+            const double X1m = xc(B, 0, i - 1), X1p = xc(B, 0, i + 1);
+            const double X2m = xc(B, 1, j - 1), X2p = xc(B, 1, j + 1);
+            const double X3m = xc(B, 2, k - 1), X3p = xc(B, 2, k + 1);
+            U(5) = (lw_mhd_A(e, 3, X1, X2p, X3) - lw_mhd_A(e, 3, X1, X2m, X3)) / B->dx[1] / 2.0 -
+                   (lw_mhd_A(e, 2, X1, X2, X3p) - lw_mhd_A(e, 2, X1, X2, X3m)) / B->dx[2] / 2.0;
+            U(6) = (lw_mhd_A(e, 1, X1, X2, X3p) - lw_mhd_A(e, 1, X1, X2, X3m)) / B->dx[2] / 2.0 -
+                   (lw_mhd_A(e, 3, X1p, X2, X3) - lw_mhd_A(e, 3, X1m, X2, X3)) / B->dx[0] / 2.0;
+            U(7) = (lw_mhd_A(e, 2, X1p, X2, X3) - lw_mhd_A(e, 2, X1m, X2, X3)) / B->dx[0] / 2.0 -
+                   (lw_mhd_A(e, 1, X1, X2p, X3) - lw_mhd_A(e, 1, X1, X2m, X3)) / B->dx[1] / 2.0;
           } break;
           case APKO_PGEN_SOD: { /* src/pgen/sod.cpp:23-50; pars = rho_l,pres_l,u_l,rho_r,pres_r,u_r,x_discont */
             double rho_l = npars > 0 ? pars[0] : 1.0, pres_l = npars > 1 ? pars[1] : 1.0;
@@ -1793,6 +1959,30 @@ int apko_pgen(apko_engine *e, int id, const double *pars, int npars) {
 
 /* linear_wave::UserWorkAfterLoop, src/pgen/linear_wave.cpp:183-295 */
 void apko_linear_wave_errors(apko_engine *e, double *out) {
+  if (e->lw.mhd) { /* linear_wave_mhd.cpp:183-330: 8 variables (psi excluded); out[0..8] */
+    double l1m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < e->nblocks; ++b) {
+      const block_t *B = &e->blk[b];
+      const double vol = B->dx[0] * B->dx[1] * B->dx[2];
+      for (int k = e->is[2]; k <= e->ie[2]; ++k)
+        for (int j = e->is[1]; j <= e->ie[1]; ++j)
+          for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+            double u[8];
+            lw_mhd_state(e, B, k, j, i, u);
+            for (int n = 0; n < 8; ++n) l1m[n] += fabs(u[n] - B->cons[IDX(e, n, k, j, i)]) * vol;
+          }
+    }
+    const double volm = (e->p.xmax[0] - e->p.xmin[0]) * (e->p.xmax[1] - e->p.xmin[1]) *
+                        (e->p.xmax[2] - e->p.xmin[2]);
+    double rmsm = 0.0;
+    for (int n = 0; n < 8; ++n) {
+      l1m[n] = l1m[n] / volm;
+      rmsm += SQR(l1m[n]);
+      out[1 + n] = l1m[n];
+    }
+    out[0] = sqrt(rmsm);
+    return;
+  }
   double l1[5] = {0, 0, 0, 0, 0};
   for (int b = 0; b < e->nblocks; ++b) {
     const block_t *B = &e->blk[b];

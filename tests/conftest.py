@@ -18,6 +18,11 @@ def pytest_collection_modifyitems(config, items):
         has_gpu = torch.cuda.is_available()
     except Exception:
         has_gpu = False
+    if os.environ.get("APK_SLOW", "0") != "1":
+        slow = pytest.mark.skip(reason="long-running CPU oracle case (set APK_SLOW=1)")
+        for item in items:
+            if "slow" in item.keywords:
+                item.add_marker(slow)
     if has_gpu:
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")

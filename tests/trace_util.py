@@ -1,0 +1,70 @@
+"""Reference-run golden traces (tests/golden/reference_traces.json, produced by running the
+unmodified reference: tests/golden/make_reference_goldens.py) and the engine set-ups that reproduce
+each case with the CPU oracle (oracle_lib.Oracle) or the CUDA product (athenapk_b200.HydroSim)."""
+import json
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_traces.json")
+TRACES = json.load(open(GOLDEN))
+GAMMA_DECK = float("1.666666666666667")  # the decks' literal; differs from 5/3 in the last bit
+
+
+def lw_kwargs(case):
+    N = case["N"] if "N" in case else 16
+    return dict(nx=(2 * N, N, N), fluid=case.get("fluid", "glmmhd"),
+                integrator=case.get("integrator", "vl2"), recon=case.get("recon", "ppm"),
+                riemann=case.get("riemann", "hlld"), ng=case.get("ng", 3), gamma=GAMMA_DECK,
+                xmin=(0.0, 0.0, 0.0), xmax=(3.0, 1.5, 1.5), cfl=0.3)
+
+
+def lw_pgen(case):
+    return case.get("problem", "linear_wave_mhd"), [case.get("wave_flag", 0), 1e-6, 0.0]
+
+
+DECKS = {
+    "sod": (dict(nx=(256, 1, 1), mb=(64, 1, 1), ng=2,
+                 bc=["outflow", "outflow", "periodic", "periodic", "periodic", "periodic"],
+                 xmin=(0.0, -0.5, -0.5), xmax=(1.0, 0.5, 0.5), gamma=1.4, cfl=0.5, recon="plm",
+                 riemann="hllc", integrator="vl2"), "sod", [], 0.4),
+    "orszag_tang_50": (dict(fluid="glmmhd", nx=(256, 256, 1), mb=(64, 256, 1), ng=3,
+                            xmin=(-0.5,) * 3, xmax=(0.5,) * 3, gamma=GAMMA_DECK, cfl=0.4,
+                            recon="ppm", riemann="hlld", integrator="vl2", fofc=True),
+                       "orszag_tang", [], 1.0),
+    # FirstOrderFluxCorrect triggered: see make_reference_goldens.py
+    "blast_fofc": (dict(fluid="euler", nx=(64, 64, 1), mb=(32, 32, 1), ng=3, xmin=(-0.5,) * 3,
+                        xmax=(0.5,) * 3, gamma=GAMMA_DECK, cfl=0.9, recon="ppm", riemann="hllc",
+                        integrator="vl2", fofc=True, dfloor=1e-8, pfloor=1e-8),
+                   "blast", [0.1, 0.001, 1.6e8, 1.0], 0.1),
+    "uniform_mhd": (dict(fluid="glmmhd", nx=(64, 64, 64), mb=(32, 32, 32), ng=3,
+                         xmin=(0.0,) * 3, xmax=(1.0,) * 3, gamma=1.0001, cfl=0.3, recon="ppm",
+                         riemann="hlld", integrator="vl2"), "uniform", [], 1000.0),
+    "orszag_tang_3d": (dict(fluid="glmmhd", nx=(64, 64, 64), mb=(32, 32, 32), ng=3,
+                            xmin=(-0.5,) * 3, xmax=(0.5,) * 3, gamma=GAMMA_DECK, cfl=0.3,
+                            recon="ppm", riemann="hlld", integrator="vl2"),
+                       "orszag_tang", [], 1000.0),
+}
+
+
+def follow_trace(engine, trace, tlim, advance, every=1):
+    """advance(engine, tlim, ncycle) runs the engine up to cycle `ncycle`; compares (time, dt) with
+    the reference's printout at all 17 digits.  Returns the number of cycles compared."""
+    n = 0
+    for c, (t, dt) in enumerate(trace):
+        if c % every and c != len(trace) - 1:
+            continue
+        if c > 0:
+            advance(engine, tlim, c)
+        got = ("%.16e" % engine.time, "%.16e" % engine.dt)
+        assert got == (t, dt), "cycle %d: got %s, reference printed %s" % (c, got, (t, dt))
+        n += 1
+    return n
+
+
+def check_lw_row(engine, case):
+    """the row the reference appended to linearwave-errors.dat: Nx1 Nx2 Nx3 Ncycle RMS L1[...] ..."""
+    row = case["lw_row"]
+    nerr = 8 if case.get("problem", "linear_wave_mhd") == "linear_wave_mhd" else 5
+    e = engine.linear_wave_errors()
+    assert engine.ncycle == int(row[3])
+    got = ["%e" % x for x in e[:1 + nerr]]
+    assert got == row[4:5 + nerr], (got, row[4:5 + nerr])
