@@ -116,14 +116,18 @@ def workload(args):
     return kw
 
 
+REF_DECK = {"orszag_tang": "orszag_tang_3d", "uniform": "uniform_mhd"}
+
+
 def cpu_sample(cycles, n=64, mb=32):
-    """time the CPU oracle (port of the reference algorithm, single thread) on a bounded sample"""
+    """time the CPU oracle (C port of the reference algorithm, single thread) on a bounded sample --
+    only used when the reference binary did not travel (baseline/_ref/serial missing)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import Oracle
     o = Oracle(fluid="glmmhd", recon="ppm", riemann="hlld", integrator="vl2", nx=(n, n, n),
-               mb=(mb,) * 3, ng=3, xmin=(0.0, 0.0, 0.0), xmax=(1.0, 1.0, 1.0), gamma=5.0 / 3.0,
+               mb=(mb,) * 3, ng=3, xmin=(-0.5, -0.5, -0.5), xmax=(0.5, 0.5, 0.5), gamma=5.0 / 3.0,
                cfl=0.3)
-    o.pgen("ot3d")
+    o.pgen("orszag_tang")
     o.initialize()
     o.run(None, 1)  # warm-up cycle
     t0 = time.time()
@@ -136,45 +140,80 @@ def _cpu_worker(q, cycles):
     q.put(cpu_sample(cycles))
 
 
+def reference_serial(pgen, copies, cycles, skip, n=64, mb=32):
+    """The UNMODIFIED reference (Kokkos-Serial build, baseline/_ref/serial) on the product arm's
+    deck: `copies` independent runs pinned to cores 0..copies-1 (the Serial backend is single
+    threaded and there is no MPI in the image), each a bounded n^3 sample with the product arm's
+    meshblock size and method.  Returns (aggregate zone-cycles/s over the cycles after `skip`,
+    mean wall seconds per cycle) or None when the binary is not there."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import run_reference as rr
+    if pgen not in REF_DECK or not rr.available("serial"):
+        return None
+    agg, rates = rr.run_copies(REF_DECK[pgen], n, mb, skip + cycles, copies, skip)
+    if not agg:
+        return None
+    per_cycle = sum((n ** 3) / r for r in rates if r > 0) / max(1, sum(1 for r in rates if r > 0))
+    return agg, per_cycle
+
+
 def run_reference(args):
-    """Reference arm: the reference's CPU implementation of the path (oracle port of the
-    Kokkos-Serial code; the reference itself needs cmake+Kokkos to build), one
-    independent 64^3 (8 meshblocks of 32^3) replica per host core, aggregate zone-cycles/s."""
+    """Reference arm: the reference's own CPU implementation of the path -- the unmodified
+    reference binary (Kokkos Serial) on the same deck as the product arm, one copy per host core,
+    aggregate zone-cycles/s (= cell-updates/s).  One step = one cycle of every copy; the copies
+    run `warmup + steps` cycles on 64^3 (8 meshblocks of 32^3; the per-cell cost of the reference
+    does not depend on the mesh size) so the run ends within a minute."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
     cores = min(os.cpu_count() or 1, 64)
-    cycles = 2
-    vals = []
-    for step in range(args.warmup + args.steps):
-        q = mp.Queue()
-        ps = [mp.Process(target=_cpu_worker, args=(q, cycles)) for _ in range(cores)]
-        t0 = time.time()
-        for p in ps:
-            p.start()
-        for p in ps:
-            p.join()
-        wall = time.time() - t0
-        each = [q.get() for _ in ps]
-        agg = sum(each)
-        if step >= args.warmup:
-            vals.append((agg, wall))
-    value = sum(v for v, _ in vals) / len(vals)
-    ms = 1e3 * sum(w for _, w in vals) / len(vals)
-    sample = ("%d independent replicas (one per core) of 64^3 GLM-MHD VL2+PPM+HLLD, 8 meshblocks "
-              "of 32^3, %d timed cycles each; aggregate zone-cycles/s" % (cores, cycles))
+    ref = reference_serial(args.pgen, cores, args.steps, args.warmup) if args.config == "uni256" else None
+    if ref is not None:
+        value, sec = ref
+        kind = "reference"
+        sample = ("%d pinned copies (one per core) of baseline/_ref/serial/bin/athenaPK, deck "
+                  "baseline/decks/%s.in at 64^3 (8 meshblocks of 32^3), VL2+PPM+HLLD, %d cycles "
+                  "timed after %d warm-up cycles; aggregate of Parthenon's own zone-cycles/wsec" %
+                  (cores, REF_DECK[args.pgen], args.steps, args.warmup))
+    else:  # the binary did not travel: oracle port, one replica per core
+        import multiprocessing as mp
+        vals = []
+        for step in range(2):
+            q = mp.Queue()
+            ps = [mp.Process(target=_cpu_worker, args=(q, 2)) for _ in range(cores)]
+            t0 = time.time()
+            for p in ps:
+                p.start()
+            for p in ps:
+                p.join()
+            vals.append((sum(q.get() for _ in ps), time.time() - t0))
+        value, sec = vals[-1][0], vals[-1][1] / 3
+        kind = "port"
+        sample = ("%d replicas (one per core) of the oracle port on 64^3 orszag_tang, 2 timed "
+                  "cycles each (reference binary not present)" % cores)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "uniform 256^3 GLM-MHD ot3d, VL2+PPM+HLLD, meshblock 32^3 "
-                                   "(CPU arm: bounded 64^3 samples, per-cell cost is size independent)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "config": {"workload": workload_name(args, None),
+                       "sample": "bounded 64^3 samples of the same deck and method, one per core"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def workload_name(args, sim):
+    if args.config == "ot2d":
+        return ("Orszag-Tang %d^2 GLM-MHD (inputs/orszag_tang.in scaled up), VL2+%s+HLLD+FOFC, "
+                "meshblock %d^2, nghost 3, cfl 0.4" % (args.n, args.recon.upper(), args.mb))
+    what = {"orszag_tang": "Orszag-Tang vortex state (baseline/decks/orszag_tang_3d.in)",
+            "uniform": "static deck state (baseline/decks/uniform_mhd.in)",
+            "ot3d": "closed-form ot3d state", "random": "white noise"}[args.pgen]
+    return ("uniform-grid %d^3 GLM-MHD, turbulence.in geometry without forcing, %s, VL2+%s+HLLD, "
+            "meshblock %d^3, %d meshblocks, nghost 3, cfl 0.3" %
+            (args.n, what, args.recon.upper(), args.mb, (args.n // args.mb) ** 3))
 
 
 def run_product(args):
@@ -208,7 +247,7 @@ def run_product(args):
     pgen_pars = (3, 0.2) if args.pgen == "random" else ()
     sim.pgen(args.pgen, pgen_pars)
     sim.initialize()
-    cells = float(args.n) ** 3
+    cells = float(kw["nx"][0]) * kw["nx"][1] * kw["nx"][2]
     stream = torch.cuda.ExternalStream(sim.stream)
 
     # ---------------- device-resident throughput ("value") ----------------
@@ -247,14 +286,21 @@ def run_product(args):
         dur_ms = tt[dom][0] / tt[dom][1]
         bytes_launch = ALG_BYTES_STAGE.get(dom, 288.0) * local_cells
         achieved = bytes_launch / (dur_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": ("k_stage_fused<glmmhd,%s,hlld,3d> (stage 2)" % args.recon) if dom ==
-                "fused_stage_other" else dom, "achieved": achieved, "peak": peak,
+        ndim = 3 if kw["nx"][2] > 1 else 2
+        roof = {"bound": "hbm", "kernel": ("k_stage_fused<glmmhd,%s,hlld,%dd> (stage 2)" % (args.recon, ndim))
+                if dom == "fused_stage_other" else dom, "achieved": achieved, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "alg_bytes_per_launch": bytes_launch, "launch_ms": dur_ms}
-        tf = os.path.join(ROOT, "profiles", "traffic_r01.json")
-        if os.path.exists(tf):
+                "traffic": None, "traffic_source": None, "alg_bytes_per_launch": bytes_launch,
+                "launch_ms": dur_ms}
+        # ncu dram__bytes of ONE launch of this kernel: a static figure from profiles/ (ncu cannot
+        # run inside the timed bench); only valid for the configuration it was captured on
+        tf = os.path.join(ROOT, "profiles", "traffic_r02.json")
+        if (os.path.exists(tf) and world == 1 and args.config == "uni256" and args.n == 256 and
+                args.recon == "ppm" and dom == "fused_stage_other"):
             try:
-                roof["traffic"] = json.load(open(tf)).get("dram_bytes_per_launch_256")
+                tj = json.load(open(tf))
+                roof["traffic"] = tj.get("dram_bytes_per_launch_256")
+                roof["traffic_source"] = "static: " + tj.get("source", "profiles/traffic_r02.json")
             except Exception:
                 pass
     task_ms = {n: (v[0] / v[1] if v[1] else None) for n, v in tt.items() if v[1]}
@@ -279,18 +325,21 @@ def run_product(args):
             roof["fp64_dfma_peak_tflops_measured"] = best
         except Exception:
             pass
+        # FP64-pipe roofline: (FP64 instructions per cell of this kernel, a static ncu count) x
+        # cells per launch / live launch time, against the live DFMA issue rate of this GPU
+        tf = os.path.join(ROOT, "profiles", "traffic_r02.json")
         try:
-            import csv
-            rows = {r[0]: r[1:] for r in csv.reader(open(os.path.join(ROOT, "profiles",
-                                                                      "ncu_r01_final_256.csv")))}
-            roof["ncu_fp64_pipe_active_pct"] = float(
-                rows["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"][-1])
-            roof["ncu_issue_active_pct"] = float(
-                rows["smsp__issue_active.avg.pct_of_peak_sustained_active"][-1])
-            roof["note"] = ("HBM is the contract roofline; the kernel is limited by the half-rate "
-                            "FP64 pipe and FP64 dependency latency (ncu figures from profiles/)")
+            tj = json.load(open(tf))
+            per_cell = tj["fp64_thread_instr_per_cell"].get(dom if args.recon == "ppm" else "", None)
+            if per_cell and roof.get("fp64_dfma_peak_tflops_measured"):
+                rate = roof["fp64_dfma_peak_tflops_measured"] * 1e12 / 2.0  # DFMA = 2 flop
+                roof["fp64_frac"] = per_cell * local_cells / (dur_ms * 1e-3) / rate
+                roof["fp64_frac_source"] = ("live launch time and live DFMA rate; FP64 instructions "
+                                            "per cell static from " + tj.get("source", "profiles/"))
         except Exception:
             pass
+        roof["note"] = ("HBM is the contract roofline; the kernel is bound by FP64 issue and "
+                        "dependency latency (fp64_frac = share of the measured DFMA issue rate)")
 
     # ---------------- end-to-end through the public API with HOST buffers ----------------
     # Every step: pinned-host conserved state (ghosts included) -> H2D -> FillDerived (cons->prim)
@@ -359,7 +408,7 @@ def run_product(args):
         e2e = {"value": cells / (pipe_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(nel * 8 * world), "d2h_bytes_per_step": int(nel * 8 * world),
                "ms_per_step": pipe_ms, "serial_value": cells / (serial_ms * 1e-3),
-               "serial_ms_per_step": serial_ms,
+               "serial_ms_per_step": serial_ms, "serial_over_pipelined": pipe_ms / serial_ms,
                "what": "every step: pinned-host conserved state (interior cells, 72 B/cell) -> H2D -> "
                        "scatter + ghost exchange + FillDerived -> 1 full cycle -> gather -> D2H; "
                        "value = three contexts round robin (copies of neighbouring steps overlap compute), "
@@ -368,29 +417,93 @@ def run_product(args):
         for sx in sims[1:]:
             sx.close()
 
+    # ---------------- strict-FP throughput and a live parity check -------------------------------
+    # N = 1: a second context in APK_FP_STRICT mode (the bit-exact arm of the parity tests) runs the
+    #        same cycles: its throughput, and the relative difference of the history sums (mass,
+    #        momenta, KE, E, ME) between the FMA mode that was timed and the strict mode.
+    # N > 1: rank 0 repeats the same cycles on ONE GPU; the all-reduced history sums of the
+    #        partitioned run must agree with it to 1e-13 (the data path is bit-identical; only the
+    #        summation order of the reducers differs).
+    total_cycles = sim.ncycle
+    hist = torch.tensor(sim.history()[:7], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    hist = hist.cpu().numpy()
+    parity, strict = None, None
+    if rank == 0 and not args.no_parity and args.config == "uni256":
+        import numpy as np
+        chk = apk.HydroSim(fp_mode="strict" if world == 1 else args.fp_mode, fused=not args.unfused,
+                           **kw)
+        chk.pgen(args.pgen, pgen_pars)
+        chk.initialize()
+        chk.execute(None, args.warmup)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cstream = torch.cuda.ExternalStream(chk.stream)
+        c0.record(cstream)
+        chk.execute(None, total_cycles)
+        c1.record(cstream)
+        torch.cuda.synchronize()
+        ref_hist = np.array(chk.history()[:7])
+        scale = np.maximum(np.abs(ref_hist), np.abs(ref_hist[[0, 4, 4, 4, 4, 5, 6]]))
+        rel = float(np.max(np.abs(hist - ref_hist) / np.maximum(scale, 1e-300)))
+        if world == 1:
+            strict = {"value": cells * (total_cycles - args.warmup) / (c0.elapsed_time(c1) * 1e-3),
+                      "unit": UNIT, "fp_mode": "strict",
+                      "what": "same workload with the -fmad=false kernels (bit-identical to the "
+                              "reference's CPU build); %d cycles" % (total_cycles - args.warmup)}
+            parity = {"vs": "APK_FP_STRICT run of the same %d cycles (history sums mass, momenta, KE, "
+                            "E, ME)" % total_cycles, "max_rel_diff": rel, "tol": 1e-6, "ok": rel <= 1e-6}
+        else:
+            parity = {"vs": "single-GPU run of the same %d cycles on rank 0 (history sums, all-reduced)"
+                            % total_cycles, "max_rel_diff": rel, "tol": 1e-13, "ok": rel <= 1e-13}
+        chk.close()
+
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.config == "uni256":
             t0 = time.time()
-            v = cpu_sample(args.cpu_cycles)
-            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": "oracle (C port of the reference's Kokkos-Serial path), 64^3 GLM-MHD "
-                             "VL2+PPM+HLLD ot3d, 8 meshblocks of 32^3, %d timed cycles, 1 thread, "
-                             "%.1f s" % (args.cpu_cycles, time.time() - t0)}
+            ref = reference_serial(args.pgen, 1, args.cpu_cycles, 2)
+            if ref is not None:
+                cpu = {"value": ref[0], "unit": UNIT, "cores": 1, "kind": "reference",
+                       "sample": "baseline/_ref/serial/bin/athenaPK (unmodified reference, Kokkos "
+                                 "Serial), deck baseline/decks/%s.in at 64^3 (8 meshblocks of 32^3), "
+                                 "VL2+PPM+HLLD, %d cycles after 2 warm-up cycles, 1 core, %.1f s"
+                                 % (REF_DECK[args.pgen], args.cpu_cycles, time.time() - t0)}
+            else:
+                v = cpu_sample(args.cpu_cycles)
+                cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                       "sample": "oracle (C port of the reference's Kokkos-Serial path), 64^3 "
+                                 "orszag_tang, %d timed cycles, 1 thread, %.1f s (reference binary "
+                                 "not present or deck not runnable by it)"
+                                 % (args.cpu_cycles, time.time() - t0)}
+        halo = ("ipc-peer-store (CUDA-IPC mapped NVLink stores inside the stage kernel; NCCL: 4-byte "
+                "stage barrier + dt min)" if sim.p2p_active else
+                ("nccl-packed send/recv" if world > 1 else "same-device in-kernel push"))
+        static_ref = None
+        try:
+            rj = json.load(open(os.path.join(ROOT, "profiles", "reference_cuda_vs_b200_r02.json")))
+            key = REF_DECK.get(args.pgen)
+            if key in rj and args.config == "uni256" and args.n == 256:
+                static_ref = {"value": rj[key]["reference_cuda_zone_cycles_per_s"], "unit": UNIT,
+                              "source": "static: profiles/reference_cuda_vs_b200_r02.json -- the "
+                                        "unmodified reference's Kokkos-CUDA sm_100 build on one B200, "
+                                        "same deck, 256^3 (measured in round 2)"}
+        except Exception:
+            pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "uniform %d^3 GLM-MHD (%s), VL2+%s+HLLD, meshblock %d^3, "
-                                       "%d meshblocks, nghost 3, cfl 0.3" %
-                                       (args.n, args.pgen, args.recon.upper(), args.mb,
-                                        sim.nblocks_global),
-                           "fp_mode": args.fp_mode, "fused": sim.fused_active,
+                "config": {"workload": workload_name(args, sim), "pgen": args.pgen,
+                           "fp_mode": args.fp_mode, "fused": sim.fused_active, "halo": halo,
                            "l2": "state (%.1f GB/GPU) >> 126 MB L2; no flush needed" %
                                  (sim.nblocks * sim.nvar * sim.n[0] * sim.n[1] * sim.n[2] * 8 * 4 / 1e9),
                            "partition": "Morton-ordered meshblock list split in %d contiguous ranges" % world},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks, "task_ms": task_ms,
+                "strict": strict, "parity_check": parity, "reference_cuda": static_ref,
+                "fofc_redone_stages": int(sim.fofc_redone_stages),
                 "host_affinity": {"first_cpu_and_count": numa},
                 "p2p_halo": bool(sim.p2p_active),
                 "alg_bytes_per_cell_update": ALG_BYTES_PER_UPDATE,
@@ -409,7 +522,9 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--n", type=int, default=256, help="mesh cells per direction")
     ap.add_argument("--mb", type=int, default=32, help="meshblock cells per direction")
-    ap.add_argument("--pgen", default="ot3d", choices=["ot3d", "uniform", "random", "orszag_tang"])
+    ap.add_argument("--pgen", default="orszag_tang", choices=["orszag_tang", "uniform", "ot3d", "random"],
+                    help="orszag_tang (default) and uniform are decks the reference runs too "
+                         "(baseline/decks); ot3d / random are closed-form states of this repo")
     ap.add_argument("--config", default="uni256", choices=["uni256", "ot2d"],
                     help="uni256: BASELINE config 4 (headline); ot2d: config 3, 2-D Orszag-Tang + FOFC")
     ap.add_argument("--recon", default="ppm", choices=["ppm", "wenoz", "plm", "weno3", "limo3"],
@@ -418,6 +533,7 @@ def main():
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--cpu-cycles", type=int, default=12)
     args = ap.parse_args()
     if args.warmup < 3:
