@@ -150,20 +150,14 @@ HydroSim::~HydroSim() {
   cudaFree(d_status_);
   cudaFree(d_fofc_work_);
   cudaFree(d_undo_);
-  cudaFree(d_send_items_);
-  cudaFree(d_recv_items_);
-  for (void *m : peer_mapped_) cudaIpcCloseMemHandle(m);
+  apk_halo_plan_destroy(halo_plan_);
+  if (!peer_mapped_.empty()) apk_p2p_unmap(peer_mapped_.data(), (int)peer_mapped_.size());
   cudaFree(d_push_[0]);
   cudaFree(d_push_[1]);
   cudaFree(d_barrier_);
   cudaFree(d_stage_);
   cudaFree(d_hist_);
   cudaFree(d_int_items_);
-  cudaFree(d_sendbuf_);
-  cudaFree(d_recvbuf_);
-  if (comm_event_) cudaEventDestroy(reinterpret_cast<cudaEvent_t>(comm_event_));
-  if (packed_event_) cudaEventDestroy(reinterpret_cast<cudaEvent_t>(packed_event_));
-  if (comm_stream_) cudaStreamDestroy(S(comm_stream_));
   if (stream_) cudaStreamDestroy(S(stream_));
 }
 
@@ -443,13 +437,6 @@ void HydroSim::BuildHaloPlan() {
   }
   send_total_ = soff;
   recv_total_ = roff;
-  if (cfg_.plan_only) return;
-  cuda_check(cudaMalloc(&d_sendbuf_, std::max<long long>(soff, 1) * sizeof(double)), "sendbuf");
-  cuda_check(cudaMalloc(&d_recvbuf_, std::max<long long>(roff, 1) * sizeof(double)), "recvbuf");
-  cuda_check(cudaMalloc(&d_send_items_, std::max<size_t>(send_items_.size(), 1) * sizeof(apk_halo_item_t)), "items");
-  cuda_check(cudaMalloc(&d_recv_items_, std::max<size_t>(recv_items_.size(), 1) * sizeof(apk_halo_item_t)), "items");
-  cuda_check(cudaMemcpy(d_send_items_, send_items_.data(), send_items_.size() * sizeof(apk_halo_item_t), cudaMemcpyHostToDevice), "items");
-  cuda_check(cudaMemcpy(d_recv_items_, recv_items_.data(), recv_items_.size() * sizeof(apk_halo_item_t), cudaMemcpyHostToDevice), "items");
 }
 
 int HydroSim::CommUniqueId(void *out, int nbytes) {
@@ -468,6 +455,12 @@ int HydroSim::InitComm(const void *uid, int nbytes) {
   ncclComm_t c;
   if (ncclCommInitRank(&c, cfg_.nranks, id, cfg_.rank) != ncclSuccess) return -2;
   comm_ = reinterpret_cast<ncclComm *>(c);
+  // the exchange itself lives behind the C-ABI (apk_halo_*): hand it the slab lists
+  std::vector<apk_halo_peer_t> hp;
+  for (const Peer &p : peers_) hp.push_back({p.rank, p.send_off, p.send_cnt, p.recv_off, p.recv_cnt});
+  abi_check(apk_halo_plan_create(send_items_.data(), (int)send_items_.size(), recv_items_.data(),
+                                 (int)recv_items_.size(), hp.data(), (int)hp.size(), send_total_,
+                                 recv_total_, comm_, &halo_plan_), "apk_halo_plan_create");
   SetupPeerPush();
   return 0;
 }
@@ -500,61 +493,36 @@ bool HydroSim::PushTarget(int b, int idx, int *rank, int *local_index) const {
 void HydroSim::SetupPeerPush() {
   p2p_ = false;
   if (!fused_ || cfg_.plan_only || cfg_.nranks == 1) return;
-  ncclComm_t c = reinterpret_cast<ncclComm_t>(comm_);
-  cudaStream_t st = S(stream_);
   const int nr = cfg_.nranks;
   const char *env = std::getenv("APK_B200_P2P");
-  int ok = !(env && env[0] == '0');
-  struct Handles {
-    cudaIpcMemHandle_t h[3];
-  };
-  Handles mine{};
-  double *bufs[3] = {d_cons_, d_prim_[0], d_prim_[1]};
-  for (int f = 0; f < 3; ++f)
-    if (cudaIpcGetMemHandle(&mine.h[f], bufs[f]) != cudaSuccess) ok = 0;
-  cudaGetLastError();
-  std::vector<Handles> all(nr);
-  char *d_all = nullptr;
-  cuda_check(cudaMalloc(&d_all, sizeof(Handles) * nr), "ipc gather");
   cuda_check(cudaMalloc(&d_barrier_, 2 * sizeof(int)), "barrier word");
   cuda_check(cudaMemset(d_barrier_, 0, 2 * sizeof(int)), "barrier word");
-  cuda_check(cudaMemcpyAsync(d_all + sizeof(Handles) * cfg_.rank, &mine, sizeof(Handles),
-                             cudaMemcpyHostToDevice, st), "ipc handles");
-  ncclAllGather(d_all + sizeof(Handles) * cfg_.rank, d_all, sizeof(Handles), ncclChar, c, st);
-  cuda_check(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * nr, cudaMemcpyDeviceToHost, st),
-             "ipc handles");
-  cuda_check(cudaStreamSynchronize(st), "ipc handles");
-  cudaFree(d_all);
-
-  std::vector<std::array<double *, 3>> peer(nr, std::array<double *, 3>{nullptr, nullptr, nullptr});
-  for (size_t b = 0; b < blocks_.size() && ok; ++b)
-    for (int idx = 0; idx < 27 && ok; ++idx) {
+  // ranks whose cons / prim buffers this rank stores into
+  std::vector<int> need(nr, 0);
+  for (size_t b = 0; b < blocks_.size(); ++b)
+    for (int idx = 0; idx < 27; ++idx) {
       const int nb = h_blocks_[b].nbr[idx];
       if (nb >= 0 || nb == APK_NBR_NONE) continue;
       int r = 0, l = 0;
-      if (!PushTarget((int)b, idx, &r, &l) || peer[r][0]) continue;
-      for (int f = 0; f < 3; ++f) {
-        void *m = nullptr;
-        if (cudaIpcOpenMemHandle(&m, all[r].h[f], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-          ok = 0;
-          cudaGetLastError();
-          break;
-        }
-        peer_mapped_.push_back(m);
-        peer[r][f] = static_cast<double *>(m);
-      }
+      if (PushTarget((int)b, idx, &r, &l)) need[r] = 1;
     }
-  // all ranks must agree
-  cuda_check(cudaMemcpyAsync(d_barrier_ + 1, &ok, sizeof(int), cudaMemcpyHostToDevice, st), "p2p flag");
-  ncclAllReduce(d_barrier_ + 1, d_barrier_ + 1, 1, ncclInt, ncclMin, c, st);
+  void *bufs[3] = {d_cons_, d_prim_[0], d_prim_[1]};
+  peer_mapped_.assign((size_t)nr * 3, nullptr);
   int all_ok = 0;
-  cuda_check(cudaMemcpyAsync(&all_ok, d_barrier_ + 1, sizeof(int), cudaMemcpyDeviceToHost, st), "p2p flag");
-  cuda_check(cudaStreamSynchronize(st), "p2p flag");
+  if (env && env[0] == '0') {
+    // every rank reads the same environment: nobody maps, everybody keeps the packed path
+    all_ok = 0;
+  } else {
+    abi_check(apk_p2p_map_peers(comm_, cfg_.rank, nr, bufs, 3, need.data(), peer_mapped_.data(),
+                                &all_ok, stream_), "apk_p2p_map_peers");
+  }
   if (!all_ok) {
-    for (void *m : peer_mapped_) cudaIpcCloseMemHandle(m);
     peer_mapped_.clear();
     return;
   }
+  std::vector<std::array<double *, 3>> peer(nr, std::array<double *, 3>{nullptr, nullptr, nullptr});
+  for (int r = 0; r < nr; ++r)
+    for (int f = 0; f < 3; ++f) peer[r][f] = static_cast<double *>(peer_mapped_[(size_t)r * 3 + f]);
   const size_t per = BlockFieldElems(), nbl = blocks_.size();
   for (int which = 0; which < 2; ++which) {
     std::vector<apk_push_dst_t> tab(nbl * 27, apk_push_dst_t{nullptr, nullptr});
@@ -583,8 +551,7 @@ void HydroSim::SetupPeerPush() {
 // cross-rank barrier in stream order: every rank's stage kernel (and its peer stores) has
 // completed before any rank's next kernel on this stream starts
 void HydroSim::StageBarrier() {
-  ncclAllReduce(d_barrier_, d_barrier_, 1, ncclInt, ncclSum, reinterpret_cast<ncclComm_t>(comm_),
-                S(stream_));
+  abi_check(apk_stage_barrier(comm_, d_barrier_, stream_), "apk_stage_barrier");
 }
 
 double *HydroSim::DevicePtr(int field, int block) {
@@ -812,8 +779,7 @@ TaskStatus HydroSim::FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, b
 TaskStatus HydroSim::FusedFofcCheck(int stage, Real gam0, Real gam1, Real beta_dt, bool last_stage) {
   unsigned long long *d_count = reinterpret_cast<unsigned long long *>(d_scalars_ + 16);
   if (cfg_.nranks > 1)
-    ncclAllReduce(d_count, d_count, 1, ncclUint64, ncclSum, reinterpret_cast<ncclComm_t>(comm_),
-                  S(stream_));
+    abi_check(apk_allreduce_scalar(comm_, d_count, 1, stream_), "apk_allreduce_scalar");
   unsigned long long *h_count = reinterpret_cast<unsigned long long *>(h_scalars_ + 2);
   cuda_check(cudaMemcpyAsync(h_count, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                              S(stream_)), "fofc count D2H");
@@ -867,34 +833,10 @@ TaskStatus HydroSim::SendBoundBufs(int with_prim, bool local_done, bool need_bar
   if (cfg_.nranks > 1) {
     nccl_inflight_ = true;
     if (!comm_) throw std::runtime_error("apk_host: multi-rank run without InitComm");
-    // one pack launch for all peers, then one grouped send/recv per peer on the COMM stream so
-    // that the NVLink transfer overlaps the same-device ghost fill below
-    abi_check(apk_halo_pack(&desc_, d_blocks_[cur_], d_send_items_, (int)send_items_.size(),
-                            with_prim, d_sendbuf_, stream_), "apk_halo_pack");
-    if (!comm_event_) {
-      cudaEvent_t ev, ev2;
-      cudaStream_t cs;
-      cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
-      cuda_check(cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming), "event");
-      cuda_check(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "comm stream");
-      comm_event_ = ev;
-      packed_event_ = ev2;
-      comm_stream_ = cs;
-    }
-    cudaStream_t cs = S(comm_stream_);
-    cuda_check(cudaEventRecord(reinterpret_cast<cudaEvent_t>(packed_event_), S(stream_)), "record");
-    cuda_check(cudaStreamWaitEvent(cs, reinterpret_cast<cudaEvent_t>(packed_event_), 0), "wait");
-    ncclComm_t c = reinterpret_cast<ncclComm_t>(comm_);
-    // offsets/counts of the plan are sized for cons+prim; a single-field exchange packs densely
-    // at half of every offset (all slab sizes are even multiples), so only live bytes travel
-    const int div = (with_prim == 1) ? 1 : 2;
-    ncclGroupStart();
-    for (const Peer &p : peers_) {
-      ncclSend(d_sendbuf_ + p.send_off / div, (size_t)(p.send_cnt / div), ncclDouble, p.rank, c, cs);
-      ncclRecv(d_recvbuf_ + p.recv_off / div, (size_t)(p.recv_cnt / div), ncclDouble, p.rank, c, cs);
-    }
-    if (ncclGroupEnd() != ncclSuccess) return TaskStatus::fail;
-    cuda_check(cudaEventRecord(reinterpret_cast<cudaEvent_t>(comm_event_), cs), "record");
+    // one pack launch for all peers, then one grouped send/recv per peer on the plan's COMM stream
+    // so that the NVLink transfer overlaps the same-device ghost fill below
+    abi_check(apk_halo_start(halo_plan_, &desc_, d_blocks_[cur_], with_prim, stream_),
+              "apk_halo_start");
   }
   // same-device neighbours: direct ghost fill, no buffers (fused stages have already pushed
   // their boundary cells into the neighbours' ghost zones, APK_FUSED_PUSH_*)
@@ -905,19 +847,23 @@ TaskStatus HydroSim::SendBoundBufs(int with_prim, bool local_done, bool need_bar
 }
 
 TaskStatus HydroSim::ReceiveBoundBufs() {
-  // The reference polls MPI_Test and returns `incomplete` (boundary_communication.cpp:200-235).
-  // The NCCL transfer is stream-ordered, so the unpack can simply be enqueued behind it; the
-  // task therefore completes immediately (no host polling, no fence).
+  // The reference polls MPI_Test and returns `incomplete` (boundary_communication.cpp:200-235);
+  // apk_halo_test offers the same contract (event query).  The transfer is stream-ordered, so the
+  // unpack can simply be enqueued behind it: by default the task completes immediately (no host
+  // polling, no fence); APK_B200_POLL_HALO=1 exercises the polling contract instead.
+  static const char *poll = std::getenv("APK_B200_POLL_HALO");
+  if (poll && poll[0] == '1' && cfg_.nranks > 1 && nccl_inflight_) {
+    const int st = apk_halo_test(halo_plan_);
+    if (st == 1) return TaskStatus::incomplete;
+    if (st != 0) return TaskStatus::fail;
+  }
   return TaskStatus::complete;
 }
 
 TaskStatus HydroSim::SetBounds(int with_prim) {
-  if (cfg_.nranks > 1 && nccl_inflight_) {
-    cuda_check(cudaStreamWaitEvent(S(stream_), reinterpret_cast<cudaEvent_t>(comm_event_), 0),
-               "wait comm");
-    abi_check(apk_halo_unpack(&desc_, d_blocks_[cur_], d_recv_items_, (int)recv_items_.size(),
-                              with_prim, d_recvbuf_, stream_), "apk_halo_unpack");
-  }
+  if (cfg_.nranks > 1 && nccl_inflight_)
+    abi_check(apk_halo_finish(halo_plan_, &desc_, d_blocks_[cur_], with_prim, stream_),
+              "apk_halo_finish");
   recv_posted_ = false;
   return TaskStatus::complete;
 }
@@ -945,8 +891,7 @@ TaskStatus HydroSim::EstimateTimestep(bool have_device_min) {
     abi_check(apk_min_dt_async(&desc_, d_blocks_[cur_], d_scalars_, stream_), "apk_min_dt_async");
   if (cfg_.nranks > 1) {
     // replaces MPI_Allreduce(MIN) of driver.cpp:237 / hydro.cpp:127
-    ncclAllReduce(d_scalars_, d_scalars_, 1, ncclDouble, ncclMin,
-                  reinterpret_cast<ncclComm_t>(comm_), S(stream_));
+    abi_check(apk_allreduce_scalar(comm_, d_scalars_, 0, stream_), "apk_allreduce_scalar");
   }
   // pinned destinations: both copies are truly asynchronous, one synchronisation per cycle
   int *h_status = reinterpret_cast<int *>(h_scalars_ + 1);

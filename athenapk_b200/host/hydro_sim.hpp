@@ -219,11 +219,9 @@ class HydroSim {
   };
   std::vector<Peer> peers_;
   std::vector<apk_halo_item_t> send_items_, recv_items_;
-  apk_halo_item_t *d_send_items_ = nullptr, *d_recv_items_ = nullptr;
-  double *d_sendbuf_ = nullptr, *d_recvbuf_ = nullptr;
   long long send_total_ = 0, recv_total_ = 0;
   ncclComm *comm_ = nullptr;
-  void *comm_event_ = nullptr, *packed_event_ = nullptr, *comm_stream_ = nullptr;
+  apk_halo_plan_t *halo_plan_ = nullptr;  // buffers, comm stream and events live behind the C-ABI
   bool recv_posted_ = false;
   // peer-to-peer ghost push (fused stages, nranks > 1): the stage kernel stores boundary cells
   // straight into the neighbour GPU's ghost zones through CUDA-IPC mapped pointers

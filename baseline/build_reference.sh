@@ -21,6 +21,12 @@ if [[ $WHAT == serial || $WHAT == all ]]; then
   make -C "$BT/serial" -j"$JOBS" athenaPK > "$BT/serial.build.log" 2>&1
   mkdir -p "$OUT/serial/bin"
   cp "$BT/serial/bin/athenaPK" "$OUT/serial/bin/athenaPK"
+  # generated config headers (KokkosCore_config.h, parthenon config.hpp): what a syntax check of
+  # integration/apk_b200_shim.cpp against the reference's headers needs (tests/test_integration_shim.py)
+  mkdir -p "$OUT/serial/generated/kokkos/desul/atomics"
+  cp -r "$BT/serial/parthenon/src/generated" "$OUT/serial/generated/parthenon"
+  cp "$BT"/serial/parthenon/Kokkos/*.h* "$OUT/serial/generated/kokkos/"
+  cp "$BT/serial/parthenon/Kokkos/core/src/desul/atomics/Config.hpp" "$OUT/serial/generated/kokkos/desul/atomics/"
   echo "serial: $(ls -la "$OUT/serial/bin/athenaPK")"
 fi
 if [[ $WHAT == cuda || $WHAT == all ]]; then

@@ -162,6 +162,55 @@ int apk_halo_unpack(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
                     const apk_halo_item_t *d_items, int nitems, int with_prim,
                     const double *d_buf, void *stream);
 
+/* ---- the multi-rank exchange as three calls that map 1:1 onto the tasks of
+ * parthenon::AddBoundaryExchangeTasks (bvals/comms/boundary_communication.cpp:405-445):
+ *   apk_halo_start  = StartReceiveBoundBufs + SendBoundBufs (:48-140,:178-199): one pack launch for
+ *                     the slabs of ALL peers, then one grouped ncclSend/ncclRecv pair per peer on the
+ *                     plan's own communication stream (so the transfer overlaps whatever the caller
+ *                     enqueues next on `stream`, e.g. the same-device ghost fill);
+ *   apk_halo_test   = ReceiveBoundBufs (:201-235): 0 = complete, 1 = incomplete (cudaEventQuery of
+ *                     the transfer) -- the polling contract of the reference's task (TaskStatus::
+ *                     incomplete re-enqueues the task); a caller may skip it, apk_halo_finish orders
+ *                     the unpack behind the transfer on the device anyway;
+ *   apk_halo_finish = SetBounds (:273-348): stream-wait on the transfer, one unpack launch.
+ * The plan owns the send/receive buffers, the device copies of the slab lists, the communication
+ * stream and its events; it does not own the communicator.  Slab lists are host arrays; both sides
+ * must order the slabs of a pair of ranks identically (HydroSim: by receiver gid and offset index,
+ * what bnd_info.cpp:105-230 derives per buffer).  Offsets / counts are in doubles, sized for
+ * cons+prim (2*nvar values per cell); single-field exchanges use half of every offset. */
+typedef struct apk_halo_peer {
+  int rank;                          /* NCCL rank of the peer                         */
+  long long send_off, send_cnt;      /* segment of the send buffer for this peer      */
+  long long recv_off, recv_cnt;      /* segment of the receive buffer from this peer  */
+} apk_halo_peer_t;
+typedef struct apk_halo_plan apk_halo_plan_t;
+int apk_halo_plan_create(const apk_halo_item_t *h_send_items, int nsend,
+                         const apk_halo_item_t *h_recv_items, int nrecv,
+                         const apk_halo_peer_t *h_peers, int npeers, long long send_total,
+                         long long recv_total, void *nccl_comm, apk_halo_plan_t **out);
+void apk_halo_plan_destroy(apk_halo_plan_t *plan);
+int apk_halo_start(apk_halo_plan_t *plan, const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                   int with_prim, void *stream);
+int apk_halo_test(apk_halo_plan_t *plan);
+int apk_halo_finish(apk_halo_plan_t *plan, const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                    int with_prim, void *stream);
+
+/* ---- peer-to-peer set-up for apk_stage_fused_p2p: every rank publishes `nbufs` device
+ * allocations (cudaIpcGetMemHandle), the handles are all-gathered over the NCCL communicator and the
+ * buffers of the ranks flagged in h_need[nranks] are mapped (cudaIpcOpenMemHandle).
+ * h_mapped[r * nbufs + f] receives rank r's buffer f as a pointer valid on THIS device (NULL for
+ * ranks not needed / this rank).  *all_ok = 1 only when EVERY rank mapped everything it needs
+ * (agreed with an all-reduce), otherwise nothing stays mapped and the caller uses apk_halo_*.
+ * apk_stage_barrier: stream-ordered cross-rank barrier (4-byte all-reduce) that separates two fused
+ * stages: all peer stores of stage s have landed before any rank starts stage s+1. */
+int apk_p2p_map_peers(void *nccl_comm, int rank, int nranks, void *const *h_local_bufs, int nbufs,
+                      const int *h_need, void **h_mapped, int *all_ok, void *stream);
+int apk_p2p_unmap(void **h_mapped, int n);
+int apk_stage_barrier(void *nccl_comm, int *d_word, void *stream);
+/* min / sum all-reduce of one device value (replaces MPI_Allreduce of driver.cpp:237,
+ * hydro.cpp:127): op 0 = min of a double, 1 = sum of an unsigned 64-bit count */
+int apk_allreduce_scalar(void *nccl_comm, void *d_value, int op, void *stream);
+
 /* ---- fused stage: calc_flux -> flux divergence update -> Dedner source -> cons->prim of the
  * interior cells (+ optional dt reduction on the last stage) without materialising fluxes
  * (K1-K3+K6+K7+K10(+K11) of SURVEY.md 2.3).  Legal only when nothing else consumes cons.flux
