@@ -78,7 +78,8 @@ class Block(C.Structure):
 ABI_SYMBOLS = [
     "apk_last_error", "apk_abi_version", "apk_stage_fused_ex", "apk_halo_plan_create",
     "apk_halo_plan_destroy", "apk_halo_start", "apk_halo_test", "apk_halo_finish", "apk_p2p_map_peers",
-    "apk_p2p_unmap", "apk_stage_barrier", "apk_allreduce_scalar", "apk_launch_count", "apk_reset_launch_count",
+    "apk_p2p_unmap", "apk_stage_barrier", "apk_allreduce_scalar", "apk_tma_maps_create",
+    "apk_tma_maps_destroy", "apk_launch_count", "apk_reset_launch_count",
     "apk_calc_fluxes", "apk_fofc_workspace_bytes", "apk_first_order_flux_correct",
     "apk_flux_div_update", "apk_dedner_source", "apk_cons_to_prim", "apk_min_dt",
     "apk_min_dt_async", "apk_fill_ghosts_local", "apk_apply_physical_bcs",

@@ -5,6 +5,10 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cuda.h>
+
+#include <vector>
+
 #include "apk_launch.h"
 
 namespace {
@@ -181,7 +185,13 @@ int apk_stage_fused_ex(const apk_pack_desc_t *d, const apk_block_t *blocks,
   // dedner_source.cpp:34 (host std::exp, like the reference)
   const double coeff =
       (d->fluid == APK_FLUID_GLMMHD) ? std::exp(-a->alpha * a->c_h * a->beta_dt / a->mindx) : 1.0;
-  int rc = DISPATCH(d, launch_stage_fused(*d, blocks, d_prim_out, *a, coeff, S(stream)));
+  int rc;
+  const int recon = (a->recon_override < 0) ? d->recon : a->recon_override;
+  if (a->d_tma_maps && d->fp_mode == APK_FP_FAST && d->ndim == 3 && d->fluid == APK_FLUID_GLMMHD &&
+      d->riemann == APK_RIEMANN_HLLD && recon == APK_RECON_PPM && d->nscalars == 0)
+    rc = apk_fast_tma::launch_stage_fused(*d, blocks, d_prim_out, *a, coeff, S(stream));
+  else
+    rc = DISPATCH(d, launch_stage_fused(*d, blocks, d_prim_out, *a, coeff, S(stream)));
   return rc ? rc : cuda_ok("apk_stage_fused");
 }
 
@@ -211,6 +221,58 @@ int apk_stage_fused(const apk_pack_desc_t *d, const apk_block_t *blocks,
   return apk_stage_fused_p2p(d, blocks, d_prim_out, nullptr, gam0, gam1, beta_dt, c_h, mindx, alpha,
                              recon_override, flags, d_dtmin, stream);
 }
+
+// ---- TMA tensor maps (driver entry point fetched at run time: no link dependency on libcuda)
+int apk_tma_maps_create(const apk_pack_desc_t *d, const apk_block_t *h_blocks, void **d_maps) {
+  if (!d || !h_blocks || !d_maps) {
+    apk_common::set_error("apk_tma_maps_create: null argument");
+    return 1;
+  }
+  const ApkGeom g = apk_make_geom(*d);
+  if (g.ndim != 3 || (g.n1 % 2) != 0) {
+    apk_common::set_error("apk_tma_maps_create: needs a 3-D pack with an even n1 (16 B strides)");
+    return 1;
+  }
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !fn) {
+    apk_common::set_error("apk_tma_maps_create: cuTensorMapEncodeTiled not available");
+    return 2;
+  }
+  const int nh = g.nhydro;
+  std::vector<CUtensorMap> maps(d->nblocks);
+  const cuuint64_t dims[4] = {(cuuint64_t)g.n1, (cuuint64_t)g.n2, (cuuint64_t)g.n3, (cuuint64_t)nh};
+  const cuuint64_t strides[3] = {(cuuint64_t)g.n1 * 8, (cuuint64_t)g.n1 * g.n2 * 8,
+                                 (cuuint64_t)g.ncell * 8};
+  const cuuint32_t box[4] = {APK_TMA_TX + 6, APK_TMA_TY + 6, 1, (cuuint32_t)nh};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int b = 0; b < d->nblocks; ++b) {
+    CUresult r = reinterpret_cast<encode_fn>(fn)(
+        &maps[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, h_blocks[b].prim, dims, strides, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      static thread_local char buf[128];
+      snprintf(buf, sizeof(buf), "apk_tma_maps_create: cuTensorMapEncodeTiled failed (%d)", (int)r);
+      apk_common::set_error(buf);
+      return 2;
+    }
+  }
+  void *dm = nullptr;
+  if (cudaMalloc(&dm, maps.size() * sizeof(CUtensorMap)) != cudaSuccess ||
+      cudaMemcpy(dm, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice) !=
+          cudaSuccess)
+    return cuda_ok("apk_tma_maps_create") ? 2 : 2;
+  *d_maps = dm;
+  return 0;
+}
+
+void apk_tma_maps_destroy(void *d_maps) { cudaFree(d_maps); }
 
 int apk_restrict_average(int ndim, int ng, int nvar, int element, const apk_amr_item_t *d_items,
                          int nitems, int fp_mode, void *stream) {

@@ -54,6 +54,17 @@ namespace {
 #ifndef APK_FUSED_TY
 #define APK_FUSED_TY 4
 #endif
+// APK_FUSED_TMA=1 (A/B variant, namespace apk_fast_tma, selected with APK_B200_FUSED_V=3): the halo'd
+// prim tile of the plane being swept -- (TX+6) x (TY+6) cells x all variables -- is staged in
+// shared memory by ONE cp.async.bulk.tensor (TMA, 4-D tensor map over [var][k][j][i]) per plane,
+// issued by one thread when the previous recon phase has released the buffer and awaited on an
+// mbarrier; the x1 / x2 reconstructions then read their stencils from shared memory with
+// compile-time strides (no per-lane global address arithmetic, no L2 round trips).  The x3
+// stencils keep their global loads (a 5-plane ring does not fit).  The tile costs 27 KB, so only
+// two CTAs fit per SM: the variant is built with 6 warps per CTA.
+#ifndef APK_FUSED_TMA
+#define APK_FUSED_TMA 0
+#endif
 constexpr int TX = 32, TY = APK_FUSED_TY, NWARPS = APK_FUSED_NWARPS, NTHREADS = NWARPS * 32;
 static_assert(NTHREADS >= TX * TY, "finalize phase needs one thread per tile cell");
 
@@ -80,6 +91,10 @@ struct Smem {
   double wly[NH][TY + 1][TX], wry[NR][RY + 1][RX];
   double wrz[NR][RY][RX], wlz[ZB][NH][TY][TX];
   double pl[NP][NPV][TY + 2][TX + 2];  // DC: prim planes, cells -1..TX x rows -1..TY
+  // TMA variant: halo'd prim tile of the current plane, cells -3..TX+2 x rows -3..TY+2
+  static constexpr bool TMA = APK_FUSED_TMA && !DC && NDIM == 3;
+  alignas(128) double tile[TMA ? NH : 1][TMA ? TY + 6 : 1][TMA ? TX + 6 : 2];
+  alignas(8) unsigned long long tma_bar;
   alignas(16) ReconTask tab[(!DC && NT > 0) ? NT : 1];
   double *push_prim[27], *push_cons[27];  // ghost-push destinations per neighbour offset (or null)
 };
@@ -90,11 +105,13 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
               double g0, double g1, double bdt, RsPars rsp, double dedner_coeff,
               EosPars eos, int ntx, int flags, unsigned long long *dtmin,
               const apk_push_dst_t *__restrict__ push, int nchunk, int *status,
-              unsigned long long *fofc_count) {
+              unsigned long long *fofc_count, const unsigned char *__restrict__ tmaps) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool DC = (RECON == APK_RECON_DC);
   using SmemT = Smem<NH, NDIM, DC>;
+  constexpr bool TMA = SmemT::TMA;
+  constexpr int TW = TX + 6, TILE_V = (TY + 6) * TW;  // tile row / variable strides (elements)
   SmemT &sm = *reinterpret_cast<SmemT *>(smem_raw);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,6 +174,10 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       e.goff = var_of_slot(n, dir) * (int)g.ncell + rc * (int)sj;
       e.stride = (dir == 0 ? 1 : (dir == 1 ? (int)sj : (int)sk)) | (dir << 28) |
                  ((n == 0 || n == 4) ? (1 << 30) : 0);
+      if (TMA && dir != 2) {  // x1 / x2 stencils come from the staged tile
+        e.goff = var_of_slot(n, dir) * TILE_V + (rc + 3) * TW + 3;
+        e.stride = (dir == 0 ? 1 : TW) | (dir << 28) | ((n == 0 || n == 4) ? (1 << 30) : 0);
+      }
       e.sl = e.sr = -1;
       if (rok) {
         if (dir == 2) {
@@ -194,6 +215,45 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   }
   const int lc = min(lane, txe - 1);
   const bool lane_ok = lane < txe;
+  // ---- TMA staging of the halo'd prim tile (one bulk tensor copy per plane) ----
+  [[maybe_unused]] unsigned tma_phase = 0;
+  [[maybe_unused]] const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(&sm.tma_bar);
+  [[maybe_unused]] auto tma_issue = [&](int k) {
+    if constexpr (TMA) {
+      if (threadIdx.x == 0) {
+        constexpr unsigned BYTES = NH * TILE_V * sizeof(double);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.tile[0][0][0]);
+        const unsigned long long map = (unsigned long long)(tmaps + (size_t)blockIdx.y * 128);
+        // the generic-proxy reads of the previous plane are ordered before the async-proxy write
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                     "r"(BYTES) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], "
+            "[%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst), "l"(map), "r"(i0 - 3), "r"(j0 - 3), "r"(k),
+            "r"(0), "r"(bar_addr) : "memory");
+      }
+    }
+  };
+  [[maybe_unused]] auto tma_wait = [&]() {
+    if constexpr (TMA) {
+      unsigned done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_addr), "r"(tma_phase) : "memory");
+      }
+      tma_phase ^= 1;
+    }
+  };
+  if constexpr (TMA) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    tma_issue(kbeg);  // the first in-plane iteration's tile
+  }
   // DC: asynchronous copy (cp.async, 8 B granules: always aligned) of one halo'd prim plane into
   // the staging ring; indices beyond the tile are clamped to valid cells and never used.  The
   // plane needed by iteration k+1 is requested at the start of iteration k and has the whole
@@ -231,6 +291,8 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       const int t_end = inplane ? NT : NZ;
       const long plane = (long)kp * sk + (long)j0 * sj + i0;
       const double *__restrict__ pbase = prim + plane + lc;
+      [[maybe_unused]] const double *tile = &sm.tile[0][0][0] + lc;
+      if (TMA && inplane) tma_wait();  // the tile of plane kp has landed
       const int zoff = (cur ^ 1) * ZBUF;
       // Software pipeline over batches of UNROLL tasks: the stencil loads of batch b+1 are in
       // flight while batch b is evaluated (two register buffers A/B, loop unrolled by two so no
@@ -252,7 +314,12 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           b.sl[u] = (ok && e.z >= 0) ? e.z + (tr < NZ ? zoff : 0) : -1;
           b.sr[u] = ok ? e.w : -1;
           b.st[u] = e.y;
-          load_stencil<RECON>(pbase + e.x, e.y & 0x0fffffff, b.v[u]);
+          if constexpr (TMA) {
+            if (tr < NZ) load_stencil<RECON>(pbase + e.x, e.y & 0x0fffffff, b.v[u]);
+            else load_stencil<RECON>(tile + e.x, e.y & 0x0fffffff, b.v[u]);
+          } else {
+            load_stencil<RECON>(pbase + e.x, e.y & 0x0fffffff, b.v[u]);
+          }
         }
       };
       auto evaluate = [&](const Batch &b) {
@@ -302,6 +369,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           if (j < tye) {
             const int c = side ? txe : -1;
             const double *q = prim + (long)var_of_slot(n, 0) * g.ncell + plane + (long)j * sj + c;
+            if constexpr (TMA) q = &sm.tile[var_of_slot(n, 0)][j + 3][c + 3];
             double ql, qr;
             recon_cell<RECON>(q, 1, dx1, (n == 0 || n == 4), ql, qr);
             if (side) sm.wrx[n][j][txe] = qr;
@@ -311,6 +379,11 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       }
     }
     if constexpr (RECON != APK_RECON_DC) __syncthreads();
+    if constexpr (TMA) {
+      // every warp has finished reading the tile of plane kp: refill it for the next swept plane
+      // while the Riemann and finalize phases run
+      if (kp + 1 >= kbeg && kp + 1 <= kend && kp >= kbeg) tma_issue(kp + 1);
+    }
     // ------------------------------------------------------------------ riemann phase
     if constexpr (RECON != APK_RECON_DC && APK_FUSED_PREFETCH) {
       // The Riemann phase touches no global memory: use it to pull everything the NEXT recon phase
@@ -323,7 +396,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       if (pn <= klast) {
         const bool next_in = (pn >= kbeg && pn <= kend);
         const int nzr = (NDIM == 3) ? tye : 0;                // rows of plane pn+R (x3 stencil top)
-        const int nyr = next_in ? (NDIM >= 2 ? tye + 2 + 2 * R : 1) : 0;  // rows of plane pn
+        const int nyr = (next_in && !TMA) ? (NDIM >= 2 ? tye + 2 + 2 * R : 1) : 0;  // rows of plane pn
         const int ylo = (NDIM >= 2) ? -1 - R : 0;
         const int nrow = nzr + nyr;
         const int lo = -(1 + R), hi = txe + R;                // cell range along x1 (inclusive)
@@ -617,7 +690,8 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
     }                                                                                            \
     kern<<<grid, NTHREADS, smem, s>>>(g, blocks, prim_out, g0, g1, bdt, rsp, coeff, eos,         \
                                       ntx, flags, dt, push, nchunk, a.d_status,                  \
-                                      a.d_fofc_count);                                           \
+                                      a.d_fofc_count,                                            \
+                                      static_cast<const unsigned char *>(a.d_tma_maps));         \
   }
   if (g.ndim == 3) APK_LAUNCH_FUSED(3)
   else if (g.ndim == 2) APK_LAUNCH_FUSED(2)
@@ -653,7 +727,17 @@ int launch_stage_rows_euler(const apk_pack_desc_t &d, const ApkGeom &g, const ap
 int launch_stage_rows_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
                           double *const *prim_out, const apk_stage_args_t &a, double coeff,
                           int recon, cudaStream_t s);
-#if APK_FUSED_PART == 0
+#if APK_FUSED_TMA
+static_assert(TX == APK_TMA_TX && TY == APK_TMA_TY, "tensor-map box and kernel tile must agree");
+// the A/B variant is built for the headline method only: GLM-MHD, PPM + HLLD (3-D meshes)
+int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
+                       double *const *prim_out, const apk_stage_args_t &a, double dedner_coeff,
+                       cudaStream_t s) {
+  const ApkGeom g = apk_make_geom(d);
+  return run_fused<APK_FLUID_GLMMHD, APK_RECON_PPM, APK_RIEMANN_HLLD>(d, g, blocks, prim_out, a,
+                                                                     dedner_coeff, s);
+}
+#elif APK_FUSED_PART == 0
 int launch_stage_fused_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
                            double *const *prim_out, const apk_stage_args_t &a,
                            double dedner_coeff, int recon, cudaStream_t s);

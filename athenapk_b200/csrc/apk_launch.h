@@ -41,6 +41,14 @@
 
 APK_DECLARE_LAUNCHERS(apk_fast)
 APK_DECLARE_LAUNCHERS(apk_strict)
+// A/B variant of the fused stage with TMA-staged prim tiles (apk_fused.cu built with
+// -DAPK_FUSED_TMA=1; GLM-MHD PPM+HLLD 3-D only)
+namespace apk_fast_tma {
+int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks, double *const *prim_out,
+                       const apk_stage_args_t &a, double dedner_coeff, cudaStream_t s);
+}
+#define APK_TMA_TX 32
+#define APK_TMA_TY 4
 
 // mode-independent (pure data movement) launchers, apk_halo.cu
 namespace apk_common {

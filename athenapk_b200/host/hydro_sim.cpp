@@ -150,6 +150,8 @@ HydroSim::~HydroSim() {
   cudaFree(d_status_);
   cudaFree(d_fofc_work_);
   cudaFree(d_undo_);
+  apk_tma_maps_destroy(d_tma_[0]);
+  apk_tma_maps_destroy(d_tma_[1]);
   apk_halo_plan_destroy(halo_plan_);
   if (!peer_mapped_.empty()) apk_p2p_unmap(peer_mapped_.data(), (int)peer_mapped_.size());
   cudaFree(d_push_[0]);
@@ -323,6 +325,11 @@ void HydroSim::UploadBlocks() {
     cuda_check(cudaMalloc(&d_blocks_[which], nbl * sizeof(apk_block_t)), "cudaMalloc blocks");
     cuda_check(cudaMemcpy(d_blocks_[which], hb.data(), nbl * sizeof(apk_block_t),
                           cudaMemcpyHostToDevice), "upload blocks");
+    // A/B: TMA-staged prim tiles for the PPM stage (APK_B200_FUSED_V=3; GLM-MHD PPM+HLLD 3-D, FMA mode)
+    const char *ver = std::getenv("APK_B200_FUSED_V");
+    if (fused_ && ver && ver[0] == '3' && ndim_ == 3 && cfg_.fluid == APK_FLUID_GLMMHD &&
+        cfg_.recon == APK_RECON_PPM && cfg_.riemann == APK_RIEMANN_HLLD && cfg_.fp_mode == APK_FP_FAST)
+      abi_check(apk_tma_maps_create(&desc_, hb.data(), &d_tma_[which]), "apk_tma_maps_create");
     cuda_check(cudaMalloc(&d_prim_out_[which], nbl * sizeof(double *)), "cudaMalloc prim_out");
     cuda_check(cudaMemcpy(d_prim_out_[which], pout.data(), nbl * sizeof(double *),
                           cudaMemcpyHostToDevice), "upload prim_out");
@@ -765,6 +772,7 @@ TaskStatus HydroSim::FusedStage(int stage, Real gam0, Real gam1, Real beta_dt, b
   a.d_status = d_status_;
   a.d_push = p2p_ ? d_push_[cur_] : nullptr;
   a.d_fofc_count = d_fofc_count;
+  a.d_tma_maps = d_tma_[cur_];
   abi_check(apk_stage_fused_ex(&desc_, d_blocks_[cur_], d_prim_out_[cur_], &a, stream_),
             "apk_stage_fused");
   cur_ ^= 1;  // prim_out becomes "prim"

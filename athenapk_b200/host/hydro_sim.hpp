@@ -208,6 +208,7 @@ class HydroSim {
   double *h_scalars_ = nullptr;  // pinned host mirror of d_scalars_[0..1] (one async D2H per cycle)
   int *d_status_ = nullptr;
   void *d_fofc_work_ = nullptr;
+  void *d_tma_[2] = {nullptr, nullptr};  // per prim parity: CUtensorMap per block (A/B variant)
   double *d_undo_ = nullptr;         // copy of a stage's input cons (fused FOFC, rk2 / rk3)
   bool last_stage_unfused_ = false;  // the cycle's last stage was redone un-fused: no device dt min
   void *stream_ = nullptr;

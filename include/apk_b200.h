@@ -274,10 +274,22 @@ typedef struct apk_stage_args {
   int *d_status;                /* may be NULL */
   const apk_push_dst_t *d_push; /* may be NULL: same-device neighbours from nbr[] */
   unsigned long long *d_fofc_count; /* may be NULL */
+  const void *d_tma_maps;       /* may be NULL.  Device array of one 128-byte CUtensorMap per block
+                                   over its prim array (apk_tma_maps_create): selects the variant of
+                                   the PPM/WENOZ stage that stages the halo'd prim tile of each plane
+                                   with cp.async.bulk.tensor (TMA) instead of per-lane loads */
 } apk_stage_args_t;
 #define APK_FUSED_FOFC_CHECK 32
 int apk_stage_fused_ex(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
                        double *const *d_prim_out, const apk_stage_args_t *args, void *stream);
+
+/* Tensor maps for the TMA variant of the fused stage: one 4-D map {n1, n2, n3, nvar} per block
+ * over h_blocks[b].prim (HOST copy of the block structs; the prim pointers are device pointers),
+ * box = (32+6) x (4+6) x 1 x nhydro, no swizzle, zero fill outside the array.  Returns a device
+ * array (cudaMalloc; release with apk_tma_maps_destroy) in *d_maps.  Requires n1 even (16-byte
+ * global strides).  Needs a driver that exports cuTensorMapEncodeTiled (CUDA >= 12). */
+int apk_tma_maps_create(const apk_pack_desc_t *desc, const apk_block_t *h_blocks, void **d_maps);
+void apk_tma_maps_destroy(void *d_maps);
 
 /* copy cons -> cons_u1 for all blocks (u1 <- u0 at stage 1, hydro_driver.cpp:474-495) */
 int apk_save_u1(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, void *stream);
