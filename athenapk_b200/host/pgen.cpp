@@ -325,7 +325,9 @@ int HydroSim::ProblemGenerator(const std::string &id, const std::vector<double> 
             const double rad = par(0, 0.1), pa = par(1, 0.1), prat = par(2, 100.0), da = par(3, 1.0);
             const double x = xc(B, 0, i), y = (ndim_ > 1) ? xc(B, 1, j) : 0.0,
                          z = (ndim_ > 2) ? xc(B, 2, k) : 0.0;
-            const double r = std::sqrt(SQR(x) + SQR(y) + SQR(z));
+            // centre of the blast: problem/blast/x1_0, x2_0, x3_0 (blast.cpp:131-133)
+            const double x0 = par(4, 0.0), y0 = par(5, 0.0), z0 = par(6, 0.0);
+            const double r = std::sqrt(SQR(x - x0) + SQR(y - y0) + SQR(z - z0));
             U(IDN) = da;
             U(IEN) = ((r < rad) ? prat * pa : pa) / gm1;
           } else {  // random

@@ -913,12 +913,23 @@ typedef struct {
   double dx[3];
   double bxmin[3], bxmax[3]; /* physical block bounds */
   int loc[3];
+  /* multilevel meshes */
+  int level;       /* refinement level (0 = root grid); loc[] is the location at this level */
+  double *coarse;  /* coarse buffer [nvar][nc3][nc2][nc1], nc = mb/2 + 2 ng (Variable::coarse_s) */
+  int has_coarser; /* some neighbour is one level coarser */
+  /* per neighbour offset (o3+1)*9+(o2+1)*3+(o1+1): 0 none, 1 same level, 2 coarser, 3 finer */
+  int ntype[27];
+  int nidx[27][4]; /* block index: the neighbour (types 1, 2) or its up to 4 abutting children */
+  int nchild[27];
 } block_t;
 
 struct apko_engine {
   apko_params p;
   int ndim, nvar, nhydro;
   int nb[3], nblocks;
+  int multilevel; /* static refinement active */
+  int nc[3];      /* coarse buffer extents */
+  int maxlevel;
   int n[3];      /* array extents incl. ghosts */
   int is[3], ie[3];
   size_t ncell;  /* n1*n2*n3 */
@@ -975,7 +986,15 @@ static double sym_logical_to_actual(double u, double xmin, double xmax) {
 static int max_pow2_divisor(int in) { return in & (~(in - 1)); }
 
 /* Block physical bounds: forest.cpp:66-141 (trees) + tree.cpp:296-318 (block in tree) */
+static void block_bounds_level(const apko_engine *e, int d, int level, int ib, double *bmin,
+                               double *bmax);
 static void block_bounds(const apko_engine *e, int d, int ib, double *bmin, double *bmax) {
+  block_bounds_level(e, d, 0, ib, bmin, bmax);
+}
+/* a block at refinement `level` with location ib (in units of blocks of that level): the tree it
+ * lives in is cut 2^(log2(mcp2) + level) times (tree.cpp:296-318) */
+static void block_bounds_level(const apko_engine *e, int d, int level, int ib, double *bmin,
+                               double *bmax) {
   const apko_params *p = &e->p;
   int any_sym = 0, mcp2 = 1 << 30;
   for (int dd = 0; dd < 3; ++dd) {
@@ -997,11 +1016,12 @@ static void block_bounds(const apko_engine *e, int d, int ib, double *bmin, doub
     return;
   }
   int ntree = e->nb[d] / mcp2;
-  int it = ib / mcp2, lx = ib % mcp2;
+  const int per_tree = mcp2 << level;
+  int it = ib / per_tree, lx = ib % per_tree;
   double tmin = sym_logical_to_actual(index_to_sym_coord(it, 0, ntree), p->xmin[d], p->xmax[d]);
   double tmax = sym_logical_to_actual(index_to_sym_coord(it, 2, ntree), p->xmin[d], p->xmax[d]);
-  *bmin = sym_logical_to_actual(index_to_sym_coord(lx, 0, mcp2), tmin, tmax);
-  *bmax = sym_logical_to_actual(index_to_sym_coord(lx, 2, mcp2), tmin, tmax);
+  *bmin = sym_logical_to_actual(index_to_sym_coord(lx, 0, per_tree), tmin, tmax);
+  *bmax = sym_logical_to_actual(index_to_sym_coord(lx, 2, per_tree), tmin, tmax);
 }
 
 static inline size_t IDX(const apko_engine *e, int n, int k, int j, int i) {
@@ -1011,6 +1031,220 @@ static inline size_t IDX(const apko_engine *e, int n, int k, int j, int i) {
 /* uniform_coordinates.hpp:110-114 */
 static inline double xc(const block_t *b, int d, int idx) {
   return b->xmin[d] + (idx + 0.5) * b->dx[d];
+}
+
+/* ---- static mesh refinement: the leaf set Parthenon's forest ends up with ------------------- */
+typedef struct {
+  int level, lx[3];
+} leaf_t;
+
+static int leaf_find(const leaf_t *L, int n, int level, const int *lx) {
+  for (int q = 0; q < n; ++q)
+    if (L[q].level == level && L[q].lx[0] == lx[0] && L[q].lx[1] == lx[1] && L[q].lx[2] == lx[2])
+      return q;
+  return -1;
+}
+
+/* leaf covering location lx of `level` (the leaf itself or an ancestor); -1: region is refined
+ * further (or outside) */
+static int leaf_cover(const leaf_t *L, int n, int level, const int *lx, int *found_level) {
+  for (int l = level; l >= 0; --l) {
+    int a[3] = {lx[0] >> (level - l), lx[1] >> (level - l), lx[2] >> (level - l)};
+    int q = leaf_find(L, n, l, a);
+    if (q >= 0) {
+      if (found_level) *found_level = l;
+      return q;
+    }
+  }
+  return -1;
+}
+
+/* mesh.cpp:1076-1096 GetStaticRefLLIndexRange */
+static void static_ref_range(const apko_engine *e, int d, int ref_level, double rmin, double rmax,
+                             int *lo, int *hi) {
+  const apko_params *p = &e->p;
+  const int lxtot = e->nb[d] * (1 << ref_level);
+  int lxmin, lxmax;
+  for (lxmin = 0; lxmin < lxtot; lxmin++) {
+    double r = index_to_sym_coord(lxmin + 1, 0, lxtot);
+    if (sym_logical_to_actual(r, p->xmin[d], p->xmax[d]) > rmin) break;
+  }
+  for (lxmax = lxmin; lxmax < lxtot; lxmax++) {
+    double r = index_to_sym_coord(lxmax + 1, 0, lxtot);
+    if (sym_logical_to_actual(r, p->xmin[d], p->xmax[d]) >= rmax) break;
+  }
+  if (lxmin % 2 == 1) lxmin--;
+  if (lxmax % 2 == 0) lxmax++;
+  *lo = lxmin;
+  *hi = lxmax;
+}
+
+/* Root grid refined until every block requested by a <parthenon/static_refinement> region exists
+ * (mesh.cpp:1100-1165) and neighbouring leaves (faces, edges, corners; periodic wrap) differ by
+ * at most one level -- the minimal properly nested tree, which is what forest.AddMeshBlock builds */
+static int build_leaves(const apko_engine *e, leaf_t **out) {
+  const apko_params *p = &e->p;
+  int cap = 64, n = 0;
+  leaf_t *L = (leaf_t *)malloc(cap * sizeof(leaf_t));
+  for (int z = 0; z < e->nb[2]; ++z)
+    for (int y = 0; y < e->nb[1]; ++y)
+      for (int x = 0; x < e->nb[0]; ++x) {
+        if (n == cap) L = (leaf_t *)realloc(L, (cap *= 2) * sizeof(leaf_t));
+        L[n].level = 0;
+        L[n].lx[0] = x; L[n].lx[1] = y; L[n].lx[2] = z;
+        n++;
+      }
+  int rlo[4][3], rhi[4][3];
+  for (int r = 0; r < p->nref; ++r)
+    for (int d = 0; d < 3; ++d) {
+      rlo[r][d] = 0;
+      rhi[r][d] = 0;
+      if (d < e->ndim)
+        static_ref_range(e, d, p->ref_level[r], p->ref_xmin[r][d], p->ref_xmax[r][d], &rlo[r][d],
+                         &rhi[r][d]);
+    }
+  const int nchild = 1 << e->ndim;
+  for (;;) {
+    char *mark = (char *)calloc(n, 1);
+    int any = 0;
+    for (int q = 0; q < n; ++q) {
+      /* (1) a requested block lies below this leaf */
+      for (int r = 0; r < p->nref && !mark[q]; ++r) {
+        const int dl = p->ref_level[r] - L[q].level;
+        if (dl <= 0) continue;
+        int hit = 1;
+        for (int d = 0; d < e->ndim; ++d) {
+          const int lo = L[q].lx[d] << dl, hi = ((L[q].lx[d] + 1) << dl) - 1;
+          if (hi < rlo[r][d] || lo > rhi[r][d]) hit = 0;
+        }
+        if (hit) mark[q] = 1;
+      }
+      /* (2) proper nesting: whatever covers a neighbour location may be at most one level coarser */
+      if (L[q].level >= 2) {
+        const int lev = L[q].level;
+        for (int o3 = (e->ndim > 2 ? -1 : 0); o3 <= (e->ndim > 2 ? 1 : 0); ++o3)
+          for (int o2 = (e->ndim > 1 ? -1 : 0); o2 <= (e->ndim > 1 ? 1 : 0); ++o2)
+            for (int o1 = -1; o1 <= 1; ++o1) {
+              int off[3] = {o1, o2, o3}, nl[3], valid = 1;
+              for (int d = 0; d < 3; ++d) {
+                const int tot = e->nb[d] << lev;
+                nl[d] = L[q].lx[d] + off[d];
+                if (nl[d] < 0 || nl[d] >= tot) {
+                  const int face = 2 * d + (nl[d] < 0 ? 0 : 1);
+                  if (p->bc[face] != APKO_BC_PERIODIC) valid = 0;
+                  nl[d] = (nl[d] + tot) % tot;
+                }
+              }
+              if (!valid) continue;
+              int fl = 0;
+              const int c = leaf_cover(L, n, lev, nl, &fl);
+              if (c >= 0 && fl < lev - 1) mark[c] = 1;
+            }
+      }
+    }
+    int n_new = n;
+    for (int q = 0; q < n; ++q) any |= mark[q];
+    if (!any) {
+      free(mark);
+      break;
+    }
+    for (int q = 0; q < n; ++q) {
+      if (!mark[q]) continue;
+      const leaf_t parent = L[q];
+      for (int c = 0; c < nchild; ++c) {
+        leaf_t ch;
+        ch.level = parent.level + 1;
+        for (int d = 0; d < 3; ++d)
+          ch.lx[d] = (d < e->ndim) ? 2 * parent.lx[d] + ((c >> d) & 1) : 0;
+        if (c == 0) {
+          L[q] = ch; /* first child replaces the parent */
+        } else {
+          if (n_new == cap) L = (leaf_t *)realloc(L, (cap *= 2) * sizeof(leaf_t));
+          L[n_new++] = ch;
+        }
+      }
+    }
+    n = n_new;
+    free(mark);
+  }
+  *out = L;
+  return n;
+}
+
+static void build_neighbor_tables(apko_engine *e) {
+  const apko_params *p = &e->p;
+  leaf_t *L = (leaf_t *)malloc(e->nblocks * sizeof(leaf_t));
+  for (int b = 0; b < e->nblocks; ++b) {
+    L[b].level = e->blk[b].level;
+    for (int d = 0; d < 3; ++d) L[b].lx[d] = e->blk[b].loc[d];
+  }
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    B->has_coarser = 0;
+    const int lev = B->level;
+    for (int o3 = -1; o3 <= 1; ++o3)
+      for (int o2 = -1; o2 <= 1; ++o2)
+        for (int o1 = -1; o1 <= 1; ++o1) {
+          const int idx = (o3 + 1) * 9 + (o2 + 1) * 3 + (o1 + 1);
+          B->ntype[idx] = 0;
+          B->nchild[idx] = 0;
+          const int off[3] = {o1, o2, o3};
+          if (!o1 && !o2 && !o3) continue;
+          int nl[3], valid = 1;
+          for (int d = 0; d < 3; ++d) {
+            if (off[d] != 0 && d >= e->ndim) valid = 0;
+            const int tot = e->nb[d] << lev;
+            nl[d] = B->loc[d] + off[d];
+            if (d < e->ndim && (nl[d] < 0 || nl[d] >= tot)) {
+              const int face = 2 * d + (nl[d] < 0 ? 0 : 1);
+              if (p->bc[face] != APKO_BC_PERIODIC) valid = 0;
+              nl[d] = (nl[d] + tot) % tot;
+            }
+          }
+          if (!valid) continue;
+          int fl = 0;
+          const int c = leaf_cover(L, e->nblocks, lev, nl, &fl);
+          if (c >= 0 && fl == lev) {
+            B->ntype[idx] = 1;
+            B->nidx[idx][0] = c;
+            B->nchild[idx] = 1;
+          } else if (c >= 0) { /* fl == lev - 1 by construction */
+            B->ntype[idx] = 2;
+            B->nidx[idx][0] = c;
+            B->nchild[idx] = 1;
+            B->has_coarser = 1;
+          } else {
+            /* finer: the children of nl that touch this block */
+            B->ntype[idx] = 3;
+            int cnt = 0;
+            for (int c3 = 0; c3 < 2; ++c3)
+              for (int c2 = 0; c2 < 2; ++c2)
+                for (int c1 = 0; c1 < 2; ++c1) {
+                  const int cb[3] = {c1, c2, c3};
+                  int ok = 1, cl[3];
+                  for (int d = 0; d < 3; ++d) {
+                    if (d >= e->ndim) {
+                      if (cb[d]) ok = 0;
+                      cl[d] = 0;
+                      continue;
+                    }
+                    if (off[d] > 0 && cb[d] != 0) ok = 0;
+                    if (off[d] < 0 && cb[d] != 1) ok = 0;
+                    cl[d] = 2 * nl[d] + cb[d];
+                  }
+                  if (!ok) continue;
+                  const int f = leaf_find(L, e->nblocks, lev + 1, cl);
+                  if (f < 0) {
+                    fprintf(stderr, "apk_oracle: mesh is not properly nested\n");
+                    abort();
+                  }
+                  B->nidx[idx][cnt++] = f;
+                }
+            B->nchild[idx] = cnt;
+          }
+        }
+  }
+  free(L);
 }
 
 apko_engine *apko_create(const apko_params *p) {
@@ -1033,6 +1267,18 @@ apko_engine *apko_create(const apko_params *p) {
     e->ie[d] = sym ? 0 : p->ng + p->mb[d] - 1;
   }
   e->ncell = (size_t)e->n[0] * e->n[1] * e->n[2];
+  leaf_t *leaves = NULL;
+  e->multilevel = 0;
+  if (p->nref > 0) {
+    /* mesh_refinement.cpp:60-70: refinement needs an even number of ghost cells */
+    if (p->ng % 2 != 0 || p->nref > 4) {
+      free(e);
+      return NULL;
+    }
+    e->nblocks = build_leaves(e, &leaves);
+    e->multilevel = 1;
+    for (int d = 0; d < 3; ++d) e->nc[d] = (d < e->ndim) ? p->mb[d] / 2 + 2 * p->ng : 1;
+  }
   e->blk = (block_t *)calloc(e->nblocks, sizeof(block_t));
   size_t nfield = e->ncell * e->nvar;
   for (int b = 0; b < e->nblocks; ++b) {
@@ -1041,17 +1287,26 @@ apko_engine *apko_create(const apko_params *p) {
     B->prim = (double *)calloc(nfield, sizeof(double));
     B->u1 = (double *)calloc(nfield, sizeof(double));
     for (int d = 0; d < 3; ++d) B->flux[d] = (double *)calloc(nfield, sizeof(double));
-    B->loc[0] = b % e->nb[0];
-    B->loc[1] = (b / e->nb[0]) % e->nb[1];
-    B->loc[2] = b / (e->nb[0] * e->nb[1]);
+    if (leaves) {
+      B->level = leaves[b].level;
+      for (int d = 0; d < 3; ++d) B->loc[d] = leaves[b].lx[d];
+      if (B->level > e->maxlevel) e->maxlevel = B->level;
+      B->coarse = (double *)calloc((size_t)e->nc[0] * e->nc[1] * e->nc[2] * e->nvar, sizeof(double));
+    } else {
+      B->loc[0] = b % e->nb[0];
+      B->loc[1] = (b / e->nb[0]) % e->nb[1];
+      B->loc[2] = b / (e->nb[0] * e->nb[1]);
+    }
     for (int d = 0; d < 3; ++d) {
-      block_bounds(e, d, B->loc[d], &B->bxmin[d], &B->bxmax[d]);
+      block_bounds_level(e, d, B->level, B->loc[d], &B->bxmin[d], &B->bxmax[d]);
       /* uniform_coordinates.hpp:32-36 */
       B->dx[d] = (B->bxmax[d] - B->bxmin[d]) / p->mb[d];
       int istart = (p->nx[d] == 1) ? 0 : p->ng;
       B->xmin[d] = B->bxmin[d] - istart * B->dx[d];
     }
   }
+  free(leaves);
+  if (e->multilevel) build_neighbor_tables(e);
   e->dt = DBL_MAX;
   e->mindx = DBL_MAX;
   e->dt_hyp = DBL_MAX;
@@ -1060,12 +1315,18 @@ apko_engine *apko_create(const apko_params *p) {
   return e;
 }
 
+void apko_block_loc(const apko_engine *e, int b, int *level, int *lx3) {
+  *level = e->blk[b].level;
+  for (int d = 0; d < 3; ++d) lx3[d] = e->blk[b].loc[d];
+}
+
 void apko_destroy(apko_engine *e) {
   if (!e) return;
   for (int b = 0; b < e->nblocks; ++b) {
     free(e->blk[b].cons);
     free(e->blk[b].prim);
     free(e->blk[b].u1);
+    free(e->blk[b].coarse);
     for (int d = 0; d < 3; ++d) free(e->blk[b].flux[d]);
   }
   free(e->blk);
@@ -1375,7 +1636,191 @@ static void apply_bc(apko_engine *e, block_t *B, int d, int outer, int type) {
   }
 }
 
+/* ---- multilevel ghost exchange (static refinement, periodic domains) ---------------------------
+ * What parthenon::AddBoundaryExchangeTasks does on a multilevel mesh
+ * (boundary_communication.cpp:405-445, index ranges bnd_info.cpp:105-230, :354-445), stated per
+ * ghost region of a block (27 neighbour offsets):
+ *   same-level neighbour : copy its interior cells;
+ *   finer neighbours     : each abutting child restricts (RestrictAverage, pr_ops.hpp:105-165) its
+ *                          interior into ITS coarse buffer and those cells become our ghost cells;
+ *   coarser neighbour    : our coarse buffer receives its interior cells (ng deep); every other
+ *                          part of our coarse buffer near the boundary is the restriction of OUR
+ *                          cells -- interior and the ghost cells filled above (ProResInfo::GetSet
+ *                          restricts the received same-level / finer ghosts) -- and the ghost cells
+ *                          are then prolongated from the coarse buffer
+ *                          (ProlongateCellMinModMultiD, custom_ops.hpp:49-186) over the ng/2 coarse
+ *                          layers that have fine ghost cells. */
+static void ml_range(const apko_engine *e, int d, int o, int coarse, int depth, int *lo, int *hi) {
+  if (d >= e->ndim) {
+    *lo = *hi = 0;
+    return;
+  }
+  const int s = coarse ? e->p.ng : e->is[d];
+  const int t = coarse ? e->p.ng + e->p.mb[d] / 2 - 1 : e->ie[d];
+  if (o == 0) { *lo = s; *hi = t; }
+  else if (o > 0) { *lo = t + 1; *hi = t + depth; }
+  else { *lo = s - depth; *hi = s - 1; }
+}
+
+#define CIDX(e, n, k, j, i) \
+  ((((size_t)(n) * (e)->nc[2] + (k)) * (e)->nc[1] + (j)) * (e)->nc[0] + (i))
+
+static void exchange_multilevel(apko_engine *e) {
+  const apko_params *p = &e->p;
+  const int ng = p->ng, nv = e->nvar;
+  for (int f = 0; f < 2 * e->ndim; ++f)
+    if (p->bc[f] != APKO_BC_PERIODIC) {
+      fprintf(stderr, "apk_oracle: refined meshes are restated for periodic domains only\n");
+      abort();
+    }
+  /* (1) same level and (2) finer neighbours -> ghost cells */
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    for (int idx = 0; idx < 27; ++idx) {
+      const int off[3] = {idx % 3 - 1, (idx / 3) % 3 - 1, idx / 9 - 1};
+      if (B->ntype[idx] == 1) {
+        const block_t *N = &e->blk[B->nidx[idx][0]];
+        int lo[3], hi[3], shift[3];
+        for (int d = 0; d < 3; ++d) {
+          ml_range(e, d, off[d], 0, ng, &lo[d], &hi[d]);
+          shift[d] = (d < e->ndim) ? -off[d] * p->mb[d] : 0;
+        }
+        for (int n = 0; n < nv; ++n)
+          for (int k = lo[2]; k <= hi[2]; ++k)
+            for (int j = lo[1]; j <= hi[1]; ++j)
+              for (int i = lo[0]; i <= hi[0]; ++i)
+                B->cons[IDX(e, n, k, j, i)] =
+                    N->cons[IDX(e, n, k + shift[2], j + shift[1], i + shift[0])];
+      } else if (B->ntype[idx] == 3) {
+        for (int c = 0; c < B->nchild[idx]; ++c) {
+          block_t *F = &e->blk[B->nidx[idx][c]];
+          /* the child's coarse cells next to the shared face / edge / corner */
+          int clo[3], chi[3];
+          for (int d = 0; d < 3; ++d) {
+            if (d >= e->ndim) { clo[d] = chi[d] = 0; continue; }
+            const int cis = ng, cie = ng + p->mb[d] / 2 - 1;
+            if (off[d] > 0) { clo[d] = cis; chi[d] = cis + ng - 1; }
+            else if (off[d] < 0) { clo[d] = cie - ng + 1; chi[d] = cie; }
+            else { clo[d] = cis; chi[d] = cie; }
+          }
+          apko_restrict_average(e->ndim, ng, 0, F->bxmin, F->dx, nv, e->n, F->cons, e->nc,
+                                F->coarse, clo, chi);
+          for (int n = 0; n < nv; ++n)
+            for (int ck = clo[2]; ck <= chi[2]; ++ck)
+              for (int cj = clo[1]; cj <= chi[1]; ++cj)
+                for (int ci = clo[0]; ci <= chi[0]; ++ci) {
+                  const int cc[3] = {ci, cj, ck};
+                  int t[3];
+                  for (int d = 0; d < 3; ++d) {
+                    if (d >= e->ndim) { t[d] = 0; continue; }
+                    if (off[d] > 0) t[d] = e->ie[d] + 1 + (cc[d] - clo[d]);
+                    else if (off[d] < 0) t[d] = e->is[d] - ng + (cc[d] - clo[d]);
+                    else t[d] = e->is[d] + (F->loc[d] & 1) * (p->mb[d] / 2) + (cc[d] - clo[d]);
+                  }
+                  B->cons[IDX(e, n, t[2], t[1], t[0])] = F->coarse[CIDX(e, n, ck, cj, ci)];
+                }
+        }
+      }
+    }
+  }
+  /* (3) coarse buffers of the blocks that have a coarser neighbour, (4) prolongation */
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    if (!B->has_coarser) continue;
+    for (int idx = 0; idx < 27; ++idx) {
+      const int off[3] = {idx % 3 - 1, (idx / 3) % 3 - 1, idx / 9 - 1};
+      int lo[3], hi[3];
+      if (idx == 13 || B->ntype[idx] == 1 || B->ntype[idx] == 3) {
+        /* restriction of our own cells: interior, or ghost cells received from same-level /
+         * finer neighbours (ng fine = ng/2 coarse layers) */
+        for (int d = 0; d < 3; ++d) ml_range(e, d, off[d], 1, ng / 2, &lo[d], &hi[d]);
+        apko_restrict_average(e->ndim, ng, 0, B->bxmin, B->dx, nv, e->n, B->cons, e->nc, B->coarse,
+                              lo, hi);
+      } else if (B->ntype[idx] == 2) {
+        const block_t *Cn = &e->blk[B->nidx[idx][0]];
+        for (int d = 0; d < 3; ++d) ml_range(e, d, off[d], 1, ng, &lo[d], &hi[d]);
+        for (int n = 0; n < nv; ++n)
+          for (int ck = lo[2]; ck <= hi[2]; ++ck)
+            for (int cj = lo[1]; cj <= hi[1]; ++cj)
+              for (int ci = lo[0]; ci <= hi[0]; ++ci) {
+                const int cc[3] = {ci, cj, ck};
+                int t[3];
+                for (int d = 0; d < 3; ++d) {
+                  if (d >= e->ndim) { t[d] = 0; continue; }
+                  /* global cell index on the coarser level (periodic wrap), then local in Cn */
+                  const long tot = (long)(e->nb[d] << (B->level - 1)) * p->mb[d];
+                  long G = (long)B->loc[d] * (p->mb[d] / 2) + (cc[d] - ng);
+                  G = ((G % tot) + tot) % tot;
+                  t[d] = e->is[d] + (int)(G - (long)Cn->loc[d] * p->mb[d]);
+                  if (t[d] < e->is[d] || t[d] > e->ie[d]) {
+                    fprintf(stderr, "apk_oracle: coarse neighbour does not cover a buffer cell\n");
+                    abort();
+                  }
+                }
+                B->coarse[CIDX(e, n, ck, cj, ci)] = Cn->cons[IDX(e, n, t[2], t[1], t[0])];
+              }
+      }
+    }
+    for (int idx = 0; idx < 27; ++idx) {
+      if (B->ntype[idx] != 2) continue;
+      const int off[3] = {idx % 3 - 1, (idx / 3) % 3 - 1, idx / 9 - 1};
+      int lo[3], hi[3];
+      for (int d = 0; d < 3; ++d) ml_range(e, d, off[d], 1, ng / 2, &lo[d], &hi[d]);
+      apko_prolongate_minmod_multid(e->ndim, ng, B->bxmin, B->dx, nv, e->n, B->cons, e->nc,
+                                    B->coarse, lo, hi);
+    }
+  }
+}
+
+/* ---- flux correction (bvals_in_one.hpp:69-80, bnd_info.cpp:71-103, hydro_driver.cpp:527-531):
+ * on a face shared with finer blocks the coarse block's flux is REPLACED by the area-weighted mean
+ * of the fine faces (RestrictAverage on the face element of the sweep direction) */
+static void flux_correction(apko_engine *e) {
+  const apko_params *p = &e->p;
+  const int ng = p->ng, nv = e->nvar;
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    for (int d = 0; d < e->ndim; ++d)
+      for (int side = -1; side <= 1; side += 2) {
+        int off[3] = {0, 0, 0};
+        off[d] = side;
+        const int idx = (off[2] + 1) * 9 + (off[1] + 1) * 3 + (off[0] + 1);
+        if (B->ntype[idx] != 3) continue;
+        for (int c = 0; c < B->nchild[idx]; ++c) {
+          block_t *F = &e->blk[B->nidx[idx][c]];
+          int clo[3], chi[3];
+          for (int dd = 0; dd < 3; ++dd) {
+            if (dd >= e->ndim) { clo[dd] = chi[dd] = 0; continue; }
+            const int cis = ng, cie = ng + p->mb[dd] / 2 - 1;
+            if (dd == d) clo[dd] = chi[dd] = (side > 0) ? cis : cie + 1;
+            else { clo[dd] = cis; chi[dd] = cie; }
+          }
+          /* the child's coarse buffer is free between exchanges: scratch for the restricted face */
+          apko_restrict_average(e->ndim, ng, d + 1, F->bxmin, F->dx, nv, e->n, F->flux[d], e->nc,
+                                F->coarse, clo, chi);
+          for (int n = 0; n < nv; ++n)
+            for (int ck = clo[2]; ck <= chi[2]; ++ck)
+              for (int cj = clo[1]; cj <= chi[1]; ++cj)
+                for (int ci = clo[0]; ci <= chi[0]; ++ci) {
+                  const int cc[3] = {ci, cj, ck};
+                  int t[3];
+                  for (int dd = 0; dd < 3; ++dd) {
+                    if (dd >= e->ndim) { t[dd] = 0; continue; }
+                    if (dd == d) t[dd] = (side > 0) ? e->ie[dd] + 1 : e->is[dd];
+                    else t[dd] = e->is[dd] + (F->loc[dd] & 1) * (p->mb[dd] / 2) + (cc[dd] - ng);
+                  }
+                  B->flux[d][IDX(e, n, t[2], t[1], t[0])] = F->coarse[CIDX(e, n, ck, cj, ci)];
+                }
+        }
+      }
+  }
+}
+
 void apko_exchange(apko_engine *e) {
+  if (e->multilevel) {
+    exchange_multilevel(e);
+    return;
+  }
   const int ng = e->p.ng;
   /* same-level neighbour copies; reads interiors only, writes ghosts only */
   for (int b = 0; b < e->nblocks; ++b) {
@@ -1553,6 +1998,7 @@ void apko_cycle(apko_engine *e) {
     const double bdt = beta[s] * e->dt;
     apko_calc_fluxes(e, recon);
     if (e->p.fofc) e->fofc_total += apko_fofc(e, g0[s], g1[s], bdt);
+    if (e->multilevel) flux_correction(e); /* hydro_driver.cpp:527-531 */
     apko_flux_div_update(e, g0[s], g1[s], bdt);
     apko_dedner(e, bdt);
     apko_exchange(e);
@@ -1918,7 +2364,10 @@ int apko_pgen(apko_engine *e, int id, const double *pars, int npars) {
             double prat = npars > 2 ? pars[2] : 100.0, da = npars > 3 ? pars[3] : 1.0;
             double x = xc(B, 0, i), y = (e->ndim > 1) ? xc(B, 1, j) : 0.0,
                    z = (e->ndim > 2) ? xc(B, 2, k) : 0.0;
-            double r = sqrt(SQR(x) + SQR(y) + SQR(z));
+            /* centre of the blast: problem/blast/x1_0, x2_0, x3_0 (blast.cpp:131-133) */
+            double x0 = npars > 4 ? pars[4] : 0.0, y0 = npars > 5 ? pars[5] : 0.0,
+                   z0 = npars > 6 ? pars[6] : 0.0;
+            double r = sqrt(SQR(x - x0) + SQR(y - y0) + SQR(z - z0));
             U(IDN) = da;
             U(IEN) = ((r < rad) ? prat * pa : pa) / gm1;
           } break;

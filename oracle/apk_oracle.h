@@ -45,6 +45,11 @@ typedef struct {
   int dedner_extended; /* hydro/glmmhd_source = dedner_extended */
   double glmmhd_alpha;
   int nscalars;
+  /* static mesh refinement (<parthenon/static_refinementN> blocks, mesh.cpp:1100-1165): up to 4
+   * regions, each refined to ref_level[r] (>= 1); nref = 0: uniform mesh */
+  int nref;
+  int ref_level[4];
+  double ref_xmin[4][3], ref_xmax[4][3];
 } apko_params;
 
 typedef struct apko_engine apko_engine;
@@ -64,6 +69,8 @@ int apko_run(apko_engine *e, double tlim, int nlim);
 void apko_cycle(apko_engine *e);
 
 int apko_num_blocks(const apko_engine *e);
+/* refinement level and logical location (at that level) of block b */
+void apko_block_loc(const apko_engine *e, int b, int *level, int *lx3);
 void apko_block_dims(const apko_engine *e, int *n /*[3] incl ghosts: n1,n2,n3*/);
 int apko_nvar(const apko_engine *e);
 double *apko_cons(apko_engine *e, int b);

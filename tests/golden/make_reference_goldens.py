@@ -93,6 +93,28 @@ def main():
             "hydro/first_order_flux_correct=true", "hydro/dfloor=1e-8", "hydro/pfloor=1e-8",
             "problem/blast/radius_outer=0.1", "problem/blast/radius_inner=0.1",
             "parthenon/output0/file_type=hst"])
+        # BASELINE config 5 on a FROZEN refined mesh: inputs/blast_3d_amr.in with refinement = static
+        # (two nested <parthenon/static_refinement> regions -> 3 levels, 56 + 56 + 64 meshblocks of
+        # 8^3), GLM-MHD WENOZ + HLLD, nghost = 4 (odd nghost is rejected with mesh refinement,
+        # mesh_refinement.cpp:60-70), blast centred off the origin so that it straddles the level
+        # boundaries: prolongation, restriction and flux correction all act on the dt-limiting cells
+        def amr(name, regions, fluid, recon, rs, ng):
+            ov = ["parthenon/mesh/refinement=static", "hydro/fluid=" + fluid,
+                  "hydro/reconstruction=" + recon, "hydro/riemann=" + rs,
+                  "parthenon/mesh/nghost=%d" % ng, "parthenon/time/nlim=20",
+                  "parthenon/output0/file_type=hst", "problem/blast/radius_outer=0.12",
+                  "problem/blast/radius_inner=0.12", "problem/blast/pressure_ratio=100",
+                  "problem/blast/pressure_ambient=0.1", "problem/blast/x1_0=0.22",
+                  "problem/blast/x2_0=0.1", "problem/blast/x3_0=-0.05"]
+            for r, (lev, lo, hi) in enumerate(regions):
+                for d in range(3):
+                    ov += ["parthenon/static_refinement%d/x%dmin=%r" % (r, d + 1, lo),
+                           "parthenon/static_refinement%d/x%dmax=%r" % (r, d + 1, hi)]
+                ov += ["parthenon/static_refinement%d/level=%d" % (r, lev)]
+            jobs[name] = ex.submit(run, os.path.join(INPUTS, "blast_3d_amr.in"), ov)
+        amr("amr_2level_plm_hlle", [(1, -0.2, 0.2)], "euler", "plm", "hlle", 2)
+        amr("amr_3level_plm_hlle", [(1, -0.2, 0.2), (2, -0.1, 0.1)], "euler", "plm", "hlle", 2)
+        amr("amr_3level_wenoz_hlld", [(1, -0.2, 0.2), (2, -0.1, 0.1)], "glmmhd", "wenoz", "hlld", 4)
         # the two same-input decks of the GPU-vs-GPU measurement (baseline/decks), small meshes
         for deck in ("uniform_mhd", "orszag_tang_3d"):
             jobs[deck] = ex.submit(run, os.path.join(ROOT, "baseline", "decks", deck + ".in"),

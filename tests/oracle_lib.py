@@ -31,6 +31,8 @@ class Params(C.Structure):
         ("vceil", C.c_double), ("eceil", C.c_double),
         ("fofc", C.c_int), ("fofc_jacobi", C.c_int), ("dedner_extended", C.c_int),
         ("glmmhd_alpha", C.c_double), ("nscalars", C.c_int),
+        ("nref", C.c_int), ("ref_level", C.c_int * 4),
+        ("ref_xmin", (C.c_double * 3) * 4), ("ref_xmax", (C.c_double * 3) * 4),
     ]
 
 
@@ -100,7 +102,9 @@ def make_params(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
                 mb=None, ng=2, bc="periodic", xmin=(0.0, 0.0, 0.0), xmax=(3.0, 1.5, 1.5),
                 gamma=5.0 / 3.0, cfl=0.3, fofc=False, fofc_jacobi=False, dedner_extended=False,
                 glmmhd_alpha=0.1, nscalars=0, dfloor=-1.0, pfloor=-1.0, efloor=-1.0,
-                vceil=float("inf"), eceil=float("inf")):
+                vceil=float("inf"), eceil=float("inf"), refine=()):
+    """refine: static refinement regions [(level, (x1min, x2min, x3min), (x1max, x2max, x3max)), ...]
+    = the <parthenon/static_refinementN> blocks of a deck"""
     p = Params()
     lib().apko_default_params(C.byref(p))
     p.fluid, p.recon, p.riemann = FLUID[fluid], RECON[recon], RIEMANN[riemann]
@@ -117,6 +121,11 @@ def make_params(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
     p.fofc, p.fofc_jacobi, p.dedner_extended = int(fofc), int(fofc_jacobi), int(dedner_extended)
     p.glmmhd_alpha, p.nscalars = glmmhd_alpha, nscalars
     p.dfloor, p.pfloor, p.efloor, p.vceil, p.eceil = dfloor, pfloor, efloor, vceil, eceil
+    p.nref = len(refine)
+    for r, (lev, lo, hi) in enumerate(refine):
+        p.ref_level[r] = lev
+        for d in range(3):
+            p.ref_xmin[r][d], p.ref_xmax[r][d] = lo[d], hi[d]
     return p
 
 

@@ -6,7 +6,7 @@ GPU tests hold to the same traces in strict FP mode."""
 import pytest
 
 from oracle_lib import Oracle
-from trace_util import DECKS, TRACES, check_lw_row, follow_trace, lw_kwargs, lw_pgen
+from trace_util import AMR_DECKS, DECKS, TRACES, check_lw_row, follow_trace, lw_kwargs, lw_pgen
 
 
 def advance(o, tlim, c):
@@ -70,3 +70,18 @@ def test_deck_traces(name):
         # the case exists to pin FirstOrderFluxCorrect in the reference's serial (Gauss-Seidel)
         # ordering: it must actually have triggered
         assert o.fofc_total > 0
+
+
+@pytest.mark.parametrize("name", sorted(AMR_DECKS))
+def test_static_refinement_traces(name):
+    """BASELINE config 5 on a frozen refined mesh (inputs/blast_3d_amr.in, refinement = static, 2 and
+    3 levels, up to 176 meshblocks of 8^3): multilevel ghost exchange (restriction, prolongation from
+    the coarse buffers) and flux correction reproduce the reference's (time, dt) at all 17 digits for
+    20 cycles -- GLM-MHD WENOZ + HLLD with nghost = 4 is the method config 5 names."""
+    kw, pgen, pars, tlim = AMR_DECKS[name]
+    o = Oracle(**kw)
+    case = TRACES[name]
+    o.pgen(pgen, pars)
+    o.initialize(tlim)
+    follow_trace(o, case["trace"], tlim, advance)
+    assert o.ncycle == case["ncycle"]

@@ -45,6 +45,22 @@ DECKS = {
 }
 
 
+def _amr(regions, fluid, recon, rs, ng):
+    return (dict(fluid=fluid, nx=(32, 32, 32), mb=(8, 8, 8), ng=ng, xmin=(-0.5,) * 3,
+                 xmax=(0.5,) * 3, gamma=GAMMA_DECK, cfl=0.3, recon=recon, riemann=rs,
+                 integrator="vl2",
+                 refine=[(lev, (lo,) * 3, (hi,) * 3) for lev, lo, hi in regions]),
+            "blast", [0.12, 0.1, 100.0, 1.0, 0.22, 0.1, -0.05], 0.1)
+
+
+# static mesh refinement (see make_reference_goldens.py): 2 and 3 levels
+AMR_DECKS = {
+    "amr_2level_plm_hlle": _amr([(1, -0.2, 0.2)], "euler", "plm", "hlle", 2),
+    "amr_3level_plm_hlle": _amr([(1, -0.2, 0.2), (2, -0.1, 0.1)], "euler", "plm", "hlle", 2),
+    "amr_3level_wenoz_hlld": _amr([(1, -0.2, 0.2), (2, -0.1, 0.1)], "glmmhd", "wenoz", "hlld", 4),
+}
+
+
 def follow_trace(engine, trace, tlim, advance, every=1):
     """advance(engine, tlim, ncycle) runs the engine up to cycle `ncycle`; compares (time, dt) with
     the reference's printout at all 17 digits.  Returns the number of cycles compared."""
