@@ -37,6 +37,8 @@ class SimConfig(C.Structure):
         ("fofc", C.c_int), ("dedner_extended", C.c_int), ("glmmhd_alpha", C.c_double),
         ("nscalars", C.c_int), ("fp_mode", C.c_int), ("fused", C.c_int),
         ("rank", C.c_int), ("nranks", C.c_int), ("plan_only", C.c_int),
+        ("nref", C.c_int), ("ref_level", C.c_int * 4),
+        ("ref_xmin", (C.c_double * 3) * 4), ("ref_xmax", (C.c_double * 3) * 4),
     ]
 
 
@@ -79,7 +81,7 @@ ABI_SYMBOLS = [
     "apk_last_error", "apk_abi_version", "apk_stage_fused_ex", "apk_halo_plan_create",
     "apk_halo_plan_destroy", "apk_halo_start", "apk_halo_test", "apk_halo_finish", "apk_p2p_map_peers",
     "apk_p2p_unmap", "apk_stage_barrier", "apk_allreduce_scalar", "apk_tma_maps_create",
-    "apk_tma_maps_destroy", "apk_launch_count", "apk_reset_launch_count",
+    "apk_tma_maps_destroy", "apk_box_copy", "apk_launch_count", "apk_reset_launch_count",
     "apk_calc_fluxes", "apk_fofc_workspace_bytes", "apk_first_order_flux_correct",
     "apk_flux_div_update", "apk_dedner_source", "apk_cons_to_prim", "apk_min_dt",
     "apk_min_dt_async", "apk_fill_ghosts_local", "apk_apply_physical_bcs",
@@ -91,7 +93,7 @@ SIM_SYMBOLS = [
     "apk_sim_last_error", "apk_sim_default_config", "apk_sim_create", "apk_sim_destroy",
     "apk_sim_nccl_unique_id", "apk_sim_init_comm", "apk_sim_pgen", "apk_sim_initialize",
     "apk_sim_execute", "apk_sim_step", "apk_sim_num_local_blocks", "apk_sim_num_global_blocks",
-    "apk_sim_nvar", "apk_sim_block_dims", "apk_sim_block_info", "apk_sim_copy_to_host",
+    "apk_sim_nvar", "apk_sim_block_dims", "apk_sim_block_level", "apk_sim_block_info", "apk_sim_copy_to_host",
     "apk_sim_copy_from_host", "apk_sim_device_ptr", "apk_sim_time", "apk_sim_dt",
     "apk_sim_ncycle", "apk_sim_c_h", "apk_sim_fofc_corrections", "apk_sim_fofc_redone_stages", "apk_sim_fused_active", "apk_sim_p2p_active",
     "apk_sim_linear_wave_period", "apk_sim_linear_wave_errors", "apk_sim_stream",
@@ -168,6 +170,7 @@ def lib():
               "apk_sim_ncycle", "apk_sim_fused_active", "apk_sim_p2p_active", "apk_sim_synchronize"):
         getattr(L, f).argtypes = [vp]
     L.apk_sim_block_dims.argtypes = [vp, ip]
+    L.apk_sim_block_level.argtypes = [vp, C.c_int]
     L.apk_sim_block_info.argtypes = [vp, C.c_int, ip, ip, dp, dp]
     L.apk_sim_copy_to_host.argtypes = [vp, C.c_int, C.c_int, vp]
     L.apk_sim_copy_from_host.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -210,8 +213,10 @@ def make_config(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
                 gamma=5.0 / 3.0, cfl=0.3, fofc=False, dedner_extended=False, glmmhd_alpha=0.1,
                 nscalars=0, dfloor=-1.0, pfloor=-1.0, efloor=-1.0, vceil=float("inf"),
                 eceil=float("inf"), fp_mode="fast", fused=True, rank=0, nranks=1,
-                plan_only=False):
-    """Input-deck style configuration (same keys/meaning as docs/input.md of the reference)."""
+                plan_only=False, refine=()):
+    """Input-deck style configuration (same keys/meaning as docs/input.md of the reference).
+    refine: static refinement regions [(level, (x1min, x2min, x3min), (x1max, x2max, x3max)), ...]
+    = the <parthenon/static_refinementN> blocks of a deck."""
     c = SimConfig()
     lib().apk_sim_default_config(C.byref(c))
     c.fluid, c.recon, c.riemann = FLUID[fluid], RECON[recon], RIEMANN[riemann]
@@ -232,6 +237,11 @@ def make_config(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
     c.fused = int(fused)
     c.rank, c.nranks = rank, nranks
     c.plan_only = int(plan_only)
+    c.nref = len(refine)
+    for r, (lev, lo, hi) in enumerate(refine):
+        c.ref_level[r] = lev
+        for d in range(3):
+            c.ref_xmin[r][d], c.ref_xmax[r][d] = lo[d], hi[d]
     return c
 
 
@@ -299,6 +309,9 @@ class HydroSim:
         dx = (C.c_double * 3)()
         self.L.apk_sim_block_info(self.h, b, C.byref(gid), loc, xmin, dx)
         return gid.value, tuple(loc), tuple(xmin), tuple(dx)
+
+    def block_level(self, b):
+        return self.L.apk_sim_block_level(self.h, b)
 
     def get(self, field, b):
         out = np.empty(self.shape, dtype=np.float64)

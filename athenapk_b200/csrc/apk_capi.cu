@@ -333,6 +333,15 @@ int apk_history_sums(const apk_pack_desc_t *d, const apk_block_t *blocks, void *
   return cuda_ok("apk_history_sums");
 }
 
+int apk_box_copy(const apk_box_item_t *d_items, int nitems, int nvar, void *stream) {
+  if (nitems < 0 || nvar < 1 || (nitems > 0 && !d_items)) {
+    apk_common::set_error("apk_box_copy: bad arguments");
+    return 1;
+  }
+  apk_common::launch_box_copy(d_items, nitems, nvar, S(stream));
+  return cuda_ok("apk_box_copy");
+}
+
 int apk_save_u1(const apk_pack_desc_t *d, const apk_block_t *blocks, void *stream) {
   if (check(d, blocks, "apk_save_u1: bad descriptor")) return 1;
   apk_common::launch_save_u1(*d, blocks, S(stream));

@@ -190,6 +190,27 @@ k_halo_copy(ApkGeom g, const apk_block_t *__restrict__ blocks,
   }
 }
 
+// box copies between arrays of different extents (multilevel exchange, flux correction)
+__global__ void __launch_bounds__(kThreads)
+k_box_copy(const apk_box_item_t *__restrict__ items, int nvar) {
+  const apk_box_item_t it = items[blockIdx.y];
+  const long cells = (long)it.ext[0] * it.ext[1] * it.ext[2];
+  const long total = cells * nvar;
+  const long ncs = (long)it.ns[0] * it.ns[1] * it.ns[2], ncd = (long)it.nd[0] * it.nd[1] * it.nd[2];
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long)gridDim.x * blockDim.x) {
+    const int n = (int)(t / cells);
+    long rem = t - (long)n * cells;
+    const int kk = (int)(rem / ((long)it.ext[0] * it.ext[1]));
+    rem -= (long)kk * it.ext[0] * it.ext[1];
+    const int jj = (int)(rem / it.ext[0]);
+    const int ii = (int)(rem - (long)jj * it.ext[0]);
+    const long cs = ((long)(it.s0[2] + kk) * it.ns[1] + (it.s0[1] + jj)) * it.ns[0] + (it.s0[0] + ii);
+    const long cd = ((long)(it.d0[2] + kk) * it.nd[1] + (it.d0[1] + jj)) * it.nd[0] + (it.d0[0] + ii);
+    it.dst[(long)n * ncd + cd] = it.src[(long)n * ncs + cs];
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_save_u1(ApkGeom g, const apk_block_t *__restrict__ blocks) {
   const long per = g.ncell * g.nvar;
@@ -268,6 +289,14 @@ int launch_halo_unpack(const apk_pack_desc_t &d, const apk_block_t *blocks,
   dim3 grid(8, nitems);
   k_halo_copy<false><<<grid, kThreads, 0, s>>>(g, blocks, items, with_prim,
                                                const_cast<double *>(buf));
+  count_launch();
+  return 0;
+}
+
+int launch_box_copy(const apk_box_item_t *items, int nitems, int nvar, cudaStream_t s) {
+  if (nitems <= 0) return 0;
+  dim3 grid(4, nitems);
+  k_box_copy<<<grid, kThreads, 0, s>>>(items, nvar);
   count_launch();
   return 0;
 }

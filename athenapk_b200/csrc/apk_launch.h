@@ -63,6 +63,7 @@ int launch_halo_unpack(const apk_pack_desc_t &d, const apk_block_t *blocks,
                        const apk_halo_item_t *items, int nitems, int with_prim,
                        const double *buf, cudaStream_t s);
 int launch_save_u1(const apk_pack_desc_t &d, const apk_block_t *blocks, cudaStream_t s);
+int launch_box_copy(const apk_box_item_t *items, int nitems, int nvar, cudaStream_t s);
 int launch_fp64_probe(int nb, int nt, int niter, double *out, cudaStream_t s);
 void count_launch(int n = 1);
 int current_device();

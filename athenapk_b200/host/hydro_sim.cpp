@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <stdexcept>
+#include <tuple>
 
 namespace apk_host {
 
@@ -116,11 +117,27 @@ HydroSim::HydroSim(const SimConfig &cfg)
     n_[d] = (cfg_.nx[d] == 1) ? 1 : cfg_.mb[d] + 2 * cfg_.ng;
   }
   nblocks_global_ = nb_[0] * nb_[1] * nb_[2];
+  multilevel_ = cfg_.nref > 0;
+  if (multilevel_) {
+    // mesh_refinement.cpp:60-70
+    if (cfg_.ng % 2 != 0)
+      throw std::runtime_error("Selected nghost is incompatible with mesh refinement because it is "
+                               "not a multiple of 2.");
+    if (cfg_.nranks != 1 || cfg_.nref > 4)
+      throw std::runtime_error("apk_host: refined meshes run on one rank (up to 4 regions)");
+    for (int f = 0; f < 2 * ndim_; ++f)
+      if (cfg_.bc[f] != APK_BC_PERIODIC)
+        throw std::runtime_error("apk_host: refined meshes are implemented for periodic domains");
+    for (int d = 0; d < ndim_; ++d)
+      if (cfg_.mb[d] % 2 != 0 || cfg_.mb[d] / 2 < cfg_.ng)
+        throw std::runtime_error("apk_host: meshblock too small for refinement (nx/2 >= nghost)");
+  }
   // FOFC decks run fused too: the stage kernel evaluates FirstOrderFluxCorrect's first attempt on
   // its own trial update, and only a stage in which a cell actually fails is redone with the
   // flux-materialising tasks (FusedFofcCheck)
+  // multilevel meshes need materialised fluxes (flux correction, hydro_driver.cpp:527-531)
   fused_ = cfg_.fused && !cfg_.dedner_extended && cfg_.riemann != APK_RIEMANN_LLF &&
-           cfg_.nscalars == 0;
+           cfg_.nscalars == 0 && !multilevel_;
   BuildMesh();
   BuildNeighbors();
   if (!cfg_.plan_only) {
@@ -150,6 +167,11 @@ HydroSim::~HydroSim() {
   cudaFree(d_status_);
   cudaFree(d_fofc_work_);
   cudaFree(d_undo_);
+  cudaFree(d_coarse_);
+  for (MlList *l : {&ml_restrict_child_, &ml_child_to_ghost_, &ml_restrict_own_, &ml_coarse_from_nbr_,
+                    &ml_prolong_, &ml_fc_restrict_[0], &ml_fc_restrict_[1], &ml_fc_restrict_[2],
+                    &ml_fc_copy_[0], &ml_fc_copy_[1], &ml_fc_copy_[2]})
+    cudaFree(l->d);
   apk_tma_maps_destroy(d_tma_[0]);
   apk_tma_maps_destroy(d_tma_[1]);
   apk_halo_plan_destroy(halo_plan_);
@@ -180,6 +202,12 @@ void HydroSim::BuildMesh() {
     const auto &l = order[g].second;
     gid_of_loc_[l[0] + nb_[0] * (l[1] + nb_[1] * l[2])] = g;
   }
+  std::vector<Leaf> leaves;
+  if (multilevel_) {
+    leaves = BuildLeaves();
+    nblocks_global_ = (int)leaves.size();
+    for (int d = 0; d < 3; ++d) nc_[d] = (d < ndim_) ? cfg_.mb[d] / 2 + 2 * cfg_.ng : 1;
+  }
   // equal split (remainder to the first ranks)
   const int base = nblocks_global_ / cfg_.nranks, rem = nblocks_global_ % cfg_.nranks;
   gid_lo_ = cfg_.rank * base + std::min(cfg_.rank, rem);
@@ -198,23 +226,26 @@ void HydroSim::BuildMesh() {
   for (int g = gid_lo_; g < gid_hi_; ++g) {
     BlockInfo B{};
     B.gid = g;
+    B.level = multilevel_ ? leaves[g].level : 0;
     for (int d = 0; d < 3; ++d) {
-      B.loc[d] = loc_of_gid_[g][d];
+      B.loc[d] = multilevel_ ? leaves[g].lx[d] : loc_of_gid_[g][d];
       if (cfg_.nx[d] == 1) {
         B.bxmin[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(0, 0, 1),
                                                         cfg_.xmin[d], cfg_.xmax[d]);
         B.bxmax[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(0, 2, 1),
                                                         cfg_.xmin[d], cfg_.xmax[d]);
       } else {
-        const int ntree = nb_[d] / mcp2, it = B.loc[d] / mcp2, lx = B.loc[d] % mcp2;
+        // a block of refinement level l: its tree is cut mcp2 * 2^l times (tree.cpp:296-318)
+        const int per_tree = mcp2 << B.level;
+        const int ntree = nb_[d] / mcp2, it = B.loc[d] / per_tree, lx = B.loc[d] % per_tree;
         const double tmin = SymmetrizedLogicalToActualPosition(
             IndexToSymmetrizedCoordinate(it, 0, ntree), cfg_.xmin[d], cfg_.xmax[d]);
         const double tmax = SymmetrizedLogicalToActualPosition(
             IndexToSymmetrizedCoordinate(it, 2, ntree), cfg_.xmin[d], cfg_.xmax[d]);
-        B.bxmin[d] =
-            SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(lx, 0, mcp2), tmin, tmax);
-        B.bxmax[d] =
-            SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(lx, 2, mcp2), tmin, tmax);
+        B.bxmin[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(lx, 0, per_tree),
+                                                        tmin, tmax);
+        B.bxmax[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(lx, 2, per_tree),
+                                                        tmin, tmax);
       }
       // uniform_coordinates.hpp:32-36
       B.dx[d] = (B.bxmax[d] - B.bxmin[d]) / cfg_.mb[d];
@@ -242,9 +273,182 @@ void HydroSim::BuildMesh() {
   desc_.eceil = cfg_.eceil;
 }
 
+// ---- static mesh refinement -----------------------------------------------------------------
+namespace {
+struct LeafKey {
+  int level, x, y, z;
+  bool operator<(const LeafKey &o) const {
+    return std::tie(level, x, y, z) < std::tie(o.level, o.x, o.y, o.z);
+  }
+};
+}  // namespace
+
+// The leaf set Parthenon's forest ends up with for <parthenon/static_refinement> regions
+// (mesh.cpp:1076-1165: index range of the requested blocks per region; forest.AddMeshBlock refines
+// down to them and keeps neighbouring leaves -- faces, edges, corners, periodic wrap -- within one
+// level of each other): the minimal properly nested tree containing the requested blocks.
+std::vector<HydroSim::Leaf> HydroSim::BuildLeaves() const {
+  int rlo[4][3] = {}, rhi[4][3] = {};
+  for (int r = 0; r < cfg_.nref; ++r)
+    for (int d = 0; d < ndim_; ++d) {
+      const int lxtot = nb_[d] * (1 << cfg_.ref_level[r]);
+      int lxmin, lxmax;
+      for (lxmin = 0; lxmin < lxtot; lxmin++) {
+        const double x = SymmetrizedLogicalToActualPosition(
+            IndexToSymmetrizedCoordinate(lxmin + 1, 0, lxtot), cfg_.xmin[d], cfg_.xmax[d]);
+        if (x > cfg_.ref_xmin[r][d]) break;
+      }
+      for (lxmax = lxmin; lxmax < lxtot; lxmax++) {
+        const double x = SymmetrizedLogicalToActualPosition(
+            IndexToSymmetrizedCoordinate(lxmax + 1, 0, lxtot), cfg_.xmin[d], cfg_.xmax[d]);
+        if (x >= cfg_.ref_xmax[r][d]) break;
+      }
+      if (lxmin % 2 == 1) lxmin--;
+      if (lxmax % 2 == 0) lxmax++;
+      rlo[r][d] = lxmin;
+      rhi[r][d] = lxmax;
+    }
+  std::map<LeafKey, int> leaves;  // value unused
+  for (int z = 0; z < nb_[2]; ++z)
+    for (int y = 0; y < nb_[1]; ++y)
+      for (int x = 0; x < nb_[0]; ++x) leaves[{0, x, y, z}] = 0;
+  auto cover = [&](int level, const int *lx, LeafKey *out) {
+    for (int l = level; l >= 0; --l) {
+      LeafKey k{l, lx[0] >> (level - l), lx[1] >> (level - l), lx[2] >> (level - l)};
+      if (leaves.count(k)) {
+        *out = k;
+        return true;
+      }
+    }
+    return false;
+  };
+  for (;;) {
+    std::vector<LeafKey> marked;
+    for (const auto &kv : leaves) {
+      const LeafKey &q = kv.first;
+      const int lx[3] = {q.x, q.y, q.z};
+      bool refine = false;
+      for (int r = 0; r < cfg_.nref && !refine; ++r) {
+        const int dl = cfg_.ref_level[r] - q.level;
+        if (dl <= 0) continue;
+        bool hit = true;
+        for (int d = 0; d < ndim_; ++d) {
+          const int lo = lx[d] << dl, hi = ((lx[d] + 1) << dl) - 1;
+          if (hi < rlo[r][d] || lo > rhi[r][d]) hit = false;
+        }
+        refine = hit;
+      }
+      if (refine) marked.push_back(q);
+      if (q.level >= 2) {  // proper nesting around this leaf
+        for (int o3 = (ndim_ > 2 ? -1 : 0); o3 <= (ndim_ > 2 ? 1 : 0); ++o3)
+          for (int o2 = (ndim_ > 1 ? -1 : 0); o2 <= (ndim_ > 1 ? 1 : 0); ++o2)
+            for (int o1 = -1; o1 <= 1; ++o1) {
+              const int off[3] = {o1, o2, o3};
+              int nl[3];
+              for (int d = 0; d < 3; ++d) {
+                const int tot = nb_[d] << q.level;
+                nl[d] = ((lx[d] + off[d]) % tot + tot) % tot;  // periodic (checked in the ctor)
+              }
+              LeafKey c{};
+              if (cover(q.level, nl, &c) && c.level < q.level - 1) marked.push_back(c);
+            }
+      }
+    }
+    if (marked.empty()) break;
+    for (const LeafKey &q : marked) {
+      if (!leaves.erase(q)) continue;  // marked twice
+      for (int c = 0; c < (1 << ndim_); ++c)
+        leaves[{q.level + 1, 2 * q.x + (c & 1), ndim_ > 1 ? 2 * q.y + ((c >> 1) & 1) : 0,
+                ndim_ > 2 ? 2 * q.z + ((c >> 2) & 1) : 0}] = 0;
+    }
+  }
+  std::vector<Leaf> out;
+  for (const auto &kv : leaves) out.push_back({kv.first.level, {kv.first.x, kv.first.y, kv.first.z}});
+  return out;
+}
+
+void HydroSim::BuildMultilevelNeighbors() {
+  std::map<LeafKey, int> index;
+  for (size_t b = 0; b < blocks_.size(); ++b)
+    index[{blocks_[b].level, blocks_[b].loc[0], blocks_[b].loc[1], blocks_[b].loc[2]}] = (int)b;
+  nbrinfo_.assign(blocks_.size(), NbrInfo{});
+  for (size_t b = 0; b < blocks_.size(); ++b) {
+    const BlockInfo &B = blocks_[b];
+    NbrInfo &N = nbrinfo_[b];
+    N.has_coarser = false;
+    for (int idx = 0; idx < 27; ++idx) {
+      N.type[idx] = 0;
+      N.nchild[idx] = 0;
+      const int off[3] = {idx % 3 - 1, (idx / 3) % 3 - 1, idx / 9 - 1};
+      if (idx == 13) continue;
+      bool valid = true;
+      int nl[3] = {0, 0, 0};
+      for (int d = 0; d < 3; ++d) {
+        if (d >= ndim_) {
+          if (off[d] != 0) valid = false;
+          continue;
+        }
+        const int tot = nb_[d] << B.level;
+        nl[d] = ((B.loc[d] + off[d]) % tot + tot) % tot;
+      }
+      if (!valid) continue;
+      auto same = index.find({B.level, nl[0], nl[1], nl[2]});
+      if (same != index.end()) {
+        N.type[idx] = 1;
+        N.idx[idx][0] = same->second;
+        N.nchild[idx] = 1;
+        continue;
+      }
+      auto coarser = (B.level > 0) ? index.find({B.level - 1, nl[0] >> 1, nl[1] >> 1, nl[2] >> 1})
+                                   : index.end();
+      if (coarser != index.end()) {
+        N.type[idx] = 2;
+        N.idx[idx][0] = coarser->second;
+        N.nchild[idx] = 1;
+        N.has_coarser = true;
+        continue;
+      }
+      N.type[idx] = 3;  // finer: the children that touch this block
+      for (int c = 0; c < 8; ++c) {
+        const int cb[3] = {c & 1, (c >> 1) & 1, (c >> 2) & 1};
+        bool ok = true;
+        int cl[3] = {0, 0, 0};
+        for (int d = 0; d < 3; ++d) {
+          if (d >= ndim_) {
+            if (cb[d]) ok = false;
+            continue;
+          }
+          if (off[d] > 0 && cb[d] != 0) ok = false;
+          if (off[d] < 0 && cb[d] != 1) ok = false;
+          cl[d] = 2 * nl[d] + cb[d];
+        }
+        if (!ok) continue;
+        auto f = index.find({B.level + 1, cl[0], cl[1], cl[2]});
+        if (f == index.end()) throw std::runtime_error("apk_host: mesh is not properly nested");
+        N.idx[idx][N.nchild[idx]++] = f->second;
+      }
+    }
+  }
+}
+
 void HydroSim::BuildNeighbors() {
   h_blocks_.assign(blocks_.size(), apk_block_t{});
   bc_face_mask_ = 0;
+  if (multilevel_) {
+    BuildMultilevelNeighbors();
+    for (size_t b = 0; b < blocks_.size(); ++b) {
+      apk_block_t &hb = h_blocks_[b];
+      for (int d = 0; d < 3; ++d) {
+        hb.dx[d] = blocks_[b].dx[d];
+        hb.xmin[d] = blocks_[b].xmin[d];
+      }
+      for (int f = 0; f < 6; ++f) hb.bc[f] = APK_BC_BLOCK;
+      // the same-level table drives apk_copy_ghosts_local; other levels go through the plan
+      for (int idx = 0; idx < 27; ++idx)
+        hb.nbr[idx] = (nbrinfo_[b].type[idx] == 1) ? nbrinfo_[b].idx[idx][0] : APK_NBR_NONE;
+    }
+    return;
+  }
   for (size_t b = 0; b < blocks_.size(); ++b) {
     apk_block_t &hb = h_blocks_[b];
     const BlockInfo &B = blocks_[b];
@@ -333,6 +537,11 @@ void HydroSim::UploadBlocks() {
     cuda_check(cudaMalloc(&d_prim_out_[which], nbl * sizeof(double *)), "cudaMalloc prim_out");
     cuda_check(cudaMemcpy(d_prim_out_[which], pout.data(), nbl * sizeof(double *),
                           cudaMemcpyHostToDevice), "upload prim_out");
+  }
+  if (multilevel_) {
+    cuda_check(cudaMalloc(&d_coarse_, CoarseElems() * nbl * sizeof(double)), "cudaMalloc coarse");
+    cuda_check(cudaMemset(d_coarse_, 0, CoarseElems() * nbl * sizeof(double)), "memset");
+    BuildMultilevelPlan();
   }
   cuda_check(cudaMalloc(&d_scalars_, 64 * sizeof(double)), "cudaMalloc scalars");
   cuda_check(cudaMemset(d_scalars_, 0, 64 * sizeof(double)), "memset scalars");
@@ -629,6 +838,7 @@ int HydroSim::LoadStateInterior(const double *h_src) {
   SendBoundBufs(0);
   ReceiveBoundBufs();
   SetBounds(0);
+  ProlongateBounds();
   ApplyBoundaryConditions(0);
   FillDerived();
   return 0;
@@ -876,6 +1086,193 @@ TaskStatus HydroSim::SetBounds(int with_prim) {
   return TaskStatus::complete;
 }
 
+// ---- multilevel exchange plan ------------------------------------------------------------------
+// What AddBoundaryExchangeTasks does on a multilevel mesh (boundary_communication.cpp:405-445; index
+// ranges bnd_info.cpp:105-230, :354-445), regrouped into six launches over item lists:
+//   1 same-level ghost copies (apk_copy_ghosts_local, the nbr[] table);
+//   2 every fine block next to a coarser one restricts the cells along the shared face / edge /
+//     corner into ITS coarse buffer (apk_restrict_average) ...
+//   3 ... and those coarse cells are copied into the coarser block's ghost cells (apk_box_copy);
+//   4 blocks with a coarser neighbour restrict their own cells -- interior and the ghost cells
+//     filled by 1 and 3 -- into their coarse buffer (what ProResInfo::GetSet schedules);
+//   5 the coarser neighbours' interior cells go into the coarse buffer, nghost deep (apk_box_copy);
+//   6 ghost cells over coarser neighbours are prolongated from the coarse buffer
+//     (apk_prolongate_minmod_multid) over the nghost/2 coarse layers that have fine ghost cells.
+void HydroSim::BuildMultilevelPlan() {
+  const int ng = cfg_.ng;
+  const size_t per = BlockFieldElems(), cper = CoarseElems();
+  auto fine_ptr = [&](double *base, int b) { return base + (size_t)b * per; };
+  auto coarse_ptr = [&](int b) { return d_coarse_ + (size_t)b * cper; };
+  const int cis = ng;
+  auto cie = [&](int d) { return ng + cfg_.mb[d] / 2 - 1; };
+  const int is[3] = {cfg_.ng, ndim_ >= 2 ? cfg_.ng : 0, ndim_ >= 3 ? cfg_.ng : 0};
+  auto ie = [&](int d) { return is[d] + cfg_.mb[d] - 1; };
+  // index range of the region of neighbour offset o in direction d (fine or coarse index space)
+  auto range = [&](int d, int o, bool coarse, int depth, int *lo, int *hi) {
+    if (d >= ndim_) { *lo = *hi = 0; return; }
+    const int s0 = coarse ? cis : is[d], t0 = coarse ? cie(d) : ie(d);
+    if (o == 0) { *lo = s0; *hi = t0; }
+    else if (o > 0) { *lo = t0 + 1; *hi = t0 + depth; }
+    else { *lo = s0 - depth; *hi = s0 - 1; }
+  };
+  auto amr_item = [&](double *fine, int b, const int *lo, const int *hi) {
+    apk_amr_item_t it{};
+    it.fine = fine;
+    it.coarse = coarse_ptr(b);
+    for (int d = 0; d < 3; ++d) {
+      it.nf[d] = n_[d];
+      it.nc[d] = nc_[d];
+      it.lo[d] = lo[d];
+      it.hi[d] = hi[d];
+      it.xmin[d] = blocks_[b].bxmin[d];
+      it.dx[d] = blocks_[b].dx[d];
+    }
+    return it;
+  };
+  std::vector<apk_amr_item_t> restrict_child, restrict_own, prolong, fc_restrict[3];
+  std::vector<apk_box_item_t> child_to_ghost, coarse_from_nbr, fc_copy[3];
+  for (size_t b = 0; b < blocks_.size(); ++b) {
+    const BlockInfo &B = blocks_[b];
+    const NbrInfo &N = nbrinfo_[b];
+    for (int idx = 0; idx < 27; ++idx) {
+      const int off[3] = {idx % 3 - 1, (idx / 3) % 3 - 1, idx / 9 - 1};
+      if (N.type[idx] == 3) {
+        for (int c = 0; c < N.nchild[idx]; ++c) {
+          const int f = N.idx[idx][c];
+          int clo[3], chi[3];
+          apk_box_item_t bx{};
+          for (int d = 0; d < 3; ++d) {
+            if (d >= ndim_) { clo[d] = chi[d] = 0; }
+            else if (off[d] > 0) { clo[d] = cis; chi[d] = cis + ng - 1; }
+            else if (off[d] < 0) { clo[d] = cie(d) - ng + 1; chi[d] = cie(d); }
+            else { clo[d] = cis; chi[d] = cie(d); }
+            bx.ns[d] = nc_[d];
+            bx.nd[d] = n_[d];
+            bx.s0[d] = clo[d];
+            bx.ext[d] = chi[d] - clo[d] + 1;
+            if (d >= ndim_) bx.d0[d] = 0;
+            else if (off[d] > 0) bx.d0[d] = ie(d) + 1;
+            else if (off[d] < 0) bx.d0[d] = is[d] - ng;
+            else bx.d0[d] = is[d] + (blocks_[f].loc[d] & 1) * (cfg_.mb[d] / 2);
+          }
+          restrict_child.push_back(amr_item(fine_ptr(d_cons_, f), f, clo, chi));
+          bx.src = coarse_ptr(f);
+          bx.dst = fine_ptr(d_cons_, (int)b);
+          child_to_ghost.push_back(bx);
+        }
+      }
+      if (!N.has_coarser) continue;
+      int lo[3], hi[3];
+      if (idx == 13 || N.type[idx] == 1 || N.type[idx] == 3) {
+        for (int d = 0; d < 3; ++d) range(d, off[d], true, ng / 2, &lo[d], &hi[d]);
+        restrict_own.push_back(amr_item(fine_ptr(d_cons_, (int)b), (int)b, lo, hi));
+      } else if (N.type[idx] == 2) {
+        const int cn = N.idx[idx][0];
+        apk_box_item_t bx{};
+        for (int d = 0; d < 3; ++d) {
+          range(d, off[d], true, ng, &lo[d], &hi[d]);
+          bx.ns[d] = n_[d];
+          bx.nd[d] = nc_[d];
+          bx.d0[d] = lo[d];
+          bx.ext[d] = hi[d] - lo[d] + 1;
+          if (d >= ndim_) { bx.s0[d] = 0; continue; }
+          // global cell index of the first buffer cell on the coarser level (periodic wrap)
+          const long tot = (long)(nb_[d] << (B.level - 1)) * cfg_.mb[d];
+          long G = (long)B.loc[d] * (cfg_.mb[d] / 2) + (lo[d] - ng);
+          G = ((G % tot) + tot) % tot;
+          bx.s0[d] = is[d] + (int)(G - (long)blocks_[cn].loc[d] * cfg_.mb[d]);
+          if (bx.s0[d] < is[d] || bx.s0[d] + bx.ext[d] - 1 > ie(d))
+            throw std::runtime_error("apk_host: coarse neighbour does not cover a buffer region");
+        }
+        bx.src = fine_ptr(d_cons_, cn);
+        bx.dst = coarse_ptr((int)b);
+        coarse_from_nbr.push_back(bx);
+        for (int d = 0; d < 3; ++d) range(d, off[d], true, ng / 2, &lo[d], &hi[d]);
+        prolong.push_back(amr_item(fine_ptr(d_cons_, (int)b), (int)b, lo, hi));
+      }
+    }
+    // flux correction: faces shared with finer blocks (bvals_in_one.hpp:69-80, bnd_info.cpp:71-103)
+    for (int d = 0; d < ndim_; ++d)
+      for (int side = -1; side <= 1; side += 2) {
+        int off[3] = {0, 0, 0};
+        off[d] = side;
+        const int idx = (off[2] + 1) * 9 + (off[1] + 1) * 3 + (off[0] + 1);
+        if (N.type[idx] != 3) continue;
+        for (int c = 0; c < N.nchild[idx]; ++c) {
+          const int f = N.idx[idx][c];
+          int clo[3], chi[3];
+          apk_box_item_t bx{};
+          for (int dd = 0; dd < 3; ++dd) {
+            if (dd >= ndim_) { clo[dd] = chi[dd] = 0; }
+            else if (dd == d) { clo[dd] = chi[dd] = (side > 0) ? cis : cie(dd) + 1; }
+            else { clo[dd] = cis; chi[dd] = cie(dd); }
+            bx.ns[dd] = nc_[dd];
+            bx.nd[dd] = n_[dd];
+            bx.s0[dd] = clo[dd];
+            bx.ext[dd] = chi[dd] - clo[dd] + 1;
+            if (dd >= ndim_) bx.d0[dd] = 0;
+            else if (dd == d) bx.d0[dd] = (side > 0) ? ie(dd) + 1 : is[dd];
+            else bx.d0[dd] = is[dd] + (blocks_[f].loc[dd] & 1) * (cfg_.mb[dd] / 2);
+          }
+          // the child's coarse buffer is free between exchanges: scratch for the restricted faces
+          fc_restrict[d].push_back(amr_item(fine_ptr(d_flux_[d], f), f, clo, chi));
+          bx.src = coarse_ptr(f);
+          bx.dst = fine_ptr(d_flux_[d], (int)b);
+          fc_copy[d].push_back(bx);
+        }
+      }
+  }
+  auto upload = [&](MlList &dst, const void *src, size_t n, size_t elem) {
+    dst.n = (int)n;
+    if (!n) return;
+    cuda_check(cudaMalloc(&dst.d, n * elem), "cudaMalloc multilevel plan");
+    cuda_check(cudaMemcpy(dst.d, src, n * elem, cudaMemcpyHostToDevice), "upload multilevel plan");
+  };
+  upload(ml_restrict_child_, restrict_child.data(), restrict_child.size(), sizeof(apk_amr_item_t));
+  upload(ml_child_to_ghost_, child_to_ghost.data(), child_to_ghost.size(), sizeof(apk_box_item_t));
+  upload(ml_restrict_own_, restrict_own.data(), restrict_own.size(), sizeof(apk_amr_item_t));
+  upload(ml_coarse_from_nbr_, coarse_from_nbr.data(), coarse_from_nbr.size(), sizeof(apk_box_item_t));
+  upload(ml_prolong_, prolong.data(), prolong.size(), sizeof(apk_amr_item_t));
+  for (int d = 0; d < 3; ++d) {
+    upload(ml_fc_restrict_[d], fc_restrict[d].data(), fc_restrict[d].size(), sizeof(apk_amr_item_t));
+    upload(ml_fc_copy_[d], fc_copy[d].data(), fc_copy[d].size(), sizeof(apk_box_item_t));
+  }
+}
+
+TaskStatus HydroSim::ProlongateBounds() {
+  if (!multilevel_) return TaskStatus::complete;
+  const int fp = cfg_.fp_mode;
+  abi_check(apk_restrict_average(ndim_, cfg_.ng, nvar_, 0,
+                                 static_cast<const apk_amr_item_t *>(ml_restrict_child_.d),
+                                 ml_restrict_child_.n, fp, stream_), "apk_restrict_average");
+  abi_check(apk_box_copy(static_cast<const apk_box_item_t *>(ml_child_to_ghost_.d),
+                         ml_child_to_ghost_.n, nvar_, stream_), "apk_box_copy");
+  abi_check(apk_restrict_average(ndim_, cfg_.ng, nvar_, 0,
+                                 static_cast<const apk_amr_item_t *>(ml_restrict_own_.d),
+                                 ml_restrict_own_.n, fp, stream_), "apk_restrict_average");
+  abi_check(apk_box_copy(static_cast<const apk_box_item_t *>(ml_coarse_from_nbr_.d),
+                         ml_coarse_from_nbr_.n, nvar_, stream_), "apk_box_copy");
+  abi_check(apk_prolongate_minmod_multid(ndim_, cfg_.ng, nvar_,
+                                         static_cast<const apk_amr_item_t *>(ml_prolong_.d),
+                                         ml_prolong_.n, fp, stream_), "apk_prolongate_minmod_multid");
+  return TaskStatus::complete;
+}
+
+// hydro_driver.cpp:527-531 (AddFluxCorrectionTasks): the flux of a coarse face shared with finer
+// blocks is replaced by the area-weighted mean of the fine faces
+TaskStatus HydroSim::FluxCorrection() {
+  if (!multilevel_) return TaskStatus::complete;
+  for (int d = 0; d < ndim_; ++d) {
+    abi_check(apk_restrict_average(ndim_, cfg_.ng, nvar_, d + 1,
+                                   static_cast<const apk_amr_item_t *>(ml_fc_restrict_[d].d),
+                                   ml_fc_restrict_[d].n, cfg_.fp_mode, stream_),
+              "apk_restrict_average (flux)");
+    abi_check(apk_box_copy(static_cast<const apk_box_item_t *>(ml_fc_copy_[d].d), ml_fc_copy_[d].n,
+                           nvar_, stream_), "apk_box_copy (flux)");
+  }
+  return TaskStatus::complete;
+}
+
 TaskStatus HydroSim::ApplyBoundaryConditions(int with_prim) {
   if (bc_face_mask_)
     abi_check(apk_apply_physical_bcs(&desc_, d_blocks_[cur_], bc_face_mask_, with_prim,
@@ -952,6 +1349,7 @@ void HydroSim::Initialize(double tlim) {
   SendBoundBufs(0);
   ReceiveBoundBufs();
   SetBounds(0);
+  ProlongateBounds();
   ApplyBoundaryConditions(0);
   FillDerived();
   dt_hyp = std::numeric_limits<Real>::max();
@@ -990,11 +1388,13 @@ void HydroSim::MakeTaskCollection(TaskList &tl, int stage) {
     if (cfg_.fofc)
       tl.AddTask("first_order_flux_correct",
                  [=] { return FirstOrderFluxCorrect(gam0, gam1, beta_dt); });
+    if (multilevel_) tl.AddTask("flux_correction", [this] { return FluxCorrection(); });
     tl.AddTask("update", [=] { return UpdateWithFluxDivergence(gam0, gam1, beta_dt); });
     tl.AddTask("source_unsplit", [=] { return AddUnsplitSources(beta_dt); });
     tl.AddTask("send", [this] { return SendBoundBufs(0); });
     tl.AddTask("recv", [this] { return ReceiveBoundBufs(); });
     tl.AddTask("set", [this] { return SetBounds(0); });
+    if (multilevel_) tl.AddTask("prolongate_bounds", [this] { return ProlongateBounds(); });
     tl.AddTask("fbound", [this] { return ApplyBoundaryConditions(0); });
     tl.AddTask("fill_derived", [this] { return FillDerived(); });
   }

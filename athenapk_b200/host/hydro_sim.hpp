@@ -51,6 +51,10 @@ struct SimConfig {
   int fused = 1;  // use apk_stage_fused when legal (no FOFC / extended source)
   int rank = 0, nranks = 1;
   int plan_only = 0;  // mesh partition + halo plan only, no CUDA (CPU-side tests of the N>1 logic)
+  // static mesh refinement: the <parthenon/static_refinementN> blocks of a deck (mesh.cpp:1100-1165)
+  int nref = 0;
+  int ref_level[4] = {0, 0, 0, 0};
+  double ref_xmin[4][3] = {}, ref_xmax[4][3] = {};
 };
 
 // time_integration/low_storage_integrator.cpp:53-132
@@ -70,7 +74,8 @@ struct SimTime {
 
 struct BlockInfo {
   int gid;        // position in the Morton-ordered global block list
-  int loc[3];     // logical location (lx1,lx2,lx3)
+  int level = 0;  // refinement level (0 = root grid)
+  int loc[3];     // logical location (lx1,lx2,lx3) at that level
   double bxmin[3], bxmax[3];
   double dx[3], xmin[3];  // UniformCartesian: dx_, xmin_ (uniform_coordinates.hpp:32-36)
 };
@@ -139,6 +144,11 @@ class HydroSim {
   TaskStatus ReceiveBoundBufs();
   TaskStatus SetBounds(int with_prim);
   TaskStatus ApplyBoundaryConditions(int with_prim);
+  // multilevel meshes: restriction into / prolongation from the coarse buffers (ProlongateBounds,
+  // boundary_communication.cpp:361-393) and flux correction (hydro_driver.cpp:527-531)
+  TaskStatus ProlongateBounds();
+  TaskStatus FluxCorrection();
+  bool Multilevel() const { return multilevel_; }
   TaskStatus FillDerived();
   TaskStatus EstimateTimestep(bool have_device_min);
   void PreStepMeshUserWorkInLoop();
@@ -208,6 +218,22 @@ class HydroSim {
   double *h_scalars_ = nullptr;  // pinned host mirror of d_scalars_[0..1] (one async D2H per cycle)
   int *d_status_ = nullptr;
   void *d_fofc_work_ = nullptr;
+  // ---- static mesh refinement ----
+  bool multilevel_ = false;
+  struct Leaf { int level; int lx[3]; };
+  std::vector<Leaf> BuildLeaves() const;
+  // neighbour kind per (block, offset): 0 none, 1 same level, 2 coarser, 3 finer
+  struct NbrInfo { int type[27]; int idx[27][4]; int nchild[27]; bool has_coarser; };
+  std::vector<NbrInfo> nbrinfo_;
+  void BuildMultilevelNeighbors();
+  void BuildMultilevelPlan();
+  double *d_coarse_ = nullptr;  // coarse buffers [nblocks][nvar][nc3][nc2][nc1] (Variable::coarse_s)
+  int nc_[3] = {1, 1, 1};
+  size_t CoarseElems() const { return (size_t)nvar_ * nc_[0] * nc_[1] * nc_[2]; }
+  // item lists of the multilevel exchange (device copies), one launch each
+  struct MlList { void *d = nullptr; int n = 0; };
+  MlList ml_restrict_child_, ml_child_to_ghost_, ml_restrict_own_, ml_coarse_from_nbr_, ml_prolong_;
+  MlList ml_fc_restrict_[3], ml_fc_copy_[3];
   void *d_tma_[2] = {nullptr, nullptr};  // per prim parity: CUtensorMap per block (A/B variant)
   double *d_undo_ = nullptr;         // copy of a stage's input cons (fused FOFC, rk2 / rk3)
   bool last_stage_unfused_ = false;  // the cycle's last stage was redone un-fused: no device dt min

@@ -52,6 +52,11 @@ apk_sim_t *apk_sim_create(const apk_sim_config_t *c) {
     k.fofc = c->fofc; k.dedner_extended = c->dedner_extended; k.glmmhd_alpha = c->glmmhd_alpha;
     k.nscalars = c->nscalars; k.fp_mode = c->fp_mode; k.fused = c->fused;
     k.rank = c->rank; k.nranks = c->nranks; k.plan_only = c->plan_only;
+    k.nref = c->nref;
+    for (int r = 0; r < 4; ++r) {
+      k.ref_level[r] = c->ref_level[r];
+      for (int i = 0; i < 3; ++i) { k.ref_xmin[r][i] = c->ref_xmin[r][i]; k.ref_xmax[r][i] = c->ref_xmax[r][i]; }
+    }
     s = new HydroSim(k);
     return 0;
   });
@@ -92,6 +97,7 @@ int apk_sim_step(apk_sim_t *s) {
 }
 int apk_sim_num_local_blocks(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->NumLocalBlocks(); }
 int apk_sim_num_global_blocks(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->NumGlobalBlocks(); }
+int apk_sim_block_level(const apk_sim_t *s, int b) { return SIM(const_cast<apk_sim_t *>(s))->Block(b).level; }
 int apk_sim_nvar(const apk_sim_t *s) { return SIM(const_cast<apk_sim_t *>(s))->nvar(); }
 void apk_sim_block_dims(const apk_sim_t *s, int *n3) {
   const int *n = SIM(const_cast<apk_sim_t *>(s))->dims();
@@ -166,6 +172,7 @@ int apk_sim_task(apk_sim_t *s, const char *name, int stage, double g0, double g1
     else if (n == "source_unsplit") st = h->AddUnsplitSources(bdt);
     else if (n == "exchange") {
       h->SendBoundBufs(0); h->ReceiveBoundBufs(); h->SetBounds(0);
+      if (h->Multilevel()) h->ProlongateBounds();
       st = h->ApplyBoundaryConditions(0);
     } else if (n == "fill_derived") st = h->FillDerived();
     else if (n == "pre_step") { h->PreStepMeshUserWorkInLoop(); st = TaskStatus::complete; }

@@ -317,6 +317,21 @@ int apk_restrict_average(int ndim, int ng, int nvar, int element, const apk_amr_
  * writes the 2^ndim fine children of every coarse cell in the range. */
 int apk_prolongate_minmod_multid(int ndim, int ng, int nvar, const apk_amr_item_t *d_items,
                                  int nitems, int fp_mode, void *stream);
+/* Copy of 3-D boxes of all variables between two [nvar][n3][n2][n1] arrays of different extents:
+ * the data movement of the multilevel exchange -- restricted fine cells (a child's coarse buffer)
+ * into the coarse block's ghost cells, a coarser neighbour's interior cells into a block's coarse
+ * buffer (the BoundaryInteriorSend / BoundaryExteriorRecv ranges of bnd_info.cpp:105-230 for
+ * neighbours on other levels), restricted face fluxes into the coarse block's flux array (flux
+ * correction, bvals_in_one.hpp:69-80).  One launch for all items. */
+typedef struct apk_box_item {
+  const double *src;
+  double *dst;
+  int ns[3], nd[3];  /* extents (i,j,k) of the source / destination arrays          */
+  int s0[3], d0[3];  /* first cell (i,j,k) of the box in the source / destination   */
+  int ext[3];        /* box extents (i,j,k)                                         */
+} apk_box_item_t;
+int apk_box_copy(const apk_box_item_t *d_items, int nitems, int nvar, void *stream);
+
 /* refinement::gradient::PressureGradient (src/refinement/gradient.cpp:18-61): per block
  * max |grad p| / p over interior +- 1 -> d_maxeps[b] and the AmrTag d_tags[b] (-1 derefine,
  * 0 same, 1 refine). */

@@ -29,6 +29,10 @@ typedef struct apk_sim_config {
   int fused;   /* use the fused stage kernel when legal */
   int rank, nranks;
   int plan_only; /* build mesh partition + halo plan only: no CUDA calls (CPU-side tests) */
+  /* static mesh refinement: <parthenon/static_refinementN> regions (level >= 1); nref = 0: uniform */
+  int nref;
+  int ref_level[4];
+  double ref_xmin[4][3], ref_xmax[4][3];
 } apk_sim_config_t;
 
 const char *apk_sim_last_error(void);
@@ -46,6 +50,7 @@ int apk_sim_num_global_blocks(const apk_sim_t *s);
 int apk_sim_nvar(const apk_sim_t *s);
 void apk_sim_block_dims(const apk_sim_t *s, int *n3);
 void apk_sim_block_info(const apk_sim_t *s, int b, int *gid, int *loc3, double *xmin3, double *dx3);
+int apk_sim_block_level(const apk_sim_t *s, int b);
 int apk_sim_copy_to_host(apk_sim_t *s, int field, int block, double *dst);
 int apk_sim_copy_from_host(apk_sim_t *s, int field, int block, const double *src);
 /* whole-pack async copies on the sim stream (host buffer: [nblocks][nvar][n3][n2][n1]) */

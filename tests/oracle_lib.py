@@ -62,6 +62,7 @@ def lib():
     L.apko_run.argtypes = [C.c_void_p, C.c_double, C.c_int]
     L.apko_cycle.argtypes = [C.c_void_p]
     L.apko_num_blocks.argtypes = [C.c_void_p]
+    L.apko_block_loc.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.apko_block_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     L.apko_nvar.argtypes = [C.c_void_p]
     for f in ("apko_cons", "apko_prim"):
@@ -148,6 +149,13 @@ class Oracle:
         if getattr(self, "h", None):
             self.L.apko_destroy(self.h)
             self.h = None
+
+    def block_loc(self, b):
+        """(refinement level, (lx1, lx2, lx3)) of block b"""
+        lev = C.c_int()
+        lx = (C.c_int * 3)()
+        self.L.apko_block_loc(self.h, b, C.byref(lev), lx)
+        return lev.value, tuple(lx)
 
     def pgen(self, name, pars=()):
         a = np.asarray(pars, dtype=np.float64)

@@ -24,6 +24,10 @@ def make_pair(apk, pgen="random", pgen_pars=(), tlim=float("inf"), **kw):
 
 def oracle_block(s, o, b):
     loc = s.block_info(b)[1]
+    if o.p.nref > 0:  # refined mesh: match blocks by (level, logical location)
+        if not hasattr(o, "_leaf_index"):
+            o._leaf_index = {o.block_loc(q): q for q in range(o.nblocks)}
+        return o._leaf_index[(s.block_level(b), tuple(loc))]
     nb = [o.p.nx[d] // o.p.mb[d] for d in range(3)]
     return loc[0] + nb[0] * (loc[1] + nb[1] * loc[2])
 

@@ -224,8 +224,8 @@ def test_fofc_deck_runs_like_reference_when_nothing_triggers(apk):
 
 
 # ---------------------------------------------------------------- golden known answers
-from trace_util import (DECKS, GAMMA_DECK, TRACES, check_lw_row, follow_trace, lw_kwargs,  # noqa: E402
-                        lw_pgen)
+from trace_util import (AMR_DECKS, DECKS, GAMMA_DECK, TRACES, check_lw_row, follow_trace,  # noqa: E402
+                        lw_kwargs, lw_pgen)
 
 LW_CASES = TRACES["linear_wave"] + TRACES["linear_wave_mhd"] + TRACES["linear_wave_mhd_families"]
 
@@ -277,6 +277,23 @@ def test_deck_reference_traces(apk, name):
         if name == "orszag_tang_50":
             assert s.fofc_corrections == 0 and s.fofc_redone_stages == 0
         s.close()
+
+
+@pytest.mark.parametrize("name", sorted(AMR_DECKS))
+def test_static_refinement_reference_traces(apk, name):
+    """BASELINE config 5 on a frozen refined mesh (inputs/blast_3d_amr.in with refinement = static:
+    2 and 3 levels, up to 176 meshblocks of 8^3; GLM-MHD WENOZ + HLLD with nghost = 4 is the method
+    config 5 names): multilevel ghost exchange -- restriction, coarse buffers, minmod prolongation --
+    and flux correction on the GPU reproduce the unmodified reference's (time, dt) at all 17 digits
+    for 20 cycles, and the final state equals the oracle's bit for bit."""
+    kw, pgen, pars, tlim = AMR_DECKS[name]
+    s, o = make_pair(apk, pgen, pars, tlim=tlim, fp_mode="strict", **kw)
+    assert s.nblocks == o.nblocks and not s.fused_active
+    follow_trace(s, TRACES[name]["trace"], tlim, _advance)
+    o.run(tlim, TRACES[name]["ncycle"])
+    assert (s.time, s.dt) == (o.time, o.dt)
+    assert_bitexact(s, o, name)
+    s.close()
 
 
 def _lw(apk, N, row, **kw):
