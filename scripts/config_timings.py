@@ -25,6 +25,13 @@ CASES = {
         dict(fluid="glmmhd", recon="ppm", riemann="hlld", integrator="vl2", nx=(256, 256, 1),
              mb=(64, 256, 1), ng=3, xmin=(-0.5, -0.5, -0.5), xmax=(0.5, 0.5, 0.5), gamma=5.0 / 3.0,
              cfl=0.4, fofc=True), "orszag_tang", (), 50),
+    # config 5 on a frozen 3-level mesh (176 meshblocks of 8^3, static refinement; the un-fused tasks
+    # with flux correction and the six-launch multilevel exchange)
+    "config5_blast_3d_static_3level_wenoz_hlld": (
+        dict(fluid="glmmhd", recon="wenoz", riemann="hlld", integrator="vl2", nx=(32, 32, 32),
+             mb=(8, 8, 8), ng=4, xmin=(-0.5, -0.5, -0.5), xmax=(0.5, 0.5, 0.5), gamma=5.0 / 3.0,
+             cfl=0.3, refine=[(1, (-0.2,) * 3, (0.2,) * 3), (2, (-0.1,) * 3, (0.1,) * 3)]),
+        "blast", (0.12, 0.1, 100.0, 1.0, 0.22, 0.1, -0.05), 50),
 }
 res = {}
 for name, (kw, pgen, pars, ncyc) in CASES.items():
@@ -37,7 +44,7 @@ for name, (kw, pgen, pars, ncyc) in CASES.items():
     s.execute(None, 5 + ncyc)
     s.synchronize()
     dt = time.time() - t0
-    cells = kw["nx"][0] * kw["nx"][1] * kw["nx"][2]
+    cells = s.nblocks_global * kw["mb"][0] * kw["mb"][1] * kw["mb"][2]
     res[name] = {"cycles_per_s": ncyc / dt, "cell_updates_per_s": cells * ncyc / dt,
                  "fused": s.fused_active, "us_per_cycle": 1e6 * dt / ncyc}
     s.close()
