@@ -658,7 +658,8 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
   const RsPars rsp = {d.gamma, 1.0 / (d.gamma - 1.0), c_h, 0.5 / c_h};
   const int ntx = (d.nx[0] + TX - 1) / TX;
   const int nty = (g.ndim >= 2) ? (d.nx[1] + TY - 1) / TY : 1;
-  // x3 chunks: aim for >= 16 waves of CTAs (tail < 6 %) while chunks stay >= 8 planes
+  // x3 chunks: aim for >= 16 waves of CTAs (tail < 6 %) while chunks stay >= 4 planes (measured at
+  // 64 meshblocks per GPU, the 8-GPU share of 256^3: 2 chunks 1.67 ms per cycle, 4 chunks 1.54 ms)
   const int sm_count = apk_common::sm_count();
   int nchunk = 1;
   if (g.ndim == 3) {
@@ -668,7 +669,7 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
     } else {
       const long slots = (long)sm_count * APK_FUSED_MINBLOCKS;
       while (nchunk < 8 && (long)ntx * nty * g.nb * nchunk < 16 * slots &&
-             d.nx[2] / (nchunk * 2) >= 8)
+             d.nx[2] / (nchunk * 2) >= 4)
         nchunk *= 2;
     }
   }

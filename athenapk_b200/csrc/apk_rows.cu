@@ -599,7 +599,7 @@ int run_rows(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *bloc
     } else {
       const long slots = (long)apk_common::sm_count() * APK_ROWS_MINBLOCKS;
       while (nchunk < 8 && (long)a.ntx * nty * g.nb * nchunk < 16 * slots &&
-             d.nx[2] / (nchunk * 2) >= 8)
+             d.nx[2] / (nchunk * 2) >= 4)
         nchunk *= 2;
     }
   }
