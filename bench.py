@@ -341,6 +341,13 @@ def run_product(args):
         roof["note"] = ("HBM is the contract roofline; the kernel is bound by FP64 issue and "
                         "dependency latency (fp64_frac = share of the measured DFMA issue rate)")
 
+    # state fingerprint for the parity check below, BEFORE the e2e phase reloads host states
+    total_cycles = sim.ncycle
+    hist = torch.tensor(sim.history()[:7], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    hist = hist.cpu().numpy()
+
     # ---------------- end-to-end through the public API with HOST buffers ----------------
     # Every step: pinned-host conserved state (ghosts included) -> H2D -> FillDerived (cons->prim)
     # -> one full cycle -> D2H of the updated conserved state into a pinned host buffer.
@@ -424,11 +431,6 @@ def run_product(args):
     # N > 1: rank 0 repeats the same cycles on ONE GPU; the all-reduced history sums of the
     #        partitioned run must agree with it to 1e-13 (the data path is bit-identical; only the
     #        summation order of the reducers differs).
-    total_cycles = sim.ncycle
-    hist = torch.tensor(sim.history()[:7], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
-    hist = hist.cpu().numpy()
     parity, strict = None, None
     if rank == 0 and not args.no_parity and args.config == "uni256":
         import numpy as np
