@@ -54,6 +54,15 @@ namespace {
 #ifndef APK_FUSED_TY
 #define APK_FUSED_TY 4
 #endif
+// APK_FUSED_PPM_LIST=1 (default): the recon phase evaluates only the limiter-free part of PPM
+// (recon_ppm_fastpath) in the warp tasks; the few cells that need the interface or the extremum
+// limiter go to a per-warp work list in shared memory and are re-evaluated with the full
+// recon_ppm() 32 at a time.  With the warp vote (APK_FUSED_PPM_LIST=0) one extremum makes all
+// 32 x UNROLL cells of a task pay for both limiters: on the Orszag-Tang state 56-60 % of the warp
+// tasks did, for ~2 % of the cells.  Same expressions per cell, bit-identical results.
+#ifndef APK_FUSED_PPM_LIST
+#define APK_FUSED_PPM_LIST 1
+#endif
 // APK_FUSED_TMA=1 (A/B variant, namespace apk_fast_tma, selected with APK_B200_FUSED_V=3): the halo'd
 // prim tile of the plane being swept -- (TX+6) x (TY+6) cells x all variables -- is staged in
 // shared memory by ONE cp.async.bulk.tensor (TMA, 4-D tensor map over [var][k][j][i]) per plane,
@@ -96,6 +105,10 @@ struct Smem {
   alignas(128) double tile[TMA ? NH : 1][TMA ? TY + 6 : 1][TMA ? TX + 6 : 2];
   alignas(8) unsigned long long tma_bar;
   alignas(16) ReconTask tab[(!DC && NT > 0) ? NT : 1];
+  // per-warp work list of cells that need a PPM limiter: (task << 5 | lane); a batch appends at most
+  // 32 * UNROLL entries to at most 31 left over
+  static constexpr int WL = 32 * (APK_FUSED_UNROLL + 1);
+  unsigned short wl[DC ? 1 : NWARPS][DC ? 2 : WL];
   double *push_prim[27], *push_cons[27];  // ghost-push destinations per neighbour offset (or null)
 };
 
@@ -304,6 +317,28 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
         double v[UNROLL][5];
         int sl[UNROLL], sr[UNROLL], st[UNROLL];
       };
+      constexpr bool LIST = (RECON == APK_RECON_PPM) && APK_FUSED_PPM_LIST;
+      [[maybe_unused]] int nlist = 0;  // entries in this warp's work list (warp uniform)
+      [[maybe_unused]] unsigned short *const wl = sm.wl[DC ? 0 : warp];
+      // full PPM for one listed cell per lane (entries [base, base + 32) of the list)
+      [[maybe_unused]] auto drain = [&](int base, int n) {
+        __syncwarp();
+        if (lane < n) {
+          const unsigned ent = wl[base + lane];
+          const int tr = ent >> 5, ln = ent & 31;
+          const int4 e = *reinterpret_cast<const int4 *>(&sm.tab[tr]);
+          const double *q = prim + plane + ln + e.x;
+          if constexpr (TMA) {
+            if (tr >= NZ) q = &sm.tile[0][0][0] + ln + e.x;
+          }
+          double s5[5], ql, qr;
+          load_stencil<RECON>(q, e.y & 0x0fffffff, s5);
+          recon_ppm(s5[0], s5[1], s5[2], s5[3], s5[4], ql, qr);
+          if (e.z >= 0) smd[e.z + (tr < NZ ? zoff : 0) + ln] = ql;
+          if (e.w >= 0) smd[e.w + ln] = qr;
+        }
+        __syncwarp();
+      };
       auto fetch = [&](Batch &b, int t0) {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
@@ -322,8 +357,29 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           }
         }
       };
-      auto evaluate = [&](const Batch &b) {
+      auto evaluate = [&](const Batch &b, [[maybe_unused]] int t0) {
         double qls[UNROLL], qrs[UNROLL];
+        if constexpr (LIST) {
+          const unsigned fl = recon_ppm_fastpath<UNROLL>(b.v, qls, qrs);
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) {
+            // only cells whose result is stored can be listed (flagged lanes are < txe: lane == ln)
+            const bool f = (fl >> u & 1) && (b.sl[u] >= 0 || b.sr[u] >= 0);
+            if (b.sl[u] >= 0 && !f) smd[b.sl[u] + lane] = qls[u];
+            if (b.sr[u] >= 0 && !f) smd[b.sr[u] + lane] = qrs[u];
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (bal) {
+              if (f) wl[nlist + __popc(bal & ((1u << lane) - 1u))] =
+                         (unsigned short)(((t0 + u * NWARPS) << 5) | lane);
+              nlist += __popc(bal);
+            }
+          }
+          while (nlist >= 32) {
+            nlist -= 32;
+            drain(nlist, 32);
+          }
+          return;
+        }
         if constexpr (RECON == APK_RECON_PPM && APK_FUSED_PPM_VOTE) {
           recon_ppm_warp<UNROLL>(b.v, qls, qrs);  // all 32 lanes are here: the loop is warp uniform
         } else {
@@ -347,11 +403,11 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
         while (t0 < t_end) {
           const bool more1 = t0 + STEP < t_end;
           if (more1) fetch(Bb, t0 + STEP);
-          evaluate(A);
+          evaluate(A, t0);
           if (!more1) break;
           const bool more2 = t0 + 2 * STEP < t_end;
           if (more2) fetch(A, t0 + 2 * STEP);
-          evaluate(Bb);
+          evaluate(Bb, t0 + STEP);
           t0 += 2 * STEP;
           if (!more2) break;
         }
@@ -359,8 +415,11 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
         for (int t0 = warp; t0 < t_end; t0 += STEP) {
           Batch A;
           fetch(A, t0);
-          evaluate(A);
+          evaluate(A, t0);
         }
+      }
+      if constexpr (LIST) {
+        if (nlist > 0) drain(0, nlist);
       }
       if (inplane) {
         // x1 end cells: cell -1 gives the L state of face 0, cell txe the R state of face txe
