@@ -98,13 +98,20 @@ struct Smem {
   static constexpr int RY = DC ? 1 : TY, RX = DC ? 1 : TX;  // R-state arrays collapse for DC
   double wlx[NH][TY][TX + 1], wrx[NR][RY][RX + 1];
   double wly[NH][TY + 1][TX], wry[NR][RY + 1][RX];
-  double wrz[NR][RY][RX], wlz[ZB][NH][TY][TX];
+  double wrz[NR][RY][RX];
+  // x3 L states / fluxes, double buffered.  Each buffer ends in a trash row: the destination of
+  // the stores of warp tasks without an L or R consumer (lean PPM path) -- the x3 double-buffer
+  // offset then maps the trash row of buffer 0 onto the trash row of buffer 1.
+  struct ZBuf {
+    double a[NH][TY][TX];
+    double trash[TX];
+  } wlz[ZB];
   double pl[NP][NPV][TY + 2][TX + 2];  // DC: prim planes, cells -1..TX x rows -1..TY
   // TMA variant: halo'd prim tile of the current plane, cells -3..TX+2 x rows -3..TY+2
   static constexpr bool TMA = APK_FUSED_TMA && !DC && NDIM == 3;
   alignas(128) double tile[TMA ? NH : 1][TMA ? TY + 6 : 1][TMA ? TX + 6 : 2];
   alignas(8) unsigned long long tma_bar;
-  alignas(16) ReconTask tab[(!DC && NT > 0) ? NT : 1];
+  alignas(16) ReconTask tab[(!DC && NT > 0) ? NT + 1 : 1];  // + one dummy task (lean PPM path)
   // per-warp work list of cells that need a PPM limiter: (task << 5 | lane); a batch appends at most
   // 32 * UNROLL entries to at most 31 left over
   static constexpr int WL = 32 * (APK_FUSED_UNROLL + 1);
@@ -171,7 +178,10 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   // 4 warps per scheduler there are too few warps to hide L2 latency otherwise).
   constexpr int NZ = SmemT::NZ, NX = SmemT::NX, NT = SmemT::NT;
   constexpr int UNROLL = (RECON == APK_RECON_DC) ? 4 : APK_FUSED_UNROLL;
-  constexpr int ZBUF = NH * TY * TX;  // elements between wlz[0] and wlz[1]
+  constexpr int ZBUF = NH * TY * TX + TX;  // elements between wlz[0] and wlz[1]
+  // lean recon phase (PPM with work lists, global-memory stencils): see the recon phase below
+  constexpr bool LEAN = (RECON == APK_RECON_PPM) && APK_FUSED_PPM_LIST && !TMA;
+  [[maybe_unused]] const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
   double *const smd = reinterpret_cast<double *>(smem_raw);
   if constexpr (RECON != APK_RECON_DC) {
     for (int t = threadIdx.x; t < NT; t += NTHREADS) {
@@ -194,7 +204,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       e.sl = e.sr = -1;
       if (rok) {
         if (dir == 2) {
-          e.sl = (int)(&sm.wlz[0][n][r][0] - smd);
+          e.sl = (int)(&sm.wlz[0].a[n][r][0] - smd);
           e.sr = (int)(&sm.wrz[n][r][0] - smd);
         } else if (dir == 0) {
           e.sl = (int)(&sm.wlx[n][r][1] - smd);
@@ -204,7 +214,21 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           if (r >= 0) e.sr = (int)(&sm.wry[n][r][0] - smd);
         }
       }
+      if constexpr (LEAN) {
+        // lean PPM path: pure stride, destinations as BYTE offsets in shared memory (rows without
+        // a consumer store into the trash row, so the loop body needs no destination tests)
+        const int tr8 = (int)(reinterpret_cast<unsigned char *>(&sm.wlz[0].trash[0]) - smem_raw);
+        e.stride &= 0x0fffffff;
+        e.sl = (e.sl >= 0) ? e.sl * 8 : tr8;
+        e.sr = (e.sr >= 0) ? e.sr * 8 : tr8;
+      }
       sm.tab[t] = e;
+    }
+    if constexpr (LEAN) {
+      if (threadIdx.x == 0) {
+        const int tr8 = (int)(reinterpret_cast<unsigned char *>(&sm.wlz[0].trash[0]) - smem_raw);
+        sm.tab[NT] = ReconTask{0, 1, tr8, tr8};  // what out-of-range task slots of a batch evaluate
+      }
     }
     __syncthreads();
   }
@@ -313,6 +337,115 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       // arrays of three resident CTAs, most of these loads are L2 hits (~300-600 cycles) that
       // nothing else can hide (measured 22 % of the recon phase in long_scoreboard before).
       constexpr int STEP = UNROLL * NWARPS;
+      if constexpr (LEAN) {
+        // ---- lean PPM recon: limiter-free fast path in the warp tasks, flagged cells to a per-warp
+        // work list (recon_ppm_fastpath, apk_math.cuh); stores through 32-bit shared addresses
+        int nlist = 0;  // entries in this warp's work list (warp uniform)
+        unsigned short *const wl = sm.wl[warp];
+        const unsigned zoff8 = (unsigned)zoff * 8u;
+        const unsigned lane8 = sbase + (unsigned)lane * 8u;
+        const double *pb = pbase;
+        asm volatile("" : "+l"(pb));  // keep the plane base as one 64-bit register pair
+        auto sts = [](unsigned addr, double x) {
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(x) : "memory");
+        };
+        constexpr int NEC = NH * TY * 2;  // x1 end cells: (slot, row, side)
+        // full PPM for one listed cell per lane (entries [base, base + n) of the list)
+        auto drain = [&](int base, int n) {
+          __syncwarp();
+          if (lane < n) {
+            const unsigned ent = wl[base + lane];
+            const int tr = ent >> 5, ln = ent & 31;
+            const double *q;
+            int st;
+            unsigned al, ar;
+            if (tr <= NT) {
+              const int4 e = *reinterpret_cast<const int4 *>(&sm.tab[tr]);
+              q = prim + plane + ln + e.x;
+              st = e.y;
+              al = sbase + ln * 8 + e.z + (tr < NZ ? zoff8 : 0u);
+              ar = sbase + ln * 8 + e.w;
+            } else {
+              const int ec = ((tr - NT - 1) << 5) | ln;
+              const int side = ec & 1, j = (ec >> 1) % TY, n2 = (ec >> 1) / TY;
+              q = prim + (long)var_of_slot(n2, 0) * g.ncell + plane + (long)j * sj + (side ? txe : -1);
+              st = 1;
+              const unsigned tr8 = sbase + (unsigned)(reinterpret_cast<unsigned char *>(&sm.wlz[0].trash[0]) - smem_raw);
+              al = side ? tr8 : sbase + (unsigned)(reinterpret_cast<unsigned char *>(&sm.wlx[n2][j][0]) - smem_raw);
+              ar = side ? sbase + (unsigned)(reinterpret_cast<unsigned char *>(&sm.wrx[n2][j][txe]) - smem_raw) : tr8;
+            }
+            double s5[5], ql, qr;
+            load_stencil<RECON>(q, st, s5);
+            recon_ppm(s5[0], s5[1], s5[2], s5[3], s5[4], ql, qr);
+            sts(al, ql);
+            sts(ar, qr);
+          }
+          __syncwarp();
+        };
+        for (int t0 = warp; t0 < t_end; t0 += STEP) {
+          double v[UNROLL][5], qls[UNROLL], qrs[UNROLL];
+          unsigned al[UNROLL], ar[UNROLL];
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) {
+            const int tr = t0 + u * NWARPS;
+            const int4 e = *reinterpret_cast<const int4 *>(&sm.tab[tr < t_end ? tr : NT]);
+            al[u] = lane8 + e.z + (tr < NZ ? zoff8 : 0u);
+            ar[u] = lane8 + e.w;
+            load_stencil<RECON>(pb + e.x, e.y, v[u]);
+          }
+          unsigned fl = recon_ppm_fastpath<UNROLL>(v, qls, qrs);
+          if (!lane_ok) fl = 0xffffffffu;  // lanes beyond a ragged tile neither store nor list
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) {
+            if (!(fl >> u & 1)) {
+              sts(al[u], qls[u]);
+              sts(ar[u], qrs[u]);
+            }
+          }
+          if (!lane_ok) fl = 0;
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u)
+            if (t0 + u * NWARPS >= t_end) fl &= ~(1u << u);
+          if (__any_sync(0xffffffffu, fl != 0)) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+              const bool f = fl >> u & 1;
+              const unsigned bal = __ballot_sync(0xffffffffu, f);
+              if (f) wl[nlist + __popc(bal & ((1u << lane) - 1u))] =
+                         (unsigned short)(((t0 + u * NWARPS) << 5) | lane);
+              nlist += __popc(bal);
+            }
+            while (nlist >= 32) {
+              nlist -= 32;
+              drain(nlist, 32);
+            }
+          }
+        }
+        if (inplane && warp * 32 < NEC) {
+          // x1 end cells: cell -1 gives the L state of face 0, cell txe the R state of face txe
+          const int ec = min(threadIdx.x, NEC - 1);
+          const int side = ec & 1, j = (ec >> 1) % TY, n = (ec >> 1) / TY;
+          const bool ok = threadIdx.x < NEC && j < tye;
+          const double *q = prim + (long)var_of_slot(n, 0) * g.ncell + plane + (long)min(j, tye - 1) * sj +
+                            (side ? txe : -1);
+          double v1[1][5], ql1[1], qr1[1];
+          load_stencil<RECON>(q, 1, v1[0]);
+          const bool f = recon_ppm_fastpath<1>(v1, ql1, qr1) && ok;
+          if (ok && !f) {
+            if (side) sm.wrx[n][j][txe] = qr1[0];
+            else sm.wlx[n][j][0] = ql1[0];
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, f);
+          if (f) wl[nlist + __popc(bal & ((1u << lane) - 1u))] =
+                     (unsigned short)(((NT + 1 + warp) << 5) | lane);
+          nlist += __popc(bal);
+        }
+        while (nlist > 0) {
+          const int n = min(nlist, 32);
+          nlist -= n;
+          drain(nlist, n);
+        }
+      } else {
       struct Batch {
         double v[UNROLL][5];
         int sl[UNROLL], sr[UNROLL], st[UNROLL];
@@ -350,7 +483,8 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           b.sr[u] = ok ? e.w : -1;
           b.st[u] = e.y;
           if constexpr (TMA) {
-            if (tr < NZ) load_stencil<RECON>(pbase + e.x, e.y & 0x0fffffff, b.v[u]);
+            // (the clamped task decides: on x3-only planes out-of-range slots repeat an x3 task)
+            if (min(tr, t_end - 1) < NZ) load_stencil<RECON>(pbase + e.x, e.y & 0x0fffffff, b.v[u]);
             else load_stencil<RECON>(tile + e.x, e.y & 0x0fffffff, b.v[u]);
           } else {
             load_stencil<RECON>(pbase + e.x, e.y & 0x0fffffff, b.v[u]);
@@ -435,6 +569,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
             else sm.wlx[n][j][0] = ql;
           }
         }
+      }
       }
     }
     if constexpr (RECON != APK_RECON_DC) __syncthreads();
@@ -544,9 +679,9 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
             }
           } else {
 #pragma unroll
-            for (int n = 0; n < NH; ++n) { L[n] = sm.wlz[cur][n][j][lane]; R[n] = sm.wrz[n][j][lane]; }
+            for (int n = 0; n < NH; ++n) { L[n] = sm.wlz[cur].a[n][j][lane]; R[n] = sm.wrz[n][j][lane]; }
           }
-          dst = &sm.wlz[cur][0][j][lane];
+          dst = &sm.wlz[cur].a[0][j][lane];
           dstride = TY * TX;
         }
         riemann_solve<FLUID, RS>(L, R, rsp, F);
@@ -601,7 +736,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           double d = du[v];
           if (NDIM == 3) {
             const int sz = slot_of_var(v, 2);
-            d += (a3 * sm.wlz[cur][sz][cj][ci] - a3 * fzlo[v]);
+            d += (a3 * sm.wlz[cur].a[sz][cj][ci] - a3 * fzlo[v]);
           }
           // update.cpp:135-137 / update.hpp:55
 #ifdef APK_STRICT
@@ -685,7 +820,7 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           const int sx = slot_of_var(v, 0), sy = slot_of_var(v, 1), sz = slot_of_var(v, 2);
           du[v] = (a1 * sm.wlx[sx][cj][ci + 1] - a1 * sm.wlx[sx][cj][ci]);
           du[v] += (a2 * sm.wly[sy][cj + 1][ci] - a2 * sm.wly[sy][cj][ci]);
-          fzlo[v] = sm.wlz[cur][sz][cj][ci];
+          fzlo[v] = sm.wlz[cur].a[sz][cj][ci];
         }
       }
     }
@@ -816,7 +951,7 @@ int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
   // straight-line SASS per plane overflows the 32 KB L1.5 instruction cache (ncu: 2.1 warps stalled
   // on `no_instruction` per issue against 0.11 here; profiles/r02_notes.md)
   static const char *ver = std::getenv("APK_B200_FUSED_V");
-  if (g.ndim >= 2 && ver && ver[0] == '2') {
+  if (g.ndim >= 2 && ver && (ver[0] == '2' || (ver[0] == '4' && recon != APK_RECON_DC))) {
     if (d.fluid == APK_FLUID_EULER)
       return launch_stage_rows_euler(d, g, blocks, prim_out, a, dedner_coeff, recon, s);
     return launch_stage_rows_mhd(d, g, blocks, prim_out, a, dedner_coeff, recon, s);

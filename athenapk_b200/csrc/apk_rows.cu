@@ -1,28 +1,27 @@
-// apk_rows.cu -- the row-task form of the fused stage kernel (2-D and 3-D meshes; replaces
-// K1-K3, K6, K7, K10, K11 and the ghost exchange of SURVEY.md 2.3 with one launch per stage).
+// apk_rows.cu -- the row-pass form of the fused stage kernel (2-D and 3-D meshes; replaces K1-K3,
+// K6, K7, K10, K11 and the ghost exchange of SURVEY.md 2.3 with one launch per stage).
 //
 // Same contract and the same tile decomposition as k_stage_fused (apk_fused.cu: a CTA of 4 warps
-// owns a 32 x 4 column of one meshblock and marches along x3), but the work inside a plane is cut
-// so that reconstructed states never leave the registers of the warp that consumes them and every
-// PPM interface value is computed ONCE:
-//   * warp w owns tile row w.  "row passes" (one code path, run for x3 and then x1) reconstruct
-//     all variables of the row along the pass direction, solve the Riemann problem of the row's
-//     faces straight from registers and
-//       x3: keep the flux in registers, FINISH the cells of the previous plane (flux divergence in
-//           the reference's association, low-storage update, Dedner damping, cons->prim, dt
-//           reduction, ghost push); the left state and the PPM interface value needed by the next
-//           plane wait in thread-private shared-memory slots (face k+1 is never recomputed),
-//       x1: left states come from the neighbouring lane (warp shuffle); fluxes go to shared memory.
-//   * x2 needs data of other rows: per variable one warp marches over rows -1..TY with a rolling
-//     register window (each value is loaded once instead of five times), writing L/R states to
-//     shared memory; after a barrier the x2 face rows (and the one x1 face per row that has no
-//     lane, face 32) are solved; after the second barrier the next plane starts.
-//   * PPM (ppm_simple.hpp:38-162): the limited 4th-order interface value between two cells is the
-//     same expression for both of them (apk_math.cuh, ppm_ifaces), so a lane evaluates one
-//     interface and obtains the other from its neighbour lane (x1), from the previous plane (x3)
-//     or from the previous row (x2).  Per cell and direction that is 1 interface + 1 cell part
-//     instead of 2 + 1, and the x2 sweep costs TY+3 interfaces + TY+2 cell parts per TY rows
-//     instead of 3 (TY+2) parts.
+// owns a 32 x 4 column of one meshblock and marches along x3), but the work inside a plane follows
+// OWNERSHIP instead of a task table: warp w owns tile row w, lane i owns cell i of that row for the
+// whole march.  Per plane a warp runs four steps through ONE copy of the reconstruction code and
+// ONE copy of the Riemann solver (runtime sweep direction; the loop body stays ~40 KB of SASS):
+//   step 0 (x3): reconstruct the own row along x3 -> Riemann problem of face k (left state: the
+//                previous plane's, kept in a thread-private shared-memory slot) -> the cells of
+//                plane k-1 now have all six fluxes: FINISH them (flux divergence in the reference's
+//                association, low-storage update, Dedner damping, cons->prim, dt reduction, ghost
+//                push) -- all of it warp-private, no barrier;
+//   step 1 (x1): reconstruct the own row along x1 (+ the two cells beside the row, one lane per
+//                (variable, side)) -> faces 0..31 of the row -> fx;
+//   step 2 (x2): reconstruct the own row along x2 and a share of rows -1 / TY -> __syncthreads ->
+//                face row w -> fy;
+//   step 3     : warp 2: face row TY, warp 3: the x1 face behind the last lane of every row;
+//                warps 0/1 prefetch the next plane -> __syncthreads.
+// Reconstructed states travel through warp-private staging slots (x3, x1) or the x2 arrays; no
+// (direction, variable, row) decode, two barriers per plane instead of three.
+// PPM (ppm_simple.hpp:38-162): every lane evaluates the limiter-free part (recon_ppm_fastpath);
+// cells that need the interface or the extremum limiter are appended to a per-warp work list and
+// re-evaluated with the full recon_ppm() 32 at a time before the step's Riemann solves.
 // Results are bit-identical to k_stage_fused in APK_FP_STRICT mode (same expression trees).
 // Compiled twice (APK_NS = apk_fast / apk_strict), see apk_launch.h.
 #include <cstdint>
@@ -45,18 +44,25 @@ namespace {
 constexpr int RTX = 32, RTY = 4, RNW = 4, RNT = RNW * 32;
 constexpr unsigned FULL = 0xffffffffu;
 
-template <int NH, bool PPM>
+template <int NH>
 struct RowsSmem {
+  double stL[RNW][NH][RTX];      // warp-private staging: L states of the own row's faces (x3, x1)
+  double stR[RNW][NH][RTX];      // ... R states
   double wly[NH][RTY + 1][RTX];  // x2: L states of face rows 0..TY (slot order of the x2 sweep)
   double wry[NH][RTY + 1][RTX];  // x2: R states
-  double fy[NH][RTY + 1][RTX];   // x2: fluxes
   double fx[NH][RTY][RTX + 1];   // x1: fluxes of faces 0..TX
+  double fy[NH][RTY + 1][RTX];   // x2: fluxes
   double xel[NH][RTY];           // x1: L / R state of the face behind the last lane, per row
   double xer[NH][RTY];
   double lz[NH][RTY][RTX];       // x3: L state of the next face (thread-private slot)
-  double iz[PPM ? NH : 1][RTY][RTX];  // x3: PPM interface value shared with the next plane
   double *push_prim[27], *push_cons[27];
+  // per-warp work list of cells that need a PPM limiter: kind << 9 | index << 5 | lane; a step
+  // appends at most NH own-row + 5 extra tasks of 32 cells
+  static constexpr int WL = (NH + 5) * 32;
+  unsigned short wl[RNW][WL];
 };
+static_assert(3 * (sizeof(RowsSmem<9>) + 1024) <= 233472 || APK_ROWS_MINBLOCKS < 3,
+              "three CTAs per SM must fit");
 
 struct RowsArgs {
   ApkGeom g;
@@ -72,169 +78,35 @@ struct RowsArgs {
   unsigned long long *fofc;
 };
 
-APK_DEV double shfl_d(double x, int src) { return __shfl_sync(FULL, x, src); }
-APK_DEV double shfl_up_d(double x) { return __shfl_up_sync(FULL, x, 1); }
-APK_DEV double shfl_down_d(double x) { return __shfl_down_sync(FULL, x, 1); }
-
-// Reconstruction of U consecutive variable slots N0.. of one tile row along `dir` (0: x1, lanes
-// are neighbours along the sweep; 2: x3, the march direction).  pc points at the lane's cell of
-// variable 0; every lane of the warp calls (clamped lanes compute valid duplicates).
-template <int NH, int RECON, int U, int N0>
-APK_DEV void row_recon_group(const double *__restrict__ pc, long ncell, long stride, int dir,
-                             double dxd, int lane, int last, double e_ilo, double *iz_slot,
-                             double (&ql)[NH], double (&qr)[NH]) {
-  double v[U][5];
+// U independent reconstructions per lane: q[u] points at the lane's cell, st = element stride along
+// the sweep, dl / dr = shared-memory index (in doubles) of the L / R destination or -1, ent[u] =
+// work-list code of the task (lane bits clear).  Must be called by all 32 lanes of the warp.
+template <int RECON, int U>
+APK_DEV void recon_group(double *smd, const double *const (&q)[U], int st, const int (&dl)[U],
+                         const int (&dr)[U], const int (&ent)[U], const bool (&pos)[U], double dxd,
+                         unsigned short *wl, int &nlist, int lane) {
+  double v[U][5], ql[U], qr[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u)
-    load_stencil<RECON>(pc + (long)var_of_slot(N0 + u, dir) * ncell, stride, v[u]);
+  for (int u = 0; u < U; ++u) load_stencil<RECON>(q[u], st, v[u]);
   if constexpr (RECON == APK_RECON_PPM) {
-    // x1: the lane evaluates its LOWER interface (cells i-2..i+1), the upper one is the lower one
-    //     of lane+1 (of the cell behind the tile for the last lane: e_ilo of the edge pass);
-    // x3: the lane evaluates the UPPER interface (planes k-1..k+2), the lower one was the upper
-    //     one of the previous plane (iz_slot)
-    double s4[U][4], inew[U], flo[U], fhi[U], qlg[U], qrg[U];
-    const int o = (dir == 0) ? 0 : 1;
+    const unsigned fl = recon_ppm_fastpath<U>(v, ql, qr);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      s4[u][0] = o ? v[u][1] : v[u][0];
-      s4[u][1] = o ? v[u][2] : v[u][1];
-      s4[u][2] = o ? v[u][3] : v[u][2];
-      s4[u][3] = o ? v[u][4] : v[u][3];
-    }
-    ppm_ifaces<U>(s4, inew);
-    if (dir == 0) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const double up = shfl_down_d(inew[u]);
-        const double ed = shfl_d(e_ilo, 2 * (N0 + u) + 1);
-        flo[u] = inew[u];
-        fhi[u] = (lane == last) ? ed : up;
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        double *slot = iz_slot + (N0 + u) * (RTY * RTX);
-        flo[u] = *slot;
-        fhi[u] = inew[u];
-        *slot = inew[u];
+      const bool f = (fl >> u & 1) && (dl[u] >= 0 || dr[u] >= 0);
+      if (dl[u] >= 0 && !f) smd[dl[u]] = ql[u];
+      if (dr[u] >= 0 && !f) smd[dr[u]] = qr[u];
+      const unsigned bal = __ballot_sync(FULL, f);
+      if (bal) {
+        if (f) wl[nlist + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(ent[u] | lane);
+        nlist += __popc(bal);
       }
     }
-    ppm_cells<U>(v, flo, fhi, qlg, qrg);
+  } else {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      ql[N0 + u] = qlg[u];
-      qr[N0 + u] = qrg[u];
-    }
-  } else {
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      recon_stencil<RECON>(v[u], dxd, (N0 + u == 0 || N0 + u == 4), ql[N0 + u], qr[N0 + u]);
-  }
-}
-
-template <int NH, int RECON>
-APK_DEV void row_recon(const double *__restrict__ pc, long ncell, long stride, int dir, double dxd,
-                       int lane, int last, double e_ilo, double *iz_slot, double (&ql)[NH],
-                       double (&qr)[NH]) {
-  row_recon_group<NH, RECON, 3, 0>(pc, ncell, stride, dir, dxd, lane, last, e_ilo, iz_slot, ql, qr);
-  if constexpr (NH == 9) {
-    row_recon_group<NH, RECON, 3, 3>(pc, ncell, stride, dir, dxd, lane, last, e_ilo, iz_slot, ql, qr);
-    row_recon_group<NH, RECON, 3, 6>(pc, ncell, stride, dir, dxd, lane, last, e_ilo, iz_slot, ql, qr);
-  } else {
-    row_recon_group<NH, RECON, 2, 3>(pc, ncell, stride, dir, dxd, lane, last, e_ilo, iz_slot, ql, qr);
-  }
-}
-
-// x1 edge pass: the two cells next to the tile row (cell -1 and cell txe) for all variables in
-// one warp pass, lane = 2 * variable + side.  e_ql: L state of face 0 (from cell -1); e_qr: R
-// state of face txe (from cell txe); e_ilo (PPM): lower interface of the lane's cell -- for
-// side 1 that is the upper interface of the row's last cell.  prow points at cell 0 of the row.
-template <int NH, int RECON>
-APK_DEV void row_edge(const double *__restrict__ prow, long ncell, int txe, double dx, int lane,
-                      double &e_ql, double &e_qr, double &e_ilo) {
-  const int ne = min(lane >> 1, NH - 1), side = lane & 1;
-  const double *q = prow + (long)ne * ncell + (side ? txe : -1);  // var_of_slot(n, 0) == n
-  double v[1][5];
-  load_stencil<RECON>(q, 1L, v[0]);
-  e_ilo = 0.0;
-  if constexpr (RECON == APK_RECON_PPM) {
-    double s4[2][4], f2[2], flo[1], fhi[1], qlg[1], qrg[1];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      s4[0][k] = v[0][k];
-      s4[1][k] = v[0][k + 1];
-    }
-    ppm_ifaces<2>(s4, f2);
-    flo[0] = f2[0];
-    fhi[0] = f2[1];
-    ppm_cells<1>(v, flo, fhi, qlg, qrg);
-    e_ql = qlg[0];
-    e_qr = qrg[0];
-    e_ilo = f2[0];
-  } else {
-    recon_stencil<RECON>(v[0], dx, (ne == 0 || ne == 4), e_ql, e_qr);
-  }
-}
-
-// x2 column task: U variable slots ns[] of the x2 sweep, lanes along x1, rows r = -1..tye with a
-// rolling register window; writes L states of face rows 1..tye... (ql of row r is the L state of
-// face r+1, qr of row r the R state of face r).  pcol points at the lane's cell of tile row 0 of
-// memory variable 0.
-template <int NH, int RECON, bool PPMS, int U>
-APK_DEV void col_task(const double *__restrict__ pcol, long ncell, long sj, int tye, double dx2,
-                      int lane, bool lane_ok, const int (&ns)[U], RowsSmem<NH, PPMS> &sm) {
-  constexpr int R = ReconTraits<RECON>::radius;
-  double w[U][5], flo[U];
-  const double *q[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    q[u] = pcol + (long)var_of_slot(ns[u], 1) * ncell;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) w[u][k] = 0.0;
-#pragma unroll
-    for (int d = -R; d <= R; ++d) w[u][2 + d] = q[u][(long)(-1 + d) * sj];
-    flo[u] = 0.0;
-  }
-  if constexpr (RECON == APK_RECON_PPM) {
-    double s4[U][4];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) s4[u][k] = w[u][k];
-    ppm_ifaces<U>(s4, flo);
-  }
-#pragma unroll 1
-  for (int r = -1; r <= tye; ++r) {
-    double ql[U], qr[U];
-    if constexpr (RECON == APK_RECON_PPM) {
-      double s4[U][4], fhi[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s4[u][k] = w[u][k + 1];
-      ppm_ifaces<U>(s4, fhi);
-      ppm_cells<U>(w, flo, fhi, ql, qr);
-#pragma unroll
-      for (int u = 0; u < U; ++u) flo[u] = fhi[u];
-    } else {
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        recon_stencil<RECON>(w[u], dx2, (ns[u] == 0 || ns[u] == 4), ql[u], qr[u]);
-    }
-    if (lane_ok) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (r < tye) sm.wly[ns[u]][r + 1][lane] = ql[u];
-        if (r >= 0) sm.wry[ns[u]][r][lane] = qr[u];
-      }
-    }
-    if (r < tye) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) w[u][k] = w[u][k + 1];
-        w[u][2 + R] = q[u][(long)(r + 1 + R) * sj];
-      }
+      recon_stencil<RECON>(v[u], dxd, pos[u], ql[u], qr[u]);
+      if (dl[u] >= 0) smd[dl[u]] = ql[u];
+      if (dr[u] >= 0) smd[dr[u]] = qr[u];
     }
   }
 }
@@ -243,11 +115,11 @@ template <int FLUID, int RECON, int RS, int NDIM>
 __global__ void __launch_bounds__(RNT, APK_ROWS_MINBLOCKS)
 k_stage_rows(const __grid_constant__ RowsArgs a) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
-  constexpr bool PPMS = (RECON == APK_RECON_PPM);
   constexpr int R = ReconTraits<RECON>::radius;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using SmemT = RowsSmem<NH, PPMS>;
+  using SmemT = RowsSmem<NH>;
   SmemT &sm = *reinterpret_cast<SmemT *>(smem_raw);
+  double *const smd = reinterpret_cast<double *>(smem_raw);
   const ApkGeom &g = a.g;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -256,7 +128,8 @@ k_stage_rows(const __grid_constant__ RowsArgs a) {
   const int i0 = g.is + tix * RTX, j0 = g.js + tiy * RTY;
   const int txe = min(RTX, g.ie + 1 - i0);  // valid cells of the tile in x1
   const int tye = min(RTY, g.je + 1 - j0);  // ... in x2
-  const long sj = g.n1, sk = (long)g.n1 * g.n2;
+  const int sj = g.n1;
+  const long sk = (long)g.n1 * g.n2;
   const long ncell = g.ncell;
   const double *__restrict__ prim = B.prim;
   double *__restrict__ cons = B.cons;
@@ -278,7 +151,7 @@ k_stage_rows(const __grid_constant__ RowsArgs a) {
   const int rj = warp, ci = lane;
   const bool row_ok = rj < tye, lane_ok = lane < txe;
   const bool owner = row_ok && lane_ok;
-  const int rjc = min(rj, tye - 1), lc = min(lane, txe - 1), last = txe - 1;
+  const int rjc = min(rj, tye - 1), lc = min(lane, txe - 1);
 
   const int nx3c = g.ke - g.ks + 1;
   const int kbeg = (NDIM == 3) ? g.ks + ((int)blockIdx.z * nx3c) / a.nchunk : g.ks;
@@ -310,32 +183,15 @@ k_stage_rows(const __grid_constant__ RowsArgs a) {
   for (int v = 0; v < NH; ++v) fzlo[v] = 0.0;
   double my_min = DBL_MAX;
 
-  // tile-relative base of the lane's (clamped) cell in plane 0, variable 0
-  const long cell0 = (long)(j0 + rjc) * sj + (i0 + lc);
-  double *const lz_slot = &sm.lz[0][rj][lane];
-  double *const iz_slot = &sm.iz[0][rj][lane];
-
-  if constexpr (NDIM == 3 && PPMS) {
-    // prime the carried x3 interface: lower interface of plane kfirst (planes kfirst-2..kfirst+1)
-    const double *pc = prim + (long)kfirst * sk + cell0;
-#pragma unroll 1
-    for (int n0 = 0; n0 < NH; n0 += 3) {
-      double s4[3][4], f3[3];
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int n = min(n0 + u, NH - 1);
-        const double *q = pc + (long)var_of_slot(n, 2) * ncell;
-        s4[u][0] = q[-2 * sk];
-        s4[u][1] = q[-sk];
-        s4[u][2] = q[0];
-        s4[u][3] = q[sk];
-      }
-      ppm_ifaces<3>(s4, f3);
-#pragma unroll
-      for (int u = 0; u < 3; ++u)
-        if (n0 + u < NH) iz_slot[(n0 + u) * (RTY * RTX)] = f3[u];
-    }
-  }
+  // shared-memory indices (in doubles) of the arrays
+  const int iStL = (int)(&sm.stL[warp][0][0] - smd), iStR = (int)(&sm.stR[warp][0][0] - smd);
+  const int iWly = (int)(&sm.wly[0][0][0] - smd), iWry = (int)(&sm.wry[0][0][0] - smd);
+  const int iFx = (int)(&sm.fx[0][0][0] - smd), iFy = (int)(&sm.fy[0][0][0] - smd);
+  const int iXel = (int)(&sm.xel[0][0] - smd), iXer = (int)(&sm.xer[0][0] - smd);
+  const int iLz = (int)(&sm.lz[0][0][0] - smd);
+  constexpr int VS_ST = RTX, VS_Y = (RTY + 1) * RTX, VS_FX = RTY * (RTX + 1), VS_Z = RTY * RTX;
+  unsigned short *const wl = sm.wl[warp];
+  int nlist = 0;  // entries in the warp's work list (warp uniform)
 
   // ---- finishing a cell: flux divergence, update, Dedner, cons->prim, stores, push, dt ----------
   auto finalize = [&](int kfin, const double (&fz_hi)[NH]) {
@@ -441,122 +297,223 @@ k_stage_rows(const __grid_constant__ RowsArgs a) {
     }
   };
 
+
   for (int kp = kfirst; kp <= klast; ++kp) {
     const bool inplane = (kp >= kbeg && kp <= kend);
-    const long plane = (long)kp * sk;
-    // ------------------------------------------------------------------ phase A: row passes
-#pragma unroll 1
-    for (int pass = (NDIM == 3) ? 0 : 1; pass < 2; ++pass) {
-      const int dir = pass ? 0 : 2;
-      if (pass == 1 && !inplane) break;
-      if (!row_ok) continue;  // warp-uniform: rows beyond a ragged tile
-      const double *pc = prim + plane + cell0;
-      double e_ql = 0.0, e_qr = 0.0, e_ilo = 0.0;
-      if (dir == 0)
-        row_edge<NH, RECON>(prim + plane + (long)(j0 + rj) * sj + i0, ncell, txe, dx1, lane, e_ql,
-                            e_qr, e_ilo);
-      double ql[NH], qr[NH];
-      row_recon<NH, RECON>(pc, ncell, dir == 0 ? 1L : sk, dir, dir == 0 ? dx1 : dx3, lane, last,
-                           e_ilo, iz_slot, ql, qr);
-      double L[NH], F[NH];
+    const double *const pplane = prim + (long)kp * sk;
+    // own-row task of step `step` (sweep direction dir), slot n, for lane ln (< txe)
+    auto row_task = [&](int dir, int n, int ln, const double *&q, int &dl, int &dr) {
+      q = pplane + (long)var_of_slot(n, dir) * ncell + (long)(j0 + rjc) * sj + (i0 + ln);
+      if (dir == 2) {
+        dl = iStL + n * VS_ST + ln;
+        dr = iStR + n * VS_ST + ln;
+      } else if (dir == 0) {
+        // ql of cell c is the L state of face c+1 (the face behind the last cell has no lane)
+        dl = (ln == txe - 1) ? iXel + n * RTY + rj : iStL + n * VS_ST + ln + 1;
+        dr = iStR + n * VS_ST + ln;
+      } else {
+        dl = iWly + n * VS_Y + (rj + 1) * RTX + ln;
+        dr = iWry + n * VS_Y + rj * RTX + ln;
+      }
+    };
+    // extra task m of the step for lane ln.  x1 (dir 0), m == 0: the two cells beside the own row,
+    // lane = 2 * slot + side; x2 (dir 1): rows -1 and tye of slot (warp + 4 m) >> 1
+    auto misc_task = [&](int dir, int m, int ln, const double *&q, int &st, int &dl, int &dr) {
+      dl = dr = -1;
       if (dir == 0) {
-#pragma unroll
-        for (int n = 0; n < NH; ++n) {
-          const double up = shfl_up_d(ql[n]);
-          const double ed = shfl_d(e_ql, 2 * n);
-          L[n] = (lane == 0) ? ed : up;
-          if (lane == last) sm.xel[n][rj] = ql[n];
+        const int n = min(ln >> 1, NH - 1), side = ln & 1;
+        q = pplane + (long)n * ncell + (long)(j0 + rjc) * sj + (i0 + (side ? txe : -1));
+        st = 1;
+        if (ln < 2 * NH) {
+          if (side == 0) dl = iStL + n * VS_ST;          // L state of face 0
+          else dr = iXer + n * RTY + rj;                  // R state of face txe
         }
-        if (lane < 2 * NH && (lane & 1)) sm.xer[lane >> 1][rj] = e_qr;
       } else {
-#pragma unroll
-        for (int n = 0; n < NH; ++n) {
-          L[n] = lz_slot[n * (RTY * RTX)];
-          lz_slot[n * (RTY * RTX)] = ql[n];
+        const int e = warp + 4 * m, n = min(e >> 1, NH - 1), which = e & 1;
+        q = pplane + (long)var_of_slot(n, 1) * ncell + (long)(j0 + (which ? tye : -1)) * sj +
+            (i0 + min(ln, txe - 1));
+        st = sj;
+        if (e < 2 * NH && ln < txe) {
+          if (which == 0) dl = iWly + n * VS_Y + ln;      // L state of face row 0
+          else dr = iWry + n * VS_Y + tye * RTX + ln;     // R state of face row tye
         }
       }
-      if (dir == 0 || kp >= kbeg) {
-        riemann_solve<FLUID, RS>(L, qr, a.rsp, F);
-        if (dir == 0) {
-          if (lane_ok) {
-#pragma unroll
-            for (int n = 0; n < NH; ++n) sm.fx[n][rj][lane] = F[n];
+    };
+    const int s0 = (NDIM == 3) ? 0 : 1, s1 = inplane ? 4 : 1;
+#pragma unroll 1
+    for (int step = s0; step < s1; ++step) {
+      const int dir = (step == 0) ? 2 : (step == 1 ? 0 : 1);
+      // ------------------------------------------------------------------ reconstruction
+      if (step < 3) {
+        const int st = (dir == 0) ? 1 : (dir == 1 ? sj : (int)sk);
+        const double dxd = (dir == 0) ? dx1 : (dir == 1 ? dx2 : dx3);
+        if (row_ok) {
+          const double *q0;
+          int dl0, dr0, dl1, dr1;
+          row_task(dir, 0, lc, q0, dl0, dr0);
+          row_task(dir, 1, lc, q0, dl1, dr1);   // q0 is reset below; dl1 - dl0 = variable stride
+          const int dls = dl1 - dl0, drs = dr1 - dr0;
+          q0 = pplane + (long)(j0 + rjc) * sj + (i0 + lc);
+          const long o1 = (long)(1 + dir) * ncell, o2 = (long)(1 + (dir + 1) % 3) * ncell,
+                     o3 = (long)(1 + (dir + 2) % 3) * ncell;
+          auto D = [&](int base, int vs, int n) { return lane_ok ? base + n * vs : -1; };
+          if constexpr (NH == 9) {
+            {
+              const double *const q[3] = {q0, q0 + 4 * ncell, q0 + 8 * ncell};
+              const int dl[3] = {D(dl0, dls, 0), D(dl0, dls, 4), D(dl0, dls, 8)};
+              const int dr[3] = {D(dr0, drs, 0), D(dr0, drs, 4), D(dr0, drs, 8)};
+              const int ent[3] = {0 << 5, 4 << 5, 8 << 5};
+              const bool pos[3] = {true, true, false};
+              recon_group<RECON, 3>(smd, q, st, dl, dr, ent, pos, dxd, wl, nlist, lane);
+            }
+            {
+              const double *const q[3] = {q0 + o1, q0 + o2, q0 + o3};
+              const int dl[3] = {D(dl0, dls, 1), D(dl0, dls, 2), D(dl0, dls, 3)};
+              const int dr[3] = {D(dr0, drs, 1), D(dr0, drs, 2), D(dr0, drs, 3)};
+              const int ent[3] = {1 << 5, 2 << 5, 3 << 5};
+              const bool pos[3] = {false, false, false};
+              recon_group<RECON, 3>(smd, q, st, dl, dr, ent, pos, dxd, wl, nlist, lane);
+            }
+            {
+              const double *const q[3] = {q0 + o1 + 4 * ncell, q0 + o2 + 4 * ncell, q0 + o3 + 4 * ncell};
+              const int dl[3] = {D(dl0, dls, 5), D(dl0, dls, 6), D(dl0, dls, 7)};
+              const int dr[3] = {D(dr0, drs, 5), D(dr0, drs, 6), D(dr0, drs, 7)};
+              const int ent[3] = {5 << 5, 6 << 5, 7 << 5};
+              const bool pos[3] = {false, false, false};
+              recon_group<RECON, 3>(smd, q, st, dl, dr, ent, pos, dxd, wl, nlist, lane);
+            }
+          } else {
+            {
+              const double *const q[2] = {q0, q0 + 4 * ncell};
+              const int dl[2] = {D(dl0, dls, 0), D(dl0, dls, 4)};
+              const int dr[2] = {D(dr0, drs, 0), D(dr0, drs, 4)};
+              const int ent[2] = {0 << 5, 4 << 5};
+              const bool pos[2] = {true, true};
+              recon_group<RECON, 2>(smd, q, st, dl, dr, ent, pos, dxd, wl, nlist, lane);
+            }
+            {
+              const double *const q[3] = {q0 + o1, q0 + o2, q0 + o3};
+              const int dl[3] = {D(dl0, dls, 1), D(dl0, dls, 2), D(dl0, dls, 3)};
+              const int dr[3] = {D(dr0, drs, 1), D(dr0, drs, 2), D(dr0, drs, 3)};
+              const int ent[3] = {1 << 5, 2 << 5, 3 << 5};
+              const bool pos[3] = {false, false, false};
+              recon_group<RECON, 3>(smd, q, st, dl, dr, ent, pos, dxd, wl, nlist, lane);
+            }
           }
-        } else {
-          // the cells of plane kp-1 now have all six fluxes (fx / fy of plane kp-1 are still in
-          // shared memory: this warp overwrites its fx row only in the x1 pass below, fy is
-          // rewritten after the next barrier)
-          if (lane_ok && kp - 1 >= kbeg) finalize(kp - 1, F);
-#pragma unroll
-          for (int n = 0; n < NH; ++n) fzlo[n] = F[n];
+        }
+        // extra tasks, two at a time
+        const int nmisc = (step == 1) ? (row_ok ? 1 : 0) : (step == 2 ? (2 * NH - warp + 3) / 4 : 0);
+#pragma unroll 1
+        for (int m0 = 0; m0 < nmisc; m0 += 2) {
+          const double *qa, *qb;
+          int sta, stb, dla, dra, dlb, drb;
+          misc_task(dir, m0, lane, qa, sta, dla, dra);
+          misc_task(dir, min(m0 + 1, nmisc - 1), lane, qb, stb, dlb, drb);
+          if (m0 + 1 >= nmisc) dlb = drb = -1;
+          const double *const q[2] = {qa, qb};
+          const int dl[2] = {dla, dlb}, dr[2] = {dra, drb};
+          const int ent[2] = {(1 << 9) | (m0 << 5), (1 << 9) | ((m0 + 1) << 5)};
+          // positivity (LimO3): slots 0 and 4 (density, pressure)
+          const int na = (dir == 0) ? (lane >> 1) : ((warp + 4 * m0) >> 1);
+          const int nb = (dir == 0) ? (lane >> 1) : ((warp + 4 * (m0 + 1)) >> 1);
+          const bool pos[2] = {na == 0 || na == 4, nb == 0 || nb == 4};
+          recon_group<RECON, 2>(smd, q, sta, dl, dr, ent, pos, dxd, wl, nlist, lane);
+        }
+        if constexpr (RECON == APK_RECON_PPM) {
+          // the cells that need a limiter: full PPM, one cell per lane
           __syncwarp();
+#pragma unroll 1
+          for (int b = 0; b < nlist; b += 32) {
+            if (b + lane < nlist) {
+              const unsigned e = wl[b + lane];
+              const int ln = e & 31, idx = (e >> 5) & 15;
+              const double *q;
+              int es = st, dl, dr;
+              if (e >> 9) misc_task(dir, idx, ln, q, es, dl, dr);
+              else row_task(dir, idx, ln, q, dl, dr);
+              double s5[5], ql, qr;
+              load_stencil<RECON>(q, es, s5);
+              recon_ppm(s5[0], s5[1], s5[2], s5[3], s5[4], ql, qr);
+              if (dl >= 0) smd[dl] = ql;
+              if (dr >= 0) smd[dr] = qr;
+            }
+          }
+          nlist = 0;
         }
+        __syncwarp();
       }
-    }
-    if (inplane) {
-      // ---------------------------------------------------------------- phase A: x2 columns
-      const double *pcol = prim + plane + (long)j0 * sj + (i0 + lc);
-      if constexpr (NH == 9) {
-        if (warp == 0) {
-          const int ns[3] = {0, 4, 8};
-          col_task<NH, RECON, PPMS, 3>(pcol, ncell, sj, tye, dx2, lane, lane_ok, ns, sm);
-        } else {
-          const int ns[2] = {warp, warp + 4};
-          col_task<NH, RECON, PPMS, 2>(pcol, ncell, sj, tye, dx2, lane, lane_ok, ns, sm);
-        }
+      if (step == 2) __syncthreads();  // the x2 states (and the x1 edge states) of all rows are in place
+      // ------------------------------------------------------------------ Riemann problems
+      bool act, fst = lane_ok;
+      int Li, Ls, Ri, Rs, Fi = 0, Fs = 0;
+      if (step == 0) {
+        act = row_ok;
+        Li = iLz + rj * RTX + lane; Ls = VS_Z;
+        Ri = iStR + lc; Rs = VS_ST;
+      } else if (step == 1) {
+        act = row_ok;
+        Li = iStL + lc; Ls = VS_ST;
+        Ri = iStR + lc; Rs = VS_ST;
+        Fi = iFx + rj * (RTX + 1) + lane; Fs = VS_FX;
       } else {
-        if (warp == 0) {
-          const int ns[2] = {0, 4};
-          col_task<NH, RECON, PPMS, 2>(pcol, ncell, sj, tye, dx2, lane, lane_ok, ns, sm);
-        } else {
-          const int ns[1] = {warp};
-          col_task<NH, RECON, PPMS, 1>(pcol, ncell, sj, tye, dx2, lane, lane_ok, ns, sm);
+        const int r = (step == 2) ? warp : RTY;
+        act = (step == 2) ? (warp <= tye) : (warp == 2 && tye == RTY);
+        Li = iWly + r * RTX + lc; Ls = VS_Y;
+        Ri = iWry + r * RTX + lc; Rs = VS_Y;
+        Fi = iFy + r * RTX + lane; Fs = VS_Y;
+        if (step == 3 && warp == 3) {  // the x1 faces behind the last lane, lane = tile row
+          const int le = min(lane, tye - 1);
+          act = true;
+          Li = iXel + le; Ls = RTY;
+          Ri = iXer + le; Rs = RTY;
+          Fi = iFx + lane * (RTX + 1) + txe; Fs = VS_FX;
+          fst = lane < tye;
         }
       }
-      __syncthreads();
-      // ---------------------------------------------------------------- phase B: x2 faces + x1 edge
-      if constexpr (APK_ROWS_PREFETCH && NDIM == 3) {
-        // pull the lines the next row passes touch for the first time into L1: the new top plane
-        // of the x3 stencils (kp+1+R) of this warp's row
-        if (row_ok && kp + 1 <= klast) {
-          const double *pn = prim + (long)(kp + 1 + R) * sk + (long)(j0 + rj) * sj + i0;
-          for (int p = lane; p < NH * 3; p += 32) {
-            const int vv = p / 3, seg = p % 3;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + (long)vv * ncell +
+      if (act) {
+        double L[NH], Rr[NH], F[NH];
+#pragma unroll
+        for (int n = 0; n < NH; ++n) {
+          L[n] = smd[Li + n * Ls];
+          Rr[n] = smd[Ri + n * Rs];
+        }
+        if (step == 0) {
+          // the L state of the next x3 face replaces the one just read (thread-private slot)
+#pragma unroll
+          for (int n = 0; n < NH; ++n) smd[Li + n * Ls] = smd[iStL + lc + n * VS_ST];
+        }
+        if (step != 0 || kp >= kbeg) {
+          riemann_solve<FLUID, RS>(L, Rr, a.rsp, F);
+          if (step == 0) {
+            // the cells of plane kp-1 now have all six fluxes (fx / fy of plane kp-1 are still in
+            // shared memory: fx is rewritten in step 1, fy after the next barrier)
+            if (lane_ok && kp - 1 >= kbeg) finalize(kp - 1, F);
+#pragma unroll
+            for (int n = 0; n < NH; ++n) fzlo[n] = F[n];
+          } else if (fst) {
+#pragma unroll
+            for (int n = 0; n < NH; ++n) smd[Fi + n * Fs] = F[n];
+          }
+        }
+      } else if (step == 3 && APK_ROWS_PREFETCH && NDIM == 3 && warp < 2) {
+        // idle warps pull what the next plane touches for the first time into L1: warp 0 the new
+        // top plane of the x3 stencils (kp+1+R), warp 1 the x2 halo rows of plane kp+1
+        if (kp + 1 <= klast) {
+          const int nrow = (warp == 0) ? tye : 2 * (R + 1);
+          const long pl = (warp == 0) ? (long)(kp + 1 + R) * sk : (long)(kp + 1) * sk;
+          for (int p = lane; p < NH * nrow * 3; p += 32) {
+            const int seg = p % 3, rv = p / 3, rr = rv % nrow, vv = rv / nrow;
+            const int jj = (warp == 0) ? rr : (rr <= R ? rr - (R + 1) : tye + rr - (R + 1));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(prim + (long)vv * ncell + pl +
+                                                         (long)(j0 + jj) * sj + i0 +
                                                          min(seg * 16, txe - 1)));
           }
         }
       }
-#pragma unroll 1
-      for (int q = 0; q < 2; ++q) {
-        // tasks: face rows 0..3 on warps 0..3, then face row 4 on warp 2 and the x1 edge faces
-        // (one per tile row, lanes = rows) on warp 3
-        const bool edge = (q == 1 && warp == 3);
-        const int r = (q == 0) ? warp : RTY;
-        if (q == 1 && warp < 2) break;
-        if (!edge && r > tye) continue;
-        double L[NH], Rr[NH], F[NH];
-        const int le = min(lane, tye - 1);
-#pragma unroll
-        for (int n = 0; n < NH; ++n) {
-          L[n] = edge ? sm.xel[n][le] : sm.wly[n][r][lc];
-          Rr[n] = edge ? sm.xer[n][le] : sm.wry[n][r][lc];
-        }
-        riemann_solve<FLUID, RS>(L, Rr, a.rsp, F);
-        if (edge) {
-          if (lane < tye) {
-#pragma unroll
-            for (int n = 0; n < NH; ++n) sm.fx[n][lane][txe] = F[n];
-          }
-        } else if (lane_ok) {
-#pragma unroll
-          for (int n = 0; n < NH; ++n) sm.fy[n][r][lane] = F[n];
-        }
-      }
-      __syncthreads();
-      if constexpr (NDIM == 2) {
-        if (owner) finalize(kp, fzlo);
-      }
+      if (step == 3) __syncthreads();
+    }
+    if constexpr (NDIM == 2) {
+      if (owner) finalize(kp, fzlo);
     }
   }
   if (a.dtmin) {
@@ -571,8 +528,7 @@ template <int FLUID, int RECON, int RS>
 int run_rows(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
              double *const *prim_out, const apk_stage_args_t &sa, double coeff, cudaStream_t s) {
   constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
-  constexpr bool PPMS = (RECON == APK_RECON_PPM);
-  RowsArgs a;
+    RowsArgs a;
   a.g = g;
   a.blocks = blocks;
   a.prim_out = prim_out;
@@ -605,7 +561,7 @@ int run_rows(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *bloc
   }
   a.nchunk = nchunk;
   dim3 grid(a.ntx * nty, g.nb, nchunk);
-  const size_t smem = sizeof(RowsSmem<NH, PPMS>);
+  const size_t smem = sizeof(RowsSmem<NH>);
   const int dev = apk_common::current_device();
 #define APK_LAUNCH_ROWS(ND)                                                                    \
   {                                                                                            \
