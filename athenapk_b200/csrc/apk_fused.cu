@@ -315,6 +315,33 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
   }
+  // prefetch targets of a plane (see the Riemann phase): one 128 B line each, decoded once --
+  // the rows of plane pn + R the x3 stencils touch for the first time and the halo rows / columns
+  // of plane pn itself; element offsets relative to prim + pn * sk (negative: none)
+  constexpr int PFN = 4;
+  [[maybe_unused]] int pf_off[PFN];
+  [[maybe_unused]] unsigned pf_zrow = 0;
+  if constexpr (RECON != APK_RECON_DC && APK_FUSED_PREFETCH) {
+    constexpr int R = ReconTraits<RECON>::radius;
+    const int nzr = (NDIM == 3) ? tye : 0;                          // rows of plane pn+R
+    const int nyr = TMA ? 0 : (NDIM >= 2 ? tye + 2 + 2 * R : 1);    // rows of plane pn
+    const int ylo = (NDIM >= 2) ? -1 - R : 0;
+    const int nrow = nzr + nyr;
+    const int lo = -(1 + R), hi = txe + R;                          // cell range along x1 (inclusive)
+    const int nseg = ((hi - lo + 1) * 8 + 127) / 128 + 1;
+#pragma unroll
+    for (int i = 0; i < PFN; ++i) {
+      const int p = threadIdx.x + i * NTHREADS;
+      pf_off[i] = -1;
+      if (p < NH * nrow * nseg) {
+        const int seg = p % nseg, rv = p / nseg, rr = rv % nrow, v = rv / nrow;
+        const long row = (rr < nzr) ? (long)R * sk + (long)(j0 + rr) * sj
+                                    : (long)(j0 + ylo + (rr - nzr)) * sj;
+        pf_off[i] = (int)((long)v * g.ncell + row + i0 + min(lo + seg * 16, hi));
+        if (rr < nzr) pf_zrow |= 1u << i;
+      }
+    }
+  }
   int cur = 0;
   for (int kp = kfirst; kp <= klast; ++kp) {
     const bool inplane = (kp >= kbeg && kp <= kend);
@@ -393,23 +420,20 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
             ar[u] = lane8 + e.w;
             load_stencil<RECON>(pb + e.x, e.y, v[u]);
           }
-          unsigned fl = recon_ppm_fastpath<UNROLL>(v, qls, qrs);
-          if (!lane_ok) fl = 0xffffffffu;  // lanes beyond a ragged tile neither store nor list
+          bool fl[UNROLL];
+          bool any = recon_ppm_fastpath<UNROLL>(v, qls, qrs, fl);
+          // (lanes beyond a ragged tile and out-of-range task slots neither store nor list)
 #pragma unroll
           for (int u = 0; u < UNROLL; ++u) {
-            if (!(fl >> u & 1)) {
+            if (lane_ok && !fl[u]) {
               sts(al[u], qls[u]);
               sts(ar[u], qrs[u]);
             }
           }
-          if (!lane_ok) fl = 0;
-#pragma unroll
-          for (int u = 0; u < UNROLL; ++u)
-            if (t0 + u * NWARPS >= t_end) fl &= ~(1u << u);
-          if (__any_sync(0xffffffffu, fl != 0)) {
+          if (__any_sync(0xffffffffu, any && lane_ok)) {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-              const bool f = fl >> u & 1;
+              const bool f = fl[u] && lane_ok && (t0 + u * NWARPS < t_end);
               const unsigned bal = __ballot_sync(0xffffffffu, f);
               if (f) wl[nlist + __popc(bal & ((1u << lane) - 1u))] =
                          (unsigned short)(((t0 + u * NWARPS) << 5) | lane);
@@ -430,7 +454,8 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
                             (side ? txe : -1);
           double v1[1][5], ql1[1], qr1[1];
           load_stencil<RECON>(q, 1, v1[0]);
-          const bool f = recon_ppm_fastpath<1>(v1, ql1, qr1) && ok;
+          bool f1[1];
+          const bool f = recon_ppm_fastpath<1>(v1, ql1, qr1, f1) && ok;
           if (ok && !f) {
             if (side) sm.wrx[n][j][txe] = qr1[0];
             else sm.wlx[n][j][0] = ql1[0];
@@ -494,11 +519,12 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       auto evaluate = [&](const Batch &b, [[maybe_unused]] int t0) {
         double qls[UNROLL], qrs[UNROLL];
         if constexpr (LIST) {
-          const unsigned fl = recon_ppm_fastpath<UNROLL>(b.v, qls, qrs);
+          bool fl[UNROLL];
+          recon_ppm_fastpath<UNROLL>(b.v, qls, qrs, fl);
 #pragma unroll
           for (int u = 0; u < UNROLL; ++u) {
             // only cells whose result is stored can be listed (flagged lanes are < txe: lane == ln)
-            const bool f = (fl >> u & 1) && (b.sl[u] >= 0 || b.sr[u] >= 0);
+            const bool f = fl[u] && (b.sl[u] >= 0 || b.sr[u] >= 0);
             if (b.sl[u] >= 0 && !f) smd[b.sl[u] + lane] = qls[u];
             if (b.sr[u] >= 0 && !f) smd[b.sr[u] + lane] = qrs[u];
             const unsigned bal = __ballot_sync(0xffffffffu, f);
@@ -585,22 +611,16 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
       // if plane kp+1 is swept in x1/x2, its halo rows/columns (one prefetch per 128 B line;
       // ~2 per thread).  Measured before: 19 % of the recon loop was spent waiting for these
       // L2/HBM misses (first use after the stencil loads).
-      constexpr int R = ReconTraits<RECON>::radius;
       const int pn = kp + 1;
       if (pn <= klast) {
+        // (line offsets relative to plane pn were decoded once per CTA: pf_off)
+        const double *pl = prim + (long)pn * sk;
         const bool next_in = (pn >= kbeg && pn <= kend);
-        const int nzr = (NDIM == 3) ? tye : 0;                // rows of plane pn+R (x3 stencil top)
-        const int nyr = (next_in && !TMA) ? (NDIM >= 2 ? tye + 2 + 2 * R : 1) : 0;  // rows of plane pn
-        const int ylo = (NDIM >= 2) ? -1 - R : 0;
-        const int nrow = nzr + nyr;
-        const int lo = -(1 + R), hi = txe + R;                // cell range along x1 (inclusive)
-        const int nseg = ((hi - lo + 1) * 8 + 127) / 128 + 1;
-        for (int p = threadIdx.x; p < NH * nrow * nseg; p += NTHREADS) {
-          const int seg = p % nseg, rv = p / nseg, rr = rv % nrow, v = rv / nrow;
-          const long row = (rr < nzr) ? (long)(pn + R) * sk + (long)(j0 + rr) * sj
-                                      : (long)pn * sk + (long)(j0 + ylo + (rr - nzr)) * sj;
-          const int c = min(lo + seg * 16, hi);
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(prim + (long)v * g.ncell + row + i0 + c));
+#pragma unroll
+        for (int i = 0; i < PFN; ++i) {
+          // x3 stencil rows always; halo rows of the plane itself only if it is swept in x1 / x2
+          if (pf_off[i] >= 0 && (next_in || (pf_zrow >> i & 1)))
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + pf_off[i]));
         }
       }
     }

@@ -89,10 +89,11 @@ APK_DEV void recon_group(double *smd, const double *const (&q)[U], int st, const
 #pragma unroll
   for (int u = 0; u < U; ++u) load_stencil<RECON>(q[u], st, v[u]);
   if constexpr (RECON == APK_RECON_PPM) {
-    const unsigned fl = recon_ppm_fastpath<U>(v, ql, qr);
+    bool fl[U];
+    recon_ppm_fastpath<U>(v, ql, qr, fl);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const bool f = (fl >> u & 1) && (dl[u] >= 0 || dr[u] >= 0);
+      const bool f = fl[u] && (dl[u] >= 0 || dr[u] >= 0);
       if (dl[u] >= 0 && !f) smd[dl[u]] = ql[u];
       if (dr[u] >= 0 && !f) smd[dr[u]] = qr[u];
       const unsigned bal = __ballot_sync(FULL, f);
