@@ -296,16 +296,36 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   // plane needed by iteration k+1 is requested at the start of iteration k and has the whole
   // iteration to land: the Riemann tasks then read L/R from shared memory instead of issuing 18
   // long-latency global loads per face (3.3 faces per cell, every value fetched ~6 times).
+  // (element slots of one variable's halo'd plane are decoded once per thread: in-plane source
+  //  offset and destination index; per plane and variable a slot then costs one address + cp.async)
+  constexpr int SP_ROWS = (NDIM >= 2) ? TY + 2 : 1, SP_PER = SP_ROWS * (TX + 2);
+  constexpr int SP_N = DC ? (SP_PER + NTHREADS - 1) / NTHREADS : 1;
+  [[maybe_unused]] int sp_src[SP_N], sp_dst[SP_N];
+  if constexpr (DC) {
+#pragma unroll
+    for (int q = 0; q < SP_N; ++q) {
+      const int e = threadIdx.x + q * NTHREADS;
+      const int r = e / (TX + 2), c = e % (TX + 2);
+      const int jj = (NDIM >= 2) ? min(r - 1, tye) : 0, ii = min(c - 1, txe);
+      sp_src[q] = (j0 + jj) * (int)sj + (i0 + ii);
+      sp_dst[q] = (e < SP_PER) ? ((NDIM >= 2) ? r : 1) * (TX + 2) + c : -1;
+    }
+  }
   auto stage_plane = [&](int k) {
     if constexpr (DC) {
-      constexpr int ROWS = (NDIM >= 2) ? TY + 2 : 1, PER = ROWS * (TX + 2);
       const int buf = k % 3;
-      for (int e = threadIdx.x; e < NH * PER; e += NTHREADS) {
-        const int v = e / PER, r = (e % PER) / (TX + 2), c = e % (TX + 2);
-        const int jj = (NDIM >= 2) ? min(r - 1, tye) : 0, ii = min(c - 1, txe);
-        const double *src = prim + (long)v * g.ncell + (long)k * sk + (long)(j0 + jj) * sj + (i0 + ii);
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.pl[buf][v][(NDIM >= 2) ? r : 1][c]);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+      const double *src = prim + (long)k * sk;
+      const unsigned dst0 = (unsigned)__cvta_generic_to_shared(&sm.pl[buf][0][0][0]);
+#pragma unroll
+      for (int v = 0; v < NH; ++v) {
+#pragma unroll
+        for (int q = 0; q < SP_N; ++q) {
+          if (sp_dst[q] >= 0) {
+            const unsigned dst = dst0 + (unsigned)(v * (TY + 2) * (TX + 2) + sp_dst[q]) * 8u;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst),
+                         "l"(src + (long)v * g.ncell + sp_src[q]) : "memory");
+          }
+        }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
