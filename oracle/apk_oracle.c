@@ -909,6 +909,7 @@ void apko_riemann_face(int fluid, int solver, int ivx, const double *wl, const d
 
 typedef struct {
   double *cons, *prim, *u1, *flux[3];
+  double *my0, *yjm2; /* RKL2 registers "MY0", "Yjm2" (hydro_driver.cpp:211-212) */
   double xmin[3]; /* coords xmin_ (incl. ghost offset), uniform_coordinates.hpp:32-36 */
   double dx[3];
   double bxmin[3], bxmax[3]; /* physical block bounds */
@@ -940,6 +941,8 @@ struct apko_engine {
   double c_h, mindx, dt_hyp;
   double new_dt; /* allowed dt voted by the last EstimateTimestep */
   long long fofc_total;
+  double dt_diff; /* "dt_diff" Param (hydro.cpp:700, 961-962) */
+  int last_s_rkl;
   /* linear wave pgen state (linear_wave.cpp:43-51) */
   struct {
     int set, wave_flag;
@@ -971,6 +974,9 @@ void apko_default_params(apko_params *p) {
   p->dfloor = p->pfloor = p->efloor = -1.0; /* hydro.cpp:507-510 */
   p->vceil = p->eceil = INFINITY;           /* hydro.cpp:525-529 */
   p->glmmhd_alpha = 0.1;                    /* hydro.cpp:295 */
+  p->cfl_diff = -1.0;
+  p->rkl2_max_dt_ratio = -1.0;              /* hydro.cpp:688 */
+  p->conduction_sat_phi = 0.3;              /* hydro.cpp:563-564 */
 }
 
 /* mesh/forest/logical_location.cpp:61-74 */
@@ -1286,6 +1292,10 @@ apko_engine *apko_create(const apko_params *p) {
     B->cons = (double *)calloc(nfield, sizeof(double));
     B->prim = (double *)calloc(nfield, sizeof(double));
     B->u1 = (double *)calloc(nfield, sizeof(double));
+    if (p->diffint == 2) { /* RKL2 registers "MY0", "Yjm2" (hydro_driver.cpp:211-212) */
+      B->my0 = (double *)calloc(nfield, sizeof(double));
+      B->yjm2 = (double *)calloc(nfield, sizeof(double));
+    }
     for (int d = 0; d < 3; ++d) B->flux[d] = (double *)calloc(nfield, sizeof(double));
     if (leaves) {
       B->level = leaves[b].level;
@@ -1326,6 +1336,8 @@ void apko_destroy(apko_engine *e) {
     free(e->blk[b].cons);
     free(e->blk[b].prim);
     free(e->blk[b].u1);
+    free(e->blk[b].my0);
+    free(e->blk[b].yjm2);
     free(e->blk[b].coarse);
     for (int d = 0; d < 3; ++d) free(e->blk[b].flux[d]);
   }
@@ -1416,6 +1428,7 @@ void apko_calc_fluxes(apko_engine *e, int recon) {
               face_flux(e, B, d, k, j, i, wl, wr);
             }
     }
+    if (e->p.diffint == 1) apko_calc_diff_fluxes(e); /* hydro.cpp:1202-1205 */
     return;
   }
   const int n1 = e->n[0];
@@ -1471,6 +1484,7 @@ void apko_calc_fluxes(apko_engine *e, int recon) {
     }
   }
   free(wl);
+  if (e->p.diffint == 1) apko_calc_diff_fluxes(e); /* hydro.cpp:1202-1205 */
 }
 
 /* ===================================================================================== */
@@ -1888,6 +1902,395 @@ void apko_cons_to_prim(apko_engine *e) {
 }
 
 /* ===================================================================================== */
+/* Diffusion: src/hydro/diffusion/{conduction,viscosity,resistivity}.cpp (fixed            */
+/* coefficients), ResetFluxes / RKL2 super time stepping of src/hydro/hydro_driver.cpp     */
+/* ===================================================================================== */
+#define PR(n, k, j, i) B->prim[IDX(e, n, k, j, i)]
+#define FX(d, n, k, j, i) B->flux[d][IDX(e, n, k, j, i)]
+
+/* hydro_driver.cpp:36-91 */
+void apko_reset_fluxes(apko_engine *e) {
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    for (int d = 0; d < e->ndim; ++d)
+      for (int n = 0; n < e->nvar; ++n)
+        for (int k = e->is[2]; k <= e->ie[2] + (d == 2); ++k)
+          for (int j = e->is[1]; j <= e->ie[1] + (d == 1); ++j)
+            for (int i = e->is[0]; i <= e->ie[0] + (d == 0); ++i) FX(d, n, k, j, i) = 0.0;
+  }
+}
+
+static inline double temp_cell(const apko_engine *e, const block_t *B, int k, int j, int i) {
+  return PR(IPR, k, j, i) / PR(IDN, k, j, i);
+}
+
+/* conduction.cpp:193-260 (ThermalFluxIsoFixed) */
+static void thermal_flux_iso_fixed(apko_engine *e, block_t *B) {
+  const double chi = e->p.thermal_diff_coeff;
+  for (int d = 0; d < e->ndim; ++d) {
+    const int o[3] = {d == 0, d == 1, d == 2};
+    for (int k = e->is[2]; k <= e->ie[2] + o[2]; ++k)
+      for (int j = e->is[1]; j <= e->ie[1] + o[1]; ++j)
+        for (int i = e->is[0]; i <= e->ie[0] + o[0]; ++i) {
+          const double T_i = temp_cell(e, B, k, j, i);
+          const double T_im1 = temp_cell(e, B, k - o[2], j - o[1], i - o[0]);
+          const double dTdx = (T_i - T_im1) / B->dx[d];
+          const double denf = 0.5 * (PR(IDN, k, j, i) + PR(IDN, k - o[2], j - o[1], i - o[0]));
+          FX(d, IEN, k, j, i) -= chi * denf * dTdx;
+        }
+  }
+}
+
+/* diffusion.hpp:24-66 */
+static double lim_vanleer_unused(double A, double B) { return (A * B > 0) ? 2.0 * A * B / (A + B) : 0.0; }
+static double lim_mc(double A, double B) {
+  return lim_minmod(2.0 * lim_minmod(A, B), (A + B) / 2.0);
+}
+static double lim4(double A, double B, double C, double D) {
+  return lim_mc(lim_mc(A, B), lim_mc(C, D));
+}
+
+/* monotonized transverse temperature difference across the d-face of cell (k,j,i) along t
+ * (conduction.cpp:291-316 and the x2 / x3 analogues) */
+static double dT_transverse(const apko_engine *e, const block_t *B, int d, int t, int k, int j,
+                            int i) {
+  const int od[3] = {d == 0, d == 1, d == 2}, ot[3] = {t == 0, t == 1, t == 2};
+  const int km = k - od[2], jm = j - od[1], im = i - od[0];
+  return lim4(temp_cell(e, B, k + ot[2], j + ot[1], i + ot[0]) - temp_cell(e, B, k, j, i),
+              temp_cell(e, B, k, j, i) - temp_cell(e, B, k - ot[2], j - ot[1], i - ot[0]),
+              temp_cell(e, B, km + ot[2], jm + ot[1], im + ot[0]) - temp_cell(e, B, km, jm, im),
+              temp_cell(e, B, km, jm, im) - temp_cell(e, B, km - ot[2], jm - ot[1], im - ot[0])) /
+         B->dx[t];
+}
+
+/* conduction.cpp:265-550 (ThermalFluxGeneral) for conduction = anisotropic, fixed coefficient
+ * (the isotropic type only reaches this function with the Spitzer coefficient); ndim >= 2 */
+static void thermal_flux_general(apko_engine *e, block_t *B) {
+  const double chi = e->p.thermal_diff_coeff;
+  const double sat_prefac = 5.0 * e->p.conduction_sat_phi; /* hydro.cpp:604 */
+  const int ndim = e->ndim;
+  for (int d = 0; d < ndim; ++d) {
+    const int o[3] = {d == 0, d == 1, d == 2};
+    for (int k = e->is[2]; k <= e->ie[2] + o[2]; ++k)
+      for (int j = e->is[1]; j <= e->ie[1] + o[1]; ++j)
+        for (int i = e->is[0]; i <= e->ie[0] + o[0]; ++i) {
+          const int km = k - o[2], jm = j - o[1], im = i - o[0];
+          double dT[3] = {0.0, 0.0, 0.0};
+          for (int t = 0; t < 3; ++t) {
+            if (t == d) {
+              dT[t] = (temp_cell(e, B, k, j, i) - temp_cell(e, B, km, jm, im)) / B->dx[d];
+            } else if (t < 2 || ndim >= 3) {
+              dT[t] = dT_transverse(e, B, d, t, k, j, i);
+            }
+          }
+          const double denf = 0.5 * (PR(IDN, k, j, i) + PR(IDN, km, jm, im));
+          const double tdf = 0.5 * (chi + chi);
+          const double Bx = 0.5 * (PR(IB1, km, jm, im) + PR(IB1, k, j, i));
+          const double By = 0.5 * (PR(IB2, km, jm, im) + PR(IB2, k, j, i));
+          const double Bz = (d == 2 || ndim >= 3) ? 0.5 * (PR(IB3, km, jm, im) + PR(IB3, k, j, i)) : 0.0;
+          double Bmag = sqrt(SQR(Bx) + SQR(By) + SQR(Bz));
+          Bmag = smax(Bmag, TINY_NUMBER);
+          const double bd = (d == 0 ? Bx : (d == 1 ? By : Bz)) / Bmag;
+          const double bDotGradT = (Bx * dT[0] + By * dT[1] + Bz * dT[2]) / Bmag;
+          const double flux_classic = -tdf * denf * bDotGradT * bd;
+          const double flux_classic_mag = fabs(tdf * denf * bDotGradT);
+          double flux_sat;
+          if (flux_classic > 0.0) {
+            flux_sat = sat_prefac * sqrt(PR(IPR, km, jm, im) / denf) * PR(IPR, km, jm, im);
+          } else if (flux_classic < 0.0) {
+            flux_sat = sat_prefac * sqrt(PR(IPR, k, j, i) / denf) * PR(IPR, k, j, i);
+          } else {
+            const double presf = 0.5 * (PR(IPR, k, j, i) + PR(IPR, km, jm, im));
+            flux_sat = sat_prefac * sqrt(presf / denf) * presf;
+          }
+          FX(d, IEN, k, j, i) += (flux_sat / (flux_sat + flux_classic_mag)) * flux_classic;
+        }
+  }
+}
+
+/* viscosity.cpp:98-291 (MomentumDiffFluxIsoFixed) */
+static void momentum_flux_iso_fixed(apko_engine *e, block_t *B) {
+  const double nu = e->p.mom_diff_coeff;
+  const int ndim = e->ndim;
+  const double dx1 = B->dx[0], dx2 = B->dx[1], dx3 = B->dx[2];
+  for (int k = e->is[2]; k <= e->ie[2]; ++k)
+    for (int j = e->is[1]; j <= e->ie[1]; ++j)
+      for (int i = e->is[0]; i <= e->ie[0] + 1; ++i) {
+        double fvx = 4.0 * (PR(IV1, k, j, i) - PR(IV1, k, j, i - 1)) / (3.0 * dx1);
+        double fvy = (PR(IV2, k, j, i) - PR(IV2, k, j, i - 1)) / dx1;
+        double fvz = (PR(IV3, k, j, i) - PR(IV3, k, j, i - 1)) / dx1;
+        if (ndim > 1) {
+          fvx -= ((PR(IV2, k, j + 1, i) + PR(IV2, k, j + 1, i - 1)) -
+                  (PR(IV2, k, j - 1, i) + PR(IV2, k, j - 1, i - 1))) / (6.0 * dx2);
+          fvy += ((PR(IV1, k, j + 1, i) + PR(IV1, k, j + 1, i - 1)) -
+                  (PR(IV1, k, j - 1, i) + PR(IV1, k, j - 1, i - 1))) / (4.0 * dx2);
+        }
+        if (ndim > 2) {
+          fvx -= ((PR(IV3, k + 1, j, i) + PR(IV3, k + 1, j, i - 1)) -
+                  (PR(IV3, k - 1, j, i) + PR(IV3, k - 1, j, i - 1))) / (6.0 * dx3);
+          fvz += ((PR(IV1, k + 1, j, i) + PR(IV1, k + 1, j, i - 1)) -
+                  (PR(IV1, k - 1, j, i) + PR(IV1, k - 1, j, i - 1))) / (4.0 * dx3);
+        }
+        const double nud = 0.5 * nu * (PR(IDN, k, j, i) + PR(IDN, k, j, i - 1));
+        FX(0, IM1, k, j, i) -= nud * fvx;
+        FX(0, IM2, k, j, i) -= nud * fvy;
+        FX(0, IM3, k, j, i) -= nud * fvz;
+        FX(0, IEN, k, j, i) -= 0.5 * nud * ((PR(IV1, k, j, i - 1) + PR(IV1, k, j, i)) * fvx +
+                                            (PR(IV2, k, j, i - 1) + PR(IV2, k, j, i)) * fvy +
+                                            (PR(IV3, k, j, i - 1) + PR(IV3, k, j, i)) * fvz);
+      }
+  if (ndim < 2) return;
+  for (int k = e->is[2]; k <= e->ie[2]; ++k)
+    for (int j = e->is[1]; j <= e->ie[1] + 1; ++j)
+      for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+        double fvx = (PR(IV1, k, j, i) - PR(IV1, k, j - 1, i)) / dx2 +
+                     ((PR(IV2, k, j, i + 1) + PR(IV2, k, j - 1, i + 1)) -
+                      (PR(IV2, k, j, i - 1) + PR(IV2, k, j - 1, i - 1))) / (4.0 * dx1);
+        double fvy = (PR(IV2, k, j, i) - PR(IV2, k, j - 1, i)) * 4.0 / (3.0 * dx2) -
+                     ((PR(IV1, k, j, i + 1) + PR(IV1, k, j - 1, i + 1)) -
+                      (PR(IV1, k, j, i - 1) + PR(IV1, k, j - 1, i - 1))) / (6.0 * dx1);
+        double fvz = (PR(IV3, k, j, i) - PR(IV3, k, j - 1, i)) / dx2;
+        if (ndim > 2) {
+          fvy -= ((PR(IV3, k + 1, j, i) + PR(IV3, k + 1, j - 1, i)) -
+                  (PR(IV3, k - 1, j, i) + PR(IV3, k - 1, j - 1, i))) / (6.0 * dx3);
+          fvz += ((PR(IV2, k + 1, j, i) + PR(IV2, k + 1, j - 1, i)) -
+                  (PR(IV2, k - 1, j, i) + PR(IV2, k - 1, j - 1, i))) / (4.0 * dx3);
+        }
+        const double nud = 0.5 * nu * (PR(IDN, k, j, i) + PR(IDN, k, j - 1, i));
+        FX(1, IM1, k, j, i) -= nud * fvx;
+        FX(1, IM2, k, j, i) -= nud * fvy;
+        FX(1, IM3, k, j, i) -= nud * fvz;
+        FX(1, IEN, k, j, i) -= 0.5 * nud * ((PR(IV1, k, j - 1, i) + PR(IV1, k, j, i)) * fvx +
+                                            (PR(IV2, k, j - 1, i) + PR(IV2, k, j, i)) * fvy +
+                                            (PR(IV3, k, j - 1, i) + PR(IV3, k, j, i)) * fvz);
+      }
+  if (ndim < 3) return;
+  for (int k = e->is[2]; k <= e->ie[2] + 1; ++k)
+    for (int j = e->is[1]; j <= e->ie[1]; ++j)
+      for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+        const double fvx = (PR(IV1, k, j, i) - PR(IV1, k - 1, j, i)) / dx3 +
+                           ((PR(IV3, k, j, i + 1) + PR(IV3, k - 1, j, i + 1)) -
+                            (PR(IV3, k, j, i - 1) + PR(IV3, k - 1, j, i - 1))) / (4.0 * dx1);
+        const double fvy = (PR(IV2, k, j, i) - PR(IV2, k - 1, j, i)) / dx3 +
+                           ((PR(IV3, k, j + 1, i) + PR(IV3, k - 1, j + 1, i)) -
+                            (PR(IV3, k, j - 1, i) + PR(IV3, k - 1, j - 1, i))) / (4.0 * dx2);
+        const double fvz = (PR(IV3, k, j, i) - PR(IV3, k - 1, j, i)) * 4.0 / (3.0 * dx3) -
+                           ((PR(IV1, k, j, i + 1) + PR(IV1, k - 1, j, i + 1)) -
+                            (PR(IV1, k, j, i - 1) + PR(IV1, k - 1, j, i - 1))) / (6.0 * dx1) -
+                           ((PR(IV2, k, j + 1, i) + PR(IV2, k - 1, j + 1, i)) -
+                            (PR(IV2, k, j - 1, i) + PR(IV2, k - 1, j - 1, i))) / (6.0 * dx2);
+        const double nud = 0.5 * nu * (PR(IDN, k, j, i) + PR(IDN, k - 1, j, i));
+        FX(2, IM1, k, j, i) -= nud * fvx;
+        FX(2, IM2, k, j, i) -= nud * fvy;
+        FX(2, IM3, k, j, i) -= nud * fvz;
+        FX(2, IEN, k, j, i) -= 0.5 * nud * ((PR(IV1, k - 1, j, i) + PR(IV1, k, j, i)) * fvx +
+                                            (PR(IV2, k - 1, j, i) + PR(IV2, k, j, i)) * fvy +
+                                            (PR(IV3, k - 1, j, i) + PR(IV3, k, j, i)) * fvz);
+      }
+}
+
+/* resistivity.cpp:89-232 (OhmicDiffFluxIsoFixed).  coords.Xf<d, face != d> is the cell-centre
+ * coordinate Xc<d> (uniform_coordinates.hpp:143-157): the spacing 2 dx is evaluated from positions */
+static void ohmic_flux_iso_fixed(apko_engine *e, block_t *B) {
+  const double eta = e->p.ohm_diff_coeff;
+  const int ndim = e->ndim;
+  const double dx1 = B->dx[0], dx2 = B->dx[1], dx3 = B->dx[2];
+  for (int k = e->is[2]; k <= e->ie[2]; ++k)
+    for (int j = e->is[1]; j <= e->ie[1]; ++j)
+      for (int i = e->is[0]; i <= e->ie[0] + 1; ++i) {
+        const double d3B1 =
+            ndim > 2 ? (0.5 * (PR(IB1, k + 1, j, i - 1) + PR(IB1, k + 1, j, i)) -
+                        0.5 * (PR(IB1, k - 1, j, i - 1) + PR(IB1, k - 1, j, i))) /
+                           (xc(B, 2, k + 1) - xc(B, 2, k - 1))
+                     : 0.0;
+        const double d1B3 = (PR(IB3, k, j, i) - PR(IB3, k, j, i - 1)) / dx1;
+        const double j2 = d3B1 - d1B3;
+        const double d1B2 = (PR(IB2, k, j, i) - PR(IB2, k, j, i - 1)) / dx1;
+        const double d2B1 =
+            ndim > 1 ? (0.5 * (PR(IB1, k, j + 1, i - 1) + PR(IB1, k, j + 1, i)) -
+                        0.5 * (PR(IB1, k, j - 1, i - 1) + PR(IB1, k, j - 1, i))) /
+                           (xc(B, 1, j + 1) - xc(B, 1, j - 1))
+                     : 0.0;
+        const double j3 = d1B2 - d2B1;
+        FX(0, IB2, k, j, i) += -eta * j3;
+        FX(0, IB3, k, j, i) += eta * j2;
+        FX(0, IEN, k, j, i) += 0.5 * eta * ((PR(IB3, k, j, i - 1) + PR(IB3, k, j, i)) * j2 -
+                                            (PR(IB2, k, j, i - 1) + PR(IB2, k, j, i)) * j3);
+      }
+  if (ndim < 2) return;
+  for (int k = e->is[2]; k <= e->ie[2]; ++k)
+    for (int j = e->is[1]; j <= e->ie[1] + 1; ++j)
+      for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+        const double d1B2 = (0.5 * (PR(IB2, k, j - 1, i + 1) + PR(IB2, k, j, i + 1)) -
+                             0.5 * (PR(IB2, k, j - 1, i - 1) + PR(IB2, k, j, i - 1))) /
+                            (xc(B, 0, i + 1) - xc(B, 0, i - 1));
+        const double d2B1 = (PR(IB1, k, j, i) - PR(IB1, k, j - 1, i)) / dx2;
+        const double j3 = d1B2 - d2B1;
+        const double d2B3 = (PR(IB3, k, j, i) - PR(IB3, k, j - 1, i)) / dx2;
+        const double d3B2 =
+            ndim > 2 ? (0.5 * (PR(IB2, k + 1, j - 1, i) + PR(IB2, k + 1, j, i)) -
+                        0.5 * (PR(IB2, k - 1, j - 1, i) + PR(IB2, k - 1, j, i))) /
+                           (xc(B, 2, k + 1) - xc(B, 2, k - 1))
+                     : 0.0;
+        const double j1 = d2B3 - d3B2;
+        FX(1, IB1, k, j, i) += eta * j3;
+        FX(1, IB3, k, j, i) += -eta * j1;
+        FX(1, IEN, k, j, i) += 0.5 * eta * ((PR(IB1, k, j - 1, i) + PR(IB1, k, j, i)) * j3 -
+                                            (PR(IB3, k, j - 1, i) + PR(IB3, k, j, i)) * j1);
+      }
+  if (ndim < 3) return;
+  for (int k = e->is[2]; k <= e->ie[2] + 1; ++k)
+    for (int j = e->is[1]; j <= e->ie[1]; ++j)
+      for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+        const double d2B3 = (0.5 * (PR(IB3, k - 1, j + 1, i) + PR(IB3, k, j + 1, i)) -
+                             0.5 * (PR(IB3, k - 1, j - 1, i) + PR(IB3, k, j - 1, i))) /
+                            (xc(B, 1, j + 1) - xc(B, 1, j - 1));
+        const double d3B2 = (PR(IB2, k, j, i) - PR(IB2, k - 1, j, i)) / dx3;
+        const double j1 = d2B3 - d3B2;
+        const double d3B1 = (PR(IB1, k, j, i) - PR(IB1, k - 1, j, i)) / dx3;
+        const double d1B3 = (0.5 * (PR(IB3, k - 1, j, i + 1) + PR(IB3, k, j, i + 1)) -
+                             0.5 * (PR(IB3, k - 1, j, i - 1) + PR(IB3, k, j, i - 1))) /
+                            (xc(B, 0, i + 1) - xc(B, 0, i - 1));
+        const double j2 = d3B1 - d1B3;
+        FX(2, IB1, k, j, i) += -eta * j2;
+        FX(2, IB2, k, j, i) += eta * j1;
+        FX(2, IEN, k, j, i) += 0.5 * eta * ((PR(IB2, k - 1, j, i) + PR(IB2, k, j, i)) * j1 -
+                                            (PR(IB1, k - 1, j, i) + PR(IB1, k, j, i)) * j2);
+      }
+}
+
+/* diffusion.cpp:19-53 (CalcDiffFluxes) */
+void apko_calc_diff_fluxes(apko_engine *e) {
+  (void)lim_vanleer_unused;
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    if (e->p.conduction == 1) thermal_flux_iso_fixed(e, B);
+    if (e->p.conduction == 2) thermal_flux_general(e, B);
+    if (e->p.viscosity == 1) momentum_flux_iso_fixed(e, B);
+    if (e->p.resistivity == 1) ohmic_flux_iso_fixed(e, B);
+  }
+}
+
+/* conduction.cpp:44-190, viscosity.cpp:34-92, resistivity.cpp:33-84 and hydro.cpp:935-946 */
+double apko_estimate_dt_diff(apko_engine *e) {
+  const int ndim = e->ndim;
+  const double fac = (ndim == 1) ? 0.5 : (ndim == 2 ? 0.25 : 1.0 / 6.0);
+  const double cfl_diff = (e->p.cfl_diff > 0.0) ? e->p.cfl_diff : e->p.cfl;
+  double dt_diff = DBL_MAX;
+  const double fixed[3] = {e->p.conduction == 1 ? e->p.thermal_diff_coeff : -1.0,
+                           e->p.viscosity == 1 ? e->p.mom_diff_coeff : -1.0,
+                           e->p.resistivity == 1 ? e->p.ohm_diff_coeff : -1.0};
+  if (e->p.conduction == 2) { /* general estimate, conduction.cpp:91-186 */
+    const double sat_prefac = 5.0 * e->p.conduction_sat_phi;
+    const double chi = e->p.thermal_diff_coeff;
+    double m = DBL_MAX;
+    for (int b = 0; b < e->nblocks; ++b) {
+      const block_t *B = &e->blk[b];
+      for (int k = e->is[2]; k <= e->ie[2]; ++k)
+        for (int j = e->is[1]; j <= e->ie[1]; ++j)
+          for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+            const double rho = PR(IDN, k, j, i), p = PR(IPR, k, j, i);
+            const double dTdx = 0.5 * (temp_cell(e, B, k, j, i + 1) - temp_cell(e, B, k, j, i - 1)) / B->dx[0];
+            const double dTdy = ndim >= 2 ? 0.5 * (temp_cell(e, B, k, j + 1, i) - temp_cell(e, B, k, j - 1, i)) / B->dx[1] : 0.0;
+            const double dTdz = ndim >= 3 ? 0.5 * (temp_cell(e, B, k + 1, j, i) - temp_cell(e, B, k - 1, j, i)) / B->dx[2] : 0.0;
+            const double gradTmag = sqrt(SQR(dTdx) + SQR(dTdy) + SQR(dTdz));
+            if (gradTmag == 0.0) continue;
+            const double Bx = PR(IB1, k, j, i), By = PR(IB2, k, j, i), Bz = PR(IB3, k, j, i);
+            const double Bmag = sqrt(SQR(Bx) + SQR(By) + SQR(Bz));
+            if (Bmag == 0.0) continue;
+            const double flux_sat = sat_prefac * sqrt(p / rho) * p;
+            const double flux_classic = chi * rho * gradTmag;
+            if (flux_classic / flux_sat > 100.) continue;
+            const double costheta = fabs(Bx * dTdx + By * dTdy + Bz * dTdz) / (Bmag * gradTmag);
+            m = fmin(m, SQR(B->dx[0]) / (chi * fabs(Bx) / Bmag * costheta + TINY_NUMBER));
+            if (ndim >= 2) m = fmin(m, SQR(B->dx[1]) / (chi * fabs(By) / Bmag * costheta + TINY_NUMBER));
+            if (ndim >= 3) m = fmin(m, SQR(B->dx[2]) / (chi * fabs(Bz) / Bmag * costheta + TINY_NUMBER));
+          }
+    }
+    dt_diff = smin(dt_diff, cfl_diff * fac * m);
+  }
+  for (int c = 0; c < 3; ++c) {
+    if (fixed[c] < 0.0) continue;
+    double m = DBL_MAX;
+    for (int b = 0; b < e->nblocks; ++b) {
+      const block_t *B = &e->blk[b];
+      m = fmin(m, SQR(B->dx[0]) / (fixed[c] + TINY_NUMBER));
+      if (ndim >= 2) m = fmin(m, SQR(B->dx[1]) / (fixed[c] + TINY_NUMBER));
+      if (ndim >= 3) m = fmin(m, SQR(B->dx[2]) / (fixed[c] + TINY_NUMBER));
+    }
+    dt_diff = smin(dt_diff, cfl_diff * fac * m);
+  }
+  return dt_diff;
+}
+
+int apko_last_s_rkl(const apko_engine *e) { return e->last_s_rkl; }
+
+/* One RKL2 super time step of length tau (AddSTSTasks, hydro_driver.cpp:170-344; RKL2StepFirst
+ * :93-126, RKL2StepOther :128-166; Meyer, Balsara & Aslam 2014) */
+void apko_sts(apko_engine *e, double tau) {
+  const double mindt_diff = e->dt_diff;
+  int s_rkl = (int)(0.5 * (sqrt(9.0 + 16.0 * tau / mindt_diff) - 1.0)) + 1;
+  if (s_rkl % 2 == 0) s_rkl += 1;
+  e->last_s_rkl = s_rkl;
+  const size_t nfield = e->ncell * e->nvar;
+  /* Y0 <- base (register u1) */
+  for (int b = 0; b < e->nblocks; ++b) memcpy(e->blk[b].u1, e->blk[b].cons, nfield * sizeof(double));
+  apko_reset_fluxes(e);
+  apko_calc_diff_fluxes(e);
+  if (e->multilevel) flux_correction(e);
+  const double mu_tilde_1 = 4. / 3. / ((double)s_rkl * (double)s_rkl + (double)s_rkl - 2.);
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    for (int l = 0; l < e->nvar; ++l)
+      for (int k = e->is[2]; k <= e->ie[2]; ++k)
+        for (int j = e->is[1]; j <= e->ie[1]; ++j)
+          for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+            const size_t c = IDX(e, l, k, j, i);
+            B->my0[c] = flux_div(e, B, l, k, j, i); /* Update::FluxDivergence, update.cpp:63-85 */
+            B->cons[c] = B->u1[c] + mu_tilde_1 * tau * B->my0[c]; /* Y_1 */
+            B->yjm2[c] = B->u1[c];                                /* Y_0 */
+          }
+  }
+  apko_exchange(e);
+  apko_cons_to_prim(e);
+  /* Meyer+2012 eq. (16) */
+  double b_j = 1. / 3., b_jm1 = 1. / 3., b_jm2 = 1. / 3.;
+  const double w1 = 4. / ((double)s_rkl * (double)s_rkl + (double)s_rkl - 2.);
+  for (int jj = 2; jj <= s_rkl; jj++) {
+    const double j = (double)jj;
+    b_j = (j * j + j - 2.0) / (2 * j * (j + 1.0));
+    const double mu_j = (2.0 * j - 1.0) / j * b_j / b_jm1;
+    const double nu_j = -(j - 1.0) / j * b_j / b_jm2;
+    const double mu_tilde_j = mu_j * w1;
+    const double gamma_tilde_j = -(1.0 - b_jm1) * mu_tilde_j;
+    apko_reset_fluxes(e);
+    apko_calc_diff_fluxes(e);
+    if (e->multilevel) flux_correction(e);
+    for (int b = 0; b < e->nblocks; ++b) {
+      block_t *B = &e->blk[b];
+      for (int l = 0; l < e->nvar; ++l)
+        for (int k = e->is[2]; k <= e->ie[2]; ++k)
+          for (int jc = e->is[1]; jc <= e->ie[1]; ++jc)
+            for (int i = e->is[0]; i <= e->ie[0]; ++i) {
+              const size_t c = IDX(e, l, k, jc, i);
+              const double MYjm1 = flux_div(e, B, l, k, jc, i);
+              const double Yj = mu_j * B->cons[c] + nu_j * B->yjm2[c] +
+                                (1.0 - mu_j - nu_j) * B->u1[c] + mu_tilde_j * tau * MYjm1 +
+                                gamma_tilde_j * tau * B->my0[c];
+              B->yjm2[c] = B->cons[c];
+              B->cons[c] = Yj;
+            }
+    }
+    apko_exchange(e);
+    apko_cons_to_prim(e);
+    b_jm2 = b_jm1;
+    b_jm1 = b_j;
+  }
+}
+#undef PR
+#undef FX
+
+/* ===================================================================================== */
 /* Timestep: src/hydro/hydro.cpp:828-976                                                  */
 /* ===================================================================================== */
 double apko_estimate_dt(apko_engine *e) {
@@ -1914,12 +2317,28 @@ double apko_estimate_dt(apko_engine *e) {
 #undef P
         }
   }
-  if (e->p.riemann == APKO_RS_NONE) return DBL_MAX; /* calc_dt_hyp=false, hydro.cpp:354-361 */
-  /* hydro.cpp:903-908: dt_hyp Param keeps the raw hyperbolic estimate (MHD only) */
-  if (e->p.fluid == APKO_FLUID_GLMMHD) {
-    if (e->p.cfl * min_dt < e->dt_hyp) e->dt_hyp = e->p.cfl * min_dt;
+  /* hydro.cpp:913-923: calc_dt_hyp = false for riemann = none (hydro.cpp:354-361) */
+  double dt_hyp = DBL_MAX, dt_min = DBL_MAX;
+  if (e->p.riemann != APKO_RS_NONE) {
+    /* hydro.cpp:903-908: dt_hyp Param keeps the raw hyperbolic estimate (MHD only) */
+    if (e->p.fluid == APKO_FLUID_GLMMHD) {
+      if (e->p.cfl * min_dt < e->dt_hyp) e->dt_hyp = e->p.cfl * min_dt;
+    }
+    dt_hyp = e->p.cfl * min_dt;
+    dt_min = smin(dt_min, dt_hyp);
   }
-  return e->p.cfl * min_dt;
+  /* hydro.cpp:935-963 */
+  if (e->p.diffint != 0) {
+    const double dt_diff = apko_estimate_dt_diff(e);
+    if (e->p.diffint == 1) {
+      dt_min = smin(dt_min, dt_diff);
+    } else {
+      const double r = e->p.rkl2_max_dt_ratio;
+      if (r > 0.0 && dt_hyp / dt_diff > r) dt_min = smin(dt_min, r * dt_diff);
+    }
+    e->dt_diff = smin(dt_diff, e->dt_diff);
+  }
+  return dt_min;
 }
 
 /* hydro.cpp:65-95 */
@@ -1955,6 +2374,7 @@ void apko_initialize(apko_engine *e, double tlim) {
   /* EvolutionDriver::InitializeBlockTimeSteps + SetGlobalTimeStep (driver.cpp:194-242) */
   e->dt = DBL_MAX;
   e->dt_hyp = DBL_MAX;
+  e->dt_diff = DBL_MAX;
   e->new_dt = apko_estimate_dt(e);
   set_global_dt(e);
 }
@@ -1991,6 +2411,8 @@ void apko_cycle(apko_engine *e) {
   }
   double g0[3], g1[3], beta[3];
   int nstages = integrator_coeffs(e->p.integrator, g0, g1, beta);
+  /* Strang-split super time stepping, first half (hydro_driver.cpp:455-458) */
+  if (e->p.diffint == 2) apko_sts(e, 0.5 * e->dt);
   for (int s = 0; s < nstages; ++s) {
     if (s == 0) apko_save_u1(e);
     /* VL2 predictor uses donor cell, hydro.cpp:459-464 */
@@ -2004,9 +2426,12 @@ void apko_cycle(apko_engine *e) {
     apko_exchange(e);
     apko_cons_to_prim(e);
     if (s == nstages - 1) {
+      /* second half of the super time step (hydro_driver.cpp:578-583) */
+      if (e->p.diffint == 2) apko_sts(e, 0.5 * e->dt);
       /* hydro_driver.cpp:589-613: reset reduction Params, then EstimateTimestep */
       e->mindx = DBL_MAX;
       e->dt_hyp = DBL_MAX;
+      e->dt_diff = DBL_MAX;
       e->new_dt = apko_estimate_dt(e);
     }
   }

@@ -50,6 +50,15 @@ typedef struct {
   int nref;
   int ref_level[4];
   double ref_xmin[4][3], ref_xmax[4][3];
+  /* <diffusion> block (src/hydro/hydro.cpp:539-702), fixed coefficients only */
+  int diffint;      /* diffusion/integrator: 0 none, 1 unsplit, 2 rkl2 */
+  int conduction;   /* 0 none, 1 isotropic, 2 anisotropic (conduction_coeff = fixed) */
+  int viscosity;    /* 0 none, 1 isotropic (viscosity_coeff = fixed) */
+  int resistivity;  /* 0 none, 1 ohmic (resistivity_coeff = fixed) */
+  double thermal_diff_coeff, mom_diff_coeff, ohm_diff_coeff; /* *_diff_coeff_code */
+  double cfl_diff;            /* diffusion/cfl; <= 0: the hyperbolic cfl (hydro.cpp:697) */
+  double rkl2_max_dt_ratio;   /* default -1 (hydro.cpp:688) */
+  double conduction_sat_phi;  /* default 0.3; fixed coefficient: prefac = 5 phi (hydro.cpp:604) */
 } apko_params;
 
 typedef struct apko_engine apko_engine;
@@ -98,6 +107,12 @@ void apko_cons_to_prim(apko_engine *e);
 double apko_estimate_dt(apko_engine *e);
 void apko_save_u1(apko_engine *e);
 void apko_set_c_h(apko_engine *e, double c_h);
+/* diffusion (src/hydro/diffusion/, hydro_driver.cpp:36-344) */
+void apko_reset_fluxes(apko_engine *e);                 /* ResetFluxes, hydro_driver.cpp:36-91 */
+void apko_calc_diff_fluxes(apko_engine *e);             /* CalcDiffFluxes: ADDS to the flux arrays */
+double apko_estimate_dt_diff(apko_engine *e);           /* min of the Estimate*Timestep functions */
+void apko_sts(apko_engine *e, double tau);              /* AddSTSTasks: one RKL2 super step */
+int apko_last_s_rkl(const apko_engine *e);              /* stages of the last super step */
 
 /* scalar building blocks for unit parity tests */
 void apko_recon_scalar(int recon, const double q[5], double dx, int positivity, double *ql_ip1,

@@ -33,7 +33,16 @@ class Params(C.Structure):
         ("glmmhd_alpha", C.c_double), ("nscalars", C.c_int),
         ("nref", C.c_int), ("ref_level", C.c_int * 4),
         ("ref_xmin", (C.c_double * 3) * 4), ("ref_xmax", (C.c_double * 3) * 4),
+        ("diffint", C.c_int), ("conduction", C.c_int), ("viscosity", C.c_int),
+        ("resistivity", C.c_int),
+        ("thermal_diff_coeff", C.c_double), ("mom_diff_coeff", C.c_double),
+        ("ohm_diff_coeff", C.c_double), ("cfl_diff", C.c_double),
+        ("rkl2_max_dt_ratio", C.c_double), ("conduction_sat_phi", C.c_double),
     ]
+
+
+DIFFINT = {"none": 0, "unsplit": 1, "rkl2": 2}
+CONDUCTION = {"none": 0, "isotropic": 1, "anisotropic": 2}
 
 
 _lib = None
@@ -88,6 +97,12 @@ def lib():
     L.apko_cons_to_prim.argtypes = [C.c_void_p]
     L.apko_save_u1.argtypes = [C.c_void_p]
     L.apko_set_c_h.argtypes = [C.c_void_p, C.c_double]
+    L.apko_reset_fluxes.argtypes = [C.c_void_p]
+    L.apko_calc_diff_fluxes.argtypes = [C.c_void_p]
+    L.apko_estimate_dt_diff.argtypes = [C.c_void_p]
+    L.apko_estimate_dt_diff.restype = C.c_double
+    L.apko_sts.argtypes = [C.c_void_p, C.c_double]
+    L.apko_last_s_rkl.argtypes = [C.c_void_p]
     L.apko_recon_scalar.argtypes = [C.c_int, dp, C.c_double, C.c_int, dp, dp]
     L.apko_riemann_face.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_double, C.c_double, dp]
     L.apko_c2p_cell.argtypes = [C.c_int, C.c_int, dp, dp] + [C.c_double] * 6
@@ -103,7 +118,9 @@ def make_params(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
                 mb=None, ng=2, bc="periodic", xmin=(0.0, 0.0, 0.0), xmax=(3.0, 1.5, 1.5),
                 gamma=5.0 / 3.0, cfl=0.3, fofc=False, fofc_jacobi=False, dedner_extended=False,
                 glmmhd_alpha=0.1, nscalars=0, dfloor=-1.0, pfloor=-1.0, efloor=-1.0,
-                vceil=float("inf"), eceil=float("inf"), refine=()):
+                vceil=float("inf"), eceil=float("inf"), refine=(), diffint="none",
+                conduction="none", thermal_diff_coeff=0.0, viscosity="none", mom_diff_coeff=0.0,
+                resistivity="none", ohm_diff_coeff=0.0, cfl_diff=-1.0, rkl2_max_dt_ratio=-1.0):
     """refine: static refinement regions [(level, (x1min, x2min, x3min), (x1max, x2max, x3max)), ...]
     = the <parthenon/static_refinementN> blocks of a deck"""
     p = Params()
@@ -122,6 +139,10 @@ def make_params(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
     p.fofc, p.fofc_jacobi, p.dedner_extended = int(fofc), int(fofc_jacobi), int(dedner_extended)
     p.glmmhd_alpha, p.nscalars = glmmhd_alpha, nscalars
     p.dfloor, p.pfloor, p.efloor, p.vceil, p.eceil = dfloor, pfloor, efloor, vceil, eceil
+    p.diffint, p.conduction = DIFFINT[diffint], CONDUCTION[conduction]
+    p.viscosity, p.resistivity = int(viscosity == "isotropic"), int(resistivity == "ohmic")
+    p.thermal_diff_coeff, p.mom_diff_coeff, p.ohm_diff_coeff = thermal_diff_coeff, mom_diff_coeff, ohm_diff_coeff
+    p.cfl_diff, p.rkl2_max_dt_ratio = cfl_diff, rkl2_max_dt_ratio
     p.nref = len(refine)
     for r, (lev, lo, hi) in enumerate(refine):
         p.ref_level[r] = lev

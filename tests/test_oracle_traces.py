@@ -6,7 +6,8 @@ GPU tests hold to the same traces in strict FP mode."""
 import pytest
 
 from oracle_lib import Oracle
-from trace_util import AMR_DECKS, DECKS, TRACES, check_lw_row, follow_trace, lw_kwargs, lw_pgen
+from trace_util import (AMR_DECKS, DECKS, DIFF_DECKS, DIFF_TRACES, TRACES, check_lw_row,
+                        follow_trace, lw_kwargs, lw_pgen)
 
 
 def advance(o, tlim, c):
@@ -85,3 +86,27 @@ def test_static_refinement_traces(name):
     o.initialize(tlim)
     follow_trace(o, case["trace"], tlim, advance)
     assert o.ncycle == case["ncycle"]
+
+
+@pytest.mark.parametrize("name", sorted(DIFF_DECKS))
+def test_diffusion_traces(name):
+    """<diffusion> block: unsplit and RKL2 super-time-stepping integration of thermal
+    conduction (isotropic; anisotropic with saturation), isotropic viscosity and Ohmic resistivity
+    with fixed coefficients (src/hydro/diffusion/*, hydro_driver.cpp:36-344) reproduce the
+    reference's (time, dt) at all 17 digits, and the number of RKL2 stages it reports."""
+    kw, pgen, pars, tlim = DIFF_DECKS[name]
+    o = Oracle(**kw)
+    o.pgen(pgen, pars)
+    o.initialize(tlim)
+    case = DIFF_TRACES[name]
+    sts = []
+
+    def adv(o, tlim, c):
+        o.run(tlim, c)
+        if kw["diffint"] == "rkl2":
+            sts.append(o.L.apko_last_s_rkl(o.h))
+
+    follow_trace(o, case["trace"], tlim, adv)
+    assert o.ncycle == case["ncycle"]
+    if kw["diffint"] == "rkl2":
+        assert sts == case["s_rkl"][1::2]  # (second super step of every cycle)

@@ -45,6 +45,45 @@ DECKS = {
 }
 
 
+# <diffusion> decks (tests/golden/make_diffusion_goldens.py -> reference_traces_diffusion.json)
+DIFF_TRACES = json.load(open(os.path.join(os.path.dirname(GOLDEN), "reference_traces_diffusion.json")))
+_OT2 = dict(fluid="glmmhd", nx=(64, 64, 1), mb=(32, 32, 1), ng=3, xmin=(-0.5,) * 3, xmax=(0.5,) * 3,
+            gamma=GAMMA_DECK, cfl=0.4, recon="ppm", riemann="hlld", integrator="vl2")
+_OT3 = dict(fluid="glmmhd", nx=(32, 32, 32), mb=(16, 16, 16), ng=3, xmin=(-0.5,) * 3,
+            xmax=(0.5,) * 3, gamma=GAMMA_DECK, cfl=0.3, recon="ppm", riemann="hlld", integrator="vl2")
+
+
+def _diff(integrator, cond=None, visc=None, ohm=None, ratio=-1.0, cfl=-1.0):
+    kw = dict(diffint=integrator, rkl2_max_dt_ratio=ratio, cfl_diff=cfl)
+    if cond:
+        kw.update(conduction=cond[0], thermal_diff_coeff=cond[1])
+    if visc:
+        kw.update(viscosity="isotropic", mom_diff_coeff=visc)
+    if ohm:
+        kw.update(resistivity="ohmic", ohm_diff_coeff=ohm)
+    return kw
+
+
+DIFF_DECKS = {
+    "ot2d_unsplit": (dict(_OT2, **_diff("unsplit", ("isotropic", 0.002), 0.002, 0.002)), "orszag_tang", [], 1.0),
+    "ot2d_unsplit_stiff": (dict(_OT2, **_diff("unsplit", ("isotropic", 0.03), 0.05, 0.04)), "orszag_tang", [], 1.0),
+    "ot2d_rkl2": (dict(_OT2, **_diff("rkl2", ("isotropic", 0.05), 0.05, 0.05)), "orszag_tang", [], 1.0),
+    "ot2d_rkl2_aniso": (dict(_OT2, **_diff("rkl2", ("anisotropic", 0.2), 0.02, 0.03, ratio=6.0, cfl=0.25)),
+                        "orszag_tang", [], 1.0),
+    "ot3d_unsplit": (dict(_OT3, **_diff("unsplit", ("isotropic", 0.004), 0.003, 0.005)), "orszag_tang", [], 1000.0),
+    "ot3d_rkl2_aniso": (dict(_OT3, **_diff("rkl2", ("anisotropic", 0.1), 0.04, 0.05)), "orszag_tang", [], 1000.0),
+    "blast2d_rkl2_hydro": (dict(fluid="euler", nx=(64, 64, 1), mb=(32, 32, 1), ng=2, xmin=(-0.5,) * 3,
+                                xmax=(0.5,) * 3, gamma=GAMMA_DECK, cfl=0.3, recon="plm", riemann="hllc",
+                                integrator="rk3", **_diff("rkl2", ("isotropic", 0.02), 0.03)),
+                           "blast", [0.1, 0.001, 1.6e8, 1.0], 0.1),
+    "sod_unsplit": (dict(nx=(256, 1, 1), mb=(64, 1, 1), ng=2,
+                         bc=["outflow", "outflow", "periodic", "periodic", "periodic", "periodic"],
+                         xmin=(0.0, -0.5, -0.5), xmax=(1.0, 0.5, 0.5), gamma=1.4, cfl=0.5, recon="plm",
+                         riemann="hllc", integrator="vl2", **_diff("unsplit", ("isotropic", 0.001), 0.002)),
+                    "sod", [], 0.4),
+}
+
+
 def _amr(regions, fluid, recon, rs, ng):
     return (dict(fluid=fluid, nx=(32, 32, 32), mb=(8, 8, 8), ng=ng, xmin=(-0.5,) * 3,
                  xmax=(0.5,) * 3, gamma=GAMMA_DECK, cfl=0.3, recon=recon, riemann=rs,
