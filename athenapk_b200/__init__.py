@@ -39,6 +39,11 @@ class SimConfig(C.Structure):
         ("rank", C.c_int), ("nranks", C.c_int), ("plan_only", C.c_int),
         ("nref", C.c_int), ("ref_level", C.c_int * 4),
         ("ref_xmin", (C.c_double * 3) * 4), ("ref_xmax", (C.c_double * 3) * 4),
+        ("diffint", C.c_int), ("conduction", C.c_int), ("viscosity", C.c_int),
+        ("resistivity", C.c_int),
+        ("thermal_diff_coeff", C.c_double), ("mom_diff_coeff", C.c_double),
+        ("ohm_diff_coeff", C.c_double), ("cfl_diff", C.c_double),
+        ("rkl2_max_dt_ratio", C.c_double), ("conduction_sat_phi", C.c_double),
     ]
 
 
@@ -88,6 +93,8 @@ ABI_SYMBOLS = [
     "apk_copy_ghosts_local", "apk_halo_pack", "apk_halo_unpack", "apk_stage_fused", "apk_stage_fused_p2p",
     "apk_save_u1", "apk_fp64_probe", "apk_restrict_average", "apk_prolongate_minmod_multid",
     "apk_tag_pressure_gradient", "apk_history_workspace_bytes", "apk_history_sums",
+    "apk_reset_fluxes", "apk_calc_diff_fluxes", "apk_rkl2_step_first", "apk_rkl2_step_other",
+    "apk_min_dt_conduction",
 ]
 SIM_SYMBOLS = [
     "apk_sim_last_error", "apk_sim_default_config", "apk_sim_create", "apk_sim_destroy",
@@ -95,7 +102,7 @@ SIM_SYMBOLS = [
     "apk_sim_execute", "apk_sim_step", "apk_sim_num_local_blocks", "apk_sim_num_global_blocks",
     "apk_sim_nvar", "apk_sim_block_dims", "apk_sim_block_level", "apk_sim_block_info", "apk_sim_copy_to_host",
     "apk_sim_copy_from_host", "apk_sim_device_ptr", "apk_sim_time", "apk_sim_dt",
-    "apk_sim_ncycle", "apk_sim_c_h", "apk_sim_fofc_corrections", "apk_sim_fofc_redone_stages", "apk_sim_fused_active", "apk_sim_p2p_active",
+    "apk_sim_ncycle", "apk_sim_c_h", "apk_sim_fofc_corrections", "apk_sim_last_s_rkl", "apk_sim_fofc_redone_stages", "apk_sim_fused_active", "apk_sim_p2p_active",
     "apk_sim_linear_wave_period", "apk_sim_linear_wave_errors", "apk_sim_stream",
     "apk_sim_pack_desc", "apk_sim_device_blocks", "apk_sim_synchronize", "apk_sim_task",
     "apk_sim_set_c_h", "apk_sim_upload_all", "apk_sim_download_all",
@@ -179,6 +186,7 @@ def lib():
     for f in ("apk_sim_time", "apk_sim_dt", "apk_sim_c_h", "apk_sim_linear_wave_period"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = C.c_double
+    L.apk_sim_last_s_rkl.argtypes = [vp]
     L.apk_sim_fofc_corrections.argtypes = [vp]
     L.apk_sim_fofc_corrections.restype = C.c_longlong
     L.apk_sim_fofc_redone_stages.argtypes = [vp]
@@ -213,7 +221,9 @@ def make_config(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
                 gamma=5.0 / 3.0, cfl=0.3, fofc=False, dedner_extended=False, glmmhd_alpha=0.1,
                 nscalars=0, dfloor=-1.0, pfloor=-1.0, efloor=-1.0, vceil=float("inf"),
                 eceil=float("inf"), fp_mode="fast", fused=True, rank=0, nranks=1,
-                plan_only=False, refine=()):
+                plan_only=False, refine=(), diffint="none", conduction="none",
+                thermal_diff_coeff=0.0, viscosity="none", mom_diff_coeff=0.0, resistivity="none",
+                ohm_diff_coeff=0.0, cfl_diff=-1.0, rkl2_max_dt_ratio=-1.0):
     """Input-deck style configuration (same keys/meaning as docs/input.md of the reference).
     refine: static refinement regions [(level, (x1min, x2min, x3min), (x1max, x2max, x3max)), ...]
     = the <parthenon/static_refinementN> blocks of a deck."""
@@ -242,6 +252,13 @@ def make_config(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
         c.ref_level[r] = lev
         for d in range(3):
             c.ref_xmin[r][d], c.ref_xmax[r][d] = lo[d], hi[d]
+    # <diffusion> block of a deck (docs/input.md), fixed coefficients
+    c.diffint = {"none": 0, "unsplit": 1, "rkl2": 2}[diffint]
+    c.conduction = {"none": 0, "isotropic": 1, "anisotropic": 2}[conduction]
+    c.viscosity = {"none": 0, "isotropic": 1}[viscosity]
+    c.resistivity = {"none": 0, "ohmic": 1}[resistivity]
+    c.thermal_diff_coeff, c.mom_diff_coeff, c.ohm_diff_coeff = thermal_diff_coeff, mom_diff_coeff, ohm_diff_coeff
+    c.cfl_diff, c.rkl2_max_dt_ratio = cfl_diff, rkl2_max_dt_ratio
     return c
 
 
@@ -402,6 +419,7 @@ class HydroSim:
     ncycle = property(lambda s: s.L.apk_sim_ncycle(s.h))
     c_h = property(lambda s: s.L.apk_sim_c_h(s.h))
     fofc_corrections = property(lambda s: s.L.apk_sim_fofc_corrections(s.h))
+    last_s_rkl = property(lambda s: s.L.apk_sim_last_s_rkl(s.h))
     fofc_redone_stages = property(lambda s: s.L.apk_sim_fofc_redone_stages(s.h))
     fused_active = property(lambda s: bool(s.L.apk_sim_fused_active(s.h)))
     p2p_active = property(lambda s: bool(s.L.apk_sim_p2p_active(s.h)))

@@ -342,6 +342,54 @@ int apk_box_copy(const apk_box_item_t *d_items, int nitems, int nvar, void *stre
   return cuda_ok("apk_box_copy");
 }
 
+int apk_reset_fluxes(const apk_pack_desc_t *d, const apk_block_t *blocks, void *stream) {
+  if (check(d, blocks, "apk_reset_fluxes: bad descriptor")) return 1;
+  DISPATCH(d, launch_reset_fluxes(*d, blocks, S(stream)));
+  return cuda_ok("apk_reset_fluxes");
+}
+
+int apk_calc_diff_fluxes(const apk_pack_desc_t *d, const apk_block_t *blocks,
+                         const apk_diffusion_t *diff, void *stream) {
+  if (check(d, blocks, "apk_calc_diff_fluxes: bad descriptor")) return 1;
+  if (!diff) {
+    apk_common::set_error("apk_calc_diff_fluxes: null diffusion parameters");
+    return 1;
+  }
+  if (DISPATCH(d, launch_diff_fluxes(*d, blocks, *diff, S(stream)))) return 1;
+  return cuda_ok("apk_calc_diff_fluxes");
+}
+
+int apk_rkl2_step_first(const apk_pack_desc_t *d, const apk_block_t *blocks, double *const *d_my0,
+                        double *const *d_yjm2, int s_rkl, double tau, void *stream) {
+  if (check(d, blocks, "apk_rkl2_step_first: bad descriptor")) return 1;
+  // Meyer+2014 eq. (18), hydro_driver.cpp:103-105
+  const double mu_tilde_1 = 4. / 3. /
+                            (static_cast<double>(s_rkl) * static_cast<double>(s_rkl) +
+                             static_cast<double>(s_rkl) - 2.);
+  DISPATCH(d, launch_rkl2_first(*d, blocks, d_my0, d_yjm2, mu_tilde_1 * tau, S(stream)));
+  return cuda_ok("apk_rkl2_step_first");
+}
+
+int apk_rkl2_step_other(const apk_pack_desc_t *d, const apk_block_t *blocks, double *const *d_my0,
+                        double *const *d_yjm2, double mu_j, double nu_j, double mu_tilde_j,
+                        double gamma_tilde_j, double tau, void *stream) {
+  if (check(d, blocks, "apk_rkl2_step_other: bad descriptor")) return 1;
+  DISPATCH(d, launch_rkl2_other(*d, blocks, d_my0, d_yjm2, mu_j, nu_j, 1.0 - mu_j - nu_j,
+                                mu_tilde_j * tau, gamma_tilde_j * tau, S(stream)));
+  return cuda_ok("apk_rkl2_step_other");
+}
+
+int apk_min_dt_conduction(const apk_pack_desc_t *d, const apk_block_t *blocks,
+                          const apk_diffusion_t *diff, double *d_out, void *stream) {
+  if (check(d, blocks, "apk_min_dt_conduction: bad descriptor")) return 1;
+  if (!diff || !d_out) {
+    apk_common::set_error("apk_min_dt_conduction: null argument");
+    return 1;
+  }
+  DISPATCH(d, launch_min_dt_conduction(*d, blocks, *diff, d_out, S(stream)));
+  return cuda_ok("apk_min_dt_conduction");
+}
+
 int apk_save_u1(const apk_pack_desc_t *d, const apk_block_t *blocks, void *stream) {
   if (check(d, blocks, "apk_save_u1: bad descriptor")) return 1;
   apk_common::launch_save_u1(*d, blocks, S(stream));

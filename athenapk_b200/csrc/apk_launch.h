@@ -34,6 +34,16 @@
                                int nitems, cudaStream_t s);                                     \
   int launch_pressure_gradient(const apk_pack_desc_t &d, const apk_block_t *blocks,             \
                                double threshold, int *tags, double *maxeps, cudaStream_t s);    \
+  int launch_reset_fluxes(const apk_pack_desc_t &d, const apk_block_t *blocks, cudaStream_t s); \
+  int launch_diff_fluxes(const apk_pack_desc_t &d, const apk_block_t *blocks,                   \
+                         const apk_diffusion_t &df, cudaStream_t s);                            \
+  int launch_rkl2_first(const apk_pack_desc_t &d, const apk_block_t *blocks,                    \
+                        double *const *my0, double *const *yjm2, double mt, cudaStream_t s);    \
+  int launch_rkl2_other(const apk_pack_desc_t &d, const apk_block_t *blocks,                    \
+                        double *const *my0, double *const *yjm2, double mu_j, double nu_j,      \
+                        double c0, double mtt, double gtt, cudaStream_t s);                     \
+  int launch_min_dt_conduction(const apk_pack_desc_t &d, const apk_block_t *blocks,             \
+                               const apk_diffusion_t &df, double *d_out, cudaStream_t s);       \
   size_t history_workspace_bytes(const apk_pack_desc_t &d);                                     \
   int launch_history(const apk_pack_desc_t &d, const apk_block_t *blocks, double *work,         \
                      cudaStream_t s);                                                           \

@@ -136,8 +136,26 @@ HydroSim::HydroSim(const SimConfig &cfg)
   // its own trial update, and only a stage in which a cell actually fails is redone with the
   // flux-materialising tasks (FusedFofcCheck)
   // multilevel meshes need materialised fluxes (flux correction, hydro_driver.cpp:527-531)
+  // diffusion (either integrator) runs on the flux-materialising tasks: unsplit adds to the
+  // hyperbolic fluxes (hydro.cpp:1202-1205), RKL2 needs the flux arrays for its sub-steps
   fused_ = cfg_.fused && !cfg_.dedner_extended && cfg_.riemann != APK_RIEMANN_LLF &&
-           cfg_.nscalars == 0 && !multilevel_;
+           cfg_.nscalars == 0 && !multilevel_ && cfg_.diffint == 0;
+  if (cfg_.diffint != 0) {
+    if (cfg_.fofc)
+      throw std::runtime_error("apk_host: first_order_flux_correct with diffusion is not supported");
+    if ((cfg_.conduction == APK_CONDUCTION_ANISOTROPIC || cfg_.resistivity) &&
+        cfg_.fluid != APK_FLUID_GLMMHD)
+      throw std::runtime_error("Anisotropic thermal conduction / resistivity require fluid = glmmhd");
+    if (cfg_.conduction == APK_CONDUCTION_ANISOTROPIC && ndim_ < 2)
+      throw std::runtime_error("apk_host: anisotropic conduction needs a 2-D or 3-D mesh");
+    diff_.conduction = cfg_.conduction;
+    diff_.viscosity = cfg_.viscosity;
+    diff_.resistivity = cfg_.resistivity;
+    diff_.thermal_diff_coeff = cfg_.thermal_diff_coeff;
+    diff_.mom_diff_coeff = cfg_.mom_diff_coeff;
+    diff_.ohm_diff_coeff = cfg_.ohm_diff_coeff;
+    diff_.conduction_sat_prefac = 5.0 * cfg_.conduction_sat_phi;  // hydro.cpp:604
+  }
   BuildMesh();
   BuildNeighbors();
   if (!cfg_.plan_only) {
@@ -158,6 +176,10 @@ HydroSim::~HydroSim() {
   cudaFree(d_prim_[1]);
   cudaFree(d_u1_);
   for (int d = 0; d < 3; ++d) cudaFree(d_flux_[d]);
+  cudaFree(d_my0_);
+  cudaFree(d_yjm2_);
+  cudaFree(d_my0_ptrs_);
+  cudaFree(d_yjm2_ptrs_);
   cudaFree(d_blocks_[0]);
   cudaFree(d_blocks_[1]);
   cudaFree(d_prim_out_[0]);
@@ -511,6 +533,21 @@ void HydroSim::UploadBlocks() {
       cuda_check(cudaMalloc(&d_flux_[d], bytes), "cudaMalloc flux");
       cuda_check(cudaMemset(d_flux_[d], 0, bytes), "memset");
     }
+  }
+  if (cfg_.diffint == 2) {  // RKL2 registers (hydro_driver.cpp:211-212)
+    cuda_check(cudaMalloc(&d_my0_, bytes), "cudaMalloc MY0");
+    cuda_check(cudaMalloc(&d_yjm2_, bytes), "cudaMalloc Yjm2");
+    cuda_check(cudaMemset(d_my0_, 0, bytes), "memset");
+    cuda_check(cudaMemset(d_yjm2_, 0, bytes), "memset");
+    std::vector<double *> pm(nbl), py(nbl);
+    for (size_t b = 0; b < nbl; ++b) {
+      pm[b] = d_my0_ + b * per;
+      py[b] = d_yjm2_ + b * per;
+    }
+    cuda_check(cudaMalloc(&d_my0_ptrs_, nbl * sizeof(double *)), "cudaMalloc MY0 table");
+    cuda_check(cudaMalloc(&d_yjm2_ptrs_, nbl * sizeof(double *)), "cudaMalloc Yjm2 table");
+    cuda_check(cudaMemcpy(d_my0_ptrs_, pm.data(), nbl * sizeof(double *), cudaMemcpyHostToDevice), "upload");
+    cuda_check(cudaMemcpy(d_yjm2_ptrs_, py.data(), nbl * sizeof(double *), cudaMemcpyHostToDevice), "upload");
   }
   if (fused_ && cfg_.fofc && cfg_.integrator != (int)Integrator::vl2 && integrator_.nstages > 1) {
     // stages after the first overwrite their input cons: keep a copy to roll back to
@@ -915,7 +952,93 @@ TaskStatus HydroSim::CalculateFluxes(int stage) {
   // flux_first_stage: VL2 predictor uses donor cell (hydro.cpp:459-464)
   const int recon = (stage == 1 && cfg_.integrator == (int)Integrator::vl2) ? APK_RECON_DC : -1;
   abi_check(apk_calc_fluxes(&desc_, d_blocks_[cur_], c_h, recon, stream_), "apk_calc_fluxes");
+  if (cfg_.diffint == 1) CalcDiffFluxes();  // hydro.cpp:1202-1205 (diffusion/integrator = unsplit)
   return TaskStatus::complete;
+}
+
+TaskStatus HydroSim::CalcDiffFluxes() {  // diffusion/diffusion.cpp:19-53
+  abi_check(apk_calc_diff_fluxes(&desc_, d_blocks_[cur_], &diff_, stream_), "apk_calc_diff_fluxes");
+  return TaskStatus::complete;
+}
+
+// AddSTSTasks (hydro_driver.cpp:170-344): one RKL2 super time step of length tau (Meyer, Balsara &
+// Aslam 2014), same task order: reset fluxes -> diffusive fluxes of base -> [flux correction] ->
+// register update -> ghost exchange -> FillDerived, s_rkl times
+TaskStatus HydroSim::SuperTimeStep(Real tau) {
+  const Real mindt_diff = dt_diff_;
+  // eq (21) using half hyperbolic timestep due to Strang split (hydro_driver.cpp:176-181)
+  int s_rkl = static_cast<int>(0.5 * (std::sqrt(9.0 + 16.0 * tau / mindt_diff) - 1.0)) + 1;
+  if (s_rkl % 2 == 0) s_rkl += 1;
+  last_s_rkl = s_rkl;
+  auto exchange_and_fill = [this] {
+    SendBoundBufs(0);
+    ReceiveBoundBufs();
+    SetBounds(0);
+    if (multilevel_) ProlongateBounds();
+    ApplyBoundaryConditions(0);
+    FillDerived();
+  };
+  abi_check(apk_reset_fluxes(&desc_, d_blocks_[cur_], stream_), "apk_reset_fluxes");
+  CalcDiffFluxes();
+  if (multilevel_) FluxCorrection();
+  abi_check(apk_rkl2_step_first(&desc_, d_blocks_[cur_], d_my0_ptrs_, d_yjm2_ptrs_, s_rkl, tau,
+                                stream_), "apk_rkl2_step_first");
+  exchange_and_fill();
+  // Meyer+2012 eq. (16) (hydro_driver.cpp:277-344)
+  Real b_j = 1. / 3., b_jm1 = 1. / 3., b_jm2 = 1. / 3.;
+  const Real w1 = 4. / (static_cast<Real>(s_rkl) * static_cast<Real>(s_rkl) +
+                        static_cast<Real>(s_rkl) - 2.);
+  for (int jj = 2; jj <= s_rkl; jj++) {
+    const Real j = static_cast<Real>(jj);
+    b_j = (j * j + j - 2.0) / (2 * j * (j + 1.0));
+    const Real mu_j = (2.0 * j - 1.0) / j * b_j / b_jm1;
+    const Real nu_j = -(j - 1.0) / j * b_j / b_jm2;
+    const Real mu_tilde_j = mu_j * w1;
+    const Real gamma_tilde_j = -(1.0 - b_jm1) * mu_tilde_j;  // -a_jm1*mu_tilde_j
+    abi_check(apk_reset_fluxes(&desc_, d_blocks_[cur_], stream_), "apk_reset_fluxes");
+    CalcDiffFluxes();
+    if (multilevel_) FluxCorrection();
+    abi_check(apk_rkl2_step_other(&desc_, d_blocks_[cur_], d_my0_ptrs_, d_yjm2_ptrs_, mu_j, nu_j,
+                                  mu_tilde_j, gamma_tilde_j, tau, stream_), "apk_rkl2_step_other");
+    exchange_and_fill();
+    b_jm2 = b_jm1;
+    b_jm1 = b_j;
+  }
+  return TaskStatus::complete;
+}
+
+// hydro.cpp:935-946: min of EstimateConductionTimestep (conduction.cpp:44-190),
+// EstimateViscosityTimestep (viscosity.cpp:34-92) and EstimateResistivityTimestep
+// (resistivity.cpp:33-84).  Fixed coefficients: the estimate depends on dx only.
+Real HydroSim::EstimateDiffusionTimestep() {
+  const Real fac = (ndim_ == 1) ? 0.5 : (ndim_ == 2 ? 0.25 : 1.0 / 6.0);
+  const Real cfl_diff = (cfg_.cfl_diff > 0.0) ? cfg_.cfl_diff : cfg_.cfl;
+  constexpr Real tiny = 1.0e-20;  // TINY_NUMBER
+  Real dt_diff = std::numeric_limits<Real>::max();
+  const Real fixed[3] = {cfg_.conduction == APK_CONDUCTION_ISOTROPIC ? cfg_.thermal_diff_coeff : -1.0,
+                         cfg_.viscosity ? cfg_.mom_diff_coeff : -1.0,
+                         cfg_.resistivity ? cfg_.ohm_diff_coeff : -1.0};
+  if (cfg_.conduction == APK_CONDUCTION_ANISOTROPIC) {
+    abi_check(apk_min_dt_conduction(&desc_, d_blocks_[cur_], &diff_, d_scalars_ + 2, stream_),
+              "apk_min_dt_conduction");
+    if (cfg_.nranks > 1)
+      abi_check(apk_allreduce_scalar(comm_, d_scalars_ + 2, 0, stream_), "apk_allreduce_scalar");
+    cuda_check(cudaMemcpyAsync(h_scalars_ + 2, d_scalars_ + 2, sizeof(double), cudaMemcpyDeviceToHost,
+                               S(stream_)), "dt_cond D2H");
+    Synchronize();
+    dt_diff = std::min(dt_diff, cfl_diff * fac * h_scalars_[2]);
+  }
+  for (int c = 0; c < 3; ++c) {
+    if (fixed[c] < 0.0) continue;
+    Real m = std::numeric_limits<Real>::max();
+    for (const auto &B : blocks_) {
+      m = std::fmin(m, B.dx[0] * B.dx[0] / (fixed[c] + tiny));
+      if (ndim_ >= 2) m = std::fmin(m, B.dx[1] * B.dx[1] / (fixed[c] + tiny));
+      if (ndim_ >= 3) m = std::fmin(m, B.dx[2] * B.dx[2] / (fixed[c] + tiny));
+    }
+    dt_diff = std::min(dt_diff, cfl_diff * fac * m);
+  }
+  return dt_diff;
 }
 
 TaskStatus HydroSim::FirstOrderFluxCorrect(Real gam0, Real gam1, Real beta_dt) {
@@ -1288,36 +1411,48 @@ TaskStatus HydroSim::FillDerived() {  // Update::FillDerived -> ConsToPrim (hydr
 TaskStatus HydroSim::EstimateTimestep(bool have_device_min) {
   // hydro.cpp:828-976 + update.hpp:269-278. have_device_min: the fused last stage already left
   // min dx/(|v|+c) in d_scalars_[0].
-  if (cfg_.riemann == APK_RIEMANN_NONE) {  // calc_dt_hyp = false, hydro.cpp:354-361
-    new_dt_ = std::numeric_limits<Real>::max();
-    return TaskStatus::complete;
+  Real min_dt = std::numeric_limits<Real>::max();
+  Real dt_hyp_local = std::numeric_limits<Real>::max();
+  if (cfg_.riemann != APK_RIEMANN_NONE) {  // calc_dt_hyp = false otherwise, hydro.cpp:354-361
+    if (!have_device_min)
+      abi_check(apk_min_dt_async(&desc_, d_blocks_[cur_], d_scalars_, stream_), "apk_min_dt_async");
+    if (cfg_.nranks > 1) {
+      // replaces MPI_Allreduce(MIN) of driver.cpp:237 / hydro.cpp:127
+      abi_check(apk_allreduce_scalar(comm_, d_scalars_, 0, stream_), "apk_allreduce_scalar");
+    }
+    // pinned destinations: both copies are truly asynchronous, one synchronisation per cycle
+    int *h_status = reinterpret_cast<int *>(h_scalars_ + 1);
+    cuda_check(cudaMemcpyAsync(h_scalars_, d_scalars_, sizeof(double), cudaMemcpyDeviceToHost,
+                               S(stream_)), "dt D2H");
+    cuda_check(cudaMemcpyAsync(h_status, d_status_, sizeof(int), cudaMemcpyDeviceToHost, S(stream_)),
+               "status D2H");
+    Synchronize();
+    const double m = h_scalars_[0];
+    const int status = *h_status;
+    if (status != 0) {
+      // PARTHENON_REQUIRE in ConsToPrim (adiabatic_hydro.hpp:77-79,111-113)
+      throw std::runtime_error(status == 1
+                                   ? "Got negative density. Consider enabling first-order flux "
+                                     "correction or setting a reasonble density floor."
+                                   : "Got negative pressure. Consider enabling first-order flux "
+                                     "correction or setting a reasonble pressure or temperature floor.");
+    }
+    const Real dt = cfg_.cfl * m;
+    if (cfg_.fluid == APK_FLUID_GLMMHD && dt < dt_hyp) dt_hyp = dt;  // hydro.cpp:903-908
+    dt_hyp_local = dt;
+    min_dt = std::min(min_dt, dt);
   }
-  if (!have_device_min)
-    abi_check(apk_min_dt_async(&desc_, d_blocks_[cur_], d_scalars_, stream_), "apk_min_dt_async");
-  if (cfg_.nranks > 1) {
-    // replaces MPI_Allreduce(MIN) of driver.cpp:237 / hydro.cpp:127
-    abi_check(apk_allreduce_scalar(comm_, d_scalars_, 0, stream_), "apk_allreduce_scalar");
+  if (cfg_.diffint != 0) {  // hydro.cpp:935-963
+    const Real dt_diff = EstimateDiffusionTimestep();
+    if (cfg_.diffint == 1) {
+      min_dt = std::min(min_dt, dt_diff);
+    } else {
+      const Real r = cfg_.rkl2_max_dt_ratio;
+      if (r > 0.0 && dt_hyp_local / dt_diff > r) min_dt = std::min(min_dt, r * dt_diff);
+    }
+    dt_diff_ = std::min(dt_diff, dt_diff_);
   }
-  // pinned destinations: both copies are truly asynchronous, one synchronisation per cycle
-  int *h_status = reinterpret_cast<int *>(h_scalars_ + 1);
-  cuda_check(cudaMemcpyAsync(h_scalars_, d_scalars_, sizeof(double), cudaMemcpyDeviceToHost,
-                             S(stream_)), "dt D2H");
-  cuda_check(cudaMemcpyAsync(h_status, d_status_, sizeof(int), cudaMemcpyDeviceToHost, S(stream_)),
-             "status D2H");
-  Synchronize();
-  const double m = h_scalars_[0];
-  const int status = *h_status;
-  if (status != 0) {
-    // PARTHENON_REQUIRE in ConsToPrim (adiabatic_hydro.hpp:77-79,111-113)
-    throw std::runtime_error(status == 1
-                                 ? "Got negative density. Consider enabling first-order flux "
-                                   "correction or setting a reasonble density floor."
-                                 : "Got negative pressure. Consider enabling first-order flux "
-                                   "correction or setting a reasonble pressure or temperature floor.");
-  }
-  const Real dt = cfg_.cfl * m;
-  if (cfg_.fluid == APK_FLUID_GLMMHD && dt < dt_hyp) dt_hyp = dt;  // hydro.cpp:903-908
-  new_dt_ = dt;
+  new_dt_ = min_dt;
   return TaskStatus::complete;
 }
 
@@ -1353,6 +1488,7 @@ void HydroSim::Initialize(double tlim) {
   ApplyBoundaryConditions(0);
   FillDerived();
   dt_hyp = std::numeric_limits<Real>::max();
+  dt_diff_ = std::numeric_limits<Real>::max();
   EstimateTimestep(false);
   SetGlobalTimeStep();
 }
@@ -1362,6 +1498,9 @@ void HydroSim::MakeTaskCollection(TaskList &tl, int stage) {
   const Real beta_dt = integrator_.beta[stage - 1] * integrator_.dt;
   const bool last = (stage == integrator_.nstages);
   // fused path: the u1 <- u0 copy is folded into the first fused stage (APK_FUSED_SAVE_U1)
+  // Strang-split super time stepping, first half (hydro_driver.cpp:455-458)
+  if (stage == 1 && cfg_.diffint == 2)
+    tl.AddTask("sts_first_half", [this] { return SuperTimeStep(0.5 * tm.dt); });
   if (stage == 1 && !fused_) tl.AddTask("init_u1", [this] { return InitU1(); });
   tl.AddTask("start_bnd", [this] { return StartReceiveBoundBufs(); });
   if (fused_) {
@@ -1399,10 +1538,14 @@ void HydroSim::MakeTaskCollection(TaskList &tl, int stage) {
     tl.AddTask("fill_derived", [this] { return FillDerived(); });
   }
   if (last) {
+    // second half of the super time step (hydro_driver.cpp:578-583)
+    if (cfg_.diffint == 2)
+      tl.AddTask("sts_second_half", [this] { return SuperTimeStep(0.5 * tm.dt); });
     // hydro_driver.cpp:589-613: reset reduction Params, then EstimateTimestep
     tl.AddTask("reset_reduction_vars", [this] {
       mindx = std::numeric_limits<Real>::max();
       dt_hyp = std::numeric_limits<Real>::max();
+      dt_diff_ = std::numeric_limits<Real>::max();
       return TaskStatus::complete;
     });
     tl.AddTask("new_dt", [this] {

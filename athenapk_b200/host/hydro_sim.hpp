@@ -55,6 +55,15 @@ struct SimConfig {
   int nref = 0;
   int ref_level[4] = {0, 0, 0, 0};
   double ref_xmin[4][3] = {}, ref_xmax[4][3] = {};
+  // <diffusion> block (hydro.cpp:539-702), fixed coefficients
+  int diffint = 0;      // diffusion/integrator: 0 none, 1 unsplit, 2 rkl2
+  int conduction = 0;   // APK_CONDUCTION_*
+  int viscosity = 0;    // 1: isotropic
+  int resistivity = 0;  // 1: ohmic
+  double thermal_diff_coeff = 0.0, mom_diff_coeff = 0.0, ohm_diff_coeff = 0.0;
+  double cfl_diff = -1.0;           // diffusion/cfl (default: the hyperbolic cfl, hydro.cpp:697)
+  double rkl2_max_dt_ratio = -1.0;  // hydro.cpp:688
+  double conduction_sat_phi = 0.3;  // hydro.cpp:563-564
 };
 
 // time_integration/low_storage_integrator.cpp:53-132
@@ -150,6 +159,11 @@ class HydroSim {
   TaskStatus FluxCorrection();
   bool Multilevel() const { return multilevel_; }
   TaskStatus FillDerived();
+  // diffusion (src/hydro/diffusion/*, hydro_driver.cpp:36-344)
+  TaskStatus CalcDiffFluxes();
+  TaskStatus SuperTimeStep(Real tau);  // AddSTSTasks: one RKL2 super step of length tau
+  Real EstimateDiffusionTimestep();    // min of the Estimate*Timestep functions (hydro.cpp:935-946)
+  int last_s_rkl = 0;
   TaskStatus EstimateTimestep(bool have_device_min);
   void PreStepMeshUserWorkInLoop();
   void SetGlobalTimeStep();
@@ -286,6 +300,10 @@ class HydroSim {
   void LinearWaveMhdState(const BlockInfo &B, int k, int j, int i, double u[8]) const;
   double LinearWaveMhdA(int c, double x1, double x2, double x3) const;
   Real new_dt_ = std::numeric_limits<Real>::max();
+  Real dt_diff_ = std::numeric_limits<Real>::max();  // "dt_diff" Param (hydro.cpp:700,961-962)
+  apk_diffusion_t diff_{};
+  double *d_my0_ = nullptr, *d_yjm2_ = nullptr;      // RKL2 registers "MY0", "Yjm2"
+  double **d_my0_ptrs_ = nullptr, **d_yjm2_ptrs_ = nullptr;
   struct Timing { double ms = 0.0; long long count = 0; };
   std::map<std::string, Timing> timing_;
   bool timing_on_ = false;

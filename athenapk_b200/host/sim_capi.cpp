@@ -38,6 +38,8 @@ void apk_sim_default_config(apk_sim_config_t *c) {
   c->vceil = d.vceil; c->eceil = d.eceil;
   c->glmmhd_alpha = d.glmmhd_alpha; c->fp_mode = d.fp_mode; c->fused = d.fused;
   c->rank = 0; c->nranks = 1;
+  c->cfl_diff = d.cfl_diff; c->rkl2_max_dt_ratio = d.rkl2_max_dt_ratio;
+  c->conduction_sat_phi = d.conduction_sat_phi;
 }
 
 apk_sim_t *apk_sim_create(const apk_sim_config_t *c) {
@@ -57,6 +59,11 @@ apk_sim_t *apk_sim_create(const apk_sim_config_t *c) {
       k.ref_level[r] = c->ref_level[r];
       for (int i = 0; i < 3; ++i) { k.ref_xmin[r][i] = c->ref_xmin[r][i]; k.ref_xmax[r][i] = c->ref_xmax[r][i]; }
     }
+    k.diffint = c->diffint; k.conduction = c->conduction; k.viscosity = c->viscosity;
+    k.resistivity = c->resistivity; k.thermal_diff_coeff = c->thermal_diff_coeff;
+    k.mom_diff_coeff = c->mom_diff_coeff; k.ohm_diff_coeff = c->ohm_diff_coeff;
+    k.cfl_diff = c->cfl_diff; k.rkl2_max_dt_ratio = c->rkl2_max_dt_ratio;
+    k.conduction_sat_phi = c->conduction_sat_phi;
     s = new HydroSim(k);
     return 0;
   });
@@ -66,6 +73,8 @@ apk_sim_t *apk_sim_create(const apk_sim_config_t *c) {
 void apk_sim_destroy(apk_sim_t *s) { delete reinterpret_cast<HydroSim *>(s); }
 
 #define SIM(s) (reinterpret_cast<HydroSim *>(s))
+
+int apk_sim_last_s_rkl(const apk_sim_t *s) { return reinterpret_cast<const HydroSim *>(s)->last_s_rkl; }
 
 int apk_sim_nccl_unique_id(void *out, int nbytes) { return HydroSim::CommUniqueId(out, nbytes); }
 int apk_sim_init_comm(apk_sim_t *s, const void *uid, int nbytes) {

@@ -124,6 +124,47 @@ int apk_min_dt(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, double 
 int apk_min_dt_async(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, double *d_out,
                      void *stream);
 
+/* ---- <diffusion> block (src/hydro/diffusion/, docs/input.md "diffusion"): fixed coefficients.
+ * apk_diffusion_t carries what hydro.cpp:539-702 puts into the Hydro package Params. */
+#define APK_CONDUCTION_NONE 0
+#define APK_CONDUCTION_ISOTROPIC 1   /* diffusion/conduction = isotropic, conduction_coeff = fixed */
+#define APK_CONDUCTION_ANISOTROPIC 2 /* ... = anisotropic (field aligned, saturated; needs glmmhd) */
+typedef struct apk_diffusion {
+  int conduction;  /* APK_CONDUCTION_* */
+  int viscosity;   /* 1: diffusion/viscosity = isotropic, viscosity_coeff = fixed */
+  int resistivity; /* 1: diffusion/resistivity = ohmic, resistivity_coeff = fixed */
+  double thermal_diff_coeff, mom_diff_coeff, ohm_diff_coeff; /* *_diff_coeff_code */
+  double conduction_sat_prefac; /* 5 * diffusion/conduction_sat_phi (hydro.cpp:604) */
+} apk_diffusion_t;
+
+/* ResetFluxes (src/hydro/hydro_driver.cpp:36-91): zero flux[d] over the faces the flux divergence
+ * reads (the RKL2 sub-steps start from pure diffusive fluxes) */
+int apk_reset_fluxes(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, void *stream);
+/* CalcDiffFluxes (src/hydro/diffusion/diffusion.cpp:19-53): ADDS the conductive / viscous / Ohmic
+ * fluxes computed from prim (ghosts valid) to flux[0..ndim-1] -- conduction.cpp:193-260 (isotropic)
+ * and :265-550 (anisotropic + saturation), viscosity.cpp:98-291, resistivity.cpp:89-232.  With
+ * diffusion/integrator = unsplit the reference calls it at the end of CalculateFluxes
+ * (hydro.cpp:1202-1205); with rkl2 inside every sub-step (hydro_driver.cpp:246, :312). */
+int apk_calc_diff_fluxes(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                         const apk_diffusion_t *diff, void *stream);
+/* First RKL2 sub-step (hydro_driver.cpp:196-208 Y0 <- base into cons_u1, :255
+ * Update::FluxDivergence into MY0, RKL2StepFirst :93-126): base = Y0 + mu~_1 tau MY0, Yjm2 = Y0.
+ * d_my0 / d_yjm2: device arrays of per-block pointers to the "MY0" / "Yjm2" registers
+ * (same layout as cons). */
+int apk_rkl2_step_first(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                        double *const *d_my0, double *const *d_yjm2, int s_rkl, double tau,
+                        void *stream);
+/* RKL2StepOther (hydro_driver.cpp:128-166) for sub-step j: reads the diffusive fluxes of base */
+int apk_rkl2_step_other(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                        double *const *d_my0, double *const *d_yjm2, double mu_j, double nu_j,
+                        double mu_tilde_j, double gamma_tilde_j, double tau, void *stream);
+/* EstimateConductionTimestep, general branch (conduction.cpp:91-186, anisotropic conduction): leaves
+ * the minimum over interior cells (before cfl_diff * fac) in d_out[0]; DBL_MAX if no cell
+ * constrains.  The fixed-coefficient estimates (conduction.cpp:64-89, viscosity.cpp:55-88,
+ * resistivity.cpp:52-80) depend on dx only and are evaluated by the caller. */
+int apk_min_dt_conduction(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
+                          const apk_diffusion_t *diff, double *d_out, void *stream);
+
 /* ---- same-device part of parthenon::AddBoundaryExchangeTasks (bvals/comms/
  * boundary_communication.cpp:48-348, bnd_info.cpp:105-230) + physical boundary conditions
  * (bvals/boundary_conditions.cpp:36-59, boundary_conditions_generic.hpp:174-262,

@@ -33,6 +33,15 @@ typedef struct apk_sim_config {
   int nref;
   int ref_level[4];
   double ref_xmin[4][3], ref_xmax[4][3];
+  /* <diffusion> (hydro.cpp:539-702), fixed coefficients */
+  int diffint;      /* diffusion/integrator: 0 none, 1 unsplit, 2 rkl2 */
+  int conduction;   /* APK_CONDUCTION_* */
+  int viscosity;    /* 1: isotropic */
+  int resistivity;  /* 1: ohmic */
+  double thermal_diff_coeff, mom_diff_coeff, ohm_diff_coeff;
+  double cfl_diff;           /* diffusion/cfl; <= 0: parthenon/time/cfl */
+  double rkl2_max_dt_ratio;  /* <= 0: no cap */
+  double conduction_sat_phi; /* default 0.3 */
 } apk_sim_config_t;
 
 const char *apk_sim_last_error(void);
@@ -74,6 +83,8 @@ double apk_sim_dt(const apk_sim_t *s);
 int apk_sim_ncycle(const apk_sim_t *s);
 double apk_sim_c_h(const apk_sim_t *s);
 long long apk_sim_fofc_corrections(const apk_sim_t *s);
+/* RKL2 stages of the last super time step (diffusion/integrator = rkl2) */
+int apk_sim_last_s_rkl(const apk_sim_t *s);
 /* fused stages whose FOFC acceptance test failed somewhere and that were redone with the
  * flux-materialising tasks (0 for decks where FOFC never triggers) */
 long long apk_sim_fofc_redone_stages(const apk_sim_t *s);

@@ -226,8 +226,8 @@ def test_fofc_deck_runs_like_reference_when_nothing_triggers(apk):
 
 
 # ---------------------------------------------------------------- golden known answers
-from trace_util import (AMR_DECKS, DECKS, GAMMA_DECK, TRACES, check_lw_row, follow_trace,  # noqa: E402
-                        lw_kwargs, lw_pgen)
+from trace_util import (AMR_DECKS, DECKS, DIFF_DECKS, DIFF_TRACES, GAMMA_DECK, TRACES,  # noqa: E402
+                        check_lw_row, follow_trace, lw_kwargs, lw_pgen)
 
 LW_CASES = TRACES["linear_wave"] + TRACES["linear_wave_mhd"] + TRACES["linear_wave_mhd_families"]
 
@@ -295,6 +295,44 @@ def test_static_refinement_reference_traces(apk, name):
     o.run(tlim, TRACES[name]["ncycle"])
     assert (s.time, s.dt) == (o.time, o.dt)
     assert_bitexact(s, o, name)
+    s.close()
+
+
+@pytest.mark.parametrize("name", sorted(DIFF_DECKS))
+def test_diffusion_reference_traces(apk, name):
+    """<diffusion> block (src/hydro/diffusion/*, hydro_driver.cpp:36-344): unsplit and
+    RKL2 super-time-stepping integration of isotropic / anisotropic (saturated) thermal conduction,
+    isotropic viscosity and Ohmic resistivity with fixed coefficients, in 1-D, 2-D and 3-D.  Strict
+    mode: every cycle's (time, dt) equals the unmodified reference's printout at all 17 digits, the
+    RKL2 stage counts equal the ones it reports, and the final state equals the oracle's bit for bit."""
+    kw, pgen, pars, tlim = DIFF_DECKS[name]
+    s, o = make_pair(apk, pgen, pars, tlim=tlim, fp_mode="strict", **kw)
+    assert not s.fused_active
+    case = DIFF_TRACES[name]
+    sts = []
+
+    def adv(s, tlim, c):
+        s.execute(tlim, c)
+        sts.append(s.last_s_rkl)
+
+    follow_trace(s, case["trace"], tlim, adv)
+    if kw["diffint"] == "rkl2":
+        assert sts == case["s_rkl"][1::2]
+    o.run(tlim, case["ncycle"])
+    assert (s.time, s.dt) == (o.time, o.dt)
+    assert_bitexact(s, o, name)
+    s.close()
+
+
+def test_diffusion_fast_mode_close_to_oracle(apk):
+    """FMA mode of the diffusion kernels: the 3-D RKL2 deck stays within 1e-12 relative L1 of the
+    oracle after 6 cycles (60 RKL2 sub-steps)."""
+    kw, pgen, pars, tlim = DIFF_DECKS["ot3d_rkl2_aniso"]
+    s, o = make_pair(apk, pgen, pars, tlim=tlim, fp_mode="fast", **kw)
+    o.run(tlim, 6)
+    s.execute(tlim, 6)
+    assert s.ncycle == o.ncycle
+    assert rel_l1(s, o, "cons") <= 1e-12
     s.close()
 
 
