@@ -45,6 +45,13 @@ CASES = [
     dict(fluid="glmmhd", recon="ppm", riemann="hlld", integrator="vl2", ng=3, nx=[64, 64, 64],
          mb=[16, 16, 16], xmin=[0, 0, 0], xmax=[1, 1, 1], pgen="ot3d", fused=True, cycles=2,
          min_world=4),
+    # <diffusion> block over several ranks: RKL2 super time stepping (every sub-step exchanges
+    # ghost zones) with anisotropic conduction, viscosity and resistivity; the anisotropic
+    # conduction time step is a device reduction + all-reduce
+    dict(fluid="glmmhd", recon="ppm", riemann="hlld", integrator="vl2", ng=3, nx=[32, 32, 32],
+         mb=[16, 16, 16], xmin=[0, 0, 0], xmax=[1, 1, 1], pgen="ot3d", fused=False, cycles=3,
+         diffint="rkl2", conduction="anisotropic", thermal_diff_coeff=0.1, viscosity="isotropic",
+         mom_diff_coeff=0.04, resistivity="ohmic", ohm_diff_coeff=0.05),
 ]
 
 
