@@ -12,6 +12,8 @@
 //   B200::DednerSource                       GLMMHD::SourceFun_t  glmmhd/glmmhd.hpp:22
 //   B200::ConsToPrim / B200::EstimateTimestep  pkg->FillDerivedMesh / EstimateTimestepMesh
 //                                                                 hydro.cpp:707-713
+//   B200::CalcDiffFluxes / ResetFluxes       CalcDiffFluxes (diffusion/diffusion.cpp:19-53), ResetFluxes
+//   B200::RKL2StepFirst / RKL2StepOther      (hydro_driver.cpp:36-166), fixed-coefficient diffusion
 //   B200::FusedStage                         calc_flux + update + source + fill_derived in one task
 //   B200::StartHalo / TestHalo / FinishHalo  the three tasks of AddBoundaryExchangeTasks
 //                                            (bvals/comms/boundary_communication.cpp:405-445)
@@ -26,6 +28,7 @@
 #include "../include/apk_b200.h"
 #include "eos/adiabatic_glmmhd.hpp"
 #include "eos/adiabatic_hydro.hpp"
+#include "hydro/diffusion/diffusion.hpp"
 #include "main.hpp"
 
 namespace Hydro::B200 {
@@ -224,6 +227,86 @@ void DednerSource(MeshData<Real> *md, const Real beta_dt) {
 }
 template void DednerSource<false>(MeshData<Real> *, const Real);
 template void DednerSource<true>(MeshData<Real> *, const Real);
+
+// ---- <diffusion>: CalcDiffFluxes (diffusion/diffusion.cpp:19-53) for the fixed-coefficient
+// processes; Spitzer coefficients stay with the reference's kernels
+static bool DiffusionSupported(parthenon::StateDescriptor *pkg) {
+  const auto cond = pkg->Param<Conduction>("conduction");
+  if (cond != Conduction::none &&
+      pkg->Param<ThermalDiffusivity>("thermal_diff").GetCoeffType() != ConductionCoeff::fixed)
+    return false;
+  return true;
+}
+
+static apk_diffusion_t DiffusionParams(parthenon::StateDescriptor *pkg) {
+  apk_diffusion_t d{};
+  const auto cond = pkg->Param<Conduction>("conduction");
+  if (cond != Conduction::none) {
+    d.conduction = (cond == Conduction::isotropic) ? APK_CONDUCTION_ISOTROPIC : APK_CONDUCTION_ANISOTROPIC;
+    d.thermal_diff_coeff = pkg->Param<ThermalDiffusivity>("thermal_diff").Get(0.0, 0.0);
+    d.conduction_sat_prefac = pkg->Param<Real>("conduction_sat_prefac");
+  }
+  if (pkg->Param<Viscosity>("viscosity") != Viscosity::none) {
+    d.viscosity = 1;
+    d.mom_diff_coeff = pkg->Param<MomentumDiffusivity>("mom_diff").Get(0.0, 0.0);
+  }
+  if (pkg->Param<Resistivity>("resistivity") != Resistivity::none) {
+    d.resistivity = 1;
+    d.ohm_diff_coeff = pkg->Param<OhmicDiffusivity>("ohm_diff").Get(0.0, 0.0);
+  }
+  return d;
+}
+
+TaskStatus CalcDiffFluxes(parthenon::StateDescriptor *pkg, MeshData<Real> *md) {
+  if (!DiffusionSupported(pkg)) return ::CalcDiffFluxes(pkg, md);
+  PackCache &c = GetCache(md, U1(md));
+  const apk_diffusion_t d = DiffusionParams(pkg);
+  Check(apk_calc_diff_fluxes(&c.desc, c.d_blocks.data(), &d, Stream()));
+  return TaskStatus::complete;
+}
+
+// ---- ResetFluxes (hydro_driver.cpp:36-91)
+TaskStatus ResetFluxes(MeshData<Real> *md) {
+  PackCache &c = GetCache(md, U1(md));
+  Check(apk_reset_fluxes(&c.desc, c.d_blocks.data(), Stream()));
+  return TaskStatus::complete;
+}
+
+// per-block "cons" pointers of an RKL2 register (MeshData "MY0" / "Yjm2", hydro_driver.cpp:211-212)
+// (pointer table stored as integers: a ParArray1D<double *> would be a rank-2 view of doubles)
+static double *const *RegisterPointers(MeshData<Real> *md) {
+  static std::map<MeshData<Real> *, parthenon::ParArray1D<std::uintptr_t>> cache;
+  auto &p = cache[md];
+  if (static_cast<int>(p.size()) != md->NumBlocks()) {
+    p = parthenon::ParArray1D<std::uintptr_t>("apk_reg_ptrs", md->NumBlocks());
+    auto h = Kokkos::create_mirror_view(p);
+    for (int b = 0; b < md->NumBlocks(); ++b)
+      h(b) = reinterpret_cast<std::uintptr_t>(md->GetBlockData(b)->Get("cons").data.data());
+    Kokkos::deep_copy(p, h);
+  }
+  return reinterpret_cast<double *const *>(p.data());
+}
+
+// ---- RKL2StepFirst (hydro_driver.cpp:93-126) incl. the Y0 <- base copy (:196-208) and
+// Update::FluxDivergence(base -> MY0) (:255); md_Yjm1 is "base", md_Y0 is "u1"
+TaskStatus RKL2StepFirst(MeshData<Real> *md_Y0, MeshData<Real> *md_Yjm1, MeshData<Real> *md_Yjm2,
+                         MeshData<Real> *md_MY0, const int s_rkl, const Real tau) {
+  PackCache &c = GetCache(md_Yjm1, md_Y0);
+  Check(apk_rkl2_step_first(&c.desc, c.d_blocks.data(), RegisterPointers(md_MY0),
+                            RegisterPointers(md_Yjm2), s_rkl, tau, Stream()));
+  return TaskStatus::complete;
+}
+
+// ---- RKL2StepOther (hydro_driver.cpp:128-166)
+TaskStatus RKL2StepOther(MeshData<Real> *md_Y0, MeshData<Real> *md_Yjm1, MeshData<Real> *md_Yjm2,
+                         MeshData<Real> *md_MY0, const Real mu_j, const Real nu_j,
+                         const Real mu_tilde_j, const Real gamma_tilde_j, const Real tau) {
+  PackCache &c = GetCache(md_Yjm1, md_Y0);
+  Check(apk_rkl2_step_other(&c.desc, c.d_blocks.data(), RegisterPointers(md_MY0),
+                            RegisterPointers(md_Yjm2), mu_j, nu_j, mu_tilde_j,
+                            gamma_tilde_j, tau, Stream()));
+  return TaskStatus::complete;
+}
 
 // ---- pkg->FillDerivedMesh (hydro.cpp:707,712): ConservedToPrimitive over the entire range
 void ConsToPrim(MeshData<Real> *md) {
