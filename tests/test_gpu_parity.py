@@ -298,6 +298,24 @@ def test_static_refinement_reference_traces(apk, name):
     s.close()
 
 
+def test_config4_full_size_reference_trace(apk):
+    """BASELINE config 4 at FULL size -- 256^3, 512 meshblocks of 32^3, GLM-MHD VL2+PPM+HLLD, the
+    Orszag-Tang state of baseline/decks/orszag_tang_3d.in, i.e. exactly what bench.py times -- in
+    strict mode through the fused stage kernel: (time, dt) of 4 cycles equal the printout of the
+    unmodified reference (tests/golden/reference_trace_config4_256.json, 4 min 22 s of its serial
+    build) at all 17 digits; dt is a minimum over all 16.8 M cells."""
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden",
+                                       "reference_trace_config4_256.json")))["orszag_tang_3d_256"]
+    kw = dict(DECKS["orszag_tang_3d"][0], nx=(256, 256, 256))
+    s = apk.HydroSim(fp_mode="strict", fused=True, **kw)
+    s.pgen("orszag_tang", [])
+    s.initialize(1000.0)
+    assert s.fused_active and s.nblocks == 512
+    follow_trace(s, case["trace"], 1000.0, _advance)
+    assert s.ncycle == case["ncycle"]
+    s.close()
+
+
 @pytest.mark.parametrize("name", sorted(DIFF_DECKS))
 def test_diffusion_reference_traces(apk, name):
     """<diffusion> block (src/hydro/diffusion/*, hydro_driver.cpp:36-344): unsplit and
