@@ -137,6 +137,26 @@ def test_floors_and_ceilings(apk):
         s.close()
 
 
+def test_energy_floor_and_ceiling(apk):
+    """hydro/efloor and hydro/eceil (specific internal energy floor / ceiling of ConsToPrim,
+    adiabatic_hydro.hpp:117-140, adiabatic_glmmhd.hpp:141-165) on the GPU, fused and un-fused,
+    hydro and GLM-MHD: the random state spans both limits, so both branches rewrite cells."""
+    for fluid, riemann in (("euler", "hllc"), ("glmmhd", "hlld")):
+        kw = dict(fluid=fluid, recon="plm", riemann=riemann, integrator="vl2", ng=2,
+                  nx=(16, 16, 16), mb=(8, 8, 8), efloor=1.35, eceil=1.65, **BOX3)
+        for fused in (False, True):
+            s, o = make_pair(apk, "random", (4, 0.3), fp_mode="strict", fused=fused, **kw)
+            ref = o.prim(0)
+            eint = ref[4] / ((kw.get("gamma", 5.0 / 3.0) - 1.0) * ref[0])
+            # the limits are active somewhere in the initial state already
+            assert np.isclose(eint.min(), 1.35) and np.isclose(eint.max(), 1.65)
+            o.run(None, 2)
+            s.execute(None, 2)
+            assert (s.time, s.dt) == (o.time, o.dt)
+            assert_bitexact(s, o, "efloor/eceil %s fused=%d" % (fluid, fused))
+            s.close()
+
+
 @pytest.mark.parametrize("nx,mb", [((64, 64, 64), (32, 32, 32)), ((48, 48, 48), (24, 24, 24)),
                                    ((32, 32, 32), (16, 16, 16))])
 def test_tma_staged_variant_is_bit_identical(apk, nx, mb, monkeypatch):
