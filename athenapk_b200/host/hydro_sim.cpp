@@ -123,8 +123,8 @@ HydroSim::HydroSim(const SimConfig &cfg)
     if (cfg_.ng % 2 != 0)
       throw std::runtime_error("Selected nghost is incompatible with mesh refinement because it is "
                                "not a multiple of 2.");
-    if (cfg_.nranks != 1 || cfg_.nref > 4)
-      throw std::runtime_error("apk_host: refined meshes run on one rank (up to 4 regions)");
+    if (cfg_.nref > 4)
+      throw std::runtime_error("apk_host: at most 4 static refinement regions");
     for (int f = 0; f < 2 * ndim_; ++f)
       if (cfg_.bc[f] != APK_BC_PERIODIC)
         throw std::runtime_error("apk_host: refined meshes are implemented for periodic domains");
@@ -224,57 +224,30 @@ void HydroSim::BuildMesh() {
     const auto &l = order[g].second;
     gid_of_loc_[l[0] + nb_[0] * (l[1] + nb_[1] * l[2])] = g;
   }
-  std::vector<Leaf> leaves;
   if (multilevel_) {
-    leaves = BuildLeaves();
-    nblocks_global_ = (int)leaves.size();
+    leaves_ = BuildLeaves();
+    nblocks_global_ = (int)leaves_.size();
     for (int d = 0; d < 3; ++d) nc_[d] = (d < ndim_) ? cfg_.mb[d] / 2 + 2 * cfg_.ng : 1;
   }
   // equal split (remainder to the first ranks)
-  const int base = nblocks_global_ / cfg_.nranks, rem = nblocks_global_ % cfg_.nranks;
-  gid_lo_ = cfg_.rank * base + std::min(cfg_.rank, rem);
-  gid_hi_ = gid_lo_ + base + (cfg_.rank < rem ? 1 : 0);
+  gid_lo_ = GidLo(cfg_.rank);
+  gid_hi_ = GidLo(cfg_.rank + 1);
   if (gid_hi_ <= gid_lo_) throw std::runtime_error("apk_host: rank without meshblocks");
-
-  // forest.cpp:66-141 + tree.cpp:296-318: tree decomposition then block-in-tree bounds
-  bool any_sym = false;
-  int mcp2 = 1 << 30;
-  for (int d = 0; d < 3; ++d) {
-    if (cfg_.nx[d] == 1) { any_sym = true; continue; }
-    mcp2 = std::min(mcp2, MaximumPowerOf2Divisor(nb_[d]));
-  }
-  if (any_sym) mcp2 = 1;
   blocks_.clear();
   for (int g = gid_lo_; g < gid_hi_; ++g) {
-    BlockInfo B{};
-    B.gid = g;
-    B.level = multilevel_ ? leaves[g].level : 0;
-    for (int d = 0; d < 3; ++d) {
-      B.loc[d] = multilevel_ ? leaves[g].lx[d] : loc_of_gid_[g][d];
-      if (cfg_.nx[d] == 1) {
-        B.bxmin[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(0, 0, 1),
-                                                        cfg_.xmin[d], cfg_.xmax[d]);
-        B.bxmax[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(0, 2, 1),
-                                                        cfg_.xmin[d], cfg_.xmax[d]);
-      } else {
-        // a block of refinement level l: its tree is cut mcp2 * 2^l times (tree.cpp:296-318)
-        const int per_tree = mcp2 << B.level;
-        const int ntree = nb_[d] / mcp2, it = B.loc[d] / per_tree, lx = B.loc[d] % per_tree;
-        const double tmin = SymmetrizedLogicalToActualPosition(
-            IndexToSymmetrizedCoordinate(it, 0, ntree), cfg_.xmin[d], cfg_.xmax[d]);
-        const double tmax = SymmetrizedLogicalToActualPosition(
-            IndexToSymmetrizedCoordinate(it, 2, ntree), cfg_.xmin[d], cfg_.xmax[d]);
-        B.bxmin[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(lx, 0, per_tree),
-                                                        tmin, tmax);
-        B.bxmax[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(lx, 2, per_tree),
-                                                        tmin, tmax);
-      }
-      // uniform_coordinates.hpp:32-36
-      B.dx[d] = (B.bxmax[d] - B.bxmin[d]) / cfg_.mb[d];
-      const int istart = (cfg_.nx[d] == 1) ? 0 : cfg_.ng;
-      B.xmin[d] = B.bxmin[d] - istart * B.dx[d];
+    if (multilevel_) blocks_.push_back(MakeBlockInfo(g, leaves_[g].level, leaves_[g].lx));
+    else blocks_.push_back(MakeBlockInfo(g, 0, loc_of_gid_[g].data()));
+  }
+  if (multilevel_) {
+    // hydro.cpp:65-95 + the MPI_Allreduce(MIN) of hydro.cpp:127: every rank knows every leaf
+    Real m = std::numeric_limits<Real>::max();
+    for (int g = 0; g < nblocks_global_; ++g) {
+      const BlockInfo B = MakeBlockInfo(g, leaves_[g].level, leaves_[g].lx);
+      m = std::fmin(m, B.dx[0]);
+      if (n_[1] > 1) m = std::fmin(m, B.dx[1]);
+      if (n_[2] > 1) m = std::fmin(m, B.dx[2]);
     }
-    blocks_.push_back(B);
+    global_mindx_ = m;
   }
 
   desc_.nblocks = (int)blocks_.size();
@@ -293,6 +266,57 @@ void HydroSim::BuildMesh() {
   desc_.efloor = cfg_.efloor;
   desc_.vceil = cfg_.vceil;
   desc_.eceil = cfg_.eceil;
+}
+
+int HydroSim::GidLo(int rank) const {
+  const int base = nblocks_global_ / cfg_.nranks, rem = nblocks_global_ % cfg_.nranks;
+  return rank * base + std::min(rank, rem);
+}
+
+int HydroSim::RankOfGid(int gid) const {
+  const int base = nblocks_global_ / cfg_.nranks, rem = nblocks_global_ % cfg_.nranks;
+  const int cut = rem * (base + 1);
+  return (gid < cut) ? gid / (base + 1) : rem + (gid - cut) / base;
+}
+
+// forest.cpp:66-141 + tree.cpp:296-318: tree decomposition then block-in-tree bounds
+BlockInfo HydroSim::MakeBlockInfo(int gid, int level, const int *loc) const {
+  bool any_sym = false;
+  int mcp2 = 1 << 30;
+  for (int d = 0; d < 3; ++d) {
+    if (cfg_.nx[d] == 1) { any_sym = true; continue; }
+    mcp2 = std::min(mcp2, MaximumPowerOf2Divisor(nb_[d]));
+  }
+  if (any_sym) mcp2 = 1;
+  BlockInfo B{};
+  B.gid = gid;
+  B.level = level;
+  for (int d = 0; d < 3; ++d) {
+    B.loc[d] = loc[d];
+    if (cfg_.nx[d] == 1) {
+      B.bxmin[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(0, 0, 1),
+                                                      cfg_.xmin[d], cfg_.xmax[d]);
+      B.bxmax[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(0, 2, 1),
+                                                      cfg_.xmin[d], cfg_.xmax[d]);
+    } else {
+      // a block of refinement level l: its tree is cut mcp2 * 2^l times (tree.cpp:296-318)
+      const int per_tree = mcp2 << B.level;
+      const int ntree = nb_[d] / mcp2, it = B.loc[d] / per_tree, lx = B.loc[d] % per_tree;
+      const double tmin = SymmetrizedLogicalToActualPosition(
+          IndexToSymmetrizedCoordinate(it, 0, ntree), cfg_.xmin[d], cfg_.xmax[d]);
+      const double tmax = SymmetrizedLogicalToActualPosition(
+          IndexToSymmetrizedCoordinate(it, 2, ntree), cfg_.xmin[d], cfg_.xmax[d]);
+      B.bxmin[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(lx, 0, per_tree),
+                                                      tmin, tmax);
+      B.bxmax[d] = SymmetrizedLogicalToActualPosition(IndexToSymmetrizedCoordinate(lx, 2, per_tree),
+                                                      tmin, tmax);
+    }
+    // uniform_coordinates.hpp:32-36
+    B.dx[d] = (B.bxmax[d] - B.bxmin[d]) / cfg_.mb[d];
+    const int istart = (cfg_.nx[d] == 1) ? 0 : cfg_.ng;
+    B.xmin[d] = B.bxmin[d] - istart * B.dx[d];
+  }
+  return B;
 }
 
 // ---- static mesh refinement -----------------------------------------------------------------
@@ -390,13 +414,16 @@ std::vector<HydroSim::Leaf> HydroSim::BuildLeaves() const {
 }
 
 void HydroSim::BuildMultilevelNeighbors() {
+  // every rank builds the topology of ALL leaves (ids = global block ids): items of the exchange
+  // plan exist wherever either side of a relation is local
   std::map<LeafKey, int> index;
-  for (size_t b = 0; b < blocks_.size(); ++b)
-    index[{blocks_[b].level, blocks_[b].loc[0], blocks_[b].loc[1], blocks_[b].loc[2]}] = (int)b;
-  nbrinfo_.assign(blocks_.size(), NbrInfo{});
-  for (size_t b = 0; b < blocks_.size(); ++b) {
-    const BlockInfo &B = blocks_[b];
-    NbrInfo &N = nbrinfo_[b];
+  for (size_t g = 0; g < leaves_.size(); ++g)
+    index[{leaves_[g].level, leaves_[g].lx[0], leaves_[g].lx[1], leaves_[g].lx[2]}] = (int)g;
+  gnbr_.assign(leaves_.size(), NbrInfo{});
+  for (size_t b = 0; b < leaves_.size(); ++b) {
+    struct { int level; int loc[3]; } B = {leaves_[b].level,
+                                           {leaves_[b].lx[0], leaves_[b].lx[1], leaves_[b].lx[2]}};
+    NbrInfo &N = gnbr_[b];
     N.has_coarser = false;
     for (int idx = 0; idx < 27; ++idx) {
       N.type[idx] = 0;
@@ -451,6 +478,8 @@ void HydroSim::BuildMultilevelNeighbors() {
       }
     }
   }
+  nbrinfo_.assign(blocks_.size(), NbrInfo{});
+  for (size_t b = 0; b < blocks_.size(); ++b) nbrinfo_[b] = gnbr_[gid_lo_ + b];
 }
 
 void HydroSim::BuildNeighbors() {
@@ -467,7 +496,9 @@ void HydroSim::BuildNeighbors() {
       for (int f = 0; f < 6; ++f) hb.bc[f] = APK_BC_BLOCK;
       // the same-level table drives apk_copy_ghosts_local; other levels go through the plan
       for (int idx = 0; idx < 27; ++idx)
-        hb.nbr[idx] = (nbrinfo_[b].type[idx] == 1) ? nbrinfo_[b].idx[idx][0] : APK_NBR_NONE;
+        hb.nbr[idx] = (nbrinfo_[b].type[idx] == 1 && IsLocal(nbrinfo_[b].idx[idx][0]))
+                          ? nbrinfo_[b].idx[idx][0] - gid_lo_
+                          : APK_NBR_NONE;  // (same-level neighbours on other ranks: ml_same_remote_)
     }
     return;
   }
@@ -578,7 +609,7 @@ void HydroSim::UploadBlocks() {
   if (multilevel_) {
     cuda_check(cudaMalloc(&d_coarse_, CoarseElems() * nbl * sizeof(double)), "cudaMalloc coarse");
     cuda_check(cudaMemset(d_coarse_, 0, CoarseElems() * nbl * sizeof(double)), "memset");
-    BuildMultilevelPlan();
+    if (cfg_.nranks == 1) BuildMultilevelPlan();  // several ranks: after the peer mapping (InitComm)
   }
   cuda_check(cudaMalloc(&d_scalars_, 64 * sizeof(double)), "cudaMalloc scalars");
   cuda_check(cudaMemset(d_scalars_, 0, 64 * sizeof(double)), "memset scalars");
@@ -599,7 +630,7 @@ void HydroSim::UploadBlocks() {
 // contributes one slab to that peer's send buffer and one to its receive buffer.  Both sides
 // order slabs by (receiver gid, receiver-side offset index) so offsets agree without talking.
 void HydroSim::BuildHaloPlan() {
-  if (cfg_.nranks == 1) return;
+  if (cfg_.nranks == 1 || multilevel_) return;  // refined meshes: peer pulls, BuildMultilevelPlan
   const int ng = cfg_.ng;
   const int s[3] = {cfg_.ng, ndim_ >= 2 ? cfg_.ng : 0, ndim_ >= 3 ? cfg_.ng : 0};
   struct Entry {
@@ -708,6 +739,25 @@ int HydroSim::InitComm(const void *uid, int nbytes) {
   ncclComm_t c;
   if (ncclCommInitRank(&c, cfg_.nranks, id, cfg_.rank) != ncclSuccess) return -2;
   comm_ = reinterpret_cast<ncclComm *>(c);
+  if (multilevel_) {
+    // refined mesh over several ranks: every cross-rank relation of the multilevel exchange
+    // (same level, fine -> coarse ghosts, coarse -> coarse buffers, flux correction) is a box copy
+    // that PULLS from the owner's memory, mapped with CUDA IPC; stage barriers order the phases
+    cuda_check(cudaMalloc(&d_barrier_, 2 * sizeof(int)), "barrier word");
+    cuda_check(cudaMemset(d_barrier_, 0, 2 * sizeof(int)), "barrier word");
+    std::vector<int> need(cfg_.nranks, 1);
+    need[cfg_.rank] = 0;
+    void *bufs[2] = {d_cons_, d_coarse_};
+    ml_peer_.assign((size_t)cfg_.nranks * 2, nullptr);
+    int all_ok = 0;
+    abi_check(apk_p2p_map_peers(comm_, cfg_.rank, cfg_.nranks, bufs, 2, need.data(), ml_peer_.data(),
+                                &all_ok, stream_), "apk_p2p_map_peers");
+    if (!all_ok)
+      throw std::runtime_error("apk_host: refined meshes on several ranks need CUDA peer access "
+                               "(IPC) between the GPUs");
+    BuildMultilevelPlan();
+    return 0;
+  }
   // the exchange itself lives behind the C-ABI (apk_halo_*): hand it the slab lists
   std::vector<apk_halo_peer_t> hp;
   for (const Peer &p : peers_) hp.push_back({p.rank, p.send_off, p.send_cnt, p.recv_off, p.recv_cnt});
@@ -1165,6 +1215,17 @@ TaskStatus HydroSim::StartReceiveBoundBufs() {
 
 TaskStatus HydroSim::SendBoundBufs(int with_prim, bool local_done, bool need_barrier) {
   nccl_inflight_ = false;
+  if (multilevel_ && cfg_.nranks > 1) {
+    // refined mesh over several ranks: every rank has finished its update (barrier), then the
+    // same-level ghost slabs of remote neighbours are pulled from the owners' memory
+    if (!comm_) throw std::runtime_error("apk_host: multi-rank run without InitComm");
+    StageBarrier();
+    abi_check(apk_copy_ghosts_local(&desc_, d_blocks_[cur_], with_prim, stream_),
+              "apk_copy_ghosts_local");
+    abi_check(apk_box_copy(static_cast<const apk_box_item_t *>(ml_same_remote_.d), ml_same_remote_.n,
+                           nvar_, stream_), "apk_box_copy (remote same level)");
+    return TaskStatus::complete;
+  }
   if (cfg_.nranks > 1 && local_done && p2p_) {
     // remote neighbours were served by peer stores of the stage kernel as well: no pack, no
     // send/recv, no unpack -- only the stage boundary
@@ -1224,8 +1285,18 @@ TaskStatus HydroSim::SetBounds(int with_prim) {
 void HydroSim::BuildMultilevelPlan() {
   const int ng = cfg_.ng;
   const size_t per = BlockFieldElems(), cper = CoarseElems();
-  auto fine_ptr = [&](double *base, int b) { return base + (size_t)b * per; };
-  auto coarse_ptr = [&](int b) { return d_coarse_ + (size_t)b * cper; };
+  // arrays of a block by GLOBAL id: local slabs, or the IPC-mapped slabs of the owning rank
+  auto cons_ptr = [&](int g) -> double * {
+    if (IsLocal(g)) return d_cons_ + (size_t)(g - gid_lo_) * per;
+    const int r = RankOfGid(g);
+    return static_cast<double *>(ml_peer_[(size_t)r * 2 + 0]) + (size_t)(g - GidLo(r)) * per;
+  };
+  auto coarse_ptr = [&](int g) -> double * {
+    if (IsLocal(g)) return d_coarse_ + (size_t)(g - gid_lo_) * cper;
+    const int r = RankOfGid(g);
+    return static_cast<double *>(ml_peer_[(size_t)r * 2 + 1]) + (size_t)(g - GidLo(r)) * cper;
+  };
+  auto flux_ptr = [&](int d, int g) { return d_flux_[d] + (size_t)(g - gid_lo_) * per; };  // local only
   const int cis = ng;
   auto cie = [&](int d) { return ng + cfg_.mb[d] / 2 - 1; };
   const int is[3] = {cfg_.ng, ndim_ >= 2 ? cfg_.ng : 0, ndim_ >= 3 ? cfg_.ng : 0};
@@ -1238,25 +1309,28 @@ void HydroSim::BuildMultilevelPlan() {
     else if (o > 0) { *lo = t0 + 1; *hi = t0 + depth; }
     else { *lo = s0 - depth; *hi = s0 - 1; }
   };
-  auto amr_item = [&](double *fine, int b, const int *lo, const int *hi) {
+  // restriction / prolongation item on a LOCAL block g (its arrays and coordinates)
+  auto amr_item = [&](double *fine, int g, const int *lo, const int *hi) {
+    const BlockInfo &L = blocks_[g - gid_lo_];
     apk_amr_item_t it{};
     it.fine = fine;
-    it.coarse = coarse_ptr(b);
+    it.coarse = coarse_ptr(g);
     for (int d = 0; d < 3; ++d) {
       it.nf[d] = n_[d];
       it.nc[d] = nc_[d];
       it.lo[d] = lo[d];
       it.hi[d] = hi[d];
-      it.xmin[d] = blocks_[b].bxmin[d];
-      it.dx[d] = blocks_[b].dx[d];
+      it.xmin[d] = L.bxmin[d];
+      it.dx[d] = L.dx[d];
     }
     return it;
   };
   std::vector<apk_amr_item_t> restrict_child, restrict_own, prolong, fc_restrict[3];
-  std::vector<apk_box_item_t> child_to_ghost, coarse_from_nbr, fc_copy[3];
-  for (size_t b = 0; b < blocks_.size(); ++b) {
-    const BlockInfo &B = blocks_[b];
-    const NbrInfo &N = nbrinfo_[b];
+  std::vector<apk_box_item_t> child_to_ghost, coarse_from_nbr, fc_copy[3], same_remote;
+  for (int b = 0; b < nblocks_global_; ++b) {  // GLOBAL ids: an item exists where its executor is local
+    const Leaf &B = leaves_[b];
+    const NbrInfo &N = gnbr_[b];
+    const bool b_local = IsLocal(b);
     for (int idx = 0; idx < 27; ++idx) {
       const int off[3] = {idx % 3 - 1, (idx / 3) % 3 - 1, idx / 9 - 1};
       if (N.type[idx] == 3) {
@@ -1276,19 +1350,43 @@ void HydroSim::BuildMultilevelPlan() {
             if (d >= ndim_) bx.d0[d] = 0;
             else if (off[d] > 0) bx.d0[d] = ie(d) + 1;
             else if (off[d] < 0) bx.d0[d] = is[d] - ng;
-            else bx.d0[d] = is[d] + (blocks_[f].loc[d] & 1) * (cfg_.mb[d] / 2);
+            else bx.d0[d] = is[d] + (leaves_[f].lx[d] & 1) * (cfg_.mb[d] / 2);
           }
-          restrict_child.push_back(amr_item(fine_ptr(d_cons_, f), f, clo, chi));
-          bx.src = coarse_ptr(f);
-          bx.dst = fine_ptr(d_cons_, (int)b);
-          child_to_ghost.push_back(bx);
+          // the fine block's owner restricts into the fine block's coarse buffer ...
+          if (IsLocal(f)) restrict_child.push_back(amr_item(cons_ptr(f), f, clo, chi));
+          // ... and the coarse block's owner pulls the result into its ghost cells
+          if (b_local) {
+            bx.src = coarse_ptr(f);
+            bx.dst = cons_ptr(b);
+            child_to_ghost.push_back(bx);
+          }
         }
+      }
+      if (!b_local) continue;
+      if (N.type[idx] == 1 && !IsLocal(N.idx[idx][0])) {
+        // same-level neighbour on another rank: pull its interior slab into my ghost slab
+        // (bnd_info.cpp:136-230; local same-level neighbours go through the nbr[] table)
+        apk_box_item_t bx{};
+        for (int d = 0; d < 3; ++d) {
+          int lo, hi;
+          range(d, off[d], false, ng, &lo, &hi);
+          bx.ns[d] = bx.nd[d] = n_[d];
+          bx.d0[d] = lo;
+          bx.ext[d] = hi - lo + 1;
+          if (d >= ndim_) bx.s0[d] = 0;
+          else if (off[d] > 0) bx.s0[d] = is[d];
+          else if (off[d] < 0) bx.s0[d] = ie(d) - ng + 1;
+          else bx.s0[d] = is[d];
+        }
+        bx.src = cons_ptr(N.idx[idx][0]);
+        bx.dst = cons_ptr(b);
+        same_remote.push_back(bx);
       }
       if (!N.has_coarser) continue;
       int lo[3], hi[3];
       if (idx == 13 || N.type[idx] == 1 || N.type[idx] == 3) {
         for (int d = 0; d < 3; ++d) range(d, off[d], true, ng / 2, &lo[d], &hi[d]);
-        restrict_own.push_back(amr_item(fine_ptr(d_cons_, (int)b), (int)b, lo, hi));
+        restrict_own.push_back(amr_item(cons_ptr(b), b, lo, hi));
       } else if (N.type[idx] == 2) {
         const int cn = N.idx[idx][0];
         apk_box_item_t bx{};
@@ -1301,17 +1399,17 @@ void HydroSim::BuildMultilevelPlan() {
           if (d >= ndim_) { bx.s0[d] = 0; continue; }
           // global cell index of the first buffer cell on the coarser level (periodic wrap)
           const long tot = (long)(nb_[d] << (B.level - 1)) * cfg_.mb[d];
-          long G = (long)B.loc[d] * (cfg_.mb[d] / 2) + (lo[d] - ng);
+          long G = (long)B.lx[d] * (cfg_.mb[d] / 2) + (lo[d] - ng);
           G = ((G % tot) + tot) % tot;
-          bx.s0[d] = is[d] + (int)(G - (long)blocks_[cn].loc[d] * cfg_.mb[d]);
+          bx.s0[d] = is[d] + (int)(G - (long)leaves_[cn].lx[d] * cfg_.mb[d]);
           if (bx.s0[d] < is[d] || bx.s0[d] + bx.ext[d] - 1 > ie(d))
             throw std::runtime_error("apk_host: coarse neighbour does not cover a buffer region");
         }
-        bx.src = fine_ptr(d_cons_, cn);
-        bx.dst = coarse_ptr((int)b);
+        bx.src = cons_ptr(cn);
+        bx.dst = coarse_ptr(b);
         coarse_from_nbr.push_back(bx);
         for (int d = 0; d < 3; ++d) range(d, off[d], true, ng / 2, &lo[d], &hi[d]);
-        prolong.push_back(amr_item(fine_ptr(d_cons_, (int)b), (int)b, lo, hi));
+        prolong.push_back(amr_item(cons_ptr(b), b, lo, hi));
       }
     }
     // flux correction: faces shared with finer blocks (bvals_in_one.hpp:69-80, bnd_info.cpp:71-103)
@@ -1335,13 +1433,15 @@ void HydroSim::BuildMultilevelPlan() {
             bx.ext[dd] = chi[dd] - clo[dd] + 1;
             if (dd >= ndim_) bx.d0[dd] = 0;
             else if (dd == d) bx.d0[dd] = (side > 0) ? ie(dd) + 1 : is[dd];
-            else bx.d0[dd] = is[dd] + (blocks_[f].loc[dd] & 1) * (cfg_.mb[dd] / 2);
+            else bx.d0[dd] = is[dd] + (leaves_[f].lx[dd] & 1) * (cfg_.mb[dd] / 2);
           }
           // the child's coarse buffer is free between exchanges: scratch for the restricted faces
-          fc_restrict[d].push_back(amr_item(fine_ptr(d_flux_[d], f), f, clo, chi));
-          bx.src = coarse_ptr(f);
-          bx.dst = fine_ptr(d_flux_[d], (int)b);
-          fc_copy[d].push_back(bx);
+          if (IsLocal(f)) fc_restrict[d].push_back(amr_item(flux_ptr(d, f), f, clo, chi));
+          if (b_local) {
+            bx.src = coarse_ptr(f);
+            bx.dst = flux_ptr(d, b);
+            fc_copy[d].push_back(bx);
+          }
         }
       }
   }
@@ -1356,6 +1456,7 @@ void HydroSim::BuildMultilevelPlan() {
   upload(ml_restrict_own_, restrict_own.data(), restrict_own.size(), sizeof(apk_amr_item_t));
   upload(ml_coarse_from_nbr_, coarse_from_nbr.data(), coarse_from_nbr.size(), sizeof(apk_box_item_t));
   upload(ml_prolong_, prolong.data(), prolong.size(), sizeof(apk_amr_item_t));
+  upload(ml_same_remote_, same_remote.data(), same_remote.size(), sizeof(apk_box_item_t));
   for (int d = 0; d < 3; ++d) {
     upload(ml_fc_restrict_[d], fc_restrict[d].data(), fc_restrict[d].size(), sizeof(apk_amr_item_t));
     upload(ml_fc_copy_[d], fc_copy[d].data(), fc_copy[d].size(), sizeof(apk_box_item_t));
@@ -1368,6 +1469,8 @@ TaskStatus HydroSim::ProlongateBounds() {
   abi_check(apk_restrict_average(ndim_, cfg_.ng, nvar_, 0,
                                  static_cast<const apk_amr_item_t *>(ml_restrict_child_.d),
                                  ml_restrict_child_.n, fp, stream_), "apk_restrict_average");
+  // (several ranks: the fine blocks' coarse buffers are complete everywhere before they are pulled)
+  if (cfg_.nranks > 1) StageBarrier();
   abi_check(apk_box_copy(static_cast<const apk_box_item_t *>(ml_child_to_ghost_.d),
                          ml_child_to_ghost_.n, nvar_, stream_), "apk_box_copy");
   abi_check(apk_restrict_average(ndim_, cfg_.ng, nvar_, 0,
@@ -1378,6 +1481,8 @@ TaskStatus HydroSim::ProlongateBounds() {
   abi_check(apk_prolongate_minmod_multid(ndim_, cfg_.ng, nvar_,
                                          static_cast<const apk_amr_item_t *>(ml_prolong_.d),
                                          ml_prolong_.n, fp, stream_), "apk_prolongate_minmod_multid");
+  // (several ranks: nobody modifies interior cells or coarse buffers while a peer still pulls them)
+  if (cfg_.nranks > 1) StageBarrier();
   return TaskStatus::complete;
 }
 
@@ -1390,8 +1495,11 @@ TaskStatus HydroSim::FluxCorrection() {
                                    static_cast<const apk_amr_item_t *>(ml_fc_restrict_[d].d),
                                    ml_fc_restrict_[d].n, cfg_.fp_mode, stream_),
               "apk_restrict_average (flux)");
+    if (cfg_.nranks > 1) StageBarrier();
     abi_check(apk_box_copy(static_cast<const apk_box_item_t *>(ml_fc_copy_[d].d), ml_fc_copy_[d].n,
                            nvar_, stream_), "apk_box_copy (flux)");
+    // the next direction reuses the same scratch cells of the coarse buffers
+    if (cfg_.nranks > 1 && d + 1 < ndim_) StageBarrier();
   }
   return TaskStatus::complete;
 }
@@ -1459,6 +1567,11 @@ TaskStatus HydroSim::EstimateTimestep(bool have_device_min) {
 void HydroSim::PreStepMeshUserWorkInLoop() {  // hydro.cpp:102-143 (+ CalculateGlobalMinDx :65-95)
   if (cfg_.fluid != APK_FLUID_GLMMHD) return;
   Real m = std::numeric_limits<Real>::max();
+  if (multilevel_) {
+    mindx = global_mindx_;
+    c_h = cfg_.cfl * mindx / dt_hyp;
+    return;
+  }
   // dx is identical on all ranks of a uniform mesh; no reduction needed
   for (const auto &B : blocks_) {
     m = std::fmin(m, B.dx[0]);

@@ -238,7 +238,14 @@ class HydroSim {
   std::vector<Leaf> BuildLeaves() const;
   // neighbour kind per (block, offset): 0 none, 1 same level, 2 coarser, 3 finer
   struct NbrInfo { int type[27]; int idx[27][4]; int nchild[27]; bool has_coarser; };
-  std::vector<NbrInfo> nbrinfo_;
+  std::vector<NbrInfo> nbrinfo_;  // per LOCAL block; idx[][] are GLOBAL block ids
+  std::vector<NbrInfo> gnbr_;     // per global block (every rank builds the whole topology)
+  std::vector<Leaf> leaves_;      // global leaf list (the partition cuts it into contiguous ranges)
+  Real global_mindx_ = 0.0;       // min dx over ALL leaves (CalculateGlobalMinDx + all-reduce)
+  int RankOfGid(int gid) const;
+  int GidLo(int rank) const;
+  bool IsLocal(int gid) const { return gid >= gid_lo_ && gid < gid_hi_; }
+  BlockInfo MakeBlockInfo(int gid, int level, const int *loc) const;
   void BuildMultilevelNeighbors();
   void BuildMultilevelPlan();
   double *d_coarse_ = nullptr;  // coarse buffers [nblocks][nvar][nc3][nc2][nc1] (Variable::coarse_s)
@@ -248,6 +255,8 @@ class HydroSim {
   struct MlList { void *d = nullptr; int n = 0; };
   MlList ml_restrict_child_, ml_child_to_ghost_, ml_restrict_own_, ml_coarse_from_nbr_, ml_prolong_;
   MlList ml_fc_restrict_[3], ml_fc_copy_[3];
+  MlList ml_same_remote_;  // same-level neighbours on other ranks: ghost slabs pulled from peer memory
+  std::vector<void *> ml_peer_;  // [rank][2]: IPC-mapped cons / coarse slabs of the other ranks
   void *d_tma_[2] = {nullptr, nullptr};  // per prim parity: CUtensorMap per block (A/B variant)
   double *d_undo_ = nullptr;         // copy of a stage's input cons (fused FOFC, rk2 / rk3)
   bool last_stage_unfused_ = false;  // the cycle's last stage was redone un-fused: no device dt min

@@ -14,6 +14,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import athenapk_b200 as apk  # noqa: E402
 from oracle_lib import Oracle  # noqa: E402
+from parity_util import oracle_block  # noqa: E402
 
 
 def main():
@@ -21,6 +22,8 @@ def main():
     torch.cuda.set_device(rank % torch.cuda.device_count())
     dist.init_process_group("gloo", rank=rank, world_size=world)
     kw = json.loads(os.environ["APK_CASE"])
+    if "refine" in kw:
+        kw["refine"] = [(lev, tuple(lo), tuple(hi)) for lev, lo, hi in kw["refine"]]
     ncyc = int(os.environ.get("APK_CYCLES", "3"))
     pgen, pars = kw.pop("pgen"), kw.pop("pgen_pars", [])
     fused = kw.pop("fused", True)
@@ -40,10 +43,8 @@ def main():
     o.initialize()
     o.run(None, ncyc)
     assert (sim.ncycle, sim.time, sim.dt) == (o.ncycle, o.time, o.dt), (sim.time, o.time, sim.dt, o.dt)
-    nb = [o.p.nx[d] // o.p.mb[d] for d in range(3)]
     for b in range(sim.nblocks):
-        loc = sim.block_info(b)[1]
-        ob = loc[0] + nb[0] * (loc[1] + nb[1] * loc[2])
+        ob = oracle_block(sim, o, b)  # (refined meshes: matched by level and logical location)
         for f, ref in (("cons", o.cons(ob)), ("prim", o.prim(ob))):
             got = sim.get(f, b)
             assert np.array_equal(got, ref), (rank, b, f, float(np.max(np.abs(got - ref))))
