@@ -393,9 +393,21 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
         const unsigned lane8 = sbase + (unsigned)lane * 8u;
         const double *pb = pbase;
         asm volatile("" : "+l"(pb));  // keep the plane base as one 64-bit register pair
+#ifdef APK_FUSED_NO_TRASH_STORES
+        // sanitizer build: stores into the trash rows (unsynchronised write-after-write BY DESIGN:
+        // nobody reads them) are skipped so that racecheck only sees real hazards
+        const unsigned trash_lo = sbase + (unsigned)(reinterpret_cast<unsigned char *>(&sm.wlz[0].trash[0]) - smem_raw);
+        const unsigned trash_sz = (unsigned)sizeof(sm.wlz[0]);
+        auto sts = [&](unsigned addr, double x) {
+          const unsigned o = (addr - trash_lo) % trash_sz;
+          if (addr >= trash_lo && o < TX * sizeof(double)) return;
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(x) : "memory");
+        };
+#else
         auto sts = [](unsigned addr, double x) {
           asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(x) : "memory");
         };
+#endif
         constexpr int NEC = NH * TY * 2;  // x1 end cells: (slot, row, side)
         // full PPM for one listed cell per lane (entries [base, base + n) of the list)
         auto drain = [&](int base, int n) {
