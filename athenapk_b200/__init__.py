@@ -102,7 +102,7 @@ SIM_SYMBOLS = [
     "apk_sim_execute", "apk_sim_step", "apk_sim_num_local_blocks", "apk_sim_num_global_blocks",
     "apk_sim_nvar", "apk_sim_block_dims", "apk_sim_block_level", "apk_sim_block_info", "apk_sim_copy_to_host",
     "apk_sim_copy_from_host", "apk_sim_device_ptr", "apk_sim_time", "apk_sim_dt",
-    "apk_sim_ncycle", "apk_sim_c_h", "apk_sim_fofc_corrections", "apk_sim_last_s_rkl", "apk_sim_fofc_redone_stages", "apk_sim_fused_active", "apk_sim_p2p_active",
+    "apk_sim_ncycle", "apk_sim_c_h", "apk_sim_fofc_corrections", "apk_sim_last_s_rkl", "apk_sim_ml_num_items", "apk_sim_ml_item", "apk_sim_fofc_redone_stages", "apk_sim_fused_active", "apk_sim_p2p_active",
     "apk_sim_linear_wave_period", "apk_sim_linear_wave_errors", "apk_sim_stream",
     "apk_sim_pack_desc", "apk_sim_device_blocks", "apk_sim_synchronize", "apk_sim_task",
     "apk_sim_set_c_h", "apk_sim_upload_all", "apk_sim_download_all",
@@ -187,6 +187,8 @@ def lib():
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = C.c_double
     L.apk_sim_last_s_rkl.argtypes = [vp]
+    L.apk_sim_ml_num_items.argtypes = [vp]
+    L.apk_sim_ml_item.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
     L.apk_sim_fofc_corrections.argtypes = [vp]
     L.apk_sim_fofc_corrections.restype = C.c_longlong
     L.apk_sim_fofc_redone_stages.argtypes = [vp]
@@ -420,6 +422,16 @@ class HydroSim:
     c_h = property(lambda s: s.L.apk_sim_c_h(s.h))
     fofc_corrections = property(lambda s: s.L.apk_sim_fofc_corrections(s.h))
     last_s_rkl = property(lambda s: s.L.apk_sim_last_s_rkl(s.h))
+
+    def ml_items(self):
+        """items of the multilevel exchange / flux-correction plan executed by this rank (refined
+        meshes): tuples (list, exec, src, dst, lo3..., ext3...) with global block ids"""
+        out = []
+        buf = (C.c_int * 10)()
+        for i in range(self.L.apk_sim_ml_num_items(self.h)):
+            self.L.apk_sim_ml_item(self.h, i, buf)
+            out.append(tuple(buf))
+        return out
     fofc_redone_stages = property(lambda s: s.L.apk_sim_fofc_redone_stages(s.h))
     fused_active = property(lambda s: bool(s.L.apk_sim_fused_active(s.h)))
     p2p_active = property(lambda s: bool(s.L.apk_sim_p2p_active(s.h)))

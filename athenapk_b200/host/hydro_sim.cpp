@@ -163,6 +163,8 @@ HydroSim::HydroSim(const SimConfig &cfg)
     cuda_check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate");
     stream_ = st;
     UploadBlocks();
+  } else if (multilevel_) {
+    BuildMultilevelPlan();  // descriptors only (ml_desc_): CPU tests of the multi-rank partition
   }
   BuildHaloPlan();
 }
@@ -1286,13 +1288,24 @@ void HydroSim::BuildMultilevelPlan() {
   const int ng = cfg_.ng;
   const size_t per = BlockFieldElems(), cper = CoarseElems();
   // arrays of a block by GLOBAL id: local slabs, or the IPC-mapped slabs of the owning rank
+  ml_desc_.clear();
+  auto desc = [&](int list, int exec, int src, int dst, const int *lo, const int *ext) {
+    MlDesc m{list, exec, src, dst, {lo[0], lo[1], lo[2]}, {ext[0], ext[1], ext[2]}};
+    ml_desc_.push_back(m);
+  };
+  auto desc_amr = [&](int list, int g, const int *lo, const int *hi) {
+    const int ext[3] = {hi[0] - lo[0] + 1, hi[1] - lo[1] + 1, hi[2] - lo[2] + 1};
+    desc(list, g, g, g, lo, ext);
+  };
   auto cons_ptr = [&](int g) -> double * {
     if (IsLocal(g)) return d_cons_ + (size_t)(g - gid_lo_) * per;
+    if (cfg_.plan_only) return nullptr;
     const int r = RankOfGid(g);
     return static_cast<double *>(ml_peer_[(size_t)r * 2 + 0]) + (size_t)(g - GidLo(r)) * per;
   };
   auto coarse_ptr = [&](int g) -> double * {
     if (IsLocal(g)) return d_coarse_ + (size_t)(g - gid_lo_) * cper;
+    if (cfg_.plan_only) return nullptr;
     const int r = RankOfGid(g);
     return static_cast<double *>(ml_peer_[(size_t)r * 2 + 1]) + (size_t)(g - GidLo(r)) * cper;
   };
@@ -1353,12 +1366,16 @@ void HydroSim::BuildMultilevelPlan() {
             else bx.d0[d] = is[d] + (leaves_[f].lx[d] & 1) * (cfg_.mb[d] / 2);
           }
           // the fine block's owner restricts into the fine block's coarse buffer ...
-          if (IsLocal(f)) restrict_child.push_back(amr_item(cons_ptr(f), f, clo, chi));
+          if (IsLocal(f)) {
+            restrict_child.push_back(amr_item(cons_ptr(f), f, clo, chi));
+            desc_amr(0, f, clo, chi);
+          }
           // ... and the coarse block's owner pulls the result into its ghost cells
           if (b_local) {
             bx.src = coarse_ptr(f);
             bx.dst = cons_ptr(b);
             child_to_ghost.push_back(bx);
+            desc(1, b, f, b, bx.s0, bx.ext);
           }
         }
       }
@@ -1381,12 +1398,14 @@ void HydroSim::BuildMultilevelPlan() {
         bx.src = cons_ptr(N.idx[idx][0]);
         bx.dst = cons_ptr(b);
         same_remote.push_back(bx);
+        desc(5, b, N.idx[idx][0], b, bx.d0, bx.ext);
       }
       if (!N.has_coarser) continue;
       int lo[3], hi[3];
       if (idx == 13 || N.type[idx] == 1 || N.type[idx] == 3) {
         for (int d = 0; d < 3; ++d) range(d, off[d], true, ng / 2, &lo[d], &hi[d]);
         restrict_own.push_back(amr_item(cons_ptr(b), b, lo, hi));
+        desc_amr(2, b, lo, hi);
       } else if (N.type[idx] == 2) {
         const int cn = N.idx[idx][0];
         apk_box_item_t bx{};
@@ -1408,8 +1427,10 @@ void HydroSim::BuildMultilevelPlan() {
         bx.src = cons_ptr(cn);
         bx.dst = coarse_ptr(b);
         coarse_from_nbr.push_back(bx);
+        desc(3, b, cn, b, bx.d0, bx.ext);
         for (int d = 0; d < 3; ++d) range(d, off[d], true, ng / 2, &lo[d], &hi[d]);
         prolong.push_back(amr_item(cons_ptr(b), b, lo, hi));
+        desc_amr(4, b, lo, hi);
       }
     }
     // flux correction: faces shared with finer blocks (bvals_in_one.hpp:69-80, bnd_info.cpp:71-103)
@@ -1436,18 +1457,22 @@ void HydroSim::BuildMultilevelPlan() {
             else bx.d0[dd] = is[dd] + (leaves_[f].lx[dd] & 1) * (cfg_.mb[dd] / 2);
           }
           // the child's coarse buffer is free between exchanges: scratch for the restricted faces
-          if (IsLocal(f)) fc_restrict[d].push_back(amr_item(flux_ptr(d, f), f, clo, chi));
+          if (IsLocal(f)) {
+            fc_restrict[d].push_back(amr_item(flux_ptr(d, f), f, clo, chi));
+            desc_amr(6 + d, f, clo, chi);
+          }
           if (b_local) {
             bx.src = coarse_ptr(f);
             bx.dst = flux_ptr(d, b);
             fc_copy[d].push_back(bx);
+            desc(9 + d, b, f, b, bx.d0, bx.ext);
           }
         }
       }
   }
   auto upload = [&](MlList &dst, const void *src, size_t n, size_t elem) {
     dst.n = (int)n;
-    if (!n) return;
+    if (!n || cfg_.plan_only) return;
     cuda_check(cudaMalloc(&dst.d, n * elem), "cudaMalloc multilevel plan");
     cuda_check(cudaMemcpy(dst.d, src, n * elem, cudaMemcpyHostToDevice), "upload multilevel plan");
   };

@@ -256,6 +256,14 @@ class HydroSim {
   MlList ml_restrict_child_, ml_child_to_ghost_, ml_restrict_own_, ml_coarse_from_nbr_, ml_prolong_;
   MlList ml_fc_restrict_[3], ml_fc_copy_[3];
   MlList ml_same_remote_;  // same-level neighbours on other ranks: ghost slabs pulled from peer memory
+ public:
+  // host-side description of every item of the plan (CPU tests of the multi-rank partition):
+  // list id (0 restrict_child, 1 child_to_ghost, 2 restrict_own, 3 coarse_from_nbr, 4 prolong,
+  // 5 same_remote, 6 + d flux restrict, 9 + d flux copy), executing block, source block,
+  // destination block (global ids), region start and extent
+  struct MlDesc { int list, exec, src, dst, lo[3], ext[3]; };
+  std::vector<MlDesc> ml_desc_;
+ private:
   std::vector<void *> ml_peer_;  // [rank][2]: IPC-mapped cons / coarse slabs of the other ranks
   void *d_tma_[2] = {nullptr, nullptr};  // per prim parity: CUtensorMap per block (A/B variant)
   double *d_undo_ = nullptr;         // copy of a stage's input cons (fused FOFC, rk2 / rk3)

@@ -74,6 +74,17 @@ void apk_sim_destroy(apk_sim_t *s) { delete reinterpret_cast<HydroSim *>(s); }
 
 #define SIM(s) (reinterpret_cast<HydroSim *>(s))
 
+int apk_sim_ml_num_items(const apk_sim_t *s) {
+  return (int)reinterpret_cast<const HydroSim *>(s)->ml_desc_.size();
+}
+int apk_sim_ml_item(const apk_sim_t *s, int i, int *out10) {
+  const auto &v = reinterpret_cast<const HydroSim *>(s)->ml_desc_;
+  if (i < 0 || i >= (int)v.size()) return -1;
+  const auto &m = v[i];
+  const int o[10] = {m.list, m.exec, m.src, m.dst, m.lo[0], m.lo[1], m.lo[2], m.ext[0], m.ext[1], m.ext[2]};
+  for (int k = 0; k < 10; ++k) out10[k] = o[k];
+  return 0;
+}
 int apk_sim_last_s_rkl(const apk_sim_t *s) { return reinterpret_cast<const HydroSim *>(s)->last_s_rkl; }
 
 int apk_sim_nccl_unique_id(void *out, int nbytes) { return HydroSim::CommUniqueId(out, nbytes); }

@@ -113,6 +113,14 @@ int apk_sim_halo_item(const apk_sim_t *s, int recv, int idx, apk_halo_item_t *ou
 int apk_sim_push_target(const apk_sim_t *s, int block, int o1, int o2, int o3, int *rank,
                         int *local_index);
 int apk_sim_neighbor(const apk_sim_t *s, int block, int o1, int o2, int o3);
+/* refined meshes: items of the multilevel exchange / flux-correction plan this rank executes
+ * (valid in plan_only mode too).  out10 = list id (0 restrict into the fine block's coarse buffer,
+ * 1 fine -> coarse ghost cells, 2 restrict own cells, 3 coarser neighbour -> coarse buffer,
+ * 4 prolongate, 5 same-level ghost slab pulled from another rank, 6+d / 9+d flux correction
+ * restrict / replace), executing block, source block, destination block (global ids), region
+ * start[3], extent[3] */
+int apk_sim_ml_num_items(const apk_sim_t *s);
+int apk_sim_ml_item(const apk_sim_t *s, int i, int *out10);
 
 #ifdef __cplusplus
 }
