@@ -95,6 +95,32 @@ CASES = {
 }
 
 
+def amr(regions, fluid, recon, rs, ng, extra):
+    """blast_3d_amr.in on a frozen refined mesh (refinement = static), as in make_reference_goldens.py"""
+    ov = ["parthenon/mesh/refinement=static", "hydro/fluid=" + fluid, "hydro/reconstruction=" + recon,
+          "hydro/riemann=" + rs, "parthenon/mesh/nghost=%d" % ng, "parthenon/time/nlim=10",
+          "parthenon/output0/file_type=hst", "problem/blast/radius_outer=0.12",
+          "problem/blast/radius_inner=0.12", "problem/blast/pressure_ratio=100",
+          "problem/blast/pressure_ambient=0.1", "problem/blast/x1_0=0.22", "problem/blast/x2_0=0.1",
+          "problem/blast/x3_0=-0.05"]
+    for r, (lev, lo, hi) in enumerate(regions):
+        for d in range(3):
+            ov += ["parthenon/static_refinement%d/x%dmin=%r" % (r, d + 1, lo),
+                   "parthenon/static_refinement%d/x%dmax=%r" % (r, d + 1, hi)]
+        ov += ["parthenon/static_refinement%d/level=%d" % (r, lev)]
+    return (BLAST, ov + extra)
+
+
+# diffusion on refined meshes: the diffusive fluxes go through the flux correction and every RKL2
+# sub-step through the multilevel ghost exchange (hydro_driver.cpp:248-273, :314-338)
+CASES["amr_2level_rkl2_hydro"] = amr([(1, -0.2, 0.2)], "euler", "plm", "hlle", 2,
+                                     diff("rkl2", ("isotropic", 0.02), 0.03))
+CASES["amr_3level_unsplit_mhd"] = amr([(1, -0.2, 0.2), (2, -0.1, 0.1)], "glmmhd", "plm", "hlld", 2,
+                                      diff("unsplit", ("isotropic", 0.0002), 0.0003, 0.0002))
+CASES["amr_3level_rkl2_mhd_aniso"] = amr([(1, -0.2, 0.2), (2, -0.1, 0.1)], "glmmhd", "wenoz", "hlld", 4,
+                                         diff("rkl2", ("anisotropic", 0.01), 0.004, 0.005))
+
+
 def main():
     out = {"_provenance": "printed by the UNMODIFIED reference (Kokkos Serial, g++ -O3, no FMA) run by "
                           "tests/golden/make_diffusion_goldens.py; trace = [time, dt] per cycle at 17 "

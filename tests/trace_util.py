@@ -84,12 +84,24 @@ DIFF_DECKS = {
 }
 
 
-def _amr(regions, fluid, recon, rs, ng):
+def _amr(regions, fluid, recon, rs, ng, **extra):
     return (dict(fluid=fluid, nx=(32, 32, 32), mb=(8, 8, 8), ng=ng, xmin=(-0.5,) * 3,
                  xmax=(0.5,) * 3, gamma=GAMMA_DECK, cfl=0.3, recon=recon, riemann=rs,
                  integrator="vl2",
-                 refine=[(lev, (lo,) * 3, (hi,) * 3) for lev, lo, hi in regions]),
+                 refine=[(lev, (lo,) * 3, (hi,) * 3) for lev, lo, hi in regions], **extra),
             "blast", [0.12, 0.1, 100.0, 1.0, 0.22, 0.1, -0.05], 0.1)
+
+
+# diffusion on refined meshes (make_diffusion_goldens.py): diffusive fluxes through the flux
+# correction, RKL2 sub-steps through the multilevel ghost exchange
+DIFF_DECKS.update({
+    "amr_2level_rkl2_hydro": _amr([(1, -0.2, 0.2)], "euler", "plm", "hlle", 2,
+                                  **_diff("rkl2", ("isotropic", 0.02), 0.03)),
+    "amr_3level_unsplit_mhd": _amr([(1, -0.2, 0.2), (2, -0.1, 0.1)], "glmmhd", "plm", "hlld", 2,
+                                   **_diff("unsplit", ("isotropic", 0.0002), 0.0003, 0.0002)),
+    "amr_3level_rkl2_mhd_aniso": _amr([(1, -0.2, 0.2), (2, -0.1, 0.1)], "glmmhd", "wenoz", "hlld", 4,
+                                      **_diff("rkl2", ("anisotropic", 0.01), 0.004, 0.005)),
+})
 
 
 # static mesh refinement (see make_reference_goldens.py): 2 and 3 levels
