@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define APK_ABI_VERSION 3
+#define APK_ABI_VERSION 4  /* 4: diffusion block (apk_calc_diff_fluxes, apk_reset_fluxes, apk_rkl2_step_*, apk_min_dt_conduction) */
 
 /* src/main.hpp:19-50 (enum values are ours; the shim translates) */
 enum { APK_FLUID_EULER = 0, APK_FLUID_GLMMHD = 1 };
