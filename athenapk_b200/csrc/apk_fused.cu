@@ -1013,6 +1013,8 @@ int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
     case APK_RIEMANN_NONE: return run_fused<APK_FLUID_EULER, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, a, dedner_coeff, s);
     case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, a, dedner_coeff, s);
     case APK_RIEMANN_HLLC: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLC>(recon, d, g, blocks, prim_out, a, dedner_coeff, s);
+    // CalculateFluxesTight (hydro.cpp:980-1022): LLF fluxes of the neighbouring cell values = donor cell + LLF
+    case APK_RIEMANN_LLF: return run_fused<APK_FLUID_EULER, APK_RECON_DC, APK_RIEMANN_LLF>(d, g, blocks, prim_out, a, dedner_coeff, s);
     }
   } else {
     return launch_stage_fused_mhd(d, g, blocks, prim_out, a, dedner_coeff, recon, s);
@@ -1028,6 +1030,7 @@ int launch_stage_fused_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk
   case APK_RIEMANN_NONE: return run_fused<APK_FLUID_GLMMHD, APK_RECON_DC, APK_RIEMANN_NONE>(d, g, blocks, prim_out, a, dedner_coeff, s);
   case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLE>(recon, d, g, blocks, prim_out, a, dedner_coeff, s);
   case APK_RIEMANN_HLLD: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLD>(recon, d, g, blocks, prim_out, a, dedner_coeff, s);
+  case APK_RIEMANN_LLF: return run_fused<APK_FLUID_GLMMHD, APK_RECON_DC, APK_RIEMANN_LLF>(d, g, blocks, prim_out, a, dedner_coeff, s);
   }
   apk_common::set_error("apk_stage_fused: unsupported fluid/riemann combination");
   return 1;

@@ -138,8 +138,8 @@ HydroSim::HydroSim(const SimConfig &cfg)
   // multilevel meshes need materialised fluxes (flux correction, hydro_driver.cpp:527-531)
   // diffusion (either integrator) runs on the flux-materialising tasks: unsplit adds to the
   // hyperbolic fluxes (hydro.cpp:1202-1205), RKL2 needs the flux arrays for its sub-steps
-  fused_ = cfg_.fused && !cfg_.dedner_extended && cfg_.riemann != APK_RIEMANN_LLF &&
-           cfg_.nscalars == 0 && !multilevel_ && cfg_.diffint == 0;
+  fused_ = cfg_.fused && !cfg_.dedner_extended && cfg_.nscalars == 0 && !multilevel_ &&
+           cfg_.diffint == 0;
   if (cfg_.diffint != 0) {
     if (cfg_.fofc)
       throw std::runtime_error("apk_host: first_order_flux_correct with diffusion is not supported");

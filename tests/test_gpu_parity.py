@@ -62,6 +62,8 @@ def test_flux_arrays_bitexact(apk, fluid, recon, riemann, ng):
     ("euler", "weno3", "hlle", "rk1", 2), ("euler", "limo3", "hllc", "vl2", 2),
     ("glmmhd", "plm", "hlle", "vl2", 2), ("glmmhd", "ppm", "hlld", "vl2", 3),
     ("glmmhd", "wenoz", "hlld", "rk3", 3), ("glmmhd", "limo3", "hlld", "rk2", 2),
+    # DC + LLF = CalculateFluxesTight (hydro.cpp:980-1022); "none" = no hyperbolic fluxes
+    ("euler", "dc", "llf", "rk2", 2), ("glmmhd", "dc", "llf", "vl2", 2),
 ])
 def test_cycles_bitexact_3d(apk, fused, fluid, recon, riemann, integrator, ng):
     """3 full cycles (all stages, ghost exchange over 2x2x2 periodic meshblocks, Dedner source,
