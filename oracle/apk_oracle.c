@@ -922,6 +922,8 @@ typedef struct {
   int ntype[27];
   int nidx[27][4]; /* block index: the neighbour (types 1, 2) or its up to 4 abutting children */
   int nchild[27];
+  /* adaptive refinement: MeshRefinement::refine_flag_, deref_count_ (mesh_refinement.hpp) */
+  int refine_flag, deref_count;
 } block_t;
 
 struct apko_engine {
@@ -943,6 +945,11 @@ struct apko_engine {
   long long fofc_total;
   double dt_diff; /* "dt_diff" Param (hydro.cpp:700, 961-962) */
   int last_s_rkl;
+  /* adaptive refinement: the problem generator is re-run while Mesh::Initialize refines
+   * (mesh.cpp:746-840); Mesh::nbnew / nbdel */
+  int pgen_id, pgen_npars;
+  double pgen_pars[16];
+  int nbnew, nbdel;
   /* linear wave pgen state (linear_wave.cpp:43-51) */
   struct {
     int set, wave_flag;
@@ -977,6 +984,8 @@ void apko_default_params(apko_params *p) {
   p->cfl_diff = -1.0;
   p->rkl2_max_dt_ratio = -1.0;              /* hydro.cpp:688 */
   p->conduction_sat_phi = 0.3;              /* hydro.cpp:563-564 */
+  p->numlevel = 1;
+  p->derefine_count = 10;                   /* mesh_refinement.cpp:56 */
 }
 
 /* mesh/forest/logical_location.cpp:61-74 */
@@ -1253,6 +1262,42 @@ static void build_neighbor_tables(apko_engine *e) {
   free(L);
 }
 
+static void block_alloc(const apko_engine *e, block_t *B) {
+  const size_t nfield = e->ncell * e->nvar;
+  B->cons = (double *)calloc(nfield, sizeof(double));
+  B->prim = (double *)calloc(nfield, sizeof(double));
+  B->u1 = (double *)calloc(nfield, sizeof(double));
+  if (e->p.diffint == 2) { /* RKL2 registers "MY0", "Yjm2" (hydro_driver.cpp:211-212) */
+    B->my0 = (double *)calloc(nfield, sizeof(double));
+    B->yjm2 = (double *)calloc(nfield, sizeof(double));
+  }
+  for (int d = 0; d < 3; ++d) B->flux[d] = (double *)calloc(nfield, sizeof(double));
+  if (e->multilevel)
+    B->coarse = (double *)calloc((size_t)e->nc[0] * e->nc[1] * e->nc[2] * e->nvar, sizeof(double));
+}
+
+static void block_free(block_t *B) {
+  free(B->cons);
+  free(B->prim);
+  free(B->u1);
+  free(B->my0);
+  free(B->yjm2);
+  free(B->coarse);
+  for (int d = 0; d < 3; ++d) free(B->flux[d]);
+}
+
+/* bounds and coordinates from (level, loc) */
+static void block_geometry(const apko_engine *e, block_t *B) {
+  const apko_params *p = &e->p;
+  for (int d = 0; d < 3; ++d) {
+    block_bounds_level(e, d, B->level, B->loc[d], &B->bxmin[d], &B->bxmax[d]);
+    /* uniform_coordinates.hpp:32-36 */
+    B->dx[d] = (B->bxmax[d] - B->bxmin[d]) / p->mb[d];
+    int istart = (p->nx[d] == 1) ? 0 : p->ng;
+    B->xmin[d] = B->bxmin[d] - istart * B->dx[d];
+  }
+}
+
 apko_engine *apko_create(const apko_params *p) {
   apko_engine *e = (apko_engine *)calloc(1, sizeof(*e));
   e->p = *p;
@@ -1275,9 +1320,9 @@ apko_engine *apko_create(const apko_params *p) {
   e->ncell = (size_t)e->n[0] * e->n[1] * e->n[2];
   leaf_t *leaves = NULL;
   e->multilevel = 0;
-  if (p->nref > 0) {
+  if (p->nref > 0 || p->adaptive) {
     /* mesh_refinement.cpp:60-70: refinement needs an even number of ghost cells */
-    if (p->ng % 2 != 0 || p->nref > 4) {
+    if (p->ng % 2 != 0 || p->nref > 4 || (p->adaptive && e->ndim < 2)) {
       free(e);
       return NULL;
     }
@@ -1286,34 +1331,19 @@ apko_engine *apko_create(const apko_params *p) {
     for (int d = 0; d < 3; ++d) e->nc[d] = (d < e->ndim) ? p->mb[d] / 2 + 2 * p->ng : 1;
   }
   e->blk = (block_t *)calloc(e->nblocks, sizeof(block_t));
-  size_t nfield = e->ncell * e->nvar;
   for (int b = 0; b < e->nblocks; ++b) {
     block_t *B = &e->blk[b];
-    B->cons = (double *)calloc(nfield, sizeof(double));
-    B->prim = (double *)calloc(nfield, sizeof(double));
-    B->u1 = (double *)calloc(nfield, sizeof(double));
-    if (p->diffint == 2) { /* RKL2 registers "MY0", "Yjm2" (hydro_driver.cpp:211-212) */
-      B->my0 = (double *)calloc(nfield, sizeof(double));
-      B->yjm2 = (double *)calloc(nfield, sizeof(double));
-    }
-    for (int d = 0; d < 3; ++d) B->flux[d] = (double *)calloc(nfield, sizeof(double));
+    block_alloc(e, B);
     if (leaves) {
       B->level = leaves[b].level;
       for (int d = 0; d < 3; ++d) B->loc[d] = leaves[b].lx[d];
       if (B->level > e->maxlevel) e->maxlevel = B->level;
-      B->coarse = (double *)calloc((size_t)e->nc[0] * e->nc[1] * e->nc[2] * e->nvar, sizeof(double));
     } else {
       B->loc[0] = b % e->nb[0];
       B->loc[1] = (b / e->nb[0]) % e->nb[1];
       B->loc[2] = b / (e->nb[0] * e->nb[1]);
     }
-    for (int d = 0; d < 3; ++d) {
-      block_bounds_level(e, d, B->level, B->loc[d], &B->bxmin[d], &B->bxmax[d]);
-      /* uniform_coordinates.hpp:32-36 */
-      B->dx[d] = (B->bxmax[d] - B->bxmin[d]) / p->mb[d];
-      int istart = (p->nx[d] == 1) ? 0 : p->ng;
-      B->xmin[d] = B->bxmin[d] - istart * B->dx[d];
-    }
+    block_geometry(e, B);
   }
   free(leaves);
   if (e->multilevel) build_neighbor_tables(e);
@@ -1322,6 +1352,7 @@ apko_engine *apko_create(const apko_params *p) {
   e->dt_hyp = DBL_MAX;
   e->new_dt = DBL_MAX;
   e->tlim = DBL_MAX;
+  e->pgen_id = -1;
   return e;
 }
 
@@ -1332,15 +1363,7 @@ void apko_block_loc(const apko_engine *e, int b, int *level, int *lx3) {
 
 void apko_destroy(apko_engine *e) {
   if (!e) return;
-  for (int b = 0; b < e->nblocks; ++b) {
-    free(e->blk[b].cons);
-    free(e->blk[b].prim);
-    free(e->blk[b].u1);
-    free(e->blk[b].my0);
-    free(e->blk[b].yjm2);
-    free(e->blk[b].coarse);
-    for (int d = 0; d < 3; ++d) free(e->blk[b].flux[d]);
-  }
+  for (int b = 0; b < e->nblocks; ++b) block_free(&e->blk[b]);
   free(e->blk);
   free(e);
 }
@@ -2365,12 +2388,405 @@ void apko_save_u1(apko_engine *e) { /* hydro_driver.cpp:474-495 */
     memcpy(e->blk[b].u1, e->blk[b].cons, e->ncell * e->nvar * sizeof(double));
 }
 
+/* ===================================================================================== */
+/* Adaptive mesh refinement: Refinement::Tag + MeshRefinement::SetRefinement               */
+/* (amr_criteria/refinement_package.cpp:205-233, mesh/mesh_refinement.cpp:72-110),         */
+/* Mesh::UpdateMeshBlockTree / RedistributeAndRefineMeshBlocks                             */
+/* (mesh/mesh-amr_loadbalance.cpp:485-995), Tree::Refine / Derefine (forest/tree.cpp)      */
+/* ===================================================================================== */
+int apko_amr_tag(apko_engine *e) {
+  const apko_params *p = &e->p;
+  const int max_level = p->numlevel - 1; /* root level is 0 here */
+  int nflag = 0;
+  for (int b = 0; b < e->nblocks; ++b) {
+    block_t *B = &e->blk[b];
+    /* CheckAllRefinement: max(derefine, package criteria) */
+    const int aret = apko_pressure_gradient_tag(e->ndim, p->ng, e->n, B->prim, IPR,
+                                                p->refine_threshold, NULL);
+    if (aret == 0) B->refine_flag = 0;
+    if (aret >= 0) B->deref_count = 0;
+    if (aret > 0) {
+      B->refine_flag = (B->level == max_level) ? 0 : 1;
+    } else if (aret < 0) {
+      if (B->level == 0) {
+        B->refine_flag = 0;
+        B->deref_count = 0;
+      } else {
+        B->deref_count++;
+        int ec = 0;
+        for (int idx = 0; idx < 27; ++idx) ec += (B->ntype[idx] == 3) ? B->nchild[idx] : 0;
+        if (ec > 0) B->refine_flag = 0;
+        else B->refine_flag = (B->deref_count >= p->derefine_count) ? -1 : 0;
+      }
+    }
+    nflag += (B->refine_flag != 0);
+  }
+  return nflag;
+}
+
+int apko_amr_flag(const apko_engine *e, int b) { return e->blk[b].refine_flag; }
+
+void apko_amr_counts(const apko_engine *e, int *nbnew, int *nbdel, int *per_level8) {
+  if (nbnew) *nbnew = e->nbnew;
+  if (nbdel) *nbdel = e->nbdel;
+  if (per_level8) {
+    for (int l = 0; l < 8; ++l) per_level8[l] = 0;
+    for (int b = 0; b < e->nblocks; ++b)
+      if (e->blk[b].level < 8) per_level8[e->blk[b].level]++;
+  }
+}
+
+typedef struct {
+  leaf_t *L;
+  int n, cap;
+} leafset_t;
+
+/* neighbour location at the same level (periodic wrap); 0 when it lies outside the domain */
+static int amr_neighbor_loc(const apko_engine *e, int level, const int *lx, const int *off,
+                            int *nl) {
+  for (int d = 0; d < 3; ++d) {
+    nl[d] = lx[d] + off[d];
+    if (d >= e->ndim) {
+      if (off[d]) return 0;
+      continue;
+    }
+    const int tot = e->nb[d] << level;
+    if (nl[d] < 0 || nl[d] >= tot) {
+      const int face = 2 * d + (nl[d] < 0 ? 0 : 1);
+      if (e->p.bc[face] != APKO_BC_PERIODIC) return 0;
+      nl[d] = (nl[d] + tot) % tot;
+    }
+  }
+  return 1;
+}
+
+/* Tree::Refine with enforce_proper_nesting (tree.cpp:95-136) */
+static int amr_refine(const apko_engine *e, leafset_t *S, int level, const int *lx) {
+  const int q = leaf_find(S->L, S->n, level, lx);
+  if (q < 0) return 0; /* can't refine a block that doesn't exist */
+  const int nchild = 1 << e->ndim;
+  for (int c = 0; c < nchild; ++c) {
+    leaf_t ch;
+    ch.level = level + 1;
+    for (int d = 0; d < 3; ++d) ch.lx[d] = (d < e->ndim) ? 2 * lx[d] + ((c >> d) & 1) : 0;
+    if (c == 0) {
+      S->L[q] = ch;
+    } else {
+      if (S->n == S->cap) S->L = (leaf_t *)realloc(S->L, (S->cap *= 2) * sizeof(leaf_t));
+      S->L[S->n++] = ch;
+    }
+  }
+  int nadded = nchild - 1;
+  if (level > 0) {
+    /* the 2^ndim blocks on level - 1 that could abut the new blocks on level + 1 */
+    int plx[3], ox[3];
+    for (int d = 0; d < 3; ++d) {
+      plx[d] = lx[d] >> 1;
+      ox[d] = lx[d] & 1;
+    }
+    for (int k = -(e->ndim > 2); k < 1; ++k)
+      for (int j = -(e->ndim > 1); j < 1; ++j)
+        for (int i = -1; i < 1; ++i) {
+          const int off[3] = {i + ox[0], (e->ndim > 1) ? j + ox[1] : 0,
+                              (e->ndim > 2) ? k + ox[2] : 0};
+          int nl[3];
+          if (!amr_neighbor_loc(e, level - 1, plx, off, nl)) continue;
+          nadded += amr_refine(e, S, level - 1, nl);
+        }
+  }
+  return nadded;
+}
+
+/* Tree::Derefine with enforce_proper_nesting (tree.cpp:217-272): lx at `level` becomes a leaf */
+static int amr_derefine(const apko_engine *e, leafset_t *S, int level, const int *lx) {
+  const int nchild = 1 << e->ndim;
+  int cq[8];
+  for (int c = 0; c < nchild; ++c) {
+    int cl[3];
+    for (int d = 0; d < 3; ++d) cl[d] = (d < e->ndim) ? 2 * lx[d] + ((c >> d) & 1) : 0;
+    cq[c] = leaf_find(S->L, S->n, level + 1, cl);
+    if (cq[c] < 0) return 0;
+    /* none of the daughter's same-level neighbours may be an internal node */
+    for (int k = -(e->ndim > 2); k <= (e->ndim > 2); ++k)
+      for (int j = -(e->ndim > 1); j <= (e->ndim > 1); ++j)
+        for (int i = -1; i <= 1; ++i) {
+          const int off[3] = {i, j, k};
+          int nl[3];
+          if (!amr_neighbor_loc(e, level + 1, cl, off, nl)) continue;
+          if (leaf_cover(S->L, S->n, level + 1, nl, NULL) < 0) return 0;
+        }
+  }
+  /* the parent takes the first daughter's slot, the others are removed (largest index first) */
+  S->L[cq[0]].level = level;
+  for (int d = 0; d < 3; ++d) S->L[cq[0]].lx[d] = lx[d];
+  for (int a = 1; a < nchild; ++a)
+    for (int b2 = a + 1; b2 < nchild; ++b2)
+      if (cq[b2] > cq[a]) {
+        int t = cq[a];
+        cq[a] = cq[b2];
+        cq[b2] = t;
+      }
+  for (int c = 1; c < nchild; ++c) {
+    /* cq[0] may be the last element: keep track of it when it is moved */
+    const int last = S->n - 1;
+    if (cq[c] != last) {
+      S->L[cq[c]] = S->L[last];
+      if (cq[0] == last) cq[0] = cq[c];
+    }
+    S->n--;
+  }
+  return nchild - 1;
+}
+
+/* position of a location in Parthenon's block list: trees in Morton order of the tree location
+ * (forest.cpp:108-144), leaves of a tree in Morton order (logical_location.hpp:150-154) */
+static uint64_t amr_interleave(const int *x, int bits) {
+  uint64_t m = 0;
+  for (int b = 0; b < bits; ++b)
+    for (int d = 0; d < 3; ++d) m |= (uint64_t)((x[d] >> b) & 1) << (3 * b + d);
+  return m;
+}
+static void amr_order_key(const apko_engine *e, int level, const int *lx, uint64_t key[2]) {
+  int mcp2 = 1 << 30, any_sym = 0;
+  for (int d = 0; d < 3; ++d) {
+    if (e->p.nx[d] == 1) {
+      any_sym = 1;
+      continue;
+    }
+    const int m = max_pow2_divisor(e->nb[d]);
+    if (m < mcp2) mcp2 = m;
+  }
+  if (any_sym) mcp2 = 1;
+  int t[3], in[3];
+  const int fin = e->p.numlevel - 1; /* finest possible level */
+  for (int d = 0; d < 3; ++d) {
+    const int per_tree = mcp2 << level;
+    t[d] = (d < e->ndim) ? lx[d] / per_tree : 0;
+    in[d] = (d < e->ndim) ? (lx[d] % per_tree) << (fin - level) : 0;
+  }
+  key[0] = amr_interleave(t, 20);
+  key[1] = amr_interleave(in, 20);
+}
+static int amr_key_less(const uint64_t a[2], int la, const uint64_t b[2], int lb) {
+  if (a[0] != b[0]) return a[0] < b[0];
+  if (a[1] != b[1]) return a[1] < b[1];
+  return la < lb;
+}
+
+/* Mesh::LoadBalancingAndAdaptiveMeshRefinement (one rank) followed by what the driver does when
+ * the mesh changed (EvolutionDriver::InitializeBlockTimeSteps, driver.cpp:128-131) */
+int apko_amr_remesh(apko_engine *e) {
+  const apko_params *p = &e->p;
+  const int ng = p->ng, nv = e->nvar;
+  const int nleaf = 1 << e->ndim;
+  /* ---- UpdateMeshBlockTree (mesh-amr_loadbalance.cpp:485-604) */
+  int tnref = 0, tnderef = 0;
+  for (int b = 0; b < e->nblocks; ++b) {
+    tnref += (e->blk[b].refine_flag == 1);
+    tnderef += (e->blk[b].refine_flag == -1);
+  }
+  if (tnref == 0 && tnderef < nleaf) return 0;
+  const int nold = e->nblocks;
+  leaf_t *old = (leaf_t *)malloc(nold * sizeof(leaf_t));
+  leafset_t S;
+  S.cap = 2 * nold + 64;
+  S.n = nold;
+  S.L = (leaf_t *)malloc(S.cap * sizeof(leaf_t));
+  for (int b = 0; b < nold; ++b) {
+    old[b].level = e->blk[b].level;
+    for (int d = 0; d < 3; ++d) old[b].lx[d] = e->blk[b].loc[d];
+    S.L[b] = old[b];
+  }
+  /* newly derefined blocks: parents whose 2^ndim daughters are all flagged, in block-list order
+   * of the first daughter */
+  leaf_t *cl = NULL;
+  uint64_t(*ckey)[2] = NULL;
+  int ctnd = 0;
+  if (tnderef >= nleaf) {
+    cl = (leaf_t *)malloc((tnderef / nleaf + 1) * sizeof(leaf_t));
+    ckey = (uint64_t(*)[2])malloc((tnderef / nleaf + 1) * sizeof(uint64_t[2]));
+    for (int b = 0; b < nold; ++b) {
+      const block_t *B = &e->blk[b];
+      if (B->refine_flag != -1) continue;
+      int lower_left = 1;
+      for (int d = 0; d < e->ndim; ++d) lower_left &= !(B->loc[d] & 1);
+      if (!lower_left) continue;
+      int all = 1;
+      for (int c = 1; c < nleaf && all; ++c) {
+        int sl[3];
+        for (int d = 0; d < 3; ++d) sl[d] = (d < e->ndim) ? B->loc[d] + ((c >> d) & 1) : 0;
+        const int q = leaf_find(old, nold, B->level, sl);
+        all = (q >= 0 && e->blk[q].refine_flag == -1);
+      }
+      if (!all) continue;
+      cl[ctnd].level = B->level - 1;
+      for (int d = 0; d < 3; ++d) cl[ctnd].lx[d] = B->loc[d] >> 1;
+      amr_order_key(e, B->level, B->loc, ckey[ctnd]);
+      ctnd++;
+    }
+    /* block-list order (insertion sort on the first daughter's key) */
+    for (int a = 1; a < ctnd; ++a)
+      for (int b2 = a; b2 > 0 && amr_key_less(ckey[b2], 0, ckey[b2 - 1], 0); --b2) {
+        leaf_t t = cl[b2];
+        cl[b2] = cl[b2 - 1];
+        cl[b2 - 1] = t;
+        uint64_t k0 = ckey[b2][0], k1 = ckey[b2][1];
+        ckey[b2][0] = ckey[b2 - 1][0];
+        ckey[b2][1] = ckey[b2 - 1][1];
+        ckey[b2 - 1][0] = k0;
+        ckey[b2 - 1][1] = k1;
+      }
+    /* "sort the lists by level": std::sort(&clderef[0], &clderef[ctnd - 1]) leaves the LAST
+     * element where it is (mesh-amr_loadbalance.cpp:587-592); finer parents first */
+    if (ctnd > 1)
+      for (int a = 1; a < ctnd - 1; ++a)
+        for (int b2 = a; b2 > 0 && cl[b2].level > cl[b2 - 1].level; --b2) {
+          leaf_t t = cl[b2];
+          cl[b2] = cl[b2 - 1];
+          cl[b2 - 1] = t;
+        }
+  }
+  int nnew = 0, ndel = 0;
+  /* Step 1: refinement, in block-list order (the closure does not depend on the order) */
+  for (int b = 0; b < nold; ++b)
+    if (e->blk[b].refine_flag == 1) nnew += amr_refine(e, &S, old[b].level, old[b].lx);
+  /* Step 2: derefinement */
+  for (int c = 0; c < ctnd; ++c) ndel += amr_derefine(e, &S, cl[c].level, cl[c].lx);
+  free(cl);
+  free(ckey);
+  e->nbnew += nnew;
+  e->nbdel += ndel;
+  if (nnew == 0 && ndel == 0) {
+    free(old);
+    free(S.L);
+    return 0;
+  }
+  /* ---- RedistributeAndRefineMeshBlocks (mesh-amr_loadbalance.cpp:626-995), one rank: the new
+   * block list in Parthenon's order */
+  {
+    uint64_t(*key)[2] = (uint64_t(*)[2])malloc(S.n * sizeof(uint64_t[2]));
+    int *ord = (int *)malloc(S.n * sizeof(int));
+    for (int q = 0; q < S.n; ++q) {
+      amr_order_key(e, S.L[q].level, S.L[q].lx, key[q]);
+      ord[q] = q;
+    }
+    /* shell sort of the permutation */
+    for (int gap = S.n / 2; gap > 0; gap /= 2)
+      for (int a = gap; a < S.n; ++a) {
+        const int t = ord[a];
+        int b2 = a;
+        for (; b2 >= gap && amr_key_less(key[t], S.L[t].level, key[ord[b2 - gap]],
+                                         S.L[ord[b2 - gap]].level);
+             b2 -= gap)
+          ord[b2] = ord[b2 - gap];
+        ord[b2] = t;
+      }
+    leaf_t *sorted = (leaf_t *)malloc(S.n * sizeof(leaf_t));
+    for (int q = 0; q < S.n; ++q) sorted[q] = S.L[ord[q]];
+    free(S.L);
+    S.L = sorted;
+    free(key);
+    free(ord);
+  }
+  block_t *oblk = e->blk;
+  block_t *nblk = (block_t *)calloc(S.n, sizeof(block_t));
+  char *moved = (char *)calloc(nold, 1);
+  int cis[3], cie[3];
+  for (int d = 0; d < 3; ++d) {
+    cis[d] = (d < e->ndim) ? ng : 0;
+    cie[d] = (d < e->ndim) ? ng + p->mb[d] / 2 - 1 : 0;
+  }
+  for (int n = 0; n < S.n; ++n) {
+    block_t *B = &nblk[n];
+    const leaf_t *lf = &S.L[n];
+    int q = leaf_find(old, nold, lf->level, lf->lx);
+    if (q >= 0) { /* same level: the block moves as it is (incl. its derefinement counter) */
+      *B = oblk[q];
+      moved[q] = 1;
+      continue;
+    }
+    B->level = lf->level;
+    for (int d = 0; d < 3; ++d) B->loc[d] = lf->lx[d];
+    block_alloc(e, B);
+    block_geometry(e, B);
+    int plx[3];
+    for (int d = 0; d < 3; ++d) plx[d] = lf->lx[d] >> 1;
+    q = (lf->level > 0) ? leaf_find(old, nold, lf->level - 1, plx) : -1;
+    if (q >= 0) {
+      /* coarse to fine (TryRecvCoarseToFine :82-146): the ENTIRE coarse buffer is the octant of
+       * the parent's array (ghost cells included), then the interior is prolongated */
+      const block_t *P = &oblk[q];
+      int s[3];
+      for (int d = 0; d < 3; ++d) s[d] = (d < e->ndim && (lf->lx[d] & 1)) ? p->mb[d] / 2 : 0;
+      for (int v = 0; v < nv; ++v)
+        for (int k = 0; k < e->nc[2]; ++k)
+          for (int j = 0; j < e->nc[1]; ++j)
+            for (int i = 0; i < e->nc[0]; ++i)
+              B->coarse[CIDX(e, v, k, j, i)] = P->cons[IDX(e, v, k + s[2], j + s[1], i + s[0])];
+      apko_prolongate_minmod_multid(e->ndim, ng, B->bxmin, B->dx, nv, e->n, B->cons, e->nc,
+                                    B->coarse, cis, cie);
+    } else {
+      /* fine to coarse (:710-748 restriction of the interiors into the daughters' coarse
+       * buffers, TryRecvFineToCoarse :163-228 copies them into the octants) */
+      for (int c = 0; c < nleaf; ++c) {
+        int clx[3];
+        for (int d = 0; d < 3; ++d) clx[d] = (d < e->ndim) ? 2 * lf->lx[d] + ((c >> d) & 1) : 0;
+        const int f = leaf_find(old, nold, lf->level + 1, clx);
+        if (f < 0) {
+          fprintf(stderr, "apk_oracle: remesh lost a block\n");
+          abort();
+        }
+        block_t *F = &oblk[f];
+        apko_restrict_average(e->ndim, ng, 0, F->bxmin, F->dx, nv, e->n, F->cons, e->nc, F->coarse,
+                              cis, cie);
+        int s[3];
+        for (int d = 0; d < 3; ++d) s[d] = (d < e->ndim && ((c >> d) & 1)) ? p->mb[d] / 2 : 0;
+        for (int v = 0; v < nv; ++v)
+          for (int k = cis[2]; k <= cie[2]; ++k)
+            for (int j = cis[1]; j <= cie[1]; ++j)
+              for (int i = cis[0]; i <= cie[0]; ++i)
+                B->cons[IDX(e, v, k + s[2], j + s[1], i + s[0])] = F->coarse[CIDX(e, v, k, j, i)];
+      }
+    }
+  }
+  for (int q = 0; q < nold; ++q)
+    if (!moved[q]) block_free(&oblk[q]);
+  free(moved);
+  free(oblk);
+  free(old);
+  free(S.L);
+  e->blk = nblk;
+  e->nblocks = S.n;
+  build_neighbor_tables(e);
+  /* :973-990 ghosts with real data, derived quantities */
+  apko_exchange(e);
+  apko_cons_to_prim(e);
+  return 1;
+}
+
 void apko_initialize(apko_engine *e, double tlim) {
   e->tlim = tlim;
   e->time = 0.0;
   e->ncycle = 0;
   apko_exchange(e);
   apko_cons_to_prim(e);
+  if (e->p.adaptive) {
+    /* Mesh::Initialize (mesh.cpp:746-840): tag, refine, re-run the problem generator on the new
+     * mesh until the number of blocks stops changing */
+    if (e->pgen_id < 0) {
+      fprintf(stderr, "apk_oracle: adaptive meshes are initialised through apko_pgen\n");
+      abort();
+    }
+    for (;;) {
+      apko_amr_tag(e);
+      const int nb_before = e->nblocks;
+      apko_amr_remesh(e);
+      if (e->nblocks == nb_before) break;
+      apko_pgen(e, e->pgen_id, e->pgen_npars ? e->pgen_pars : NULL, e->pgen_npars);
+      apko_exchange(e);
+      apko_cons_to_prim(e);
+    }
+  }
   /* EvolutionDriver::InitializeBlockTimeSteps + SetGlobalTimeStep (driver.cpp:194-242) */
   e->dt = DBL_MAX;
   e->dt_hyp = DBL_MAX;
@@ -2433,10 +2849,14 @@ void apko_cycle(apko_engine *e) {
       e->dt_hyp = DBL_MAX;
       e->dt_diff = DBL_MAX;
       e->new_dt = apko_estimate_dt(e);
+      /* hydro_driver.cpp:662-670 */
+      if (e->p.adaptive) apko_amr_tag(e);
     }
   }
   e->ncycle++;
   e->time += e->dt;
+  /* driver.cpp:128-131 */
+  if (e->p.adaptive && apko_amr_remesh(e)) e->new_dt = apko_estimate_dt(e);
   set_global_dt(e);
 }
 
@@ -2688,6 +3108,11 @@ int apko_pgen(apko_engine *e, int id, const double *pars, int npars) {
   const apko_params *p = &e->p;
   const double gm1 = p->gamma - 1.0;
   const int mhd = (p->fluid == APKO_FLUID_GLMMHD);
+  if (pars != e->pgen_pars) {
+    e->pgen_id = id;
+    e->pgen_npars = npars > 16 ? 16 : (npars < 0 ? 0 : npars);
+    for (int q = 0; q < e->pgen_npars; ++q) e->pgen_pars[q] = pars[q];
+  }
   if (id == APKO_PGEN_LINEAR_WAVE) lw_setup(e, pars, npars, 0);
   if (id == APKO_PGEN_LINEAR_WAVE_MHD) {
     if (!mhd) return -1;

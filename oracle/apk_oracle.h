@@ -59,6 +59,11 @@ typedef struct {
   double cfl_diff;            /* diffusion/cfl; <= 0: the hyperbolic cfl (hydro.cpp:697) */
   double rkl2_max_dt_ratio;   /* default -1 (hydro.cpp:688) */
   double conduction_sat_phi;  /* default 0.3; fixed coefficient: prefac = 5 phi (hydro.cpp:604) */
+  /* adaptive mesh refinement (parthenon/mesh/refinement = adaptive): numlevel levels in total,
+   * derefine_count (mesh_refinement.cpp:56), <refinement> type = pressure_gradient with
+   * threshold_pressure_gradient (src/refinement/gradient.cpp:18-61) */
+  int adaptive, numlevel, derefine_count;
+  double refine_threshold;
 } apko_params;
 
 typedef struct apko_engine apko_engine;
@@ -78,6 +83,14 @@ int apko_run(apko_engine *e, double tlim, int nlim);
 void apko_cycle(apko_engine *e);
 
 int apko_num_blocks(const apko_engine *e);
+/* adaptive meshes: blocks created / destroyed so far (Mesh::nbnew, nbdel) and blocks per level */
+void apko_amr_counts(const apko_engine *e, int *nbnew, int *nbdel, int *per_level8);
+/* the two halves of the per-cycle AMR step, exposed for unit tests: Refinement::Tag on every
+ * block (returns the number of non-zero flags) and Mesh::LoadBalancingAndAdaptiveMeshRefinement
+ * (returns 1 when the mesh changed; ghost cells, prim and the dt vote are rebuilt) */
+int apko_amr_tag(apko_engine *e);
+int apko_amr_remesh(apko_engine *e);
+int apko_amr_flag(const apko_engine *e, int b); /* refine_flag_ of block b */
 /* refinement level and logical location (at that level) of block b */
 void apko_block_loc(const apko_engine *e, int b, int *level, int *lx3);
 void apko_block_dims(const apko_engine *e, int *n /*[3] incl ghosts: n1,n2,n3*/);

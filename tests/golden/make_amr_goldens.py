@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Generates tests/golden/reference_traces_amr.json by RUNNING THE UNMODIFIED REFERENCE
+(baseline/_ref/serial/bin/athenaPK, built by baseline/build_reference.sh) on inputs/blast_3d_amr.in
+with `refinement = adaptive` (BASELINE config 5) and the CLI overrides recorded per case.  Kept per
+case: Parthenon's per-cycle `time` / `dt` printout at all 17 digits (driver.cpp:301-306), the number
+of meshblocks it prints every cycle (`ncycle_out_mesh = -1`, driver.cpp:311-330) with the count
+per level, and the created / destroyed totals of the closing message (driver.cpp:177-181).
+
+  python tests/golden/make_amr_goldens.py          (about 3 minutes)
+
+The parity tests (CPU oracle here, CUDA path on the GPU box) read only the JSON."""
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+BIN = os.path.join(ROOT, "baseline", "_ref", "serial", "bin", "athenaPK")
+DECK = "/root/reference/inputs/blast_3d_amr.in"
+CYCLE = re.compile(r"cycle=(\d+) time=(\S+) dt=(\S+)")
+MESH = re.compile(r"Total number of MeshBlocks = (\d+)\n(?:Number of .*\n)*((?:  Physical level = .*\n)+)")
+LEVEL = re.compile(r"Physical level = (\d+) .*: (\d+) MeshBlocks")
+TOTALS = re.compile(r"Number of MeshBlocks = (\d+); (\d+)  created, (\d+) destroyed")
+
+BLAST = ["problem/blast/radius_outer=0.12", "problem/blast/radius_inner=0.12",
+         "problem/blast/pressure_ratio=100", "problem/blast/pressure_ambient=0.1",
+         "problem/blast/x1_0=0.22", "problem/blast/x2_0=0.1", "problem/blast/x3_0=-0.05"]
+COMMON = ["parthenon/output0/file_type=hst", "parthenon/time/ncycle_out_mesh=-1"]
+
+CASES = {
+    # the deck as it is (Euler, PLM + HLLE, nghost = 2, 3 levels), blast off the origin
+    "adaptive_3d_plm_hlle": ["parthenon/time/nlim=30"] + BLAST,
+    # BASELINE config 5's method: GLM-MHD, WENOZ + HLLD, nghost = 4 (odd nghost is rejected with
+    # mesh refinement, mesh_refinement.cpp:60-70)
+    "adaptive_3d_wenoz_hlld": ["parthenon/time/nlim=12", "hydro/fluid=glmmhd",
+                               "hydro/reconstruction=wenoz", "hydro/riemann=hlld",
+                               "parthenon/mesh/nghost=4"] + BLAST,
+    # 2-D, 4 levels, quick derefinement (derefine_count = 3) behind the expanding shock
+    "adaptive_2d_plm_hllc": ["parthenon/time/nlim=120", "parthenon/mesh/nx1=64",
+                             "parthenon/mesh/nx2=64", "parthenon/mesh/nx3=1",
+                             "parthenon/meshblock/nx3=1", "parthenon/mesh/numlevel=4",
+                             "parthenon/mesh/derefine_count=3", "hydro/riemann=hllc",
+                             "refinement/threshold_pressure_gradient=0.2"] + BLAST,
+}
+
+
+def run(overrides):
+    with tempfile.TemporaryDirectory() as tmp:
+        cmd = [BIN, "-i", DECK] + overrides + COMMON
+        p = subprocess.run(cmd, cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if p.returncode != 0:
+            raise RuntimeError(" ".join(cmd) + "\n" + p.stdout[-2000:])
+    trace = [[m.group(2), m.group(3)] for m in CYCLE.finditer(p.stdout)]
+    # one mesh printout per cycle line ("Current Mesh structure" / "New Mesh structure")
+    blocks = []
+    for m in MESH.finditer(p.stdout):
+        per = {int(a): int(b) for a, b in LEVEL.findall(m.group(2))}
+        blocks.append([int(m.group(1))] + [per.get(l, 0) for l in range(max(per) + 1)])
+    tot = TOTALS.search(p.stdout)
+    return {"overrides": overrides, "ncycle": len(trace) - 1, "trace": trace, "blocks": blocks,
+            "final": [int(tot.group(1)), int(tot.group(2)), int(tot.group(3))]}
+
+
+def main():
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        jobs = {k: ex.submit(run, ov) for k, ov in CASES.items()}
+    out = {"_provenance": "printed by the UNMODIFIED reference (Kokkos Serial, g++ -O3, no FMA) run by "
+                          "tests/golden/make_amr_goldens.py; trace = [time, dt] per cycle at 17 digits, "
+                          "blocks = [total, level 0, level 1, ...] per cycle, final = [blocks, created, destroyed]"}
+    for k, f in jobs.items():
+        out[k] = f.result()
+        print(k, out[k]["ncycle"], out[k]["trace"][-1], out[k]["final"], len(out[k]["blocks"]), flush=True)
+    json.dump(out, open(os.path.join(HERE, "reference_traces_amr.json"), "w"), indent=0)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

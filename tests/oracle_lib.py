@@ -38,6 +38,8 @@ class Params(C.Structure):
         ("thermal_diff_coeff", C.c_double), ("mom_diff_coeff", C.c_double),
         ("ohm_diff_coeff", C.c_double), ("cfl_diff", C.c_double),
         ("rkl2_max_dt_ratio", C.c_double), ("conduction_sat_phi", C.c_double),
+        ("adaptive", C.c_int), ("numlevel", C.c_int), ("derefine_count", C.c_int),
+        ("refine_threshold", C.c_double),
     ]
 
 
@@ -71,6 +73,10 @@ def lib():
     L.apko_run.argtypes = [C.c_void_p, C.c_double, C.c_int]
     L.apko_cycle.argtypes = [C.c_void_p]
     L.apko_num_blocks.argtypes = [C.c_void_p]
+    L.apko_amr_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.apko_amr_tag.argtypes = [C.c_void_p]
+    L.apko_amr_remesh.argtypes = [C.c_void_p]
+    L.apko_amr_flag.argtypes = [C.c_void_p, C.c_int]
     L.apko_block_loc.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.apko_block_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     L.apko_nvar.argtypes = [C.c_void_p]
@@ -120,9 +126,12 @@ def make_params(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
                 glmmhd_alpha=0.1, nscalars=0, dfloor=-1.0, pfloor=-1.0, efloor=-1.0,
                 vceil=float("inf"), eceil=float("inf"), refine=(), diffint="none",
                 conduction="none", thermal_diff_coeff=0.0, viscosity="none", mom_diff_coeff=0.0,
-                resistivity="none", ohm_diff_coeff=0.0, cfl_diff=-1.0, rkl2_max_dt_ratio=-1.0):
+                resistivity="none", ohm_diff_coeff=0.0, cfl_diff=-1.0, rkl2_max_dt_ratio=-1.0,
+                adaptive=None):
     """refine: static refinement regions [(level, (x1min, x2min, x3min), (x1max, x2max, x3max)), ...]
-    = the <parthenon/static_refinementN> blocks of a deck"""
+    = the <parthenon/static_refinementN> blocks of a deck.
+    adaptive: dict(numlevel=, threshold=, derefine_count=10) = parthenon/mesh/refinement = adaptive
+    with <refinement> type = pressure_gradient"""
     p = Params()
     lib().apko_default_params(C.byref(p))
     p.fluid, p.recon, p.riemann = FLUID[fluid], RECON[recon], RIEMANN[riemann]
@@ -143,6 +152,10 @@ def make_params(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
     p.viscosity, p.resistivity = int(viscosity == "isotropic"), int(resistivity == "ohmic")
     p.thermal_diff_coeff, p.mom_diff_coeff, p.ohm_diff_coeff = thermal_diff_coeff, mom_diff_coeff, ohm_diff_coeff
     p.cfl_diff, p.rkl2_max_dt_ratio = cfl_diff, rkl2_max_dt_ratio
+    if adaptive:
+        p.adaptive, p.numlevel = 1, adaptive["numlevel"]
+        p.derefine_count = adaptive.get("derefine_count", 10)
+        p.refine_threshold = adaptive["threshold"]
     p.nref = len(refine)
     for r, (lev, lo, hi) in enumerate(refine):
         p.ref_level[r] = lev
@@ -164,7 +177,16 @@ class Oracle:
         self.L.apko_block_dims(self.h, n)
         self.n = tuple(n)  # (n1, n2, n3)
         self.nvar = self.L.apko_nvar(self.h)
-        self.nblocks = self.L.apko_num_blocks(self.h)
+
+    @property
+    def nblocks(self):
+        return self.L.apko_num_blocks(self.h)
+
+    def amr_counts(self):
+        """(blocks created, blocks destroyed, [blocks per level])"""
+        a, b, lv = C.c_int(), C.c_int(), (C.c_int * 8)()
+        self.L.apko_amr_counts(self.h, C.byref(a), C.byref(b), lv)
+        return a.value, b.value, list(lv)
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -6,8 +6,9 @@ GPU tests hold to the same traces in strict FP mode."""
 import pytest
 
 from oracle_lib import Oracle
-from trace_util import (AMR_DECKS, DECKS, DIFF_DECKS, DIFF_TRACES, TRACES, check_lw_row,
-                        follow_trace, lw_kwargs, lw_pgen)
+from trace_util import (ADAPTIVE_DECKS, ADAPTIVE_TRACES, AMR_DECKS, DECKS, DIFF_DECKS, DIFF_TRACES,
+                        TRACES, check_lw_row, follow_adaptive_trace, follow_trace, lw_kwargs,
+                        lw_pgen)
 
 
 def advance(o, tlim, c):
@@ -85,6 +86,24 @@ def test_static_refinement_traces(name):
     o.pgen(pgen, pars)
     o.initialize(tlim)
     follow_trace(o, case["trace"], tlim, advance)
+    assert o.ncycle == case["ncycle"]
+
+
+@pytest.mark.parametrize("name", sorted(ADAPTIVE_DECKS))
+def test_adaptive_refinement_traces(name):
+    """BASELINE config 5 as the reference runs it (inputs/blast_3d_amr.in, refinement = adaptive,
+    pressure-gradient criterion): the refinement loop of Mesh::Initialize, the per-cycle tagging with
+    the derefinement counter, Tree::Refine / Derefine with proper nesting, the data move (minmod
+    prolongation of new fine blocks, restriction into new coarse blocks) and the rebuilt exchange
+    reproduce the reference's (time, dt) at all 17 digits AND its meshblock counts per level every
+    cycle, plus the created / destroyed totals (3-D: up to 680 blocks, 91 destroyed; 2-D, 4 levels,
+    derefine_count = 3: 714 created, 300 destroyed in 120 cycles)."""
+    kw, pgen, pars, tlim = ADAPTIVE_DECKS[name]
+    o = Oracle(**kw)
+    o.pgen(pgen, pars)
+    o.initialize(tlim)
+    case = ADAPTIVE_TRACES[name]
+    follow_adaptive_trace(o, case, tlim, advance, lambda o: o.amr_counts())
     assert o.ncycle == case["ncycle"]
 
 

@@ -112,6 +112,44 @@ AMR_DECKS = {
 }
 
 
+# adaptive mesh refinement (tests/golden/make_amr_goldens.py -> reference_traces_amr.json):
+# inputs/blast_3d_amr.in with refinement = adaptive, <refinement> type = pressure_gradient
+ADAPTIVE_TRACES = json.load(open(os.path.join(os.path.dirname(GOLDEN), "reference_traces_amr.json")))
+_BLAST_OFF = [0.12, 0.1, 100.0, 1.0, 0.22, 0.1, -0.05]
+
+
+def _adaptive(fluid, recon, rs, ng, numlevel, threshold=0.1, derefine_count=10, nx=(32, 32, 32),
+              mb=(8, 8, 8)):
+    return (dict(fluid=fluid, nx=nx, mb=mb, ng=ng, xmin=(-0.5,) * 3, xmax=(0.5,) * 3,
+                 gamma=GAMMA_DECK, cfl=0.3, recon=recon, riemann=rs, integrator="vl2",
+                 adaptive=dict(numlevel=numlevel, threshold=threshold, derefine_count=derefine_count)),
+            "blast", _BLAST_OFF, 0.1)
+
+
+ADAPTIVE_DECKS = {
+    "adaptive_3d_plm_hlle": _adaptive("euler", "plm", "hlle", 2, 3),
+    "adaptive_3d_wenoz_hlld": _adaptive("glmmhd", "wenoz", "hlld", 4, 3),
+    "adaptive_2d_plm_hllc": _adaptive("euler", "plm", "hllc", 2, 4, threshold=0.2, derefine_count=3,
+                                      nx=(64, 64, 1), mb=(8, 8, 1)),
+}
+
+
+def follow_adaptive_trace(engine, case, tlim, advance, counts):
+    """like follow_trace, plus the number of meshblocks (total and per level) the reference prints
+    every cycle; counts(engine) -> (created, destroyed, [blocks per level])"""
+    for c, (t, dt) in enumerate(case["trace"]):
+        if c > 0:
+            advance(engine, tlim, c)
+        got = ("%.16e" % engine.time, "%.16e" % engine.dt)
+        assert got == (t, dt), "cycle %d: got %s, reference printed %s" % (c, got, (t, dt))
+        created, destroyed, per_level = counts(engine)
+        want = case["blocks"][c]
+        assert [engine.nblocks] + per_level[:len(want) - 1] == want, (c, per_level, want)
+    created, destroyed, _ = counts(engine)
+    # Mesh::nbnew / nbdel also count the refinement during Mesh::Initialize
+    assert [engine.nblocks, created, destroyed] == case["final"]
+
+
 def follow_trace(engine, trace, tlim, advance, every=1):
     """advance(engine, tlim, ncycle) runs the engine up to cycle `ncycle`; compares (time, dt) with
     the reference's printout at all 17 digits.  Returns the number of cycles compared."""
