@@ -44,6 +44,8 @@ class SimConfig(C.Structure):
         ("thermal_diff_coeff", C.c_double), ("mom_diff_coeff", C.c_double),
         ("ohm_diff_coeff", C.c_double), ("cfl_diff", C.c_double),
         ("rkl2_max_dt_ratio", C.c_double), ("conduction_sat_phi", C.c_double),
+        ("adaptive", C.c_int), ("numlevel", C.c_int), ("derefine_count", C.c_int),
+        ("refine_threshold", C.c_double),
     ]
 
 
@@ -109,6 +111,8 @@ SIM_SYMBOLS = [
     "apk_sim_interior_elems", "apk_sim_load_interior", "apk_sim_store_interior", "apk_sim_history",
     "apk_sim_enable_task_timing", "apk_sim_task_timing", "apk_sim_num_peers", "apk_sim_peer",
     "apk_sim_num_halo_items", "apk_sim_halo_item", "apk_sim_neighbor", "apk_sim_push_target",
+    "apk_sim_amr_counts", "apk_sim_amr_tag", "apk_sim_amr_remesh", "apk_sim_amr_flag",
+    "apk_sim_amr_update_tree", "apk_sim_amr_timing",
 ]
 
 _lib = None
@@ -214,6 +218,13 @@ def lib():
     L.apk_sim_num_halo_items.argtypes = [vp, C.c_int]
     L.apk_sim_halo_item.argtypes = [vp, C.c_int, C.c_int, C.POINTER(HaloItem)]
     L.apk_sim_neighbor.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.apk_sim_amr_counts.argtypes = [vp, ip, ip, ip]
+    L.apk_sim_amr_tag.argtypes = [vp]
+    L.apk_sim_amr_remesh.argtypes = [vp]
+    L.apk_sim_amr_flag.argtypes = [vp, C.c_int]
+    L.apk_sim_amr_timing.argtypes = [vp, dp]
+    L.apk_sim_amr_timing.restype = C.c_longlong
+    L.apk_sim_amr_update_tree.argtypes = [C.POINTER(SimConfig), C.c_int, ip, ip, C.c_int, ip, ip, ip]
     _lib = L
     return L
 
@@ -225,10 +236,12 @@ def make_config(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
                 eceil=float("inf"), fp_mode="fast", fused=True, rank=0, nranks=1,
                 plan_only=False, refine=(), diffint="none", conduction="none",
                 thermal_diff_coeff=0.0, viscosity="none", mom_diff_coeff=0.0, resistivity="none",
-                ohm_diff_coeff=0.0, cfl_diff=-1.0, rkl2_max_dt_ratio=-1.0):
+                ohm_diff_coeff=0.0, cfl_diff=-1.0, rkl2_max_dt_ratio=-1.0, adaptive=None):
     """Input-deck style configuration (same keys/meaning as docs/input.md of the reference).
     refine: static refinement regions [(level, (x1min, x2min, x3min), (x1max, x2max, x3max)), ...]
-    = the <parthenon/static_refinementN> blocks of a deck."""
+    = the <parthenon/static_refinementN> blocks of a deck.
+    adaptive: dict(numlevel=, threshold=, derefine_count=10) = parthenon/mesh/refinement = adaptive
+    with <refinement> type = pressure_gradient."""
     c = SimConfig()
     lib().apk_sim_default_config(C.byref(c))
     c.fluid, c.recon, c.riemann = FLUID[fluid], RECON[recon], RIEMANN[riemann]
@@ -261,7 +274,28 @@ def make_config(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
     c.resistivity = {"none": 0, "ohmic": 1}[resistivity]
     c.thermal_diff_coeff, c.mom_diff_coeff, c.ohm_diff_coeff = thermal_diff_coeff, mom_diff_coeff, ohm_diff_coeff
     c.cfl_diff, c.rkl2_max_dt_ratio = cfl_diff, rkl2_max_dt_ratio
+    if adaptive:
+        c.adaptive, c.numlevel = 1, adaptive["numlevel"]
+        c.derefine_count = adaptive.get("derefine_count", 10)
+        c.refine_threshold = adaptive["threshold"]
     return c
+
+
+def amr_update_tree(cfg, leaves, flags):
+    """Mesh::UpdateMeshBlockTree of the host driver on plain lists (no GPU needed): leaves =
+    [(level, lx1, lx2, lx3)], flags = refine_flag_ per leaf.  Returns (new leaves or None when
+    nothing changes, blocks created, blocks destroyed)."""
+    n = len(leaves)
+    a = (C.c_int * (4 * n))(*[v for l in leaves for v in l])
+    f = (C.c_int * n)(*flags)
+    cap = 8 * n + 64
+    out = (C.c_int * (4 * cap))()
+    nnew, ndel = C.c_int(), C.c_int()
+    rc = lib().apk_sim_amr_update_tree(C.byref(cfg), n, a, f, cap, out, C.byref(nnew), C.byref(ndel))
+    if rc < 0:
+        raise RuntimeError("apk_sim_amr_update_tree: " + lib().apk_sim_last_error().decode())
+    new = [tuple(out[4 * b:4 * b + 4]) for b in range(rc)] if rc else None
+    return new, nnew.value, ndel.value
 
 
 class HydroSim:
@@ -278,9 +312,32 @@ class HydroSim:
         self.L.apk_sim_block_dims(self.h, n)
         self.n = tuple(n)
         self.nvar = self.L.apk_sim_nvar(self.h)
-        self.nblocks = self.L.apk_sim_num_local_blocks(self.h)
-        self.nblocks_global = self.L.apk_sim_num_global_blocks(self.h)
         self.shape = (self.nvar, self.n[2], self.n[1], self.n[0])
+
+    # (adaptive meshes change both whenever the mesh does)
+    nblocks = property(lambda s: s.L.apk_sim_num_local_blocks(s.h))
+    nblocks_global = property(lambda s: s.L.apk_sim_num_global_blocks(s.h))
+
+    def amr_counts(self):
+        """(meshblocks created, destroyed, [blocks per level]) -- Mesh::nbnew / nbdel"""
+        a, b, lv = C.c_int(), C.c_int(), (C.c_int * 8)()
+        self.L.apk_sim_amr_counts(self.h, C.byref(a), C.byref(b), lv)
+        return a.value, b.value, list(lv)
+
+    def amr_timing(self):
+        """(#remeshes, {phase: host ms summed}) of the AMR step"""
+        ms = (C.c_double * 5)()
+        n = self.L.apk_sim_amr_timing(self.h, ms)
+        return n, dict(zip(("tag", "tree", "rebuild", "move", "fill"), list(ms)))
+
+    def amr_tag(self):
+        self._chk(self.L.apk_sim_amr_tag(self.h), "amr_tag")
+
+    def amr_remesh(self):
+        return self._chk(self.L.apk_sim_amr_remesh(self.h), "amr_remesh")
+
+    def amr_flags(self):
+        return [self.L.apk_sim_amr_flag(self.h, b) for b in range(self.nblocks)]
 
     def close(self):
         if getattr(self, "h", None):

@@ -117,7 +117,14 @@ HydroSim::HydroSim(const SimConfig &cfg)
     n_[d] = (cfg_.nx[d] == 1) ? 1 : cfg_.mb[d] + 2 * cfg_.ng;
   }
   nblocks_global_ = nb_[0] * nb_[1] * nb_[2];
-  multilevel_ = cfg_.nref > 0;
+  multilevel_ = cfg_.nref > 0 || cfg_.adaptive;
+  if (cfg_.adaptive) {
+    if (cfg_.nranks != 1)
+      throw std::runtime_error("apk_host: adaptive remeshing runs on one rank (static refinement "
+                               "runs on several)");
+    if (ndim_ < 2 || cfg_.numlevel < 1)
+      throw std::runtime_error("apk_host: refinement = adaptive needs a 2-D or 3-D mesh and numlevel >= 1");
+  }
   if (multilevel_) {
     // mesh_refinement.cpp:60-70
     if (cfg_.ng % 2 != 0)
@@ -173,31 +180,17 @@ HydroSim::~HydroSim() {
   if (cfg_.plan_only) return;
   cudaDeviceSynchronize();
   if (comm_) ncclCommDestroy(reinterpret_cast<ncclComm_t>(comm_));
-  cudaFree(d_cons_);
-  cudaFree(d_prim_[0]);
-  cudaFree(d_prim_[1]);
-  cudaFree(d_u1_);
-  for (int d = 0; d < 3; ++d) cudaFree(d_flux_[d]);
-  cudaFree(d_my0_);
-  cudaFree(d_yjm2_);
-  cudaFree(d_my0_ptrs_);
-  cudaFree(d_yjm2_ptrs_);
-  cudaFree(d_blocks_[0]);
-  cudaFree(d_blocks_[1]);
-  cudaFree(d_prim_out_[0]);
-  cudaFree(d_prim_out_[1]);
+  apk_tma_maps_destroy(d_tma_[0]);
+  apk_tma_maps_destroy(d_tma_[1]);
+  d_tma_[0] = d_tma_[1] = nullptr;
+  ReleaseMeshArrays();
+  SlabFree(d_cons_);
+  for (auto &kv : slab_pool_) cudaFree(kv.first);
+  cudaFree(d_tags_);
+  cudaFree(d_maxeps_);
   cudaFree(d_scalars_);
   if (h_scalars_) cudaFreeHost(h_scalars_);
   cudaFree(d_status_);
-  cudaFree(d_fofc_work_);
-  cudaFree(d_undo_);
-  cudaFree(d_coarse_);
-  for (MlList *l : {&ml_restrict_child_, &ml_child_to_ghost_, &ml_restrict_own_, &ml_coarse_from_nbr_,
-                    &ml_prolong_, &ml_fc_restrict_[0], &ml_fc_restrict_[1], &ml_fc_restrict_[2],
-                    &ml_fc_copy_[0], &ml_fc_copy_[1], &ml_fc_copy_[2]})
-    cudaFree(l->d);
-  apk_tma_maps_destroy(d_tma_[0]);
-  apk_tma_maps_destroy(d_tma_[1]);
   apk_halo_plan_destroy(halo_plan_);
   if (!peer_mapped_.empty()) apk_p2p_unmap(peer_mapped_.data(), (int)peer_mapped_.size());
   cudaFree(d_push_[0]);
@@ -214,6 +207,7 @@ void HydroSim::Synchronize() { cuda_check(cudaStreamSynchronize(S(stream_)), "sy
 // Block list in Morton (Z) order like Parthenon's forest (forest.cpp:106-160); contiguous gid
 // ranges go to ranks (what Parthenon's load balancer does for equal-cost blocks).
 void HydroSim::BuildMesh() {
+  nblocks_global_ = nb_[0] * nb_[1] * nb_[2];  // (a remesh comes back here with the old leaf count)
   std::vector<std::pair<std::uint64_t, std::array<int, 3>>> order;
   for (int z = 0; z < nb_[2]; ++z)
     for (int y = 0; y < nb_[1]; ++y)
@@ -227,7 +221,7 @@ void HydroSim::BuildMesh() {
     gid_of_loc_[l[0] + nb_[0] * (l[1] + nb_[1] * l[2])] = g;
   }
   if (multilevel_) {
-    leaves_ = BuildLeaves();
+    if (leaves_.empty()) leaves_ = BuildLeaves();  // (a remesh installs the new leaf list itself)
     nblocks_global_ = (int)leaves_.size();
     for (int d = 0; d < 3; ++d) nc_[d] = (d < ndim_) ? cfg_.mb[d] / 2 + 2 * cfg_.ng : 1;
   }
@@ -547,31 +541,97 @@ void HydroSim::BuildNeighbors() {
   }
 }
 
+// Device slabs come from a small recycling pool: an adaptive run remeshes almost every cycle, and
+// cudaMalloc / cudaFree (a device-wide synchronisation each) would dominate it.
+void *HydroSim::SlabAlloc(size_t bytes, const char *what) {
+  int best = -1;
+  for (size_t q = 0; q < slab_pool_.size(); ++q)
+    if (slab_pool_[q].second >= bytes && slab_pool_[q].second <= 2 * bytes + (1u << 20) &&
+        (best < 0 || slab_pool_[q].second < slab_pool_[best].second))
+      best = (int)q;
+  void *p = nullptr;
+  if (best >= 0) {
+    p = slab_pool_[best].first;
+    slab_pool_.erase(slab_pool_.begin() + best);
+    return p;
+  }
+  // grow with some head room so that the next few remeshes fit
+  const size_t cap = cfg_.adaptive ? bytes + bytes / 4 : bytes;
+  cuda_check(cudaMalloc(&p, cap), what);
+  slab_size_[p] = cap;
+  return p;
+}
+
+void HydroSim::SlabFree(void *p) {
+  if (!p) return;
+  auto it = slab_size_.find(p);
+  if (it == slab_size_.end()) {
+    cudaFree(p);
+    return;
+  }
+  slab_pool_.push_back({p, it->second});
+  // keep the pool bounded: drop the smallest slabs beyond 48 entries
+  while (slab_pool_.size() > 48) {
+    size_t m = 0;
+    for (size_t q = 1; q < slab_pool_.size(); ++q)
+      if (slab_pool_[q].second < slab_pool_[m].second) m = q;
+    slab_size_.erase(slab_pool_[m].first);
+    cudaFree(slab_pool_[m].first);
+    slab_pool_.erase(slab_pool_.begin() + m);
+  }
+}
+
+// everything UploadBlocks allocates for one mesh, except the cons slab (a remesh still reads it)
+void HydroSim::ReleaseMeshArrays() {
+  auto slab = [&](double *&p) { SlabFree(p); p = nullptr; };
+  slab(d_prim_[0]);
+  slab(d_prim_[1]);
+  slab(d_u1_);
+  for (int d = 0; d < 3; ++d) slab(d_flux_[d]);
+  slab(d_my0_);
+  slab(d_yjm2_);
+  slab(d_coarse_);
+  auto fr = [](auto *&p) { cudaFree(p); p = nullptr; };
+  auto pooled = [&](auto *&p) { SlabFree(p); p = nullptr; };
+  fr(d_my0_ptrs_);
+  fr(d_yjm2_ptrs_);
+  pooled(d_blocks_[0]);
+  pooled(d_blocks_[1]);
+  pooled(d_prim_out_[0]);
+  pooled(d_prim_out_[1]);
+  fr(d_undo_);
+  fr(d_fofc_work_);
+  fr(d_hist_);
+  fr(d_stage_);
+  fr(d_int_items_);
+  for (MlList *l : {&ml_restrict_child_, &ml_child_to_ghost_, &ml_restrict_own_, &ml_coarse_from_nbr_,
+                    &ml_prolong_, &ml_fc_restrict_[0], &ml_fc_restrict_[1], &ml_fc_restrict_[2],
+                    &ml_fc_copy_[0], &ml_fc_copy_[1], &ml_fc_copy_[2], &ml_same_remote_}) {
+    SlabFree(l->d);
+    l->d = nullptr;
+    l->n = 0;
+  }
+}
+
 void HydroSim::UploadBlocks() {
   const size_t per = BlockFieldElems();
   const size_t nbl = blocks_.size();
   const size_t bytes = per * nbl * sizeof(double);
-  cuda_check(cudaMalloc(&d_cons_, bytes), "cudaMalloc cons");
-  cuda_check(cudaMalloc(&d_prim_[0], bytes), "cudaMalloc prim");
-  cuda_check(cudaMalloc(&d_u1_, bytes), "cudaMalloc u1");
-  cuda_check(cudaMemset(d_cons_, 0, bytes), "memset");
-  cuda_check(cudaMemset(d_prim_[0], 0, bytes), "memset");
-  cuda_check(cudaMemset(d_u1_, 0, bytes), "memset");
-  if (fused_) {
-    cuda_check(cudaMalloc(&d_prim_[1], bytes), "cudaMalloc prim scratch");
-    cuda_check(cudaMemset(d_prim_[1], 0, bytes), "memset");
-  }
+  auto slab = [&](const char *what) {
+    double *p = static_cast<double *>(SlabAlloc(bytes, what));
+    cuda_check(cudaMemsetAsync(p, 0, bytes, S(stream_)), "memset");
+    return p;
+  };
+  d_cons_ = slab("cudaMalloc cons");
+  d_prim_[0] = slab("cudaMalloc prim");
+  d_u1_ = slab("cudaMalloc u1");
+  if (fused_) d_prim_[1] = slab("cudaMalloc prim scratch");
   if (!fused_ || cfg_.fofc) {
-    for (int d = 0; d < ndim_; ++d) {
-      cuda_check(cudaMalloc(&d_flux_[d], bytes), "cudaMalloc flux");
-      cuda_check(cudaMemset(d_flux_[d], 0, bytes), "memset");
-    }
+    for (int d = 0; d < ndim_; ++d) d_flux_[d] = slab("cudaMalloc flux");
   }
   if (cfg_.diffint == 2) {  // RKL2 registers (hydro_driver.cpp:211-212)
-    cuda_check(cudaMalloc(&d_my0_, bytes), "cudaMalloc MY0");
-    cuda_check(cudaMalloc(&d_yjm2_, bytes), "cudaMalloc Yjm2");
-    cuda_check(cudaMemset(d_my0_, 0, bytes), "memset");
-    cuda_check(cudaMemset(d_yjm2_, 0, bytes), "memset");
+    d_my0_ = slab("cudaMalloc MY0");
+    d_yjm2_ = slab("cudaMalloc Yjm2");
     std::vector<double *> pm(nbl), py(nbl);
     for (size_t b = 0; b < nbl; ++b) {
       pm[b] = d_my0_ + b * per;
@@ -596,7 +656,7 @@ void HydroSim::UploadBlocks() {
       for (int d = 0; d < 3; ++d) hb[b].flux[d] = d_flux_[d] ? d_flux_[d] + b * per : nullptr;
       pout[b] = fused_ ? d_prim_[1 - which] + b * per : nullptr;
     }
-    cuda_check(cudaMalloc(&d_blocks_[which], nbl * sizeof(apk_block_t)), "cudaMalloc blocks");
+    d_blocks_[which] = static_cast<apk_block_t *>(SlabAlloc(nbl * sizeof(apk_block_t), "cudaMalloc blocks"));
     cuda_check(cudaMemcpy(d_blocks_[which], hb.data(), nbl * sizeof(apk_block_t),
                           cudaMemcpyHostToDevice), "upload blocks");
     // A/B: TMA-staged prim tiles for the PPM stage (APK_B200_FUSED_V=3; GLM-MHD PPM+HLLD 3-D, FMA mode)
@@ -604,25 +664,29 @@ void HydroSim::UploadBlocks() {
     if (fused_ && ver && ver[0] == '3' && ndim_ == 3 && cfg_.fluid == APK_FLUID_GLMMHD &&
         cfg_.recon == APK_RECON_PPM && cfg_.riemann == APK_RIEMANN_HLLD && cfg_.fp_mode == APK_FP_FAST)
       abi_check(apk_tma_maps_create(&desc_, hb.data(), &d_tma_[which]), "apk_tma_maps_create");
-    cuda_check(cudaMalloc(&d_prim_out_[which], nbl * sizeof(double *)), "cudaMalloc prim_out");
+    d_prim_out_[which] = static_cast<double **>(SlabAlloc(nbl * sizeof(double *), "cudaMalloc prim_out"));
     cuda_check(cudaMemcpy(d_prim_out_[which], pout.data(), nbl * sizeof(double *),
                           cudaMemcpyHostToDevice), "upload prim_out");
   }
   if (multilevel_) {
-    cuda_check(cudaMalloc(&d_coarse_, CoarseElems() * nbl * sizeof(double)), "cudaMalloc coarse");
-    cuda_check(cudaMemset(d_coarse_, 0, CoarseElems() * nbl * sizeof(double)), "memset");
+    const size_t cbytes = CoarseElems() * nbl * sizeof(double);
+    d_coarse_ = static_cast<double *>(SlabAlloc(cbytes, "cudaMalloc coarse"));
+    cuda_check(cudaMemsetAsync(d_coarse_, 0, cbytes, S(stream_)), "memset");
     if (cfg_.nranks == 1) BuildMultilevelPlan();  // several ranks: after the peer mapping (InitComm)
   }
-  cuda_check(cudaMalloc(&d_scalars_, 64 * sizeof(double)), "cudaMalloc scalars");
-  cuda_check(cudaMemset(d_scalars_, 0, 64 * sizeof(double)), "memset scalars");
-  {
+  // the slabs are zeroed on the simulation stream; everything that follows (blocking copies of the
+  // problem generator, kernels on any stream) must see them cleared
+  cuda_check(cudaStreamSynchronize(S(stream_)), "sync after memset");
+  if (!d_scalars_) {
+    cuda_check(cudaMalloc(&d_scalars_, 64 * sizeof(double)), "cudaMalloc scalars");
+    cuda_check(cudaMemset(d_scalars_, 0, 64 * sizeof(double)), "memset scalars");
     const double big = DBL_MAX;
     cuda_check(cudaMemcpy(d_scalars_ + 8, &big, sizeof(double), cudaMemcpyHostToDevice), "scalars");
+    cuda_check(cudaHostAlloc(reinterpret_cast<void **>(&h_scalars_), 8 * sizeof(double),
+                             cudaHostAllocDefault), "pinned scalars");
+    cuda_check(cudaMalloc(&d_status_, sizeof(int)), "cudaMalloc status");
+    cuda_check(cudaMemset(d_status_, 0, sizeof(int)), "memset");
   }
-  cuda_check(cudaHostAlloc(reinterpret_cast<void **>(&h_scalars_), 8 * sizeof(double),
-                           cudaHostAllocDefault), "pinned scalars");
-  cuda_check(cudaMalloc(&d_status_, sizeof(int)), "cudaMalloc status");
-  cuda_check(cudaMemset(d_status_, 0, sizeof(int)), "memset");
   if (cfg_.fofc) {
     cuda_check(cudaMalloc(&d_fofc_work_, apk_fofc_workspace_bytes(&desc_)), "cudaMalloc fofc");
   }
@@ -1473,7 +1537,7 @@ void HydroSim::BuildMultilevelPlan() {
   auto upload = [&](MlList &dst, const void *src, size_t n, size_t elem) {
     dst.n = (int)n;
     if (!n || cfg_.plan_only) return;
-    cuda_check(cudaMalloc(&dst.d, n * elem), "cudaMalloc multilevel plan");
+    dst.d = SlabAlloc(n * elem, "cudaMalloc multilevel plan");
     cuda_check(cudaMemcpy(dst.d, src, n * elem, cudaMemcpyHostToDevice), "upload multilevel plan");
   };
   upload(ml_restrict_child_, restrict_child.data(), restrict_child.size(), sizeof(apk_amr_item_t));
@@ -1619,12 +1683,29 @@ void HydroSim::Initialize(double tlim) {
   tm.tlim = tlim;
   cur_ = 0;
   // Mesh::Initialize: exchange ghosts, BCs, FillDerived
-  SendBoundBufs(0);
-  ReceiveBoundBufs();
-  SetBounds(0);
-  ProlongateBounds();
-  ApplyBoundaryConditions(0);
-  FillDerived();
+  auto fill = [this] {
+    SendBoundBufs(0);
+    ReceiveBoundBufs();
+    SetBounds(0);
+    ProlongateBounds();
+    ApplyBoundaryConditions(0);
+    FillDerived();
+  };
+  fill();
+  if (cfg_.adaptive) {
+    // mesh.cpp:746-840: tag, refine, re-run the problem generator on the new mesh until the number
+    // of meshblocks stops changing
+    if (pgen_id_.empty())
+      throw std::runtime_error("apk_host: adaptive meshes are initialised through ProblemGenerator");
+    for (;;) {
+      TagRefinement();
+      const int nb_before = nblocks_global_;
+      LoadBalancingAndAdaptiveMeshRefinement();
+      if (nblocks_global_ == nb_before) break;
+      ProblemGenerator(pgen_id_, pgen_pars_);
+      fill();
+    }
+  }
   dt_hyp = std::numeric_limits<Real>::max();
   dt_diff_ = std::numeric_limits<Real>::max();
   EstimateTimestep(false);
@@ -1691,6 +1772,8 @@ void HydroSim::MakeTaskCollection(TaskList &tl, int stage) {
       last_stage_unfused_ = false;
       return EstimateTimestep(have);
     });
+    // hydro_driver.cpp:662-670
+    if (cfg_.adaptive) tl.AddTask("tag_refine", [this] { return TagRefinement(); });
   }
 }
 
@@ -1722,6 +1805,8 @@ int HydroSim::Execute(double tlim, int nlim) {  // driver.cpp:67-165
     tm.ncycle++;
     tm.time += tm.dt;
     cycles_done++;
+    // driver.cpp:128-131: remesh, and new block time steps when the mesh changed
+    if (cfg_.adaptive && LoadBalancingAndAdaptiveMeshRefinement()) EstimateTimestep(false);
     SetGlobalTimeStep();
   }
   Synchronize();

@@ -64,6 +64,10 @@ struct SimConfig {
   double cfl_diff = -1.0;           // diffusion/cfl (default: the hyperbolic cfl, hydro.cpp:697)
   double rkl2_max_dt_ratio = -1.0;  // hydro.cpp:688
   double conduction_sat_phi = 0.3;  // hydro.cpp:563-564
+  // adaptive mesh refinement: parthenon/mesh/refinement = adaptive, numlevel, derefine_count
+  // (mesh_refinement.cpp:56); <refinement> type = pressure_gradient, threshold_pressure_gradient
+  int adaptive = 0, numlevel = 1, derefine_count = 10;
+  double refine_threshold = 0.0;
 };
 
 // time_integration/low_storage_integrator.cpp:53-132
@@ -96,6 +100,13 @@ struct TaskList {  // minimal stand-in for parthenon::TaskList (tasks/tasks.hpp)
   }
   TaskStatus Execute();  // re-polls `incomplete` tasks like Parthenon's task loop
 };
+
+// Mesh::UpdateMeshBlockTree (mesh-amr_loadbalance.cpp:485-604) on plain leaf lists
+// {level, lx1, lx2, lx3}: returns 1 when the mesh changes, with the new leaves in the order of
+// Parthenon's block list and the numbers of blocks created / destroyed (hydro_amr.cpp)
+int UpdateMeshBlockTree(const SimConfig &cfg, const std::vector<std::array<int, 4>> &old_leaves,
+                        const std::vector<int> &flags, std::vector<std::array<int, 4>> *new_leaves,
+                        int *nnew, int *ndel);
 
 class HydroSim {
  public:
@@ -158,6 +169,18 @@ class HydroSim {
   TaskStatus ProlongateBounds();
   TaskStatus FluxCorrection();
   bool Multilevel() const { return multilevel_; }
+  // adaptive refinement (one rank): Refinement::Tag + MeshRefinement::SetRefinement on every block
+  // (hydro_driver.cpp:662-670), and Mesh::LoadBalancingAndAdaptiveMeshRefinement followed by
+  // EvolutionDriver::InitializeBlockTimeSteps when the mesh changed (driver.cpp:128-131);
+  // returns true when blocks were created or destroyed
+  TaskStatus TagRefinement();
+  bool LoadBalancingAndAdaptiveMeshRefinement();
+  int nbnew = 0, nbdel = 0;  // Mesh::nbnew, nbdel
+  // host wall time spent so far in: 0 tagging, 1 tree update, 2 rebuilding mesh tables / device
+  // arrays / exchange plan, 3 data move (copy, prolongate, restrict), 4 ghost cells + FillDerived
+  double amr_ms[5] = {0, 0, 0, 0, 0};
+  long long amr_remeshes = 0;
+  int RefineFlag(int b) const { return refine_flag_[b]; }
   TaskStatus FillDerived();
   // diffusion (src/hydro/diffusion/*, hydro_driver.cpp:36-344)
   TaskStatus CalcDiffFluxes();
@@ -204,6 +227,18 @@ class HydroSim {
 
  private:
   void BuildMesh();
+  void ReleaseMeshArrays();  // everything UploadBlocks allocates per mesh, except the cons slab
+  // device slabs are recycled across remeshes (cudaMalloc / cudaFree only when the mesh outgrows them)
+  std::vector<std::pair<void *, size_t>> slab_pool_;
+  std::map<void *, size_t> slab_size_;
+  void *SlabAlloc(size_t bytes, const char *what);
+  void SlabFree(void *p);
+  std::vector<int> refine_flag_, deref_count_;  // MeshRefinement::refine_flag_, deref_count_
+  int *d_tags_ = nullptr;
+  double *d_maxeps_ = nullptr;
+  size_t tags_cap_ = 0;
+  std::string pgen_id_;
+  std::vector<double> pgen_pars_;
   void BuildNeighbors();
   void BuildHaloPlan();
   void UploadBlocks();

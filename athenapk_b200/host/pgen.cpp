@@ -242,6 +242,10 @@ int HydroSim::ProblemGenerator(const std::string &id, const std::vector<double> 
                      id == "uniform" || id == "ot3d" || id == "random" || id == "blast";
   if (!known) return -1;
   if (id == "orszag_tang" && !mhd) return -2;
+  if (&pars != &pgen_pars_) {  // adaptive meshes re-run the generator while Mesh::Initialize refines
+    pgen_id_ = id;
+    pgen_pars_ = pars;
+  }
   std::vector<double> host(BlockFieldElems());
   for (size_t b = 0; b < blocks_.size(); ++b) {
     const BlockInfo &B = blocks_[b];

@@ -40,6 +40,7 @@ void apk_sim_default_config(apk_sim_config_t *c) {
   c->rank = 0; c->nranks = 1;
   c->cfl_diff = d.cfl_diff; c->rkl2_max_dt_ratio = d.rkl2_max_dt_ratio;
   c->conduction_sat_phi = d.conduction_sat_phi;
+  c->numlevel = d.numlevel; c->derefine_count = d.derefine_count;
 }
 
 apk_sim_t *apk_sim_create(const apk_sim_config_t *c) {
@@ -64,6 +65,8 @@ apk_sim_t *apk_sim_create(const apk_sim_config_t *c) {
     k.mom_diff_coeff = c->mom_diff_coeff; k.ohm_diff_coeff = c->ohm_diff_coeff;
     k.cfl_diff = c->cfl_diff; k.rkl2_max_dt_ratio = c->rkl2_max_dt_ratio;
     k.conduction_sat_phi = c->conduction_sat_phi;
+    k.adaptive = c->adaptive; k.numlevel = c->numlevel; k.derefine_count = c->derefine_count;
+    k.refine_threshold = c->refine_threshold;
     s = new HydroSim(k);
     return 0;
   });
@@ -84,6 +87,53 @@ int apk_sim_ml_item(const apk_sim_t *s, int i, int *out10) {
   const int o[10] = {m.list, m.exec, m.src, m.dst, m.lo[0], m.lo[1], m.lo[2], m.ext[0], m.ext[1], m.ext[2]};
   for (int k = 0; k < 10; ++k) out10[k] = o[k];
   return 0;
+}
+int apk_sim_amr_counts(const apk_sim_t *s, int *nbnew, int *nbdel, int *per_level8) {
+  const HydroSim *h = reinterpret_cast<const HydroSim *>(s);
+  if (nbnew) *nbnew = h->nbnew;
+  if (nbdel) *nbdel = h->nbdel;
+  if (per_level8) {
+    for (int l = 0; l < 8; ++l) per_level8[l] = 0;
+    for (int b = 0; b < h->NumLocalBlocks(); ++b)
+      if (h->Block(b).level < 8) per_level8[h->Block(b).level]++;
+  }
+  return 0;
+}
+int apk_sim_amr_update_tree(const apk_sim_config_t *c, int nold, const int *leaves4,
+                            const int *flags, int cap, int *out4, int *nnew, int *ndel) {
+  int n = -1;
+  int rc = guarded([&] {
+    SimConfig k;
+    for (int i = 0; i < 3; ++i) { k.nx[i] = c->nx[i]; k.mb[i] = c->mb[i]; }
+    for (int i = 0; i < 6; ++i) k.bc[i] = c->bc[i];
+    k.numlevel = c->numlevel;
+    std::vector<std::array<int, 4>> in(nold), out;
+    for (int b = 0; b < nold; ++b) in[b] = {leaves4[4 * b], leaves4[4 * b + 1], leaves4[4 * b + 2], leaves4[4 * b + 3]};
+    const int changed = apk_host::UpdateMeshBlockTree(k, in, std::vector<int>(flags, flags + nold), &out, nnew, ndel);
+    if (!changed) { n = 0; return 0; }
+    if ((int)out.size() > cap) return -1;
+    for (size_t b = 0; b < out.size(); ++b)
+      for (int q = 0; q < 4; ++q) out4[4 * b + q] = out[b][q];
+    n = (int)out.size();
+    return 0;
+  });
+  return rc ? rc : n;
+}
+long long apk_sim_amr_timing(const apk_sim_t *s, double *ms5) {
+  const HydroSim *h = reinterpret_cast<const HydroSim *>(s);
+  for (int q = 0; q < 5; ++q) ms5[q] = h->amr_ms[q];
+  return h->amr_remeshes;
+}
+int apk_sim_amr_tag(apk_sim_t *s) {
+  return guarded([&] { SIM(s)->TagRefinement(); return 0; });
+}
+int apk_sim_amr_remesh(apk_sim_t *s) {
+  int changed = 0;
+  int rc = guarded([&] { changed = SIM(s)->LoadBalancingAndAdaptiveMeshRefinement() ? 1 : 0; return 0; });
+  return rc ? rc : changed;
+}
+int apk_sim_amr_flag(const apk_sim_t *s, int b) {
+  return reinterpret_cast<const HydroSim *>(s)->RefineFlag(b);
 }
 int apk_sim_last_s_rkl(const apk_sim_t *s) { return reinterpret_cast<const HydroSim *>(s)->last_s_rkl; }
 
@@ -111,6 +161,7 @@ int apk_sim_step(apk_sim_t *s) {
     if (h->Step() != apk_host::TaskStatus::complete) return -1;
     h->tm.ncycle++;
     h->tm.time += h->tm.dt;
+    if (h->Config().adaptive && h->LoadBalancingAndAdaptiveMeshRefinement()) h->EstimateTimestep(false);
     h->SetGlobalTimeStep();
     return 0;
   });

@@ -42,6 +42,11 @@ typedef struct apk_sim_config {
   double cfl_diff;           /* diffusion/cfl; <= 0: parthenon/time/cfl */
   double rkl2_max_dt_ratio;  /* <= 0: no cap */
   double conduction_sat_phi; /* default 0.3 */
+  /* adaptive mesh refinement (one rank): parthenon/mesh/refinement = adaptive with numlevel levels
+   * in total and derefine_count (default 10, mesh_refinement.cpp:56); <refinement> type =
+   * pressure_gradient with threshold_pressure_gradient (src/refinement/gradient.cpp:18-61) */
+  int adaptive, numlevel, derefine_count;
+  double refine_threshold;
 } apk_sim_config_t;
 
 const char *apk_sim_last_error(void);
@@ -60,6 +65,24 @@ int apk_sim_nvar(const apk_sim_t *s);
 void apk_sim_block_dims(const apk_sim_t *s, int *n3);
 void apk_sim_block_info(const apk_sim_t *s, int b, int *gid, int *loc3, double *xmin3, double *dx3);
 int apk_sim_block_level(const apk_sim_t *s, int b);
+/* adaptive meshes (block counts and block order change whenever the mesh does): meshblocks created
+ * / destroyed so far (Mesh::nbnew, nbdel; the refinement during initialisation counts) and blocks
+ * per level; the two halves of the per-cycle AMR step for unit tests -- Refinement::Tag on every
+ * block (amr_criteria/refinement_package.cpp:205-233 + mesh_refinement.cpp:72-110) and
+ * Mesh::LoadBalancingAndAdaptiveMeshRefinement (mesh-amr_loadbalance.cpp:312-340; returns 1 when
+ * the mesh changed: ghost cells and prim are rebuilt, the caller re-estimates dt) */
+int apk_sim_amr_counts(const apk_sim_t *s, int *nbnew, int *nbdel, int *per_level8);
+int apk_sim_amr_tag(apk_sim_t *s);
+int apk_sim_amr_remesh(apk_sim_t *s);
+int apk_sim_amr_flag(const apk_sim_t *s, int b);
+/* host wall time (ms, summed) of the AMR step: 0 tagging, 1 tree update, 2 rebuilding mesh tables /
+ * device arrays / exchange plan, 3 data move, 4 ghost cells + FillDerived; returns #remeshes */
+long long apk_sim_amr_timing(const apk_sim_t *s, double *ms5);
+/* the tree update alone (no device state; CPU tests): leaves4 = nold x {level, lx1, lx2, lx3},
+ * flags = refine_flag_ per leaf (-1 / 0 / 1); returns 0 when nothing changes, else the number of
+ * new leaves written to out4 (capacity cap leaves) in the order of Parthenon's block list, or < 0 */
+int apk_sim_amr_update_tree(const apk_sim_config_t *c, int nold, const int *leaves4,
+                            const int *flags, int cap, int *out4, int *nnew, int *ndel);
 int apk_sim_copy_to_host(apk_sim_t *s, int field, int block, double *dst);
 int apk_sim_copy_from_host(apk_sim_t *s, int field, int block, const double *src);
 /* whole-pack async copies on the sim stream (host buffer: [nblocks][nvar][n3][n2][n1]) */

@@ -950,6 +950,8 @@ struct apko_engine {
   int pgen_id, pgen_npars;
   double pgen_pars[16];
   int nbnew, nbdel;
+  int *amr_last; /* input of the last apko_amr_remesh: {level, lx1, lx2, lx3, refine_flag} per block */
+  int amr_last_n;
   /* linear wave pgen state (linear_wave.cpp:43-51) */
   struct {
     int set, wave_flag;
@@ -1003,7 +1005,7 @@ static int max_pow2_divisor(int in) { return in & (~(in - 1)); }
 /* Block physical bounds: forest.cpp:66-141 (trees) + tree.cpp:296-318 (block in tree) */
 static void block_bounds_level(const apko_engine *e, int d, int level, int ib, double *bmin,
                                double *bmax);
-static void block_bounds(const apko_engine *e, int d, int ib, double *bmin, double *bmax) {
+__attribute__((unused)) static void block_bounds(const apko_engine *e, int d, int ib, double *bmin, double *bmax) {
   block_bounds_level(e, d, 0, ib, bmin, bmax);
 }
 /* a block at refinement `level` with location ib (in units of blocks of that level): the tree it
@@ -1364,6 +1366,7 @@ void apko_block_loc(const apko_engine *e, int b, int *level, int *lx3) {
 void apko_destroy(apko_engine *e) {
   if (!e) return;
   for (int b = 0; b < e->nblocks; ++b) block_free(&e->blk[b]);
+  free(e->amr_last);
   free(e->blk);
   free(e);
 }
@@ -2425,6 +2428,10 @@ int apko_amr_tag(apko_engine *e) {
 }
 
 int apko_amr_flag(const apko_engine *e, int b) { return e->blk[b].refine_flag; }
+const int *apko_amr_last_input(const apko_engine *e, int *n) {
+  *n = e->amr_last_n;
+  return e->amr_last;
+}
 
 void apko_amr_counts(const apko_engine *e, int *nbnew, int *nbdel, int *per_level8) {
   if (nbnew) *nbnew = e->nbnew;
@@ -2500,7 +2507,7 @@ static int amr_refine(const apko_engine *e, leafset_t *S, int level, const int *
 /* Tree::Derefine with enforce_proper_nesting (tree.cpp:217-272): lx at `level` becomes a leaf */
 static int amr_derefine(const apko_engine *e, leafset_t *S, int level, const int *lx) {
   const int nchild = 1 << e->ndim;
-  int cq[8];
+  int cq[8] = {0};
   for (int c = 0; c < nchild; ++c) {
     int cl[3];
     for (int d = 0; d < 3; ++d) cl[d] = (d < e->ndim) ? 2 * lx[d] + ((c >> d) & 1) : 0;
@@ -2579,6 +2586,14 @@ int apko_amr_remesh(apko_engine *e) {
   const apko_params *p = &e->p;
   const int ng = p->ng, nv = e->nvar;
   const int nleaf = 1 << e->ndim;
+  free(e->amr_last);
+  e->amr_last_n = e->nblocks;
+  e->amr_last = (int *)malloc((size_t)e->nblocks * 5 * sizeof(int));
+  for (int b = 0; b < e->nblocks; ++b) {
+    e->amr_last[5 * b] = e->blk[b].level;
+    for (int d = 0; d < 3; ++d) e->amr_last[5 * b + 1 + d] = e->blk[b].loc[d];
+    e->amr_last[5 * b + 4] = e->blk[b].refine_flag;
+  }
   /* ---- UpdateMeshBlockTree (mesh-amr_loadbalance.cpp:485-604) */
   int tnref = 0, tnderef = 0;
   for (int b = 0; b < e->nblocks; ++b) {

@@ -91,6 +91,8 @@ void apko_amr_counts(const apko_engine *e, int *nbnew, int *nbdel, int *per_leve
 int apko_amr_tag(apko_engine *e);
 int apko_amr_remesh(apko_engine *e);
 int apko_amr_flag(const apko_engine *e, int b); /* refine_flag_ of block b */
+/* what the last apko_amr_remesh started from: n x {level, lx1, lx2, lx3, refine_flag} */
+const int *apko_amr_last_input(const apko_engine *e, int *n);
 /* refinement level and logical location (at that level) of block b */
 void apko_block_loc(const apko_engine *e, int b, int *level, int *lx3);
 void apko_block_dims(const apko_engine *e, int *n /*[3] incl ghosts: n1,n2,n3*/);

@@ -77,6 +77,8 @@ def lib():
     L.apko_amr_tag.argtypes = [C.c_void_p]
     L.apko_amr_remesh.argtypes = [C.c_void_p]
     L.apko_amr_flag.argtypes = [C.c_void_p, C.c_int]
+    L.apko_amr_last_input.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.apko_amr_last_input.restype = C.POINTER(C.c_int)
     L.apko_block_loc.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.apko_block_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     L.apko_nvar.argtypes = [C.c_void_p]
@@ -192,6 +194,13 @@ class Oracle:
         if getattr(self, "h", None):
             self.L.apko_destroy(self.h)
             self.h = None
+
+    def amr_last_input(self):
+        """(leaves [(level, lx1, lx2, lx3)], flags) the last remesh started from"""
+        n = C.c_int()
+        p = self.L.apko_amr_last_input(self.h, C.byref(n))
+        a = np.ctypeslib.as_array(p, shape=(n.value, 5)).copy() if n.value else np.zeros((0, 5), int)
+        return [tuple(int(v) for v in r[:4]) for r in a], [int(r[4]) for r in a]
 
     def block_loc(self, b):
         """(refinement level, (lx1, lx2, lx3)) of block b"""

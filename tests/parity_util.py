@@ -24,6 +24,11 @@ def make_pair(apk, pgen="random", pgen_pars=(), tlim=float("inf"), **kw):
 
 def oracle_block(s, o, b):
     loc = s.block_info(b)[1]
+    if o.p.adaptive:  # the mesh changes: index by (level, logical location), rebuilt per block count
+        if getattr(o, "_leaf_index_n", None) != (o.nblocks, o.ncycle):
+            o._leaf_index = {o.block_loc(q): q for q in range(o.nblocks)}
+            o._leaf_index_n = (o.nblocks, o.ncycle)
+        return o._leaf_index[(s.block_level(b), tuple(loc))]
     if o.p.nref > 0:  # refined mesh: match blocks by (level, logical location)
         if not hasattr(o, "_leaf_index"):
             o._leaf_index = {o.block_loc(q): q for q in range(o.nblocks)}

@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 
 import oracle_lib
+from parity_util import assert_bitexact, make_pair
+from trace_util import ADAPTIVE_DECKS, ADAPTIVE_TRACES, follow_adaptive_trace
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -148,4 +150,48 @@ def test_pressure_gradient_tags(apk):
         assert got_eps[b] == m, (b, got_eps[b], m)
         assert got_tags[b] == tag
     assert set(got_tags.tolist()) >= {1}  # the threshold is the median: some blocks refine
+    s.close()
+
+
+# ---- adaptive mesh refinement end to end (BASELINE config 5 as the reference runs it) -------------
+@pytest.mark.parametrize("name", sorted(ADAPTIVE_DECKS))
+def test_adaptive_refinement_reference_traces(apk, name):
+    """inputs/blast_3d_amr.in with refinement = adaptive on the GPU, strict mode: device-side
+    pressure-gradient tags, host tree update, prolongation of new fine blocks / restriction into new
+    coarse blocks on the device, rebuilt multilevel exchange.  Every cycle's (time, dt) equals the
+    unmodified reference's printout at all 17 digits, the meshblock counts per level equal the ones
+    it prints every cycle, the created / destroyed totals match, and the final state -- same
+    meshblocks in the same order -- equals the oracle's bit for bit."""
+    kw, pgen, pars, tlim = ADAPTIVE_DECKS[name]
+    s, o = make_pair(apk, pgen, pars, tlim=tlim, fp_mode="strict", **kw)
+    case = ADAPTIVE_TRACES[name]
+    assert not s.fused_active
+    follow_adaptive_trace(s, case, tlim, lambda s, t, c: s.execute(t, c), lambda s: s.amr_counts())
+    assert s.ncycle == case["ncycle"]
+    o.run(tlim, case["ncycle"])
+    assert (s.time, s.dt, s.nblocks) == (o.time, o.dt, o.nblocks)
+    leaves = [(s.block_level(b),) + tuple(s.block_info(b)[1]) for b in range(s.nblocks)]
+    assert leaves == [(o.block_loc(b)[0],) + o.block_loc(b)[1] for b in range(o.nblocks)]
+    assert_bitexact(s, o, name)
+    s.close()
+
+
+def test_adaptive_refinement_fast_mode_conserves(apk):
+    """the benchmarked FP mode on the adaptive config-5 deck: restriction, prolongation and the flux
+    correction are conservative, so total mass / momentum / energy stay put (1e-13 relative) while
+    the mesh goes from 435 to ~580 meshblocks; the block count follows the reference's within 5 %."""
+    kw, pgen, pars, tlim = ADAPTIVE_DECKS["adaptive_3d_wenoz_hlld"]
+    s = apk.HydroSim(fp_mode="fast", **kw)
+    s.pgen(pgen, pars)
+    s.initialize(tlim)
+    case = ADAPTIVE_TRACES["adaptive_3d_wenoz_hlld"]
+    assert s.nblocks == case["blocks"][0][0]
+    h0 = s.history()
+    s.execute(tlim, case["ncycle"])
+    h1 = s.history()
+    assert abs(h1[0] - h0[0]) <= 1e-13 * abs(h0[0])          # mass
+    assert abs(h1[5] - h0[5]) <= 1e-13 * abs(h0[5])          # total energy
+    assert np.max(np.abs(h1[1:4] - h0[1:4])) <= 1e-13 * abs(h0[0])
+    assert abs(s.nblocks - case["final"][0]) <= 0.05 * case["final"][0]
+    assert abs(s.dt - float(case["trace"][-1][1])) <= 1e-6 * s.dt
     s.close()
