@@ -326,9 +326,10 @@ class HydroSim:
 
     def amr_timing(self):
         """(#remeshes, {phase: host ms summed}) of the AMR step"""
-        ms = (C.c_double * 5)()
+        ms = (C.c_double * 8)()
         n = self.L.apk_sim_amr_timing(self.h, ms)
-        return n, dict(zip(("tag", "tree", "rebuild", "move", "fill"), list(ms)))
+        return n, dict(zip(("tag", "tree", "rebuild", "move", "fill", "rebuild_mesh",
+                            "rebuild_neighbors", "rebuild_device"), list(ms)))
 
     def amr_tag(self):
         self._chk(self.L.apk_sim_amr_tag(self.h), "amr_tag")

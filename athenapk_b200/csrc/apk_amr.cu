@@ -324,7 +324,10 @@ int launch_history(const apk_pack_desc_t &d, const apk_block_t *blocks, double *
 int launch_restrict_average(int ndim, int ng, int nvar, int el, const apk_amr_item_t *items,
                             int nitems, cudaStream_t s) {
   if (nitems <= 0) return 0;
-  dim3 grid(64, nitems);
+  // items of the multilevel exchange are small (a face region of an 8^3 block: 4 x 4 x 2 coarse
+  // cells x nvar): two CTAs per item loop over it.  (64 CTAs per item made the exchange of a
+  // 600-block mesh launch ~600 k nearly empty CTAs: 1.2 ms per exchange, measured.)
+  dim3 grid(2, nitems);
   k_restrict_average<<<grid, kThreads, 0, s>>>(ndim, ng, nvar, el, items);
   apk_common::count_launch();
   return 0;
@@ -333,7 +336,7 @@ int launch_restrict_average(int ndim, int ng, int nvar, int el, const apk_amr_it
 int launch_prolongate_minmod(int ndim, int ng, int nvar, const apk_amr_item_t *items, int nitems,
                              cudaStream_t s) {
   if (nitems <= 0) return 0;
-  dim3 grid(64, nitems);
+  dim3 grid(2, nitems);
   k_prolongate_minmod<<<grid, kThreads, 0, s>>>(ndim, ng, nvar, items);
   apk_common::count_launch();
   return 0;

@@ -281,11 +281,14 @@ int UpdateMeshBlockTree(const SimConfig &cfg, const std::vector<std::array<int, 
   *nnew_out = nnew;
   *ndel_out = ndel;
   if (nnew == 0 && ndel == 0) return 0;
-  std::vector<Loc> newloc(F.leaves.begin(), F.leaves.end());
-  std::sort(newloc.begin(), newloc.end(),
-            [&](const Loc &a, const Loc &b) { return order_key(a) < order_key(b); });
+  std::vector<std::pair<std::tuple<std::uint64_t, std::uint64_t, int>, Loc>> keyed;
+  keyed.reserve(F.leaves.size());
+  for (const Loc &l : F.leaves) keyed.push_back({order_key(l), l});
+  std::sort(keyed.begin(), keyed.end(),
+            [](const auto &a, const auto &b) { return a.first < b.first; });
   new_leaves->clear();
-  for (const Loc &l : newloc) new_leaves->push_back({l.level, l.lx[0], l.lx[1], l.lx[2]});
+  for (const auto &kl : keyed)
+    new_leaves->push_back({kl.second.level, kl.second.lx[0], kl.second.lx[1], kl.second.lx[2]});
   return 1;
 }
 
@@ -321,11 +324,17 @@ bool HydroSim::LoadBalancingAndAdaptiveMeshRefinement() {
   d_cons_ = nullptr;
   Synchronize();
   ReleaseMeshArrays();
+  ArenaBegin((double)new_leaves.size() / (double)nold);
   leaves_.clear();
   for (const auto &l : new_leaves) leaves_.push_back(Leaf{l[0], {l[1], l[2], l[3]}});
   BuildMesh();
+  double t1 = NowMs();
+  amr_ms[5] += t1 - t0;
   BuildNeighbors();
+  amr_ms[6] += NowMs() - t1;
+  t1 = NowMs();
   UploadBlocks();  // new (zeroed) slabs, block tables, the multilevel exchange plan
+  amr_ms[7] += NowMs() - t1;
   amr_ms[2] += NowMs() - t0;
   t0 = NowMs();
 

@@ -13,6 +13,7 @@
 #include <map>
 #include <stdexcept>
 #include <tuple>
+#include <unordered_map>
 
 namespace apk_host {
 
@@ -185,7 +186,10 @@ HydroSim::~HydroSim() {
   d_tma_[0] = d_tma_[1] = nullptr;
   ReleaseMeshArrays();
   SlabFree(d_cons_);
-  for (auto &kv : slab_pool_) cudaFree(kv.first);
+  for (Arena &A : arena_) {
+    for (void *p : A.extra) cudaFree(p);
+    cudaFree(A.base);
+  }
   cudaFree(d_tags_);
   cudaFree(d_maxeps_);
   cudaFree(d_scalars_);
@@ -412,7 +416,20 @@ std::vector<HydroSim::Leaf> HydroSim::BuildLeaves() const {
 void HydroSim::BuildMultilevelNeighbors() {
   // every rank builds the topology of ALL leaves (ids = global block ids): items of the exchange
   // plan exist wherever either side of a relation is local
-  std::map<LeafKey, int> index;
+  // (hashed: an adaptive run rebuilds these tables after every remesh)
+  struct PackedIndex {
+    std::unordered_map<std::uint64_t, int> m;
+    static std::uint64_t key(const LeafKey &k) {
+      return ((std::uint64_t)k.level << 60) | ((std::uint64_t)k.x << 40) | ((std::uint64_t)k.y << 20) |
+             (std::uint64_t)k.z;
+    }
+    int &operator[](const LeafKey &k) { return m[key(k)]; }
+    std::unordered_map<std::uint64_t, int>::const_iterator find(const LeafKey &k) const {
+      return m.find(key(k));
+    }
+    std::unordered_map<std::uint64_t, int>::const_iterator end() const { return m.end(); }
+  } index;
+  index.m.reserve(leaves_.size() * 2);
   for (size_t g = 0; g < leaves_.size(); ++g)
     index[{leaves_[g].level, leaves_[g].lx[0], leaves_[g].lx[1], leaves_[g].lx[2]}] = (int)g;
   gnbr_.assign(leaves_.size(), NbrInfo{});
@@ -541,44 +558,44 @@ void HydroSim::BuildNeighbors() {
   }
 }
 
-// Device slabs come from a small recycling pool: an adaptive run remeshes almost every cycle, and
-// cudaMalloc / cudaFree (a device-wide synchronisation each) would dominate it.
+// Per-mesh device arrays (see Arena in hydro_sim.hpp).
+void HydroSim::ArenaBegin(double growth) {
+  const size_t last = arena_[arena_cur_].want;
+  arena_cur_ ^= 1;
+  Arena &A = arena_[arena_cur_];
+  for (void *p : A.extra) cudaFree(p);
+  A.extra.clear();
+  const size_t need = (size_t)((double)std::max(last, A.want) * std::max(growth, 1.0) * 1.05) + (8u << 20);
+  if (A.cap < need) {
+    cudaFree(A.base);
+    A.base = nullptr;
+    A.cap = need + need / 2;
+    cuda_check(cudaMalloc(reinterpret_cast<void **>(&A.base), A.cap), "cudaMalloc mesh arena");
+  }
+  A.used = A.want = 0;
+}
+
 void *HydroSim::SlabAlloc(size_t bytes, const char *what) {
-  int best = -1;
-  for (size_t q = 0; q < slab_pool_.size(); ++q)
-    if (slab_pool_[q].second >= bytes && slab_pool_[q].second <= 2 * bytes + (1u << 20) &&
-        (best < 0 || slab_pool_[q].second < slab_pool_[best].second))
-      best = (int)q;
   void *p = nullptr;
-  if (best >= 0) {
-    p = slab_pool_[best].first;
-    slab_pool_.erase(slab_pool_.begin() + best);
+  if (!cfg_.adaptive) {
+    cuda_check(cudaMalloc(&p, bytes), what);
     return p;
   }
-  // grow with some head room so that the next few remeshes fit
-  const size_t cap = cfg_.adaptive ? bytes + bytes / 4 : bytes;
-  cuda_check(cudaMalloc(&p, cap), what);
-  slab_size_[p] = cap;
+  Arena &A = arena_[arena_cur_];
+  const size_t off = (A.used + 255) & ~(size_t)255;
+  A.want += bytes + 256;
+  if (off + bytes <= A.cap) {
+    A.used = off + bytes;
+    return A.base + off;
+  }
+  cuda_check(cudaMalloc(&p, bytes), what);
+  A.extra.push_back(p);
   return p;
 }
 
 void HydroSim::SlabFree(void *p) {
-  if (!p) return;
-  auto it = slab_size_.find(p);
-  if (it == slab_size_.end()) {
-    cudaFree(p);
-    return;
-  }
-  slab_pool_.push_back({p, it->second});
-  // keep the pool bounded: drop the smallest slabs beyond 48 entries
-  while (slab_pool_.size() > 48) {
-    size_t m = 0;
-    for (size_t q = 1; q < slab_pool_.size(); ++q)
-      if (slab_pool_[q].second < slab_pool_[m].second) m = q;
-    slab_size_.erase(slab_pool_[m].first);
-    cudaFree(slab_pool_[m].first);
-    slab_pool_.erase(slab_pool_.begin() + m);
-  }
+  if (!p || cfg_.adaptive) return;  // (arena memory is reclaimed when its arena has its next turn)
+  cudaFree(p);
 }
 
 // everything UploadBlocks allocates for one mesh, except the cons slab (a remesh still reads it)
@@ -617,17 +634,21 @@ void HydroSim::UploadBlocks() {
   const size_t per = BlockFieldElems();
   const size_t nbl = blocks_.size();
   const size_t bytes = per * nbl * sizeof(double);
-  auto slab = [&](const char *what) {
+  // (a remesh re-enters with recycled slabs: prim, u1, the fluxes and the coarse buffers are
+  // rewritten in full before they are read -- FillDerived over the entire index range, InitU1,
+  // CalculateFluxes, the exchange -- so only cons is cleared again)
+  const bool first = (d_scalars_ == nullptr);
+  auto slab = [&](const char *what, bool clear = true) {
     double *p = static_cast<double *>(SlabAlloc(bytes, what));
-    cuda_check(cudaMemsetAsync(p, 0, bytes, S(stream_)), "memset");
+    if (clear || first) cuda_check(cudaMemsetAsync(p, 0, bytes, S(stream_)), "memset");
     return p;
   };
   d_cons_ = slab("cudaMalloc cons");
-  d_prim_[0] = slab("cudaMalloc prim");
-  d_u1_ = slab("cudaMalloc u1");
-  if (fused_) d_prim_[1] = slab("cudaMalloc prim scratch");
+  d_prim_[0] = slab("cudaMalloc prim", false);
+  d_u1_ = slab("cudaMalloc u1", false);
+  if (fused_) d_prim_[1] = slab("cudaMalloc prim scratch", false);
   if (!fused_ || cfg_.fofc) {
-    for (int d = 0; d < ndim_; ++d) d_flux_[d] = slab("cudaMalloc flux");
+    for (int d = 0; d < ndim_; ++d) d_flux_[d] = slab("cudaMalloc flux", false);
   }
   if (cfg_.diffint == 2) {  // RKL2 registers (hydro_driver.cpp:211-212)
     d_my0_ = slab("cudaMalloc MY0");
@@ -671,7 +692,7 @@ void HydroSim::UploadBlocks() {
   if (multilevel_) {
     const size_t cbytes = CoarseElems() * nbl * sizeof(double);
     d_coarse_ = static_cast<double *>(SlabAlloc(cbytes, "cudaMalloc coarse"));
-    cuda_check(cudaMemsetAsync(d_coarse_, 0, cbytes, S(stream_)), "memset");
+    if (first) cuda_check(cudaMemsetAsync(d_coarse_, 0, cbytes, S(stream_)), "memset");
     if (cfg_.nranks == 1) BuildMultilevelPlan();  // several ranks: after the peer mapping (InitComm)
   }
   // the slabs are zeroed on the simulation stream; everything that follows (blocking copies of the

@@ -178,7 +178,8 @@ class HydroSim {
   int nbnew = 0, nbdel = 0;  // Mesh::nbnew, nbdel
   // host wall time spent so far in: 0 tagging, 1 tree update, 2 rebuilding mesh tables / device
   // arrays / exchange plan, 3 data move (copy, prolongate, restrict), 4 ghost cells + FillDerived
-  double amr_ms[5] = {0, 0, 0, 0, 0};
+  // (5..7 split 2 into: release + mesh, neighbour tables, device arrays + exchange plan)
+  double amr_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long amr_remeshes = 0;
   int RefineFlag(int b) const { return refine_flag_[b]; }
   TaskStatus FillDerived();
@@ -228,9 +229,18 @@ class HydroSim {
  private:
   void BuildMesh();
   void ReleaseMeshArrays();  // everything UploadBlocks allocates per mesh, except the cons slab
-  // device slabs are recycled across remeshes (cudaMalloc / cudaFree only when the mesh outgrows them)
-  std::vector<std::pair<void *, size_t>> slab_pool_;
-  std::map<void *, size_t> slab_size_;
+  // Per-mesh device arrays.  Static meshes: one cudaMalloc each.  Adaptive meshes: bump allocation
+  // from two grow-only arenas used alternately (the old cons slab must outlive the construction of
+  // the new mesh), so a remesh costs no cudaMalloc / cudaFree once the arenas have reached their
+  // size; requests that do not fit fall back to cudaMalloc until the arena is regrown at its next turn
+  struct Arena {
+    char *base = nullptr;
+    size_t cap = 0, used = 0, want = 0;
+    std::vector<void *> extra;
+  };
+  Arena arena_[2];
+  int arena_cur_ = 0;
+  void ArenaBegin(double growth);  // switch arenas before the arrays of a new mesh are allocated
   void *SlabAlloc(size_t bytes, const char *what);
   void SlabFree(void *p);
   std::vector<int> refine_flag_, deref_count_;  // MeshRefinement::refine_flag_, deref_count_

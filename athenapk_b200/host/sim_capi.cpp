@@ -119,9 +119,9 @@ int apk_sim_amr_update_tree(const apk_sim_config_t *c, int nold, const int *leav
   });
   return rc ? rc : n;
 }
-long long apk_sim_amr_timing(const apk_sim_t *s, double *ms5) {
+long long apk_sim_amr_timing(const apk_sim_t *s, double *ms8) {
   const HydroSim *h = reinterpret_cast<const HydroSim *>(s);
-  for (int q = 0; q < 5; ++q) ms5[q] = h->amr_ms[q];
+  for (int q = 0; q < 8; ++q) ms8[q] = h->amr_ms[q];
   return h->amr_remeshes;
 }
 int apk_sim_amr_tag(apk_sim_t *s) {

@@ -76,8 +76,9 @@ int apk_sim_amr_tag(apk_sim_t *s);
 int apk_sim_amr_remesh(apk_sim_t *s);
 int apk_sim_amr_flag(const apk_sim_t *s, int b);
 /* host wall time (ms, summed) of the AMR step: 0 tagging, 1 tree update, 2 rebuilding mesh tables /
- * device arrays / exchange plan, 3 data move, 4 ghost cells + FillDerived; returns #remeshes */
-long long apk_sim_amr_timing(const apk_sim_t *s, double *ms5);
+ * device arrays / exchange plan, 3 data move, 4 ghost cells + FillDerived, 5..7 = 2 split into
+ * release + mesh, neighbour tables, device arrays + plan; returns #remeshes */
+long long apk_sim_amr_timing(const apk_sim_t *s, double *ms8);
 /* the tree update alone (no device state; CPU tests): leaves4 = nold x {level, lx1, lx2, lx3},
  * flags = refine_flag_ per leaf (-1 / 0 / 1); returns 0 when nothing changes, else the number of
  * new leaves written to out4 (capacity cap leaves) in the order of Parthenon's block list, or < 0 */

@@ -42,5 +42,17 @@ for name, ncyc in (("adaptive_3d_wenoz_hlld", 40), ("adaptive_3d_plm_hlle", 60))
                  "destroyed": destroyed, "per_level": per_level[:4], "init_s": t_init,
                  "remeshes": n_amr - n_pre,
                  "amr_ms_per_cycle": {k: (ms_amr[k] - ms_pre[k]) / ncyc for k in ms_amr}}
+    # device time per task (CUDA events around every task; perturbs the wall clock, hence after it)
+    s.enable_task_timing(True)
+    c0 = s.ncycle
+    s.execute(tlim, c0 + 10)
+    s.synchronize()
+    tasks = {}
+    for t in ("init_u1", "calc_flux", "flux_correction", "update", "source_unsplit", "send", "set",
+              "prolongate_bounds", "fill_derived", "new_dt", "tag_refine"):
+        ms, cnt = s.task_timing(t)
+        if cnt:
+            tasks[t] = ms / 10.0
+    res[name]["task_ms_per_cycle"] = tasks
     s.close()
 print(json.dumps(res, indent=1))
