@@ -88,6 +88,7 @@ struct ReconTask {
   int sl, sr;  // shared-memory element index of the L / R destination of lane 0, or -1
 };
 
+// NH = number of variables the arrays hold: the hydro / GLM-MHD variables plus the passive scalars
 template <int NH, int NDIM, bool DC>
 struct Smem {
   static constexpr int NZ = (NDIM == 3) ? NH * TY : 0, NX = NH * TY,
@@ -119,14 +120,22 @@ struct Smem {
   double *push_prim[27], *push_cons[27];  // ghost-push destinations per neighbour offset (or null)
 };
 
-template <int FLUID, int RECON, int RS, int NDIM>
+// NS passive scalars ride along (hydro.cpp:1089-1097): reconstructed like every other primitive,
+// flux = mass flux x upwind state, s = (rho s) / rho in cons -> prim.  NS = 0 is the headline kernel;
+// NS > 0 instantiations live in their own translation units (APK_FUSED_NS).
+template <int FLUID, int RECON, int RS, int NDIM, int NS = 0>
 __global__ void __launch_bounds__(NTHREADS, APK_FUSED_MINBLOCKS)
 k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *__restrict__ prim_out,
               double g0, double g1, double bdt, RsPars rsp, double dedner_coeff,
               EosPars eos, int ntx, int flags, unsigned long long *dtmin,
               const apk_push_dst_t *__restrict__ push, int nchunk, int *status,
               unsigned long long *fofc_count, const unsigned char *__restrict__ tmaps) {
-  constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
+  constexpr int NHY = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;  // hydro / GLM-MHD variables
+  constexpr int NH = NHY + NS;                               // all variables of the pack
+  // sweep-local slot <-> memory variable (scalars are not permuted; for Euler, slots 5..7 would
+  // otherwise be taken for magnetic field components)
+  auto var_of_slot = [](int n, int dir) { return n >= NHY ? n : APK_NS::var_of_slot(n, dir); };
+  auto slot_of_var = [](int v, int dir) { return v >= NHY ? v : APK_NS::slot_of_var(v, dir); };
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool DC = (RECON == APK_RECON_DC);
   using SmemT = Smem<NH, NDIM, DC>;
@@ -736,7 +745,19 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
           dst = &sm.wlz[cur].a[0][j][lane];
           dstride = TY * TX;
         }
-        riemann_solve<FLUID, RS>(L, R, rsp, F);
+        if constexpr (NS == 0) {
+          riemann_solve<FLUID, RS>(L, R, rsp, F);
+        } else {
+          double Lh[NHY], Rh[NHY], Fh[NHY];
+#pragma unroll
+          for (int n = 0; n < NHY; ++n) { Lh[n] = L[n]; Rh[n] = R[n]; }
+          riemann_solve<FLUID, RS>(Lh, Rh, rsp, Fh);
+#pragma unroll
+          for (int n = 0; n < NHY; ++n) F[n] = Fh[n];
+          // passive scalars: upwinded by the sign of the mass flux (hydro.cpp:1089-1097)
+#pragma unroll
+          for (int n = NHY; n < NH; ++n) F[n] = (Fh[0] >= 0.0) ? Fh[0] * L[n] : Fh[0] * R[n];
+        }
 #pragma unroll
         for (int n = 0; n < NH; ++n) dst[n * dstride] = F[n];
       }
@@ -800,11 +821,25 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
         bool fofc_bad = false;
         if (flags & APK_FUSED_FOFC_CHECK) {
           // first attempt of FirstOrderFluxCorrect on this very trial update (hydro.cpp:1287-1306)
-          fofc_bad = fofc_needs_correction<NH>(u);
+          if constexpr (NS == 0) fofc_bad = fofc_needs_correction<NH>(u);  // (host: no FOFC with scalars)
           if (fofc_bad) atomicAdd(fofc_count, 1ULL);
         }
         if constexpr (FLUID == APK_FLUID_GLMMHD) u[8] *= dedner_coeff;  // dedner_source.cpp:72
-        const int err = cons_to_prim<NH>(u, w, eos);
+        int err;
+        if constexpr (NS == 0) {
+          err = cons_to_prim<NH>(u, w, eos);
+        } else {
+          double uh[NHY], wh[NHY];
+#pragma unroll
+          for (int v = 0; v < NHY; ++v) uh[v] = u[v];
+          err = cons_to_prim<NHY>(uh, wh, eos);
+#pragma unroll
+          for (int v = 0; v < NHY; ++v) { u[v] = uh[v]; w[v] = wh[v]; }
+          // scalars: s = (rho s) / rho with the floored density (adiabatic_hydro.hpp:137-141)
+          const double di = frcp(uh[0]);
+#pragma unroll
+          for (int v = NHY; v < NH; ++v) w[v] = u[v] * di;
+        }
         // PARTHENON_REQUIRE of ConsToPrim (a cell FOFC flagged is redone by the caller instead)
         if (err && status && !fofc_bad) atomicMax(status, err);
 #pragma unroll
@@ -891,14 +926,14 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   }
 }
 
-template <int FLUID, int RECON, int RS>
+template <int FLUID, int RECON, int RS, int NS = 0>
 int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
               double *const *prim_out, const apk_stage_args_t &a, double coeff, cudaStream_t s) {
   const double g0 = a.gam0, g1 = a.gam1, bdt = a.beta_dt, c_h = a.c_h;
   const int flags = a.flags;
   double *d_dtmin = a.d_dtmin;
   const apk_push_dst_t *push = a.d_push;
-  constexpr int NH = (FLUID == APK_FLUID_GLMMHD) ? 9 : 5;
+  constexpr int NH = ((FLUID == APK_FLUID_GLMMHD) ? 9 : 5) + NS;
   const EosPars eos = {d.gamma, d.dfloor, d.pfloor, d.efloor, d.vceil, d.eceil};
   // IEEE quotients evaluated once on the host (== frcp / fdiv on the device)
   const RsPars rsp = {d.gamma, 1.0 / (d.gamma - 1.0), c_h, 0.5 / c_h};
@@ -927,7 +962,7 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
   unsigned long long *dt = reinterpret_cast<unsigned long long *>(d_dtmin);
 #define APK_LAUNCH_FUSED(ND)                                                                     \
   {                                                                                              \
-    auto kern = k_stage_fused<FLUID, RECON, RS, ND>;                                             \
+    auto kern = k_stage_fused<FLUID, RECON, RS, ND, NS>;                                         \
     /* per-device attribute (a process may drive several GPUs): set once per device */          \
     static unsigned long long attr_set = 0;                                                      \
     const int dev = apk_common::current_device();                                                \
@@ -948,16 +983,16 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
   return 0;
 }
 
-template <int FLUID, int RS>
+template <int FLUID, int RS, int NS = 0>
 int fused_recon(int recon, const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
                 double *const *prim_out, const apk_stage_args_t &a, double coeff, cudaStream_t s) {
   switch (recon) {
-  case APK_RECON_DC: return run_fused<FLUID, APK_RECON_DC, RS>(d, g, blocks, prim_out, a, coeff, s);
-  case APK_RECON_PLM: return run_fused<FLUID, APK_RECON_PLM, RS>(d, g, blocks, prim_out, a, coeff, s);
-  case APK_RECON_PPM: return run_fused<FLUID, APK_RECON_PPM, RS>(d, g, blocks, prim_out, a, coeff, s);
-  case APK_RECON_WENOZ: return run_fused<FLUID, APK_RECON_WENOZ, RS>(d, g, blocks, prim_out, a, coeff, s);
-  case APK_RECON_WENO3: return run_fused<FLUID, APK_RECON_WENO3, RS>(d, g, blocks, prim_out, a, coeff, s);
-  case APK_RECON_LIMO3: return run_fused<FLUID, APK_RECON_LIMO3, RS>(d, g, blocks, prim_out, a, coeff, s);
+  case APK_RECON_DC: return run_fused<FLUID, APK_RECON_DC, RS, NS>(d, g, blocks, prim_out, a, coeff, s);
+  case APK_RECON_PLM: return run_fused<FLUID, APK_RECON_PLM, RS, NS>(d, g, blocks, prim_out, a, coeff, s);
+  case APK_RECON_PPM: return run_fused<FLUID, APK_RECON_PPM, RS, NS>(d, g, blocks, prim_out, a, coeff, s);
+  case APK_RECON_WENOZ: return run_fused<FLUID, APK_RECON_WENOZ, RS, NS>(d, g, blocks, prim_out, a, coeff, s);
+  case APK_RECON_WENO3: return run_fused<FLUID, APK_RECON_WENO3, RS, NS>(d, g, blocks, prim_out, a, coeff, s);
+  case APK_RECON_LIMO3: return run_fused<FLUID, APK_RECON_LIMO3, RS, NS>(d, g, blocks, prim_out, a, coeff, s);
   }
   apk_common::set_error("apk_stage_fused: unknown reconstruction");
   return 1;
@@ -974,7 +1009,40 @@ int launch_stage_rows_euler(const apk_pack_desc_t &d, const ApkGeom &g, const ap
 int launch_stage_rows_mhd(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
                           double *const *prim_out, const apk_stage_args_t &a, double coeff,
                           int recon, cudaStream_t s);
-#if APK_FUSED_TMA
+int launch_stage_fused_ns1(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
+                           double *const *prim_out, const apk_stage_args_t &a, double coeff,
+                           int recon, cudaStream_t s);
+int launch_stage_fused_ns2(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
+                           double *const *prim_out, const apk_stage_args_t &a, double coeff,
+                           int recon, cudaStream_t s);
+#if defined(APK_FUSED_NS) && APK_FUSED_NS > 0
+// translation unit of the kernels with APK_FUSED_NS passive scalars (both fluids)
+#define APK_CAT2(a, b) a##b
+#define APK_CAT(a, b) APK_CAT2(a, b)
+int APK_CAT(launch_stage_fused_ns, APK_FUSED_NS)(const apk_pack_desc_t &d, const ApkGeom &g,
+                                                 const apk_block_t *blocks, double *const *prim_out,
+                                                 const apk_stage_args_t &a, double coeff, int recon,
+                                                 cudaStream_t s) {
+  constexpr int NS = APK_FUSED_NS;
+  if (d.fluid == APK_FLUID_EULER) {
+    switch (d.riemann) {
+    case APK_RIEMANN_NONE: return run_fused<APK_FLUID_EULER, APK_RECON_DC, APK_RIEMANN_NONE, NS>(d, g, blocks, prim_out, a, coeff, s);
+    case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLE, NS>(recon, d, g, blocks, prim_out, a, coeff, s);
+    case APK_RIEMANN_HLLC: return fused_recon<APK_FLUID_EULER, APK_RIEMANN_HLLC, NS>(recon, d, g, blocks, prim_out, a, coeff, s);
+    case APK_RIEMANN_LLF: return run_fused<APK_FLUID_EULER, APK_RECON_DC, APK_RIEMANN_LLF, NS>(d, g, blocks, prim_out, a, coeff, s);
+    }
+  } else {
+    switch (d.riemann) {
+    case APK_RIEMANN_NONE: return run_fused<APK_FLUID_GLMMHD, APK_RECON_DC, APK_RIEMANN_NONE, NS>(d, g, blocks, prim_out, a, coeff, s);
+    case APK_RIEMANN_HLLE: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLE, NS>(recon, d, g, blocks, prim_out, a, coeff, s);
+    case APK_RIEMANN_HLLD: return fused_recon<APK_FLUID_GLMMHD, APK_RIEMANN_HLLD, NS>(recon, d, g, blocks, prim_out, a, coeff, s);
+    case APK_RIEMANN_LLF: return run_fused<APK_FLUID_GLMMHD, APK_RECON_DC, APK_RIEMANN_LLF, NS>(d, g, blocks, prim_out, a, coeff, s);
+    }
+  }
+  apk_common::set_error("apk_stage_fused: unsupported fluid/riemann combination");
+  return 1;
+}
+#elif APK_FUSED_TMA
 static_assert(TX == APK_TMA_TX && TY == APK_TMA_TY, "tensor-map box and kernel tile must agree");
 // the A/B variant is built for the headline method only: GLM-MHD, PPM + HLLD (3-D meshes)
 int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
@@ -995,7 +1063,14 @@ int launch_stage_fused(const apk_pack_desc_t &d, const apk_block_t *blocks,
   const ApkGeom g = apk_make_geom(d);
   const int recon = (a.recon_override < 0) ? d.recon : a.recon_override;
   if (d.nscalars != 0) {
-    apk_common::set_error("apk_stage_fused: passive scalars need the un-fused tasks");
+    // kernels with passive scalars are built for 1 and 2 scalars (own translation units)
+    if (a.flags & APK_FUSED_FOFC_CHECK) {
+      apk_common::set_error("apk_stage_fused: FOFC with passive scalars needs the un-fused tasks");
+      return 1;
+    }
+    if (d.nscalars == 1) return launch_stage_fused_ns1(d, g, blocks, prim_out, a, dedner_coeff, recon, s);
+    if (d.nscalars == 2) return launch_stage_fused_ns2(d, g, blocks, prim_out, a, dedner_coeff, recon, s);
+    apk_common::set_error("apk_stage_fused: more than 2 passive scalars need the un-fused tasks");
     return 1;
   }
   // APK_B200_FUSED_V=2 selects the row-task kernel (apk_rows.cu, 2-D / 3-D meshes) for A/B runs:

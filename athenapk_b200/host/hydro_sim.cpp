@@ -146,8 +146,10 @@ HydroSim::HydroSim(const SimConfig &cfg)
   // multilevel meshes need materialised fluxes (flux correction, hydro_driver.cpp:527-531)
   // diffusion (either integrator) runs on the flux-materialising tasks: unsplit adds to the
   // hyperbolic fluxes (hydro.cpp:1202-1205), RKL2 needs the flux arrays for its sub-steps
-  fused_ = cfg_.fused && !cfg_.dedner_extended && cfg_.nscalars == 0 && !multilevel_ &&
-           cfg_.diffint == 0;
+  // passive scalars: the fused kernels are built for 1 and 2 scalars (more run un-fused, as do
+  // scalars with FOFC, whose acceptance test the fused kernel evaluates on the hydro variables only)
+  const bool scalars_ok = cfg_.nscalars == 0 || (cfg_.nscalars <= 2 && !cfg_.fofc);
+  fused_ = cfg_.fused && !cfg_.dedner_extended && scalars_ok && !multilevel_ && cfg_.diffint == 0;
   if (cfg_.diffint != 0) {
     if (cfg_.fofc)
       throw std::runtime_error("apk_host: first_order_flux_correct with diffusion is not supported");
