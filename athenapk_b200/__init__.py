@@ -112,7 +112,8 @@ SIM_SYMBOLS = [
     "apk_sim_enable_task_timing", "apk_sim_task_timing", "apk_sim_num_peers", "apk_sim_peer",
     "apk_sim_num_halo_items", "apk_sim_halo_item", "apk_sim_neighbor", "apk_sim_push_target",
     "apk_sim_amr_counts", "apk_sim_amr_tag", "apk_sim_amr_remesh", "apk_sim_amr_flag",
-    "apk_sim_amr_update_tree", "apk_sim_amr_timing",
+    "apk_sim_amr_update_tree", "apk_sim_amr_timing", "apk_sim_enable_history",
+    "apk_sim_finalize_outputs",
 ]
 
 _lib = None
@@ -222,6 +223,8 @@ def lib():
     L.apk_sim_amr_tag.argtypes = [vp]
     L.apk_sim_amr_remesh.argtypes = [vp]
     L.apk_sim_amr_flag.argtypes = [vp, C.c_int]
+    L.apk_sim_enable_history.argtypes = [vp, C.c_char_p, C.c_double, C.c_char_p]
+    L.apk_sim_finalize_outputs.argtypes = [vp]
     L.apk_sim_amr_timing.argtypes = [vp, dp]
     L.apk_sim_amr_timing.restype = C.c_longlong
     L.apk_sim_amr_update_tree.argtypes = [C.POINTER(SimConfig), C.c_int, ip, ip, C.c_int, ip, ip, ip]
@@ -317,6 +320,14 @@ class HydroSim:
     # (adaptive meshes change both whenever the mesh does)
     nblocks = property(lambda s: s.L.apk_sim_num_local_blocks(s.h))
     nblocks_global = property(lambda s: s.L.apk_sim_num_global_blocks(s.h))
+
+    def enable_history(self, fname, dt, data_format="%12.5e"):
+        """append Parthenon-format .hst rows during execute(): <parthenon/outputN> file_type = hst"""
+        self._chk(self.L.apk_sim_enable_history(self.h, fname.encode(), dt, data_format.encode()),
+                  "enable_history")
+
+    def finalize_outputs(self):
+        self._chk(self.L.apk_sim_finalize_outputs(self.h), "finalize_outputs")
 
     def amr_counts(self):
         """(meshblocks created, destroyed, [blocks per level]) -- Mesh::nbnew / nbdel"""

@@ -981,6 +981,73 @@ void HydroSim::History(double *out8) {
   abi_check(apk_history_sums(&desc_, d_blocks_[cur_], d_hist_, out8, stream_), "apk_history_sums");
 }
 
+void HydroSim::EnableHistoryOutput(const std::string &fname, double dt, const std::string &data_format) {
+  hst_name_ = fname;
+  hst_dt_ = dt;
+  hst_fmt_ = " " + (data_format.empty() ? std::string("%12.5e") : data_format);  // outputs.cpp:267-268
+  hst_next_time_ = tm.time;
+  hst_file_number_ = 0;
+  hst_last_cycle_ = -1;
+}
+
+// history.cpp:172-209
+void HydroSim::WriteHistoryRow() {
+  double sums[8];
+  History(sums);
+  if (cfg_.nranks > 1) {  // MPI_Reduce(SUM) of history.cpp:146-168
+    cuda_check(cudaMemcpyAsync(d_scalars_ + 16, sums, 8 * sizeof(double), cudaMemcpyHostToDevice,
+                               S(stream_)), "history H2D");
+    if (ncclAllReduce(d_scalars_ + 16, d_scalars_ + 16, 8, ncclDouble, ncclSum,
+                      reinterpret_cast<ncclComm_t>(comm_), S(stream_)) != ncclSuccess)
+      throw std::runtime_error("apk_host: ncclAllReduce (history) failed");
+    cuda_check(cudaMemcpyAsync(sums, d_scalars_ + 16, 8 * sizeof(double), cudaMemcpyDeviceToHost,
+                               S(stream_)), "history D2H");
+    Synchronize();
+  }
+  hst_last_cycle_ = tm.ncycle;
+  if (cfg_.rank != 0) {
+    hst_file_number_++;
+    return;
+  }
+  FILE *f = std::fopen(hst_name_.c_str(), hst_file_number_ == 0 ? "w" : "a");
+  if (!f) throw std::runtime_error("Output file '" + hst_name_ + "' could not be opened");
+  static const char *labels[8] = {"mass", "1-mom", "2-mom", "3-mom", "KE", "tot-E", "ME", "relDivB"};
+  const int nq = (cfg_.fluid == APK_FLUID_GLMMHD) ? 8 : 6;
+  if (hst_file_number_ == 0) {
+    int iout = 1;
+    std::fprintf(f, "#  History data\n");
+    std::fprintf(f, "# [%d]=time    ", iout++);
+    std::fprintf(f, " [%d]=dt      ", iout++);
+    std::fprintf(f, " [%d]=cycle   ", iout++);
+    std::fprintf(f, " [%d]=nbtotal ", iout++);
+    for (int q = 0; q < nq; ++q) std::fprintf(f, " [%d]=%-8s", iout++, labels[q]);
+    std::fprintf(f, "\n");
+  }
+  std::fprintf(f, hst_fmt_.c_str(), tm.time);
+  std::fprintf(f, hst_fmt_.c_str(), tm.dt);
+  std::fprintf(f, " %12d", tm.ncycle);
+  std::fprintf(f, " %12d", nblocks_global_);
+  for (int q = 0; q < nq; ++q) std::fprintf(f, hst_fmt_.c_str(), sums[q]);
+  std::fprintf(f, "\n");
+  std::fclose(f);
+  hst_file_number_++;
+}
+
+// outputs.cpp:445-485 for one `hst` output block
+void HydroSim::MakeOutputs(bool final_signal) {
+  if (hst_name_.empty() || hst_dt_ < 0.0) return;
+  const bool due = (tm.ncycle == 0) || (tm.time >= hst_next_time_) ||
+                   (tm.tlim > 0.0 && tm.time >= tm.tlim) || final_signal;
+  if (!due) return;
+  WriteHistoryRow();
+  if (hst_dt_ > 0.0) hst_next_time_ += hst_dt_;  // history.cpp:213-216
+}
+
+void HydroSim::FinalizeOutputs() {
+  if (hst_last_cycle_ == tm.ncycle && tm.ncycle != 0) return;  // (already written by an earlier call)
+  MakeOutputs(true);
+}
+
 size_t HydroSim::InteriorElems() const {
   return blocks_.size() * (size_t)nvar_ * cfg_.mb[0] * cfg_.mb[1] * cfg_.mb[2];
 }
@@ -1822,6 +1889,8 @@ int HydroSim::Execute(double tlim, int nlim) {  // driver.cpp:67-165
     if (tm.time < tm.tlim && (tm.tlim - tm.time) < tm.dt) tm.dt = tm.tlim - tm.time;
   }
   tm.nlim = nlim;
+  // driver.cpp:88-93: the initial dump
+  if (tm.ncycle == 0 && hst_file_number_ == 0) MakeOutputs(false);
   while (tm.KeepGoing()) {
     PreStepMeshUserWorkInLoop();
     if (Step() != TaskStatus::complete) throw std::runtime_error("Step failed to complete all tasks.");
@@ -1831,6 +1900,8 @@ int HydroSim::Execute(double tlim, int nlim) {  // driver.cpp:67-165
     // driver.cpp:128-131: remesh, and new block time steps when the mesh changed
     if (cfg_.adaptive && LoadBalancingAndAdaptiveMeshRefinement()) EstimateTimestep(false);
     SetGlobalTimeStep();
+    // driver.cpp:141-143: the last output of a run is left to the `final` signal
+    if (tm.KeepGoing()) MakeOutputs(false);
   }
   Synchronize();
   return tm.ncycle - n0;

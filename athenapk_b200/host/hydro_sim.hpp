@@ -210,6 +210,12 @@ class HydroSim {
   // Everything is enqueued on the simulation stream (no host synchronisation).
   // HydroHst volume sums of the local blocks (hydro.cpp:145-208): mass, mom1-3, KE, E, ME, relDivB
   void History(double *out8);
+  // Parthenon's history output (`file_type = hst`, outputs/history.cpp:172-209; scheduling
+  // outputs.cpp:445-485 and driver.cpp:95-165): Execute() appends a row at cycle 0, then whenever
+  // time >= next_time while the run keeps going; FinalizeOutputs() is the `final` signal after the
+  // loop.  Same header, columns ("mass", "1-mom", ... hydro.cpp:422-441) and number format.
+  void EnableHistoryOutput(const std::string &fname, double dt, const std::string &data_format);
+  void FinalizeOutputs();
   size_t InteriorElems() const;
   int LoadStateInterior(const double *h_src);
   int StoreStateInterior(double *h_dst);
@@ -247,6 +253,11 @@ class HydroSim {
   int *d_tags_ = nullptr;
   double *d_maxeps_ = nullptr;
   size_t tags_cap_ = 0;
+  std::string hst_name_, hst_fmt_ = " %12.5e";
+  double hst_dt_ = -1.0, hst_next_time_ = 0.0;
+  int hst_file_number_ = 0, hst_last_cycle_ = -1;
+  void MakeOutputs(bool final_signal);
+  void WriteHistoryRow();
   std::string pgen_id_;
   std::vector<double> pgen_pars_;
   void BuildNeighbors();

@@ -135,6 +135,15 @@ int apk_sim_amr_remesh(apk_sim_t *s) {
 int apk_sim_amr_flag(const apk_sim_t *s, int b) {
   return reinterpret_cast<const HydroSim *>(s)->RefineFlag(b);
 }
+int apk_sim_enable_history(apk_sim_t *s, const char *fname, double dt, const char *data_format) {
+  return guarded([&] {
+    SIM(s)->EnableHistoryOutput(fname, dt, data_format ? data_format : "");
+    return 0;
+  });
+}
+int apk_sim_finalize_outputs(apk_sim_t *s) {
+  return guarded([&] { SIM(s)->FinalizeOutputs(); return 0; });
+}
 int apk_sim_last_s_rkl(const apk_sim_t *s) { return reinterpret_cast<const HydroSim *>(s)->last_s_rkl; }
 
 int apk_sim_nccl_unique_id(void *out, int nbytes) { return HydroSim::CommUniqueId(out, nbytes); }

@@ -95,6 +95,12 @@ int apk_sim_download_all(apk_sim_t *s, int field, double *dst);
  * enqueued on the simulation stream without host synchronisation (host buffers should be pinned). */
 /* HydroHst volume sums of the local blocks (hydro.cpp:145-208): mass, mom1-3, KE, E, ME, relDivB */
 int apk_sim_history(apk_sim_t *s, double *out8);
+/* Parthenon's history file (`<parthenon/outputN> file_type = hst`, outputs/history.cpp:172-209):
+ * apk_sim_execute appends a row at cycle 0 and whenever time >= next_time (every `dt`) while the
+ * run keeps going, apk_sim_finalize_outputs writes the final row (the `final` signal of
+ * driver.cpp:158-160).  Same header, columns and number format (data_format, default "%12.5e"). */
+int apk_sim_enable_history(apk_sim_t *s, const char *fname, double dt, const char *data_format);
+int apk_sim_finalize_outputs(apk_sim_t *s);
 long long apk_sim_interior_elems(const apk_sim_t *s);
 int apk_sim_load_interior(apk_sim_t *s, const double *src);
 int apk_sim_store_interior(apk_sim_t *s, double *dst);

@@ -1656,23 +1656,50 @@ void apko_dedner(apko_engine *e, double bdt) {
 /* bvals/boundary_conditions.cpp:36-59, boundary_conditions_generic.hpp:174-262,          */
 /* src/bvals/boundary_conditions_apk.hpp:38-85                                            */
 /* ===================================================================================== */
-static void apply_bc(apko_engine *e, block_t *B, int d, int outer, int type) {
+/* GenericBC (boundary_conditions_generic.hpp:174-262) on an array of extents n[] whose interior is
+ * [is, ie]: the fine block (cellbounds) or its coarse buffer (c_cellbounds, `coarse = true`) */
+static void apply_bc_array(const apko_engine *e, double *arr, const int *n, const int *is,
+                           const int *ie, int d, int outer, int type) {
   if (e->p.nx[d] == 1) return;
-  int lo[3] = {0, 0, 0}, hi[3] = {e->n[0] - 1, e->n[1] - 1, e->n[2] - 1};
-  const int ref = outer ? e->ie[d] : e->is[d];
-  if (outer) lo[d] = e->ie[d] + 1;
-  else hi[d] = e->is[d] - 1;
+  int lo[3] = {0, 0, 0}, hi[3] = {n[0] - 1, n[1] - 1, n[2] - 1};
+  const int ref = outer ? ie[d] : is[d];
+  if (outer) lo[d] = ie[d] + 1;
+  else hi[d] = is[d] - 1;
   const int offset = 2 * ref + (outer ? 1 : -1);
-  for (int n = 0; n < e->nvar; ++n) {
+  const size_t ncell = (size_t)n[0] * n[1] * n[2];
+  for (int v = 0; v < e->nvar; ++v) {
     /* AthenaPK ReflectBC flips v == DIR, i.e. the normal momentum (euler only) */
-    const double sgn = (type == APKO_BC_REFLECT && n == d + 1) ? -1.0 : 1.0;
+    const double sgn = (type == APKO_BC_REFLECT && v == d + 1) ? -1.0 : 1.0;
+    double *a = arr + (size_t)v * ncell;
     for (int k = lo[2]; k <= hi[2]; ++k)
       for (int j = lo[1]; j <= hi[1]; ++j)
         for (int i = lo[0]; i <= hi[0]; ++i) {
           int c[3] = {i, j, k};
           c[d] = (type == APKO_BC_REFLECT) ? offset - c[d] : ref;
-          B->cons[IDX(e, n, k, j, i)] = sgn * B->cons[IDX(e, n, c[2], c[1], c[0])];
+          a[((size_t)k * n[1] + j) * n[0] + i] = sgn * a[((size_t)c[2] * n[1] + c[1]) * n[0] + c[0]];
         }
+  }
+}
+
+static void apply_bc(apko_engine *e, block_t *B, int d, int outer, int type) {
+  apply_bc_array(e, B->cons, e->n, e->is, e->ie, d, outer, type);
+}
+
+/* physical BCs of a block of a refined mesh, in face order (boundary_conditions.cpp:36-59), on the
+ * block itself or on its coarse buffer (ApplyBoundaryConditionsOnCoarseOrFine) */
+static void apply_block_bcs(apko_engine *e, block_t *B, int coarse) {
+  int cis[3], cie[3];
+  for (int d = 0; d < 3; ++d) {
+    cis[d] = (d < e->ndim) ? e->p.ng : 0;
+    cie[d] = (d < e->ndim) ? e->p.ng + e->p.mb[d] / 2 - 1 : 0;
+  }
+  for (int face = 0; face < 2 * e->ndim; ++face) {
+    const int d = face / 2, outer = face % 2;
+    if (e->p.bc[face] == APKO_BC_PERIODIC) continue;
+    const int last = (e->nb[d] << B->level) - 1;
+    if (outer ? (B->loc[d] != last) : (B->loc[d] != 0)) continue;
+    if (coarse) apply_bc_array(e, B->coarse, e->nc, cis, cie, d, outer, e->p.bc[face]);
+    else apply_bc(e, B, d, outer, e->p.bc[face]);
   }
 }
 
@@ -1708,11 +1735,6 @@ static void ml_range(const apko_engine *e, int d, int o, int coarse, int depth, 
 static void exchange_multilevel(apko_engine *e) {
   const apko_params *p = &e->p;
   const int ng = p->ng, nv = e->nvar;
-  for (int f = 0; f < 2 * e->ndim; ++f)
-    if (p->bc[f] != APKO_BC_PERIODIC) {
-      fprintf(stderr, "apk_oracle: refined meshes are restated for periodic domains only\n");
-      abort();
-    }
   /* (1) same level and (2) finer neighbours -> ghost cells */
   for (int b = 0; b < e->nblocks; ++b) {
     block_t *B = &e->blk[b];
@@ -1801,6 +1823,8 @@ static void exchange_multilevel(apko_engine *e) {
               }
       }
     }
+    /* physical boundaries of the coarse buffer (cbound, boundary_communication.cpp:438-440) */
+    apply_block_bcs(e, B, 1);
     for (int idx = 0; idx < 27; ++idx) {
       if (B->ntype[idx] != 2) continue;
       const int off[3] = {idx % 3 - 1, (idx / 3) % 3 - 1, idx / 9 - 1};
@@ -1810,6 +1834,8 @@ static void exchange_multilevel(apko_engine *e) {
                                     B->coarse, lo, hi);
     }
   }
+  /* fbound */
+  for (int b = 0; b < e->nblocks; ++b) apply_block_bcs(e, &e->blk[b], 0);
 }
 
 /* ---- flux correction (bvals_in_one.hpp:69-80, bnd_info.cpp:71-103, hydro_driver.cpp:527-531):

@@ -48,6 +48,44 @@ CASES = {
 }
 
 
+# refined meshes on NON-periodic domains: physical boundary conditions on the coarse buffers before
+# the prolongation and on the blocks after it (boundary_communication.cpp:437-442), the blast placed
+# on the domain boundary inside the refined region
+def _bc(ix1, ox1, ix2, ox2, ix3="periodic", ox3="periodic"):
+    return ["parthenon/mesh/ix1_bc=" + ix1, "parthenon/mesh/ox1_bc=" + ox1,
+            "parthenon/mesh/ix2_bc=" + ix2, "parthenon/mesh/ox2_bc=" + ox2,
+            "parthenon/mesh/ix3_bc=" + ix3, "parthenon/mesh/ox3_bc=" + ox3]
+
+
+def _blast(x, y, z):
+    return BLAST[:4] + ["problem/blast/x1_0=%r" % x, "problem/blast/x2_0=%r" % y,
+                        "problem/blast/x3_0=%r" % z]
+
+
+_2D = ["parthenon/mesh/nx1=64", "parthenon/mesh/nx2=64", "parthenon/mesh/nx3=1",
+       "parthenon/meshblock/nx3=1"]
+CASES.update({
+    "static_2d_outflow": ["parthenon/time/nlim=40", "parthenon/mesh/refinement=static",
+                          "parthenon/static_refinement0/x1min=-0.5", "parthenon/static_refinement0/x1max=-0.2",
+                          "parthenon/static_refinement0/x2min=-0.5", "parthenon/static_refinement0/x2max=-0.1",
+                          "parthenon/static_refinement0/level=2"] + _2D +
+                         _bc("outflow", "outflow", "outflow", "outflow") + _blast(-0.42, -0.4, 0.0),
+    "adaptive_2d_reflect_outflow": ["parthenon/time/nlim=80", "parthenon/mesh/derefine_count=5",
+                                    "hydro/riemann=hllc"] + _2D +
+                                   _bc("reflecting", "outflow", "outflow", "reflecting") +
+                                   _blast(-0.42, 0.41, 0.0),
+    "static_3d_outflow_wenoz_hlld": ["parthenon/time/nlim=10", "parthenon/mesh/refinement=static",
+                                     "hydro/fluid=glmmhd", "hydro/reconstruction=wenoz",
+                                     "hydro/riemann=hlld", "parthenon/mesh/nghost=4",
+                                     "parthenon/static_refinement0/x1min=0.1", "parthenon/static_refinement0/x1max=0.5",
+                                     "parthenon/static_refinement0/x2min=-0.5", "parthenon/static_refinement0/x2max=-0.2",
+                                     "parthenon/static_refinement0/x3min=-0.2", "parthenon/static_refinement0/x3max=0.2",
+                                     "parthenon/static_refinement0/level=2"] +
+                                    _bc("outflow", "outflow", "outflow", "outflow", "outflow", "outflow") +
+                                    _blast(0.4, -0.41, 0.05),
+})
+
+
 def run(overrides):
     with tempfile.TemporaryDirectory() as tmp:
         cmd = [BIN, "-i", DECK] + overrides + COMMON
@@ -60,9 +98,9 @@ def run(overrides):
     for m in MESH.finditer(p.stdout):
         per = {int(a): int(b) for a, b in LEVEL.findall(m.group(2))}
         blocks.append([int(m.group(1))] + [per.get(l, 0) for l in range(max(per) + 1)])
-    tot = TOTALS.search(p.stdout)
+    tot = TOTALS.search(p.stdout)  # (printed by adaptive runs only)
     return {"overrides": overrides, "ncycle": len(trace) - 1, "trace": trace, "blocks": blocks,
-            "final": [int(tot.group(1)), int(tot.group(2)), int(tot.group(3))]}
+            "final": [int(tot.group(1)), int(tot.group(2)), int(tot.group(3))] if tot else None}
 
 
 def main():

@@ -134,5 +134,11 @@ def main():
     json.dump(out, open(os.path.join(HERE, "reference_traces.json"), "w"), indent=0)
 
 
+# tests/golden/reference_orszag_tang_50.hst: the history file the reference writes for
+#   athenaPK -i inputs/orszag_tang.in parthenon/time/nlim=50 parthenon/output0/file_type=hst \
+#            parthenon/output0/dt=-1 parthenon/output1/dt=0.005
+# (copied as written: parthenon.out1.hst)
+
+
 if __name__ == "__main__":
     sys.exit(main())

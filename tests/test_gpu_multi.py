@@ -63,6 +63,10 @@ CASES = [
          mb=[8, 8, 1], xmin=[-0.5, -0.5, -0.5], xmax=[0.5, 0.5, 0.5], gamma=1.666666666666667,
          refine=[[1, [-0.2] * 3, [0.2] * 3]], pgen="blast",
          pgen_pars=[0.12, 0.1, 100.0, 1.0, 0.22, 0.1, -0.05], fused=False, cycles=8, amr=True),
+    # a passive scalar through the fused stage kernel: the peer stores carry nhydro + 1 variables
+    dict(fluid="glmmhd", recon="ppm", riemann="hlld", integrator="vl2", ng=3, nx=[32, 32, 32],
+         mb=[16, 16, 16], xmin=[0, 0, 0], xmax=[1, 1, 1], pgen="random", pgen_pars=[3, 0.2],
+         fused=True, nscalars=1),
 ]
 
 

@@ -371,6 +371,33 @@ def test_static_refinement_reference_traces(apk, name):
     s.close()
 
 
+def test_history_file_matches_reference(apk, tmp_path):
+    """`file_type = hst` (outputs/history.cpp:172-209, scheduling outputs.cpp:445-485): the history
+    file written during a 50-cycle Orszag-Tang run (config 3, FOFC on, output every 0.005) equals the
+    file the unmodified reference wrote (tests/golden/reference_orszag_tang_50.hst) -- same header,
+    same rows at the same cycles, every printed digit of time, dt, mass, KE, tot-E, ME and relDivB;
+    the momentum sums are round-off noise (1e-17) and are compared to 1e-15 absolute."""
+    kw, pgen, pars, tlim = DECKS["orszag_tang_50"]
+    s = apk.HydroSim(fp_mode="strict", **kw)
+    s.pgen(pgen, pars)
+    s.initialize(tlim)
+    out = str(tmp_path / "parthenon.out1.hst")
+    s.enable_history(out, 0.005)
+    s.execute(tlim, 50)
+    s.finalize_outputs()
+    s.close()
+    got = open(out).read().splitlines()
+    ref = open(os.path.join(os.path.dirname(__file__), "golden",
+                            "reference_orszag_tang_50.hst")).read().splitlines()
+    assert got[:2] == ref[:2]
+    assert len(got) == len(ref)
+    for g, r in zip(got[2:], ref[2:]):
+        gt, rt = g.split(), r.split()
+        assert gt[:5] == rt[:5] and gt[7:] == rt[7:], (g, r)
+        assert all(abs(float(a) - float(b)) < 1e-15 for a, b in zip(gt[5:7], rt[5:7]))
+        assert len(g) == len(r)
+
+
 def test_config4_full_size_reference_trace(apk):
     """BASELINE config 4 at FULL size -- 256^3, 512 meshblocks of 32^3, GLM-MHD VL2+PPM+HLLD, the
     Orszag-Tang state of baseline/decks/orszag_tang_3d.in, i.e. exactly what bench.py times -- in

@@ -6,7 +6,7 @@ GPU tests hold to the same traces in strict FP mode."""
 import pytest
 
 from oracle_lib import Oracle
-from trace_util import (ADAPTIVE_DECKS, ADAPTIVE_TRACES, AMR_DECKS, DECKS, DIFF_DECKS, DIFF_TRACES,
+from trace_util import (ADAPTIVE_DECKS, ADAPTIVE_TRACES, AMR_DECKS, BOUNDARY_AMR_DECKS, DECKS, DIFF_DECKS, DIFF_TRACES,
                         TRACES, check_lw_row, follow_adaptive_trace, follow_trace, lw_kwargs,
                         lw_pgen)
 
@@ -99,6 +99,23 @@ def test_adaptive_refinement_traces(name):
     cycle, plus the created / destroyed totals (3-D: up to 680 blocks, 91 destroyed; 2-D, 4 levels,
     derefine_count = 3: 714 created, 300 destroyed in 120 cycles)."""
     kw, pgen, pars, tlim = ADAPTIVE_DECKS[name]
+    o = Oracle(**kw)
+    o.pgen(pgen, pars)
+    o.initialize(tlim)
+    case = ADAPTIVE_TRACES[name]
+    follow_adaptive_trace(o, case, tlim, advance, lambda o: o.amr_counts())
+    assert o.ncycle == case["ncycle"]
+
+
+@pytest.mark.parametrize("name", sorted(BOUNDARY_AMR_DECKS))
+def test_refined_meshes_with_physical_boundaries(name):
+    """refined meshes (static and adaptive) on NON-periodic domains: the physical boundary
+    conditions (outflow, reflecting) are applied to the coarse buffers before the prolongation and
+    to the blocks after it (boundary_communication.cpp:437-442), the tree does not wrap around.
+    The blast sits on the domain boundary inside the refined region; 17-digit (time, dt) and
+    meshblock counts of three reference runs (2-D static, 2-D adaptive with reflecting walls, 3-D
+    static with config 5's method)."""
+    kw, pgen, pars, tlim = BOUNDARY_AMR_DECKS[name]
     o = Oracle(**kw)
     o.pgen(pgen, pars)
     o.initialize(tlim)
