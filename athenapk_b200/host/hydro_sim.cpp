@@ -133,9 +133,10 @@ HydroSim::HydroSim(const SimConfig &cfg)
                                "not a multiple of 2.");
     if (cfg_.nref > 4)
       throw std::runtime_error("apk_host: at most 4 static refinement regions");
-    for (int f = 0; f < 2 * ndim_; ++f)
-      if (cfg_.bc[f] != APK_BC_PERIODIC)
-        throw std::runtime_error("apk_host: refined meshes are implemented for periodic domains");
+    if (cfg_.nranks > 1)
+      for (int f = 0; f < 2 * ndim_; ++f)
+        if (cfg_.bc[f] != APK_BC_PERIODIC)
+          throw std::runtime_error("apk_host: refined meshes on non-periodic domains run on one rank");
     for (int d = 0; d < ndim_; ++d)
       if (cfg_.mb[d] % 2 != 0 || cfg_.mb[d] / 2 < cfg_.ng)
         throw std::runtime_error("apk_host: meshblock too small for refinement (nx/2 >= nghost)");
@@ -393,12 +394,17 @@ std::vector<HydroSim::Leaf> HydroSim::BuildLeaves() const {
             for (int o1 = -1; o1 <= 1; ++o1) {
               const int off[3] = {o1, o2, o3};
               int nl[3];
+              bool inside = true;
               for (int d = 0; d < 3; ++d) {
                 const int tot = nb_[d] << q.level;
-                nl[d] = ((lx[d] + off[d]) % tot + tot) % tot;  // periodic (checked in the ctor)
+                nl[d] = lx[d] + off[d];
+                if (nl[d] < 0 || nl[d] >= tot) {
+                  if (d < ndim_ && cfg_.bc[2 * d] != APK_BC_PERIODIC) inside = false;
+                  nl[d] = (nl[d] % tot + tot) % tot;
+                }
               }
               LeafKey c{};
-              if (cover(q.level, nl, &c) && c.level < q.level - 1) marked.push_back(c);
+              if (inside && cover(q.level, nl, &c) && c.level < q.level - 1) marked.push_back(c);
             }
       }
     }
@@ -453,7 +459,11 @@ void HydroSim::BuildMultilevelNeighbors() {
           continue;
         }
         const int tot = nb_[d] << B.level;
-        nl[d] = ((B.loc[d] + off[d]) % tot + tot) % tot;
+        nl[d] = B.loc[d] + off[d];
+        if (nl[d] < 0 || nl[d] >= tot) {
+          if (cfg_.bc[2 * d] != APK_BC_PERIODIC) valid = false;  // physical boundary: no neighbour
+          nl[d] = (nl[d] % tot + tot) % tot;
+        }
       }
       if (!valid) continue;
       auto same = index.find({B.level, nl[0], nl[1], nl[2]});
@@ -508,7 +518,17 @@ void HydroSim::BuildNeighbors() {
         hb.dx[d] = blocks_[b].dx[d];
         hb.xmin[d] = blocks_[b].xmin[d];
       }
-      for (int f = 0; f < 6; ++f) hb.bc[f] = APK_BC_BLOCK;
+      // tree.cpp:320-333 GetBlockBCs at the block's own level
+      for (int f = 0; f < 6; ++f) {
+        const int d = f / 2;
+        const int last = (nb_[d] << blocks_[b].level) - 1;
+        const bool on_edge = (f % 2 == 0) ? (blocks_[b].loc[d] == 0) : (blocks_[b].loc[d] == last);
+        hb.bc[f] = APK_BC_BLOCK;
+        if (d < ndim_ && on_edge && cfg_.bc[f] != APK_BC_PERIODIC) {
+          hb.bc[f] = cfg_.bc[f];
+          bc_face_mask_ |= 1u << f;
+        }
+      }
       // the same-level table drives apk_copy_ghosts_local; other levels go through the plan
       for (int idx = 0; idx < 27; ++idx)
         hb.nbr[idx] = (nbrinfo_[b].type[idx] == 1 && IsLocal(nbrinfo_[b].idx[idx][0]))
@@ -618,6 +638,7 @@ void HydroSim::ReleaseMeshArrays() {
   pooled(d_blocks_[1]);
   pooled(d_prim_out_[0]);
   pooled(d_prim_out_[1]);
+  pooled(d_cblocks_);
   fr(d_undo_);
   fr(d_fofc_work_);
   fr(d_hist_);
@@ -696,6 +717,26 @@ void HydroSim::UploadBlocks() {
     d_coarse_ = static_cast<double *>(SlabAlloc(cbytes, "cudaMalloc coarse"));
     if (first) cuda_check(cudaMemsetAsync(d_coarse_, 0, cbytes, S(stream_)), "memset");
     if (cfg_.nranks == 1) BuildMultilevelPlan();  // several ranks: after the peer mapping (InitComm)
+    if (bc_face_mask_) {
+      // physical BCs on the coarse buffers (ApplyBoundaryConditionsOnCoarseOrFine(coarse = true)):
+      // the same kernel on a second block table whose arrays are the coarse buffers
+      desc_coarse_ = desc_;
+      for (int d = 0; d < ndim_; ++d) desc_coarse_.nx[d] = cfg_.mb[d] / 2;
+      std::vector<apk_block_t> cb = h_blocks_;
+      for (size_t b = 0; b < nbl; ++b) {
+        cb[b].cons = d_coarse_ + b * CoarseElems();
+        cb[b].prim = cb[b].cons_u1 = nullptr;
+        for (int d = 0; d < 3; ++d) {
+          cb[b].flux[d] = nullptr;
+          cb[b].dx[d] = (d < ndim_) ? 2.0 * h_blocks_[b].dx[d] : h_blocks_[b].dx[d];
+        }
+        // (every array pointer of a descriptor must be set: the coarse buffer stands in)
+        cb[b].prim = cb[b].cons_u1 = cb[b].cons;
+      }
+      d_cblocks_ = static_cast<apk_block_t *>(SlabAlloc(nbl * sizeof(apk_block_t), "cudaMalloc coarse blocks"));
+      cuda_check(cudaMemcpy(d_cblocks_, cb.data(), nbl * sizeof(apk_block_t), cudaMemcpyHostToDevice),
+                 "upload coarse blocks");
+    }
   }
   // the slabs are zeroed on the simulation stream; everything that follows (blocking copies of the
   // problem generator, kernels on any stream) must see them cleared
@@ -1657,6 +1698,10 @@ TaskStatus HydroSim::ProlongateBounds() {
                                  ml_restrict_own_.n, fp, stream_), "apk_restrict_average");
   abi_check(apk_box_copy(static_cast<const apk_box_item_t *>(ml_coarse_from_nbr_.d),
                          ml_coarse_from_nbr_.n, nvar_, stream_), "apk_box_copy");
+  // cbound (boundary_communication.cpp:437-440): physical BCs on the coarse buffers
+  if (bc_face_mask_ && d_cblocks_)
+    abi_check(apk_apply_physical_bcs(&desc_coarse_, d_cblocks_, bc_face_mask_, 0, stream_),
+              "apk_apply_physical_bcs (coarse buffers)");
   abi_check(apk_prolongate_minmod_multid(ndim_, cfg_.ng, nvar_,
                                          static_cast<const apk_amr_item_t *>(ml_prolong_.d),
                                          ml_prolong_.n, fp, stream_), "apk_prolongate_minmod_multid");

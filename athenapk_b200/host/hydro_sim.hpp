@@ -304,6 +304,8 @@ class HydroSim {
   BlockInfo MakeBlockInfo(int gid, int level, const int *loc) const;
   void BuildMultilevelNeighbors();
   void BuildMultilevelPlan();
+  apk_block_t *d_cblocks_ = nullptr;  // block table over the coarse buffers (physical BCs on them)
+  apk_pack_desc_t desc_coarse_{};
   double *d_coarse_ = nullptr;  // coarse buffers [nblocks][nvar][nc3][nc2][nc1] (Variable::coarse_s)
   int nc_[3] = {1, 1, 1};
   size_t CoarseElems() const { return (size_t)nvar_ * nc_[0] * nc_[1] * nc_[2]; }
