@@ -46,7 +46,11 @@ class SimConfig(C.Structure):
         ("rkl2_max_dt_ratio", C.c_double), ("conduction_sat_phi", C.c_double),
         ("adaptive", C.c_int), ("numlevel", C.c_int), ("derefine_count", C.c_int),
         ("refine_threshold", C.c_double),
+        ("refine_type", C.c_int), ("refine_threshold2", C.c_double),
     ]
+
+
+REFINE_TYPE = {"pressure_gradient": 0, "xyvelocity_gradient": 1, "maxdensity": 2}
 
 
 class HaloItem(C.Structure):
@@ -94,7 +98,7 @@ ABI_SYMBOLS = [
     "apk_min_dt_async", "apk_fill_ghosts_local", "apk_apply_physical_bcs",
     "apk_copy_ghosts_local", "apk_halo_pack", "apk_halo_unpack", "apk_stage_fused", "apk_stage_fused_p2p",
     "apk_save_u1", "apk_fp64_probe", "apk_restrict_average", "apk_prolongate_minmod_multid",
-    "apk_tag_pressure_gradient", "apk_history_workspace_bytes", "apk_history_sums",
+    "apk_tag_pressure_gradient", "apk_tag_refinement", "apk_history_workspace_bytes", "apk_history_sums",
     "apk_reset_fluxes", "apk_calc_diff_fluxes", "apk_rkl2_step_first", "apk_rkl2_step_other",
     "apk_min_dt_conduction",
 ]
@@ -219,6 +223,7 @@ def lib():
     L.apk_sim_num_halo_items.argtypes = [vp, C.c_int]
     L.apk_sim_halo_item.argtypes = [vp, C.c_int, C.c_int, C.POINTER(HaloItem)]
     L.apk_sim_neighbor.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.apk_tag_refinement.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double, vp, vp, vp]
     L.apk_sim_amr_counts.argtypes = [vp, ip, ip, ip]
     L.apk_sim_amr_tag.argtypes = [vp]
     L.apk_sim_amr_remesh.argtypes = [vp]
@@ -281,6 +286,8 @@ def make_config(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
         c.adaptive, c.numlevel = 1, adaptive["numlevel"]
         c.derefine_count = adaptive.get("derefine_count", 10)
         c.refine_threshold = adaptive["threshold"]
+        c.refine_type = REFINE_TYPE[adaptive.get("type", "pressure_gradient")]
+        c.refine_threshold2 = adaptive.get("threshold2", 0.0)
     return c
 
 

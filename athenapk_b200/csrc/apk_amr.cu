@@ -191,13 +191,21 @@ k_prolongate_minmod(int ndim, int ng, int nvar, const apk_amr_item_t *__restrict
   }
 }
 
-// gradient.cpp:18-61: max over interior +- 1 of |grad p| / p (central differences, no dx)
+// Refinement criteria of src/refinement: per block the maximum over a criterion-specific range of
+//   CRIT 0  |grad p| / p, central differences without dx, interior +- 1 (gradient.cpp:18-61)
+//   CRIT 1  sqrt((dv1/dx2)^2 + (dv2/dx1)^2) of the x1-x2 velocities, undivided central differences,
+//           interior +- 1 in x1 and x2 (gradient.cpp:64-95)
+//   CRIT 2  density, interior plus the first ghost cell beyond ie (other.cpp:18-44: `ib.e + 1`)
+template <int CRIT>
 __global__ void __launch_bounds__(kThreads)
-k_pressure_gradient(ApkGeom g, const apk_block_t *__restrict__ blocks,
-                    unsigned long long *maxeps_bits) {
+k_refinement_measure(ApkGeom g, const apk_block_t *__restrict__ blocks,
+                     unsigned long long *measure_bits) {
   const apk_block_t &B = blocks[blockIdx.y];
-  const double *w = B.prim + 4 * g.ncell;  // IPR
-  const int e1 = g.ie - g.is + 3, e2 = g.je - g.js + 3, e3 = (g.ndim == 3) ? g.ke - g.ks + 3 : 1;
+  const int lo1 = (CRIT == 2) ? 0 : -1, hi1 = 1;                      // x1: is+lo1 .. ie+hi1
+  const int pad2 = (CRIT == 2) ? 0 : 1;                                // x2: js-pad2 .. je+pad2
+  const int pad3 = (CRIT == 0 && g.ndim == 3) ? 1 : 0;
+  const int e1 = g.ie - g.is + 1 + hi1 - lo1, e2 = g.je - g.js + 1 + 2 * pad2,
+            e3 = g.ke - g.ks + 1 + 2 * pad3;
   const long total = (long)e1 * e2 * e3;
   const long sj = g.n1, sk = (long)g.n1 * g.n2;
   double m = 0.0;
@@ -206,29 +214,40 @@ k_pressure_gradient(ApkGeom g, const apk_block_t *__restrict__ blocks,
     const int kk = (int)(t / ((long)e1 * e2));
     const long r = t - (long)kk * e1 * e2;
     const int jj = (int)(r / e1), ii = (int)(r - (long)jj * e1);
-    const int k = (g.ndim == 3) ? g.ks - 1 + kk : g.ks, j = g.js - 1 + jj, i = g.is - 1 + ii;
-    const double *p = w + (long)k * sk + (long)j * sj + i;
-    const double a = 0.5 * (p[1] - p[-1]), b = 0.5 * (p[sj] - p[-sj]);
-    double s = a * a + b * b;
-    if (g.ndim == 3) {
-      const double c = 0.5 * (p[sk] - p[-sk]);
-      s = s + c * c;
+    const int k = g.ks - pad3 + kk, j = g.js - pad2 + jj, i = g.is + lo1 + ii;
+    const long c = (long)k * sk + (long)j * sj + i;
+    if (CRIT == 0) {
+      const double *p = B.prim + 4 * g.ncell + c;  // IPR
+      const double a = 0.5 * (p[1] - p[-1]), b = 0.5 * (p[sj] - p[-sj]);
+      double s = a * a + b * b;
+      if (g.ndim == 3) {
+        const double cc = 0.5 * (p[sk] - p[-sk]);
+        s = s + cc * cc;
+      }
+      m = fmax(m, sqrt(s) / p[0]);
+    } else if (CRIT == 1) {
+      const double *v1 = B.prim + 1 * g.ncell + c, *v2 = B.prim + 2 * g.ncell + c;
+      const double vgy = fabs(v2[1] - v2[-1]) * 0.5;
+      const double vgx = fabs(v1[sj] - v1[-sj]) * 0.5;
+      const double vg = sqrt(vgx * vgx + vgy * vgy);
+      if (vg > m) m = vg;
+    } else {
+      m = fmax(m, B.prim[c]);  // IDN
     }
-    m = fmax(m, sqrt(s) / p[0]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  // eps >= 0: the IEEE bit pattern is monotone, atomicMax on the integer image is exact
+  // measure >= 0: the IEEE bit pattern is monotone, atomicMax on the integer image is exact
   if ((threadIdx.x & 31) == 0 && m > 0.0)
-    atomicMax(maxeps_bits + blockIdx.y, (unsigned long long)__double_as_longlong(m));
+    atomicMax(measure_bits + blockIdx.y, (unsigned long long)__double_as_longlong(m));
 }
 
-__global__ void k_pressure_gradient_tags(int nb, double threshold, const double *maxeps,
-                                         int *tags) {
+__global__ void k_refinement_tags(int nb, double refine_above, double derefine_below,
+                                  const double *measure, int *tags) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
-  const double m = maxeps[b];
-  tags[b] = (m > threshold) ? 1 : ((m < 0.25 * threshold) ? -1 : 0);
+  const double m = measure[b];
+  tags[b] = (m > refine_above) ? 1 : ((m < derefine_below) ? -1 : 0);
 }
 
 // ---- history sums (hydro.cpp:145-208).  Level 1: one CTA per (block, slice) reduces its cells in
@@ -342,15 +361,20 @@ int launch_prolongate_minmod(int ndim, int ng, int nvar, const apk_amr_item_t *i
   return 0;
 }
 
-int launch_pressure_gradient(const apk_pack_desc_t &d, const apk_block_t *blocks, double threshold,
-                             int *tags, double *maxeps, cudaStream_t s) {
+int launch_refinement_tags(const apk_pack_desc_t &d, const apk_block_t *blocks, int criterion,
+                           double refine_above, double derefine_below, int *tags, double *measure,
+                           cudaStream_t s) {
   const ApkGeom g = apk_make_geom(d);
-  cudaMemsetAsync(maxeps, 0, sizeof(double) * g.nb, s);
-  if (g.ndim >= 2) {  // gradient.cpp:58-60: 1-D meshes are never tagged
-    dim3 grid(32, g.nb);
-    k_pressure_gradient<<<grid, kThreads, 0, s>>>(g, blocks,
-                                                  reinterpret_cast<unsigned long long *>(maxeps));
-    k_pressure_gradient_tags<<<(g.nb + 127) / 128, 128, 0, s>>>(g.nb, threshold, maxeps, tags);
+  cudaMemsetAsync(measure, 0, sizeof(double) * g.nb, s);
+  // gradient.cpp:58-60: 1-D meshes are never tagged by the gradient criteria
+  if (g.ndim >= 2 || criterion == 2) {
+    dim3 grid(4, g.nb);
+    unsigned long long *bits = reinterpret_cast<unsigned long long *>(measure);
+    if (criterion == 0) k_refinement_measure<0><<<grid, kThreads, 0, s>>>(g, blocks, bits);
+    else if (criterion == 1) k_refinement_measure<1><<<grid, kThreads, 0, s>>>(g, blocks, bits);
+    else k_refinement_measure<2><<<grid, kThreads, 0, s>>>(g, blocks, bits);
+    k_refinement_tags<<<(g.nb + 127) / 128, 128, 0, s>>>(g.nb, refine_above, derefine_below, measure,
+                                                          tags);
     apk_common::count_launch(2);
   } else {
     cudaMemsetAsync(tags, 0, sizeof(int) * g.nb, s);

@@ -301,15 +301,27 @@ int apk_prolongate_minmod_multid(int ndim, int ng, int nvar, const apk_amr_item_
   return cuda_ok("apk_prolongate_minmod_multid");
 }
 
-int apk_tag_pressure_gradient(const apk_pack_desc_t *d, const apk_block_t *blocks, double threshold,
-                              int *d_tags, double *d_maxeps, void *stream) {
-  if (check(d, blocks, "apk_tag_pressure_gradient: bad descriptor")) return 1;
-  if (!d_tags || !d_maxeps) {
-    apk_common::set_error("apk_tag_pressure_gradient: null output");
+int apk_tag_refinement(const apk_pack_desc_t *d, const apk_block_t *blocks, int criterion,
+                       double refine_above, double derefine_below, int *d_tags, double *d_measure,
+                       void *stream) {
+  if (check(d, blocks, "apk_tag_refinement: bad descriptor")) return 1;
+  if (!d_tags || !d_measure || criterion < 0 || criterion > 2) {
+    apk_common::set_error("apk_tag_refinement: null output or unknown criterion");
     return 1;
   }
-  DISPATCH(d, launch_pressure_gradient(*d, blocks, threshold, d_tags, d_maxeps, S(stream)));
-  return cuda_ok("apk_tag_pressure_gradient");
+  if (criterion == APK_REFINE_XYVELOCITY_GRADIENT && d->ndim < 2) {
+    apk_common::set_error("apk_tag_refinement: the velocity-gradient criterion needs a 2-D or 3-D mesh");
+    return 1;
+  }
+  DISPATCH(d, launch_refinement_tags(*d, blocks, criterion, refine_above, derefine_below, d_tags,
+                                     d_measure, S(stream)));
+  return cuda_ok("apk_tag_refinement");
+}
+
+int apk_tag_pressure_gradient(const apk_pack_desc_t *d, const apk_block_t *blocks, double threshold,
+                              int *d_tags, double *d_maxeps, void *stream) {
+  return apk_tag_refinement(d, blocks, APK_REFINE_PRESSURE_GRADIENT, threshold, 0.25 * threshold,
+                            d_tags, d_maxeps, stream);
 }
 
 size_t apk_history_workspace_bytes(const apk_pack_desc_t *d) {

@@ -32,8 +32,9 @@
                               int nitems, cudaStream_t s);                                      \
   int launch_prolongate_minmod(int ndim, int ng, int nvar, const apk_amr_item_t *items,         \
                                int nitems, cudaStream_t s);                                     \
-  int launch_pressure_gradient(const apk_pack_desc_t &d, const apk_block_t *blocks,             \
-                               double threshold, int *tags, double *maxeps, cudaStream_t s);    \
+  int launch_refinement_tags(const apk_pack_desc_t &d, const apk_block_t *blocks,               \
+                             int criterion, double refine_above, double derefine_below,         \
+                             int *tags, double *measure, cudaStream_t s);                       \
   int launch_reset_fluxes(const apk_pack_desc_t &d, const apk_block_t *blocks, cudaStream_t s); \
   int launch_diff_fluxes(const apk_pack_desc_t &d, const apk_block_t *blocks,                   \
                          const apk_diffusion_t &df, cudaStream_t s);                            \

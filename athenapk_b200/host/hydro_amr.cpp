@@ -158,8 +158,13 @@ TaskStatus HydroSim::TagRefinement() {
     cuda_check(cudaMalloc(&d_tags_, tags_cap_ * sizeof(int)), "cudaMalloc tags");
     cuda_check(cudaMalloc(&d_maxeps_, tags_cap_ * sizeof(double)), "cudaMalloc maxeps");
   }
-  abi_check(apk_tag_pressure_gradient(&desc_, d_blocks_[cur_], cfg_.refine_threshold, d_tags_,
-                                      d_maxeps_, stream_), "apk_tag_pressure_gradient");
+  // thresholds of the criterion (gradient.cpp:58-60,91-93; other.cpp:39-41)
+  const double above = cfg_.refine_threshold;
+  const double below = (cfg_.refine_type == APK_REFINE_PRESSURE_GRADIENT)     ? 0.25 * above
+                       : (cfg_.refine_type == APK_REFINE_XYVELOCITY_GRADIENT) ? 0.5 * above
+                                                                               : cfg_.refine_threshold2;
+  abi_check(apk_tag_refinement(&desc_, d_blocks_[cur_], cfg_.refine_type, above, below, d_tags_,
+                               d_maxeps_, stream_), "apk_tag_refinement");
   std::vector<int> tags(nbl);
   cuda_check(cudaMemcpyAsync(tags.data(), d_tags_, nbl * sizeof(int), cudaMemcpyDeviceToHost,
                              S(stream_)), "tags D2H");

@@ -68,6 +68,11 @@ struct SimConfig {
   // (mesh_refinement.cpp:56); <refinement> type = pressure_gradient, threshold_pressure_gradient
   int adaptive = 0, numlevel = 1, derefine_count = 10;
   double refine_threshold = 0.0;
+  // <refinement> type (hydro.cpp:788-816): APK_REFINE_PRESSURE_GRADIENT (refine_threshold =
+  // threshold_pressure_gradient), _XYVELOCITY_GRADIENT (threshold_xyvelocity_gradient), _MAXDENSITY
+  // (refine_threshold = maxdensity_refine_above, refine_threshold2 = maxdensity_deref_below)
+  int refine_type = APK_REFINE_PRESSURE_GRADIENT;
+  double refine_threshold2 = 0.0;
 };
 
 // time_integration/low_storage_integrator.cpp:53-132

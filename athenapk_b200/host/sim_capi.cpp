@@ -67,6 +67,7 @@ apk_sim_t *apk_sim_create(const apk_sim_config_t *c) {
     k.conduction_sat_phi = c->conduction_sat_phi;
     k.adaptive = c->adaptive; k.numlevel = c->numlevel; k.derefine_count = c->derefine_count;
     k.refine_threshold = c->refine_threshold;
+    k.refine_type = c->refine_type; k.refine_threshold2 = c->refine_threshold2;
     s = new HydroSim(k);
     return 0;
   });

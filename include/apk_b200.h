@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define APK_ABI_VERSION 4  /* 4: diffusion block (apk_calc_diff_fluxes, apk_reset_fluxes, apk_rkl2_step_*, apk_min_dt_conduction) */
+#define APK_ABI_VERSION 5  /* 5: apk_tag_refinement (all <refinement> criteria); 4: diffusion block */
 
 /* src/main.hpp:19-50 (enum values are ours; the shim translates) */
 enum { APK_FLUID_EULER = 0, APK_FLUID_GLMMHD = 1 };
@@ -378,6 +378,19 @@ int apk_box_copy(const apk_box_item_t *d_items, int nitems, int nvar, void *stre
  * 0 same, 1 refine). */
 int apk_tag_pressure_gradient(const apk_pack_desc_t *desc, const apk_block_t *d_blocks,
                               double threshold, int *d_tags, double *d_maxeps, void *stream);
+/* All `<refinement> type` criteria of src/refinement (hydro.cpp:788-816): per block a measure
+ * (d_measure[b]) and the AmrTag (d_tags[b] = 1 when measure > refine_above, -1 when measure <
+ * derefine_below, else 0):
+ *   APK_REFINE_PRESSURE_GRADIENT    max |grad p| / p over interior +- 1 (gradient.cpp:18-61;
+ *                                   derefine_below = 0.25 threshold)
+ *   APK_REFINE_XYVELOCITY_GRADIENT  max sqrt((dv1/dx2)^2 + (dv2/dx1)^2), undivided differences
+ *                                   (gradient.cpp:64-95; derefine_below = 0.5 threshold)
+ *   APK_REFINE_MAXDENSITY           max density (other.cpp:18-44; maxdensity_refine_above /
+ *                                   maxdensity_deref_below) */
+enum { APK_REFINE_PRESSURE_GRADIENT = 0, APK_REFINE_XYVELOCITY_GRADIENT = 1, APK_REFINE_MAXDENSITY = 2 };
+int apk_tag_refinement(const apk_pack_desc_t *desc, const apk_block_t *d_blocks, int criterion,
+                       double refine_above, double derefine_below, int *d_tags, double *d_measure,
+                       void *stream);
 
 /* ---- history reducers HydroHst<...> (src/hydro/hydro.cpp:145-208, registered :422-441): volume
  * sums over the interior cells of the pack: out8 = {mass, mom1, mom2, mom3, kinetic energy, total

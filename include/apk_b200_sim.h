@@ -47,6 +47,10 @@ typedef struct apk_sim_config {
    * pressure_gradient with threshold_pressure_gradient (src/refinement/gradient.cpp:18-61) */
   int adaptive, numlevel, derefine_count;
   double refine_threshold;
+  /* <refinement> type = APK_REFINE_* (apk_b200.h); refine_threshold is threshold_pressure_gradient /
+   * threshold_xyvelocity_gradient / maxdensity_refine_above, refine_threshold2 maxdensity_deref_below */
+  int refine_type;
+  double refine_threshold2;
 } apk_sim_config_t;
 
 const char *apk_sim_last_error(void);

@@ -2430,8 +2430,15 @@ int apko_amr_tag(apko_engine *e) {
   for (int b = 0; b < e->nblocks; ++b) {
     block_t *B = &e->blk[b];
     /* CheckAllRefinement: max(derefine, package criteria) */
-    const int aret = apko_pressure_gradient_tag(e->ndim, p->ng, e->n, B->prim, IPR,
-                                                p->refine_threshold, NULL);
+    int aret;
+    if (p->refine_type == 1)
+      aret = apko_velocity_gradient_tag(e->ndim, p->ng, e->n, B->prim, p->refine_threshold, NULL);
+    else if (p->refine_type == 2)
+      aret = apko_max_density_tag(e->ndim, p->ng, e->n, B->prim, p->refine_threshold,
+                                  p->refine_threshold2, NULL);
+    else
+      aret = apko_pressure_gradient_tag(e->ndim, p->ng, e->n, B->prim, IPR, p->refine_threshold,
+                                        NULL);
     if (aret == 0) B->refine_flag = 0;
     if (aret >= 0) B->deref_count = 0;
     if (aret > 0) {
@@ -3578,5 +3585,46 @@ int apko_pressure_gradient_tag(int ndim, int ng, const int *n, const double *pri
   if (maxeps_out) *maxeps_out = maxeps;
   if (maxeps > threshold) return 1;
   if (maxeps < 0.25 * threshold) return -1;
+  return 0;
+}
+
+int apko_velocity_gradient_tag(int ndim, int ng, const int *n, const double *prim, double threshold,
+                               double *vgmax_out) {
+  /* gradient.cpp:64-95: k over the interior, j and i over interior +- 1 */
+  const size_t n1 = n[0], n2 = n[1], ncell = (size_t)n[0] * n[1] * n[2];
+  const double *v1 = prim + (size_t)IV1 * ncell, *v2 = prim + (size_t)IV2 * ncell;
+#define AT(a, k, j, i) a[((size_t)(k)*n2 + (j)) * n1 + (i)]
+  const int is = ng, ie = n[0] - ng - 1, js = ng, je = n[1] - ng - 1;
+  const int ks = (ndim == 3) ? ng : 0, ke = (ndim == 3) ? n[2] - ng - 1 : 0;
+  double vgmax = 0.0;
+  for (int k = ks; k <= ke; ++k)
+    for (int j = js - 1; j <= je + 1; ++j)
+      for (int i = is - 1; i <= ie + 1; ++i) {
+        const double vgy = fabs(AT(v2, k, j, i + 1) - AT(v2, k, j, i - 1)) * 0.5;
+        const double vgx = fabs(AT(v1, k, j + 1, i) - AT(v1, k, j - 1, i)) * 0.5;
+        const double vg = sqrt(vgx * vgx + vgy * vgy);
+        if (vg > vgmax) vgmax = vg;
+      }
+#undef AT
+  if (vgmax_out) *vgmax_out = vgmax;
+  if (vgmax > threshold) return 1;
+  if (vgmax < 0.5 * threshold) return -1;
+  return 0;
+}
+
+int apko_max_density_tag(int ndim, int ng, const int *n, const double *prim, double refine_above,
+                         double deref_below, double *maxrho_out) {
+  /* other.cpp:18-44: note the x1 range ib.s .. ib.e + 1 */
+  const size_t n1 = n[0], n2 = n[1];
+  const int is = ng, ie = n[0] - ng - 1;
+  const int js = (ndim >= 2) ? ng : 0, je = (ndim >= 2) ? n[1] - ng - 1 : 0;
+  const int ks = (ndim == 3) ? ng : 0, ke = (ndim == 3) ? n[2] - ng - 1 : 0;
+  double maxrho = 0.0;
+  for (int k = ks; k <= ke; ++k)
+    for (int j = js; j <= je; ++j)
+      for (int i = is; i <= ie + 1; ++i) maxrho = fmax(maxrho, prim[((size_t)k * n2 + j) * n1 + i]);
+  if (maxrho_out) *maxrho_out = maxrho;
+  if (maxrho > refine_above) return 1;
+  if (maxrho < deref_below) return -1;
   return 0;
 }

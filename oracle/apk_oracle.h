@@ -64,6 +64,12 @@ typedef struct {
    * threshold_pressure_gradient (src/refinement/gradient.cpp:18-61) */
   int adaptive, numlevel, derefine_count;
   double refine_threshold;
+  /* <refinement> type: 0 pressure_gradient (refine_threshold = threshold_pressure_gradient),
+   * 1 xyvelocity_gradient (threshold_xyvelocity_gradient; gradient.cpp:64-95), 2 maxdensity
+   * (refine_threshold = maxdensity_refine_above, refine_threshold2 = maxdensity_deref_below;
+   * other.cpp:18-44) */
+  int refine_type;
+  double refine_threshold2;
 } apko_params;
 
 typedef struct apko_engine apko_engine;
@@ -156,6 +162,12 @@ void apko_prolongate_minmod_multid(int ndim, int ng, const double *xmin_block, c
  * prim [nv][n3][n2][n1]; returns the tag (-1 derefine, 0 same, 1 refine), *maxeps_out = max eps */
 int apko_pressure_gradient_tag(int ndim, int ng, const int *n, const double *prim, int ipr,
                                double threshold, double *maxeps_out);
+/* refinement::gradient::VelocityGradient (gradient.cpp:64-95) and refinement::other::MaxDensity
+ * (other.cpp:18-44) for one block */
+int apko_velocity_gradient_tag(int ndim, int ng, const int *n, const double *prim, double threshold,
+                               double *vgmax_out);
+int apko_max_density_tag(int ndim, int ng, const int *n, const double *prim, double refine_above,
+                         double deref_below, double *maxrho_out);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,17 @@ CASES.update({
 })
 
 
+# the other <refinement> criteria (src/refinement/gradient.cpp:64-95, other.cpp:18-44)
+CASES.update({
+    "adaptive_2d_xyvelocity": ["parthenon/time/nlim=80", "parthenon/mesh/derefine_count=5",
+                               "refinement/type=xyvelocity_gradient",
+                               "refinement/threshold_xyvelocity_gradient=0.05"] + _2D + BLAST,
+    "adaptive_2d_maxdensity": ["parthenon/time/nlim=80", "parthenon/mesh/derefine_count=5",
+                               "refinement/type=maxdensity", "refinement/maxdensity_refine_above=1.3",
+                               "refinement/maxdensity_deref_below=1.1", "hydro/riemann=hllc"] + _2D + BLAST,
+})
+
+
 def run(overrides):
     with tempfile.TemporaryDirectory() as tmp:
         cmd = [BIN, "-i", DECK] + overrides + COMMON
@@ -104,15 +115,19 @@ def run(overrides):
 
 
 def main():
+    only = sys.argv[1:]  # (a subset of the cases: the others are kept from the existing file)
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        jobs = {k: ex.submit(run, ov) for k, ov in CASES.items()}
+        jobs = {k: ex.submit(run, ov) for k, ov in CASES.items() if not only or k in only}
     out = {"_provenance": "printed by the UNMODIFIED reference (Kokkos Serial, g++ -O3, no FMA) run by "
                           "tests/golden/make_amr_goldens.py; trace = [time, dt] per cycle at 17 digits, "
                           "blocks = [total, level 0, level 1, ...] per cycle, final = [blocks, created, destroyed]"}
     for k, f in jobs.items():
         out[k] = f.result()
         print(k, out[k]["ncycle"], out[k]["trace"][-1], out[k]["final"], len(out[k]["blocks"]), flush=True)
-    json.dump(out, open(os.path.join(HERE, "reference_traces_amr.json"), "w"), indent=0)
+    path = os.path.join(HERE, "reference_traces_amr.json")
+    if only:
+        out = dict(json.load(open(path)), **out)
+    json.dump(out, open(path, "w"), indent=0)
 
 
 if __name__ == "__main__":

@@ -40,10 +40,14 @@ class Params(C.Structure):
         ("rkl2_max_dt_ratio", C.c_double), ("conduction_sat_phi", C.c_double),
         ("adaptive", C.c_int), ("numlevel", C.c_int), ("derefine_count", C.c_int),
         ("refine_threshold", C.c_double),
+        ("refine_type", C.c_int), ("refine_threshold2", C.c_double),
     ]
 
 
 DIFFINT = {"none": 0, "unsplit": 1, "rkl2": 2}
+# <refinement> type; threshold = threshold_pressure_gradient / threshold_xyvelocity_gradient /
+# maxdensity_refine_above, threshold2 = maxdensity_deref_below
+REFINE_TYPE = {"pressure_gradient": 0, "xyvelocity_gradient": 1, "maxdensity": 2}
 CONDUCTION = {"none": 0, "isotropic": 1, "anisotropic": 2}
 
 
@@ -158,6 +162,8 @@ def make_params(fluid="euler", recon="plm", riemann="hlle", integrator="vl2", nx
         p.adaptive, p.numlevel = 1, adaptive["numlevel"]
         p.derefine_count = adaptive.get("derefine_count", 10)
         p.refine_threshold = adaptive["threshold"]
+        p.refine_type = REFINE_TYPE[adaptive.get("type", "pressure_gradient")]
+        p.refine_threshold2 = adaptive.get("threshold2", 0.0)
     p.nref = len(refine)
     for r, (lev, lo, hi) in enumerate(refine):
         p.ref_level[r] = lev

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(apk):
         assert hasattr(L, n), n
     assert set(declared("apk_b200.h")) == set(apk.ABI_SYMBOLS)
     assert set(declared("apk_b200_sim.h")) == set(apk.SIM_SYMBOLS)
-    assert L.apk_abi_version() == 4
+    assert L.apk_abi_version() == 5
 
 
 def test_struct_layouts_match_c(apk, tmp_path):

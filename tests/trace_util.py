@@ -119,10 +119,11 @@ _BLAST_OFF = [0.12, 0.1, 100.0, 1.0, 0.22, 0.1, -0.05]
 
 
 def _adaptive(fluid, recon, rs, ng, numlevel, threshold=0.1, derefine_count=10, nx=(32, 32, 32),
-              mb=(8, 8, 8)):
+              mb=(8, 8, 8), **criterion):
     return (dict(fluid=fluid, nx=nx, mb=mb, ng=ng, xmin=(-0.5,) * 3, xmax=(0.5,) * 3,
                  gamma=GAMMA_DECK, cfl=0.3, recon=recon, riemann=rs, integrator="vl2",
-                 adaptive=dict(numlevel=numlevel, threshold=threshold, derefine_count=derefine_count)),
+                 adaptive=dict(numlevel=numlevel, threshold=threshold, derefine_count=derefine_count,
+                               **criterion)),
             "blast", _BLAST_OFF, 0.1)
 
 
@@ -131,6 +132,12 @@ ADAPTIVE_DECKS = {
     "adaptive_3d_wenoz_hlld": _adaptive("glmmhd", "wenoz", "hlld", 4, 3),
     "adaptive_2d_plm_hllc": _adaptive("euler", "plm", "hllc", 2, 4, threshold=0.2, derefine_count=3,
                                       nx=(64, 64, 1), mb=(8, 8, 1)),
+    # the other <refinement> criteria: x1-x2 velocity gradient, maximum density
+    "adaptive_2d_xyvelocity": _adaptive("euler", "plm", "hlle", 2, 3, threshold=0.05, derefine_count=5,
+                                        nx=(64, 64, 1), mb=(8, 8, 1), type="xyvelocity_gradient"),
+    "adaptive_2d_maxdensity": _adaptive("euler", "plm", "hllc", 2, 3, threshold=1.3, derefine_count=5,
+                                        nx=(64, 64, 1), mb=(8, 8, 1), type="maxdensity",
+                                        threshold2=1.1),
 }
 
 
