@@ -591,7 +591,7 @@ void HydroSim::ArenaBegin(double growth) {
   if (A.cap < need) {
     cudaFree(A.base);
     A.base = nullptr;
-    A.cap = need + need / 2;
+    A.cap = 2 * need;  // (a growing mesh regrows an arena rarely: cudaMalloc of GBs costs tens of ms)
     cuda_check(cudaMalloc(reinterpret_cast<void **>(&A.base), A.cap), "cudaMalloc mesh arena");
   }
   A.used = A.want = 0;
