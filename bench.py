@@ -12,6 +12,7 @@ ghost exchange, dt reduction).
   python bench.py --impl reference ...                      # reference arm: the UNMODIFIED reference,
                                                             # Kokkos-Serial build, one copy per core
   python bench.py --config ot2d                             # BASELINE config 3 (Orszag-Tang, FOFC on)
+  python bench.py --config blast_amr --steps 40             # BASELINE config 5 (adaptive AMR blast)
 
 Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the byte model.
 """
@@ -516,6 +517,72 @@ def run_product(args):
         dist.destroy_process_group()
 
 
+def run_blast_amr(args):
+    """--config blast_amr: BASELINE config 5 as the reference runs it (baseline/decks/blast_amr.in:
+    inputs/blast_3d_amr.in with refinement = adaptive, GLM-MHD WENOZ + HLLD, nghost 4, 3 levels) on
+    ONE GPU.  A parity-test configuration, not the headline; metric = Parthenon's zone-cycles per
+    wall second including tagging and remeshing, with the unmodified reference beside it: its
+    Kokkos-Serial build timed here on one host core (bounded: 6 cycles) and its Kokkos-CUDA build on
+    the same B200 (static record, profiles/reference_cuda_vs_b200_config5_r02.json)."""
+    import torch
+    import athenapk_b200 as apk
+    assert args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1, "blast_amr runs on one GPU"
+    torch.cuda.set_device(0)
+    g = float("1.666666666666667")
+    kw = dict(fluid="glmmhd", recon="wenoz", riemann="hlld", integrator="vl2", nx=(32, 32, 32),
+              mb=(8, 8, 8), ng=4, xmin=(-0.5,) * 3, xmax=(0.5,) * 3, gamma=g, cfl=0.3,
+              adaptive=dict(numlevel=3, threshold=0.1, derefine_count=10))
+    sim = apk.HydroSim(fp_mode=args.fp_mode, **kw)
+    sim.pgen("blast", (0.12, 0.1, 100.0, 1.0, 0.22, 0.1, -0.05))
+    sim.initialize(0.1)
+    nb0 = sim.nblocks
+    sim.execute(0.1, args.warmup)
+    sim.synchronize()
+    apk.reset_launch_count()
+    n_pre, ms_pre = sim.amr_timing()
+    sampler = ClockSampler(0).start()
+    zones, t0 = 0, time.time()
+    for c in range(args.warmup, args.warmup + args.steps):
+        zones += sim.nblocks * 512
+        sim.execute(0.1, c + 1)
+    sim.synchronize()
+    sec = time.time() - t0
+    clocks = sampler.stop()
+    launches = apk.launch_count()
+    n_amr, ms_amr = sim.amr_timing()
+    created, destroyed, per_level = sim.amr_counts()
+    value = zones / sec
+    line = {"metric": "zone-cycles/sec, adaptive AMR blast (BASELINE config 5: WENOZ+HLLD, 3 levels)",
+            "value": value, "unit": "zone-cycles/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3 / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "baseline/decks/blast_amr.in: 32^3 root grid, 8^3 meshblocks, 3 levels, "
+                                   "refinement = adaptive (pressure gradient), GLM-MHD VL2+WENOZ+HLLD, "
+                                   "nghost 4; tagging + remeshing inside the timed region (host wall clock)",
+                       "fp_mode": args.fp_mode, "fused": False, "blocks_start": nb0,
+                       "blocks_end": sim.nblocks, "created": created, "destroyed": destroyed,
+                       "per_level": per_level[:3], "remeshes": n_amr - n_pre,
+                       "l2": "state (200 MB) > 126 MB L2"},
+            "amr_host_ms_per_cycle": {k: (ms_amr[k] - ms_pre[k]) / args.steps for k in ms_amr},
+            "gpu_launches": launches, "clocks": clocks, "roofline": None, "e2e": None}
+    ref = os.path.join(ROOT, "profiles", "reference_cuda_vs_b200_config5_r02.json")
+    if os.path.exists(ref):
+        r = json.load(open(ref))["reference_kokkos_cuda_sm100"]
+        line["reference_cuda"] = {"value": r["zone_cycles_per_s_steady"], "unit": "zone-cycles/s",
+                                  "source": "static: profiles/reference_cuda_vs_b200_config5_r02.json"}
+    sim.close()
+    if not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import run_reference as rr
+        if rr.available("serial"):
+            res = rr.run("serial", "blast_amr", 32, 8, 6, cpu=0)
+            line["cpu_baseline"] = {"value": res["zone_cycles_per_wallsecond"], "unit": "zone-cycles/s",
+                                    "cores": 1, "kind": "reference",
+                                    "sample": "baseline/_ref/serial/bin/athenaPK on the same deck, 6 "
+                                              "cycles, 1 core, %.0f s" % res["wall_s"]}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -527,8 +594,9 @@ def main():
     ap.add_argument("--pgen", default="orszag_tang", choices=["orszag_tang", "uniform", "ot3d", "random"],
                     help="orszag_tang (default) and uniform are decks the reference runs too "
                          "(baseline/decks); ot3d / random are closed-form states of this repo")
-    ap.add_argument("--config", default="uni256", choices=["uni256", "ot2d"],
-                    help="uni256: BASELINE config 4 (headline); ot2d: config 3, 2-D Orszag-Tang + FOFC")
+    ap.add_argument("--config", default="uni256", choices=["uni256", "ot2d", "blast_amr"],
+                    help="uni256: BASELINE config 4 (headline); ot2d: config 3, 2-D Orszag-Tang + FOFC; "
+                         "blast_amr: config 5, adaptive AMR blast (one GPU)")
     ap.add_argument("--recon", default="ppm", choices=["ppm", "wenoz", "plm", "weno3", "limo3"],
                     help="reconstruction of the corrector stage (headline metric: ppm)")
     ap.add_argument("--fp-mode", dest="fp_mode", default="fast", choices=["fast", "strict"])
@@ -542,6 +610,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "blast_amr":
+        run_blast_amr(args)
     else:
         run_product(args)
 

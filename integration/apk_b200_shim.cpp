@@ -17,6 +17,7 @@
 //   B200::FusedStage                         calc_flux + update + source + fill_derived in one task
 //   B200::StartHalo / TestHalo / FinishHalo  the three tasks of AddBoundaryExchangeTasks
 //                                            (bvals/comms/boundary_communication.cpp:405-445)
+//   B200::CheckRefinementMesh<criterion>     pkg->CheckRefinementMesh (state_descriptor.hpp:396-397)
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -378,6 +379,33 @@ TaskStatus FinishHalo(std::shared_ptr<MeshData<Real>> &md) {
   return TaskStatus::complete;
 }
 
+// ---- refinement tagging: pkg->CheckRefinementMesh (interface/state_descriptor.hpp:396-397, called
+// by Refinement::CheckAllRefinement(md), amr_criteria/refinement_package.cpp:53-68) instead of the
+// per-block CheckRefinementBlock functions of src/refinement (hydro.cpp:788-816): ONE launch tags
+// every block of the MeshData.  AmrTag is an int-sized enum (basic_types.hpp:64), so the kernel
+// writes the tag array in place; Parthenon's scatter-max semantics (tags start at `derefine`, a
+// criterion can only raise them) hold because this is the only criterion of the Hydro package.
+template <int CRITERION>
+void CheckRefinementMesh(MeshData<Real> *md, parthenon::ParArray1D<parthenon::AmrTag> &delta_level) {
+  PackCache &c = GetCache(md, nullptr);
+  auto pkg = md->GetBlockData(0)->GetBlockPointer()->packages.Get("Hydro");
+  static_assert(sizeof(parthenon::AmrTag) == sizeof(int), "AmrTag is stored as int");
+  double above, below;
+  if (CRITERION == APK_REFINE_PRESSURE_GRADIENT) {
+    above = pkg->Param<Real>("refinement/threshold_pressure_gradient");
+    below = 0.25 * above;  // gradient.cpp:59
+  } else if (CRITERION == APK_REFINE_XYVELOCITY_GRADIENT) {
+    above = pkg->Param<Real>("refinement/threshold_xyvelocity_gradient");
+    below = 0.5 * above;   // gradient.cpp:92
+  } else {
+    above = pkg->Param<Real>("refinement/maxdensity_refine_above");
+    below = pkg->Param<Real>("refinement/maxdensity_deref_below");
+  }
+  parthenon::ParArray1D<double> measure("apk_refinement_measure", md->NumBlocks());
+  Check(apk_tag_refinement(&c.desc, c.d_blocks.data(), CRITERION, above, below,
+                           reinterpret_cast<int *>(delta_level.data()), measure.data(), Stream()));
+}
+
 // ---- registration (called from Hydro::Initialize instead of the flux_functions lookup,
 // hydro.cpp:381-480, and the FillDerivedMesh / EstimateTimestepMesh assignments :707-713)
 void Register(parthenon::StateDescriptor *pkg, const bool vl2, const bool extended_dedner) {
@@ -391,6 +419,17 @@ void Register(parthenon::StateDescriptor *pkg, const bool vl2, const bool extend
   using SourceFun_t = std::function<void(MeshData<Real> *, const Real)>;
   SourceFun_t src = extended_dedner ? SourceFun_t(DednerSource<true>) : SourceFun_t(DednerSource<false>);
   pkg->AddParam<SourceFun_t>("apk_b200_glmmhd_source", src);
+  // <refinement> type (hydro.cpp:788-816): the mesh-level hook replaces CheckRefinementBlock
+  if (pkg->AllParams().hasKey("refinement/threshold_pressure_gradient")) {
+    pkg->CheckRefinementBlock = nullptr;
+    pkg->CheckRefinementMesh = CheckRefinementMesh<APK_REFINE_PRESSURE_GRADIENT>;
+  } else if (pkg->AllParams().hasKey("refinement/threshold_xyvelocity_gradient")) {
+    pkg->CheckRefinementBlock = nullptr;
+    pkg->CheckRefinementMesh = CheckRefinementMesh<APK_REFINE_XYVELOCITY_GRADIENT>;
+  } else if (pkg->AllParams().hasKey("refinement/maxdensity_refine_above")) {
+    pkg->CheckRefinementBlock = nullptr;
+    pkg->CheckRefinementMesh = CheckRefinementMesh<APK_REFINE_MAXDENSITY>;
+  }
 }
 
 }  // namespace Hydro::B200
