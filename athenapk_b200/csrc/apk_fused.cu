@@ -926,6 +926,29 @@ k_stage_fused(ApkGeom g, const apk_block_t *__restrict__ blocks, double *const *
   }
 }
 
+// x3 chunks (blockIdx.z): the march of a tile along x3 is cut into `c` chunks so that small packs
+// (strong scaling: 64 meshblocks per GPU at 8 GPUs) fill every SM for several waves; a chunk re-does
+// one x3 reconstruction plane and one face row of its lower neighbour.  Rule fitted to measurements
+// on one B200 with 32^3 meshblocks (ms per cycle; T = tiles, 444 resident CTA slots):
+//   T =  512 (8-GPU share of 256^3): c = 2: ~1.30   4: 1.209   5: 1.239   6: 1.235   8: 1.248
+//   T = 1000 (~4-GPU share):         c = 2: 2.659   4: 2.661   8: 2.795
+//   T = 1728 (~2-GPU share):         c = 1: 4.411   2: 4.369   4: 4.430
+//   T = 4096 (one GPU):              c = 2: 8.599   3: 8.698
+// -> equal chunks only (c divides nx3; 3, 5, 6 chunks of 32 planes are unequal and slower), at least
+// 8 planes per chunk, at least 2 chunks when that allows, and the smallest such c that gives
+// >= 7.5 waves of CTAs (else the largest).  The previous rule chose 8 chunks for T <= 1024
+// (3-5 % slower).  APK_B200_KCHUNKS overrides.
+inline int pick_x3_chunks(long tiles, long slots, int nx3) {
+  static const char *env = std::getenv("APK_B200_KCHUNKS");
+  if (env && std::atoi(env) > 0) return std::min(std::atoi(env), nx3);
+  int cmax = 1;
+  for (int c = 2; c <= 8; c *= 2)
+    if (nx3 % c == 0 && nx3 / c >= 8) cmax = c;
+  for (int c = (cmax >= 2 ? 2 : 1); c < cmax; c *= 2)
+    if (2 * tiles * c >= 15 * slots) return c;
+  return cmax;
+}
+
 template <int FLUID, int RECON, int RS, int NS = 0>
 int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blocks,
               double *const *prim_out, const apk_stage_args_t &a, double coeff, cudaStream_t s) {
@@ -939,22 +962,7 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
   const RsPars rsp = {d.gamma, 1.0 / (d.gamma - 1.0), c_h, 0.5 / c_h};
   const int ntx = (d.nx[0] + TX - 1) / TX;
   const int nty = (g.ndim >= 2) ? (d.nx[1] + TY - 1) / TY : 1;
-  // x3 chunks: aim for >= 16 waves of CTAs (tail < 6 %) while chunks stay >= 4 planes (measured at
-  // 64 meshblocks per GPU, the 8-GPU share of 256^3: 2 chunks 1.67 ms per cycle, 4 chunks 1.54 ms)
   const int sm_count = apk_common::sm_count();
-  int nchunk = 1;
-  if (g.ndim == 3) {
-    static const char *env = std::getenv("APK_B200_KCHUNKS");
-    if (env && std::atoi(env) > 0) {
-      nchunk = std::min(std::atoi(env), d.nx[2]);
-    } else {
-      const long slots = (long)sm_count * APK_FUSED_MINBLOCKS;
-      while (nchunk < 8 && (long)ntx * nty * g.nb * nchunk < 16 * slots &&
-             d.nx[2] / (nchunk * 2) >= 4)
-        nchunk *= 2;
-    }
-  }
-  dim3 grid(ntx * nty, g.nb, nchunk);
   constexpr bool DC = (RECON == APK_RECON_DC);
   static_assert(!DC || 3 * (sizeof(Smem<9, 3, DC>) + 1024) <= 233472 || APK_FUSED_MINBLOCKS < 3 ||
                     TY != 4, "DC stage must keep 3 CTAs per SM");
@@ -970,6 +978,16 @@ int run_fused(const apk_pack_desc_t &d, const ApkGeom &g, const apk_block_t *blo
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
       if (dev < 64) attr_set |= 1ULL << dev;                                                     \
     }                                                                                            \
+    static int occ_cache[64] = {0};                                                              \
+    int occ = (dev < 64) ? occ_cache[dev] : 0;                                                   \
+    if (occ == 0) {                                                                              \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NTHREADS, smem);                 \
+      if (occ < 1) occ = 1;                                                                      \
+      if (dev < 64) occ_cache[dev] = occ;                                                        \
+    }                                                                                            \
+    const int nchunk = (ND == 3) ? pick_x3_chunks((long)ntx * nty * g.nb, (long)sm_count * occ,  \
+                                                  d.nx[2]) : 1;                                  \
+    dim3 grid(ntx * nty, g.nb, nchunk);                                                          \
     kern<<<grid, NTHREADS, smem, s>>>(g, blocks, prim_out, g0, g1, bdt, rsp, coeff, eos,         \
                                       ntx, flags, dt, push, nchunk, a.d_status,                  \
                                       a.d_fofc_count,                                            \
