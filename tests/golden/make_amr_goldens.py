@@ -97,9 +97,20 @@ CASES.update({
 })
 
 
-def run(overrides):
+# GLM-MHD with B != 0 on an adaptive mesh: the Orszag-Tang vortex (inputs/orszag_tang.in, FOFC on)
+# -- c_h = cfl * mindx / dt_hyp follows the finest level after every remesh (hydro.cpp:102-143)
+CASES["adaptive_2d_orszag_tang_mhd"] = [
+    "parthenon/mesh/refinement=adaptive", "parthenon/mesh/numlevel=3", "parthenon/mesh/derefine_count=5",
+    "parthenon/mesh/nx1=64", "parthenon/mesh/nx2=64", "parthenon/meshblock/nx1=8",
+    "parthenon/meshblock/nx2=8", "parthenon/mesh/nghost=4", "parthenon/time/nlim=60",
+    "parthenon/output0/dt=-1", "parthenon/output1/dt=-1", "refinement/type=pressure_gradient",
+    "refinement/threshold_pressure_gradient=0.05"]
+DECK_OF = {"adaptive_2d_orszag_tang_mhd": "/root/reference/inputs/orszag_tang.in"}
+
+
+def run(overrides, deck=DECK):
     with tempfile.TemporaryDirectory() as tmp:
-        cmd = [BIN, "-i", DECK] + overrides + COMMON
+        cmd = [BIN, "-i", deck] + overrides + COMMON
         p = subprocess.run(cmd, cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if p.returncode != 0:
             raise RuntimeError(" ".join(cmd) + "\n" + p.stdout[-2000:])
@@ -117,7 +128,8 @@ def run(overrides):
 def main():
     only = sys.argv[1:]  # (a subset of the cases: the others are kept from the existing file)
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        jobs = {k: ex.submit(run, ov) for k, ov in CASES.items() if not only or k in only}
+        jobs = {k: ex.submit(run, ov, DECK_OF.get(k, DECK)) for k, ov in CASES.items()
+                if not only or k in only}
     out = {"_provenance": "printed by the UNMODIFIED reference (Kokkos Serial, g++ -O3, no FMA) run by "
                           "tests/golden/make_amr_goldens.py; trace = [time, dt] per cycle at 17 digits, "
                           "blocks = [total, level 0, level 1, ...] per cycle, final = [blocks, created, destroyed]"}

@@ -141,6 +141,12 @@ ADAPTIVE_DECKS = {
 }
 
 
+# GLM-MHD with B != 0 on an adaptive mesh: inputs/orszag_tang.in (FOFC on) with refinement = adaptive
+ADAPTIVE_DECKS["adaptive_2d_orszag_tang_mhd"] = (
+    dict(fluid="glmmhd", nx=(64, 64, 1), mb=(8, 8, 1), ng=4, xmin=(-0.5,) * 3, xmax=(0.5,) * 3,
+         gamma=GAMMA_DECK, cfl=0.4, recon="ppm", riemann="hlld", integrator="vl2", fofc=True,
+         adaptive=dict(numlevel=3, threshold=0.05, derefine_count=5)), "orszag_tang", [], 1.0)
+
 # refined meshes on non-periodic domains (physical BCs on coarse buffers and blocks)
 _OUT4 = ["outflow"] * 4 + ["periodic"] * 2
 BOUNDARY_AMR_DECKS = {
