@@ -106,6 +106,19 @@ CASES["adaptive_2d_orszag_tang_mhd"] = [
     "parthenon/output0/dt=-1", "parthenon/output1/dt=-1", "refinement/type=pressure_gradient",
     "refinement/threshold_pressure_gradient=0.05"]
 DECK_OF = {"adaptive_2d_orszag_tang_mhd": "/root/reference/inputs/orszag_tang.in"}
+# a three-stage integrator (flux correction and multilevel exchange in every stage) and RKL2 super
+# time stepping (every sub-step through the exchange) on adaptive meshes
+CASES.update({
+    "adaptive_2d_rk3_weno3_hllc": ["parthenon/time/nlim=40", "parthenon/time/integrator=rk3",
+                                   "hydro/reconstruction=weno3", "hydro/riemann=hllc",
+                                   "parthenon/mesh/derefine_count=4"] + _2D + BLAST,
+    "adaptive_2d_rkl2_diffusion": ["parthenon/time/nlim=30", "parthenon/mesh/derefine_count=4",
+                                   "diffusion/integrator=rkl2", "diffusion/conduction=isotropic",
+                                   "diffusion/conduction_coeff=fixed",
+                                   "diffusion/thermal_diff_coeff_code=0.02",
+                                   "diffusion/viscosity=isotropic", "diffusion/viscosity_coeff=fixed",
+                                   "diffusion/mom_diff_coeff_code=0.03"] + _2D + BLAST,
+})
 
 
 def run(overrides, deck=DECK):

@@ -147,6 +147,15 @@ ADAPTIVE_DECKS["adaptive_2d_orszag_tang_mhd"] = (
          gamma=GAMMA_DECK, cfl=0.4, recon="ppm", riemann="hlld", integrator="vl2", fofc=True,
          adaptive=dict(numlevel=3, threshold=0.05, derefine_count=5)), "orszag_tang", [], 1.0)
 
+# a three-stage integrator and RKL2 super time stepping on adaptive meshes
+_A2D = dict(fluid="euler", nx=(64, 64, 1), mb=(8, 8, 1), ng=2, xmin=(-0.5,) * 3, xmax=(0.5,) * 3,
+            gamma=GAMMA_DECK, cfl=0.3, adaptive=dict(numlevel=3, threshold=0.1, derefine_count=4))
+ADAPTIVE_DECKS["adaptive_2d_rk3_weno3_hllc"] = (
+    dict(_A2D, recon="weno3", riemann="hllc", integrator="rk3"), "blast", _BLAST_OFF, 0.1)
+ADAPTIVE_DECKS["adaptive_2d_rkl2_diffusion"] = (
+    dict(_A2D, recon="plm", riemann="hlle", integrator="vl2", diffint="rkl2", conduction="isotropic",
+         thermal_diff_coeff=0.02, viscosity="isotropic", mom_diff_coeff=0.03), "blast", _BLAST_OFF, 0.1)
+
 # refined meshes on non-periodic domains (physical BCs on coarse buffers and blocks)
 _OUT4 = ["outflow"] * 4 + ["periodic"] * 2
 BOUNDARY_AMR_DECKS = {
