@@ -371,6 +371,28 @@ def test_static_refinement_reference_traces(apk, name):
     s.close()
 
 
+@pytest.mark.parametrize("res", [16, 32])
+def test_reference_regression_diffusion_linwave3d(apk, res):
+    """the reference's own regression case tst/regression/test_suites/diffusion_linwave3d on the
+    GPU (strict mode): the history file the unmodified reference wrote -- 201 rows over three wave
+    periods, 427 / 1093 cycles -- row by row at every printed digit of time, dt, mass, KE, tot-E,
+    ME and MaxAbsV2, and the test's own acceptance criterion (fitted decay rate of the slow mode
+    within 22 % / 5 % of the analytic value); FMA mode passes the criterion too."""
+    import diffusion_linwave_util as dl
+    kw, pgen, pars = dl.deck(res)
+    for fp_mode in ("strict", "fast"):
+        s = apk.HydroSim(fp_mode=fp_mode, **kw)
+        s.pgen(pgen, pars)
+        tlim = 3.0 * s.lw_tlim
+        s.initialize(tlim)
+        rows = dl.history_rows(s, tlim, lambda s, t, c: s.execute(t, c), lambda s: s.history(),
+                               lambda s: np.abs(s.get("prim", 0)[2][2:-2, 2:-2, 2:-2]).max())
+        if fp_mode == "strict":
+            dl.check_rows(rows, dl.reference_rows(res))
+        assert dl.decay_rate_error(rows) <= dl.REL_TOL[res]
+        s.close()
+
+
 def test_history_file_matches_reference(apk, tmp_path):
     """`file_type = hst` (outputs/history.cpp:172-209, scheduling outputs.cpp:445-485): the history
     file written during a 50-cycle Orszag-Tang run (config 3, FOFC on, output every 0.005) equals the

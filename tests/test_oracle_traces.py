@@ -124,6 +124,25 @@ def test_refined_meshes_with_physical_boundaries(name):
     assert o.ncycle == case["ncycle"]
 
 
+def test_reference_regression_diffusion_linwave3d():
+    """the reference's own regression case diffusion_linwave3d at N = 16 (see
+    tests/diffusion_linwave_util.py): its history file row by row, and its acceptance criterion"""
+    import numpy as np
+    import diffusion_linwave_util as dl
+    kw, pgen, pars = dl.deck(16)
+    o = Oracle(**kw)
+    o.pgen(pgen, pars)
+    tlim = 3.0 * o.lw_tlim
+    o.initialize(tlim)
+    rows = dl.history_rows(o, tlim, advance, lambda o: o.history(),
+                           lambda o: np.abs(o.prim(0)[2][2:-2, 2:-2, 2:-2]).max())
+    dl.check_rows(rows, dl.reference_rows(16))
+    assert o.ncycle == 427
+    assert dl.decay_rate_error(rows) <= dl.REL_TOL[16]
+    assert dl.decay_rate_error(dl.reference_rows(16)) <= dl.REL_TOL[16]
+    assert dl.decay_rate_error(dl.reference_rows(32)) <= dl.REL_TOL[32]
+
+
 @pytest.mark.parametrize("name", sorted(DIFF_DECKS))
 def test_diffusion_traces(name):
     """<diffusion> block: unsplit and RKL2 super-time-stepping integration of thermal
