@@ -50,11 +50,19 @@ def history_rows(engine, tlim, advance, history, max_abs_v2, dt_out=0.03):
     return [[x.strip() for x in r] for r in rows]
 
 
-def check_rows(rows, ref):
+def check_rows(rows, ref, sums_last_digit=False):
+    """sums_last_digit: the volume sums may differ by one unit of the last printed digit -- the
+    device reducers add in another order than the reference's serial loop, and tot-E of this deck
+    (17.04375...) sits on a rounding boundary of the 6-digit format.  time, dt, cycle and MaxAbsV2
+    (a maximum: order independent) are always compared as printed."""
     assert len(rows) == len(ref)
-    cols = [0, 1, 2, 3, 4, 8, 9, 10, 12]  # time dt cycle nbtotal mass KE tot-E ME MaxAbsV2
+    exact = [0, 1, 2, 3, 12] if sums_last_digit else [0, 1, 2, 3, 4, 8, 9, 10, 12]
+    sums = [4, 8, 9, 10] if sums_last_digit else []  # mass KE tot-E ME
     for g, r in zip(rows, ref):
-        assert [g[c] for c in cols] == [r[c] for c in cols], (g, r)
+        assert [g[c] for c in exact] == [r[c] for c in exact], (g, r)
+        for c in sums:
+            a, b = float(g[c]), float(r[c])
+            assert abs(a - b) <= 1.01e-5 * 10.0 ** np.floor(np.log10(abs(b))), (c, g, r)
 
 
 def decay_rate_error(rows):
