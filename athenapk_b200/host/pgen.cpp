@@ -239,7 +239,8 @@ int HydroSim::ProblemGenerator(const std::string &id, const std::vector<double> 
   }
   const bool known = id == "linear_wave" || id == "linear_wave_mhd" || id == "sod" ||
                      id == "orszag_tang" ||
-                     id == "uniform" || id == "ot3d" || id == "random" || id == "blast";
+                     id == "uniform" || id == "ot3d" || id == "random" || id == "blast" ||
+                     id == "lw_implode";
   if (!known) return -1;
   if (id == "orszag_tang" && !mhd) return -2;
   if (&pars != &pgen_pars_) {  // adaptive meshes re-run the generator while Mesh::Initialize refines
@@ -325,6 +326,23 @@ int HydroSim::ProblemGenerator(const std::string &id, const std::vector<double> 
               eb = 0.5 * (SQR(U(IB1)) + SQR(U(IB2)) + SQR(U(IB3)));
             }
             U(IEN) = p0 / gm1 + 0.5 * d0 * (SQR(v1) + SQR(v2) + SQR(v3)) + eb;
+          } else if (id == "lw_implode") {  // lw_implode.cpp:34-75 (Liska-Wendroff implosion)
+            const double d_in = par(0, 0.125), p_in = par(1, 0.14), d_out = par(2, 1.0),
+                         p_out = par(3, 1.0);
+            // y0 between cell centres so that the initial state is symmetric (:47-60)
+            double y0 = 0.5 * (cfg_.xmax[1] + cfg_.xmin[1]);
+            for (int jj = js; jj < js + cfg_.mb[1]; ++jj)
+              if (xc(B, 1, jj) > y0) {
+                y0 = (B.xmin[1] + jj * B.dx[1]) + 0.5 * B.dx[1];
+                break;
+              }
+            if (xc(B, 1, j) > (y0 - xc(B, 0, i))) {
+              U(IDN) = d_out;
+              U(IEN) = p_out / gm1;
+            } else {
+              U(IDN) = d_in;
+              U(IEN) = p_in / gm1;
+            }
           } else if (id == "blast") {
             const double rad = par(0, 0.1), pa = par(1, 0.1), prat = par(2, 100.0), da = par(3, 1.0);
             const double x = xc(B, 0, i), y = (ndim_ > 1) ? xc(B, 1, j) : 0.0,

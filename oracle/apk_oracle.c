@@ -3256,6 +3256,25 @@ int apko_pgen(apko_engine *e, int id, const double *pars, int npars) {
             }
             U(IEN) = p0 / gm1 + 0.5 * d0 * (SQR(v1) + SQR(v2) + SQR(v3)) + eb;
           } break;
+          case APKO_PGEN_LW_IMPLODE: { /* src/pgen/lw_implode.cpp:34-75 (Liska-Wendroff implosion);
+                                          pars = d_in, p_in, d_out, p_out */
+            const double d_in = npars > 0 ? pars[0] : 0.125, p_in = npars > 1 ? pars[1] : 0.14;
+            const double d_out = npars > 2 ? pars[2] : 1.0, p_out = npars > 3 ? pars[3] : 1.0;
+            /* y0 between cell centres so that the initial state is symmetric (:47-60) */
+            double y0 = 0.5 * (p->xmax[1] + p->xmin[1]);
+            for (int jj = e->is[1]; jj <= e->ie[1]; jj++)
+              if (xc(B, 1, jj) > y0) {
+                y0 = (B->xmin[1] + jj * B->dx[1]) + 0.5 * B->dx[1];
+                break;
+              }
+            if (xc(B, 1, j) > (y0 - xc(B, 0, i))) {
+              U(IDN) = d_out;
+              U(IEN) = p_out / gm1;
+            } else {
+              U(IDN) = d_in;
+              U(IEN) = p_in / gm1;
+            }
+          } break;
           case APKO_PGEN_BLAST: { /* src/pgen/blast.cpp (spherical over-pressure; B=0);
                                      pars = radius, pamb, prat, damb */
             double rad = npars > 0 ? pars[0] : 0.1, pa = npars > 1 ? pars[1] : 0.1;

@@ -371,6 +371,36 @@ def test_static_refinement_reference_traces(apk, name):
     s.close()
 
 
+def test_reference_regression_lw_implode_symmetry(apk):
+    """the reference's regression case lw_implode_symmetry (tst/regression/CMakeLists.txt:73-74,
+    inputs/lw_implode.in as it is: Liska-Wendroff implosion, 256^2 in one meshblock, reflecting
+    walls, VL2 + PLM + HLLC, t = 2.5, ~10^4 cycles) through the fused stage kernel: the (time, dt)
+    the unmodified reference printed every 500th cycle and at the end, at 17 digits (strict mode),
+    the same final cycle count, and the case's own criterion -- max relative asymmetry of the
+    density under transposition <= 1e-11 (lw_implode_symmetry.py:56-61) -- in strict and FMA mode."""
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden",
+                                       "reference_traces_lw_implode.json")))["n256"]
+    kw = dict(fluid="euler", nx=(256, 256, 1), ng=3, xmin=(0.0, 0.0, -0.5), xmax=(0.3, 0.3, 0.5),
+              gamma=1.4, cfl=0.4, recon="plm", riemann="hllc", integrator="vl2",
+              bc=["reflecting"] * 4 + ["periodic"] * 2)
+    for fp_mode in ("strict", "fast"):
+        s = apk.HydroSim(fp_mode=fp_mode, **kw)
+        s.pgen("lw_implode", [])
+        s.initialize(2.5)
+        assert s.fused_active
+        if fp_mode == "strict":
+            for cyc, t, dt in case["samples"]:
+                s.execute(2.5, cyc)
+                assert ("%.16e" % s.time, "%.16e" % s.dt) == (t, dt), cyc
+            assert s.ncycle == case["ncycle"]
+        else:
+            s.execute(2.5, -1)
+            assert abs(s.ncycle - case["ncycle"]) <= 2
+        rho = s.get("prim", 0)[0][0, 3:-3, 3:-3]
+        assert np.max(2 * np.abs(rho - rho.T) / (rho + rho.T)) <= 1e-11, fp_mode
+        s.close()
+
+
 @pytest.mark.parametrize("res", [16, 32])
 def test_reference_regression_diffusion_linwave3d(apk, res):
     """the reference's own regression case tst/regression/test_suites/diffusion_linwave3d on the

@@ -124,6 +124,26 @@ def test_refined_meshes_with_physical_boundaries(name):
     assert o.ncycle == case["ncycle"]
 
 
+def test_reference_regression_lw_implode_64():
+    """the deck of the reference's regression case lw_implode_symmetry (inputs/lw_implode.in:
+    Liska-Wendroff implosion, reflecting walls, VL2 + PLM + HLLC) at 64^2: 300 cycles of the
+    reference's (time, dt) at 17 digits, and the property the case asserts -- density symmetric
+    under transposition (lw_implode_symmetry.py:56-61; here exactly, the oracle has no FMA)"""
+    import json
+    import os
+    import numpy as np
+    case = json.load(open(os.path.join(os.path.dirname(__file__), "golden",
+                                       "reference_traces_lw_implode.json")))["n64"]
+    o = Oracle(fluid="euler", nx=(64, 64, 1), ng=3, xmin=(0.0, 0.0, -0.5), xmax=(0.3, 0.3, 0.5),
+               gamma=1.4, cfl=0.4, recon="plm", riemann="hllc", integrator="vl2",
+               bc=["reflecting"] * 4 + ["periodic"] * 2)
+    o.pgen("lw_implode", [])
+    o.initialize(2.5)
+    follow_trace(o, case["trace"], 2.5, advance)
+    rho = o.prim(0)[0][0, 3:-3, 3:-3]
+    assert np.max(2 * np.abs(rho - rho.T) / (rho + rho.T)) == 0.0
+
+
 def test_reference_regression_diffusion_linwave3d():
     """the reference's own regression case diffusion_linwave3d at N = 16 (see
     tests/diffusion_linwave_util.py): its history file row by row, and its acceptance criterion"""
