@@ -240,7 +240,8 @@ int HydroSim::ProblemGenerator(const std::string &id, const std::vector<double> 
   const bool known = id == "linear_wave" || id == "linear_wave_mhd" || id == "sod" ||
                      id == "orszag_tang" ||
                      id == "uniform" || id == "ot3d" || id == "random" || id == "blast" ||
-                     id == "lw_implode";
+                     id == "lw_implode" || id == "diffusion";
+  if (id == "diffusion" && !mhd && (int)par(0, 20) != 30) return -2;  // diffusion.cpp:35-37
   if (!known) return -1;
   if (id == "orszag_tang" && !mhd) return -2;
   if (&pars != &pgen_pars_) {  // adaptive meshes re-run the generator while Mesh::Initialize refines
@@ -326,6 +327,49 @@ int HydroSim::ProblemGenerator(const std::string &id, const std::vector<double> 
               eb = 0.5 * (SQR(U(IB1)) + SQR(U(IB2)) + SQR(U(IB3)));
             }
             U(IEN) = p0 / gm1 + 0.5 * d0 * (SQR(v1) + SQR(v2) + SQR(v3)) + eb;
+          } else if (id == "diffusion") {  // src/pgen/diffusion.cpp:28-158
+            // pars = iprob, Bx, By, t0, amp, diffusion coefficient of the process under test
+            const int iprob = (int)par(0, 20);
+            const double Bx = par(1, 0.0), By = par(2, 0.0), t0 = par(3, 0.5), amp = par(4, 1e-6),
+                         dc = par(5, 0.0);
+            const double X = xc(B, 0, i), Y = xc(B, 1, j), Z = xc(B, 2, k);
+            double eint = -1.0;
+            U(IDN) = 1.0;
+            if (iprob == 0) {         // step functions along x1 / x2 / x3
+              U(IB1) = Bx; U(IB2) = By;
+              eint = X <= 0.0 ? 10.0 : 12.0;
+            } else if (iprob == 1) {
+              U(IB2) = Bx; U(IB3) = By;
+              eint = Y <= 0.0 ? 10.0 : 12.0;
+            } else if (iprob == 2) {
+              U(IB3) = Bx; U(IB1) = By;
+              eint = Z <= 0.0 ? 10.0 : 12.0;
+            } else if (iprob == 10) {  // heat diffusion of a 1-D Gaussian
+              U(IB1) = Bx; U(IB2) = By;
+              const double eff = Bx == 0.0 ? dc : dc * Bx * Bx;
+              eint = 1 + amp / std::sqrt(4. * M_PI * eff * t0) *
+                             std::exp(-(std::pow(X, 2.)) / (4. * eff * t0));
+            } else if (iprob >= 20 && iprob <= 22) {  // ring diffusion in a coordinate plane
+              const double x = iprob == 20 ? X : (iprob == 21 ? Y : Z);
+              const double y = iprob == 20 ? Y : (iprob == 21 ? Z : X);
+              const double r = std::sqrt(SQR(x) + SQR(y)), phi = std::atan2(y, x);
+              const int b1 = iprob == 20 ? IB1 : (iprob == 21 ? IB2 : IB3);
+              const int b2 = iprob == 20 ? IB2 : (iprob == 21 ? IB3 : IB1);
+              U(b1) = y / r;
+              U(b2) = -x / r;
+              eint = (std::abs(r - 0.6) < 0.1 && std::abs(phi) < M_PI / 12.0) ? 12.0 : 10.0;
+            } else if (iprob == 30) {  // viscous diffusion of a 1-D Gaussian
+              U(IM2) = U(IDN) * amp / std::pow(std::sqrt(4. * M_PI * dc * t0), 1.0) *
+                       std::exp(-(std::pow(X, 2.)) / (4. * dc * t0));
+              eint = 1.0 / (cfg_.gamma * (cfg_.gamma - 1.0));
+            } else if (iprob == 40) {  // Ohmic diffusion of a 1-D Gaussian
+              U(IB2) = amp / std::pow(std::sqrt(4. * M_PI * dc * t0), 1.0) *
+                       std::exp(-(std::pow(X, 2.)) / (4. * dc * t0));
+              eint = 1.0 / (cfg_.gamma * (cfg_.gamma - 1.0));
+            }
+            if (!(eint > 0.0)) return -2;  // "Missing init of eint"
+            U(IEN) = U(IDN) * eint + 0.5 * ((SQR(U(IM1)) + SQR(U(IM2)) + SQR(U(IM3))) / U(IDN));
+            if (mhd) U(IEN) += 0.5 * (SQR(U(IB1)) + SQR(U(IB2)) + SQR(U(IB3)));
           } else if (id == "lw_implode") {  // lw_implode.cpp:34-75 (Liska-Wendroff implosion)
             const double d_in = par(0, 0.125), p_in = par(1, 0.14), d_out = par(2, 1.0),
                          p_out = par(3, 1.0);

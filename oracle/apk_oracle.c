@@ -3256,6 +3256,50 @@ int apko_pgen(apko_engine *e, int id, const double *pars, int npars) {
             }
             U(IEN) = p0 / gm1 + 0.5 * d0 * (SQR(v1) + SQR(v2) + SQR(v3)) + eb;
           } break;
+          case APKO_PGEN_DIFFUSION: { /* src/pgen/diffusion.cpp:28-158; pars = iprob, Bx, By, t0, amp,
+                                         diffusion coefficient of the process under test */
+            const int iprob = npars > 0 ? (int)pars[0] : 20;
+            const double Bx = npars > 1 ? pars[1] : 0.0, By = npars > 2 ? pars[2] : 0.0;
+            const double t0 = npars > 3 ? pars[3] : 0.5, amp = npars > 4 ? pars[4] : 1e-6;
+            const double dc = npars > 5 ? pars[5] : 0.0;
+            const double X = xc(B, 0, i), Y = xc(B, 1, j), Z = xc(B, 2, k);
+            double eint = -1.0;
+            if (!mhd && iprob != 30) return -1; /* diffusion.cpp:35-37 */
+            U(IDN) = 1.0;
+            if (iprob == 0) {
+              U(IB1) = Bx; U(IB2) = By;
+              eint = X <= 0.0 ? 10.0 : 12.0;
+            } else if (iprob == 1) {
+              U(IB2) = Bx; U(IB3) = By;
+              eint = Y <= 0.0 ? 10.0 : 12.0;
+            } else if (iprob == 2) {
+              U(IB3) = Bx; U(IB1) = By;
+              eint = Z <= 0.0 ? 10.0 : 12.0;
+            } else if (iprob == 10) {
+              U(IB1) = Bx; U(IB2) = By;
+              const double eff = Bx == 0.0 ? dc : dc * Bx * Bx;
+              eint = 1 + amp / sqrt(4. * M_PI * eff * t0) * exp(-(pow(X, 2.)) / (4. * eff * t0));
+            } else if (iprob >= 20 && iprob <= 22) {
+              const double x = iprob == 20 ? X : (iprob == 21 ? Y : Z);
+              const double y = iprob == 20 ? Y : (iprob == 21 ? Z : X);
+              const double r = sqrt(SQR(x) + SQR(y)), phi = atan2(y, x);
+              const int b1 = iprob == 20 ? IB1 : (iprob == 21 ? IB2 : IB3);
+              const int b2 = iprob == 20 ? IB2 : (iprob == 21 ? IB3 : IB1);
+              U(b1) = y / r;
+              U(b2) = -x / r;
+              eint = (fabs(r - 0.6) < 0.1 && fabs(phi) < M_PI / 12.0) ? 12.0 : 10.0;
+            } else if (iprob == 30) {
+              U(IM2) = U(IDN) * amp / pow(sqrt(4. * M_PI * dc * t0), 1.0) *
+                       exp(-(pow(X, 2.)) / (4. * dc * t0));
+              eint = 1.0 / (p->gamma * (p->gamma - 1.0));
+            } else if (iprob == 40) {
+              U(IB2) = amp / pow(sqrt(4. * M_PI * dc * t0), 1.0) * exp(-(pow(X, 2.)) / (4. * dc * t0));
+              eint = 1.0 / (p->gamma * (p->gamma - 1.0));
+            }
+            if (!(eint > 0.0)) return -1;
+            U(IEN) = U(IDN) * eint + 0.5 * ((SQR(U(IM1)) + SQR(U(IM2)) + SQR(U(IM3))) / U(IDN));
+            if (mhd) U(IEN) += 0.5 * (SQR(U(IB1)) + SQR(U(IB2)) + SQR(U(IB3)));
+          } break;
           case APKO_PGEN_LW_IMPLODE: { /* src/pgen/lw_implode.cpp:34-75 (Liska-Wendroff implosion);
                                           pars = d_in, p_in, d_out, p_out */
             const double d_in = npars > 0 ? pars[0] : 0.125, p_in = npars > 1 ? pars[1] : 0.14;

@@ -30,7 +30,7 @@ enum { APKO_INT_RK1 = 0, APKO_INT_RK2, APKO_INT_VL2, APKO_INT_RK3 };
 enum { APKO_BC_PERIODIC = 0, APKO_BC_OUTFLOW = 1, APKO_BC_REFLECT = 2 };
 enum { APKO_PGEN_LINEAR_WAVE = 0, APKO_PGEN_SOD, APKO_PGEN_ORSZAG_TANG, APKO_PGEN_UNIFORM,
        APKO_PGEN_OT3D, APKO_PGEN_BLAST, APKO_PGEN_RANDOM, APKO_PGEN_LINEAR_WAVE_MHD,
-       APKO_PGEN_LW_IMPLODE };
+       APKO_PGEN_LW_IMPLODE, APKO_PGEN_DIFFUSION };
 
 typedef struct {
   int fluid, recon, riemann, integrator;

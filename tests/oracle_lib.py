@@ -18,7 +18,7 @@ RIEMANN = {"none": 0, "hlle": 1, "llf": 2, "hllc": 3, "hlld": 4}
 INTEGRATOR = {"rk1": 0, "rk2": 1, "vl2": 2, "rk3": 3}
 BC = {"periodic": 0, "outflow": 1, "reflecting": 2}
 PGEN = {"linear_wave": 0, "sod": 1, "orszag_tang": 2, "uniform": 3, "ot3d": 4, "blast": 5,
-        "random": 6, "linear_wave_mhd": 7, "lw_implode": 8}
+        "random": 6, "linear_wave_mhd": 7, "lw_implode": 8, "diffusion": 9}
 
 
 class Params(C.Structure):

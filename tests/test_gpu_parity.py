@@ -371,6 +371,37 @@ def test_static_refinement_reference_traces(apk, name):
     s.close()
 
 
+@pytest.mark.parametrize("integrator", ["unsplit", "rkl2"])
+def test_reference_regression_diffusion_visc(apk, integrator):
+    """the reference's regression suite case `diffusion` (viscous diffusion of a 1-D Gaussian,
+    tests/diffusion_suite_util.py) on the GPU: the history file the unmodified reference wrote at
+    N = 256 row by row (strict mode), and the case's acceptance criterion -- L1 error against the
+    analytic profile converging at a rate <= -1.95 over N = 256, 512, 1024 -- in strict and FMA
+    mode (unsplit: 1518 / 6069 / 24273 cycles; RKL2: 8 / 31 / 122 super steps)."""
+    import diffusion_suite_util as ds
+    kw, pgen, pars = ds.deck(256, integrator)
+    s = apk.HydroSim(fp_mode="strict", **kw)
+    s.pgen(pgen, pars)
+    s.initialize(ds.TLIM)
+    rows = ds.history_rows(s, lambda s, t, c: s.execute(t, c), lambda s: s.history(), 4)
+    ds.check_rows(rows, ds.reference_rows(integrator))
+    s.close()
+    for fp_mode in ("strict", "fast"):
+        l1 = []
+        for res in (256, 512, 1024):
+            kw, pgen, pars = ds.deck(res, integrator)
+            s = apk.HydroSim(fp_mode=fp_mode, **kw)
+            s.pgen(pgen, pars)
+            s.initialize(ds.TLIM)
+            s.execute(ds.TLIM, -1)
+            order = np.argsort([s.block_info(b)[1][0] for b in range(s.nblocks)])
+            v2 = np.concatenate([s.get("prim", int(b))[2][0, 0, 2:66] for b in order])
+            x = -6.0 + (np.arange(res) + 0.5) * (12.0 / res)
+            l1.append(ds.l1_error(x, v2))
+            s.close()
+        assert ds.convergence_rate([256, 512, 1024], l1) <= -1.95, (fp_mode, l1)
+
+
 def test_reference_regression_lw_implode_symmetry(apk):
     """the reference's regression case lw_implode_symmetry (tst/regression/CMakeLists.txt:73-74,
     inputs/lw_implode.in as it is: Liska-Wendroff implosion, 256^2 in one meshblock, reflecting

@@ -124,6 +124,33 @@ def test_refined_meshes_with_physical_boundaries(name):
     assert o.ncycle == case["ncycle"]
 
 
+@pytest.mark.parametrize("integrator", ["unsplit", "rkl2"])
+def test_reference_regression_diffusion_visc(integrator):
+    """the reference's regression suite case `diffusion` (viscous half; see
+    tests/diffusion_suite_util.py): its history file at N = 256 row by row, and its acceptance
+    criterion (L1 error against the analytic Gaussian converging at a rate <= -1.95 over N = 256,
+    512, 1024)"""
+    import numpy as np
+    import diffusion_suite_util as ds
+    kw, pgen, pars = ds.deck(256, integrator)
+    o = Oracle(**kw)
+    o.pgen(pgen, pars)
+    o.initialize(ds.TLIM)
+    ds.check_rows(ds.history_rows(o, advance, lambda o: o.history(), 4), ds.reference_rows(integrator))
+    l1 = []
+    for res in (256, 512, 1024):
+        kw, pgen, pars = ds.deck(res, integrator)
+        o = Oracle(**kw)
+        o.pgen(pgen, pars)
+        o.initialize(ds.TLIM)
+        o.run(ds.TLIM, -1)
+        dx = 12.0 / res
+        x = -6.0 + (np.arange(res) + 0.5) * dx
+        v2 = np.concatenate([o.prim(b)[2][0, 0, 2:66] for b in range(o.nblocks)])
+        l1.append(ds.l1_error(x, v2))
+    assert ds.convergence_rate([256, 512, 1024], l1) <= -1.95
+
+
 def test_reference_regression_lw_implode_64():
     """the deck of the reference's regression case lw_implode_symmetry (inputs/lw_implode.in:
     Liska-Wendroff implosion, reflecting walls, VL2 + PLM + HLLC) at 64^2: 300 cycles of the
