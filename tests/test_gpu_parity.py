@@ -402,6 +402,35 @@ def test_reference_regression_diffusion_visc(apk, integrator):
         assert ds.convergence_rate([256, 512, 1024], l1) <= -1.95, (fp_mode, l1)
 
 
+@pytest.mark.parametrize("integrator", ["unsplit", "rkl2"])
+def test_reference_regression_aniso_therm_cond_gauss_conv(apk, integrator):
+    """the reference's regression suite case aniso_therm_cond_gauss_conv on the GPU (tests/
+    aniso_cond_suite_util.py): isotropic conduction and anisotropic conduction along a field that is
+    aligned, at 45 degrees or perpendicular; N = 128 / 256 / 512 by 32 cells (unsplit: up to ~12 000
+    cycles).  The case's acceptance criterion: L1 error against the analytic Gaussian converges at a
+    rate <= -1.98; with a perpendicular field nothing diffuses.  FMA mode (the benchmarked mode);
+    RKL2 also in strict mode, where the errors equal the oracle's."""
+    import aniso_cond_suite_util as au
+    for fp_mode in (("fast", "strict") if integrator == "rkl2" else ("fast",)):
+        for field in ("none", "aligned", "angle", "perp"):
+            l1 = []
+            for res in (128, 256, 512):
+                kw, pgen, pars, bx = au.deck(res, field, integrator)
+                s = apk.HydroSim(fp_mode=fp_mode, **kw)
+                s.pgen(pgen, pars)
+                s.initialize(au.TLIM)
+                s.execute(au.TLIM, -1)
+                order = np.argsort([s.block_info(b)[1][0] for b in range(s.nblocks)])
+                temp = np.concatenate([s.get("prim", int(b))[4][0, 2, 2:66] for b in order])
+                x = -6.0 + (np.arange(res) + 0.5) * (12.0 / res)
+                l1.append(au.l1_error(x, temp, bx, field))
+                s.close()
+            if field == "perp":
+                assert max(l1) <= 1e-14, l1
+            else:
+                assert au.rate([128, 256, 512], l1) <= -1.98, (fp_mode, field, l1)
+
+
 def test_reference_regression_lw_implode_symmetry(apk):
     """the reference's regression case lw_implode_symmetry (tst/regression/CMakeLists.txt:73-74,
     inputs/lw_implode.in as it is: Liska-Wendroff implosion, 256^2 in one meshblock, reflecting

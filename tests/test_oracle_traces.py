@@ -151,6 +151,30 @@ def test_reference_regression_diffusion_visc(integrator):
     assert ds.convergence_rate([256, 512, 1024], l1) <= -1.95
 
 
+@pytest.mark.parametrize("field", ["angle", "perp"])
+def test_reference_regression_aniso_therm_cond_gauss_conv_rkl2(field):
+    """the reference's regression suite case aniso_therm_cond_gauss_conv (tests/
+    aniso_cond_suite_util.py), RKL2 integrator, field at 45 degrees: L1 error against the analytic
+    Gaussian converges at a rate <= -1.98 over N = 128, 256, 512; perpendicular field: nothing
+    diffuses.  (Unsplit integrator and the other field configurations: GPU test.)"""
+    import numpy as np
+    import aniso_cond_suite_util as au
+    l1 = []
+    for res in (128, 256, 512):
+        kw, pgen, pars, bx = au.deck(res, field, "rkl2")
+        o = Oracle(**kw)
+        o.pgen(pgen, pars)
+        o.initialize(au.TLIM)
+        o.run(au.TLIM, -1)
+        x = -6.0 + (np.arange(res) + 0.5) * (12.0 / res)
+        temp = np.concatenate([o.prim(b)[4][0, 2, 2:66] for b in range(o.nblocks)])
+        l1.append(au.l1_error(x, temp, bx, field))
+    if field == "perp":
+        assert max(l1) <= 1e-14
+    else:
+        assert au.rate([128, 256, 512], l1) <= -1.98, l1
+
+
 def test_reference_regression_lw_implode_64():
     """the deck of the reference's regression case lw_implode_symmetry (inputs/lw_implode.in:
     Liska-Wendroff implosion, reflecting walls, VL2 + PLM + HLLC) at 64^2: 300 cycles of the
