@@ -431,6 +431,31 @@ def test_reference_regression_aniso_therm_cond_gauss_conv(apk, integrator):
                 assert au.rate([128, 256, 512], l1) <= -1.98, (fp_mode, field, l1)
 
 
+def test_reference_regression_aniso_therm_cond_ring_conv(apk):
+    """the reference's regression suite case aniso_therm_cond_ring_conv on the GPU (tests/
+    ring_cond_suite_util.py; FMA mode): anisotropic conduction around a ring of field lines to
+    t = 200 with RKL2 (up to ~4400 super steps of ~14 stages at N = 256), all four acceptance
+    criteria of the case: no temperature below the background, L2 error at N = 256 <= 0.0264, L1
+    converging at a rate <= -0.53 and L2 at <= -0.35 over N = 32, 64, 128, 256."""
+    import ring_cond_suite_util as ru
+    ress, l1s, l2s = (32, 64, 128, 256), [], []
+    for res in ress:
+        kw, pgen, pars = ru.deck(res)
+        s = apk.HydroSim(fp_mode="fast", **kw)
+        s.pgen(pgen, pars)
+        s.initialize(ru.TLIM)
+        s.execute(ru.TLIM, -1)
+        blocks = [(s.block_info(b)[2], s.block_info(b)[3], s.get("prim", b)) for b in range(s.nblocks)]
+        tmin, l1, l2 = ru.errors(blocks, res)
+        s.close()
+        assert tmin >= 10.0, (res, tmin)
+        l1s.append(l1)
+        l2s.append(l2)
+    assert l2s[-1] <= 0.0264, l2s
+    assert ru.rate(ress, l1s) <= -0.53, l1s
+    assert ru.rate(ress, l2s) <= -0.35, l2s
+
+
 def test_reference_regression_lw_implode_symmetry(apk):
     """the reference's regression case lw_implode_symmetry (tst/regression/CMakeLists.txt:73-74,
     inputs/lw_implode.in as it is: Liska-Wendroff implosion, 256^2 in one meshblock, reflecting

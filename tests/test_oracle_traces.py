@@ -175,6 +175,29 @@ def test_reference_regression_aniso_therm_cond_gauss_conv_rkl2(field):
         assert au.rate([128, 256, 512], l1) <= -1.98, l1
 
 
+def test_reference_regression_aniso_therm_cond_ring_small():
+    """the reference's regression suite case aniso_therm_cond_ring_conv (tests/
+    ring_cond_suite_util.py) at N = 32 and 64 (the full criterion up to N = 256: GPU test): no
+    undershoot below the background temperature, and L1 errors within 5 % of the published values
+    of Balsara, Tilley & Howk (2007) the case plots its results against (0.0407, 0.0326)"""
+    import ctypes as C
+    import ring_cond_suite_util as ru
+    for res, published in ((32, 0.0407), (64, 0.0326)):
+        kw, pgen, pars = ru.deck(res)
+        o = Oracle(**kw)
+        o.pgen(pgen, pars)
+        o.initialize(ru.TLIM)
+        o.run(ru.TLIM, -1)
+        blocks = []
+        for b in range(o.nblocks):
+            xmin, dx = (C.c_double * 3)(), (C.c_double * 3)()
+            o.L.apko_block_coords(o.h, b, xmin, dx)
+            blocks.append((list(xmin), list(dx), o.prim(b)))
+        tmin, l1, l2 = ru.errors(blocks, res)
+        assert tmin >= 10.0
+        assert abs(l1 - published) <= 0.05 * published, (res, l1)
+
+
 def test_reference_regression_lw_implode_64():
     """the deck of the reference's regression case lw_implode_symmetry (inputs/lw_implode.in:
     Liska-Wendroff implosion, reflecting walls, VL2 + PLM + HLLC) at 64^2: 300 cycles of the
