@@ -456,6 +456,26 @@ def test_reference_regression_aniso_therm_cond_ring_conv(apk):
     assert ru.rate(ress, l2s) <= -0.35, l2s
 
 
+def test_reference_regression_aniso_therm_cond_ring_multid(apk):
+    """the reference's regression suite case aniso_therm_cond_ring_multid on the GPU (tests/
+    ring_multid_suite_util.py; strict mode): the ring-conduction problem with the unsplit
+    integrator at N = 64 to t = 200 on a 2-D mesh and on 3-D meshes with the ring in each coordinate
+    plane (27 000 - 41 000 cycles each).  The case's criteria: no undershoot, 2-D and 3-D errors
+    equal to 4 decimals, the three orientations equal to 14 decimals."""
+    import ring_multid_suite_util as rm
+    errs = {}
+    for plane in ("2d", "x1x2", "x2x3", "x3x1"):
+        kw, pgen, pars, iprob = rm.deck(64, plane)
+        s = apk.HydroSim(fp_mode="strict", **kw)
+        s.pgen(pgen, pars)
+        s.initialize(200.0)
+        s.execute(200.0, -1)
+        blocks = [(s.block_info(b)[2], s.block_info(b)[3], s.get("prim", b)) for b in range(s.nblocks)]
+        errs[plane] = rm.errors(blocks, kw["nx"], kw["mb"], iprob)
+        s.close()
+    rm.check(errs)
+
+
 def test_reference_regression_lw_implode_symmetry(apk):
     """the reference's regression case lw_implode_symmetry (tst/regression/CMakeLists.txt:73-74,
     inputs/lw_implode.in as it is: Liska-Wendroff implosion, 256^2 in one meshblock, reflecting

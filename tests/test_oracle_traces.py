@@ -198,6 +198,29 @@ def test_reference_regression_aniso_therm_cond_ring_small():
         assert abs(l1 - published) <= 0.05 * published, (res, l1)
 
 
+def test_reference_regression_aniso_therm_cond_ring_multid_small():
+    """the reference's regression suite case aniso_therm_cond_ring_multid (tests/
+    ring_multid_suite_util.py) at a reduced size (N = 24, t = 30; the case itself: GPU test): the
+    anisotropic-conduction restatement treats the three coordinate planes alike to 14 decimals and
+    agrees with the 2-D run to 4"""
+    import ctypes as C
+    import ring_multid_suite_util as rm
+    errs = {}
+    for plane in ("2d", "x1x2", "x2x3", "x3x1"):
+        kw, pgen, pars, iprob = rm.deck(24, plane)
+        o = Oracle(**kw)
+        o.pgen(pgen, pars)
+        o.initialize(30.0)
+        o.run(30.0, -1)
+        blocks = []
+        for b in range(o.nblocks):
+            xmin, dx = (C.c_double * 3)(), (C.c_double * 3)()
+            o.L.apko_block_coords(o.h, b, xmin, dx)
+            blocks.append((list(xmin), list(dx), o.prim(b)))
+        errs[plane] = rm.errors(blocks, kw["nx"], kw["mb"], iprob)
+    rm.check(errs)
+
+
 def test_reference_regression_lw_implode_64():
     """the deck of the reference's regression case lw_implode_symmetry (inputs/lw_implode.in:
     Liska-Wendroff implosion, reflecting walls, VL2 + PLM + HLLC) at 64^2: 300 cycles of the
