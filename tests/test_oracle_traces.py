@@ -103,8 +103,11 @@ def test_adaptive_refinement_traces(name):
     o.pgen(pgen, pars)
     o.initialize(tlim)
     case = ADAPTIVE_TRACES[name]
-    follow_adaptive_trace(o, case, tlim, advance, lambda o: o.amr_counts())
-    assert o.ncycle == case["ncycle"]
+    # (the 30-cycle 3-D deck: 16 cycles here -- refinement and the first derefinement at cycle 12;
+    # the GPU test follows all 30 and compares the final state with the oracle's)
+    short = 16 if name == "adaptive_3d_plm_hlle" else None
+    follow_adaptive_trace(o, case, tlim, advance, lambda o: o.amr_counts(), max_cycles=short)
+    assert o.ncycle == (short if short else case["ncycle"])
 
 
 @pytest.mark.parametrize("name", sorted(BOUNDARY_AMR_DECKS))

@@ -180,10 +180,13 @@ BOUNDARY_AMR_DECKS = {
 }
 
 
-def follow_adaptive_trace(engine, case, tlim, advance, counts):
+def follow_adaptive_trace(engine, case, tlim, advance, counts, max_cycles=None):
     """like follow_trace, plus the number of meshblocks (total and per level) the reference prints
-    every cycle; counts(engine) -> (created, destroyed, [blocks per level])"""
+    every cycle; counts(engine) -> (created, destroyed, [blocks per level]).  max_cycles: follow
+    only the first cycles of the trace (CPU tests of long 3-D decks; the GPU tests follow all)"""
     for c, (t, dt) in enumerate(case["trace"]):
+        if max_cycles is not None and c > max_cycles:
+            return
         if c > 0:
             advance(engine, tlim, c)
         got = ("%.16e" % engine.time, "%.16e" % engine.dt)
