@@ -224,6 +224,29 @@ def test_reference_regression_aniso_therm_cond_ring_multid_small():
     rm.check(errs)
 
 
+def test_reference_regression_diffusion_ohm_criterion():
+    """the Ohmic half of the reference's regression suite case `diffusion` (iprob = 40: resistive
+    diffusion of a 1-D Gaussian B2 profile).  The reference's serial build segfaults on it in this
+    container, so only the case's acceptance criterion is available: L1 error against the analytic
+    Gaussian converging at a rate <= -1.95 (oracle; RKL2 -- the unsplit run gives the same errors
+    as the viscous one)"""
+    import numpy as np
+    import diffusion_suite_util as ds
+    l1 = []
+    for res in (256, 512, 1024):
+        kw, pgen, pars = ds.deck(res, "rkl2")
+        kw.update(fluid="glmmhd", viscosity="none", mom_diff_coeff=0.0, resistivity="ohmic",
+                  ohm_diff_coeff=ds.DIFF_COEFF)
+        o = Oracle(**kw)
+        o.pgen(pgen, [40, 0.0, 0.0, ds.T0, ds.AMP, ds.DIFF_COEFF])
+        o.initialize(ds.TLIM)
+        o.run(ds.TLIM, -1)
+        x = -6.0 + (np.arange(res) + 0.5) * (12.0 / res)
+        by = np.concatenate([o.prim(b)[6][0, 0, 2:66] for b in range(o.nblocks)])
+        l1.append(ds.l1_error(x, by))
+    assert ds.convergence_rate([256, 512, 1024], l1) <= -1.95
+
+
 def test_reference_regression_lw_implode_64():
     """the deck of the reference's regression case lw_implode_symmetry (inputs/lw_implode.in:
     Liska-Wendroff implosion, reflecting walls, VL2 + PLM + HLLC) at 64^2: 300 cycles of the
